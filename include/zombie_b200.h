@@ -1,0 +1,194 @@
+/* zombie_b200 C ABI — the drop-in boundary for Zombie's random-walk hot path on B200.
+ *
+ * The reference has no FFI: its operator API is the header-only C++ template surface
+ * (zombie/point_estimation/walk_on_stars.h:40-46, walk_on_spheres.h:38-44,
+ * zombie/utils/fcpw_geometric_queries.h:84-150). Each entry point below names the reference
+ * interface it replaces. All pointers are plain host pointers unless the function name ends
+ * in _dev, in which case they are CUDA device pointers on the context's device. No function
+ * ever calls exit(); errors are returned as codes and described by zb_last_error().
+ *
+ * Conventions: vectors are packed float[dim] per item (AoS of dim floats), dim is 2 or 3 and
+ * fixed per scene. Primitive indices are the caller's input-order indices, like
+ * fcpw::Interaction::primitiveIndex (fcpw/fcpw.inl:188-204).
+ */
+#ifndef ZOMBIE_B200_H
+#define ZOMBIE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZB_ABI_VERSION 1
+
+enum zb_status {
+    ZB_OK = 0,
+    ZB_ERR_INVALID_ARGUMENT = 1,
+    ZB_ERR_CUDA = 2,
+    ZB_ERR_OUT_OF_MEMORY = 3,
+    ZB_ERR_UNSUPPORTED = 4,
+    ZB_ERR_NO_DEVICE = 5
+};
+
+/* zombie::SampleType (point_estimation/common.h:139-143) */
+enum zb_sample_type { ZB_IN_DOMAIN = 0, ZB_ON_ABSORBING_BOUNDARY = 1, ZB_ON_REFLECTING_BOUNDARY = 2 };
+/* zombie::EstimationQuantity (common.h:145-149) */
+enum zb_estimation_quantity { ZB_SOLUTION = 0, ZB_SOLUTION_AND_GRADIENT = 1, ZB_SKIP = 2 };
+/* which FcpwXBoundaryHandler the reflecting mesh would have used (fcpw_geometric_queries.h:84-128) */
+enum zb_reflecting_kind { ZB_REFLECTING_NONE = 0, ZB_REFLECTING_NEUMANN = 1, ZB_REFLECTING_ROBIN = 2 };
+/* estimator: WalkOnSpheres::solve or WalkOnStars::solve */
+enum zb_estimator { ZB_WALK_ON_SPHERES = 0, ZB_WALK_ON_STARS = 1 };
+enum zb_boundary_id { ZB_ABSORBING = 0, ZB_REFLECTING = 1 };
+
+/* Field-for-field mirror of zombie::WalkSettings (point_estimation/common.h:75-90);
+ * bools widened to int32 so the layout is the same from C, C++ and ctypes. */
+typedef struct zb_walk_settings {
+    float epsilonShellForAbsorbingBoundary;
+    float epsilonShellForReflectingBoundary;
+    float silhouettePrecision;
+    float russianRouletteThreshold;
+    float splittingThreshold;
+    int32_t maxWalkLength;
+    int32_t stepsBeforeApplyingTikhonov;
+    int32_t stepsBeforeUsingMaximalSpheres;
+    int32_t solveDoubleSided;
+    int32_t useGradientControlVariates;
+    int32_t useGradientAntitheticVariates;
+    int32_t useCosineSamplingForDerivatives;
+    int32_t ignoreAbsorbingBoundaryContribution;
+    int32_t ignoreReflectingBoundaryContribution;
+    int32_t ignoreSourceContribution;
+    int32_t printLogs;
+} zb_walk_settings;
+
+/* Data-described zombie::PDE (core/pde.h:20-45). std::function callbacks cannot run on the
+ * device, so each callback is derived from a closed-form solution family (see
+ * zombie_b200/analytic.h) or is a constant. */
+enum zb_pde_mode { ZB_PDE_MANUFACTURED = 0, ZB_PDE_CONSTANT = 1 };
+typedef struct zb_pde_desc {
+    float absorptionCoeff;               /* pde.h:26 */
+    int32_t isSourceConstant;            /* pde.h:27 */
+    int32_t areRobinConditionsPureNeumann; /* pde.h:28 */
+    int32_t areRobinCoeffsNonnegative;   /* pde.h:29 */
+    int32_t mode;                        /* zb_pde_mode */
+    int32_t family;                      /* zb_solution_family when mode == MANUFACTURED */
+    float params[16];
+    float robinCoeff;                    /* constant mu returned by pde.robinCoeff */
+    float sourceValue;                   /* CONSTANT mode: pde.source */
+    float dirichletValue;                /* CONSTANT mode: pde.dirichlet */
+    float robinValue;                    /* CONSTANT mode: pde.robin */
+    int32_t kelvin;                      /* 1: callbacks wrapped like KelvinTransform::transformPde (kelvin_transform.h:282-348) */
+    float kelvinOrigin[3];
+} zb_pde_desc;
+
+/* SoA mirror of std::vector<zombie::SamplePoint<float,DIM>> (common.h:152-195). rngState/rngInc
+ * are pcg32::state / pcg32::inc and are in/out, as is firstSphereRadius. */
+typedef struct zb_sample_points {
+    int32_t n;
+    const float *pt;                     /* n*dim */
+    const float *normal;                 /* n*dim */
+    const float *directionForDerivative; /* n*dim or NULL (= e_0) */
+    const int32_t *type;                 /* zb_sample_type */
+    const int32_t *estimationQuantity;   /* zb_estimation_quantity */
+    const float *distToAbsorbingBoundary;
+    const float *distToReflectingBoundary;
+    const uint8_t *estimateBoundaryNormalAligned; /* or NULL (= false) */
+    const int32_t *nWalks;               /* the nWalks vector of solve() */
+    uint64_t *rngState;                  /* in/out */
+    uint64_t *rngInc;                    /* in/out */
+    float *firstSphereRadius;            /* in/out */
+} zb_sample_points;
+
+/* SoA mirror of std::vector<zombie::SampleStatistics<float,DIM>> (common.h:201-395), in/out so
+ * that repeated solves refine progressively exactly like the reference (common.h:268-310). */
+typedef struct zb_statistics {
+    float *solutionMean;
+    float *solutionM2;
+    float *gradientMean;                 /* n*dim */
+    float *gradientM2;                   /* n*dim */
+    float *totalFirstSourceContribution;
+    float *totalDerivativeContribution;
+    int32_t *nSolutionEstimates;
+    int32_t *nGradientEstimates;
+    int32_t *totalWalkLength;
+    int32_t *totalSplits;
+} zb_statistics;
+
+typedef struct zb_context zb_context;
+typedef struct zb_scene zb_scene;
+
+/* ---- context ---------------------------------------------------------------------------- */
+const char *zb_last_error(void);
+int zb_abi_version(void);
+int zb_device_count(void);
+/* one context per process and device; owns its CUDA stream and scratch buffers */
+int zb_context_create(int device, zb_context **out);
+void zb_context_destroy(zb_context *ctx);
+/* runs subsequent work of this context on a caller-owned cudaStream_t (e.g. torch's current stream) */
+int zb_context_set_stream(zb_context *ctx, void *cudaStream);
+int zb_context_synchronize(zb_context *ctx);
+int zb_context_device(const zb_context *ctx);
+int zb_context_sm_count(const zb_context *ctx);
+
+/* ---- geometry: replaces Fcpw{Dirichlet,Neumann,Robin}BoundaryHandler::buildAccelerationStructure
+ * + populateGeometricQueriesFor*Boundary (fcpw_geometric_queries.h:569-586, 650-676, 870-995,
+ * 1063-1291) and the GeometricQueries(domainIsWatertight, domainMin, domainMax) constructor
+ * (core/geometric_queries.h:135-147). Either mesh may be empty (n == 0). Indices are dim per
+ * primitive (line segments in 2D, triangles in 3D). minRobin/maxRobin are per reflecting
+ * primitive and only read for ZB_REFLECTING_ROBIN. ------------------------------------------ */
+int zb_scene_create(zb_context *ctx, int dim,
+                    const float *absorbingPositions, int nAbsorbingVertices,
+                    const int32_t *absorbingIndices, int nAbsorbingPrimitives,
+                    const float *reflectingPositions, int nReflectingVertices,
+                    const int32_t *reflectingIndices, int nReflectingPrimitives,
+                    int reflectingKind, const float *minRobinCoeff, const float *maxRobinCoeff,
+                    int solveDoubleSided, float silhouettePrecision,
+                    int domainIsWatertight, const float *domainMin, const float *domainMax,
+                    zb_scene **out);
+void zb_scene_destroy(zb_scene *scene);
+/* FcpwRobinBoundaryHandler::updateCoefficientValues (fcpw_geometric_queries.h:997-1010) */
+int zb_scene_update_robin_coefficients(zb_scene *scene, const float *minRobinCoeff, const float *maxRobinCoeff);
+/* bytes of device memory held by the scene's acceleration structures, and node counts */
+int zb_scene_stats(const zb_scene *scene, int boundary, int64_t *bytes, int32_t *nNodes, int32_t *nLeaves, int32_t *maxDepth);
+
+/* ---- batched geometric queries (host buffers). These are what the GeometricQueries callbacks
+ * bind to; they also expose the primitive index so parity with FCPW can be checked exactly. ---- */
+/* Aggregate::findClosestPoint with BoundingSphere(x, maxR2) (fcpw_geometric_queries.h:1069-1096;
+ * fcpw/aggregates/bvh.inl:1391-1418). prim = -1 when nothing lies within the radius. normal may be NULL. */
+int zb_closest_point(zb_scene *scene, int boundary, int n, const float *x, const float *maxRadius /* NULL = inf */,
+                     int32_t *prim, float *dist, float *pt, float *normal);
+/* Aggregate::intersect(Ray(origin, dir, tMax)) closest hit (bvh.inl:753-771). prim = -1 on miss. */
+int zb_intersect_ray(zb_scene *scene, int boundary, int n, const float *origin, const float *dir, const float *tMax,
+                     int32_t *prim, float *dist, float *pt, float *normal);
+/* !Aggregate::hasLineOfSight(a, b) (fcpw/core/primitive.h:202-212): 1 = occluded */
+int zb_occluded(zb_scene *scene, int boundary, int n, const float *a, const float *b, uint8_t *occluded);
+/* Aggregate::intersect(sphere, randNums, branchTraversalWeight) (bvh.inl:1257-1288) with the
+ * harmonic branch weight of getBranchTraversalWeightCallback (fcpw_geometric_queries.h:1391-1398).
+ * prim = -1 when no primitive was sampled. */
+int zb_sample_sphere(zb_scene *scene, int boundary, int n, const float *x, const float *radius, const float *randNums /* n*dim */,
+                     int32_t *prim, float *pt, float *normal, float *pdf);
+/* GeometricQueries::computeStarRadiusForReflectingBoundary (fcpw_geometric_queries.h:1250-1291) */
+int zb_star_radius(zb_scene *scene, int n, const float *x, const float *minRadius, const float *maxRadius,
+                   float silhouettePrecision, const uint8_t *flipNormalOrientation /* or NULL */, float *radius);
+/* GeometricQueries::insideDomain is not on the walk path; outsideBoundingDomain is evaluated inline. */
+
+/* ---- estimators: replace WalkOnSpheres::solve / WalkOnStars::solve (vector overloads,
+ * walk_on_spheres.h:132-168, walk_on_stars.h:151-187). stats and pts->rng* / firstSphereRadius
+ * are in/out. walkSteps (optional) receives the number of walk steps taken by this call. ------ */
+int zb_solve(zb_scene *scene, int estimator, const zb_pde_desc *pde, const zb_walk_settings *settings,
+             const zb_sample_points *pts, zb_statistics *stats, int64_t *walkSteps);
+/* same, all arrays already resident on the context's device; asynchronous on the context stream.
+ * walkSteps_dev points to one int64 on the device. */
+int zb_solve_dev(zb_scene *scene, int estimator, const zb_pde_desc *pde, const zb_walk_settings *settings,
+                 const zb_sample_points *pts_dev, zb_statistics *stats_dev, int64_t *walkSteps_dev);
+
+/* pcg32 known-answer hook (deps/pcg32/pcg32.h:53-100): seeds a device generator with
+ * (initstate, initseq) and returns n successive nextUInt() values */
+int zb_pcg32_kat(zb_context *ctx, uint64_t initstate, uint64_t initseq, int n, uint32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* ZOMBIE_B200_H */

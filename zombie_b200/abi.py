@@ -1,0 +1,183 @@
+"""ctypes mirrors of the C ABI structs declared in include/zombie_b200.h."""
+import ctypes as C
+
+import numpy as np
+
+ZB_OK = 0
+
+# enum zb_sample_type / zb_estimation_quantity / zb_reflecting_kind / zb_estimator / zb_boundary_id
+IN_DOMAIN, ON_ABSORBING_BOUNDARY, ON_REFLECTING_BOUNDARY = 0, 1, 2
+SOLUTION, SOLUTION_AND_GRADIENT, SKIP = 0, 1, 2
+REFLECTING_NONE, REFLECTING_NEUMANN, REFLECTING_ROBIN = 0, 1, 2
+WALK_ON_SPHERES, WALK_ON_STARS = 0, 1
+ABSORBING, REFLECTING = 0, 1
+PDE_MANUFACTURED, PDE_CONSTANT = 0, 1
+(SOL_CONSTANT, SOL_EXP_DIR, SOL_QUADRATIC, SOL_INV_DIST, SOL_SIN_EXP_2D, SOL_CUBIC_2D,
+ SOL_LINEAR, SOL_TRIG_3D) = range(8)
+
+FLT_MAX = float(np.finfo(np.float32).max)
+
+
+class WalkSettings(C.Structure):
+    """zb_walk_settings == zombie::WalkSettings (point_estimation/common.h:19-91)."""
+    _fields_ = [("epsilonShellForAbsorbingBoundary", C.c_float),
+                ("epsilonShellForReflectingBoundary", C.c_float),
+                ("silhouettePrecision", C.c_float),
+                ("russianRouletteThreshold", C.c_float),
+                ("splittingThreshold", C.c_float),
+                ("maxWalkLength", C.c_int32),
+                ("stepsBeforeApplyingTikhonov", C.c_int32),
+                ("stepsBeforeUsingMaximalSpheres", C.c_int32),
+                ("solveDoubleSided", C.c_int32),
+                ("useGradientControlVariates", C.c_int32),
+                ("useGradientAntitheticVariates", C.c_int32),
+                ("useCosineSamplingForDerivatives", C.c_int32),
+                ("ignoreAbsorbingBoundaryContribution", C.c_int32),
+                ("ignoreReflectingBoundaryContribution", C.c_int32),
+                ("ignoreSourceContribution", C.c_int32),
+                ("printLogs", C.c_int32)]
+
+    @classmethod
+    def default(cls, epsilonShellForAbsorbingBoundary=1e-3, epsilonShellForReflectingBoundary=1e-3,
+                maxWalkLength=1024, solveDoubleSided=False, **kw):
+        """The short WalkSettings constructor (common.h:21-40)."""
+        s = cls(epsilonShellForAbsorbingBoundary, epsilonShellForReflectingBoundary, 1e-3, 0.0, FLT_MAX,
+                maxWalkLength, 0, maxWalkLength, int(solveDoubleSided), 1, 1, 0, 0, 0, 0, 0)
+        for k, v in kw.items():
+            if not hasattr(s, k):
+                raise AttributeError(k)
+            setattr(s, k, v)
+        return s
+
+
+class PdeDesc(C.Structure):
+    """zb_pde_desc: data-described zombie::PDE (core/pde.h:20-45)."""
+    _fields_ = [("absorptionCoeff", C.c_float),
+                ("isSourceConstant", C.c_int32),
+                ("areRobinConditionsPureNeumann", C.c_int32),
+                ("areRobinCoeffsNonnegative", C.c_int32),
+                ("mode", C.c_int32),
+                ("family", C.c_int32),
+                ("params", C.c_float * 16),
+                ("robinCoeff", C.c_float),
+                ("sourceValue", C.c_float),
+                ("dirichletValue", C.c_float),
+                ("robinValue", C.c_float),
+                ("kelvin", C.c_int32),
+                ("kelvinOrigin", C.c_float * 3)]
+
+    @classmethod
+    def manufactured(cls, family, params, absorptionCoeff=0.0, robinCoeff=0.0, isSourceConstant=False):
+        d = cls()
+        d.absorptionCoeff = absorptionCoeff
+        d.isSourceConstant = int(isSourceConstant)
+        d.areRobinConditionsPureNeumann = int(robinCoeff == 0.0)
+        d.areRobinCoeffsNonnegative = int(robinCoeff >= 0.0)
+        d.mode = PDE_MANUFACTURED
+        d.family = family
+        for i, p in enumerate(params):
+            d.params[i] = p
+        d.robinCoeff = robinCoeff
+        return d
+
+
+class SamplePoints(C.Structure):
+    _fields_ = [("n", C.c_int32),
+                ("pt", C.c_void_p), ("normal", C.c_void_p), ("directionForDerivative", C.c_void_p),
+                ("type", C.c_void_p), ("estimationQuantity", C.c_void_p),
+                ("distToAbsorbingBoundary", C.c_void_p), ("distToReflectingBoundary", C.c_void_p),
+                ("estimateBoundaryNormalAligned", C.c_void_p), ("nWalks", C.c_void_p),
+                ("rngState", C.c_void_p), ("rngInc", C.c_void_p), ("firstSphereRadius", C.c_void_p)]
+
+
+class Statistics(C.Structure):
+    _fields_ = [("solutionMean", C.c_void_p), ("solutionM2", C.c_void_p),
+                ("gradientMean", C.c_void_p), ("gradientM2", C.c_void_p),
+                ("totalFirstSourceContribution", C.c_void_p), ("totalDerivativeContribution", C.c_void_p),
+                ("nSolutionEstimates", C.c_void_p), ("nGradientEstimates", C.c_void_p),
+                ("totalWalkLength", C.c_void_p), ("totalSplits", C.c_void_p)]
+
+
+def ptr(a):
+    """void* of a C-contiguous numpy array (None -> NULL)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class HostSamplePoints:
+    """Owns the numpy arrays behind a zb_sample_points (SoA of zombie::SamplePoint)."""
+
+    def __init__(self, pt, distToAbsorbingBoundary, distToReflectingBoundary=None, nWalks=1,
+                 estimationQuantity=SOLUTION, type=IN_DOMAIN, normal=None, seed=0xC0FFEE, streams=None):
+        from .procedural import pcg32_seed
+        pt = np.ascontiguousarray(pt, dtype=np.float32)
+        n, dim = pt.shape
+        self.n, self.dim = n, dim
+        self.pt = pt
+        self.normal = np.zeros((n, dim), np.float32) if normal is None else np.ascontiguousarray(normal, np.float32)
+        self.directionForDerivative = np.zeros((n, dim), np.float32)
+        self.directionForDerivative[:, 0] = 1.0
+        self.type = np.full(n, type, np.int32) if np.isscalar(type) else np.ascontiguousarray(type, np.int32)
+        self.estimationQuantity = (np.full(n, estimationQuantity, np.int32) if np.isscalar(estimationQuantity)
+                                   else np.ascontiguousarray(estimationQuantity, np.int32))
+        self.distToAbsorbingBoundary = np.ascontiguousarray(distToAbsorbingBoundary, np.float32)
+        self.distToReflectingBoundary = (np.full(n, FLT_MAX, np.float32) if distToReflectingBoundary is None
+                                         else np.ascontiguousarray(distToReflectingBoundary, np.float32))
+        self.estimateBoundaryNormalAligned = np.zeros(n, np.uint8)
+        self.nWalks = np.full(n, nWalks, np.int32) if np.isscalar(nWalks) else np.ascontiguousarray(nWalks, np.int32)
+        if streams is None:
+            streams = np.arange(n, dtype=np.uint64)
+        self.rngState, self.rngInc = pcg32_seed(np.full(n, seed, np.uint64), np.asarray(streams, np.uint64))
+        self.rngState = np.ascontiguousarray(self.rngState)
+        self.rngInc = np.ascontiguousarray(self.rngInc)
+        self.firstSphereRadius = np.zeros(n, np.float32)
+
+    def as_struct(self):
+        return SamplePoints(self.n, ptr(self.pt), ptr(self.normal), ptr(self.directionForDerivative),
+                            ptr(self.type), ptr(self.estimationQuantity), ptr(self.distToAbsorbingBoundary),
+                            ptr(self.distToReflectingBoundary), ptr(self.estimateBoundaryNormalAligned),
+                            ptr(self.nWalks), ptr(self.rngState), ptr(self.rngInc), ptr(self.firstSphereRadius))
+
+    def subset(self, idx):
+        o = object.__new__(HostSamplePoints)
+        o.n, o.dim = len(idx), self.dim
+        for k in ("pt", "normal", "directionForDerivative", "type", "estimationQuantity",
+                  "distToAbsorbingBoundary", "distToReflectingBoundary", "estimateBoundaryNormalAligned",
+                  "nWalks", "rngState", "rngInc", "firstSphereRadius"):
+            setattr(o, k, np.ascontiguousarray(getattr(self, k)[idx]))
+        return o
+
+
+class HostStatistics:
+    """Owns the numpy arrays behind a zb_statistics (SoA of zombie::SampleStatistics)."""
+
+    def __init__(self, n, dim):
+        self.n, self.dim = n, dim
+        self.solutionMean = np.zeros(n, np.float32)
+        self.solutionM2 = np.zeros(n, np.float32)
+        self.gradientMean = np.zeros((n, dim), np.float32)
+        self.gradientM2 = np.zeros((n, dim), np.float32)
+        self.totalFirstSourceContribution = np.zeros(n, np.float32)
+        self.totalDerivativeContribution = np.zeros(n, np.float32)
+        self.nSolutionEstimates = np.zeros(n, np.int32)
+        self.nGradientEstimates = np.zeros(n, np.int32)
+        self.totalWalkLength = np.zeros(n, np.int32)
+        self.totalSplits = np.zeros(n, np.int32)
+
+    def as_struct(self):
+        return Statistics(ptr(self.solutionMean), ptr(self.solutionM2), ptr(self.gradientMean), ptr(self.gradientM2),
+                          ptr(self.totalFirstSourceContribution), ptr(self.totalDerivativeContribution),
+                          ptr(self.nSolutionEstimates), ptr(self.nGradientEstimates),
+                          ptr(self.totalWalkLength), ptr(self.totalSplits))
+
+    # SampleStatistics getters (common.h:313-377)
+    def solution_variance(self):
+        return self.solutionM2 / np.maximum(1, self.nSolutionEstimates - 1)
+
+    def gradient_variance(self):
+        return self.gradientM2 / np.maximum(1, self.nGradientEstimates - 1)[:, None]
+
+    def mean_walk_length(self):
+        return self.totalWalkLength / np.maximum(1, self.nSolutionEstimates)
