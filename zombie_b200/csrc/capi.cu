@@ -1,0 +1,801 @@
+// C ABI of libzombie_b200.so (include/zombie_b200.h): contexts, scenes (boundary meshes -> wide BVHs on
+// the device), batched geometric queries and the walk-on-spheres / walk-on-stars solve.
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/zombie_b200.h"
+#include "walk.cuh"
+#include "wide_bvh.h"
+
+using namespace zb;
+
+namespace {
+
+thread_local std::string g_lastError;
+// zb_solve knows from the host arrays whether any point asks for gradients and tells zb_solve_dev
+// so that solution-only runs do not allocate gradient records; zb_solve_dev alone assumes they may
+thread_local bool g_gradientHint = true;
+
+int fail(int code, const std::string& msg)
+{
+    g_lastError = msg;
+    return code;
+}
+
+#define ZB_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t err__ = (expr);                                                                \
+        if (err__ != cudaSuccess) {                                                                \
+            return fail(err__ == cudaErrorMemoryAllocation ? ZB_ERR_OUT_OF_MEMORY : ZB_ERR_CUDA,  \
+                        std::string(#expr) + ": " + cudaGetErrorString(err__));                    \
+        }                                                                                          \
+    } while (0)
+
+// grow-only device allocation
+struct DeviceBuffer {
+    void *ptr = nullptr;
+    size_t capacity = 0;
+    ~DeviceBuffer() { if (ptr) cudaFree(ptr); }
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= capacity) return cudaSuccess;
+        if (ptr) { cudaFree(ptr); ptr = nullptr; capacity = 0; }
+        size_t want = bytes + bytes/8 + 256;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e == cudaSuccess) capacity = want;
+        return e;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(ptr); }
+};
+
+} // namespace
+
+struct zb_context {
+    int device = 0;
+    int smCount = 0;
+    cudaStream_t stream = nullptr;
+    bool ownsStream = false;
+    DeviceBuffer status, counters, perPoint, strat, records, scanTemp, io;
+    int *hostStatus = nullptr; // pinned
+};
+
+struct DeviceBvhStorage {
+    HostBvh host;
+    DeviceBuffer nodes, prims, primIndex, cones, adjacency;
+    BvhView view{};
+    bool present = false;
+    size_t bytes() const { return nodes.capacity + prims.capacity + primIndex.capacity + cones.capacity + adjacency.capacity; }
+};
+
+struct zb_scene {
+    zb_context *ctx = nullptr;
+    int dim = 3;
+    int reflectingKind = ZB_REFLECTING_NONE;
+    DeviceBvhStorage boundary[2];
+    float domainMin[3] = {0, 0, 0}, domainMax[3] = {0, 0, 0};
+    int watertight = 1;
+    int solveDoubleSided = 0;
+    float silhouettePrecision = 1e-3f;
+};
+
+namespace {
+
+int uploadBvh(zb_context *ctx, DeviceBvhStorage& s, int snchSign)
+{
+    const HostBvh& h = s.host;
+    ZB_CUDA(s.nodes.reserve(h.nodes.size()*sizeof(WideNode)));
+    ZB_CUDA(s.prims.reserve(h.prims.size()*sizeof(float)));
+    ZB_CUDA(s.primIndex.reserve(h.primIndex.size()*sizeof(int32_t)));
+    ZB_CUDA(cudaMemcpyAsync(s.nodes.ptr, h.nodes.data(), h.nodes.size()*sizeof(WideNode), cudaMemcpyHostToDevice, ctx->stream));
+    ZB_CUDA(cudaMemcpyAsync(s.prims.ptr, h.prims.data(), h.prims.size()*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    ZB_CUDA(cudaMemcpyAsync(s.primIndex.ptr, h.primIndex.data(), h.primIndex.size()*sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    s.view.nodes = s.nodes.as<uint4>();
+    s.view.prims = s.prims.as<float4>();
+    s.view.primIndex = s.primIndex.as<int>();
+    s.view.cones = nullptr;
+    s.view.adjacency = nullptr;
+    if (!h.cones.empty()) {
+        ZB_CUDA(s.cones.reserve(h.cones.size()*sizeof(ChildCone)));
+        ZB_CUDA(s.adjacency.reserve(h.adjacency.size()*sizeof(PrimAdjacency)));
+        ZB_CUDA(cudaMemcpyAsync(s.cones.ptr, h.cones.data(), h.cones.size()*sizeof(ChildCone), cudaMemcpyHostToDevice, ctx->stream));
+        ZB_CUDA(cudaMemcpyAsync(s.adjacency.ptr, h.adjacency.data(), h.adjacency.size()*sizeof(PrimAdjacency), cudaMemcpyHostToDevice, ctx->stream));
+        s.view.cones = s.cones.as<float4>();
+        s.view.adjacency = s.adjacency.as<float4>();
+    }
+    s.view.nPrims = h.nPrims;
+    s.view.snchSign = snchSign;
+    s.present = true;
+    ZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZB_OK;
+}
+
+int checkStatus(zb_context *ctx, const char *what)
+{
+    ZB_CUDA(cudaMemcpyAsync(ctx->hostStatus, ctx->status.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    int st = *ctx->hostStatus;
+    if (st != 0) {
+        ZB_CUDA(cudaMemsetAsync(ctx->status.ptr, 0, sizeof(int), ctx->stream));
+        std::string msg = std::string(what) + ":";
+        if (st & kStatusStackOverflow) msg += " BVH traversal stack overflow";
+        if (st & kStatusSplitOverflow) msg += " walk split queue overflow (more than 6 pending splits)";
+        return fail(ZB_ERR_UNSUPPORTED, msg);
+    }
+    return ZB_OK;
+}
+
+// ---- batched query kernels ---------------------------------------------------------------------
+template <int DIM>
+__global__ void closestPointKernel(BvhView bvh, int n, const float *x, const float *maxRadius,
+                                   int *prim, float *dist, float *pt, float *normal, int *status)
+{
+    int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Vec<DIM> q = loadVec<DIM>(x + (size_t)DIM*i);
+    float r2 = kMaxFloat;
+    if (maxRadius && maxRadius[i] < kMaxFloat) r2 = maxRadius[i]*maxRadius[i];
+    ClosestHit<DIM> hit;
+    bool found = closestPoint<DIM>(bvh, q, r2, hit, status);
+    prim[i] = found ? bvh.primIndex[hit.prim] : -1;
+    dist[i] = found ? hit.d : kMaxFloat;
+    if (pt) storeVec<DIM>(pt + (size_t)DIM*i, found ? hit.p : vzero<DIM>());
+    if (normal) {
+        Vec<DIM> nrm = vzero<DIM>();
+        if (found) { Prim<DIM> p; p.load(bvh, (uint32_t)hit.prim); nrm = unitNormal<DIM>(p); }
+        storeVec<DIM>(normal + (size_t)DIM*i, nrm);
+    }
+}
+
+template <int DIM>
+__global__ void intersectRayKernel(BvhView bvh, int n, const float *origin, const float *dir, const float *tMax,
+                                   int *prim, float *dist, float *pt, float *normal, int *status)
+{
+    int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Vec<DIM> o = loadVec<DIM>(origin + (size_t)DIM*i), d = loadVec<DIM>(dir + (size_t)DIM*i);
+    RayHit<DIM> hit;
+    bool found = intersectRay<DIM, false>(bvh, o, d, tMax ? tMax[i] : kMaxFloat, hit, status);
+    prim[i] = found ? bvh.primIndex[hit.prim] : -1;
+    dist[i] = found ? hit.t : kMaxFloat;
+    Vec<DIM> p = vzero<DIM>(), nrm = vzero<DIM>();
+    if (found) {
+        Prim<DIM> tri;
+        tri.load(bvh, (uint32_t)hit.prim);
+        p = tri.pointAt(hit.bv, hit.bw);
+        nrm = unitNormal<DIM>(tri);
+    }
+    if (pt) storeVec<DIM>(pt + (size_t)DIM*i, p);
+    if (normal) storeVec<DIM>(normal + (size_t)DIM*i, nrm);
+}
+
+template <int DIM>
+__global__ void occludedKernel(BvhView bvh, int n, const float *a, const float *b, uint8_t *out, int *status)
+{
+    int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // Aggregate::hasLineOfSight (fcpw/core/primitive.h:202-212)
+    Vec<DIM> pa = loadVec<DIM>(a + (size_t)DIM*i), pb = loadVec<DIM>(b + (size_t)DIM*i);
+    Vec<DIM> d = pb - pa;
+    float len = norm(d);
+    RayHit<DIM> hit;
+    out[i] = intersectRay<DIM, true>(bvh, pa, d/len, len, hit, status) ? 1 : 0;
+}
+
+template <int DIM>
+__global__ void sampleSphereKernel(BvhView bvh, int n, const float *x, const float *radius, const float *rand,
+                                   int *prim, float *pt, float *normal, float *pdf)
+{
+    int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Vec<DIM> q = loadVec<DIM>(x + (size_t)DIM*i), u = loadVec<DIM>(rand + (size_t)DIM*i);
+    SphereSample<DIM> s;
+    bool found = sampleSphere<DIM>(bvh, q, radius[i]*radius[i], u, s);
+    prim[i] = found ? bvh.primIndex[s.prim] : -1;
+    pdf[i] = found ? s.pdf : 0.0f;
+    if (pt) storeVec<DIM>(pt + (size_t)DIM*i, s.p);
+    if (normal) storeVec<DIM>(normal + (size_t)DIM*i, s.n);
+}
+
+template <int DIM>
+__global__ void starRadiusKernel(SolveArgs a, int n, const float *x, const float *minR, const float *maxR,
+                                 float precision, const uint8_t *flip, float *out)
+{
+    int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Vec<DIM> q = loadVec<DIM>(x + (size_t)DIM*i);
+    out[i] = starRadiusQuery<DIM>(a, q, minR[i], maxR[i], precision, flip ? flip[i] != 0 : false);
+}
+
+__global__ void pcg32Kernel(uint64_t initstate, uint64_t initseq, int n, uint32_t *out)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        Pcg32 rng;
+        rng.seed(initstate, initseq);
+        for (int i = 0; i < n; i++) out[i] = rng.nextUInt();
+    }
+}
+
+// carves typed device sub-buffers out of one allocation
+struct Carver {
+    char *base;
+    size_t offset = 0;
+    explicit Carver(void *p): base(reinterpret_cast<char *>(p)) {}
+    template <typename T> T *take(size_t count) {
+        offset = (offset + 255) & ~size_t(255);
+        T *p = base ? reinterpret_cast<T *>(base + offset) : nullptr;
+        offset += count*sizeof(T);
+        return p;
+    }
+};
+
+// staging of host arrays for the batched query entry points
+struct IoPlan {
+    std::vector<std::pair<const void *, size_t>> inputs;   // host src, bytes
+    std::vector<std::pair<void *, size_t>> outputs;        // host dst, bytes
+    std::vector<size_t> inOffsets, outOffsets;
+    size_t total = 0;
+    size_t addIn(const void *src, size_t bytes) {
+        total = (total + 255) & ~size_t(255);
+        inputs.push_back({src, bytes}); inOffsets.push_back(total);
+        size_t o = total; total += bytes; return o;
+    }
+    size_t addOut(void *dst, size_t bytes) {
+        total = (total + 255) & ~size_t(255);
+        outputs.push_back({dst, bytes}); outOffsets.push_back(total);
+        size_t o = total; total += bytes; return o;
+    }
+};
+
+int stageIn(zb_context *ctx, IoPlan& plan)
+{
+    ZB_CUDA(ctx->io.reserve(plan.total + 256));
+    for (size_t k = 0; k < plan.inputs.size(); k++) {
+        if (plan.inputs[k].first && plan.inputs[k].second)
+            ZB_CUDA(cudaMemcpyAsync(ctx->io.as<char>() + plan.inOffsets[k], plan.inputs[k].first, plan.inputs[k].second,
+                                    cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return ZB_OK;
+}
+
+int stageOut(zb_context *ctx, IoPlan& plan)
+{
+    for (size_t k = 0; k < plan.outputs.size(); k++) {
+        if (plan.outputs[k].first && plan.outputs[k].second)
+            ZB_CUDA(cudaMemcpyAsync(plan.outputs[k].first, ctx->io.as<char>() + plan.outOffsets[k], plan.outputs[k].second,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    ZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZB_OK;
+}
+
+template <typename T> T *at(zb_context *ctx, size_t offset, const void *hostPtr)
+{
+    return hostPtr ? reinterpret_cast<T *>(ctx->io.as<char>() + offset) : nullptr;
+}
+
+inline int blocksFor(int n, int threads) { return (n + threads - 1)/threads; }
+
+void fillSceneArgs(const zb_scene *scene, SolveArgs& a)
+{
+    std::memset(&a, 0, sizeof(a));
+    a.absorbing = scene->boundary[ZB_ABSORBING].view;
+    a.reflecting = scene->boundary[ZB_REFLECTING].view;
+    a.hasAbsorbing = scene->boundary[ZB_ABSORBING].present ? 1 : 0;
+    a.hasReflecting = scene->boundary[ZB_REFLECTING].present ? 1 : 0;
+    a.reflectingKind = scene->reflectingKind;
+    for (int k = 0; k < 3; k++) { a.domainMin[k] = scene->domainMin[k]; a.domainMax[k] = scene->domainMax[k]; }
+    a.status = scene->ctx->status.as<int>();
+}
+
+template <int DIM>
+int solveRange(zb_scene *scene, SolveArgs& a, int n, bool anyGradient)
+{
+    zb_context *ctx = scene->ctx;
+    cudaStream_t stream = ctx->stream;
+
+    // per-point scratch
+    Carver pp(nullptr);
+    pp.take<int>(n); pp.take<long long>(n + 1); pp.take<int>(n); pp.take<long long>(n + 1); pp.take<unsigned long long>(n);
+    ZB_CUDA(ctx->perPoint.reserve(pp.offset + 256));
+    Carver pc(ctx->perPoint.ptr);
+    a.taskCount = pc.take<int>(n);
+    a.taskOffset = pc.take<long long>(n + 1);
+    a.stratCount = pc.take<int>(n);
+    a.stratOffset = pc.take<long long>(n + 1);
+    a.pointState = pc.take<unsigned long long>(n);
+    a.pts.n = n;
+    a.anyGradient = anyGradient ? 1 : 0;
+
+    const int threads = 128;
+    countTasksKernel<DIM><<<blocksFor(n, threads), threads, 0, stream>>>(a);
+    ZB_CUDA(cudaGetLastError());
+
+    // exclusive scans (n + 1 outputs: scanning n + 1 inputs whose last element is ignored)
+    // cub accumulates in the type of the explicit init value (long long), not of the int inputs
+    size_t tempBytes = 0;
+    ZB_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, tempBytes, a.taskCount, a.taskOffset, cub::Sum(), (long long)0, n, stream));
+    ZB_CUDA(ctx->scanTemp.reserve(tempBytes + 256));
+    ZB_CUDA(cub::DeviceScan::ExclusiveScan(ctx->scanTemp.ptr, tempBytes, a.taskCount, a.taskOffset, cub::Sum(), (long long)0, n, stream));
+    ZB_CUDA(cub::DeviceScan::ExclusiveScan(ctx->scanTemp.ptr, tempBytes, a.stratCount, a.stratOffset, cub::Sum(), (long long)0, n, stream));
+    // totals: last offset + last count
+    long long lastOffsets[2];
+    int lastCounts[2];
+    ZB_CUDA(cudaMemcpyAsync(&lastOffsets[0], a.taskOffset + (n - 1), sizeof(long long), cudaMemcpyDeviceToHost, stream));
+    ZB_CUDA(cudaMemcpyAsync(&lastOffsets[1], a.stratOffset + (n - 1), sizeof(long long), cudaMemcpyDeviceToHost, stream));
+    ZB_CUDA(cudaMemcpyAsync(&lastCounts[0], a.taskCount + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
+    ZB_CUDA(cudaMemcpyAsync(&lastCounts[1], a.stratCount + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
+    ZB_CUDA(cudaStreamSynchronize(stream));
+    long long totalTasks = lastOffsets[0] + lastCounts[0];
+    long long totalStrat = lastOffsets[1] + lastCounts[1];
+    ZB_CUDA(cudaMemcpyAsync(a.taskOffset + n, &totalTasks, sizeof(long long), cudaMemcpyHostToDevice, stream));
+    ZB_CUDA(cudaMemcpyAsync(a.stratOffset + n, &totalStrat, sizeof(long long), cudaMemcpyHostToDevice, stream));
+    a.totalTasks = totalTasks;
+
+    ZB_CUDA(ctx->strat.reserve((size_t)totalStrat*sizeof(float) + 256));
+    a.strat = ctx->strat.as<float>();
+
+    size_t nt = (size_t)std::max<long long>(totalTasks, 1);
+    Carver rc0(nullptr);
+    rc0.take<float>(nt); rc0.take<int>(nt); rc0.take<int>(nt);
+    if (anyGradient) { rc0.take<float>(nt); rc0.take<float>(nt*DIM); rc0.take<float>(nt*DIM); }
+    ZB_CUDA(ctx->records.reserve(rc0.offset + 256));
+    Carver rc(ctx->records.ptr);
+    a.recSolution = rc.take<float>(nt);
+    a.recLength = rc.take<int>(nt);
+    a.recFlags = rc.take<int>(nt);
+    if (anyGradient) {
+        a.recFirstSource = rc.take<float>(nt);
+        a.recGradBoundary = rc.take<float>(nt*DIM);
+        a.recGradSource = rc.take<float>(nt*DIM);
+    }
+    a.taskCounter = ctx->counters.as<unsigned long long>();
+    ZB_CUDA(cudaMemsetAsync(a.taskCounter, 0, sizeof(unsigned long long), stream));
+
+    preparePointsKernel<DIM><<<blocksFor(n, threads), threads, 0, stream>>>(a);
+    ZB_CUDA(cudaGetLastError());
+
+    if (totalTasks > 0) {
+        // persistent grid: a whole number of waves of 128-thread CTAs over all SMs
+        int perSm = 0;
+        if (a.estimator == ZB_WALK_ON_STARS) {
+            ZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, walkKernel<DIM, true>, 128, 0));
+        } else {
+            ZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, walkKernel<DIM, false>, 128, 0));
+        }
+        perSm = std::max(1, perSm);
+        long long wantBlocks = (totalTasks + 127)/128;
+        int grid = (int)std::min<long long>((long long)ctx->smCount*perSm, wantBlocks);
+        grid = std::max(1, grid);
+        if (a.estimator == ZB_WALK_ON_STARS) walkKernel<DIM, true><<<grid, 128, 0, stream>>>(a);
+        else walkKernel<DIM, false><<<grid, 128, 0, stream>>>(a);
+        ZB_CUDA(cudaGetLastError());
+    }
+
+    reducePointsKernel<DIM><<<blocksFor(n, threads), threads, 0, stream>>>(a);
+    ZB_CUDA(cudaGetLastError());
+    return ZB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *zb_last_error(void) { return g_lastError.c_str(); }
+int zb_abi_version(void) { return ZB_ABI_VERSION; }
+
+int zb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int zb_context_create(int device, zb_context **out)
+{
+    if (!out) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_context_create: out is NULL");
+    *out = nullptr;
+    int n = zb_device_count();
+    if (n <= 0) return fail(ZB_ERR_NO_DEVICE, "zb_context_create: no CUDA device is visible (this library has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_context_create: device index out of range");
+    ZB_CUDA(cudaSetDevice(device));
+    zb_context *ctx = new zb_context();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    ZB_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->smCount = prop.multiProcessorCount;
+    ZB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->ownsStream = true;
+    ZB_CUDA(ctx->status.reserve(256));
+    ZB_CUDA(ctx->counters.reserve(256));
+    ZB_CUDA(cudaMemset(ctx->status.ptr, 0, 256));
+    ZB_CUDA(cudaMemset(ctx->counters.ptr, 0, 256));
+    ZB_CUDA(cudaMallocHost(&ctx->hostStatus, 64));
+    *out = ctx;
+    return ZB_OK;
+}
+
+void zb_context_destroy(zb_context *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->ownsStream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->hostStatus) cudaFreeHost(ctx->hostStatus);
+    delete ctx;
+}
+
+int zb_context_set_stream(zb_context *ctx, void *cudaStream)
+{
+    if (!ctx) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_context_set_stream: ctx is NULL");
+    if (ctx->ownsStream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    ctx->stream = reinterpret_cast<cudaStream_t>(cudaStream);
+    ctx->ownsStream = false;
+    return ZB_OK;
+}
+
+int zb_context_synchronize(zb_context *ctx)
+{
+    if (!ctx) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_context_synchronize: ctx is NULL");
+    ZB_CUDA(cudaSetDevice(ctx->device));
+    ZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZB_OK;
+}
+
+int zb_context_device(const zb_context *ctx) { return ctx ? ctx->device : -1; }
+int zb_context_sm_count(const zb_context *ctx) { return ctx ? ctx->smCount : 0; }
+
+int zb_scene_create(zb_context *ctx, int dim,
+                    const float *absorbingPositions, int nAbsorbingVertices,
+                    const int32_t *absorbingIndices, int nAbsorbingPrimitives,
+                    const float *reflectingPositions, int nReflectingVertices,
+                    const int32_t *reflectingIndices, int nReflectingPrimitives,
+                    int reflectingKind, const float *minRobinCoeff, const float *maxRobinCoeff,
+                    int solveDoubleSided, float silhouettePrecision,
+                    int domainIsWatertight, const float *domainMin, const float *domainMax,
+                    zb_scene **out)
+{
+    if (!ctx || !out) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_scene_create: ctx/out is NULL");
+    *out = nullptr;
+    if (dim != 2 && dim != 3) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_scene_create: dim must be 2 or 3");
+    if (nAbsorbingPrimitives < 0 || nReflectingPrimitives < 0) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_scene_create: negative primitive count");
+    if (nReflectingPrimitives > 0 && reflectingKind != ZB_REFLECTING_NEUMANN && reflectingKind != ZB_REFLECTING_ROBIN)
+        return fail(ZB_ERR_INVALID_ARGUMENT, "zb_scene_create: reflecting mesh given but reflectingKind is not NEUMANN or ROBIN");
+    if (nReflectingPrimitives > 0 && reflectingKind == ZB_REFLECTING_ROBIN && (!minRobinCoeff || !maxRobinCoeff))
+        return fail(ZB_ERR_INVALID_ARGUMENT, "zb_scene_create: Robin boundary needs min/max coefficient arrays");
+    ZB_CUDA(cudaSetDevice(ctx->device));
+
+    zb_scene *scene = new zb_scene();
+    scene->ctx = ctx;
+    scene->dim = dim;
+    scene->watertight = domainIsWatertight;
+    scene->solveDoubleSided = solveDoubleSided;
+    scene->silhouettePrecision = silhouettePrecision;
+    scene->reflectingKind = nReflectingPrimitives > 0 ? reflectingKind : ZB_REFLECTING_NONE;
+    for (int k = 0; k < 3; k++) {
+        // defaults of GeometricQueries() (geometric_queries.h:128-137)
+        scene->domainMin[k] = domainMin && k < dim ? domainMin[k] : -kMaxFloat;
+        scene->domainMax[k] = domainMax && k < dim ? domainMax[k] : kMaxFloat;
+    }
+
+    const char *err = nullptr;
+    if (nAbsorbingPrimitives > 0) {
+        ReflectingOptions none;
+        if (!buildWideBvh(dim, absorbingPositions, nAbsorbingVertices, absorbingIndices, nAbsorbingPrimitives,
+                          none, scene->boundary[ZB_ABSORBING].host, &err)) {
+            delete scene;
+            return fail(ZB_ERR_INVALID_ARGUMENT, std::string("zb_scene_create: absorbing mesh: ") + (err ? err : "?"));
+        }
+        int rc = uploadBvh(ctx, scene->boundary[ZB_ABSORBING], 1);
+        if (rc != ZB_OK) { delete scene; return rc; }
+    }
+    if (nReflectingPrimitives > 0) {
+        ReflectingOptions opt;
+        opt.enabled = true;
+        opt.solveDoubleSided = solveDoubleSided != 0;
+        opt.silhouettePrecision = silhouettePrecision;
+        opt.minCoeff = reflectingKind == ZB_REFLECTING_ROBIN ? minRobinCoeff : nullptr;
+        opt.maxCoeff = reflectingKind == ZB_REFLECTING_ROBIN ? maxRobinCoeff : nullptr;
+        if (!buildWideBvh(dim, reflectingPositions, nReflectingVertices, reflectingIndices, nReflectingPrimitives,
+                          opt, scene->boundary[ZB_REFLECTING].host, &err)) {
+            delete scene;
+            return fail(ZB_ERR_INVALID_ARGUMENT, std::string("zb_scene_create: reflecting mesh: ") + (err ? err : "?"));
+        }
+        int rc = uploadBvh(ctx, scene->boundary[ZB_REFLECTING], reflectingKind == ZB_REFLECTING_NEUMANN ? -1 : 1);
+        if (rc != ZB_OK) { delete scene; return rc; }
+    }
+    *out = scene;
+    return ZB_OK;
+}
+
+void zb_scene_destroy(zb_scene *scene)
+{
+    if (!scene) return;
+    cudaSetDevice(scene->ctx->device);
+    cudaStreamSynchronize(scene->ctx->stream);
+    delete scene;
+}
+
+int zb_scene_update_robin_coefficients(zb_scene *scene, const float *minRobinCoeff, const float *maxRobinCoeff)
+{
+    if (!scene || !minRobinCoeff || !maxRobinCoeff) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_scene_update_robin_coefficients: NULL argument");
+    DeviceBvhStorage& s = scene->boundary[ZB_REFLECTING];
+    if (!s.present || scene->reflectingKind != ZB_REFLECTING_ROBIN)
+        return fail(ZB_ERR_INVALID_ARGUMENT, "zb_scene_update_robin_coefficients: scene has no Robin boundary");
+    ZB_CUDA(cudaSetDevice(scene->ctx->device));
+    updateCoefficients(s.host, minRobinCoeff, maxRobinCoeff);
+    ZB_CUDA(cudaMemcpyAsync(s.cones.ptr, s.host.cones.data(), s.host.cones.size()*sizeof(ChildCone), cudaMemcpyHostToDevice, scene->ctx->stream));
+    ZB_CUDA(cudaMemcpyAsync(s.adjacency.ptr, s.host.adjacency.data(), s.host.adjacency.size()*sizeof(PrimAdjacency), cudaMemcpyHostToDevice, scene->ctx->stream));
+    ZB_CUDA(cudaStreamSynchronize(scene->ctx->stream));
+    return ZB_OK;
+}
+
+int zb_scene_stats(const zb_scene *scene, int boundary, int64_t *bytes, int32_t *nNodes, int32_t *nLeaves, int32_t *maxDepth)
+{
+    if (!scene || boundary < 0 || boundary > 1) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_scene_stats: invalid argument");
+    const DeviceBvhStorage& s = scene->boundary[boundary];
+    if (bytes) *bytes = s.present ? (int64_t)s.bytes() : 0;
+    if (nNodes) *nNodes = s.present ? (int32_t)s.host.nodes.size() : 0;
+    if (nLeaves) *nLeaves = s.present ? s.host.nLeaves : 0;
+    if (maxDepth) *maxDepth = s.present ? s.host.maxDepth : 0;
+    return ZB_OK;
+}
+
+#define ZB_QUERY_PROLOGUE(name)                                                                         \
+    if (!scene) return fail(ZB_ERR_INVALID_ARGUMENT, name ": scene is NULL");                          \
+    if (n < 0) return fail(ZB_ERR_INVALID_ARGUMENT, name ": n < 0");                                   \
+    if (n == 0) return ZB_OK;                                                                          \
+    zb_context *ctx = scene->ctx;                                                                      \
+    ZB_CUDA(cudaSetDevice(ctx->device));                                                               \
+    const int dim = scene->dim;                                                                        \
+    (void)dim;
+
+#define ZB_BOUNDARY(name)                                                                               \
+    if (boundary < 0 || boundary > 1 || !scene->boundary[boundary].present)                            \
+        return fail(ZB_ERR_INVALID_ARGUMENT, name ": the requested boundary is empty");                \
+    const BvhView bvh = scene->boundary[boundary].view;
+
+int zb_closest_point(zb_scene *scene, int boundary, int n, const float *x, const float *maxRadius,
+                     int32_t *prim, float *dist, float *pt, float *normal)
+{
+    ZB_QUERY_PROLOGUE("zb_closest_point")
+    ZB_BOUNDARY("zb_closest_point")
+    if (!x || !prim || !dist) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_closest_point: x/prim/dist is NULL");
+    IoPlan plan;
+    size_t oX = plan.addIn(x, sizeof(float)*dim*n), oR = plan.addIn(maxRadius, maxRadius ? sizeof(float)*n : 0);
+    size_t oP = plan.addOut(prim, sizeof(int32_t)*n), oD = plan.addOut(dist, sizeof(float)*n);
+    size_t oPt = plan.addOut(pt, pt ? sizeof(float)*dim*n : 0), oN = plan.addOut(normal, normal ? sizeof(float)*dim*n : 0);
+    int rc = stageIn(ctx, plan);
+    if (rc != ZB_OK) return rc;
+    int threads = 128, blocks = blocksFor(n, threads);
+    if (dim == 3) closestPointKernel<3><<<blocks, threads, 0, ctx->stream>>>(bvh, n, at<float>(ctx, oX, x), at<float>(ctx, oR, maxRadius),
+        at<int>(ctx, oP, prim), at<float>(ctx, oD, dist), at<float>(ctx, oPt, pt), at<float>(ctx, oN, normal), ctx->status.as<int>());
+    else closestPointKernel<2><<<blocks, threads, 0, ctx->stream>>>(bvh, n, at<float>(ctx, oX, x), at<float>(ctx, oR, maxRadius),
+        at<int>(ctx, oP, prim), at<float>(ctx, oD, dist), at<float>(ctx, oPt, pt), at<float>(ctx, oN, normal), ctx->status.as<int>());
+    ZB_CUDA(cudaGetLastError());
+    rc = stageOut(ctx, plan);
+    if (rc != ZB_OK) return rc;
+    return checkStatus(ctx, "zb_closest_point");
+}
+
+int zb_intersect_ray(zb_scene *scene, int boundary, int n, const float *origin, const float *dir, const float *tMax,
+                     int32_t *prim, float *dist, float *pt, float *normal)
+{
+    ZB_QUERY_PROLOGUE("zb_intersect_ray")
+    ZB_BOUNDARY("zb_intersect_ray")
+    if (!origin || !dir || !prim || !dist) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_intersect_ray: origin/dir/prim/dist is NULL");
+    IoPlan plan;
+    size_t oO = plan.addIn(origin, sizeof(float)*dim*n), oDir = plan.addIn(dir, sizeof(float)*dim*n), oT = plan.addIn(tMax, tMax ? sizeof(float)*n : 0);
+    size_t oP = plan.addOut(prim, sizeof(int32_t)*n), oD = plan.addOut(dist, sizeof(float)*n);
+    size_t oPt = plan.addOut(pt, pt ? sizeof(float)*dim*n : 0), oN = plan.addOut(normal, normal ? sizeof(float)*dim*n : 0);
+    int rc = stageIn(ctx, plan);
+    if (rc != ZB_OK) return rc;
+    int threads = 128, blocks = blocksFor(n, threads);
+    if (dim == 3) intersectRayKernel<3><<<blocks, threads, 0, ctx->stream>>>(bvh, n, at<float>(ctx, oO, origin), at<float>(ctx, oDir, dir), at<float>(ctx, oT, tMax),
+        at<int>(ctx, oP, prim), at<float>(ctx, oD, dist), at<float>(ctx, oPt, pt), at<float>(ctx, oN, normal), ctx->status.as<int>());
+    else intersectRayKernel<2><<<blocks, threads, 0, ctx->stream>>>(bvh, n, at<float>(ctx, oO, origin), at<float>(ctx, oDir, dir), at<float>(ctx, oT, tMax),
+        at<int>(ctx, oP, prim), at<float>(ctx, oD, dist), at<float>(ctx, oPt, pt), at<float>(ctx, oN, normal), ctx->status.as<int>());
+    ZB_CUDA(cudaGetLastError());
+    rc = stageOut(ctx, plan);
+    if (rc != ZB_OK) return rc;
+    return checkStatus(ctx, "zb_intersect_ray");
+}
+
+int zb_occluded(zb_scene *scene, int boundary, int n, const float *a, const float *b, uint8_t *occluded)
+{
+    ZB_QUERY_PROLOGUE("zb_occluded")
+    ZB_BOUNDARY("zb_occluded")
+    if (!a || !b || !occluded) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_occluded: NULL argument");
+    IoPlan plan;
+    size_t oA = plan.addIn(a, sizeof(float)*dim*n), oB = plan.addIn(b, sizeof(float)*dim*n);
+    size_t oO = plan.addOut(occluded, (size_t)n);
+    int rc = stageIn(ctx, plan);
+    if (rc != ZB_OK) return rc;
+    int threads = 128, blocks = blocksFor(n, threads);
+    if (dim == 3) occludedKernel<3><<<blocks, threads, 0, ctx->stream>>>(bvh, n, at<float>(ctx, oA, a), at<float>(ctx, oB, b), at<uint8_t>(ctx, oO, occluded), ctx->status.as<int>());
+    else occludedKernel<2><<<blocks, threads, 0, ctx->stream>>>(bvh, n, at<float>(ctx, oA, a), at<float>(ctx, oB, b), at<uint8_t>(ctx, oO, occluded), ctx->status.as<int>());
+    ZB_CUDA(cudaGetLastError());
+    rc = stageOut(ctx, plan);
+    if (rc != ZB_OK) return rc;
+    return checkStatus(ctx, "zb_occluded");
+}
+
+int zb_sample_sphere(zb_scene *scene, int boundary, int n, const float *x, const float *radius, const float *randNums,
+                     int32_t *prim, float *pt, float *normal, float *pdf)
+{
+    ZB_QUERY_PROLOGUE("zb_sample_sphere")
+    ZB_BOUNDARY("zb_sample_sphere")
+    if (!x || !radius || !randNums || !prim || !pdf) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_sample_sphere: NULL argument");
+    IoPlan plan;
+    size_t oX = plan.addIn(x, sizeof(float)*dim*n), oR = plan.addIn(radius, sizeof(float)*n), oU = plan.addIn(randNums, sizeof(float)*dim*n);
+    size_t oP = plan.addOut(prim, sizeof(int32_t)*n), oPt = plan.addOut(pt, pt ? sizeof(float)*dim*n : 0);
+    size_t oN = plan.addOut(normal, normal ? sizeof(float)*dim*n : 0), oPdf = plan.addOut(pdf, sizeof(float)*n);
+    int rc = stageIn(ctx, plan);
+    if (rc != ZB_OK) return rc;
+    int threads = 128, blocks = blocksFor(n, threads);
+    if (dim == 3) sampleSphereKernel<3><<<blocks, threads, 0, ctx->stream>>>(bvh, n, at<float>(ctx, oX, x), at<float>(ctx, oR, radius), at<float>(ctx, oU, randNums),
+        at<int>(ctx, oP, prim), at<float>(ctx, oPt, pt), at<float>(ctx, oN, normal), at<float>(ctx, oPdf, pdf));
+    else sampleSphereKernel<2><<<blocks, threads, 0, ctx->stream>>>(bvh, n, at<float>(ctx, oX, x), at<float>(ctx, oR, radius), at<float>(ctx, oU, randNums),
+        at<int>(ctx, oP, prim), at<float>(ctx, oPt, pt), at<float>(ctx, oN, normal), at<float>(ctx, oPdf, pdf));
+    ZB_CUDA(cudaGetLastError());
+    return stageOut(ctx, plan);
+}
+
+int zb_star_radius(zb_scene *scene, int n, const float *x, const float *minRadius, const float *maxRadius,
+                   float silhouettePrecision, const uint8_t *flipNormalOrientation, float *radius)
+{
+    ZB_QUERY_PROLOGUE("zb_star_radius")
+    if (!x || !minRadius || !maxRadius || !radius) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_star_radius: NULL argument");
+    IoPlan plan;
+    size_t oX = plan.addIn(x, sizeof(float)*dim*n), oMn = plan.addIn(minRadius, sizeof(float)*n), oMx = plan.addIn(maxRadius, sizeof(float)*n);
+    size_t oF = plan.addIn(flipNormalOrientation, flipNormalOrientation ? (size_t)n : 0);
+    size_t oR = plan.addOut(radius, sizeof(float)*n);
+    int rc = stageIn(ctx, plan);
+    if (rc != ZB_OK) return rc;
+    SolveArgs a;
+    fillSceneArgs(scene, a);
+    int threads = 128, blocks = blocksFor(n, threads);
+    if (dim == 3) starRadiusKernel<3><<<blocks, threads, 0, ctx->stream>>>(a, n, at<float>(ctx, oX, x), at<float>(ctx, oMn, minRadius), at<float>(ctx, oMx, maxRadius),
+        silhouettePrecision, at<uint8_t>(ctx, oF, flipNormalOrientation), at<float>(ctx, oR, radius));
+    else starRadiusKernel<2><<<blocks, threads, 0, ctx->stream>>>(a, n, at<float>(ctx, oX, x), at<float>(ctx, oMn, minRadius), at<float>(ctx, oMx, maxRadius),
+        silhouettePrecision, at<uint8_t>(ctx, oF, flipNormalOrientation), at<float>(ctx, oR, radius));
+    ZB_CUDA(cudaGetLastError());
+    rc = stageOut(ctx, plan);
+    if (rc != ZB_OK) return rc;
+    return checkStatus(ctx, "zb_star_radius");
+}
+
+int zb_solve_dev(zb_scene *scene, int estimator, const zb_pde_desc *pde, const zb_walk_settings *settings,
+                 const zb_sample_points *pts, zb_statistics *stats, int64_t *walkSteps_dev)
+{
+    if (!scene || !pde || !settings || !pts || !stats) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_solve_dev: NULL argument");
+    if (estimator != ZB_WALK_ON_SPHERES && estimator != ZB_WALK_ON_STARS) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_solve_dev: unknown estimator");
+    if (pts->n < 0) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_solve_dev: negative point count");
+    if (pts->n == 0) return ZB_OK;
+    if (!pts->pt || !pts->normal || !pts->type || !pts->estimationQuantity || !pts->distToAbsorbingBoundary ||
+        !pts->distToReflectingBoundary || !pts->nWalks || !pts->rngState || !pts->rngInc || !pts->firstSphereRadius)
+        return fail(ZB_ERR_INVALID_ARGUMENT, "zb_solve_dev: a required sample-point array is NULL");
+    if (pde->mode != ZB_PDE_MANUFACTURED && pde->mode != ZB_PDE_CONSTANT) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_solve_dev: unknown pde mode");
+    if (pde->kelvin) return fail(ZB_ERR_UNSUPPORTED, "zb_solve_dev: Kelvin-transformed PDEs are not implemented yet");
+    if (settings->printLogs) return fail(ZB_ERR_UNSUPPORTED, "zb_solve_dev: printLogs is not supported on the device");
+    zb_context *ctx = scene->ctx;
+    ZB_CUDA(cudaSetDevice(ctx->device));
+
+    SolveArgs a;
+    fillSceneArgs(scene, a);
+    a.estimator = estimator;
+    a.ws = *settings;
+    a.pde = *pde;
+    a.pts = *pts;
+    a.stats = *stats;
+    a.walkSteps = ctx->counters.as<long long>() + 1;
+    ZB_CUDA(cudaMemsetAsync(a.walkSteps, 0, sizeof(long long), ctx->stream));
+
+    int rc = scene->dim == 3 ? solveRange<3>(scene, a, pts->n, g_gradientHint) : solveRange<2>(scene, a, pts->n, g_gradientHint);
+    if (rc != ZB_OK) return rc;
+    if (walkSteps_dev) {
+        ZB_CUDA(cudaMemcpyAsync(walkSteps_dev, a.walkSteps, sizeof(long long), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return checkStatus(ctx, "zb_solve_dev");
+}
+
+int zb_solve(zb_scene *scene, int estimator, const zb_pde_desc *pde, const zb_walk_settings *settings,
+             const zb_sample_points *pts, zb_statistics *stats, int64_t *walkSteps)
+{
+    if (!scene || !pts || !stats) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_solve: NULL argument");
+    if (pts->n < 0) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_solve: negative point count");
+    if (walkSteps) *walkSteps = 0;
+    if (pts->n == 0) return ZB_OK;
+    if (!pts->pt || !pts->normal || !pts->type || !pts->estimationQuantity || !pts->distToAbsorbingBoundary ||
+        !pts->distToReflectingBoundary || !pts->nWalks || !pts->rngState || !pts->rngInc || !pts->firstSphereRadius)
+        return fail(ZB_ERR_INVALID_ARGUMENT, "zb_solve: a required sample-point array is NULL");
+    if (!stats->solutionMean || !stats->solutionM2 || !stats->gradientMean || !stats->gradientM2 ||
+        !stats->totalFirstSourceContribution || !stats->totalDerivativeContribution || !stats->nSolutionEstimates ||
+        !stats->nGradientEstimates || !stats->totalWalkLength || !stats->totalSplits)
+        return fail(ZB_ERR_INVALID_ARGUMENT, "zb_solve: a statistics array is NULL");
+    zb_context *ctx = scene->ctx;
+    ZB_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)pts->n, dim = (size_t)scene->dim;
+
+    IoPlan plan;
+    zb_sample_points dp = *pts;
+    zb_statistics ds = *stats;
+    size_t o;
+#define IN_OUT(field, hostPtr, bytes, type)                                                       \
+    o = plan.addIn(hostPtr, bytes); plan.outputs.push_back({(void *)(hostPtr), bytes}); plan.outOffsets.push_back(o); field##Off = o;
+#define IN_ONLY(hostPtr, bytes) plan.addIn(hostPtr, (hostPtr) ? (bytes) : 0)
+    size_t ptOff = IN_ONLY(pts->pt, 4*dim*n), nOff = IN_ONLY(pts->normal, 4*dim*n),
+           ddOff = IN_ONLY(pts->directionForDerivative, 4*dim*n), tyOff = IN_ONLY(pts->type, 4*n),
+           eqOff = IN_ONLY(pts->estimationQuantity, 4*n), daOff = IN_ONLY(pts->distToAbsorbingBoundary, 4*n),
+           drOff = IN_ONLY(pts->distToReflectingBoundary, 4*n), naOff = IN_ONLY(pts->estimateBoundaryNormalAligned, n),
+           nwOff = IN_ONLY(pts->nWalks, 4*n), incOff = IN_ONLY(pts->rngInc, 8*n);
+    size_t rngStateOff, fsrOff, meanOff, m2Off, gmeanOff, gm2Off, fsOff, dcOff, nsOff, ngOff, wlOff, spOff;
+    IN_OUT(rngState, pts->rngState, 8*n, uint64_t)
+    IN_OUT(fsr, pts->firstSphereRadius, 4*n, float)
+    IN_OUT(mean, stats->solutionMean, 4*n, float)
+    IN_OUT(m2, stats->solutionM2, 4*n, float)
+    IN_OUT(gmean, stats->gradientMean, 4*dim*n, float)
+    IN_OUT(gm2, stats->gradientM2, 4*dim*n, float)
+    IN_OUT(fs, stats->totalFirstSourceContribution, 4*n, float)
+    IN_OUT(dc, stats->totalDerivativeContribution, 4*n, float)
+    IN_OUT(ns, stats->nSolutionEstimates, 4*n, int)
+    IN_OUT(ng, stats->nGradientEstimates, 4*n, int)
+    IN_OUT(wl, stats->totalWalkLength, 4*n, int)
+    IN_OUT(sp, stats->totalSplits, 4*n, int)
+#undef IN_OUT
+#undef IN_ONLY
+    size_t stepsOff = plan.total = (plan.total + 255) & ~size_t(255);
+    plan.total += 8;
+    int rc = stageIn(ctx, plan);
+    if (rc != ZB_OK) return rc;
+    char *base = ctx->io.as<char>();
+    dp.pt = (const float *)(base + ptOff);
+    dp.normal = (const float *)(base + nOff);
+    dp.directionForDerivative = pts->directionForDerivative ? (const float *)(base + ddOff) : nullptr;
+    dp.type = (const int32_t *)(base + tyOff);
+    dp.estimationQuantity = (const int32_t *)(base + eqOff);
+    dp.distToAbsorbingBoundary = (const float *)(base + daOff);
+    dp.distToReflectingBoundary = (const float *)(base + drOff);
+    dp.estimateBoundaryNormalAligned = pts->estimateBoundaryNormalAligned ? (const uint8_t *)(base + naOff) : nullptr;
+    dp.nWalks = (const int32_t *)(base + nwOff);
+    dp.rngInc = (uint64_t *)(base + incOff);
+    dp.rngState = (uint64_t *)(base + rngStateOff);
+    dp.firstSphereRadius = (float *)(base + fsrOff);
+    ds.solutionMean = (float *)(base + meanOff);
+    ds.solutionM2 = (float *)(base + m2Off);
+    ds.gradientMean = (float *)(base + gmeanOff);
+    ds.gradientM2 = (float *)(base + gm2Off);
+    ds.totalFirstSourceContribution = (float *)(base + fsOff);
+    ds.totalDerivativeContribution = (float *)(base + dcOff);
+    ds.nSolutionEstimates = (int32_t *)(base + nsOff);
+    ds.nGradientEstimates = (int32_t *)(base + ngOff);
+    ds.totalWalkLength = (int32_t *)(base + wlOff);
+    ds.totalSplits = (int32_t *)(base + spOff);
+
+    bool anyGradient = false;
+    for (size_t i = 0; i < n && !anyGradient; i++) anyGradient = pts->estimationQuantity[i] == ZB_SOLUTION_AND_GRADIENT;
+    g_gradientHint = anyGradient;
+    rc = zb_solve_dev(scene, estimator, pde, settings, &dp, &ds, (int64_t *)(base + stepsOff));
+    g_gradientHint = true;
+    if (rc != ZB_OK) return rc;
+    if (walkSteps) ZB_CUDA(cudaMemcpyAsync(walkSteps, base + stepsOff, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    return stageOut(ctx, plan);
+}
+
+int zb_pcg32_kat(zb_context *ctx, uint64_t initstate, uint64_t initseq, int n, uint32_t *out)
+{
+    if (!ctx || !out || n < 0) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_pcg32_kat: invalid argument");
+    if (n == 0) return ZB_OK;
+    ZB_CUDA(cudaSetDevice(ctx->device));
+    ZB_CUDA(ctx->io.reserve(sizeof(uint32_t)*(size_t)n));
+    pcg32Kernel<<<1, 32, 0, ctx->stream>>>(initstate, initseq, n, ctx->io.as<uint32_t>());
+    ZB_CUDA(cudaGetLastError());
+    ZB_CUDA(cudaMemcpyAsync(out, ctx->io.ptr, sizeof(uint32_t)*(size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    ZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZB_OK;
+}
+
+} // extern "C"

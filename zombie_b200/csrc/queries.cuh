@@ -1,0 +1,838 @@
+// Device-side geometric queries over the wide quantised BVH (wide_bvh.h): closest point, closest
+// ray hit / occlusion, stochastic primitive sampling inside a sphere, and the star radius for
+// Neumann / Robin boundaries. One thread runs one query; the traversal stack lives in local
+// memory and children are ordered by a register sorting network so the nearest child is popped
+// first. These replace the five stack-based traversals of fcpw::Bvh
+// (fcpw/aggregates/bvh.inl:656-771, 1141-1288, 1291-1418, 1436-1596) and
+// ReflectanceBvh::computeSquaredStarRadius (zombie/utils/reflectance_boundary_bvh/bvh.h:370-506).
+#pragma once
+
+#include "vec.cuh"
+
+namespace zb {
+
+struct BvhView {
+    const uint4 *nodes;        // 5 per node
+    const float4 *prims;       // 3D: 3 per triangle (v0|index, v1, v2); 2D: 1 per segment (ax, ay, bx, by)
+    const int *primIndex;      // leaf order -> caller's primitive index
+    const float4 *cones;       // 2 per child slot (16 per node); reflecting boundaries only
+    const float4 *adjacency;   // 3 per primitive; reflecting boundaries only
+    int nPrims;
+    int snchSign;              // 1: Robin handler convention; -1: FCPW SNCH (Neumann handler) convention
+};
+
+constexpr int kStackSize = 64;
+constexpr uint32_t kLeafFlag = 0x80000000u;
+
+// status bits raised by kernels (read back by the host after each launch)
+enum : int { kStatusStackOverflow = 1 };
+
+struct NodeRegs {
+    uint4 q[5];
+};
+
+ZB_DEV void loadNode(const uint4 *nodes, uint32_t idx, NodeRegs& n)
+{
+    const uint4 *p = nodes + (size_t)idx*5;
+#pragma unroll
+    for (int i = 0; i < 5; i++) n.q[i] = __ldg(p + i);
+}
+
+ZB_DEV float byteF(uint32_t w, int i) { return (float)((w >> (8*i)) & 0xffu); }
+
+// word holding the quantised coordinate bytes of children 0..3 / 4..7: axis 0..2, side 0 = lo, 1 = hi
+ZB_DEV uint32_t qword(const NodeRegs& n, int axis, int side, int half)
+{
+    int w = 8 + 6*side + 2*axis + half; // index into the 20 words of the node
+    const uint32_t *words = reinterpret_cast<const uint32_t *>(&n.q[0]);
+    return words[w];
+}
+
+template <int DIM>
+struct NodeFrame {
+    float o[DIM], s[DIM];
+};
+
+template <int DIM>
+ZB_DEV NodeFrame<DIM> nodeFrame(const NodeRegs& n)
+{
+    NodeFrame<DIM> f;
+    f.o[0] = __uint_as_float(n.q[0].x);
+    f.o[1] = __uint_as_float(n.q[0].y);
+    if (DIM == 3) f.o[DIM - 1] = __uint_as_float(n.q[0].z);
+    uint32_t e = n.q[0].w;
+    f.s[0] = __uint_as_float((e & 0xffu) << 23);
+    f.s[1] = __uint_as_float(((e >> 8) & 0xffu) << 23);
+    if (DIM == 3) f.s[DIM - 1] = __uint_as_float(((e >> 16) & 0xffu) << 23);
+    return f;
+}
+
+template <int DIM>
+ZB_DEV void childBox(const NodeRegs& n, const NodeFrame<DIM>& f, int c, float lo[DIM], float hi[DIM])
+{
+#pragma unroll
+    for (int k = 0; k < DIM; k++) {
+        lo[k] = fmaf(f.s[k], byteF(qword(n, k, 0, c >> 2), c & 3), f.o[k]);
+        hi[k] = fmaf(f.s[k], byteF(qword(n, k, 1, c >> 2), c & 3), f.o[k]);
+    }
+}
+
+ZB_DEV uint32_t childMeta(const NodeRegs& n, int c)
+{
+    uint32_t w = c < 4 ? n.q[1].z : n.q[1].w;
+    return (w >> (8*(c & 3))) & 0xffu;
+}
+
+// stack reference of child slot c: internal -> node index; leaf -> flag | count << 28 | first primitive
+ZB_DEV uint32_t childRef(const NodeRegs& n, uint32_t meta)
+{
+    uint32_t count = meta >> 5;
+    if (count) return kLeafFlag | (count << 28) | (n.q[1].y + (meta & 31u));
+    return n.q[1].x + (meta & 31u) - 1u;
+}
+
+ZB_DEV void cswap(uint32_t& a, uint32_t& b) { uint32_t lo = min(a, b); b = max(a, b); a = lo; }
+
+// ascending sort of 8 keys (19 compare-exchanges)
+ZB_DEV void sort8(uint32_t k[8])
+{
+    cswap(k[0], k[1]); cswap(k[2], k[3]); cswap(k[4], k[5]); cswap(k[6], k[7]);
+    cswap(k[0], k[2]); cswap(k[1], k[3]); cswap(k[4], k[6]); cswap(k[5], k[7]);
+    cswap(k[1], k[2]); cswap(k[5], k[6]); cswap(k[0], k[4]); cswap(k[3], k[7]);
+    cswap(k[1], k[5]); cswap(k[2], k[6]);
+    cswap(k[1], k[4]); cswap(k[3], k[6]);
+    cswap(k[2], k[4]); cswap(k[3], k[5]);
+    cswap(k[3], k[4]);
+}
+
+ZB_DEV float keyValue(uint32_t key) { return __uint_as_float(key & ~7u); }
+
+// ------------------------------------------------------------------------------------------
+// primitives
+// ------------------------------------------------------------------------------------------
+
+// closest point on triangle (pa, pb, pc) to x by Voronoi-region classification (Ericson, Real-Time
+// Collision Detection 5.1.5), the same classification order and comparisons as
+// fcpw/geometry/triangles.inl:374-458 so that region ties resolve identically.
+ZB_DEV float closestPointTriangle(const Vec<3>& pa, const Vec<3>& pb, const Vec<3>& pc, const Vec<3>& x,
+                                  Vec<3>& pt, float& bu, float& bv)
+{
+    Vec<3> ab = pb - pa, ac = pc - pa, ax = x - pa;
+    float d1 = dot(ab, ax), d2 = dot(ac, ax);
+    if (d1 <= 0.0f && d2 <= 0.0f) { bu = 1.0f; bv = 0.0f; pt = pa; return norm(x - pt); }
+
+    Vec<3> bx = x - pb;
+    float d3 = dot(ab, bx), d4 = dot(ac, bx);
+    if (d3 >= 0.0f && d4 <= d3) { bu = 0.0f; bv = 1.0f; pt = pb; return norm(x - pt); }
+
+    Vec<3> cx = x - pc;
+    float d5 = dot(ab, cx), d6 = dot(ac, cx);
+    if (d6 >= 0.0f && d5 <= d6) { bu = 0.0f; bv = 0.0f; pt = pc; return norm(x - pt); }
+
+    float vc = d1*d4 - d3*d2;
+    if (vc <= 0.0f && d1 >= 0.0f && d3 <= 0.0f) {
+        float v = d1/(d1 - d3);
+        bu = 1.0f - v; bv = v;
+        pt = pa + ab*v;
+        return norm(x - pt);
+    }
+
+    float vb = d5*d2 - d1*d6;
+    if (vb <= 0.0f && d2 >= 0.0f && d6 <= 0.0f) {
+        float w = d2/(d2 - d6);
+        bu = 1.0f - w; bv = 0.0f;
+        pt = pa + ac*w;
+        return norm(x - pt);
+    }
+
+    float va = d3*d6 - d5*d4;
+    if (va <= 0.0f && (d4 - d3) >= 0.0f && (d5 - d6) >= 0.0f) {
+        float w = (d4 - d3)/((d4 - d3) + (d5 - d6));
+        bu = 0.0f; bv = 1.0f - w;
+        pt = pb + (pc - pb)*w;
+        return norm(x - pt);
+    }
+
+    float denom = 1.0f/(va + vb + vc);
+    float v = vb*denom, w = vc*denom;
+    bu = 1.0f - v - w; bv = v;
+    pt = pa + ab*v + ac*w;
+    return norm(x - pt);
+}
+
+// fcpw/geometry/line_segments.inl:200-227
+template <int DIM>
+ZB_DEV float closestPointSegment(const Vec<DIM>& pa, const Vec<DIM>& pb, const Vec<DIM>& x, Vec<DIM>& pt, float& t)
+{
+    Vec<DIM> u = pb - pa, v = x - pa;
+    float c1 = dot(u, v);
+    if (c1 <= 0.0f) { pt = pa; t = 0.0f; return norm(x - pt); }
+    float c2 = dot(u, u);
+    if (c2 <= c1) { pt = pb; t = 1.0f; return norm(x - pt); }
+    t = c1/c2;
+    pt = pa + u*t;
+    return norm(x - pt);
+}
+
+template <int DIM> struct Prim;
+
+template <> struct Prim<3> {
+    Vec<3> a, b, c;
+    int index;
+    ZB_DEV void load(const BvhView& bvh, uint32_t i) {
+        float4 v0 = __ldg(bvh.prims + (size_t)3*i), v1 = __ldg(bvh.prims + (size_t)3*i + 1), v2 = __ldg(bvh.prims + (size_t)3*i + 2);
+        a = make3(v0.x, v0.y, v0.z); b = make3(v1.x, v1.y, v1.z); c = make3(v2.x, v2.y, v2.z);
+        index = __float_as_int(v0.w);
+    }
+    ZB_DEV float closest(const Vec<3>& x, Vec<3>& pt, float& u, float& v) const { return closestPointTriangle(a, b, c, x, pt, u, v); }
+    // unnormalised normal (b-a)x(c-a): fcpw Triangle::normal()
+    ZB_DEV Vec<3> rawNormal() const { return cross(b - a, c - a); }
+    ZB_DEV float area() const { return 0.5f*norm(rawNormal()); } // triangles.inl:34-37
+    // Moller-Trumbore with the parallel cutoff and inclusive bounds of triangles.inl:222-260
+    ZB_DEV bool intersect(const Vec<3>& o, const Vec<3>& d, float tMax, float& t, float& bv, float& bw) const {
+        Vec<3> v1 = b - a, v2 = c - a;
+        Vec<3> p = cross(d, v2);
+        float det = dot(v1, p);
+        if (fabsf(det) <= kEpsilon) return false;
+        float invDet = 1.0f/det;
+        Vec<3> s = o - a;
+        float v = dot(s, p)*invDet;
+        if (v < 0.0f || v > 1.0f) return false;
+        Vec<3> q = cross(s, v1);
+        float w = dot(d, q)*invDet;
+        if (w < 0.0f || v + w > 1.0f) return false;
+        float tt = dot(v2, q)*invDet;
+        if (tt >= 0.0f && tt <= tMax) { t = tt; bv = v; bw = w; return true; }
+        return false;
+    }
+    ZB_DEV Vec<3> pointAt(float bv, float bw) const { return a + (b - a)*bv + (c - a)*bw; }
+    // uniform point: triangles.inl:113-131 (uses randNums[1], randNums[2]); returns pdf 2/|n|
+    ZB_DEV float sample(const Vec<3>& rand, Vec<3>& p, Vec<3>& n) const {
+        n = rawNormal();
+        float area2 = norm(n);
+        float u1 = sqrtf(rand[1]), u2 = rand[2];
+        float u = 1.0f - u1, v = u2*u1, w = 1.0f - u - v;
+        p = a*u + b*v + c*w;
+        n = n/area2;
+        return 2.0f/area2;
+    }
+};
+
+template <> struct Prim<2> {
+    Vec<2> a, b;
+    int index;
+    ZB_DEV void load(const BvhView& bvh, uint32_t i) {
+        float4 v = __ldg(bvh.prims + i);
+        a = make2(v.x, v.y); b = make2(v.z, v.w);
+        index = __ldg(bvh.primIndex + i);
+    }
+    ZB_DEV float closest(const Vec<2>& x, Vec<2>& pt, float& u, float& v) const { v = 0.0f; return closestPointSegment<2>(a, b, x, pt, u); }
+    ZB_DEV Vec<2> rawNormal() const { Vec<2> s = b - a; return make2(s[1], -s[0]); }
+    ZB_DEV float area() const { return norm(b - a); }
+    // line_segments.inl:140-175
+    ZB_DEV bool intersect(const Vec<2>& o, const Vec<2>& d, float tMax, float& t, float& bs, float& unused) const {
+        Vec<2> u = a - o, v = b - a;
+        float dv = cross2(d, v);
+        if (fabsf(dv) <= kEpsilon) return false;
+        float ud = cross2(u, d);
+        float s = ud/dv;
+        if (s >= 0.0f && s <= 1.0f) {
+            float uv = cross2(u, v);
+            float tt = uv/dv;
+            if (tt >= 0.0f && tt <= tMax) { t = tt; bs = s; unused = 0.0f; return true; }
+        }
+        return false;
+    }
+    ZB_DEV Vec<2> pointAt(float s, float) const { return a + (b - a)*s; }
+    // line_segments.inl:83-98 (uses randNums[1])
+    ZB_DEV float sample(const Vec<2>& rand, Vec<2>& p, Vec<2>& n) const {
+        Vec<2> s = b - a;
+        float len = norm(s);
+        p = a + s*rand[1];
+        n = make2(s[1], -s[0])/len;
+        return 1.0f/len;
+    }
+};
+
+template <int DIM>
+ZB_DEV Vec<DIM> unitNormal(const Prim<DIM>& p) { Vec<DIM> n = p.rawNormal(); return n/norm(n); }
+
+// ------------------------------------------------------------------------------------------
+// closest point
+// ------------------------------------------------------------------------------------------
+
+template <int DIM>
+struct ClosestHit {
+    float d;        // distance (kMaxFloat when nothing found)
+    int prim;       // leaf-order primitive, -1 when nothing found
+    Vec<DIM> p;
+};
+
+// squared distance bounds from x to the box [lo, hi]
+template <int DIM>
+ZB_DEV void boxDistance2(const float lo[DIM], const float hi[DIM], const Vec<DIM>& x, float& d2min, float& d2max)
+{
+    d2min = 0.0f; d2max = 0.0f;
+#pragma unroll
+    for (int k = 0; k < DIM; k++) {
+        float u = lo[k] - x[k], v = x[k] - hi[k];
+        float dn = fmaxf(fmaxf(u, v), 0.0f);
+        float df = fminf(u, v);
+        d2min = fmaf(dn, dn, d2min);
+        d2max = fmaf(df, df, d2max);
+    }
+}
+
+// Aggregate::findClosestPoint(BoundingSphere(x, r2)) — bvh.inl:1291-1418. The search radius also
+// shrinks by each child's farthest-corner distance (bvh.inl:1339-1343), which bounds the stack.
+template <int DIM>
+ZB_DEV bool closestPoint(const BvhView& bvh, const Vec<DIM>& x, float r2, ClosestHit<DIM>& hit, int *status)
+{
+    uint2 stack[kStackSize];
+    int sp = 0;
+    stack[sp++] = make_uint2(0u, 0u);
+    hit.d = kMaxFloat;
+    hit.prim = -1;
+    hit.p = x;
+
+    while (sp > 0) {
+        uint2 e = stack[--sp];
+        if (keyValue(e.x) > r2) continue;
+        if (e.y & kLeafFlag) {
+            uint32_t first = e.y & 0x0fffffffu, count = (e.y >> 28) & 7u;
+            for (uint32_t i = 0; i < count; i++) {
+                Prim<DIM> prim;
+                prim.load(bvh, first + i);
+                Vec<DIM> pt;
+                float u, v;
+                float d = prim.closest(x, pt, u, v);
+                float d2 = d*d;
+                if (d2 <= r2) { // triangles.inl:479: inclusive, later primitives replace equal distances
+                    r2 = d2;
+                    hit.d = d;
+                    hit.prim = (int)(first + i);
+                    hit.p = pt;
+                }
+            }
+            continue;
+        }
+
+        NodeRegs n;
+        loadNode(bvh.nodes, e.y, n);
+        NodeFrame<DIM> f = nodeFrame<DIM>(n);
+        uint32_t keys[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            float lo[DIM], hi[DIM], d2min, d2max;
+            childBox<DIM>(n, f, c, lo, hi);
+            boxDistance2<DIM>(lo, hi, x, d2min, d2max);
+            bool valid = childMeta(n, c) != 0u;
+            if (valid) r2 = fminf(r2, d2max);
+            keys[c] = valid ? ((__float_as_uint(d2min) & ~7u) | (uint32_t)c) : 0xffffffffu;
+        }
+        sort8(keys);
+#pragma unroll
+        for (int c = 7; c >= 0; c--) {
+            uint32_t key = keys[c];
+            if (key != 0xffffffffu && keyValue(key) <= r2) {
+                if (sp < kStackSize) stack[sp++] = make_uint2(key, childRef(n, childMeta(n, key & 7u)));
+                else if (status) atomicOr(status, kStatusStackOverflow);
+            }
+        }
+    }
+    return hit.prim >= 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// rays
+// ------------------------------------------------------------------------------------------
+
+template <int DIM>
+struct RayHit {
+    float t;
+    int prim;     // leaf order, -1 on miss
+    float bv, bw; // barycentric parameters of the hit
+};
+
+// Aggregate::intersect(Ray) closest hit or occlusion — bvh.inl:656-771; slab test of
+// fcpw/core/bounding_volumes.h:99-114 on the decoded child boxes.
+template <int DIM, bool ANY_HIT>
+ZB_DEV bool intersectRay(const BvhView& bvh, const Vec<DIM>& o, const Vec<DIM>& d, float tMax, RayHit<DIM>& hit, int *status)
+{
+    uint2 stack[kStackSize];
+    int sp = 0;
+    stack[sp++] = make_uint2(0u, 0u);
+    hit.t = kMaxFloat;
+    hit.prim = -1;
+    hit.bv = hit.bw = 0.0f;
+    float invD[DIM];
+#pragma unroll
+    for (int k = 0; k < DIM; k++) invD[k] = 1.0f/d[k];
+
+    while (sp > 0) {
+        uint2 e = stack[--sp];
+        if (keyValue(e.x) > tMax) continue;
+        if (e.y & kLeafFlag) {
+            uint32_t first = e.y & 0x0fffffffu, count = (e.y >> 28) & 7u;
+            for (uint32_t i = 0; i < count; i++) {
+                Prim<DIM> prim;
+                prim.load(bvh, first + i);
+                float t, bv, bw;
+                if (prim.intersect(o, d, tMax, t, bv, bw)) {
+                    if (ANY_HIT) { hit.prim = (int)(first + i); hit.t = t; return true; }
+                    tMax = fminf(tMax, t);
+                    hit.t = t; hit.prim = (int)(first + i); hit.bv = bv; hit.bw = bw;
+                }
+            }
+            continue;
+        }
+
+        NodeRegs n;
+        loadNode(bvh.nodes, e.y, n);
+        NodeFrame<DIM> f = nodeFrame<DIM>(n);
+        uint32_t keys[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            float lo[DIM], hi[DIM];
+            childBox<DIM>(n, f, c, lo, hi);
+            float tNear = 0.0f, tFar = tMax;
+#pragma unroll
+            for (int k = 0; k < DIM; k++) {
+                float t0 = (lo[k] - o[k])*invD[k], t1 = (hi[k] - o[k])*invD[k];
+                tNear = fmaxf(tNear, fminf(t0, t1));
+                tFar = fminf(tFar, fmaxf(t0, t1));
+            }
+            bool valid = childMeta(n, c) != 0u && tNear <= tFar;
+            keys[c] = valid ? ((__float_as_uint(tNear) & ~7u) | (uint32_t)c) : 0xffffffffu;
+        }
+        sort8(keys);
+#pragma unroll
+        for (int c = 7; c >= 0; c--) {
+            uint32_t key = keys[c];
+            if (key != 0xffffffffu) {
+                if (sp < kStackSize) stack[sp++] = make_uint2(key, childRef(n, childMeta(n, key & 7u)));
+                else if (status) atomicOr(status, kStatusStackOverflow);
+            }
+        }
+    }
+    return hit.prim >= 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// stochastic sampling of one primitive inside a sphere
+// ------------------------------------------------------------------------------------------
+
+// getBranchTraversalWeightCallback (fcpw_geometric_queries.h:1391-1398): |G_harmonic3D(max(r, 1e-2))|
+ZB_DEV float branchWeight(float r2)
+{
+    float r = fmaxf(sqrtf(r2), 1e-2f);
+    return fabsf(1.0f/(4.0f*kPiF*r));
+}
+
+template <int DIM>
+struct SphereSample {
+    int prim;    // leaf order, -1 when no primitive intersects the sphere
+    Vec<DIM> p, n;
+    float pdf;
+};
+
+// Aggregate::intersect(sphere, randNums, branchTraversalWeight) — bvh.inl:1141-1288: one stochastic
+// root-to-leaf descent; here every level chooses among up to 8 children in proportion to the
+// traversal weight of the child box centroid, then a primitive of the chosen leaf in proportion
+// to its area by reservoir selection, all driven by the single random number rand[0].
+template <int DIM>
+ZB_DEV bool sampleSphere(const BvhView& bvh, const Vec<DIM>& x, float r2, const Vec<DIM>& rand, SphereSample<DIM>& out)
+{
+    out.prim = -1;
+    out.pdf = 0.0f;
+    out.p = x;
+    out.n = vzero<DIM>();
+    float u = rand[0];
+    float traversalPdf = 1.0f;
+    uint32_t nodeIdx = 0;
+
+    while (true) {
+        NodeRegs n;
+        loadNode(bvh.nodes, nodeIdx, n);
+        NodeFrame<DIM> f = nodeFrame<DIM>(n);
+        float weight[8], d2far[8];
+        float total = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            float lo[DIM], hi[DIM], d2min, d2max;
+            childBox<DIM>(n, f, c, lo, hi);
+            boxDistance2<DIM>(lo, hi, x, d2min, d2max);
+            float w = 0.0f;
+            if (childMeta(n, c) != 0u && d2min <= r2) {
+                float c2 = 0.0f;
+#pragma unroll
+                for (int k = 0; k < DIM; k++) { float dc = x[k] - 0.5f*(lo[k] + hi[k]); c2 = fmaf(dc, dc, c2); }
+                w = branchWeight(c2);
+            }
+            weight[c] = w;
+            d2far[c] = d2max;
+            total += w;
+        }
+        if (!(total > 0.0f)) return false;
+
+        // select a child: u is rescaled to [0,1) after each decision, as in bvh.inl:1237-1247
+        int chosen = -1;
+        float d2NodeMax = 0.0f, prob = 0.0f;
+        float remaining = total;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            if (chosen < 0 && weight[c] > 0.0f) {
+                float p = weight[c]/remaining;
+                if (u < p || weight[c] >= remaining) {
+                    chosen = c;
+                    u = fminf(u/p, 0.99999994f);
+                    prob = weight[c]/total;
+                    d2NodeMax = d2far[c];
+                } else {
+                    u = (u - p)/(1.0f - p);
+                    remaining -= weight[c];
+                }
+            }
+        }
+        if (chosen < 0) return false;
+        traversalPdf *= prob;
+        uint32_t meta = childMeta(n, chosen);
+        uint32_t count = meta >> 5;
+        if (count == 0u) {
+            nodeIdx = n.q[1].x + (meta & 31u) - 1u;
+            continue;
+        }
+
+        // leaf: reservoir-select a primitive by area among those touching the sphere (bvh.inl:1163-1216)
+        uint32_t first = n.q[1].y + (meta & 31u);
+        float totalArea = 0.0f, selectedArea = 0.0f;
+        int selected = -1;
+        for (uint32_t i = 0; i < count; i++) {
+            Prim<DIM> prim;
+            prim.load(bvh, first + i);
+            bool inside = d2NodeMax <= r2;
+            if (!inside) {
+                Vec<DIM> pt;
+                float a, b;
+                float d = prim.closest(x, pt, a, b);
+                inside = d*d <= r2;
+            }
+            if (inside) {
+                float area = prim.area();
+                totalArea += area;
+                float selectionProb = area/totalArea;
+                if (u < selectionProb) {
+                    u = u/selectionProb;
+                    selected = (int)(first + i);
+                    selectedArea = area;
+                } else {
+                    u = (u - selectionProb)/(1.0f - selectionProb);
+                }
+            }
+        }
+        if (selected < 0) return false;
+        Prim<DIM> prim;
+        prim.load(bvh, (uint32_t)selected);
+        float pointPdf = prim.sample(rand, out.p, out.n);
+        out.prim = selected;
+        out.pdf = selectedArea*traversalPdf/totalArea*pointPdf;
+        return true;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// star radius (visibility silhouettes + Robin reflectance bound)
+// ------------------------------------------------------------------------------------------
+
+// silhouette_edges.inl:83-111 / silhouette_vertices.inl:59-85: is the edge (3D) or vertex (2D) shared by
+// faces with unit normals n0, n1 a visibility silhouette as seen along viewDir (|viewDir| = d)?
+ZB_DEV bool isSilhouetteEdge3(const Vec<3>& pa, const Vec<3>& pb, const Vec<3>& n0, const Vec<3>& n1,
+                              const Vec<3>& viewDir, float d, bool flip, float precision, float convention)
+{
+    float sign = flip ? 1.0f : -1.0f;
+    if (d <= precision) {
+        Vec<3> e = pb - pa;
+        e = e/norm(e);
+        float angle = atan2f(dot(e, cross(n0, n1)), dot(n0, n1));
+        return sign*angle > precision;
+    }
+    Vec<3> vd = viewDir/d;
+    float dot0 = convention*dot(vd, n0), dot1 = convention*dot(vd, n1);
+    if (fabsf(dot0) <= precision) return sign*dot1 > precision;
+    if (fabsf(dot1) <= precision) return sign*dot0 > precision;
+    return dot0*dot1 < 0.0f;
+}
+
+ZB_DEV bool isSilhouetteVertex2(const Vec<2>& n0, const Vec<2>& n1, const Vec<2>& viewDir, float d,
+                                bool flip, float precision, float convention)
+{
+    float sign = flip ? 1.0f : -1.0f;
+    if (d <= precision) return sign*cross2(n0, n1) > precision;
+    Vec<2> vd = viewDir/d;
+    float dot0 = convention*dot(vd, n0), dot1 = convention*dot(vd, n1);
+    if (fabsf(dot0) <= precision) return sign*dot1 > precision;
+    if (fabsf(dot1) <= precision) return sign*dot0 > precision;
+    return dot0*dot1 < 0.0f;
+}
+
+// distance from x to silhouette candidate j of the primitive (edge j -> j+1 of a triangle, vertex j
+// of a segment) and whether it is a silhouette given the adjacent normal nj
+ZB_DEV bool candidateSilhouette(const Prim<3>& t, int j, const Vec<3>& x, const Vec<3>& nj, const Vec<3>& n0,
+                                bool hasAdjacent, bool flip, float precision, float convention, float& sd)
+{
+    Vec<3> pj = j == 0 ? t.a : (j == 1 ? t.b : t.c);
+    Vec<3> pk = j == 0 ? t.b : (j == 1 ? t.c : t.a);
+    Vec<3> pt;
+    float tt;
+    sd = closestPointSegment<3>(pj, pk, x, pt, tt);
+    if (!hasAdjacent) return true;
+    return isSilhouetteEdge3(pj, pk, nj, n0, x - pt, sd, flip, precision, convention);
+}
+
+ZB_DEV bool candidateSilhouette(const Prim<2>& s, int j, const Vec<2>& x, const Vec<2>& nj, const Vec<2>& n0,
+                                bool hasAdjacent, bool flip, float precision, float convention, float& sd)
+{
+    Vec<2> vd = x - (j == 0 ? s.a : s.b);
+    sd = norm(vd);
+    if (!hasAdjacent) return true;
+    return j == 0 ? isSilhouetteVertex2(n0, nj, vd, sd, flip, precision, convention)
+                  : isSilhouetteVertex2(nj, n0, vd, sd, flip, precision, convention);
+}
+
+// farthest vertex (zombie/core/geometry_helpers.h:51-63, 163-180)
+ZB_DEV float farthestVertex(const Prim<3>& t, const Vec<3>& x, Vec<3>& far)
+{
+    float da = norm2(x - t.a), db = norm2(x - t.b), dc = norm2(x - t.c);
+    if (da >= db && da >= dc) { far = t.a; return sqrtf(da); }
+    if (db >= da && db >= dc) { far = t.b; return sqrtf(db); }
+    far = t.c;
+    return sqrtf(dc);
+}
+
+ZB_DEV float farthestVertex(const Prim<2>& s, const Vec<2>& x, Vec<2>& far)
+{
+    float da = norm2(x - s.a), db = norm2(x - s.b);
+    if (da > db) { far = s.a; return sqrtf(da); }
+    far = s.b;
+    return sqrtf(db);
+}
+
+ZB_DEV float clampLikeStd(float v, float lo, float hi) { return v < lo ? lo : (hi < v ? hi : v); }
+
+// radius inside which the reflectance of a primitive with Robin coefficient mu stays bounded,
+// given the distance h to its supporting plane/line and the cosine range it subtends
+// (RobinTriangleBound / RobinLineSegmentBound, robin_bounds.h:13-74). Returns kMaxFloat for "no bound".
+template <int DIM>
+ZB_DEV float robinRadiusBound(float h, float mu, float cosLower, float cosUpper)
+{
+    if (DIM == 3) {
+        float maxCos = sqrtf(h*mu);
+        if (!(maxCos >= cosLower)) return kMaxFloat;
+        float c = clampLikeStd(maxCos/1.7320508075688772935f, cosLower, cosUpper);
+        return h*h*mu/(c*(h*mu - c*c));
+    }
+    float c = clampLikeStd(sqrtf(h*mu)/1.4142135623730950488f, cosLower, cosUpper);
+    return (h/c)*expf(c*c/(h*mu));
+}
+
+// Shrinks r2 by what one reflecting primitive allows: the distance to each of its silhouette
+// edges/vertices, and for a non-zero Robin coefficient the radius inside which the reflectance
+// stays bounded (reflectance_boundary_bvh/geometry.h:85-236).
+template <int DIM>
+ZB_DEV void primStarRadius2(const BvhView& bvh, uint32_t primIdx, const Vec<DIM>& x, float& r2, bool flip,
+                            float precision, bool silhouetteTests)
+{
+    Prim<DIM> prim;
+    prim.load(bvh, primIdx);
+    Vec<DIM> closestPt;
+    float bu, bv;
+    float closestDist = prim.closest(x, closestPt, bu, bv);
+    float closestDist2 = closestDist*closestDist;
+    if (closestDist2 > r2) return;
+
+    // PrimAdjacency: n[3][3], minCoeff, maxCoeff, flags
+    float4 a0 = __ldg(bvh.adjacency + (size_t)3*primIdx), a1 = __ldg(bvh.adjacency + (size_t)3*primIdx + 1),
+           a2 = __ldg(bvh.adjacency + (size_t)3*primIdx + 2);
+    float maxCoeff = a2.z;
+    uint32_t flags = __float_as_uint(a2.w);
+    if (!(maxCoeff < kMaxFloat - kEpsilon)) { // perfectly absorbing
+        r2 = fminf(r2, closestDist2);
+        return;
+    }
+
+    Vec<DIM> n0 = unitNormal<DIM>(prim);
+    if (silhouetteTests) {
+        const float adjN[3][3] = {{a0.x, a0.y, a0.z}, {a0.w, a1.x, a1.y}, {a1.z, a1.w, a2.x}};
+        float convention = (float)bvh.snchSign;
+#pragma unroll
+        for (int j = 0; j < DIM; j++) {
+            if ((flags >> (4 + j)) & 1u) continue; // ignoreAdjacentFace
+            Vec<DIM> nj;
+#pragma unroll
+            for (int k = 0; k < DIM; k++) nj[k] = adjN[j][k];
+            float sd;
+            if (candidateSilhouette(prim, j, x, nj, n0, (flags >> j) & 1u, flip, precision, convention, sd)) {
+                r2 = fminf(r2, sd*sd);
+            }
+        }
+    }
+
+    if (maxCoeff > kEpsilon) { // reflectance case
+        if (closestDist < kEpsilon) {
+            r2 = closestDist; // sic (geometry.h:216)
+        } else if (r2 > closestDist2) {
+            Vec<DIM> far;
+            float farDist = farthestVertex(prim, x, far);
+            float h = fabsf(dot(n0, prim.a - x)/dot(n0, n0)); // findClosestPointPlane (geometry.h:62-70)
+            if (h > 0.0f) {
+                float cosUpper = fabsf(dot((x - closestPt)/closestDist, n0));
+                float cosLower = fabsf(dot((x - far)/farDist, n0));
+                float radius = robinRadiusBound<DIM>(h, maxCoeff, cosLower, cosUpper);
+                if (radius < kMaxFloat) r2 = fminf(r2, radius*radius);
+            } else {
+                r2 = fminf(r2, closestDist2);
+            }
+        }
+    }
+}
+
+// BoundingCone::overlap (fcpw/core/bounding_volumes.h:275-321): can a normal inside the cone be
+// orthogonal to a direction from x to the box? Also returns the range of angles between the two.
+template <int DIM>
+ZB_DEV bool coneOverlap(const float axis[3], float halfAngle, float radius, const Vec<DIM>& x,
+                        const float lo[DIM], const float hi[DIM], float distToBox, float& minAngle, float& maxAngle)
+{
+    minAngle = 0.0f;
+    maxAngle = kHalfPiF;
+    if (halfAngle >= kHalfPiF || distToBox < kEpsilon) return true;
+
+    Vec<DIM> c, view, ext;
+#pragma unroll
+    for (int k = 0; k < DIM; k++) { c[k] = 0.5f*(lo[k] + hi[k]); view[k] = c[k] - x[k]; ext[k] = hi[k] - c[k]; }
+    float l = norm(view);
+    view = view/l;
+    float ad = 0.0f;
+#pragma unroll
+    for (int k = 0; k < DIM; k++) ad = fmaf(axis[k], view[k], ad);
+    float dAxisAngle = acosf(fmaxf(-1.0f, fminf(1.0f, ad)));
+    if (kHalfPiF >= dAxisAngle - halfAngle && kHalfPiF <= dAxisAngle + halfAngle) return true;
+
+    float viewHalfAngle;
+    if (l > radius) {
+        viewHalfAngle = asinf(radius/l);
+    } else {
+        float d = 0.0f;
+#pragma unroll
+        for (int k = 0; k < DIM; k++) d = fmaf(ext[k], fabsf(view[k]), d);
+        float s = l - d;
+        if (s <= 0.0f) return true;
+        float proj;
+        if (DIM == 2) {
+            proj = fabsf(ext[0]*fabsf(view[1]) + ext[1]*fabsf(view[0]));
+        } else {
+            // maximal projection of the box half-extent onto the plane orthogonal to `view`
+            float sgn = copysignf(1.0f, view[DIM - 1]);
+            float a = -1.0f/(sgn + view[DIM - 1]);
+            float b = view[0]*view[1]*a;
+            float b1x = 1.0f + sgn*view[0]*view[0]*a, b1y = sgn*b, b1z = -sgn*view[0];
+            float b2x = b, b2y = sgn + view[1]*view[1]*a, b2z = -view[1];
+            float r1 = ext[0]*fabsf(b1x) + ext[1]*fabsf(b1y) + ext[DIM - 1]*fabsf(b1z);
+            float r2 = ext[0]*fabsf(b2x) + ext[1]*fabsf(b2y) + ext[DIM - 1]*fabsf(b2z);
+            proj = sqrtf(r1*r1 + r2*r2);
+        }
+        viewHalfAngle = atan2f(proj, s);
+    }
+    float sum = halfAngle + viewHalfAngle + 1e-5f;
+    minAngle = dAxisAngle - sum;
+    maxAngle = dAxisAngle + sum;
+    return sum >= kHalfPiF ? true : (kHalfPiF >= minAngle && kHalfPiF <= maxAngle);
+}
+
+// GeometricQueries::computeStarRadiusForReflectingBoundary for both the Neumann and the Robin
+// handler (fcpw_geometric_queries.h:1250-1291): returns the squared radius, <= r2Max.
+template <int DIM>
+ZB_DEV float starRadius2(const BvhView& bvh, const Vec<DIM>& x, float r2, bool flip, float precision, int *status)
+{
+    uint2 stack[kStackSize];
+    int sp = 0;
+    stack[sp++] = make_uint2(0u, 0u);
+
+    while (sp > 0) {
+        uint2 e = stack[--sp];
+        // bit 2 of the key marks "no silhouette inside this subtree" (reflectance bvh.h:474-476 sign trick)
+        bool silhouetteTests = !(e.x & 4u);
+        if (__uint_as_float(e.x & ~7u) > r2) continue;
+        if (e.y & kLeafFlag) {
+            uint32_t first = e.y & 0x0fffffffu, count = (e.y >> 28) & 7u;
+            for (uint32_t i = 0; i < count; i++) primStarRadius2<DIM>(bvh, first + i, x, r2, flip, precision, silhouetteTests);
+            continue;
+        }
+
+        NodeRegs n;
+        loadNode(bvh.nodes, e.y, n);
+        NodeFrame<DIM> f = nodeFrame<DIM>(n);
+        uint32_t keys[8];
+        uint32_t noSil = 0u;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            keys[c] = 0xffffffffu;
+            uint32_t meta = childMeta(n, c);
+            if (meta == 0u) continue;
+            float lo[DIM], hi[DIM], d2min, d2max;
+            childBox<DIM>(n, f, c, lo, hi);
+            boxDistance2<DIM>(lo, hi, x, d2min, d2max);
+            if (d2min > r2) continue;
+            float4 c0 = __ldg(bvh.cones + ((size_t)e.y*8 + c)*2), c1 = __ldg(bvh.cones + ((size_t)e.y*8 + c)*2 + 1);
+            float minCoeff = c1.y, maxCoeff = c1.z;
+            float lower = d2min, upper = d2max;
+            bool hasSil = true;
+            if (minCoeff < kMaxFloat - kEpsilon) {
+                float axis[3] = {c0.x, c0.y, c0.z};
+                float minAngle, maxAngle;
+                if (coneOverlap<DIM>(axis, c0.w, c1.x, x, lo, hi, d2min, minAngle, maxAngle)) {
+                    upper = kMaxFloat;
+                } else {
+                    hasSil = false;
+                    if (maxCoeff > kEpsilon) {
+                        // RobinBvhNodeBound (robin_bounds.h:102-154): radius range over the whole subtree
+                        float rMin = sqrtf(d2min), rMax = sqrtf(d2max);
+                        float minCos = fminf(fabsf(cosf(minAngle)), fabsf(cosf(maxAngle)));
+                        if (DIM == 3) {
+                            if (rMax < minCos/maxCoeff) lower = kMaxFloat;
+                            else { float rb = rMin/(1.0f - minCos/(maxCoeff*rMax)); lower = rb*rb; }
+                            if (rMin < 1.0f/minCoeff) upper = kMaxFloat;
+                            else { float rb = rMax/(1.0f - 1.0f/(minCoeff*rMin)); upper = rb*rb; }
+                        } else {
+                            float rb = rMin*expf(minCos/(maxCoeff*rMax));
+                            lower = rb*rb;
+                            rb = rMax*expf(1.0f/(minCoeff*rMin));
+                            upper = rb*rb;
+                        }
+                        // keep the pruning bound conservative under float rounding
+                        lower *= 0.9999f;
+                        upper *= 1.0001f;
+                    } else {
+                        continue; // perfectly reflecting and no silhouette: nothing inside can shrink the radius
+                    }
+                }
+            }
+            r2 = fminf(r2, upper);
+            if (!hasSil) noSil |= 1u << c;
+            keys[c] = (__float_as_uint(lower) & ~7u) | (uint32_t)c;
+        }
+        sort8(keys);
+#pragma unroll
+        for (int c = 7; c >= 0; c--) {
+            uint32_t key = keys[c];
+            if (key != 0xffffffffu && keyValue(key) <= r2) {
+                uint32_t slot = key & 7u;
+                uint32_t tagged = (key & ~7u) | (((noSil >> slot) & 1u) ? 4u : 0u);
+                if (sp < kStackSize) stack[sp++] = make_uint2(tagged, childRef(n, childMeta(n, slot)));
+                else if (status) atomicOr(status, kStatusStackOverflow);
+            }
+        }
+    }
+    return r2;
+}
+
+} // namespace zb

@@ -1,0 +1,49 @@
+// Minimal fixed-size float vectors for device and host code (the reference uses Eigen::Matrix<float,DIM,1>).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#define ZB_DEV __device__ __forceinline__
+#define ZB_HOSTDEV __host__ __device__ __forceinline__
+
+namespace zb {
+
+constexpr float kMaxFloat = 3.402823466e+38f;
+constexpr float kEpsilon = 1.192092896e-07f; // fcpw::epsilon = numeric_limits<float>::epsilon()
+constexpr float kPiF = 3.14159265358979323846f;
+constexpr float kHalfPiF = 1.57079632679489661923f;
+
+template <int D>
+struct Vec {
+    float v[D];
+    ZB_HOSTDEV float& operator[](int i) { return v[i]; }
+    ZB_HOSTDEV const float& operator[](int i) const { return v[i]; }
+};
+
+template <int D> ZB_HOSTDEV Vec<D> vzero() { Vec<D> r; for (int i = 0; i < D; i++) r.v[i] = 0.0f; return r; }
+template <int D> ZB_HOSTDEV Vec<D> operator+(const Vec<D>& a, const Vec<D>& b) { Vec<D> r; for (int i = 0; i < D; i++) r.v[i] = a.v[i] + b.v[i]; return r; }
+template <int D> ZB_HOSTDEV Vec<D> operator-(const Vec<D>& a, const Vec<D>& b) { Vec<D> r; for (int i = 0; i < D; i++) r.v[i] = a.v[i] - b.v[i]; return r; }
+template <int D> ZB_HOSTDEV Vec<D> operator-(const Vec<D>& a) { Vec<D> r; for (int i = 0; i < D; i++) r.v[i] = -a.v[i]; return r; }
+template <int D> ZB_HOSTDEV Vec<D> operator*(const Vec<D>& a, float s) { Vec<D> r; for (int i = 0; i < D; i++) r.v[i] = a.v[i]*s; return r; }
+template <int D> ZB_HOSTDEV Vec<D> operator*(float s, const Vec<D>& a) { return a*s; }
+template <int D> ZB_HOSTDEV Vec<D> operator/(const Vec<D>& a, float s) { Vec<D> r; for (int i = 0; i < D; i++) r.v[i] = a.v[i]/s; return r; }
+template <int D> ZB_HOSTDEV float dot(const Vec<D>& a, const Vec<D>& b) { float s = a.v[0]*b.v[0]; for (int i = 1; i < D; i++) s += a.v[i]*b.v[i]; return s; }
+template <int D> ZB_HOSTDEV float norm2(const Vec<D>& a) { return dot(a, a); }
+template <int D> ZB_HOSTDEV float norm(const Vec<D>& a) { return sqrtf(dot(a, a)); }
+ZB_HOSTDEV Vec<3> cross(const Vec<3>& a, const Vec<3>& b) {
+    Vec<3> r;
+    r.v[0] = a.v[1]*b.v[2] - a.v[2]*b.v[1];
+    r.v[1] = a.v[2]*b.v[0] - a.v[0]*b.v[2];
+    r.v[2] = a.v[0]*b.v[1] - a.v[1]*b.v[0];
+    return r;
+}
+ZB_HOSTDEV float cross2(const Vec<2>& a, const Vec<2>& b) { return a.v[0]*b.v[1] - a.v[1]*b.v[0]; }
+ZB_HOSTDEV Vec<3> make3(float x, float y, float z) { Vec<3> r; r.v[0] = x; r.v[1] = y; r.v[2] = z; return r; }
+ZB_HOSTDEV Vec<2> make2(float x, float y) { Vec<2> r; r.v[0] = x; r.v[1] = y; return r; }
+
+template <int D> ZB_HOSTDEV Vec<D> loadVec(const float *p) { Vec<D> r; for (int i = 0; i < D; i++) r.v[i] = p[i]; return r; }
+template <int D> ZB_HOSTDEV void storeVec(float *p, const Vec<D>& a) { for (int i = 0; i < D; i++) p[i] = a.v[i]; }
+
+} // namespace zb

@@ -1,0 +1,825 @@
+// Walk-on-spheres / walk-on-stars estimator kernels.
+//
+// Reference: WalkOnSpheres::solve / WalkOnStars::solve run a TBB parallel_for over sample points
+// and, per point, nWalks sequential walks that share the point's pcg32 and update its Welford
+// statistics in place (walk_on_spheres.h:132-168,229-414; walk_on_stars.h:151-187,346-848).
+//
+// Here the unit of scheduling is one *walk* (a "task"), not one point:
+//   1. countTasks      one thread per point: how many walks it launches, how many stratified numbers
+//   2. preparePoints   one thread per point: first-sphere radius (a star-radius query) and the
+//                      Latin-hypercube samples of the gradient estimator, drawn from the point's rng
+//   3. walkKernel      persistent threads; every lane runs one walk at a time and, when it ends,
+//                      pulls the next task from a warp-local chunk that a leader lane refills
+//                      with one global atomic (warp-level compaction of finished walks); a walk
+//                      ends by writing one fixed-size record
+//   4. reducePoints    one thread per point folds its walks' records, in walk order, into the
+//                      (n, mean, M2) statistics with the reference's Welford update and running
+//                      control variates — atomic-free and deterministic for a fixed seed
+#pragma once
+
+#include "greens.cuh"
+#include "pde.cuh"
+#include "queries.cuh"
+
+namespace zb {
+
+enum : int { kStatusSplitOverflow = 2 };
+constexpr int kSplitStack = 6;
+constexpr int kTaskChunk = 64; // tasks a warp reserves per global atomic
+
+struct SolveArgs {
+    BvhView absorbing, reflecting;
+    int hasAbsorbing, hasReflecting, reflectingKind, estimator;
+    float domainMin[3], domainMax[3];
+    zb_walk_settings ws;
+    zb_pde_desc pde;
+    zb_sample_points pts; // device pointers
+    zb_statistics stats;  // device pointers
+    // per-point scratch
+    int *taskCount;
+    long long *taskOffset;  // exclusive scan of taskCount, n + 1 entries
+    int *stratCount;
+    long long *stratOffset; // exclusive scan of stratCount, n + 1 entries
+    float *strat;
+    unsigned long long *pointState; // the point's rng state after drawing its stratified samples
+    // per-task records
+    float *recSolution, *recFirstSource, *recGradBoundary, *recGradSource;
+    int *recLength, *recFlags;
+    unsigned long long *taskCounter;
+    int *status;
+    long long *walkSteps;
+    long long totalTasks;
+    int anyGradient;
+};
+
+template <int DIM>
+struct WalkState {
+    Vec<DIM> pt, normal, prevDir;
+    float prevDist, throughput, reflContrib, srcContrib;
+    int walkLength;
+    bool onRefl;
+};
+
+// SphereSampler<DIM>::sampleUnitSphereUniform (zombie/core/sampling.h:104-107, 164-170)
+ZB_DEV Vec<3> uniformDirection(const float *u, Vec<3> *)
+{
+    float z = 1.0f - 2.0f*u[0];
+    float r = sqrtf(fmaxf(0.0f, 1.0f - z*z));
+    float phi = 2.0f*kPiF*u[1];
+    float s, c;
+    sincosf(phi, &s, &c);
+    return make3(r*c, r*s, z);
+}
+ZB_DEV Vec<2> uniformDirection(const float *u, Vec<2> *)
+{
+    float phi = 2.0f*kPiF*u[0];
+    float s, c;
+    sincosf(phi, &s, &c);
+    return make2(c, s);
+}
+template <int DIM>
+ZB_DEV Vec<DIM> uniformDirection(Pcg32& rng)
+{
+    float u[2];
+    for (int k = 0; k < DIM - 1; k++) u[k] = rng.nextFloat();
+    return uniformDirection(u, (Vec<DIM> *)nullptr);
+}
+
+// cosine-weighted hemisphere about +e_{DIM-1} (sampling.h:119-127, 184-214)
+ZB_DEV Vec<3> cosineHemisphere(const float *u, Vec<3> *)
+{
+    float u1 = 2.0f*u[0] - 1.0f, u2 = 2.0f*u[1] - 1.0f;
+    float dx = 0.0f, dy = 0.0f;
+    if (!(u1 == 0.0f && u2 == 0.0f)) {
+        float theta, r;
+        if (fabsf(u1) > fabsf(u2)) { r = u1; theta = 0.25f*kPiF*(u2/u1); }
+        else { r = u2; theta = 0.5f*kPiF*(1.0f - 0.5f*(u1/u2)); }
+        dx = r*cosf(theta); dy = r*sinf(theta);
+    }
+    float z = sqrtf(fmaxf(0.0f, 1.0f - (dx*dx + dy*dy)));
+    return make3(dx, dy, z);
+}
+ZB_DEV Vec<2> cosineHemisphere(const float *u, Vec<2> *)
+{
+    float u1 = 2.0f*u[0] - 1.0f;
+    return make2(u1, sqrtf(fmaxf(0.0f, 1.0f - u1*u1)));
+}
+// SphereSampler::transformCoordinates (sampling.h:149-156, 236-247)
+ZB_DEV void alignWith(const Vec<3>& n, Vec<3>& d)
+{
+    float sign = copysignf(1.0f, n[2]);
+    float a = -1.0f/(sign + n[2]);
+    float b = n[0]*n[1]*a;
+    Vec<3> b1 = make3(1.0f + sign*n[0]*n[0]*a, sign*b, -sign*n[0]);
+    Vec<3> b2 = make3(b, sign + n[1]*n[1]*a, -n[1]);
+    d = b1*d[0] + b2*d[1] + n*d[2];
+}
+ZB_DEV void alignWith(const Vec<2>& n, Vec<2>& d)
+{
+    Vec<2> s = make2(n[1], -n[0]);
+    d = s*d[0] + n*d[1];
+}
+
+// offsetPointAlongDirectionImpl (zombie/core/geometric_queries.h:176-207): integer-ULP ray-origin offset
+template <int DIM>
+ZB_DEV Vec<DIM> offsetPoint(const Vec<DIM>& p, const Vec<DIM>& n)
+{
+    Vec<DIM> r;
+#pragma unroll
+    for (int k = 0; k < DIM; k++) {
+        int nOff = (int)(n[k]*256.0f);
+        float pOff = __int_as_float(__float_as_int(p[k]) + (p[k] < 0.0f ? -nOff : nOff));
+        r[k] = fabsf(p[k]) < (1.0f/32.0f) ? p[k] + (1.0f/65536.0f)*n[k] : pOff;
+    }
+    return r;
+}
+
+template <int DIM>
+ZB_DEV bool outsideDomain(const SolveArgs& a, const Vec<DIM>& x)
+{
+    bool out = false;
+#pragma unroll
+    for (int k = 0; k < DIM; k++) out = out || x[k] < a.domainMin[k] || x[k] > a.domainMax[k];
+    return out;
+}
+
+// GeometricQueries::computeDistToAbsorbingBoundary (+ the closest point, reused at termination)
+template <int DIM>
+ZB_DEV float distToAbsorbing(const SolveArgs& a, const Vec<DIM>& x, Vec<DIM>& proj, int& projPrim)
+{
+    if (!a.hasAbsorbing) {
+        // default of GeometricQueries::populate (geometric_queries.h:213-218)
+        float s = 0.0f;
+#pragma unroll
+        for (int k = 0; k < DIM; k++) { float m = fminf(a.domainMin[k] - x[k], x[k] - a.domainMax[k]); s += m*m; }
+        proj = x;
+        projPrim = -1;
+        return sqrtf(s);
+    }
+    ClosestHit<DIM> hit;
+    closestPoint<DIM>(a.absorbing, x, kMaxFloat, hit, a.status);
+    proj = hit.p;
+    projPrim = hit.prim;
+    return hit.d;
+}
+
+// GeometricQueries::computeStarRadiusForReflectingBoundary (fcpw_geometric_queries.h:1250-1291)
+template <int DIM>
+ZB_DEV float starRadiusQuery(const SolveArgs& a, const Vec<DIM>& x, float minRadius, float maxRadius, float precision, bool flip)
+{
+    if (!a.hasReflecting) return maxRadius;
+    if (minRadius > maxRadius) return maxRadius;
+    bool flipNormals = !flip; // "FCPW's internal convention requires normals to be flipped"
+    float r2max = maxRadius < kMaxFloat ? maxRadius*maxRadius : kMaxFloat;
+    float r2 = starRadius2<DIM>(a.reflecting, x, r2max, flipNormals, precision, a.status);
+    if (a.reflectingKind == ZB_REFLECTING_NEUMANN && !(r2 < r2max)) return fmaxf(maxRadius, minRadius);
+    return fmaxf(sqrtf(r2), minRadius);
+}
+
+// star radius as the walk uses it (walk_on_stars.h:382-398, 577-596): query + 1% shrink
+template <int DIM>
+ZB_DEV float shrunkStarRadius(const SolveArgs& a, const Vec<DIM>& x, float distA, bool flip)
+{
+    float r = starRadiusQuery<DIM>(a, x, a.ws.epsilonShellForReflectingBoundary, distA, a.ws.silhouettePrecision, flip);
+    if (a.hasReflecting && a.ws.epsilonShellForReflectingBoundary <= distA) {
+        r = fmaxf(0.99f*r, a.ws.epsilonShellForReflectingBoundary);
+    }
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// 1. task counts
+// ------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void countTasksKernel(SolveArgs a)
+{
+    int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= a.pts.n) return;
+    int quantity = a.pts.estimationQuantity[i];
+    int type = a.pts.type[i];
+    int nWalks = a.pts.nWalks[i];
+    int tasks = 0, strat = 0;
+    if (quantity == ZB_SOLUTION_AND_GRADIENT) {
+        int nAnti = 1;
+        if (a.ws.useGradientAntitheticVariates) { nWalks = max(1, nWalks/2); nAnti = 2; }
+        nWalks = max(0, nWalks);
+        tasks = nWalks*nAnti;
+        strat = 2*nWalks*(DIM - 1);
+    } else if (quantity == ZB_SOLUTION) {
+        if (type == ZB_ON_ABSORBING_BOUNDARY) tasks = 0;
+        else if (a.pts.distToAbsorbingBoundary[i] <= a.ws.epsilonShellForAbsorbingBoundary) tasks = 1;
+        else tasks = max(0, nWalks);
+    }
+    a.taskCount[i] = tasks;
+    a.stratCount[i] = strat;
+}
+
+// ------------------------------------------------------------------------------------------
+// 2. per-point preparation
+// ------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void preparePointsKernel(SolveArgs a)
+{
+    int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= a.pts.n) return;
+    int quantity = a.pts.estimationQuantity[i];
+    Pcg32 rng;
+    rng.state = a.pts.rngState[i];
+    rng.inc = a.pts.rngInc[i];
+    float distA = a.pts.distToAbsorbingBoundary[i];
+    bool wost = a.estimator == ZB_WALK_ON_STARS;
+
+    if (quantity == ZB_SOLUTION_AND_GRADIENT) {
+        float boundaryDist = wost ? fminf(distA, a.pts.distToReflectingBoundary[i]) : distA;
+        a.pts.firstSphereRadius[i] = 0.99f*boundaryDist;
+        // generateStratifiedSamples<DIM-1>(2*nWalks) (sampling.h:436-458): jittered diagonal, then one
+        // Fisher-Yates shuffle per dimension
+        int nSamples = a.stratCount[i]/(DIM - 1);
+        float *s = a.strat + a.stratOffset[i];
+        if (nSamples > 0) {
+            const float oneMinusEps = 1.0f - kEpsilon;
+            float inv = 1.0f/nSamples;
+            for (int k = 0; k < nSamples; k++) {
+                for (int j = 0; j < DIM - 1; j++) {
+                    float sj = (k + rng.nextFloat())*inv;
+                    s[(DIM - 1)*k + j] = fminf(sj, oneMinusEps);
+                }
+            }
+            for (int j = 0; j < DIM - 1; j++) {
+                for (int k = 0; k < nSamples; k++) {
+                    int other = k + (int)rng.nextUInt((uint32_t)(nSamples - k));
+                    float t = s[(DIM - 1)*k + j];
+                    s[(DIM - 1)*k + j] = s[(DIM - 1)*other + j];
+                    s[(DIM - 1)*other + j] = t;
+                }
+            }
+        }
+    } else if (quantity == ZB_SOLUTION && a.pts.type[i] != ZB_ON_ABSORBING_BOUNDARY) {
+        bool hasPrev = a.stats.nSolutionEstimates[i] > 0;
+        if (!hasPrev) {
+            float radius;
+            if (!wost) {
+                radius = distA;
+            } else if (distA <= a.ws.epsilonShellForAbsorbingBoundary || a.ws.stepsBeforeUsingMaximalSpheres == 0) {
+                radius = distA;
+            } else {
+                PdeEval<DIM> pde{a.pde};
+                if (a.pts.type[i] == ZB_ON_REFLECTING_BOUNDARY && pde.hasNonZeroRobinCoeff()) {
+                    radius = a.ws.epsilonShellForReflectingBoundary;
+                } else {
+                    bool flip = a.ws.solveDoubleSided && a.pts.type[i] == ZB_ON_REFLECTING_BOUNDARY &&
+                                a.pts.estimateBoundaryNormalAligned && a.pts.estimateBoundaryNormalAligned[i];
+                    Vec<DIM> x = loadVec<DIM>(a.pts.pt + (size_t)DIM*i);
+                    radius = shrunkStarRadius<DIM>(a, x, distA, flip);
+                }
+            }
+            a.pts.firstSphereRadius[i] = radius;
+        }
+    }
+    a.pointState[i] = rng.state;
+}
+
+// ------------------------------------------------------------------------------------------
+// 3. the walks
+// ------------------------------------------------------------------------------------------
+
+// everything a lane keeps between steps
+template <int DIM>
+struct Lane {
+    WalkState<DIM> st;
+    GreensBall<DIM> g;
+    Pcg32 rng;
+    Vec<DIM> proj;         // closest absorbing-boundary point of st.pt (valid when distA is)
+    float distA;
+    float firstSphereRadius;
+    float total;           // contribution summed over this walk and its splits
+    float firstSource;
+    Vec<DIM> gradBoundary, gradSource;
+    long long task;
+    int totalLength;
+    int splits;
+    int nQueued;
+    bool firstStep, flip, outerFlip, success, active, gradient;
+};
+
+template <int DIM>
+ZB_DEV int findPoint(const long long *offsets, int n, long long task)
+{
+    int lo = 0, hi = n; // offsets[lo] <= task < offsets[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (offsets[mid] <= task) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+template <int DIM, bool WOST>
+ZB_DEV void beginTask(const SolveArgs& a, Lane<DIM>& L, long long task)
+{
+    PdeEval<DIM> pde{a.pde};
+    int i = findPoint<DIM>(a.taskOffset, a.pts.n, task);
+    int t = (int)(task - a.taskOffset[i]);
+    Vec<DIM> x = loadVec<DIM>(a.pts.pt + (size_t)DIM*i);
+    bool yukawa = a.pde.absorptionCoeff > 0.0f && a.ws.stepsBeforeApplyingTikhonov == 0;
+    L.task = task;
+    L.active = true;
+    L.total = 0.0f;
+    L.totalLength = 0;
+    L.splits = -1;
+    L.nQueued = 0;
+    L.success = false;
+    L.firstSource = 0.0f;
+    L.gradBoundary = vzero<DIM>();
+    L.gradSource = vzero<DIM>();
+    L.g.init(yukawa, a.pde.absorptionCoeff);
+    L.st.reflContrib = 0.0f;
+    L.st.srcContrib = 0.0f;
+    L.st.throughput = 1.0f;
+    L.st.walkLength = 0;
+    L.firstStep = true;
+    L.gradient = a.pts.estimationQuantity[i] == ZB_SOLUTION_AND_GRADIENT;
+    int projPrim;
+
+    if (!L.gradient) {
+        // estimateSolution (walk_on_spheres.h:354-372; walk_on_stars.h:553-608)
+        L.rng = walkGenerator(a.pointState[i], a.pts.rngInc[i], (uint32_t)t);
+        L.st.pt = x;
+        L.distA = a.pts.distToAbsorbingBoundary[i];
+        L.firstSphereRadius = a.pts.firstSphereRadius[i];
+        L.flip = false;
+        if (WOST) {
+            Vec<DIM> n = loadVec<DIM>(a.pts.normal + (size_t)DIM*i);
+            L.st.normal = n;
+            L.st.prevDir = n;
+            L.st.prevDist = kMaxFloat;
+            L.st.onRefl = a.pts.type[i] == ZB_ON_REFLECTING_BOUNDARY;
+            if (a.ws.solveDoubleSided && L.st.onRefl && a.pts.estimateBoundaryNormalAligned &&
+                a.pts.estimateBoundaryNormalAligned[i]) {
+                L.st.normal = -n;
+                L.st.prevDir = -n;
+                L.flip = true;
+            }
+        } else {
+            L.st.normal = vzero<DIM>();
+            L.st.prevDir = vzero<DIM>();
+            L.st.prevDist = 0.0f;
+            L.st.onRefl = false;
+        }
+        L.outerFlip = L.flip;
+        L.proj = x;
+        if (!(L.distA > a.ws.epsilonShellForAbsorbingBoundary)) {
+            // the walk loop will not run: the terminal projection needs the closest point now
+            distToAbsorbing<DIM>(a, x, L.proj, projPrim);
+        }
+        return;
+    }
+
+    // estimateSolutionAndGradient (walk_on_spheres.h:417-520; walk_on_stars.h:665-783): the first
+    // ball is sampled explicitly; antithetic twins share one generator and mirror the samples
+    int nAnti = a.ws.useGradientAntitheticVariates ? 2 : 1;
+    int w = t/nAnti, anti = t - w*nAnti;
+    L.rng = walkGenerator(a.pointState[i], a.pts.rngInc[i], (uint32_t)w);
+    const float *strat = a.strat + a.stratOffset[i];
+    float R1 = a.pts.firstSphereRadius[i];
+    L.g.updateBall(x, R1);
+    L.st.pt = x;
+    L.st.normal = vzero<DIM>();
+    L.st.prevDir = vzero<DIM>();
+    L.st.prevDist = 0.0f;
+    L.st.onRefl = false;
+    L.flip = false;
+    L.outerFlip = false;
+
+    if (!a.ws.ignoreSourceContribution) {
+        float gnorm = L.g.norm();
+        if (a.pde.isSourceConstant) {
+            L.firstSource = gnorm*pde.source(x);
+        } else {
+            Vec<DIM> dir = uniformDirection(strat + (DIM - 1)*(2*w + 0), (Vec<DIM> *)nullptr);
+            float sourceRadius, sourcePdf;
+            Vec<DIM> sourcePt = L.g.sampleVolume(dir, L.rng, sourceRadius, sourcePdf);
+            if (anti == 1) sourcePt = x - (sourcePt - x);
+            L.firstSource = gnorm*pde.source(sourcePt);
+            L.gradSource = L.g.gradient(sourceRadius, sourcePt)/(sourcePdf*gnorm);
+        }
+        L.st.srcContrib += L.st.throughput*L.firstSource;
+    }
+
+    const float *ub = strat + (DIM - 1)*(2*w + 1);
+    Vec<DIM> boundaryDir;
+    float boundaryPdf;
+    if (a.ws.useCosineSamplingForDerivatives) {
+        boundaryDir = cosineHemisphere(ub, (Vec<DIM> *)nullptr);
+        if (L.rng.nextFloat() < 0.5f) boundaryDir[DIM - 1] *= -1.0f;
+        float cosTheta = fabsf(boundaryDir[DIM - 1]);
+        boundaryPdf = 0.5f*(DIM == 3 ? cosTheta/kPiF : cosTheta/2.0f);
+        Vec<DIM> axis = a.pts.directionForDerivative ? loadVec<DIM>(a.pts.directionForDerivative + (size_t)DIM*i) : vzero<DIM>();
+        if (!a.pts.directionForDerivative) axis[0] = 1.0f;
+        alignWith(axis, boundaryDir);
+    } else {
+        boundaryDir = uniformDirection(ub, (Vec<DIM> *)nullptr);
+        boundaryPdf = sphereDirectionPdf<DIM>(1.0f);
+    }
+    Vec<DIM> boundaryPt = L.g.c + boundaryDir*L.g.R;
+    if (anti == 1) boundaryPt = x - (boundaryPt - x);
+    if (WOST) {
+        L.st.prevDist = L.g.R;
+        L.st.prevDir = (boundaryPt - x)/L.g.R;
+    }
+    L.st.pt = boundaryPt;
+    L.st.throughput *= L.g.poissonKernel()/boundaryPdf;
+    L.gradBoundary = L.g.poissonKernelGradient(boundaryPt)/(boundaryPdf*L.st.throughput);
+    L.firstSphereRadius = 0.0f;
+    L.distA = distToAbsorbing<DIM>(a, boundaryPt, L.proj, projPrim);
+}
+
+// outcome of one step
+enum StepResult { kContinue = 0, kReached, kRoulette, kMaxLength, kEscaped };
+
+// applyWeightWindow (walk_on_spheres.h:193-227; walk_on_stars.h:310-343)
+template <int DIM>
+ZB_DEV bool weightWindow(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *queue)
+{
+    WalkState<DIM>& st = L.st;
+    if (st.throughput > a.ws.splittingThreshold) {
+        float left = st.throughput - a.ws.splittingThreshold;
+        st.throughput = a.ws.splittingThreshold;
+        WalkState<DIM> split = st;
+        split.reflContrib = 0.0f;
+        split.srcContrib = 0.0f;
+        split.walkLength = 0;
+        int copies = 0;
+        while (left > a.ws.splittingThreshold) { left -= a.ws.splittingThreshold; copies++; }
+        if (L.rng.nextFloat() < left/a.ws.splittingThreshold) copies++;
+        for (int c = 0; c < copies; c++) {
+            if (L.nQueued < kSplitStack) queue[L.nQueued++] = split;
+            else atomicOr(a.status, kStatusSplitOverflow);
+        }
+    } else if (st.throughput < a.ws.russianRouletteThreshold) {
+        float survival = st.throughput/a.ws.russianRouletteThreshold;
+        if (survival < L.rng.nextFloat()) {
+            st.throughput = 0.0f;
+            return true;
+        }
+        st.throughput = a.ws.russianRouletteThreshold;
+    }
+    return false;
+}
+
+// one iteration of the while loop of WalkOnStars::walk (walk_on_stars.h:357-487) or
+// WalkOnSpheres::walk (walk_on_spheres.h:237-288)
+template <int DIM, bool WOST>
+ZB_DEV StepResult walkStep(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *queue)
+{
+    PdeEval<DIM> pde{a.pde};
+    WalkState<DIM>& st = L.st;
+    if (!(L.distA > a.ws.epsilonShellForAbsorbingBoundary)) return kReached;
+
+    if (!WOST) {
+        L.g.updateBall(st.pt, L.distA);
+        if (!a.ws.ignoreSourceContribution) {
+            float contribution;
+            if (a.pde.isSourceConstant) {
+                contribution = L.g.norm()*pde.source(st.pt);
+            } else {
+                Vec<DIM> sdir = uniformDirection<DIM>(L.rng);
+                float r, pdf;
+                Vec<DIM> sourcePt = L.g.sampleVolume(sdir, L.rng, r, pdf);
+                contribution = L.g.norm()*pde.source(sourcePt);
+            }
+            st.srcContrib += st.throughput*contribution;
+        }
+        Vec<DIM> dir = uniformDirection<DIM>(L.rng);
+        st.pt = st.pt + dir*L.distA;
+        st.throughput *= L.g.directionSampledPoissonKernel(st.pt);
+        if (outsideDomain<DIM>(a, st.pt)) return kEscaped;
+    } else {
+        // --- star radius (walk_on_stars.h:359-399)
+        float starRadius;
+        if (L.firstStep && L.firstSphereRadius > 0.0f) {
+            starRadius = L.firstSphereRadius;
+        } else {
+            L.flip = false;
+            if (a.ws.solveDoubleSided && st.onRefl) {
+                if (st.prevDist > 0.0f && dot(st.prevDir, st.normal) < 0.0f) {
+                    st.normal = -st.normal;
+                    L.flip = true;
+                }
+            }
+            if (a.ws.stepsBeforeUsingMaximalSpheres <= st.walkLength) {
+                starRadius = L.distA;
+            } else if (st.onRefl && pde.hasNonZeroRobinCoeff()) {
+                starRadius = a.ws.epsilonShellForReflectingBoundary;
+            } else {
+                starRadius = shrunkStarRadius<DIM>(a, st.pt, L.distA, L.flip);
+            }
+        }
+        L.g.updateBall(st.pt, starRadius);
+
+        // --- direction, hemispherical on the reflecting boundary (:410-416)
+        Vec<DIM> dir = uniformDirection<DIM>(L.rng);
+        if (st.onRefl && dot(st.normal, dir) > 0.0f) dir = -dir;
+
+        // --- first reflecting-boundary hit inside the star (:419-436)
+        Vec<DIM> nextPt, nextNormal = vzero<DIM>();
+        float nextDist;
+        bool hitRefl = false;
+        {
+            Vec<DIM> origin = st.onRefl ? offsetPoint<DIM>(st.pt, -st.normal) : st.pt;
+            if (a.hasReflecting) {
+                RayHit<DIM> hit;
+                if (intersectRay<DIM, false>(a.reflecting, origin, dir, starRadius, hit, a.status)) {
+                    Prim<DIM> prim;
+                    prim.load(a.reflecting, (uint32_t)hit.prim);
+                    hitRefl = true;
+                    nextPt = prim.pointAt(hit.bv, hit.bw);
+                    nextNormal = unitNormal<DIM>(prim);
+                    nextDist = hit.t;
+                }
+            }
+            if (!hitRefl) {
+                nextPt = origin + dir*starRadius;
+                nextDist = starRadius;
+            }
+        }
+
+        // --- Neumann / Robin data inside the star (:190-250)
+        if (a.hasReflecting && !a.ws.ignoreReflectingBoundaryContribution) {
+            Vec<DIM> rand;
+            for (int k = 0; k < DIM; k++) rand[k] = L.rng.nextFloat();
+            SphereSample<DIM> bs;
+            if (sampleSphere<DIM>(a.reflecting, st.pt, starRadius*starRadius, rand, bs)) {
+                Vec<DIM> toSample = bs.p - st.pt;
+                float distToSample = norm(toSample);
+                float alpha = st.onRefl ? 2.0f : 1.0f;
+                bool aligned = false;
+                if (a.ws.solveDoubleSided) {
+                    toSample = toSample/distToSample;
+                    if (L.flip) {
+                        aligned = true;
+                    } else if (dot(toSample, bs.n) < -a.ws.silhouettePrecision) {
+                        bool flipSample = true;
+                        if (alpha > 1.0f) flipSample = dot(toSample, st.normal) < -a.ws.silhouettePrecision;
+                        if (flipSample) aligned = true;
+                    }
+                }
+                Vec<DIM> sampleNormal = aligned ? -bs.n : bs.n;
+                if (bs.pdf > 0.0f && distToSample < starRadius) {
+                    // intersectsWithReflectingBoundary (fcpw_geometric_queries.h:1218-1226)
+                    Vec<DIM> p1 = st.onRefl ? offsetPoint<DIM>(st.pt, -st.normal) : st.pt;
+                    Vec<DIM> p2 = offsetPoint<DIM>(bs.p, -sampleNormal);
+                    Vec<DIM> d12 = p2 - p1;
+                    float len = norm(d12);
+                    RayHit<DIM> occ;
+                    bool blocked = intersectRay<DIM, true>(a.reflecting, p1, d12/len, len, occ, a.status);
+                    if (!blocked) {
+                        float r = fmaxf(L.g.rClamp, distToSample);
+                        float G = L.g.evaluate(r);
+                        float h = pde.robin(bs.p, bs.n);
+                        st.reflContrib += st.throughput*alpha*G*h/bs.pdf;
+                    }
+                }
+            }
+        }
+
+        // --- source inside the star, sampled along the step direction (:253-275)
+        if (!a.ws.ignoreSourceContribution) {
+            float sourceRadius, sourcePdf;
+            Vec<DIM> sourcePt = L.g.sampleVolume(dir, L.rng, sourceRadius, sourcePdf);
+            if (sourceRadius <= nextDist) {
+                st.srcContrib += st.throughput*(L.g.norm()*pde.source(sourcePt));
+            }
+        }
+
+        // --- move (:446-452) and throughput (:278-307)
+        st.prevDist = nextDist;
+        st.prevDir = dir;
+        st.pt = nextPt;
+        st.normal = nextNormal;
+        st.onRefl = hitRefl;
+        float factor;
+        if (st.onRefl && st.prevDist > kEpsilon) {
+            float mu = 0.0f;
+            Vec<DIM> n = st.normal;
+            if (!a.pde.areRobinConditionsPureNeumann) {
+                if (a.ws.solveDoubleSided && dot(st.prevDir, st.normal) < 0.0f) n = -n;
+                mu = pde.robinCoeff();
+            }
+            float reflectance = L.g.reflectance(st.prevDist, st.prevDir, n, mu);
+            float maxReflectance = a.pde.areRobinCoeffsNonnegative ? 1.0f : 2.0f;
+            factor = reflectance < 0.0f ? 0.0f : (maxReflectance < reflectance ? maxReflectance : reflectance);
+        } else {
+            factor = L.g.directionSampledPoissonKernel(st.pt);
+        }
+        st.throughput *= factor;
+        if (!st.onRefl && outsideDomain<DIM>(a, st.pt)) return kEscaped;
+    }
+
+    if (weightWindow<DIM>(a, L, queue)) return kRoulette;
+    st.walkLength++;
+    if (st.walkLength >= a.ws.maxWalkLength) return kMaxLength;
+    if (a.pde.absorptionCoeff > 0.0f && a.ws.stepsBeforeApplyingTikhonov == st.walkLength) {
+        L.g.init(true, a.pde.absorptionCoeff);
+    }
+    int projPrim;
+    L.distA = distToAbsorbing<DIM>(a, st.pt, L.proj, projPrim);
+    L.firstStep = false;
+    return kContinue;
+}
+
+// a walk state finished: fold it into the task total and start a queued split or emit the record
+template <int DIM, bool WOST>
+ZB_DEV void finishState(const SolveArgs& a, Lane<DIM>& L, StepResult code, WalkState<DIM> *queue)
+{
+    PdeEval<DIM> pde{a.pde};
+    L.splits++;
+    if (code != kEscaped) {
+        // getTerminalContribution (walk_on_spheres.h:294-318; walk_on_stars.h:493-516): the projection
+        // onto the absorbing boundary was already computed by the last distance query
+        float terminal = 0.0f;
+        bool project = WOST ? code == kReached : (code == kReached || code == kMaxLength);
+        if (project && !a.ws.ignoreAbsorbingBoundaryContribution) {
+            terminal = pde.dirichlet(a.hasAbsorbing ? L.proj : L.st.pt);
+        }
+        L.total += L.st.throughput*terminal + L.st.reflContrib + L.st.srcContrib;
+        L.totalLength += L.st.walkLength;
+        L.success = true;
+    }
+    if (L.nQueued > 0) {
+        L.st = queue[--L.nQueued];
+        bool yukawa = a.pde.absorptionCoeff > 0.0f && a.ws.stepsBeforeApplyingTikhonov == 0;
+        L.g.init(yukawa, a.pde.absorptionCoeff);
+        int projPrim;
+        L.distA = distToAbsorbing<DIM>(a, L.st.pt, L.proj, projPrim);
+        L.firstSphereRadius = 0.0f;
+        L.firstStep = true;
+        L.flip = L.outerFlip;
+        return;
+    }
+    long long t = L.task;
+    a.recSolution[t] = L.total;
+    a.recLength[t] = L.totalLength;
+    a.recFlags[t] = (L.success ? (int)0x80000000 : 0) | (L.splits & 0x7fffffff);
+    if (a.anyGradient) {
+        a.recFirstSource[t] = L.firstSource;
+        for (int k = 0; k < DIM; k++) {
+            a.recGradBoundary[(size_t)DIM*t + k] = L.gradBoundary[k];
+            a.recGradSource[(size_t)DIM*t + k] = L.gradSource[k];
+        }
+    }
+    L.active = false;
+}
+
+template <int DIM, bool WOST>
+__global__ void __launch_bounds__(128) walkKernel(SolveArgs a)
+{
+    Lane<DIM> L;
+    L.active = false;
+    WalkState<DIM> queue[kSplitStack];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    long long chunkNext = 0, chunkEnd = 0; // warp-uniform
+    bool exhausted = false;                // warp-uniform: the global queue is empty
+
+    while (true) {
+        // ---- warp-level compaction: lanes whose walk ended take the next tasks of the warp's chunk
+        unsigned need = __ballot_sync(full, !L.active);
+        if (need) {
+            int want = __popc(need);
+            if (!exhausted && chunkEnd - chunkNext < want) {
+                // keep what is left of the old chunk and append a fresh one when it is contiguous;
+                // otherwise drain the old chunk first
+                if (chunkNext == chunkEnd) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(a.taskCounter, (unsigned long long)kTaskChunk);
+                    base = __shfl_sync(full, base, 0);
+                    chunkNext = (long long)base;
+                    chunkEnd = min((long long)base + kTaskChunk, a.totalTasks);
+                    if (chunkNext >= a.totalTasks) { exhausted = true; chunkNext = chunkEnd = 0; }
+                }
+            }
+            long long avail = chunkEnd - chunkNext;
+            int rank = __popc(need & ((1u << lane) - 1u));
+            if (!L.active && rank < avail) beginTask<DIM, WOST>(a, L, chunkNext + rank);
+            chunkNext += min((long long)want, avail);
+        }
+        if (!__any_sync(full, L.active)) {
+            if (exhausted) break;
+            continue;
+        }
+        if (L.active) {
+            StepResult r = walkStep<DIM, WOST>(a, L, queue);
+            if (r != kContinue) finishState<DIM, WOST>(a, L, r, queue);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// 4. per-point reduction (SampleStatistics::update / add* — common.h:201-395)
+// ------------------------------------------------------------------------------------------
+ZB_DEV void welford(float estimate, float& mean, float& m2, int n)
+{
+    float delta = estimate - mean;
+    mean += delta/n;
+    float delta2 = estimate - mean;
+    m2 += delta*delta2;
+}
+
+template <int DIM>
+ZB_DEV long long reducePoint(const SolveArgs& a, int i)
+{
+    int quantity = a.pts.estimationQuantity[i];
+    PdeEval<DIM> pde{a.pde};
+
+    float mean = a.stats.solutionMean[i], m2 = a.stats.solutionM2[i];
+    int nSol = a.stats.nSolutionEstimates[i], nGrad = a.stats.nGradientEstimates[i];
+    int walkLength = a.stats.totalWalkLength[i], splits = a.stats.totalSplits[i];
+    float firstSourceTotal = a.stats.totalFirstSourceContribution[i];
+    float derivativeTotal = a.stats.totalDerivativeContribution[i];
+    float gmean[DIM], gm2[DIM];
+    for (int k = 0; k < DIM; k++) { gmean[k] = a.stats.gradientMean[(size_t)DIM*i + k]; gm2[k] = a.stats.gradientM2[(size_t)DIM*i + k]; }
+
+    if (quantity == ZB_SOLUTION && a.pts.type[i] == ZB_ON_ABSORBING_BOUNDARY) {
+        if (nSol == 0) {
+            float value = 0.0f;
+            if (!a.ws.ignoreAbsorbingBoundaryContribution) value = pde.dirichlet(loadVec<DIM>(a.pts.pt + (size_t)DIM*i));
+            nSol += 1;
+            welford(value, mean, m2, nSol);
+            a.pts.firstSphereRadius[i] = 0.0f;
+        }
+    } else {
+        long long begin = a.taskOffset[i], end = a.taskOffset[i + 1];
+        bool gradient = quantity == ZB_SOLUTION_AND_GRADIENT;
+        int nAnti = gradient && a.ws.useGradientAntitheticVariates ? 2 : 1;
+        Vec<DIM> ddir = vzero<DIM>();
+        if (gradient) {
+            if (a.pts.directionForDerivative) ddir = loadVec<DIM>(a.pts.directionForDerivative + (size_t)DIM*i);
+            else ddir[0] = 1.0f;
+        }
+        float cvBoundary = 0.0f, cvSource = 0.0f;
+        for (long long t = begin; t < end; t++) {
+            if (gradient && (t - begin)%nAnti == 0 && a.ws.useGradientControlVariates) {
+                // control variates are the running means before this antithetic pair (walk_on_stars.h:693-699)
+                cvBoundary = mean;
+                cvSource = firstSourceTotal/max(1, nSol);
+            }
+            int flags = a.recFlags[t];
+            walkLength += a.recLength[t];
+            if (!(flags & (int)0x80000000)) continue;
+            float total = a.recSolution[t];
+            if (gradient) {
+                float firstSource = a.recFirstSource[t];
+                float boundaryContribution = total - firstSource;
+                float derivative = 0.0f;
+                float est[DIM];
+                for (int k = 0; k < DIM; k++) {
+                    float gb = (boundaryContribution - cvBoundary)*a.recGradBoundary[(size_t)DIM*t + k];
+                    float gs = (firstSource - cvSource)*a.recGradSource[(size_t)DIM*t + k];
+                    derivative += gb*ddir[k];
+                    derivative += gs*ddir[k];
+                    est[k] = gb + gs;
+                }
+                nSol += 1;
+                welford(total, mean, m2, nSol);
+                firstSourceTotal += firstSource;
+                nGrad += 1;
+                for (int k = 0; k < DIM; k++) welford(est[k], gmean[k], gm2[k], nGrad);
+                derivativeTotal += derivative;
+            } else {
+                nSol += 1;
+                welford(total, mean, m2, nSol);
+            }
+            splits += flags & 0x7fffffff;
+        }
+        // the point's generator moves on, so a later solve() on the same points draws fresh walks
+        Pcg32 rng;
+        rng.state = a.pointState[i];
+        rng.inc = a.pts.rngInc[i];
+        rng.advance((uint64_t)(end - begin) + 1u);
+        a.pts.rngState[i] = rng.state;
+    }
+
+    long long stepsTaken = (long long)walkLength - (long long)a.stats.totalWalkLength[i];
+    a.stats.solutionMean[i] = mean;
+    a.stats.solutionM2[i] = m2;
+    a.stats.nSolutionEstimates[i] = nSol;
+    a.stats.nGradientEstimates[i] = nGrad;
+    a.stats.totalWalkLength[i] = walkLength;
+    a.stats.totalSplits[i] = splits;
+    a.stats.totalFirstSourceContribution[i] = firstSourceTotal;
+    a.stats.totalDerivativeContribution[i] = derivativeTotal;
+    for (int k = 0; k < DIM; k++) { a.stats.gradientMean[(size_t)DIM*i + k] = gmean[k]; a.stats.gradientM2[(size_t)DIM*i + k] = gm2[k]; }
+    return stepsTaken;
+}
+
+template <int DIM>
+__global__ void reducePointsKernel(SolveArgs a)
+{
+    int i = blockIdx.x*blockDim.x + threadIdx.x;
+    long long stepsTaken = 0; // walk steps of this launch = the metric's numerator (sum of walkLength++)
+    if (i < a.pts.n && a.pts.estimationQuantity[i] != ZB_SKIP) stepsTaken = reducePoint<DIM>(a, i);
+    for (int o = 16; o > 0; o >>= 1) stepsTaken += __shfl_down_sync(0xffffffffu, stepsTaken, o);
+    if ((threadIdx.x & 31) == 0 && stepsTaken) atomicAdd((unsigned long long *)a.walkSteps, (unsigned long long)stepsTaken);
+}
+
+} // namespace zb

@@ -1,0 +1,223 @@
+"""ctypes binding of zombie_b200/libzombie_b200.so (the C ABI declared in include/zombie_b200.h).
+
+There is no CPU fallback: loading fails loudly when the CUDA library has not been built, and every
+call raises ZombieError when the library reports an error (including "no CUDA device").
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzombie_b200.so")
+_lib = None
+
+# every symbol include/zombie_b200.h declares
+SYMBOLS = ["zb_last_error", "zb_abi_version", "zb_device_count", "zb_context_create", "zb_context_destroy",
+           "zb_context_set_stream", "zb_context_synchronize", "zb_context_device", "zb_context_sm_count",
+           "zb_scene_create", "zb_scene_destroy", "zb_scene_update_robin_coefficients", "zb_scene_stats",
+           "zb_closest_point", "zb_intersect_ray", "zb_occluded", "zb_sample_sphere", "zb_star_radius",
+           "zb_solve", "zb_solve_dev", "zb_pcg32_kat"]
+
+
+class ZombieError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ZombieError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(zombie_b200 has no CPU fallback)" % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        l.zb_last_error.restype = C.c_char_p
+        vp, i, f = C.c_void_p, C.c_int, C.c_float
+        l.zb_context_create.argtypes = [i, C.POINTER(vp)]
+        l.zb_context_destroy.argtypes = [vp]
+        l.zb_context_destroy.restype = None
+        l.zb_context_set_stream.argtypes = [vp, vp]
+        l.zb_context_synchronize.argtypes = [vp]
+        l.zb_context_device.argtypes = [vp]
+        l.zb_context_sm_count.argtypes = [vp]
+        l.zb_scene_create.argtypes = [vp, i, vp, i, vp, i, vp, i, vp, i, i, vp, vp, i, f, i, vp, vp, C.POINTER(vp)]
+        l.zb_scene_destroy.argtypes = [vp]
+        l.zb_scene_destroy.restype = None
+        l.zb_scene_update_robin_coefficients.argtypes = [vp, vp, vp]
+        l.zb_scene_stats.argtypes = [vp, i, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        l.zb_closest_point.argtypes = [vp, i, i] + [vp]*6
+        l.zb_intersect_ray.argtypes = [vp, i, i] + [vp]*7
+        l.zb_occluded.argtypes = [vp, i, i] + [vp]*3
+        l.zb_sample_sphere.argtypes = [vp, i, i] + [vp]*7
+        l.zb_star_radius.argtypes = [vp, i, vp, vp, vp, f, vp, vp]
+        l.zb_solve.argtypes = [vp, i, vp, vp, vp, vp, vp]
+        l.zb_solve_dev.argtypes = [vp, i, vp, vp, vp, vp, vp]
+        l.zb_pcg32_kat.argtypes = [vp, C.c_uint64, C.c_uint64, i, vp]
+        _lib = l
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise ZombieError("%s failed (%d): %s" % (what, rc, lib().zb_last_error().decode()))
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def device_count():
+    return lib().zb_device_count()
+
+
+class Context:
+    """zb_context: one per process and device."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        _check(lib().zb_context_create(device, C.byref(self._h)), "zb_context_create")
+
+    def close(self):
+        if self._h:
+            lib().zb_context_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def sm_count(self):
+        return lib().zb_context_sm_count(self._h)
+
+    @property
+    def device(self):
+        return lib().zb_context_device(self._h)
+
+    def set_stream(self, cuda_stream):
+        _check(lib().zb_context_set_stream(self._h, C.c_void_p(cuda_stream)), "zb_context_set_stream")
+
+    def synchronize(self):
+        _check(lib().zb_context_synchronize(self._h), "zb_context_synchronize")
+
+    def pcg32(self, initstate, initseq, n):
+        out = np.zeros(n, np.uint32)
+        _check(lib().zb_pcg32_kat(self._h, initstate, initseq, n, abi.ptr(out)), "zb_pcg32_kat")
+        return out
+
+
+class Scene:
+    """zb_scene: the Fcpw{Dirichlet,Neumann,Robin}BoundaryHandler + GeometricQueries of the reference
+    (zombie/utils/fcpw_geometric_queries.h:84-150, 1063-1291) on the device."""
+
+    def __init__(self, ctx, dim, absorbing=None, reflecting=None, reflecting_kind=abi.REFLECTING_NONE,
+                 min_robin=None, max_robin=None, solve_double_sided=False, silhouette_precision=1e-3,
+                 watertight=True, domain_min=None, domain_max=None):
+        self.ctx = ctx
+        self.dim = dim
+        ap, ai = absorbing if absorbing is not None else (np.zeros((0, dim), np.float32), np.zeros((0, dim), np.int32))
+        rp, ri = reflecting if reflecting is not None else (np.zeros((0, dim), np.float32), np.zeros((0, dim), np.int32))
+        ap, rp = _f32(ap), _f32(rp)
+        ai = np.ascontiguousarray(ai, np.int32)
+        ri = np.ascontiguousarray(ri, np.int32)
+        allp = np.concatenate([ap, rp], axis=0)
+        if domain_min is None:
+            domain_min = allp.min(axis=0) - 1e-3
+        if domain_max is None:
+            domain_max = allp.max(axis=0) + 1e-3
+        self.domain_min, self.domain_max = _f32(domain_min), _f32(domain_max)
+        mn = _f32(min_robin) if min_robin is not None else np.zeros(len(ri), np.float32)
+        mx = _f32(max_robin) if max_robin is not None else np.zeros(len(ri), np.float32)
+        self._h = C.c_void_p()
+        _check(lib().zb_scene_create(ctx._h, dim, abi.ptr(ap), len(ap), abi.ptr(ai), len(ai),
+                                     abi.ptr(rp), len(rp), abi.ptr(ri), len(ri),
+                                     reflecting_kind, abi.ptr(mn), abi.ptr(mx),
+                                     int(solve_double_sided), silhouette_precision, int(watertight),
+                                     abi.ptr(self.domain_min), abi.ptr(self.domain_max), C.byref(self._h)),
+               "zb_scene_create")
+
+    def close(self):
+        if self._h:
+            lib().zb_scene_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stats(self, which):
+        b, n, l, d = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int32()
+        _check(lib().zb_scene_stats(self._h, which, C.byref(b), C.byref(n), C.byref(l), C.byref(d)), "zb_scene_stats")
+        return {"bytes": b.value, "nodes": n.value, "leaves": l.value, "max_depth": d.value}
+
+    def update_robin_coefficients(self, min_robin, max_robin):
+        mn, mx = _f32(min_robin), _f32(max_robin)
+        _check(lib().zb_scene_update_robin_coefficients(self._h, abi.ptr(mn), abi.ptr(mx)), "zb_scene_update_robin_coefficients")
+
+    def closest_point(self, which, x, max_radius=None, want_normal=True):
+        x = _f32(x)
+        n = len(x)
+        prim = np.zeros(n, np.int32)
+        dist = np.zeros(n, np.float32)
+        pt = np.zeros((n, self.dim), np.float32)
+        nrm = np.zeros((n, self.dim), np.float32) if want_normal else None
+        _check(lib().zb_closest_point(self._h, which, n, abi.ptr(x), abi.ptr(_f32(max_radius)),
+                                      abi.ptr(prim), abi.ptr(dist), abi.ptr(pt), abi.ptr(nrm)), "zb_closest_point")
+        return prim, dist, pt, nrm
+
+    def intersect_ray(self, which, origin, direction, tmax=None):
+        o, d = _f32(origin), _f32(direction)
+        n = len(o)
+        prim = np.zeros(n, np.int32)
+        dist = np.zeros(n, np.float32)
+        pt = np.zeros((n, self.dim), np.float32)
+        nrm = np.zeros((n, self.dim), np.float32)
+        _check(lib().zb_intersect_ray(self._h, which, n, abi.ptr(o), abi.ptr(d), abi.ptr(_f32(tmax)),
+                                      abi.ptr(prim), abi.ptr(dist), abi.ptr(pt), abi.ptr(nrm)), "zb_intersect_ray")
+        return prim, dist, pt, nrm
+
+    def occluded(self, which, a, b):
+        a, b = _f32(a), _f32(b)
+        out = np.zeros(len(a), np.uint8)
+        _check(lib().zb_occluded(self._h, which, len(a), abi.ptr(a), abi.ptr(b), abi.ptr(out)), "zb_occluded")
+        return out
+
+    def sample_sphere(self, x, radius, rand_nums, which=abi.REFLECTING):
+        x, radius, u = _f32(x), _f32(radius), _f32(rand_nums)
+        n = len(x)
+        prim = np.zeros(n, np.int32)
+        pt = np.zeros((n, self.dim), np.float32)
+        nrm = np.zeros((n, self.dim), np.float32)
+        pdf = np.zeros(n, np.float32)
+        _check(lib().zb_sample_sphere(self._h, which, n, abi.ptr(x), abi.ptr(radius), abi.ptr(u),
+                                      abi.ptr(prim), abi.ptr(pt), abi.ptr(nrm), abi.ptr(pdf)), "zb_sample_sphere")
+        return prim, pt, nrm, pdf
+
+    def star_radius(self, x, min_radius, max_radius, precision=1e-3, flip=None):
+        x, mn, mx = _f32(x), _f32(min_radius), _f32(max_radius)
+        out = np.zeros(len(x), np.float32)
+        fl = None if flip is None else np.ascontiguousarray(flip, np.uint8)
+        _check(lib().zb_star_radius(self._h, len(x), abi.ptr(x), abi.ptr(mn), abi.ptr(mx), precision,
+                                    abi.ptr(fl), abi.ptr(out)), "zb_star_radius")
+        return out
+
+    def solve(self, estimator, pde, settings, pts, stats):
+        """WalkOnSpheres::solve / WalkOnStars::solve (vector overloads) with host arrays; pts and stats
+        are updated in place like the reference's samplePts / statistics. Returns the walk steps taken."""
+        steps = C.c_int64(0)
+        ps, ss = pts.as_struct(), stats.as_struct()
+        _check(lib().zb_solve(self._h, estimator, C.byref(pde), C.byref(settings), C.byref(ps), C.byref(ss),
+                              C.byref(steps)), "zb_solve")
+        return steps.value
+
+    def solve_dev(self, estimator, pde, settings, pts_struct, stats_struct, steps_dev_ptr=None):
+        """Same with every array already resident on the device (abi.SamplePoints / abi.Statistics of
+        device pointers); asynchronous on the context's stream."""
+        _check(lib().zb_solve_dev(self._h, estimator, C.byref(pde), C.byref(settings), C.byref(pts_struct),
+                                  C.byref(stats_struct), C.c_void_p(steps_dev_ptr)), "zb_solve_dev")
