@@ -129,6 +129,13 @@ void zb_context_destroy(zb_context *ctx);
 int zb_context_set_stream(zb_context *ctx, void *cudaStream);
 int zb_context_synchronize(zb_context *ctx);
 int zb_context_device(const zb_context *ctx);
+/* Measurement hook (no reference counterpart; the reference only prints whole seconds,
+ * zombie/utils/progress.h:32-39): CUDA-event durations, on the context's stream, of the last
+ * zb_solve/zb_solve_dev — the per-point preparation kernels, the persistent walk kernel and the
+ * per-point reduction — plus the number of walks it ran, the walk kernel's grid size and the
+ * number of kernels this context has launched so far. Blocks until that solve has finished. */
+int zb_context_last_solve_profile(zb_context *ctx, float *prepareMs, float *walkMs, float *reduceMs,
+                                  int64_t *walks, int32_t *walkGrid, int64_t *kernelLaunches);
 int zb_context_sm_count(const zb_context *ctx);
 
 /* ---- geometry: replaces Fcpw{Dirichlet,Neumann,Robin}BoundaryHandler::buildAccelerationStructure

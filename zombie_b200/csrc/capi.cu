@@ -61,6 +61,10 @@ struct zb_context {
     bool ownsStream = false;
     DeviceBuffer status, counters, perPoint, strat, records, scanTemp, io;
     int *hostStatus = nullptr; // pinned
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; // solve start | walk start | walk end | solve end
+    bool profiled = false;
+    long long lastTasks = 0;
+    int lastGrid = 0, launches = 0;
 };
 
 struct DeviceBvhStorage {
@@ -123,23 +127,30 @@ int checkStatus(zb_context *ctx, const char *what)
         std::string msg = std::string(what) + ":";
         if (st & kStatusStackOverflow) msg += " BVH traversal stack overflow";
         if (st & kStatusSplitOverflow) msg += " walk split queue overflow (more than 6 pending splits)";
+        if (st & kStatusCoopOverflow) msg += " cooperative traversal stack overflow";
         return fail(ZB_ERR_UNSUPPORTED, msg);
     }
     return ZB_OK;
 }
 
 // ---- batched query kernels ---------------------------------------------------------------------
+constexpr size_t kCoopSmem = 4*sizeof(WarpShared); // 128-thread CTAs
+
 template <int DIM>
-__global__ void closestPointKernel(BvhView bvh, int n, const float *x, const float *maxRadius,
-                                   int *prim, float *dist, float *pt, float *normal, int *status)
+__global__ void __launch_bounds__(128) closestPointKernel(BvhView bvh, int n, const float *x, const float *maxRadius,
+                                                          int *prim, float *dist, float *pt, float *normal, int *status)
 {
+    extern __shared__ __align__(16) unsigned char zbShared[];
+    WarpShared& ws = reinterpret_cast<WarpShared *>(zbShared)[threadIdx.x >> 5];
     int i = blockIdx.x*blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Vec<DIM> q = loadVec<DIM>(x + (size_t)DIM*i);
+    bool has = i < n;
+    Vec<DIM> q = has ? loadVec<DIM>(x + (size_t)DIM*i) : vzero<DIM>();
     float r2 = kMaxFloat;
-    if (maxRadius && maxRadius[i] < kMaxFloat) r2 = maxRadius[i]*maxRadius[i];
+    if (has && maxRadius && maxRadius[i] < kMaxFloat) r2 = maxRadius[i]*maxRadius[i];
     ClosestHit<DIM> hit;
-    bool found = closestPoint<DIM>(bvh, q, r2, hit, status);
+    coopClosestPoint<DIM>(bvh, ws, has, q, r2, hit, status);
+    if (!has) return;
+    bool found = hit.prim >= 0;
     prim[i] = found ? bvh.primIndex[hit.prim] : -1;
     dist[i] = found ? hit.d : kMaxFloat;
     if (pt) storeVec<DIM>(pt + (size_t)DIM*i, found ? hit.p : vzero<DIM>());
@@ -201,13 +212,21 @@ __global__ void sampleSphereKernel(BvhView bvh, int n, const float *x, const flo
 }
 
 template <int DIM>
-__global__ void starRadiusKernel(SolveArgs a, int n, const float *x, const float *minR, const float *maxR,
-                                 float precision, const uint8_t *flip, float *out)
+__global__ void __launch_bounds__(128) starRadiusKernel(SolveArgs a, int n, const float *x, const float *minR, const float *maxR,
+                                                        float precision, const uint8_t *flip, float *out)
 {
+    extern __shared__ __align__(16) unsigned char zbShared[];
+    WarpShared& ws = reinterpret_cast<WarpShared *>(zbShared)[threadIdx.x >> 5];
     int i = blockIdx.x*blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Vec<DIM> q = loadVec<DIM>(x + (size_t)DIM*i);
-    out[i] = starRadiusQuery<DIM>(a, q, minR[i], maxR[i], precision, flip ? flip[i] != 0 : false);
+    bool has = i < n;
+    Vec<DIM> q = has ? loadVec<DIM>(x + (size_t)DIM*i) : vzero<DIM>();
+    float mn = has ? minR[i] : 0.0f, mx = has ? maxR[i] : 0.0f;
+    bool fl = has && flip ? flip[i] != 0 : false;
+    float result = mx, r2max = 0.0f;
+    bool query = has && starQueryNeeded<DIM>(a, mn, mx, result, r2max);
+    float r2 = coopStarRadius2<DIM>(a.reflecting, ws, query, q, r2max, !fl, precision, a.status);
+    if (query) result = starQueryResult(a, r2, r2max, mn, mx);
+    if (has) out[i] = result;
 }
 
 __global__ void pcg32Kernel(uint64_t initstate, uint64_t initseq, int n, uint32_t *out)
@@ -311,6 +330,7 @@ int solveRange(zb_scene *scene, SolveArgs& a, int n, bool anyGradient)
     a.anyGradient = anyGradient ? 1 : 0;
 
     const int threads = 128;
+    ZB_CUDA(cudaEventRecord(ctx->ev[0], stream));
     countTasksKernel<DIM><<<blocksFor(n, threads), threads, 0, stream>>>(a);
     ZB_CUDA(cudaGetLastError());
 
@@ -355,28 +375,40 @@ int solveRange(zb_scene *scene, SolveArgs& a, int n, bool anyGradient)
     a.taskCounter = ctx->counters.as<unsigned long long>();
     ZB_CUDA(cudaMemsetAsync(a.taskCounter, 0, sizeof(unsigned long long), stream));
 
-    preparePointsKernel<DIM><<<blocksFor(n, threads), threads, 0, stream>>>(a);
+    ZB_CUDA(cudaFuncSetAttribute(preparePointsKernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
+    preparePointsKernel<DIM><<<blocksFor(n, threads), threads, kCoopSmem, stream>>>(a);
     ZB_CUDA(cudaGetLastError());
 
+    ZB_CUDA(cudaEventRecord(ctx->ev[1], stream));
+    ctx->lastTasks = totalTasks;
+    ctx->lastGrid = 0;
+    ctx->launches += 5; // count, 2 scans (init + scan kernels counted once each), prepare, reduce
     if (totalTasks > 0) {
         // persistent grid: a whole number of waves of 128-thread CTAs over all SMs
         int perSm = 0;
         if (a.estimator == ZB_WALK_ON_STARS) {
-            ZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, walkKernel<DIM, true>, 128, 0));
+            ZB_CUDA(cudaFuncSetAttribute(walkKernel<DIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
+            ZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, walkKernel<DIM, true>, 128, kCoopSmem));
         } else {
-            ZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, walkKernel<DIM, false>, 128, 0));
+            ZB_CUDA(cudaFuncSetAttribute(walkKernel<DIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
+            ZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, walkKernel<DIM, false>, 128, kCoopSmem));
         }
         perSm = std::max(1, perSm);
         long long wantBlocks = (totalTasks + 127)/128;
         int grid = (int)std::min<long long>((long long)ctx->smCount*perSm, wantBlocks);
         grid = std::max(1, grid);
-        if (a.estimator == ZB_WALK_ON_STARS) walkKernel<DIM, true><<<grid, 128, 0, stream>>>(a);
-        else walkKernel<DIM, false><<<grid, 128, 0, stream>>>(a);
+        if (a.estimator == ZB_WALK_ON_STARS) walkKernel<DIM, true><<<grid, 128, kCoopSmem, stream>>>(a);
+        else walkKernel<DIM, false><<<grid, 128, kCoopSmem, stream>>>(a);
         ZB_CUDA(cudaGetLastError());
+        ctx->lastGrid = grid;
+        ctx->launches += 1;
     }
+    ZB_CUDA(cudaEventRecord(ctx->ev[2], stream));
 
     reducePointsKernel<DIM><<<blocksFor(n, threads), threads, 0, stream>>>(a);
     ZB_CUDA(cudaGetLastError());
+    ZB_CUDA(cudaEventRecord(ctx->ev[3], stream));
+    ctx->profiled = true;
     return ZB_OK;
 }
 
@@ -414,6 +446,7 @@ int zb_context_create(int device, zb_context **out)
     ZB_CUDA(cudaMemset(ctx->status.ptr, 0, 256));
     ZB_CUDA(cudaMemset(ctx->counters.ptr, 0, 256));
     ZB_CUDA(cudaMallocHost(&ctx->hostStatus, 64));
+    for (int k = 0; k < 4; k++) ZB_CUDA(cudaEventCreate(&ctx->ev[k]));
     *out = ctx;
     return ZB_OK;
 }
@@ -425,6 +458,7 @@ void zb_context_destroy(zb_context *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->ownsStream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->hostStatus) cudaFreeHost(ctx->hostStatus);
+    for (int k = 0; k < 4; k++) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     delete ctx;
 }
 
@@ -442,6 +476,26 @@ int zb_context_synchronize(zb_context *ctx)
     if (!ctx) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_context_synchronize: ctx is NULL");
     ZB_CUDA(cudaSetDevice(ctx->device));
     ZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZB_OK;
+}
+
+int zb_context_last_solve_profile(zb_context *ctx, float *prepareMs, float *walkMs, float *reduceMs,
+                                  int64_t *walks, int32_t *walkGrid, int64_t *kernelLaunches)
+{
+    if (!ctx) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_context_last_solve_profile: ctx is NULL");
+    if (!ctx->profiled) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_context_last_solve_profile: no solve has run on this context");
+    ZB_CUDA(cudaSetDevice(ctx->device));
+    ZB_CUDA(cudaEventSynchronize(ctx->ev[3]));
+    float t01 = 0, t12 = 0, t23 = 0;
+    ZB_CUDA(cudaEventElapsedTime(&t01, ctx->ev[0], ctx->ev[1]));
+    ZB_CUDA(cudaEventElapsedTime(&t12, ctx->ev[1], ctx->ev[2]));
+    ZB_CUDA(cudaEventElapsedTime(&t23, ctx->ev[2], ctx->ev[3]));
+    if (prepareMs) *prepareMs = t01;
+    if (walkMs) *walkMs = t12;
+    if (reduceMs) *reduceMs = t23;
+    if (walks) *walks = ctx->lastTasks;
+    if (walkGrid) *walkGrid = ctx->lastGrid;
+    if (kernelLaunches) *kernelLaunches = ctx->launches;
     return ZB_OK;
 }
 
@@ -571,9 +625,11 @@ int zb_closest_point(zb_scene *scene, int boundary, int n, const float *x, const
     int rc = stageIn(ctx, plan);
     if (rc != ZB_OK) return rc;
     int threads = 128, blocks = blocksFor(n, threads);
-    if (dim == 3) closestPointKernel<3><<<blocks, threads, 0, ctx->stream>>>(bvh, n, at<float>(ctx, oX, x), at<float>(ctx, oR, maxRadius),
+    ZB_CUDA(cudaFuncSetAttribute(closestPointKernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
+    ZB_CUDA(cudaFuncSetAttribute(closestPointKernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
+    if (dim == 3) closestPointKernel<3><<<blocks, threads, kCoopSmem, ctx->stream>>>(bvh, n, at<float>(ctx, oX, x), at<float>(ctx, oR, maxRadius),
         at<int>(ctx, oP, prim), at<float>(ctx, oD, dist), at<float>(ctx, oPt, pt), at<float>(ctx, oN, normal), ctx->status.as<int>());
-    else closestPointKernel<2><<<blocks, threads, 0, ctx->stream>>>(bvh, n, at<float>(ctx, oX, x), at<float>(ctx, oR, maxRadius),
+    else closestPointKernel<2><<<blocks, threads, kCoopSmem, ctx->stream>>>(bvh, n, at<float>(ctx, oX, x), at<float>(ctx, oR, maxRadius),
         at<int>(ctx, oP, prim), at<float>(ctx, oD, dist), at<float>(ctx, oPt, pt), at<float>(ctx, oN, normal), ctx->status.as<int>());
     ZB_CUDA(cudaGetLastError());
     rc = stageOut(ctx, plan);
@@ -658,9 +714,11 @@ int zb_star_radius(zb_scene *scene, int n, const float *x, const float *minRadiu
     SolveArgs a;
     fillSceneArgs(scene, a);
     int threads = 128, blocks = blocksFor(n, threads);
-    if (dim == 3) starRadiusKernel<3><<<blocks, threads, 0, ctx->stream>>>(a, n, at<float>(ctx, oX, x), at<float>(ctx, oMn, minRadius), at<float>(ctx, oMx, maxRadius),
+    ZB_CUDA(cudaFuncSetAttribute(starRadiusKernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
+    ZB_CUDA(cudaFuncSetAttribute(starRadiusKernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
+    if (dim == 3) starRadiusKernel<3><<<blocks, threads, kCoopSmem, ctx->stream>>>(a, n, at<float>(ctx, oX, x), at<float>(ctx, oMn, minRadius), at<float>(ctx, oMx, maxRadius),
         silhouettePrecision, at<uint8_t>(ctx, oF, flipNormalOrientation), at<float>(ctx, oR, radius));
-    else starRadiusKernel<2><<<blocks, threads, 0, ctx->stream>>>(a, n, at<float>(ctx, oX, x), at<float>(ctx, oMn, minRadius), at<float>(ctx, oMx, maxRadius),
+    else starRadiusKernel<2><<<blocks, threads, kCoopSmem, ctx->stream>>>(a, n, at<float>(ctx, oX, x), at<float>(ctx, oMn, minRadius), at<float>(ctx, oMx, maxRadius),
         silhouettePrecision, at<uint8_t>(ctx, oF, flipNormalOrientation), at<float>(ctx, oR, radius));
     ZB_CUDA(cudaGetLastError());
     rc = stageOut(ctx, plan);
@@ -784,6 +842,19 @@ int zb_solve(zb_scene *scene, int estimator, const zb_pde_desc *pde, const zb_wa
     if (walkSteps) ZB_CUDA(cudaMemcpyAsync(walkSteps, base + stepsOff, 8, cudaMemcpyDeviceToHost, ctx->stream));
     return stageOut(ctx, plan);
 }
+
+#ifdef ZB_STATS
+// debug build only: reads and clears the traversal counters (see queries.cuh)
+int zb_debug_counters(zb_context *ctx, unsigned long long *out16)
+{
+    ZB_CUDA(cudaSetDevice(ctx->device));
+    ZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ZB_CUDA(cudaMemcpyFromSymbol(out16, g_zbCounters, sizeof(unsigned long long)*16));
+    unsigned long long zero[16] = {0};
+    ZB_CUDA(cudaMemcpyToSymbol(g_zbCounters, zero, sizeof(zero)));
+    return ZB_OK;
+}
+#endif
 
 int zb_pcg32_kat(zb_context *ctx, uint64_t initstate, uint64_t initseq, int n, uint32_t *out)
 {

@@ -21,6 +21,35 @@ struct BvhView {
     int snchSign;              // 1: Robin handler convention; -1: FCPW SNCH (Neumann handler) convention
 };
 
+// optional traversal counters (build with -DZB_STATS): [2q] = nodes visited, [2q+1] = primitives tested,
+// [10+q] = number of queries, q = 0 closest point, 1 ray, 2 occlusion ray, 3 sphere sample, 4 star radius
+#if defined(ZB_HOST_STATS)
+// tools/host_probe.cu: per-query records on the host pass, nothing on the device pass
+#if defined(__CUDA_ARCH__)
+#define ZB_COUNT_DECL
+#define ZB_COUNT_NODE
+#define ZB_COUNT_PRIM
+#define ZB_COUNT_FLUSH(q)
+#else
+void zbHostRecord(int query, int nodes, int prims);
+#define ZB_COUNT_DECL int zbNodes = 0, zbPrims = 0;
+#define ZB_COUNT_NODE zbNodes++;
+#define ZB_COUNT_PRIM zbPrims++;
+#define ZB_COUNT_FLUSH(q) zbHostRecord((q), zbNodes, zbPrims);
+#endif
+#elif defined(ZB_STATS)
+__device__ unsigned long long g_zbCounters[16];
+#define ZB_COUNT_DECL int zbNodes = 0, zbPrims = 0;
+#define ZB_COUNT_NODE zbNodes++;
+#define ZB_COUNT_PRIM zbPrims++;
+#define ZB_COUNT_FLUSH(q) { atomicAdd(&g_zbCounters[2*(q)], (unsigned long long)zbNodes); atomicAdd(&g_zbCounters[2*(q) + 1], (unsigned long long)zbPrims); atomicAdd(&g_zbCounters[10 + (q)], 1ull); }
+#else
+#define ZB_COUNT_DECL
+#define ZB_COUNT_NODE
+#define ZB_COUNT_PRIM
+#define ZB_COUNT_FLUSH(q)
+#endif
+
 constexpr int kStackSize = 64;
 constexpr uint32_t kLeafFlag = 0x80000000u;
 
@@ -35,7 +64,7 @@ ZB_DEV void loadNode(const uint4 *nodes, uint32_t idx, NodeRegs& n)
 {
     const uint4 *p = nodes + (size_t)idx*5;
 #pragma unroll
-    for (int i = 0; i < 5; i++) n.q[i] = __ldg(p + i);
+    for (int i = 0; i < 5; i++) n.q[i] = zb_ldg(p + i);
 }
 
 ZB_DEV float byteF(uint32_t w, int i) { return (float)((w >> (8*i)) & 0xffu); }
@@ -57,13 +86,13 @@ template <int DIM>
 ZB_DEV NodeFrame<DIM> nodeFrame(const NodeRegs& n)
 {
     NodeFrame<DIM> f;
-    f.o[0] = __uint_as_float(n.q[0].x);
-    f.o[1] = __uint_as_float(n.q[0].y);
-    if (DIM == 3) f.o[DIM - 1] = __uint_as_float(n.q[0].z);
+    f.o[0] = zb_uint_as_float(n.q[0].x);
+    f.o[1] = zb_uint_as_float(n.q[0].y);
+    if (DIM == 3) f.o[DIM - 1] = zb_uint_as_float(n.q[0].z);
     uint32_t e = n.q[0].w;
-    f.s[0] = __uint_as_float((e & 0xffu) << 23);
-    f.s[1] = __uint_as_float(((e >> 8) & 0xffu) << 23);
-    if (DIM == 3) f.s[DIM - 1] = __uint_as_float(((e >> 16) & 0xffu) << 23);
+    f.s[0] = zb_uint_as_float((e & 0xffu) << 23);
+    f.s[1] = zb_uint_as_float(((e >> 8) & 0xffu) << 23);
+    if (DIM == 3) f.s[DIM - 1] = zb_uint_as_float(((e >> 16) & 0xffu) << 23);
     return f;
 }
 
@@ -91,7 +120,7 @@ ZB_DEV uint32_t childRef(const NodeRegs& n, uint32_t meta)
     return n.q[1].x + (meta & 31u) - 1u;
 }
 
-ZB_DEV void cswap(uint32_t& a, uint32_t& b) { uint32_t lo = min(a, b); b = max(a, b); a = lo; }
+ZB_DEV void cswap(uint32_t& a, uint32_t& b) { uint32_t lo = zb_umin(a, b); b = zb_umax(a, b); a = lo; }
 
 // ascending sort of 8 keys (19 compare-exchanges)
 ZB_DEV void sort8(uint32_t k[8])
@@ -105,11 +134,32 @@ ZB_DEV void sort8(uint32_t k[8])
     cswap(k[3], k[4]);
 }
 
-ZB_DEV float keyValue(uint32_t key) { return __uint_as_float(key & ~7u); }
+ZB_DEV float keyValue(uint32_t key) { return zb_uint_as_float(key & ~7u); }
 
 // ------------------------------------------------------------------------------------------
 // primitives
 // ------------------------------------------------------------------------------------------
+
+// ---- uncontracted arithmetic ---------------------------------------------------------------
+// The primitive tests below use explicit round-to-nearest multiplies and adds (never fused into
+// FMAs) in the evaluation order of the reference's fixed-size vector library (dot of 3 terms =
+// x0*y0 + (x1*y1 + x2*y2)), so that for the same primitive and query they return bit-identical
+// distances, parameters and points to FCPW's CPU build (-O3, no FMA contraction on x86-64).
+ZB_DEV float xdot(const Vec<3>& a, const Vec<3>& b)
+{
+    return zb_fadd(zb_fmul(a[0], b[0]), zb_fadd(zb_fmul(a[1], b[1]), zb_fmul(a[2], b[2])));
+}
+ZB_DEV float xdot(const Vec<2>& a, const Vec<2>& b) { return zb_fadd(zb_fmul(a[0], b[0]), zb_fmul(a[1], b[1])); }
+template <int D> ZB_DEV float xnorm(const Vec<D>& a) { return sqrtf(xdot(a, a)); }
+template <int D> ZB_DEV Vec<D> xscale(const Vec<D>& a, float s) { Vec<D> r; for (int i = 0; i < D; i++) r[i] = zb_fmul(a[i], s); return r; }
+template <int D> ZB_DEV Vec<D> xadd(const Vec<D>& a, const Vec<D>& b) { Vec<D> r; for (int i = 0; i < D; i++) r[i] = zb_fadd(a[i], b[i]); return r; }
+// a*b - c*d without contraction
+ZB_DEV float xdiffprod(float a, float b, float c, float d) { return zb_fsub(zb_fmul(a, b), zb_fmul(c, d)); }
+ZB_DEV Vec<3> xcross(const Vec<3>& a, const Vec<3>& b)
+{
+    return make3(xdiffprod(a[1], b[2], a[2], b[1]), xdiffprod(a[2], b[0], a[0], b[2]), xdiffprod(a[0], b[1], a[1], b[0]));
+}
+ZB_DEV float xcross2(const Vec<2>& a, const Vec<2>& b) { return xdiffprod(a[0], b[1], a[1], b[0]); }
 
 // closest point on triangle (pa, pb, pc) to x by Voronoi-region classification (Ericson, Real-Time
 // Collision Detection 5.1.5), the same classification order and comparisons as
@@ -118,46 +168,46 @@ ZB_DEV float closestPointTriangle(const Vec<3>& pa, const Vec<3>& pb, const Vec<
                                   Vec<3>& pt, float& bu, float& bv)
 {
     Vec<3> ab = pb - pa, ac = pc - pa, ax = x - pa;
-    float d1 = dot(ab, ax), d2 = dot(ac, ax);
-    if (d1 <= 0.0f && d2 <= 0.0f) { bu = 1.0f; bv = 0.0f; pt = pa; return norm(x - pt); }
+    float d1 = xdot(ab, ax), d2 = xdot(ac, ax);
+    if (d1 <= 0.0f && d2 <= 0.0f) { bu = 1.0f; bv = 0.0f; pt = pa; return xnorm(x - pt); }
 
     Vec<3> bx = x - pb;
-    float d3 = dot(ab, bx), d4 = dot(ac, bx);
-    if (d3 >= 0.0f && d4 <= d3) { bu = 0.0f; bv = 1.0f; pt = pb; return norm(x - pt); }
+    float d3 = xdot(ab, bx), d4 = xdot(ac, bx);
+    if (d3 >= 0.0f && d4 <= d3) { bu = 0.0f; bv = 1.0f; pt = pb; return xnorm(x - pt); }
 
     Vec<3> cx = x - pc;
-    float d5 = dot(ab, cx), d6 = dot(ac, cx);
-    if (d6 >= 0.0f && d5 <= d6) { bu = 0.0f; bv = 0.0f; pt = pc; return norm(x - pt); }
+    float d5 = xdot(ab, cx), d6 = xdot(ac, cx);
+    if (d6 >= 0.0f && d5 <= d6) { bu = 0.0f; bv = 0.0f; pt = pc; return xnorm(x - pt); }
 
-    float vc = d1*d4 - d3*d2;
+    float vc = xdiffprod(d1, d4, d3, d2);
     if (vc <= 0.0f && d1 >= 0.0f && d3 <= 0.0f) {
         float v = d1/(d1 - d3);
         bu = 1.0f - v; bv = v;
-        pt = pa + ab*v;
-        return norm(x - pt);
+        pt = xadd(pa, xscale(ab, v));
+        return xnorm(x - pt);
     }
 
-    float vb = d5*d2 - d1*d6;
+    float vb = xdiffprod(d5, d2, d1, d6);
     if (vb <= 0.0f && d2 >= 0.0f && d6 <= 0.0f) {
         float w = d2/(d2 - d6);
         bu = 1.0f - w; bv = 0.0f;
-        pt = pa + ac*w;
-        return norm(x - pt);
+        pt = xadd(pa, xscale(ac, w));
+        return xnorm(x - pt);
     }
 
-    float va = d3*d6 - d5*d4;
+    float va = xdiffprod(d3, d6, d5, d4);
     if (va <= 0.0f && (d4 - d3) >= 0.0f && (d5 - d6) >= 0.0f) {
         float w = (d4 - d3)/((d4 - d3) + (d5 - d6));
         bu = 0.0f; bv = 1.0f - w;
-        pt = pb + (pc - pb)*w;
-        return norm(x - pt);
+        pt = xadd(pb, xscale(pc - pb, w));
+        return xnorm(x - pt);
     }
 
-    float denom = 1.0f/(va + vb + vc);
-    float v = vb*denom, w = vc*denom;
+    float denom = 1.0f/(zb_fadd(zb_fadd(va, vb), vc));
+    float v = zb_fmul(vb, denom), w = zb_fmul(vc, denom);
     bu = 1.0f - v - w; bv = v;
-    pt = pa + ab*v + ac*w;
-    return norm(x - pt);
+    pt = xadd(xadd(pa, xscale(ab, v)), xscale(ac, w));
+    return xnorm(x - pt);
 }
 
 // fcpw/geometry/line_segments.inl:200-227
@@ -165,13 +215,13 @@ template <int DIM>
 ZB_DEV float closestPointSegment(const Vec<DIM>& pa, const Vec<DIM>& pb, const Vec<DIM>& x, Vec<DIM>& pt, float& t)
 {
     Vec<DIM> u = pb - pa, v = x - pa;
-    float c1 = dot(u, v);
-    if (c1 <= 0.0f) { pt = pa; t = 0.0f; return norm(x - pt); }
-    float c2 = dot(u, u);
-    if (c2 <= c1) { pt = pb; t = 1.0f; return norm(x - pt); }
+    float c1 = xdot(u, v);
+    if (c1 <= 0.0f) { pt = pa; t = 0.0f; return xnorm(x - pt); }
+    float c2 = xdot(u, u);
+    if (c2 <= c1) { pt = pb; t = 1.0f; return xnorm(x - pt); }
     t = c1/c2;
-    pt = pa + u*t;
-    return norm(x - pt);
+    pt = xadd(pa, xscale(u, t));
+    return xnorm(x - pt);
 }
 
 template <int DIM> struct Prim;
@@ -180,32 +230,32 @@ template <> struct Prim<3> {
     Vec<3> a, b, c;
     int index;
     ZB_DEV void load(const BvhView& bvh, uint32_t i) {
-        float4 v0 = __ldg(bvh.prims + (size_t)3*i), v1 = __ldg(bvh.prims + (size_t)3*i + 1), v2 = __ldg(bvh.prims + (size_t)3*i + 2);
+        float4 v0 = zb_ldg(bvh.prims + (size_t)3*i), v1 = zb_ldg(bvh.prims + (size_t)3*i + 1), v2 = zb_ldg(bvh.prims + (size_t)3*i + 2);
         a = make3(v0.x, v0.y, v0.z); b = make3(v1.x, v1.y, v1.z); c = make3(v2.x, v2.y, v2.z);
-        index = __float_as_int(v0.w);
+        index = zb_float_as_int(v0.w);
     }
     ZB_DEV float closest(const Vec<3>& x, Vec<3>& pt, float& u, float& v) const { return closestPointTriangle(a, b, c, x, pt, u, v); }
     // unnormalised normal (b-a)x(c-a): fcpw Triangle::normal()
-    ZB_DEV Vec<3> rawNormal() const { return cross(b - a, c - a); }
+    ZB_DEV Vec<3> rawNormal() const { return xcross(b - a, c - a); }
     ZB_DEV float area() const { return 0.5f*norm(rawNormal()); } // triangles.inl:34-37
     // Moller-Trumbore with the parallel cutoff and inclusive bounds of triangles.inl:222-260
     ZB_DEV bool intersect(const Vec<3>& o, const Vec<3>& d, float tMax, float& t, float& bv, float& bw) const {
         Vec<3> v1 = b - a, v2 = c - a;
-        Vec<3> p = cross(d, v2);
-        float det = dot(v1, p);
+        Vec<3> p = xcross(d, v2);
+        float det = xdot(v1, p);
         if (fabsf(det) <= kEpsilon) return false;
         float invDet = 1.0f/det;
         Vec<3> s = o - a;
-        float v = dot(s, p)*invDet;
+        float v = zb_fmul(xdot(s, p), invDet);
         if (v < 0.0f || v > 1.0f) return false;
-        Vec<3> q = cross(s, v1);
-        float w = dot(d, q)*invDet;
-        if (w < 0.0f || v + w > 1.0f) return false;
-        float tt = dot(v2, q)*invDet;
+        Vec<3> q = xcross(s, v1);
+        float w = zb_fmul(xdot(d, q), invDet);
+        if (w < 0.0f || zb_fadd(v, w) > 1.0f) return false;
+        float tt = zb_fmul(xdot(v2, q), invDet);
         if (tt >= 0.0f && tt <= tMax) { t = tt; bv = v; bw = w; return true; }
         return false;
     }
-    ZB_DEV Vec<3> pointAt(float bv, float bw) const { return a + (b - a)*bv + (c - a)*bw; }
+    ZB_DEV Vec<3> pointAt(float bv, float bw) const { return xadd(xadd(a, xscale(b - a, bv)), xscale(c - a, bw)); }
     // uniform point: triangles.inl:113-131 (uses randNums[1], randNums[2]); returns pdf 2/|n|
     ZB_DEV float sample(const Vec<3>& rand, Vec<3>& p, Vec<3>& n) const {
         n = rawNormal();
@@ -222,9 +272,9 @@ template <> struct Prim<2> {
     Vec<2> a, b;
     int index;
     ZB_DEV void load(const BvhView& bvh, uint32_t i) {
-        float4 v = __ldg(bvh.prims + i);
+        float4 v = zb_ldg(bvh.prims + i);
         a = make2(v.x, v.y); b = make2(v.z, v.w);
-        index = __ldg(bvh.primIndex + i);
+        index = zb_ldg(bvh.primIndex + i);
     }
     ZB_DEV float closest(const Vec<2>& x, Vec<2>& pt, float& u, float& v) const { v = 0.0f; return closestPointSegment<2>(a, b, x, pt, u); }
     ZB_DEV Vec<2> rawNormal() const { Vec<2> s = b - a; return make2(s[1], -s[0]); }
@@ -232,18 +282,18 @@ template <> struct Prim<2> {
     // line_segments.inl:140-175
     ZB_DEV bool intersect(const Vec<2>& o, const Vec<2>& d, float tMax, float& t, float& bs, float& unused) const {
         Vec<2> u = a - o, v = b - a;
-        float dv = cross2(d, v);
+        float dv = xcross2(d, v);
         if (fabsf(dv) <= kEpsilon) return false;
-        float ud = cross2(u, d);
+        float ud = xcross2(u, d);
         float s = ud/dv;
         if (s >= 0.0f && s <= 1.0f) {
-            float uv = cross2(u, v);
+            float uv = xcross2(u, v);
             float tt = uv/dv;
             if (tt >= 0.0f && tt <= tMax) { t = tt; bs = s; unused = 0.0f; return true; }
         }
         return false;
     }
-    ZB_DEV Vec<2> pointAt(float s, float) const { return a + (b - a)*s; }
+    ZB_DEV Vec<2> pointAt(float s, float) const { return xadd(a, xscale(b - a, s)); }
     // line_segments.inl:83-98 (uses randNums[1])
     ZB_DEV float sample(const Vec<2>& rand, Vec<2>& p, Vec<2>& n) const {
         Vec<2> s = b - a;
@@ -255,7 +305,7 @@ template <> struct Prim<2> {
 };
 
 template <int DIM>
-ZB_DEV Vec<DIM> unitNormal(const Prim<DIM>& p) { Vec<DIM> n = p.rawNormal(); return n/norm(n); }
+ZB_DEV Vec<DIM> unitNormal(const Prim<DIM>& p) { Vec<DIM> n = p.rawNormal(); return n/xnorm(n); }
 
 // ------------------------------------------------------------------------------------------
 // closest point
@@ -294,6 +344,7 @@ ZB_DEV bool closestPoint(const BvhView& bvh, const Vec<DIM>& x, float r2, Closes
     hit.d = kMaxFloat;
     hit.prim = -1;
     hit.p = x;
+    ZB_COUNT_DECL
 
     while (sp > 0) {
         uint2 e = stack[--sp];
@@ -306,6 +357,7 @@ ZB_DEV bool closestPoint(const BvhView& bvh, const Vec<DIM>& x, float r2, Closes
                 Vec<DIM> pt;
                 float u, v;
                 float d = prim.closest(x, pt, u, v);
+                ZB_COUNT_PRIM
                 float d2 = d*d;
                 if (d2 <= r2) { // triangles.inl:479: inclusive, later primitives replace equal distances
                     r2 = d2;
@@ -319,6 +371,7 @@ ZB_DEV bool closestPoint(const BvhView& bvh, const Vec<DIM>& x, float r2, Closes
 
         NodeRegs n;
         loadNode(bvh.nodes, e.y, n);
+        ZB_COUNT_NODE
         NodeFrame<DIM> f = nodeFrame<DIM>(n);
         uint32_t keys[8];
 #pragma unroll
@@ -328,7 +381,7 @@ ZB_DEV bool closestPoint(const BvhView& bvh, const Vec<DIM>& x, float r2, Closes
             boxDistance2<DIM>(lo, hi, x, d2min, d2max);
             bool valid = childMeta(n, c) != 0u;
             if (valid) r2 = fminf(r2, d2max);
-            keys[c] = valid ? ((__float_as_uint(d2min) & ~7u) | (uint32_t)c) : 0xffffffffu;
+            keys[c] = valid ? ((zb_float_as_uint(d2min) & ~7u) | (uint32_t)c) : 0xffffffffu;
         }
         sort8(keys);
 #pragma unroll
@@ -336,10 +389,11 @@ ZB_DEV bool closestPoint(const BvhView& bvh, const Vec<DIM>& x, float r2, Closes
             uint32_t key = keys[c];
             if (key != 0xffffffffu && keyValue(key) <= r2) {
                 if (sp < kStackSize) stack[sp++] = make_uint2(key, childRef(n, childMeta(n, key & 7u)));
-                else if (status) atomicOr(status, kStatusStackOverflow);
+                else if (status) zb_atomic_or(status, kStatusStackOverflow);
             }
         }
     }
+    ZB_COUNT_FLUSH(0)
     return hit.prim >= 0;
 }
 
@@ -368,6 +422,7 @@ ZB_DEV bool intersectRay(const BvhView& bvh, const Vec<DIM>& o, const Vec<DIM>& 
     float invD[DIM];
 #pragma unroll
     for (int k = 0; k < DIM; k++) invD[k] = 1.0f/d[k];
+    ZB_COUNT_DECL
 
     while (sp > 0) {
         uint2 e = stack[--sp];
@@ -378,8 +433,9 @@ ZB_DEV bool intersectRay(const BvhView& bvh, const Vec<DIM>& o, const Vec<DIM>& 
                 Prim<DIM> prim;
                 prim.load(bvh, first + i);
                 float t, bv, bw;
+                ZB_COUNT_PRIM
                 if (prim.intersect(o, d, tMax, t, bv, bw)) {
-                    if (ANY_HIT) { hit.prim = (int)(first + i); hit.t = t; return true; }
+                    if (ANY_HIT) { hit.prim = (int)(first + i); hit.t = t; ZB_COUNT_FLUSH(2) return true; }
                     tMax = fminf(tMax, t);
                     hit.t = t; hit.prim = (int)(first + i); hit.bv = bv; hit.bw = bw;
                 }
@@ -389,6 +445,7 @@ ZB_DEV bool intersectRay(const BvhView& bvh, const Vec<DIM>& o, const Vec<DIM>& 
 
         NodeRegs n;
         loadNode(bvh.nodes, e.y, n);
+        ZB_COUNT_NODE
         NodeFrame<DIM> f = nodeFrame<DIM>(n);
         uint32_t keys[8];
 #pragma unroll
@@ -403,7 +460,7 @@ ZB_DEV bool intersectRay(const BvhView& bvh, const Vec<DIM>& o, const Vec<DIM>& 
                 tFar = fminf(tFar, fmaxf(t0, t1));
             }
             bool valid = childMeta(n, c) != 0u && tNear <= tFar;
-            keys[c] = valid ? ((__float_as_uint(tNear) & ~7u) | (uint32_t)c) : 0xffffffffu;
+            keys[c] = valid ? ((zb_float_as_uint(tNear) & ~7u) | (uint32_t)c) : 0xffffffffu;
         }
         sort8(keys);
 #pragma unroll
@@ -411,10 +468,11 @@ ZB_DEV bool intersectRay(const BvhView& bvh, const Vec<DIM>& o, const Vec<DIM>& 
             uint32_t key = keys[c];
             if (key != 0xffffffffu) {
                 if (sp < kStackSize) stack[sp++] = make_uint2(key, childRef(n, childMeta(n, key & 7u)));
-                else if (status) atomicOr(status, kStatusStackOverflow);
+                else if (status) zb_atomic_or(status, kStatusStackOverflow);
             }
         }
     }
+    ZB_COUNT_FLUSH(ANY_HIT ? 2 : 1)
     return hit.prim >= 0;
 }
 
@@ -651,10 +709,10 @@ ZB_DEV void primStarRadius2(const BvhView& bvh, uint32_t primIdx, const Vec<DIM>
     if (closestDist2 > r2) return;
 
     // PrimAdjacency: n[3][3], minCoeff, maxCoeff, flags
-    float4 a0 = __ldg(bvh.adjacency + (size_t)3*primIdx), a1 = __ldg(bvh.adjacency + (size_t)3*primIdx + 1),
-           a2 = __ldg(bvh.adjacency + (size_t)3*primIdx + 2);
+    float4 a0 = zb_ldg(bvh.adjacency + (size_t)3*primIdx), a1 = zb_ldg(bvh.adjacency + (size_t)3*primIdx + 1),
+           a2 = zb_ldg(bvh.adjacency + (size_t)3*primIdx + 2);
     float maxCoeff = a2.z;
-    uint32_t flags = __float_as_uint(a2.w);
+    uint32_t flags = zb_float_as_uint(a2.w);
     if (!(maxCoeff < kMaxFloat - kEpsilon)) { // perfectly absorbing
         r2 = fminf(r2, closestDist2);
         return;
@@ -748,6 +806,49 @@ ZB_DEV bool coneOverlap(const float axis[3], float halfAngle, float radius, cons
     return sum >= kHalfPiF ? true : (kHalfPiF >= minAngle && kHalfPiF <= maxAngle);
 }
 
+// ReflectanceBvh::visitNode (reflectance_boundary_bvh/bvh.h:370-412) for child slot c of a wide node
+// whose box [lo, hi] lies within d2min..d2max of x: bounds [lower, upper] on the squared star radius
+// anything inside the child can produce, and whether a silhouette may hide inside. Returns false when
+// the child cannot shrink the radius at all.
+template <int DIM>
+ZB_DEV bool starChildBounds(const BvhView& bvh, uint32_t nodeIdx, int c, const Vec<DIM>& x, const float lo[DIM], const float hi[DIM],
+                            float d2min, float d2max, float& lower, float& upper, bool& hasSil)
+{
+    float4 c0 = zb_ldg(bvh.cones + ((size_t)nodeIdx*8 + c)*2), c1 = zb_ldg(bvh.cones + ((size_t)nodeIdx*8 + c)*2 + 1);
+    float minCoeff = c1.y, maxCoeff = c1.z;
+    lower = d2min;
+    upper = d2max;
+    hasSil = true;
+    if (minCoeff < kMaxFloat - kEpsilon) {
+        float axis[3] = {c0.x, c0.y, c0.z};
+        float minAngle, maxAngle;
+        if (coneOverlap<DIM>(axis, c0.w, c1.x, x, lo, hi, d2min, minAngle, maxAngle)) {
+            upper = kMaxFloat;
+        } else {
+            hasSil = false;
+            if (!(maxCoeff > kEpsilon)) return false; // perfectly reflecting and no silhouette inside
+            // RobinBvhNodeBound (robin_bounds.h:102-154): radius range over the whole subtree
+            float rMin = sqrtf(d2min), rMax = sqrtf(d2max);
+            float minCos = fminf(fabsf(cosf(minAngle)), fabsf(cosf(maxAngle)));
+            if (DIM == 3) {
+                if (rMax < minCos/maxCoeff) lower = kMaxFloat;
+                else { float rb = rMin/(1.0f - minCos/(maxCoeff*rMax)); lower = rb*rb; }
+                if (rMin < 1.0f/minCoeff) upper = kMaxFloat;
+                else { float rb = rMax/(1.0f - 1.0f/(minCoeff*rMin)); upper = rb*rb; }
+            } else {
+                float rb = rMin*expf(minCos/(maxCoeff*rMax));
+                lower = rb*rb;
+                rb = rMax*expf(1.0f/(minCoeff*rMin));
+                upper = rb*rb;
+            }
+            // keep the pruning bounds conservative under float rounding
+            lower *= 0.9999f;
+            upper *= 1.0001f;
+        }
+    }
+    return true;
+}
+
 // GeometricQueries::computeStarRadiusForReflectingBoundary for both the Neumann and the Robin
 // handler (fcpw_geometric_queries.h:1250-1291): returns the squared radius, <= r2Max.
 template <int DIM>
@@ -756,20 +857,22 @@ ZB_DEV float starRadius2(const BvhView& bvh, const Vec<DIM>& x, float r2, bool f
     uint2 stack[kStackSize];
     int sp = 0;
     stack[sp++] = make_uint2(0u, 0u);
+    ZB_COUNT_DECL
 
     while (sp > 0) {
         uint2 e = stack[--sp];
         // bit 2 of the key marks "no silhouette inside this subtree" (reflectance bvh.h:474-476 sign trick)
         bool silhouetteTests = !(e.x & 4u);
-        if (__uint_as_float(e.x & ~7u) > r2) continue;
+        if (zb_uint_as_float(e.x & ~7u) > r2) continue;
         if (e.y & kLeafFlag) {
             uint32_t first = e.y & 0x0fffffffu, count = (e.y >> 28) & 7u;
-            for (uint32_t i = 0; i < count; i++) primStarRadius2<DIM>(bvh, first + i, x, r2, flip, precision, silhouetteTests);
+            for (uint32_t i = 0; i < count; i++) { ZB_COUNT_PRIM primStarRadius2<DIM>(bvh, first + i, x, r2, flip, precision, silhouetteTests); }
             continue;
         }
 
         NodeRegs n;
         loadNode(bvh.nodes, e.y, n);
+        ZB_COUNT_NODE
         NodeFrame<DIM> f = nodeFrame<DIM>(n);
         uint32_t keys[8];
         uint32_t noSil = 0u;
@@ -782,43 +885,12 @@ ZB_DEV float starRadius2(const BvhView& bvh, const Vec<DIM>& x, float r2, bool f
             childBox<DIM>(n, f, c, lo, hi);
             boxDistance2<DIM>(lo, hi, x, d2min, d2max);
             if (d2min > r2) continue;
-            float4 c0 = __ldg(bvh.cones + ((size_t)e.y*8 + c)*2), c1 = __ldg(bvh.cones + ((size_t)e.y*8 + c)*2 + 1);
-            float minCoeff = c1.y, maxCoeff = c1.z;
-            float lower = d2min, upper = d2max;
-            bool hasSil = true;
-            if (minCoeff < kMaxFloat - kEpsilon) {
-                float axis[3] = {c0.x, c0.y, c0.z};
-                float minAngle, maxAngle;
-                if (coneOverlap<DIM>(axis, c0.w, c1.x, x, lo, hi, d2min, minAngle, maxAngle)) {
-                    upper = kMaxFloat;
-                } else {
-                    hasSil = false;
-                    if (maxCoeff > kEpsilon) {
-                        // RobinBvhNodeBound (robin_bounds.h:102-154): radius range over the whole subtree
-                        float rMin = sqrtf(d2min), rMax = sqrtf(d2max);
-                        float minCos = fminf(fabsf(cosf(minAngle)), fabsf(cosf(maxAngle)));
-                        if (DIM == 3) {
-                            if (rMax < minCos/maxCoeff) lower = kMaxFloat;
-                            else { float rb = rMin/(1.0f - minCos/(maxCoeff*rMax)); lower = rb*rb; }
-                            if (rMin < 1.0f/minCoeff) upper = kMaxFloat;
-                            else { float rb = rMax/(1.0f - 1.0f/(minCoeff*rMin)); upper = rb*rb; }
-                        } else {
-                            float rb = rMin*expf(minCos/(maxCoeff*rMax));
-                            lower = rb*rb;
-                            rb = rMax*expf(1.0f/(minCoeff*rMin));
-                            upper = rb*rb;
-                        }
-                        // keep the pruning bound conservative under float rounding
-                        lower *= 0.9999f;
-                        upper *= 1.0001f;
-                    } else {
-                        continue; // perfectly reflecting and no silhouette: nothing inside can shrink the radius
-                    }
-                }
-            }
+            float lower, upper;
+            bool hasSil;
+            if (!starChildBounds<DIM>(bvh, e.y, c, x, lo, hi, d2min, d2max, lower, upper, hasSil)) continue;
             r2 = fminf(r2, upper);
             if (!hasSil) noSil |= 1u << c;
-            keys[c] = (__float_as_uint(lower) & ~7u) | (uint32_t)c;
+            keys[c] = (zb_float_as_uint(lower) & ~7u) | (uint32_t)c;
         }
         sort8(keys);
 #pragma unroll
@@ -828,10 +900,11 @@ ZB_DEV float starRadius2(const BvhView& bvh, const Vec<DIM>& x, float r2, bool f
                 uint32_t slot = key & 7u;
                 uint32_t tagged = (key & ~7u) | (((noSil >> slot) & 1u) ? 4u : 0u);
                 if (sp < kStackSize) stack[sp++] = make_uint2(tagged, childRef(n, childMeta(n, slot)));
-                else if (status) atomicOr(status, kStatusStackOverflow);
+                else if (status) zb_atomic_or(status, kStatusStackOverflow);
             }
         }
     }
+    ZB_COUNT_FLUSH(4)
     return r2;
 }
 

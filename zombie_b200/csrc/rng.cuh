@@ -39,7 +39,7 @@ struct Pcg32 {
     ZB_HOSTDEV float nextFloat() {
         uint32_t u = (nextUInt() >> 9) | 0x3f800000u;
 #if defined(__CUDA_ARCH__)
-        return __uint_as_float(u) - 1.0f;
+        return zb_uint_as_float(u) - 1.0f;
 #else
         float f;
         memcpy(&f, &u, 4);

@@ -5,8 +5,40 @@
 #include <math.h>
 #include <stdint.h>
 
-#define ZB_DEV __device__ __forceinline__
+// Query and walk code is host+device so that tools/host_probe.cu can single-step the exact device
+// logic on a CPU for debugging and traversal statistics; the shipped library only ever calls it from
+// kernels (there is no CPU execution path behind the C ABI).
+#define ZB_DEV __host__ __device__ __forceinline__
 #define ZB_HOSTDEV __host__ __device__ __forceinline__
+
+#if !defined(__CUDA_ARCH__)
+#include <string.h>
+#include <algorithm>
+// host stand-ins for the device intrinsics used below (compile host code with -ffp-contract=off)
+template <typename T> static inline T zb_ldg(const T *p) { return *p; }
+static inline float zb_uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline uint32_t zb_float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline int zb_float_as_int(float f) { int u; memcpy(&u, &f, 4); return u; }
+static inline float zb_int_as_float(int u) { float f; memcpy(&f, &u, 4); return f; }
+static inline float zb_fmul(float a, float b) { volatile float r = a*b; return r; }
+static inline float zb_fadd(float a, float b) { volatile float r = a + b; return r; }
+static inline float zb_fsub(float a, float b) { volatile float r = a - b; return r; }
+static inline int zb_atomic_or(int *p, int v) { int o = *p; *p |= v; return o; }
+static inline uint32_t zb_umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
+static inline uint32_t zb_umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
+#else
+#define zb_ldg __ldg
+#define zb_uint_as_float __uint_as_float
+#define zb_float_as_uint __float_as_uint
+#define zb_float_as_int __float_as_int
+#define zb_int_as_float __int_as_float
+#define zb_fmul __fmul_rn
+#define zb_fadd __fadd_rn
+#define zb_fsub __fsub_rn
+#define zb_atomic_or atomicOr
+#define zb_umin min
+#define zb_umax max
+#endif
 
 namespace zb {
 

@@ -19,6 +19,7 @@
 
 #include "greens.cuh"
 #include "pde.cuh"
+#include "coop.cuh"
 #include "queries.cuh"
 
 namespace zb {
@@ -128,7 +129,7 @@ ZB_DEV Vec<DIM> offsetPoint(const Vec<DIM>& p, const Vec<DIM>& n)
 #pragma unroll
     for (int k = 0; k < DIM; k++) {
         int nOff = (int)(n[k]*256.0f);
-        float pOff = __int_as_float(__float_as_int(p[k]) + (p[k] < 0.0f ? -nOff : nOff));
+        float pOff = zb_int_as_float(zb_float_as_int(p[k]) + (p[k] < 0.0f ? -nOff : nOff));
         r[k] = fabsf(p[k]) < (1.0f/32.0f) ? p[k] + (1.0f/65536.0f)*n[k] : pOff;
     }
     return r;
@@ -176,6 +177,33 @@ ZB_DEV float starRadiusQuery(const SolveArgs& a, const Vec<DIM>& x, float minRad
     return fmaxf(sqrtf(r2), minRadius);
 }
 
+// the cases of computeStarRadiusForReflectingBoundary that need no traversal; otherwise returns true and
+// the squared search radius to hand to the (cooperative) query
+template <int DIM>
+ZB_DEV bool starQueryNeeded(const SolveArgs& a, float minRadius, float maxRadius, float& trivial, float& r2max)
+{
+    trivial = maxRadius;
+    if (!a.hasReflecting || minRadius > maxRadius) return false;
+    r2max = maxRadius < kMaxFloat ? maxRadius*maxRadius : kMaxFloat;
+    return true;
+}
+
+// result of the query -> radius returned by the reference's lambda (fcpw_geometric_queries.h:1266-1268, 1288-1290)
+ZB_DEV float starQueryResult(const SolveArgs& a, float r2, float r2max, float minRadius, float maxRadius)
+{
+    if (a.reflectingKind == ZB_REFLECTING_NEUMANN && !(r2 < r2max)) return fmaxf(maxRadius, minRadius);
+    return fmaxf(sqrtf(r2), minRadius);
+}
+
+// the 1% shrink the walk applies to a queried star radius (walk_on_stars.h:392-398, 589-594)
+ZB_DEV float shrinkStarRadius(const SolveArgs& a, float r, float distA)
+{
+    if (a.hasReflecting && a.ws.epsilonShellForReflectingBoundary <= distA) {
+        r = fmaxf(0.99f*r, a.ws.epsilonShellForReflectingBoundary);
+    }
+    return r;
+}
+
 // star radius as the walk uses it (walk_on_stars.h:382-398, 577-596): query + 1% shrink
 template <int DIM>
 ZB_DEV float shrunkStarRadius(const SolveArgs& a, const Vec<DIM>& x, float distA, bool flip)
@@ -191,10 +219,8 @@ ZB_DEV float shrunkStarRadius(const SolveArgs& a, const Vec<DIM>& x, float distA
 // 1. task counts
 // ------------------------------------------------------------------------------------------
 template <int DIM>
-__global__ void countTasksKernel(SolveArgs a)
+ZB_DEV void countTasksPoint(const SolveArgs& a, int i)
 {
-    int i = blockIdx.x*blockDim.x + threadIdx.x;
-    if (i >= a.pts.n) return;
     int quantity = a.pts.estimationQuantity[i];
     int type = a.pts.type[i];
     int nWalks = a.pts.nWalks[i];
@@ -214,14 +240,23 @@ __global__ void countTasksKernel(SolveArgs a)
     a.stratCount[i] = strat;
 }
 
+template <int DIM>
+__global__ void countTasksKernel(SolveArgs a)
+{
+    int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i < a.pts.n) countTasksPoint<DIM>(a, i);
+}
+
 // ------------------------------------------------------------------------------------------
 // 2. per-point preparation
 // ------------------------------------------------------------------------------------------
+// Everything of the per-point preparation except a possibly needed star-radius query: returns true
+// when firstSphereRadius[i] still has to be set from a query at the point (with `flip`).
 template <int DIM>
-__global__ void preparePointsKernel(SolveArgs a)
+ZB_DEV bool preparePointNoQuery(const SolveArgs& a, int i, bool& flip)
 {
-    int i = blockIdx.x*blockDim.x + threadIdx.x;
-    if (i >= a.pts.n) return;
+    bool needStar = false;
+    flip = false;
     int quantity = a.pts.estimationQuantity[i];
     Pcg32 rng;
     rng.state = a.pts.rngState[i];
@@ -267,16 +302,50 @@ __global__ void preparePointsKernel(SolveArgs a)
                 if (a.pts.type[i] == ZB_ON_REFLECTING_BOUNDARY && pde.hasNonZeroRobinCoeff()) {
                     radius = a.ws.epsilonShellForReflectingBoundary;
                 } else {
-                    bool flip = a.ws.solveDoubleSided && a.pts.type[i] == ZB_ON_REFLECTING_BOUNDARY &&
-                                a.pts.estimateBoundaryNormalAligned && a.pts.estimateBoundaryNormalAligned[i];
-                    Vec<DIM> x = loadVec<DIM>(a.pts.pt + (size_t)DIM*i);
-                    radius = shrunkStarRadius<DIM>(a, x, distA, flip);
+                    flip = a.ws.solveDoubleSided && a.pts.type[i] == ZB_ON_REFLECTING_BOUNDARY &&
+                           a.pts.estimateBoundaryNormalAligned && a.pts.estimateBoundaryNormalAligned[i];
+                    needStar = true;
+                    radius = distA;
                 }
             }
             a.pts.firstSphereRadius[i] = radius;
         }
     }
     a.pointState[i] = rng.state;
+    return needStar;
+}
+
+// one thread per point, thread-per-query star radius (host probe and debugging)
+template <int DIM>
+ZB_DEV void preparePoint(const SolveArgs& a, int i)
+{
+    bool flip;
+    if (preparePointNoQuery<DIM>(a, i, flip)) {
+        Vec<DIM> x = loadVec<DIM>(a.pts.pt + (size_t)DIM*i);
+        a.pts.firstSphereRadius[i] = shrunkStarRadius<DIM>(a, x, a.pts.distToAbsorbingBoundary[i], flip);
+    }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(128) preparePointsKernel(SolveArgs a)
+{
+#if defined(__CUDA_ARCH__)
+    extern __shared__ __align__(16) unsigned char zbShared[];
+    WarpShared& ws = reinterpret_cast<WarpShared *>(zbShared)[threadIdx.x >> 5];
+    int i = blockIdx.x*blockDim.x + threadIdx.x;
+    bool flip = false, needStar = false;
+    if (i < a.pts.n) needStar = preparePointNoQuery<DIM>(a, i, flip);
+    float eps = a.ws.epsilonShellForReflectingBoundary;
+    float distA = needStar ? a.pts.distToAbsorbingBoundary[i] : 0.0f;
+    float trivial = 0.0f, r2max = 0.0f;
+    bool query = needStar && starQueryNeeded<DIM>(a, eps, distA, trivial, r2max);
+    if (__any_sync(0xffffffffu, query)) {
+        Vec<DIM> x = query ? loadVec<DIM>(a.pts.pt + (size_t)DIM*i) : vzero<DIM>();
+        float r2 = coopStarRadius2<DIM>(a.reflecting, ws, query, x, r2max, !flip, a.ws.silhouettePrecision, a.status);
+        if (query) trivial = starQueryResult(a, r2, r2max, eps, distA);
+    }
+    if (needStar) a.pts.firstSphereRadius[i] = shrinkStarRadius(a, trivial, distA);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -300,6 +369,8 @@ struct Lane {
     int splits;
     int nQueued;
     bool firstStep, flip, outerFlip, success, active, gradient;
+    bool needClosest; // distA / proj must be recomputed at st.pt before the walk continues
+    bool keepDistA;   // ... but only proj is wanted: keep the caller-provided distA (sample point inside the epsilon shell)
 };
 
 template <int DIM>
@@ -338,7 +409,8 @@ ZB_DEV void beginTask(const SolveArgs& a, Lane<DIM>& L, long long task)
     L.st.walkLength = 0;
     L.firstStep = true;
     L.gradient = a.pts.estimationQuantity[i] == ZB_SOLUTION_AND_GRADIENT;
-    int projPrim;
+    L.needClosest = false;
+    L.keepDistA = false;
 
     if (!L.gradient) {
         // estimateSolution (walk_on_spheres.h:354-372; walk_on_stars.h:553-608)
@@ -368,8 +440,9 @@ ZB_DEV void beginTask(const SolveArgs& a, Lane<DIM>& L, long long task)
         L.outerFlip = L.flip;
         L.proj = x;
         if (!(L.distA > a.ws.epsilonShellForAbsorbingBoundary)) {
-            // the walk loop will not run: the terminal projection needs the closest point now
-            distToAbsorbing<DIM>(a, x, L.proj, projPrim);
+            // the walk loop will not run: the terminal projection still needs the closest point
+            L.needClosest = true;
+            L.keepDistA = true;
         }
         return;
     }
@@ -430,7 +503,19 @@ ZB_DEV void beginTask(const SolveArgs& a, Lane<DIM>& L, long long task)
     L.st.throughput *= L.g.poissonKernel()/boundaryPdf;
     L.gradBoundary = L.g.poissonKernelGradient(boundaryPt)/(boundaryPdf*L.st.throughput);
     L.firstSphereRadius = 0.0f;
-    L.distA = distToAbsorbing<DIM>(a, boundaryPt, L.proj, projPrim);
+    L.distA = kMaxFloat;
+    L.needClosest = true;
+}
+
+// thread-per-query resolution of a pending distance query (host probe; the kernel does it cooperatively)
+template <int DIM>
+ZB_DEV void resolveClosest(const SolveArgs& a, Lane<DIM>& L)
+{
+    int projPrim;
+    float d = distToAbsorbing<DIM>(a, L.st.pt, L.proj, projPrim);
+    if (!L.keepDistA) L.distA = d;
+    L.needClosest = false;
+    L.keepDistA = false;
 }
 
 // outcome of one step
@@ -453,7 +538,7 @@ ZB_DEV bool weightWindow(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *queue
         if (L.rng.nextFloat() < left/a.ws.splittingThreshold) copies++;
         for (int c = 0; c < copies; c++) {
             if (L.nQueued < kSplitStack) queue[L.nQueued++] = split;
-            else atomicOr(a.status, kStatusSplitOverflow);
+            else zb_atomic_or(a.status, kStatusSplitOverflow);
         }
     } else if (st.throughput < a.ws.russianRouletteThreshold) {
         float survival = st.throughput/a.ws.russianRouletteThreshold;
@@ -466,14 +551,47 @@ ZB_DEV bool weightWindow(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *queue
     return false;
 }
 
-// one iteration of the while loop of WalkOnStars::walk (walk_on_stars.h:357-487) or
-// WalkOnSpheres::walk (walk_on_spheres.h:237-288)
-template <int DIM, bool WOST>
-ZB_DEV StepResult walkStep(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *queue)
+// Star radius of the coming WoSt step (walk_on_stars.h:359-399). Returns true when a star-radius
+// query at st.pt is needed (r2max = its squared search radius); otherwise starRadius is final.
+template <int DIM>
+ZB_DEV bool stepStarPrologue(const SolveArgs& a, Lane<DIM>& L, float& starRadius, float& r2max)
 {
     PdeEval<DIM> pde{a.pde};
     WalkState<DIM>& st = L.st;
-    if (!(L.distA > a.ws.epsilonShellForAbsorbingBoundary)) return kReached;
+    if (L.firstStep && L.firstSphereRadius > 0.0f) {
+        starRadius = L.firstSphereRadius;
+        return false;
+    }
+    L.flip = false;
+    if (a.ws.solveDoubleSided && st.onRefl) {
+        if (st.prevDist > 0.0f && dot(st.prevDir, st.normal) < 0.0f) {
+            st.normal = -st.normal;
+            L.flip = true;
+        }
+    }
+    if (a.ws.stepsBeforeUsingMaximalSpheres <= st.walkLength) {
+        starRadius = L.distA;
+        return false;
+    }
+    if (st.onRefl && pde.hasNonZeroRobinCoeff()) {
+        starRadius = a.ws.epsilonShellForReflectingBoundary;
+        return false;
+    }
+    if (!starQueryNeeded<DIM>(a, a.ws.epsilonShellForReflectingBoundary, L.distA, starRadius, r2max)) {
+        starRadius = shrinkStarRadius(a, starRadius, L.distA);
+        return false;
+    }
+    return true;
+}
+
+// The rest of one iteration of the while loop of WalkOnStars::walk (walk_on_stars.h:401-487) given the
+// star radius, or the whole iteration of WalkOnSpheres::walk (walk_on_spheres.h:237-288). The distance
+// to the absorbing boundary at the new position is left pending (L.needClosest).
+template <int DIM, bool WOST>
+ZB_DEV StepResult stepBody(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *queue, float starRadius)
+{
+    PdeEval<DIM> pde{a.pde};
+    WalkState<DIM>& st = L.st;
 
     if (!WOST) {
         L.g.updateBall(st.pt, L.distA);
@@ -494,26 +612,6 @@ ZB_DEV StepResult walkStep(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *que
         st.throughput *= L.g.directionSampledPoissonKernel(st.pt);
         if (outsideDomain<DIM>(a, st.pt)) return kEscaped;
     } else {
-        // --- star radius (walk_on_stars.h:359-399)
-        float starRadius;
-        if (L.firstStep && L.firstSphereRadius > 0.0f) {
-            starRadius = L.firstSphereRadius;
-        } else {
-            L.flip = false;
-            if (a.ws.solveDoubleSided && st.onRefl) {
-                if (st.prevDist > 0.0f && dot(st.prevDir, st.normal) < 0.0f) {
-                    st.normal = -st.normal;
-                    L.flip = true;
-                }
-            }
-            if (a.ws.stepsBeforeUsingMaximalSpheres <= st.walkLength) {
-                starRadius = L.distA;
-            } else if (st.onRefl && pde.hasNonZeroRobinCoeff()) {
-                starRadius = a.ws.epsilonShellForReflectingBoundary;
-            } else {
-                starRadius = shrunkStarRadius<DIM>(a, st.pt, L.distA, L.flip);
-            }
-        }
         L.g.updateBall(st.pt, starRadius);
 
         // --- direction, hemispherical on the reflecting boundary (:410-416)
@@ -621,11 +719,25 @@ ZB_DEV StepResult walkStep(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *que
     if (a.pde.absorptionCoeff > 0.0f && a.ws.stepsBeforeApplyingTikhonov == st.walkLength) {
         L.g.init(true, a.pde.absorptionCoeff);
     }
-    int projPrim;
-    L.distA = distToAbsorbing<DIM>(a, st.pt, L.proj, projPrim);
+    L.needClosest = true;
     L.firstStep = false;
     return kContinue;
 }
+
+// thread-per-query version of one whole step (host probe)
+template <int DIM, bool WOST>
+ZB_DEV StepResult walkStep(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *queue)
+{
+    if (L.needClosest) resolveClosest<DIM>(a, L);
+    if (!(L.distA > a.ws.epsilonShellForAbsorbingBoundary)) return kReached;
+    float starRadius = 0.0f, r2max = 0.0f;
+    if (WOST && stepStarPrologue<DIM>(a, L, starRadius, r2max)) {
+        starRadius = shrunkStarRadius<DIM>(a, L.st.pt, L.distA, L.flip);
+    }
+    return stepBody<DIM, WOST>(a, L, queue, starRadius);
+}
+
+
 
 // a walk state finished: fold it into the task total and start a queued split or emit the record
 template <int DIM, bool WOST>
@@ -649,8 +761,9 @@ ZB_DEV void finishState(const SolveArgs& a, Lane<DIM>& L, StepResult code, WalkS
         L.st = queue[--L.nQueued];
         bool yukawa = a.pde.absorptionCoeff > 0.0f && a.ws.stepsBeforeApplyingTikhonov == 0;
         L.g.init(yukawa, a.pde.absorptionCoeff);
-        int projPrim;
-        L.distA = distToAbsorbing<DIM>(a, L.st.pt, L.proj, projPrim);
+        L.distA = kMaxFloat;
+        L.needClosest = true;
+        L.keepDistA = false;
         L.firstSphereRadius = 0.0f;
         L.firstStep = true;
         L.flip = L.outerFlip;
@@ -673,8 +786,13 @@ ZB_DEV void finishState(const SolveArgs& a, Lane<DIM>& L, StepResult code, WalkS
 template <int DIM, bool WOST>
 __global__ void __launch_bounds__(128) walkKernel(SolveArgs a)
 {
+#if defined(__CUDA_ARCH__)
+    extern __shared__ __align__(16) unsigned char zbShared[];
+    WarpShared& ws = reinterpret_cast<WarpShared *>(zbShared)[threadIdx.x >> 5];
     Lane<DIM> L;
     L.active = false;
+    L.needClosest = false;
+    L.keepDistA = false;
     WalkState<DIM> queue[kSplitStack];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -707,11 +825,51 @@ __global__ void __launch_bounds__(128) walkKernel(SolveArgs a)
             if (exhausted) break;
             continue;
         }
-        if (L.active) {
-            StepResult r = walkStep<DIM, WOST>(a, L, queue);
+
+        // ---- pending distance-to-absorbing-boundary queries of the warp, cooperatively
+        bool qc = L.active && L.needClosest;
+        if (__any_sync(full, qc)) {
+            if (a.hasAbsorbing) {
+                ClosestHit<DIM> hit;
+                coopClosestPoint<DIM>(a.absorbing, ws, qc, L.st.pt, kMaxFloat, hit, a.status);
+                if (qc) {
+                    if (!L.keepDistA) L.distA = hit.d;
+                    L.proj = hit.p;
+                    L.needClosest = false;
+                    L.keepDistA = false;
+                }
+            } else if (qc) {
+                resolveClosest<DIM>(a, L);
+            }
+        }
+
+        // ---- walks that arrived inside the epsilon shell (loop condition of walk())
+        if (L.active && !L.needClosest && !(L.distA > a.ws.epsilonShellForAbsorbingBoundary)) {
+            finishState<DIM, WOST>(a, L, kReached, queue);
+        }
+        bool ready = L.active && !L.needClosest;
+
+        // ---- star radii of the warp, cooperatively
+        float starRadius = 0.0f;
+        if (WOST) {
+            float r2max = 0.0f;
+            bool qs = ready && stepStarPrologue<DIM>(a, L, starRadius, r2max);
+            if (__any_sync(full, qs)) {
+                float r2 = coopStarRadius2<DIM>(a.reflecting, ws, qs, L.st.pt, r2max, !L.flip, a.ws.silhouettePrecision, a.status);
+                if (qs) {
+                    float r = starQueryResult(a, r2, r2max, a.ws.epsilonShellForReflectingBoundary, L.distA);
+                    starRadius = shrinkStarRadius(a, r, L.distA);
+                }
+            }
+        }
+
+        // ---- the rest of the step, one thread per walk
+        if (ready) {
+            StepResult r = stepBody<DIM, WOST>(a, L, queue, starRadius);
             if (r != kContinue) finishState<DIM, WOST>(a, L, r, queue);
         }
     }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -818,8 +976,10 @@ __global__ void reducePointsKernel(SolveArgs a)
     int i = blockIdx.x*blockDim.x + threadIdx.x;
     long long stepsTaken = 0; // walk steps of this launch = the metric's numerator (sum of walkLength++)
     if (i < a.pts.n && a.pts.estimationQuantity[i] != ZB_SKIP) stepsTaken = reducePoint<DIM>(a, i);
+#if defined(__CUDA_ARCH__)
     for (int o = 16; o > 0; o >>= 1) stepsTaken += __shfl_down_sync(0xffffffffu, stepsTaken, o);
     if ((threadIdx.x & 31) == 0 && stepsTaken) atomicAdd((unsigned long long *)a.walkSteps, (unsigned long long)stepsTaken);
+#endif
 }
 
 } // namespace zb

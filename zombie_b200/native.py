@@ -11,12 +11,13 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzombie_b200.so")
+LIB_PATH = os.environ.get("ZOMBIE_B200_LIB", os.path.join(_HERE, "libzombie_b200.so"))
 _lib = None
 
 # every symbol include/zombie_b200.h declares
 SYMBOLS = ["zb_last_error", "zb_abi_version", "zb_device_count", "zb_context_create", "zb_context_destroy",
            "zb_context_set_stream", "zb_context_synchronize", "zb_context_device", "zb_context_sm_count",
+           "zb_context_last_solve_profile",
            "zb_scene_create", "zb_scene_destroy", "zb_scene_update_robin_coefficients", "zb_scene_stats",
            "zb_closest_point", "zb_intersect_ray", "zb_occluded", "zb_sample_sphere", "zb_star_radius",
            "zb_solve", "zb_solve_dev", "zb_pcg32_kat"]
@@ -42,6 +43,8 @@ def lib():
         l.zb_context_synchronize.argtypes = [vp]
         l.zb_context_device.argtypes = [vp]
         l.zb_context_sm_count.argtypes = [vp]
+        l.zb_context_last_solve_profile.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                                    C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
         l.zb_scene_create.argtypes = [vp, i, vp, i, vp, i, vp, i, vp, i, i, vp, vp, i, f, i, vp, vp, C.POINTER(vp)]
         l.zb_scene_destroy.argtypes = [vp]
         l.zb_scene_destroy.restype = None
@@ -103,6 +106,14 @@ class Context:
 
     def synchronize(self):
         _check(lib().zb_context_synchronize(self._h), "zb_context_synchronize")
+
+    def last_solve_profile(self):
+        p, w, r = C.c_float(), C.c_float(), C.c_float()
+        walks, grid, launches = C.c_int64(), C.c_int32(), C.c_int64()
+        _check(lib().zb_context_last_solve_profile(self._h, C.byref(p), C.byref(w), C.byref(r), C.byref(walks),
+                                                   C.byref(grid), C.byref(launches)), "zb_context_last_solve_profile")
+        return {"prepare_ms": p.value, "walk_ms": w.value, "reduce_ms": r.value, "walks": walks.value,
+                "walk_grid": grid.value, "launches": launches.value}
 
     def pcg32(self, initstate, initseq, n):
         out = np.zeros(n, np.uint32)
