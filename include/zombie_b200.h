@@ -159,6 +159,13 @@ int zb_scene_update_robin_coefficients(zb_scene *scene, const float *minRobinCoe
 /* bytes of device memory held by the scene's acceleration structures, and node counts */
 int zb_scene_stats(const zb_scene *scene, int boundary, int64_t *bytes, int32_t *nNodes, int32_t *nLeaves, int32_t *maxDepth);
 
+/* Host-only self-check of the acceleration-structure builder (no device needed; used by the CPU tests):
+ * builds the wide quantised hierarchy for the mesh exactly as zb_scene_create does and verifies that every
+ * primitive is referenced once and lies inside the quantised box of every enclosing child slot.
+ * Outputs: node / leaf counts, depth, and the number of violations (0 = sound). */
+int zb_host_bvh_check(int dim, const float *positions, int nVertices, const int32_t *indices, int nPrimitives,
+                      int reflecting, int32_t *nNodes, int32_t *nLeaves, int32_t *maxDepth, int64_t *violations);
+
 /* ---- batched geometric queries (host buffers). These are what the GeometricQueries callbacks
  * bind to; they also expose the primitive index so parity with FCPW can be checked exactly. ---- */
 /* Aggregate::findClosestPoint with BoundingSphere(x, maxR2) (fcpw_geometric_queries.h:1069-1096;
@@ -193,6 +200,14 @@ int zb_solve_dev(zb_scene *scene, int estimator, const zb_pde_desc *pde, const z
 /* pcg32 known-answer hook (deps/pcg32/pcg32.h:53-100): seeds a device generator with
  * (initstate, initseq) and returns n successive nextUInt() values */
 int zb_pcg32_kat(zb_context *ctx, uint64_t initstate, uint64_t initseq, int n, uint32_t *out);
+/* the device generator run through the whole sequence of deps/pcg32/pcg32-demo.cpp:64-104 (per round: 6
+ * nextUInt, 65 nextUInt(2), 33 nextUInt(6)+1, pcg32::shuffle of 52 cards), so that the committed output of
+ * the reference's demo (deps/pcg32/pcg32-demo.out) pins nextUInt(bound) and the shuffle as well.
+ * u32: rounds*6, coins: rounds*65, rolls: rounds*33, cards: rounds*52 */
+int zb_pcg32_demo(zb_context *ctx, uint64_t initstate, uint64_t initseq, int rounds,
+                  uint32_t *u32, uint8_t *coins, uint8_t *rolls, uint8_t *cards);
+/* n successive nextFloat() values (deps/pcg32/pcg32.h:103-112) */
+int zb_pcg32_floats(zb_context *ctx, uint64_t initstate, uint64_t initseq, int n, float *out);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,8 @@ def lib():
         _lib.zref_solve.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_int, C.c_void_p]
         _lib.zref_pcg32.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+        _lib.zref_pcg32_demo.argtypes = [C.c_uint64, C.c_uint64, C.c_int] + [C.c_void_p]*4
+        _lib.zref_pcg32_floats.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
     return _lib
 
 
@@ -52,6 +54,22 @@ def hardware_threads():
 def pcg32(initstate, initseq, n):
     out = np.zeros(n, np.uint32)
     lib().zref_pcg32(initstate, initseq, n, abi.ptr(out))
+    return out
+
+
+def pcg32_demo(initstate, initseq, rounds):
+    """the sequence deps/pcg32/pcg32-demo.cpp prints: (u32 [r,6], coins [r,65], rolls [r,33], cards [r,52])"""
+    u = np.zeros((rounds, 6), np.uint32)
+    coins = np.zeros((rounds, 65), np.uint8)
+    rolls = np.zeros((rounds, 33), np.uint8)
+    cards = np.zeros((rounds, 52), np.uint8)
+    lib().zref_pcg32_demo(initstate, initseq, rounds, abi.ptr(u), abi.ptr(coins), abi.ptr(rolls), abi.ptr(cards))
+    return u, coins, rolls, cards
+
+
+def pcg32_floats(initstate, initseq, n):
+    out = np.zeros(n, np.float32)
+    lib().zref_pcg32_floats(initstate, initseq, n, abi.ptr(out))
     return out
 
 

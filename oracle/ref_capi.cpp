@@ -411,4 +411,27 @@ void zref_pcg32(uint64_t initstate, uint64_t initseq, int n, uint32_t *out)
     for (int i = 0; i < n; i++) out[i] = rng.nextUInt();
 }
 
+// the whole of deps/pcg32/pcg32-demo.cpp:64-104 per round: 6 x nextUInt, 65 x nextUInt(2), 33 x nextUInt(6),
+// shuffle of 52 cards (bounded rejection sampling + Fisher-Yates) — pins nextUInt(bound) and shuffle
+void zref_pcg32_demo(uint64_t initstate, uint64_t initseq, int rounds, uint32_t *u32, uint8_t *coins, uint8_t *rolls, uint8_t *cards)
+{
+    pcg32 rng;
+    rng.seed(initstate, initseq);
+    for (int r = 0; r < rounds; r++) {
+        for (int i = 0; i < 6; i++) u32[6*r + i] = rng.nextUInt();
+        for (int i = 0; i < 65; i++) coins[65*r + i] = (uint8_t)rng.nextUInt(2);
+        for (int i = 0; i < 33; i++) rolls[33*r + i] = (uint8_t)(rng.nextUInt(6) + 1);
+        uint8_t *c = cards + 52*r;
+        for (int i = 0; i < 52; i++) c[i] = (uint8_t)i;
+        rng.shuffle(c, c + 52);
+    }
+}
+
+// nextFloat stream (deps/pcg32/pcg32.h:103-112)
+void zref_pcg32_floats(uint64_t initstate, uint64_t initseq, int n, float *out)
+{
+    pcg32 rng(initstate, initseq);
+    for (int i = 0; i < n; i++) out[i] = rng.nextFloat();
+}
+
 } // extern "C"

@@ -1,0 +1,228 @@
+"""GPU parity tests of the estimators (zb_solve = WalkOnSpheres::solve / WalkOnStars::solve) through the C ABI.
+Per BASELINE.json's north_star the gate is statistical: per-point estimates agree with the reference's CPU
+solver within 3 standard errors (>= 99 % of points; the reference is non-reproducible run to run by design,
+SURVEY.md §8a row R), and both converge to the exact solution at the same RMSE-vs-walk-count rate."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import cases
+from tests.conftest import GOLDEN
+from zombie_b200 import abi, native, procedural as P, workloads
+
+pytestmark = pytest.mark.gpu
+
+
+class Ref:
+    """a golden reference solve (tests/golden/solve_*.npz) dressed as HostStatistics"""
+    def __init__(self, name):
+        g = np.load(os.path.join(GOLDEN, "solve_%s.npz" % name))
+        self.g = g
+        self.solutionMean, self.solutionM2, self.nSolutionEstimates = g["mean"], g["m2"], g["n"]
+        self.gradientMean, self.gradientM2, self.nGradientEstimates = g["gmean"], g["gm2"], g["ngrad"]
+        self.totalWalkLength = g["walkLength"]
+
+    def solution_variance(self):
+        return self.solutionM2/np.maximum(1, self.nSolutionEstimates - 1)
+
+    def gradient_variance(self):
+        return self.gradientM2/np.maximum(1, self.nGradientEstimates - 1)[:, None]
+
+
+GOLDEN_CASES = {
+    "wos3d": dict(dim=3, estimator=abi.WALK_ON_SPHERES, kind=abi.REFLECTING_NONE, pde=lambda: cases.quadratic_pde(), quantity=abi.SOLUTION),
+    "wos2d": dict(dim=2, estimator=abi.WALK_ON_SPHERES, kind=abi.REFLECTING_NONE, pde=lambda: cases.quadratic_pde(dim=2), quantity=abi.SOLUTION),
+    "wost3d_neumann": dict(dim=3, estimator=abi.WALK_ON_STARS, kind=abi.REFLECTING_NEUMANN, pde=lambda: cases.quadratic_pde(), quantity=abi.SOLUTION),
+    "wost3d_robin_grad": dict(dim=3, estimator=abi.WALK_ON_STARS, kind=abi.REFLECTING_ROBIN, pde=lambda: cases.exp_pde(1.0, 1.0)[0],
+                              quantity=abi.SOLUTION_AND_GRADIENT),
+    "wost2d_neumann_window": dict(dim=2, estimator=abi.WALK_ON_STARS, kind=abi.REFLECTING_NEUMANN, pde=lambda: cases.quadratic_pde(dim=2),
+                                  quantity=abi.SOLUTION,
+                                  settings=lambda: abi.WalkSettings.default(russianRouletteThreshold=0.99, splittingThreshold=1.5)),
+}
+
+
+def make_scene(ctx, c):
+    whole, absorbing, reflecting = cases.mesh3d(3) if c["dim"] == 3 else cases.mesh2d(512)
+    if c["kind"] == abi.REFLECTING_NONE:
+        return native.Scene(ctx, c["dim"], absorbing=whole)
+    return native.Scene(ctx, c["dim"], **cases.scene_kwargs(c["dim"], c["kind"], absorbing, reflecting, mu=1.0))
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_CASES))
+def test_estimates_match_reference_golden(ctx, name):
+    c = GOLDEN_CASES[name]
+    r = Ref(name)
+    sc = make_scene(ctx, c)
+    x = r.g["pt"]
+    dr = r.g["distR"] if len(r.g["distR"]) else None
+    # distances to the boundaries computed on the device agree with the ones the reference used
+    _, da, _, _ = sc.closest_point(abi.ABSORBING, x)
+    assert np.allclose(da, r.g["distA"], rtol=1e-6, atol=0)
+    pts = abi.HostSamplePoints(x, da, dr, nWalks=128, estimationQuantity=c["quantity"], seed=0xBEEF)
+    st = abi.HostStatistics(pts.n, c["dim"])
+    settings = c.get("settings", abi.WalkSettings.default)()
+    steps = sc.solve(c["estimator"], c["pde"](), settings, pts, st)
+    assert steps == int(st.totalWalkLength.sum()) and steps > 0
+    assert np.array_equal(st.nSolutionEstimates, r.nSolutionEstimates)
+    z = cases.z_scores(st, r)
+    assert np.mean(np.abs(z) < 3.0) >= 0.985, "only %.4f of the points within 3 standard errors" % np.mean(np.abs(z) < 3.0)
+    assert abs(z.mean()) < 0.25 and 0.8 < z.std() < 1.25, (z.mean(), z.std())
+    # same walk-length distribution (the metric's numerator)
+    assert abs(steps/float(r.g["steps"]) - 1.0) < 0.03
+    # first-sphere radius: same star-radius query, same 1 % shrink
+    assert np.allclose(pts.firstSphereRadius, r.g["firstSphereRadius"], rtol=1e-5, atol=1e-7)
+    if c["quantity"] == abi.SOLUTION_AND_GRADIENT:
+        assert np.array_equal(st.nGradientEstimates, r.nGradientEstimates)
+        se = np.sqrt(st.gradient_variance()/np.maximum(1, st.nGradientEstimates)[:, None] +
+                     r.gradient_variance()/np.maximum(1, r.nGradientEstimates)[:, None])
+        zg = (st.gradientMean - r.gradientMean)/np.maximum(se, 1e-9)
+        assert np.mean(np.abs(zg) < 3.0) >= 0.985
+        assert abs(zg.mean()) < 0.25 and 0.8 < zg.std() < 1.25
+    sc.close()
+
+
+def test_convergence_rate_matches_reference(ctx, ref):
+    """RMSE vs exact solution decays like W^-1/2 with the same constant for both implementations"""
+    w = workloads.config3(subdivisions=4, n_points=1024, n_walks=16)
+    rs = ref.RefScene(3, **w.scene_kwargs())
+    gs = native.Scene(ctx, 3, **w.scene_kwargs())
+    _, da, _, _ = gs.closest_point(abi.ABSORBING, w.points)
+    _, dr, _, _ = gs.closest_point(abi.REFLECTING, w.points)
+    exact = w.exact(w.points)
+    walks = [16, 64, 256]
+    rm = {"gpu": [], "ref": []}
+    for W in walks:
+        for impl, scene in (("gpu", gs), ("ref", rs)):
+            pts = abi.HostSamplePoints(w.points, da, dr, nWalks=W, estimationQuantity=abi.SOLUTION, seed=1000 + W)
+            st = abi.HostStatistics(pts.n, 3)
+            scene.solve(w.estimator, w.pde, w.settings, pts, st)
+            rm[impl].append(float(np.sqrt(np.mean((st.solutionMean - exact)**2))))
+    slope_gpu = np.polyfit(np.log(walks), np.log(rm["gpu"]), 1)[0]
+    slope_ref = np.polyfit(np.log(walks), np.log(rm["ref"]), 1)[0]
+    assert -0.62 < slope_gpu < -0.38 and -0.62 < slope_ref < -0.38, (rm, slope_gpu, slope_ref)
+    for a, b in zip(rm["gpu"], rm["ref"]):
+        assert 0.85 < a/b < 1.18, rm
+    rs.close(); gs.close()
+
+
+def test_gradient_estimates_match_exact(ctx):
+    w = workloads.config3(subdivisions=4, n_points=2048, n_walks=256)
+    gs = native.Scene(ctx, 3, **w.scene_kwargs())
+    _, da, _, _ = gs.closest_point(abi.ABSORBING, w.points)
+    _, dr, _, _ = gs.closest_point(abi.REFLECTING, w.points)
+    pts = abi.HostSamplePoints(w.points, da, dr, nWalks=256, estimationQuantity=abi.SOLUTION_AND_GRADIENT)
+    st = abi.HostStatistics(pts.n, 3)
+    gs.solve(w.estimator, w.pde, w.settings, pts, st)
+    # antithetic pairs: nWalks/2 pairs x 2 estimates
+    assert (st.nSolutionEstimates == 256).all() and (st.nGradientEstimates == 256).all()
+    se = np.sqrt(st.gradient_variance()/st.nGradientEstimates[:, None])
+    zg = (st.gradientMean - w.exact_gradient(w.points))/np.maximum(se, 1e-9)
+    assert np.mean(np.abs(zg) < 3.5) > 0.97 and abs(zg.mean()) < 0.35
+    z = (st.solutionMean - w.exact(w.points))/np.maximum(np.sqrt(st.solution_variance()/st.nSolutionEstimates), 1e-9)
+    assert np.mean(np.abs(z) < 3.5) > 0.97
+    gs.close()
+
+
+def test_progressive_refinement_and_determinism(ctx):
+    """solve() twice on the same points/statistics adds walks (walk_on_stars.h:525,568; common.h:381-386);
+    the same seeds give bit-identical statistics (atomic-free, fixed-order reduction)"""
+    c = GOLDEN_CASES["wost3d_neumann"]
+    sc = make_scene(ctx, c)
+    x = cases.query_points(500, 3, 0.7, seed=77)
+    _, da, _, _ = sc.closest_point(abi.ABSORBING, x)
+    _, dr, _, _ = sc.closest_point(abi.REFLECTING, x)
+    runs = []
+    for rep in range(2):
+        pts = abi.HostSamplePoints(x, da, dr, nWalks=32, estimationQuantity=abi.SOLUTION)
+        st = abi.HostStatistics(pts.n, 3)
+        s1 = sc.solve(c["estimator"], c["pde"](), abi.WalkSettings.default(), pts, st)
+        mean1, state1 = st.solutionMean.copy(), pts.rngState.copy()
+        s2 = sc.solve(c["estimator"], c["pde"](), abi.WalkSettings.default(), pts, st)
+        assert (st.nSolutionEstimates == 64).all()
+        assert int(st.totalWalkLength.sum()) == s1 + s2
+        assert not np.array_equal(mean1, st.solutionMean) and not np.array_equal(state1, pts.rngState)
+        runs.append((mean1, st.solutionMean.copy(), st.solutionM2.copy(), st.totalWalkLength.copy()))
+    for a, b in zip(runs[0], runs[1]):
+        assert np.array_equal(a, b)
+    z = (runs[0][1] - cases.quadratic_exact(x))/np.sqrt(np.maximum(runs[0][2]/63/64, 1e-12))
+    assert np.mean(np.abs(z) < 3.5) > 0.97
+    sc.close()
+
+
+def test_sample_types_and_skip(ctx):
+    """OnAbsorbingBoundary points record pde.dirichlet once (walk_on_stars.h:528-544); Skip leaves the
+    statistics untouched; points inside the epsilon shell take one walk of zero steps"""
+    (pos, tri), _, _ = cases.mesh3d(3)
+    sc = native.Scene(ctx, 3, absorbing=(pos, tri))
+    x = cases.query_points(64, 3, 0.6, seed=5)
+    c = pos[tri[:16]].mean(axis=1)                      # on the boundary
+    allx = np.concatenate([x, c]).astype(np.float32)
+    _, da, _, _ = sc.closest_point(abi.ABSORBING, allx)
+    types = np.array([abi.IN_DOMAIN]*64 + [abi.ON_ABSORBING_BOUNDARY]*16, np.int32)
+    quantity = np.full(80, abi.SOLUTION, np.int32)
+    quantity[:8] = abi.SKIP
+    pts = abi.HostSamplePoints(allx, da, None, nWalks=16, estimationQuantity=quantity, type=types)
+    st = abi.HostStatistics(80, 3)
+    sc.solve(abi.WALK_ON_SPHERES, cases.quadratic_pde(), abi.WalkSettings.default(), pts, st)
+    assert (st.nSolutionEstimates[:8] == 0).all() and (st.solutionMean[:8] == 0).all()
+    assert (st.nSolutionEstimates[8:64] == 16).all()
+    assert (st.nSolutionEstimates[64:] == 1).all() and (st.totalWalkLength[64:] == 0).all()
+    assert np.allclose(st.solutionMean[64:], cases.quadratic_exact(c), atol=1e-6)
+    sc.close()
+
+
+def test_device_resident_solve_matches_host_solve(ctx):
+    """zb_solve_dev on torch tensors == zb_solve on host arrays (same seeds -> identical statistics)"""
+    import torch
+    c = GOLDEN_CASES["wost3d_robin_grad"]
+    sc = make_scene(ctx, c)
+    x = cases.query_points(300, 3, 0.7, seed=9)
+    _, da, _, _ = sc.closest_point(abi.ABSORBING, x)
+    _, dr, _, _ = sc.closest_point(abi.REFLECTING, x)
+    pts = abi.HostSamplePoints(x, da, dr, nWalks=32, estimationQuantity=abi.SOLUTION_AND_GRADIENT)
+    st = abi.HostStatistics(pts.n, 3)
+    hp = abi.HostSamplePoints(x, da, dr, nWalks=32, estimationQuantity=abi.SOLUTION_AND_GRADIENT)
+    hs = abi.HostStatistics(pts.n, 3)
+    steps_host = sc.solve(c["estimator"], c["pde"](), abi.WalkSettings.default(), hp, hs)
+
+    dev = torch.device("cuda", 0)
+    keys_p = ("pt", "normal", "directionForDerivative", "type", "estimationQuantity", "distToAbsorbingBoundary",
+              "distToReflectingBoundary", "estimateBoundaryNormalAligned", "nWalks", "rngState", "rngInc", "firstSphereRadius")
+    keys_s = ("solutionMean", "solutionM2", "gradientMean", "gradientM2", "totalFirstSourceContribution",
+              "totalDerivativeContribution", "nSolutionEstimates", "nGradientEstimates", "totalWalkLength", "totalSplits")
+    t = {}
+    for k in keys_p:
+        a = getattr(pts, k)
+        t[k] = torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a).to(dev)
+    for k in keys_s:
+        t[k] = torch.from_numpy(getattr(st, k)).to(dev)
+    steps = torch.zeros(1, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    ps = abi.SamplePoints(pts.n, *[t[k].data_ptr() for k in keys_p])
+    ss = abi.Statistics(*[t[k].data_ptr() for k in keys_s])
+    sc.solve_dev(c["estimator"], c["pde"](), abi.WalkSettings.default(), ps, ss, steps.data_ptr())
+    ctx.synchronize()
+    assert int(steps.item()) == steps_host
+    assert np.array_equal(t["solutionMean"].cpu().numpy(), hs.solutionMean)
+    assert np.array_equal(t["gradientMean"].cpu().numpy(), hs.gradientMean)
+    assert np.array_equal(t["totalWalkLength"].cpu().numpy(), hs.totalWalkLength)
+    sc.close()
+
+
+def test_2d_demo_like_config(ctx):
+    """BASELINE configs[0] and configs[1] at reduced grid: 2D WoS Dirichlet and 2D WoSt mixed with the demo's
+    weight window, against the exact solutions"""
+    for w in (workloads.config1(1024, 24, 128), workloads.config2(1024, 24, 256)):
+        sc = native.Scene(ctx, 2, **w.scene_kwargs())
+        _, da, _, _ = sc.closest_point(abi.ABSORBING, w.points)
+        dr = None
+        if w.reflecting is not None:
+            _, dr, _, _ = sc.closest_point(abi.REFLECTING, w.points)
+        pts = abi.HostSamplePoints(w.points, da, dr, nWalks=w.n_walks, estimationQuantity=w.quantity)
+        st = abi.HostStatistics(pts.n, 2)
+        sc.solve(w.estimator, w.pde, w.settings, pts, st)
+        se = np.sqrt(st.solution_variance()/np.maximum(1, st.nSolutionEstimates))
+        z = (st.solutionMean - w.exact(w.points))/np.maximum(se, 1e-4)
+        assert np.mean(np.abs(z) < 4.0) > 0.96, (w.name, np.mean(np.abs(z) < 4.0), z.mean())
+        sc.close()

@@ -1,0 +1,79 @@
+"""CPU test (gloo, world_size 2) of the multi-GPU path's host logic: interleaved sharding of the evaluation
+points + gather of the per-point statistics reproduces the single-process result exactly. The per-shard solver
+here is the test oracle (the compiled reference) because there is no GPU in this container; on the GPU box the
+same sharding code drives zb_solve on each rank (bench.py --gpus N)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tests import cases
+from zombie_b200 import abi, sharding
+
+
+def test_shards_partition_the_points():
+    for n, world in ((10, 1), (10, 3), (1 << 20, 8), (7, 8)):
+        allidx = np.concatenate([sharding.shard_indices(n, r, world) for r in range(world)])
+        assert sorted(allidx.tolist()) == list(range(n))
+        assert max(len(sharding.shard_indices(n, r, world)) for r in range(world)) == sharding.shard_size(n, world)
+
+
+def test_pack_unpack_roundtrip():
+    st = abi.HostStatistics(5, 3)
+    rng = np.random.RandomState(0)
+    for k in sharding.STAT_FLOAT_KEYS:
+        getattr(st, k)[...] = rng.normal(size=getattr(st, k).shape)
+    for k in sharding.STAT_INT_KEYS:
+        getattr(st, k)[...] = rng.randint(0, 100, size=5)
+    fp, ip = sharding.pack_statistics(st, 8)
+    back = sharding.unpack_statistics(fp, ip, 5, 3)
+    for k in sharding.STAT_FLOAT_KEYS + sharding.STAT_INT_KEYS:
+        assert np.array_equal(getattr(st, k), getattr(back, k))
+
+
+def _solve(points, idx, n_walks):
+    from oracle import ref
+    (pos, tri), absorbing, reflecting = cases.mesh3d(2)
+    rs = ref.RefScene(3, **cases.scene_kwargs(3, abi.REFLECTING_NEUMANN, absorbing, reflecting))
+    x = points[idx]
+    _, da, _, _ = rs.closest_point(abi.ABSORBING, x)
+    _, dr, _, _ = rs.closest_point(abi.REFLECTING, x)
+    pts = abi.HostSamplePoints(x, da, dr, nWalks=n_walks, estimationQuantity=abi.SOLUTION, streams=idx.astype(np.uint64))
+    st = abi.HostStatistics(len(idx), 3)
+    rs.solve(abi.WALK_ON_STARS, cases.quadratic_pde(), abi.WalkSettings.default(), pts, st, threads=1)
+    return st
+
+
+def _worker(rank, world, port, n, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    points = cases.query_points(n, 3, 0.7, seed=3)
+    idx = sharding.shard_indices(n, rank, world)
+    st = _solve(points, idx, 8)
+    full = sharding.gather_statistics(st, n, 3, rank, world, device="cpu")
+    if rank == 0:
+        np.savez(out, mean=full.solutionMean, m2=full.solutionM2, n=full.nSolutionEstimates, wl=full.totalWalkLength)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_solve_equals_single_process(ref, tmp_path):
+    n = 101   # ragged: the shards have 51 and 50 points
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path/"gathered.npz")
+    mp.spawn(_worker, args=(2, port, n, out), nprocs=2, join=True)
+    g = np.load(out)
+    points = cases.query_points(n, 3, 0.7, seed=3)
+    single = _solve(points, np.arange(n, dtype=np.int64), 8)
+    assert np.array_equal(g["mean"], single.solutionMean)
+    assert np.array_equal(g["m2"], single.solutionM2)
+    assert np.array_equal(g["n"], single.nSolutionEstimates)
+    assert np.array_equal(g["wl"], single.totalWalkLength)

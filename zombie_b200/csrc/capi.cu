@@ -238,6 +238,33 @@ __global__ void pcg32Kernel(uint64_t initstate, uint64_t initseq, int n, uint32_
     }
 }
 
+__global__ void pcg32DemoKernel(uint64_t initstate, uint64_t initseq, int rounds, uint32_t *u32, uint8_t *coins, uint8_t *rolls, uint8_t *cards)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    Pcg32 rng;
+    rng.seed(initstate, initseq);
+    for (int r = 0; r < rounds; r++) {
+        for (int i = 0; i < 6; i++) u32[6*r + i] = rng.nextUInt();
+        for (int i = 0; i < 65; i++) coins[65*r + i] = (uint8_t)rng.nextUInt(2u);
+        for (int i = 0; i < 33; i++) rolls[33*r + i] = (uint8_t)(rng.nextUInt(6u) + 1u);
+        uint8_t *c = cards + 52*r;
+        for (int i = 0; i < 52; i++) c[i] = (uint8_t)i;
+        // pcg32::shuffle (deps/pcg32/pcg32.h:169-172)
+        for (int it = 51; it > 0; it--) {
+            uint32_t j = rng.nextUInt((uint32_t)(it + 1));
+            uint8_t t = c[it]; c[it] = c[j]; c[j] = t;
+        }
+    }
+}
+
+__global__ void pcg32FloatKernel(uint64_t initstate, uint64_t initseq, int n, float *out)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    Pcg32 rng;
+    rng.seed(initstate, initseq);
+    for (int i = 0; i < n; i++) out[i] = rng.nextFloat();
+}
+
 // carves typed device sub-buffers out of one allocation
 struct Carver {
     char *base;
@@ -598,6 +625,22 @@ int zb_scene_stats(const zb_scene *scene, int boundary, int64_t *bytes, int32_t 
     return ZB_OK;
 }
 
+int zb_host_bvh_check(int dim, const float *positions, int nVertices, const int32_t *indices, int nPrimitives,
+                      int reflecting, int32_t *nNodes, int32_t *nLeaves, int32_t *maxDepth, int64_t *violations)
+{
+    HostBvh h;
+    ReflectingOptions opt;
+    opt.enabled = reflecting != 0;
+    const char *err = nullptr;
+    if (!buildWideBvh(dim, positions, nVertices, indices, nPrimitives, opt, h, &err))
+        return fail(ZB_ERR_INVALID_ARGUMENT, std::string("zb_host_bvh_check: ") + (err ? err : "?"));
+    if (nNodes) *nNodes = (int32_t)h.nodes.size();
+    if (nLeaves) *nLeaves = h.nLeaves;
+    if (maxDepth) *maxDepth = h.maxDepth;
+    if (violations) *violations = validateWideBvh(h, dim, positions, indices);
+    return ZB_OK;
+}
+
 #define ZB_QUERY_PROLOGUE(name)                                                                         \
     if (!scene) return fail(ZB_ERR_INVALID_ARGUMENT, name ": scene is NULL");                          \
     if (n < 0) return fail(ZB_ERR_INVALID_ARGUMENT, name ": n < 0");                                   \
@@ -867,6 +910,37 @@ int zb_pcg32_kat(zb_context *ctx, uint64_t initstate, uint64_t initseq, int n, u
     ZB_CUDA(cudaMemcpyAsync(out, ctx->io.ptr, sizeof(uint32_t)*(size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     ZB_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZB_OK;
+}
+
+int zb_pcg32_demo(zb_context *ctx, uint64_t initstate, uint64_t initseq, int rounds,
+                  uint32_t *u32, uint8_t *coins, uint8_t *rolls, uint8_t *cards)
+{
+    if (!ctx || !u32 || !coins || !rolls || !cards || rounds < 0) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_pcg32_demo: invalid argument");
+    if (rounds == 0) return ZB_OK;
+    ZB_CUDA(cudaSetDevice(ctx->device));
+    IoPlan plan;
+    size_t oU = plan.addOut(u32, sizeof(uint32_t)*6*(size_t)rounds), oC = plan.addOut(coins, 65*(size_t)rounds),
+           oR = plan.addOut(rolls, 33*(size_t)rounds), oK = plan.addOut(cards, 52*(size_t)rounds);
+    int rc = stageIn(ctx, plan);
+    if (rc != ZB_OK) return rc;
+    pcg32DemoKernel<<<1, 32, 0, ctx->stream>>>(initstate, initseq, rounds, at<uint32_t>(ctx, oU, u32), at<uint8_t>(ctx, oC, coins),
+                                               at<uint8_t>(ctx, oR, rolls), at<uint8_t>(ctx, oK, cards));
+    ZB_CUDA(cudaGetLastError());
+    return stageOut(ctx, plan);
+}
+
+int zb_pcg32_floats(zb_context *ctx, uint64_t initstate, uint64_t initseq, int n, float *out)
+{
+    if (!ctx || !out || n < 0) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_pcg32_floats: invalid argument");
+    if (n == 0) return ZB_OK;
+    ZB_CUDA(cudaSetDevice(ctx->device));
+    IoPlan plan;
+    size_t o = plan.addOut(out, sizeof(float)*(size_t)n);
+    int rc = stageIn(ctx, plan);
+    if (rc != ZB_OK) return rc;
+    pcg32FloatKernel<<<1, 32, 0, ctx->stream>>>(initstate, initseq, n, at<float>(ctx, o, out));
+    ZB_CUDA(cudaGetLastError());
+    return stageOut(ctx, plan);
 }
 
 } // extern "C"

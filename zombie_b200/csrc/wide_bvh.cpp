@@ -558,6 +558,65 @@ bool buildWideBvh(int dim, const float *positions, int nV, const int32_t *indice
     return true;
 }
 
+long long validateWideBvh(const HostBvh& bvh, int dim, const float *positions, const int32_t *indices)
+{
+    long long bad = 0;
+    std::vector<int> seen(bvh.nPrims, 0);
+    std::vector<int> parentCount(bvh.nodes.size(), 0);
+    // boxes of all ancestors' child slots on the path to a node: checked top-down with an explicit stack
+    struct Item { uint32_t node; std::vector<float> boxes; }; // boxes: 6 floats per enclosing slot
+    std::vector<Item> stack;
+    stack.push_back({0u, {}});
+    while (!stack.empty()) {
+        Item it = std::move(stack.back());
+        stack.pop_back();
+        const WideNode& wn = bvh.nodes[it.node];
+        const uint8_t *meta = reinterpret_cast<const uint8_t *>(&wn.w[6]);
+        int nInternal = 0;
+        for (int c = 0; c < kWidth; c++) {
+            uint8_t m = meta[c];
+            if (m == 0) continue;
+            float lo[3], hi[3];
+            decodeChildBox(wn, c, lo, hi);
+            std::vector<float> boxes = it.boxes;
+            boxes.insert(boxes.end(), lo, lo + 3);
+            boxes.insert(boxes.end(), hi, hi + 3);
+            int count = m >> 5;
+            if (count > 0) {
+                if (count > kMaxLeafSize) bad++;
+                int first = (int)wn.w[5] + (m & 31);
+                for (int i = 0; i < count; i++) {
+                    int slot = first + i;
+                    if (slot < 0 || slot >= bvh.nPrims) { bad++; continue; }
+                    seen[slot]++;
+                    int p = bvh.primIndex[slot];
+                    for (int v = 0; v < dim; v++) {
+                        const float *q = positions + (size_t)dim*indices[(size_t)dim*p + v];
+                        for (size_t b = 0; b < boxes.size(); b += 6) {
+                            for (int k = 0; k < dim; k++) {
+                                if (q[k] < boxes[b + k] || q[k] > boxes[b + 3 + k]) bad++;
+                            }
+                        }
+                        // the de-indexed copy the device reads must be the caller's vertex
+                        const float *pf = &bvh.prims[(size_t)(dim == 3 ? 12 : 4)*slot + (dim == 3 ? 4*v : 2*v)];
+                        for (int k = 0; k < dim; k++) if (pf[k] != q[k]) bad++;
+                    }
+                }
+            } else {
+                uint32_t child = wn.w[4] + (m & 31) - 1;
+                if ((m & 31) - 1 != nInternal) bad++; // internal children are ranked in slot order
+                nInternal++;
+                if (child >= bvh.nodes.size() || child <= it.node) { bad++; continue; }
+                parentCount[child]++;
+                stack.push_back({child, std::move(boxes)});
+            }
+        }
+    }
+    for (int i = 0; i < bvh.nPrims; i++) if (seen[i] != 1) bad++;
+    for (size_t i = 1; i < bvh.nodes.size(); i++) if (parentCount[i] != 1) bad++;
+    return bad;
+}
+
 void updateCoefficients(HostBvh& bvh, const float *minCoeff, const float *maxCoeff)
 {
     if (bvh.adjacency.empty()) return;

@@ -87,6 +87,11 @@ bool buildWideBvh(int dim, const float *positions, int nV, const int32_t *indice
 // (FcpwRobinBoundaryHandler::updateCoefficientValues, fcpw_geometric_queries.h:997-1010).
 void updateCoefficients(HostBvh& bvh, const float *minCoeff, const float *maxCoeff);
 
+// Self-check of a built hierarchy (host only, used by the CPU test-suite): every primitive appears exactly
+// once, lies inside the decoded (quantised) box of every ancestor child slot, internal children are
+// contiguous, leaves hold 1..4 primitives. Returns the number of violations found.
+long long validateWideBvh(const HostBvh& bvh, int dim, const float *positions, const int32_t *indices);
+
 // decodes child `slot` of `node` exactly as the device does
 void decodeChildBox(const WideNode& node, int slot, float lo[3], float hi[3]);
 

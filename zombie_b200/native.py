@@ -18,9 +18,9 @@ _lib = None
 SYMBOLS = ["zb_last_error", "zb_abi_version", "zb_device_count", "zb_context_create", "zb_context_destroy",
            "zb_context_set_stream", "zb_context_synchronize", "zb_context_device", "zb_context_sm_count",
            "zb_context_last_solve_profile",
-           "zb_scene_create", "zb_scene_destroy", "zb_scene_update_robin_coefficients", "zb_scene_stats",
+           "zb_host_bvh_check", "zb_scene_create", "zb_scene_destroy", "zb_scene_update_robin_coefficients", "zb_scene_stats",
            "zb_closest_point", "zb_intersect_ray", "zb_occluded", "zb_sample_sphere", "zb_star_radius",
-           "zb_solve", "zb_solve_dev", "zb_pcg32_kat"]
+           "zb_solve", "zb_solve_dev", "zb_pcg32_kat", "zb_pcg32_demo", "zb_pcg32_floats"]
 
 
 class ZombieError(RuntimeError):
@@ -57,7 +57,11 @@ def lib():
         l.zb_star_radius.argtypes = [vp, i, vp, vp, vp, f, vp, vp]
         l.zb_solve.argtypes = [vp, i, vp, vp, vp, vp, vp]
         l.zb_solve_dev.argtypes = [vp, i, vp, vp, vp, vp, vp]
+        l.zb_host_bvh_check.argtypes = [i, vp, i, vp, i, i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                        C.POINTER(C.c_int64)]
         l.zb_pcg32_kat.argtypes = [vp, C.c_uint64, C.c_uint64, i, vp]
+        l.zb_pcg32_demo.argtypes = [vp, C.c_uint64, C.c_uint64, i, vp, vp, vp, vp]
+        l.zb_pcg32_floats.argtypes = [vp, C.c_uint64, C.c_uint64, i, vp]
         _lib = l
     return _lib
 
@@ -73,6 +77,16 @@ def _f32(a):
 
 def device_count():
     return lib().zb_device_count()
+
+
+def host_bvh_check(dim, positions, indices, reflecting=False):
+    """zb_host_bvh_check: builds the wide BVH on the host and validates it (no device needed)."""
+    pos = _f32(positions)
+    idx = np.ascontiguousarray(indices, np.int32)
+    n, l, d, v = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+    _check(lib().zb_host_bvh_check(dim, abi.ptr(pos), len(pos), abi.ptr(idx), len(idx), int(reflecting),
+                                   C.byref(n), C.byref(l), C.byref(d), C.byref(v)), "zb_host_bvh_check")
+    return {"nodes": n.value, "leaves": l.value, "max_depth": d.value, "violations": v.value}
 
 
 class Context:
@@ -118,6 +132,21 @@ class Context:
     def pcg32(self, initstate, initseq, n):
         out = np.zeros(n, np.uint32)
         _check(lib().zb_pcg32_kat(self._h, initstate, initseq, n, abi.ptr(out)), "zb_pcg32_kat")
+        return out
+
+
+    def pcg32_demo(self, initstate, initseq, rounds):
+        u = np.zeros((rounds, 6), np.uint32)
+        coins = np.zeros((rounds, 65), np.uint8)
+        rolls = np.zeros((rounds, 33), np.uint8)
+        cards = np.zeros((rounds, 52), np.uint8)
+        _check(lib().zb_pcg32_demo(self._h, initstate, initseq, rounds, abi.ptr(u), abi.ptr(coins), abi.ptr(rolls),
+                                   abi.ptr(cards)), "zb_pcg32_demo")
+        return u, coins, rolls, cards
+
+    def pcg32_floats(self, initstate, initseq, n):
+        out = np.zeros(n, np.float32)
+        _check(lib().zb_pcg32_floats(self._h, initstate, initseq, n, abi.ptr(out)), "zb_pcg32_floats")
         return out
 
 
