@@ -81,6 +81,23 @@ def make_points(w, idx, dist_a, dist_r, seed_base):
 # ------------------------------------------------------------------------------------------------
 # reference arm: the unmodified reference (oracle/_ref, built from /root/reference by oracle/Makefile)
 # ------------------------------------------------------------------------------------------------
+def ref_solve_sample(scene, w, idx):
+    """one WalkOnStars::solve of the reference (TBB default arena) on the evaluation points idx; (steps, seconds)"""
+    _, da, _, _ = scene.closest_point(abi.ABSORBING, w.points[idx])
+    _, dr, _, _ = scene.closest_point(abi.REFLECTING, w.points[idx])
+    pts = abi.HostSamplePoints(w.points[idx], da, dr, nWalks=w.n_walks, estimationQuantity=w.quantity, streams=idx.astype(np.uint64))
+    st = abi.HostStatistics(len(idx), 3)
+    return scene.solve(w.estimator, w.pde, w.settings, pts, st, threads=0)
+
+
+def ref_sample_size(scene, w, target_s, cap):
+    """number of evaluation points the reference solves in about target_s seconds on this host (pilot run)"""
+    rng = np.random.RandomState(321)
+    n0 = 64
+    _, secs = ref_solve_sample(scene, w, np.sort(rng.choice(len(w.points), n0, replace=False)))
+    return int(min(cap, max(n0, n0*target_s/max(secs, 1e-3))))
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -91,21 +108,19 @@ def run_reference(args, rank, world):
     w = workloads.config3(args.subdiv, args.points, args.walks)
     scene = ref.RefScene(3, **w.scene_kwargs())
     cores = ref.hardware_threads()
-    n = args.ref_points
+    n_runs = args.warmup + args.steps
+    n = args.ref_points or ref_sample_size(scene, w, min(20.0, 150.0/max(1, n_runs)), 16384)
     rng = np.random.RandomState(123)
     total_steps, total_secs = 0, 0.0
-    for s in range(args.warmup + args.steps):
+    for s in range(n_runs):
         idx = np.sort(rng.choice(len(w.points), n, replace=False))
-        _, da, _, _ = scene.closest_point(abi.ABSORBING, w.points[idx])
-        _, dr, _, _ = scene.closest_point(abi.REFLECTING, w.points[idx])
-        pts = abi.HostSamplePoints(w.points[idx], da, dr, nWalks=w.n_walks, estimationQuantity=w.quantity, streams=idx.astype(np.uint64))
-        st = abi.HostStatistics(n, 3)
-        steps, secs = scene.solve(w.estimator, w.pde, w.settings, pts, st, threads=0)
+        steps, secs = ref_solve_sample(scene, w, idx)
         if s >= args.warmup:
             total_steps += steps
             total_secs += secs
     value = total_steps/total_secs
-    sample = "%d random evaluation points x %d walks of the workload per step, TBB default arena" % (n, w.n_walks)
+    sample = ("%d random evaluation points x %d walks of the workload per step, TBB default arena (%d threads), -O3 -DNDEBUG"
+              % (n, w.n_walks, cores))
     print(json.dumps({
         "impl": "reference", "metric": "walk steps/sec", "value": value, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3*total_secs/args.steps, "higher_is_better": True,
@@ -302,13 +317,9 @@ def cpu_baseline(args, w):
     if not ref.available():
         return {"value": None, "unit": "steps/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
     scene = ref.RefScene(3, **w.scene_kwargs())
-    n = args.ref_points
+    n = args.ref_points or ref_sample_size(scene, w, 20.0, 16384)
     idx = np.sort(np.random.RandomState(123).choice(len(w.points), n, replace=False))
-    _, da, _, _ = scene.closest_point(abi.ABSORBING, w.points[idx])
-    _, dr, _, _ = scene.closest_point(abi.REFLECTING, w.points[idx])
-    pts = abi.HostSamplePoints(w.points[idx], da, dr, nWalks=w.n_walks, estimationQuantity=w.quantity, streams=idx.astype(np.uint64))
-    st = abi.HostStatistics(n, 3)
-    steps, secs = scene.solve(w.estimator, w.pde, w.settings, pts, st, threads=0)
+    steps, secs = ref_solve_sample(scene, w, idx)
     return {"value": steps/secs, "unit": "steps/s", "cores": ref.hardware_threads(), "kind": "reference",
             "sample": "%d random evaluation points x %d walks of the workload (%.1f s), TBB default arena, -O3 -DNDEBUG" % (n, w.n_walks, secs)}
 
@@ -323,7 +334,7 @@ def main():
     ap.add_argument("--subdiv", type=int, default=8, help="icosphere subdivisions (8 -> 1,310,720 triangles)")
     ap.add_argument("--points", type=int, default=1 << 20)
     ap.add_argument("--walks", type=int, default=64)
-    ap.add_argument("--ref-points", type=int, default=4096, help="evaluation points per CPU-reference sample")
+    ap.add_argument("--ref-points", type=int, default=0, help="evaluation points per CPU-reference sample (0: sized by a pilot run to about 20 s)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -88,3 +88,46 @@ def test_walk_settings_defaults_match_reference_short_constructor():
     assert s.stepsBeforeApplyingTikhonov == 0 and s.stepsBeforeUsingMaximalSpheres == 77
     assert s.solveDoubleSided == 1 and s.useGradientControlVariates == 1 and s.useGradientAntitheticVariates == 1
     assert s.useCosineSamplingForDerivatives == 0 and s.ignoreSourceContribution == 0 and s.printLogs == 0
+
+
+def test_merge_statistics_equals_one_pass_welford():
+    """sharding.merge_statistics == SampleStatistics::merge (common.h:268-310): merging the Welford states of two
+    batches equals one Welford pass over their concatenation."""
+    from zombie_b200 import abi, sharding
+    rng = np.random.RandomState(5)
+    n, dim = 17, 3
+
+    def welford(samples):  # samples [n, k, ...]
+        st_mean = np.zeros(samples.shape[:1] + samples.shape[2:], np.float64)
+        st_m2 = np.zeros_like(st_mean)
+        for j in range(samples.shape[1]):
+            d = samples[:, j] - st_mean
+            st_mean += d/(j + 1)
+            st_m2 += d*(samples[:, j] - st_mean)
+        return st_mean, st_m2
+
+    def make(sol, grad):
+        st = abi.HostStatistics(n, dim)
+        m, m2 = welford(sol)
+        st.solutionMean, st.solutionM2 = m.astype(np.float32), m2.astype(np.float32)
+        g, g2 = welford(grad)
+        st.gradientMean, st.gradientM2 = g.astype(np.float32), g2.astype(np.float32)
+        st.nSolutionEstimates[:] = sol.shape[1]
+        st.nGradientEstimates[:] = grad.shape[1]
+        st.totalWalkLength[:] = 7*sol.shape[1]
+        return st
+
+    sa, sb = rng.normal(size=(n, 40)), rng.normal(size=(n, 24)) + 0.5
+    ga, gb = rng.normal(size=(n, 40, dim)), rng.normal(size=(n, 24, dim))
+    merged = sharding.merge_statistics(make(sa, ga), make(sb, gb))
+    whole = make(np.concatenate([sa, sb], 1), np.concatenate([ga, gb], 1))
+    assert np.allclose(merged.solutionMean, whole.solutionMean, atol=1e-5)
+    assert np.allclose(merged.solutionM2, whole.solutionM2, rtol=1e-4)
+    assert np.allclose(merged.gradientMean, whole.gradientMean, atol=1e-5)
+    assert np.allclose(merged.gradientM2, whole.gradientM2, rtol=1e-4)
+    assert np.array_equal(merged.nSolutionEstimates, whole.nSolutionEstimates)
+    assert np.array_equal(merged.totalWalkLength, whole.totalWalkLength)
+    # merging an empty batch is the identity
+    empty = abi.HostStatistics(n, dim)
+    same = sharding.merge_statistics(whole, empty)
+    assert np.array_equal(same.solutionMean, whole.solutionMean) and np.array_equal(same.gradientM2, whole.gradientM2)

@@ -69,3 +69,33 @@ def gather_statistics(local_stats, n_total, dim, rank, world, device="cpu"):
         full_f[idx] = of[r, :len(idx)]
         full_i[idx] = oi[r, :len(idx)]
     return unpack_statistics(full_f, full_i, n_total, dim)
+
+
+def merge_statistics(a, b):
+    """SampleStatistics::merge (common.h:268-310), vectorised over points: folds the statistics b of a second,
+    independent batch of walks at the same points (e.g. the walks of each point split across ranks) into a."""
+    def merge_moments(mean_a, m2_a, n_a, mean_b, m2_b, n_b):
+        n = n_a + n_b
+        f1, f2, fn = n_a.astype(np.float32), n_b.astype(np.float32), np.maximum(1, n).astype(np.float32)
+        shape = (-1,) + (1,)*(mean_a.ndim - 1)
+        f1, f2, fn = f1.reshape(shape), f2.reshape(shape), fn.reshape(shape)
+        delta = mean_b - mean_a
+        mean = np.where(f1 == 0, mean_b, mean_a + delta*(f2/fn))
+        m2 = np.where(f1 == 0, m2_b, m2_a + m2_b + delta*delta*(f1*f2/fn))
+        keep = (f2 == 0)
+        return (np.where(keep, mean_a, mean).astype(np.float32), np.where(keep, m2_a, m2).astype(np.float32))
+
+    out = abi.HostStatistics(a.n, a.dim)
+    out.solutionMean, out.solutionM2 = merge_moments(a.solutionMean, a.solutionM2, a.nSolutionEstimates,
+                                                     b.solutionMean, b.solutionM2, b.nSolutionEstimates)
+    out.gradientMean, out.gradientM2 = merge_moments(a.gradientMean, a.gradientM2, a.nGradientEstimates,
+                                                     b.gradientMean, b.gradientM2, b.nGradientEstimates)
+    out.gradientMean = np.ascontiguousarray(out.gradientMean)
+    out.gradientM2 = np.ascontiguousarray(out.gradientM2)
+    out.nSolutionEstimates = a.nSolutionEstimates + b.nSolutionEstimates
+    out.nGradientEstimates = a.nGradientEstimates + b.nGradientEstimates
+    out.totalFirstSourceContribution = a.totalFirstSourceContribution + b.totalFirstSourceContribution
+    out.totalDerivativeContribution = a.totalDerivativeContribution + b.totalDerivativeContribution
+    out.totalWalkLength = a.totalWalkLength + b.totalWalkLength
+    out.totalSplits = a.totalSplits + b.totalSplits
+    return out
