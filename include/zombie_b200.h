@@ -197,6 +197,60 @@ int zb_solve(zb_scene *scene, int estimator, const zb_pde_desc *pde, const zb_wa
 int zb_solve_dev(zb_scene *scene, int estimator, const zb_pde_desc *pde, const zb_walk_settings *settings,
                  const zb_sample_points *pts_dev, zb_statistics *stats_dev, int64_t *walkSteps_dev);
 
+/* ---- Boundary Value Caching: replaces the splat stage of bvc::BoundaryValueCaching
+ * (zombie/variance_reduction/boundary_value_caching.h:371-502, 682-811): every cache sample is splatted onto
+ * every evaluation point with the free-space Green's function of the PDE (Harmonic / Yukawa,
+ * zombie/core/distributions.h:124-321). ------------------------------------------------------------------ */
+/* SoA of the zombie::SamplePoint fields the splat reads (common.h:182-194). type: ZB_ON_ABSORBING_BOUNDARY /
+ * ZB_ON_REFLECTING_BOUNDARY = boundary sample (splatBoundaryData), ZB_IN_DOMAIN = source sample
+ * (splatSourceData, `contribution` = pde.source at the sample). Always host arrays (caches are small). */
+typedef struct zb_bvc_samples {
+    int32_t n;
+    const float *pt;                              /* n*dim */
+    const float *normal;                          /* n*dim */
+    const int32_t *type;                          /* zb_sample_type */
+    const uint8_t *estimateBoundaryNormalAligned; /* or NULL (= false) */
+    const float *pdf;
+    const float *solution;
+    const float *normalDerivative;
+    const float *contribution;
+    const float *robinCoeff;
+} zb_bvc_samples;
+
+/* SoA of bvc::EvaluationPoint (boundary_value_caching.h:18-56). Its five SampleStatistics (absorbing,
+ * absorbing normal-aligned, reflecting, reflecting normal-aligned, source) are kept as (count, sums): a
+ * Welford mean over N estimates is sum/N. bucketCount / bucketSum are in/out, so repeated splats accumulate
+ * like the reference's statistics and shards merge by addition; solution / gradient are outputs. */
+#define ZB_BVC_BUCKETS 5
+typedef struct zb_bvc_eval_points {
+    int32_t n;
+    const float *pt;                       /* n*dim */
+    const int32_t *type;                   /* zb_sample_type */
+    const float *distToAbsorbingBoundary;
+    const float *distToReflectingBoundary;
+    int32_t *bucketCount;                  /* n*5, in/out */
+    float *bucketSum;                      /* n*5*(1+dim): solution, gradient[dim]; in/out */
+    float *solution;                       /* n: EvaluationPoint::getEstimatedSolution (:263-273) */
+    float *gradient;                       /* n*dim: EvaluationPoint::getEstimatedGradient (:276-286) */
+} zb_bvc_eval_points;
+
+/* BoundaryValueCaching::splat(pde, samplePts, radiusClamp, kernelRegularization,
+ * robinCoeffCutoffForNormalDerivative, cutoffDistToAbsorbingBoundary, cutoffDistToReflectingBoundary,
+ * evalPts) (:482-502). absorptionCoeff = pde.absorptionCoeff selects Yukawa (> 0) or harmonic kernels.
+ * 2D Yukawa (modified Bessel functions) is not implemented: ZB_ERR_UNSUPPORTED. pairs (optional) receives the
+ * number of (sample, evaluation point) pairs evaluated. Evaluation-point arrays are host pointers. */
+int zb_bvc_splat(zb_context *ctx, int dim, float absorptionCoeff, const zb_bvc_samples *samples,
+                 float radiusClamp, float kernelRegularization, float robinCoeffCutoffForNormalDerivative,
+                 float cutoffDistToAbsorbingBoundary, float cutoffDistToReflectingBoundary,
+                 zb_bvc_eval_points *evalPts, int64_t *pairs);
+/* same with the evaluation-point arrays resident on the context's device; asynchronous on its stream */
+int zb_bvc_splat_dev(zb_context *ctx, int dim, float absorptionCoeff, const zb_bvc_samples *samples,
+                     float radiusClamp, float kernelRegularization, float robinCoeffCutoffForNormalDerivative,
+                     float cutoffDistToAbsorbingBoundary, float cutoffDistToReflectingBoundary,
+                     zb_bvc_eval_points *evalPts_dev, int64_t *pairs);
+/* CUDA-event duration of the last zb_bvc_splat(_dev) kernel on this context (measurement hook) */
+int zb_context_last_splat_ms(zb_context *ctx, float *ms);
+
 /* pcg32 known-answer hook (deps/pcg32/pcg32.h:53-100): seeds a device generator with
  * (initstate, initseq) and returns n successive nextUInt() values */
 int zb_pcg32_kat(zb_context *ctx, uint64_t initstate, uint64_t initseq, int n, uint32_t *out);

@@ -37,6 +37,7 @@ def lib():
                                           C.c_void_p, C.c_void_p, C.c_int]
         _lib.zref_solve.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_int, C.c_void_p]
+        _lib.zref_bvc_splat.argtypes = [C.c_int, C.c_float, C.c_void_p] + [C.c_float]*5 + [C.c_int] + [C.c_void_p]*9
         _lib.zref_pcg32.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
         _lib.zref_pcg32_demo.argtypes = [C.c_uint64, C.c_uint64, C.c_int] + [C.c_void_p]*4
         _lib.zref_pcg32_floats.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
@@ -71,6 +72,25 @@ def pcg32_floats(initstate, initseq, n):
     out = np.zeros(n, np.float32)
     lib().zref_pcg32_floats(initstate, initseq, n, abi.ptr(out))
     return out
+
+
+def bvc_splat(dim, absorption_coeff, samples, eval_pts, radius_clamp=1e-3, kernel_regularization=0.0,
+              robin_cutoff=abi.FLT_MAX, cutoff_a=0.0, cutoff_r=0.0):
+    """bvc::BoundaryValueCaching::splat of the reference on abi.HostBvcSamples / abi.HostBvcEvalPoints.
+    Returns (solution [n], gradient [n, dim], bucketCount [n, 5], bucketMean [n, 5, 1 + dim], seconds)."""
+    n = eval_pts.n
+    sol = np.zeros(n, np.float32)
+    grad = np.zeros((n, dim), np.float32)
+    cnt = np.zeros((n, 5), np.int32)
+    mean = np.zeros((n, 5, 1 + dim), np.float32)
+    secs = C.c_double(0.0)
+    ss = samples.as_struct()
+    rc = lib().zref_bvc_splat(dim, absorption_coeff, C.byref(ss), radius_clamp, kernel_regularization, robin_cutoff,
+                              cutoff_a, cutoff_r, n, abi.ptr(eval_pts.pt), abi.ptr(eval_pts.type),
+                              abi.ptr(eval_pts.distToAbsorbingBoundary), abi.ptr(eval_pts.distToReflectingBoundary),
+                              abi.ptr(sol), abi.ptr(grad), abi.ptr(cnt), abi.ptr(mean), C.byref(secs))
+    assert rc == 0
+    return sol, grad, cnt, mean, secs.value
 
 
 class RefScene:

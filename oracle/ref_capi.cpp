@@ -14,6 +14,7 @@
 #include <zombie/point_estimation/walk_on_stars.h>
 #include <zombie/utils/fcpw_geometric_queries.h>
 #include <zombie/variance_reduction/kelvin_transform.h>
+#include <zombie/variance_reduction/boundary_value_caching.h>
 #include "oneapi/tbb/global_control.h"
 #include "oneapi/tbb/task_arena.h"
 
@@ -329,6 +330,63 @@ int solve(RefScene<DIM>& s, int estimator, const zb_pde_desc *pdeDesc, const zb_
     return ZB_OK;
 }
 
+// read access to the five protected SampleStatistics of bvc::EvaluationPoint (boundary_value_caching.h:44-51)
+template <size_t DIM>
+struct EvalAccess: public bvc::EvaluationPoint<float, DIM> {
+    using Base = bvc::EvaluationPoint<float, DIM>;
+    static SampleStatistics<float, DIM>& bucket(Base& e, int b) {
+        switch (b) {
+        case 0: return e.*(&EvalAccess::absorbingBoundaryStatistics);
+        case 1: return e.*(&EvalAccess::absorbingBoundaryNormalAlignedStatistics);
+        case 2: return e.*(&EvalAccess::reflectingBoundaryStatistics);
+        case 3: return e.*(&EvalAccess::reflectingBoundaryNormalAlignedStatistics);
+        default: return e.*(&EvalAccess::sourceStatistics);
+        }
+    }
+};
+
+// BoundaryValueCaching::splat(pde, samplePts, ..., evalPts) (boundary_value_caching.h:482-502) on caller-made
+// sample points; the GeometricQueries / WalkOnStars the class holds are not touched by splat
+template <size_t DIM>
+int bvcSplat(float absorptionCoeff, const zb_bvc_samples *s, float radiusClamp, float kernelRegularization,
+             float robinCutoff, float cutoffA, float cutoffR, int nEval, const float *evalPt, const int32_t *evalType,
+             const float *distA, const float *distR, float *solution, float *gradient, int32_t *bucketCount, float *bucketMean)
+{
+    GeometricQueries<DIM> queries;
+    WalkOnStars<float, DIM> wost(queries);
+    bvc::BoundaryValueCaching<float, DIM> cache(queries, wost);
+    PDE<float, DIM> pde;
+    pde.absorptionCoeff = absorptionCoeff;
+
+    std::vector<SamplePoint<float, DIM>> samplePts;
+    for (int i = 0; i < s->n; i++) {
+        SamplePoint<float, DIM> p(toVec<DIM>(s->pt + DIM*i), toVec<DIM>(s->normal + DIM*i), (SampleType)s->type[i],
+                                  EstimationQuantity::Solution, s->pdf[i], 0.0f, 0.0f);
+        p.solution = s->solution[i];
+        p.normalDerivative = s->normalDerivative[i];
+        p.contribution = s->contribution[i];
+        p.robinCoeff = s->robinCoeff[i];
+        p.estimateBoundaryNormalAligned = s->estimateBoundaryNormalAligned && s->estimateBoundaryNormalAligned[i];
+        samplePts.push_back(p);
+    }
+    std::vector<bvc::EvaluationPoint<float, DIM>> evalPts;
+    for (int i = 0; i < nEval; i++) {
+        evalPts.emplace_back(toVec<DIM>(evalPt + DIM*i), Vec<DIM>::Zero(), (SampleType)evalType[i], distA[i], distR[i]);
+    }
+    cache.splat(pde, samplePts, radiusClamp, kernelRegularization, robinCutoff, cutoffA, cutoffR, evalPts);
+    for (int i = 0; i < nEval; i++) {
+        solution[i] = evalPts[i].getEstimatedSolution();
+        for (size_t k = 0; k < DIM; k++) gradient[DIM*i + k] = evalPts[i].getEstimatedGradient((int)k);
+        for (int b = 0; b < 5; b++) {
+            SampleStatistics<float, DIM>& st = EvalAccess<DIM>::bucket(evalPts[i], b);
+            bucketCount[5*i + b] = st.getSolutionEstimateCount();
+            bucketMean[(5*i + b)*(1 + DIM)] = st.getEstimatedSolution();
+            for (size_t k = 0; k < DIM; k++) bucketMean[(5*i + b)*(1 + DIM) + 1 + k] = st.getEstimatedGradient((int)k);
+        }
+    }
+    return 0;
+}
+
 } // namespace
 
 #define DISPATCH(scene, expr2, expr3) \
@@ -432,6 +490,21 @@ void zref_pcg32_floats(uint64_t initstate, uint64_t initseq, int n, float *out)
 {
     pcg32 rng(initstate, initseq);
     for (int i = 0; i < n; i++) out[i] = rng.nextFloat();
+}
+
+// BVC splat through the reference (seconds = time inside the call)
+int zref_bvc_splat(int dim, float absorptionCoeff, const zb_bvc_samples *s, float radiusClamp, float kernelRegularization,
+                   float robinCutoff, float cutoffA, float cutoffR, int nEval, const float *evalPt, const int32_t *evalType,
+                   const float *distA, const float *distR, float *solution, float *gradient, int32_t *bucketCount,
+                   float *bucketMean, double *seconds)
+{
+    auto t0 = std::chrono::steady_clock::now();
+    int rc = dim == 2 ? bvcSplat<2>(absorptionCoeff, s, radiusClamp, kernelRegularization, robinCutoff, cutoffA, cutoffR, nEval,
+                                    evalPt, evalType, distA, distR, solution, gradient, bucketCount, bucketMean)
+                      : bvcSplat<3>(absorptionCoeff, s, radiusClamp, kernelRegularization, robinCutoff, cutoffA, cutoffR, nEval,
+                                    evalPt, evalType, distA, distR, solution, gradient, bucketCount, bucketMean);
+    if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
 }
 
 } // extern "C"

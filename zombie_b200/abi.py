@@ -181,3 +181,67 @@ class HostStatistics:
 
     def mean_walk_length(self):
         return self.totalWalkLength / np.maximum(1, self.nSolutionEstimates)
+
+
+BVC_BUCKETS = 5  # absorbing, absorbing normal-aligned, reflecting, reflecting normal-aligned, source
+
+
+class BvcSamples(C.Structure):
+    """zb_bvc_samples: SoA of the zombie::SamplePoint fields BoundaryValueCaching::splat reads."""
+    _fields_ = [("n", C.c_int32), ("pt", C.c_void_p), ("normal", C.c_void_p), ("type", C.c_void_p),
+                ("estimateBoundaryNormalAligned", C.c_void_p), ("pdf", C.c_void_p), ("solution", C.c_void_p),
+                ("normalDerivative", C.c_void_p), ("contribution", C.c_void_p), ("robinCoeff", C.c_void_p)]
+
+
+class BvcEvalPoints(C.Structure):
+    """zb_bvc_eval_points: SoA of bvc::EvaluationPoint with (count, sums) per statistics bucket."""
+    _fields_ = [("n", C.c_int32), ("pt", C.c_void_p), ("type", C.c_void_p), ("distToAbsorbingBoundary", C.c_void_p),
+                ("distToReflectingBoundary", C.c_void_p), ("bucketCount", C.c_void_p), ("bucketSum", C.c_void_p),
+                ("solution", C.c_void_p), ("gradient", C.c_void_p)]
+
+
+class HostBvcSamples:
+    def __init__(self, pt, normal, type, pdf, solution, normalDerivative, contribution, robinCoeff, aligned=None):
+        self.pt = np.ascontiguousarray(pt, np.float32)
+        self.n, self.dim = self.pt.shape
+        self.normal = np.ascontiguousarray(normal, np.float32)
+        self.type = np.ascontiguousarray(type, np.int32)
+        self.estimateBoundaryNormalAligned = (np.zeros(self.n, np.uint8) if aligned is None
+                                              else np.ascontiguousarray(aligned, np.uint8))
+        self.pdf = np.ascontiguousarray(pdf, np.float32)
+        self.solution = np.ascontiguousarray(solution, np.float32)
+        self.normalDerivative = np.ascontiguousarray(normalDerivative, np.float32)
+        self.contribution = np.ascontiguousarray(contribution, np.float32)
+        self.robinCoeff = np.ascontiguousarray(robinCoeff, np.float32)
+
+    def as_struct(self):
+        return BvcSamples(self.n, ptr(self.pt), ptr(self.normal), ptr(self.type), ptr(self.estimateBoundaryNormalAligned),
+                          ptr(self.pdf), ptr(self.solution), ptr(self.normalDerivative), ptr(self.contribution),
+                          ptr(self.robinCoeff))
+
+    def subset(self, idx):
+        return HostBvcSamples(self.pt[idx], self.normal[idx], self.type[idx], self.pdf[idx], self.solution[idx],
+                              self.normalDerivative[idx], self.contribution[idx], self.robinCoeff[idx],
+                              self.estimateBoundaryNormalAligned[idx])
+
+
+class HostBvcEvalPoints:
+    def __init__(self, pt, distToAbsorbingBoundary, distToReflectingBoundary, type=IN_DOMAIN):
+        self.pt = np.ascontiguousarray(pt, np.float32)
+        self.n, self.dim = self.pt.shape
+        self.type = np.full(self.n, type, np.int32) if np.isscalar(type) else np.ascontiguousarray(type, np.int32)
+        self.distToAbsorbingBoundary = np.ascontiguousarray(distToAbsorbingBoundary, np.float32)
+        self.distToReflectingBoundary = np.ascontiguousarray(distToReflectingBoundary, np.float32)
+        self.bucketCount = np.zeros((self.n, BVC_BUCKETS), np.int32)
+        self.bucketSum = np.zeros((self.n, BVC_BUCKETS, 1 + self.dim), np.float32)
+        self.solution = np.zeros(self.n, np.float32)
+        self.gradient = np.zeros((self.n, self.dim), np.float32)
+
+    def as_struct(self):
+        return BvcEvalPoints(self.n, ptr(self.pt), ptr(self.type), ptr(self.distToAbsorbingBoundary),
+                             ptr(self.distToReflectingBoundary), ptr(self.bucketCount), ptr(self.bucketSum),
+                             ptr(self.solution), ptr(self.gradient))
+
+    def bucket_mean(self):
+        """per-bucket Welford means [n, 5, 1 + dim] (0 where a bucket is empty)"""
+        return self.bucketSum/np.maximum(1, self.bucketCount)[:, :, None]

@@ -1,11 +1,14 @@
 """Builds zombie_b200/libzombie_b200.so (sm_100a only) with nvcc. The library is built in-tree so
-that it travels with the repository snapshot; there is no JIT and no CPU fallback."""
+that it travels with the repository snapshot; there is no JIT and no CPU fallback. Translation units are
+compiled in parallel into zombie_b200/build/*.o and linked; only stale objects are rebuilt."""
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libzombie_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -13,38 +16,60 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 
 
 def _sources():
-    cu = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
-    cpp = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cpp")]
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu") or f.endswith(".cpp")]
     inc = os.path.join(HERE, "..", "include")
-    deps += [os.path.join(inc, "zombie_b200.h"), os.path.join(inc, "zombie_b200", "analytic.h")]
-    return cu, cpp, deps
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh") or f.endswith(".h")]
+    headers += [os.path.join(inc, "zombie_b200.h"), os.path.join(inc, "zombie_b200", "analytic.h"), os.path.abspath(__file__)]
+    return srcs, headers
+
+
+def _obj(src):
+    return os.path.join(OBJ, os.path.basename(src) + ".o")
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
 
 
 def needs_build():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    _, _, deps = _sources()
-    return any(os.path.getmtime(d) > t for d in deps)
+    srcs, headers = _sources()
+    return _stale(LIB, srcs + headers)
 
 
 def build(force=False, verbose=False, extra=()):
     if not force and not needs_build():
         return LIB
-    cu, cpp, _ = _sources()
-    cmd = [NVCC] + ARCH + COMMON + list(extra) + ["-shared", "-o", LIB] + cu + cpp
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd))
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if verbose or r.returncode != 0:
-        sys.stderr.write(r.stdout)
-    if r.returncode != 0:
+    srcs, headers = _sources()
+    os.makedirs(OBJ, exist_ok=True)
+
+    def compile_one(src):
+        obj = _obj(src)
+        if not force and not _stale(obj, [src] + headers):
+            return 0, ""
+        cmd = [NVCC] + ARCH + COMMON + list(extra) + (["-Xptxas=-v"] if verbose else []) + ["-c", src, "-o", obj]
+        if verbose:
+            print(" ".join(cmd))
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        return r.returncode, r.stdout
+
+    with ThreadPoolExecutor(max_workers=max(1, min(len(srcs), os.cpu_count() or 1))) as pool:
+        results = list(pool.map(compile_one, srcs))
+    failed = [out for rc, out in results if rc != 0]
+    if verbose or failed:
+        sys.stderr.write("".join(out for _, out in results))
+    if failed:
         raise RuntimeError("nvcc failed building libzombie_b200.so")
+    r = subprocess.run([NVCC] + ARCH + ["-shared", "-o", LIB] + [_obj(s) for s in srcs], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("linking libzombie_b200.so failed")
     return LIB
 
 
 if __name__ == "__main__":
-    build(force=True, verbose="-v" in sys.argv)
+    build(force="-f" in sys.argv, verbose="-v" in sys.argv)
     print(LIB)

@@ -9,63 +9,17 @@
 #include <vector>
 
 #include "../../include/zombie_b200.h"
+#include "capi_common.h"
 #include "walk.cuh"
 #include "wide_bvh.h"
 
 using namespace zb;
 
 namespace {
-
-thread_local std::string g_lastError;
 // zb_solve knows from the host arrays whether any point asks for gradients and tells zb_solve_dev
 // so that solution-only runs do not allocate gradient records; zb_solve_dev alone assumes they may
 thread_local bool g_gradientHint = true;
-
-int fail(int code, const std::string& msg)
-{
-    g_lastError = msg;
-    return code;
-}
-
-#define ZB_CUDA(expr)                                                                              \
-    do {                                                                                           \
-        cudaError_t err__ = (expr);                                                                \
-        if (err__ != cudaSuccess) {                                                                \
-            return fail(err__ == cudaErrorMemoryAllocation ? ZB_ERR_OUT_OF_MEMORY : ZB_ERR_CUDA,  \
-                        std::string(#expr) + ": " + cudaGetErrorString(err__));                    \
-        }                                                                                          \
-    } while (0)
-
-// grow-only device allocation
-struct DeviceBuffer {
-    void *ptr = nullptr;
-    size_t capacity = 0;
-    ~DeviceBuffer() { if (ptr) cudaFree(ptr); }
-    cudaError_t reserve(size_t bytes) {
-        if (bytes <= capacity) return cudaSuccess;
-        if (ptr) { cudaFree(ptr); ptr = nullptr; capacity = 0; }
-        size_t want = bytes + bytes/8 + 256;
-        cudaError_t e = cudaMalloc(&ptr, want);
-        if (e == cudaSuccess) capacity = want;
-        return e;
-    }
-    template <typename T> T *as() const { return reinterpret_cast<T *>(ptr); }
-};
-
 } // namespace
-
-struct zb_context {
-    int device = 0;
-    int smCount = 0;
-    cudaStream_t stream = nullptr;
-    bool ownsStream = false;
-    DeviceBuffer status, counters, perPoint, strat, records, scanTemp, io;
-    int *hostStatus = nullptr; // pinned
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; // solve start | walk start | walk end | solve end
-    bool profiled = false;
-    long long lastTasks = 0;
-    int lastGrid = 0, launches = 0;
-};
 
 struct DeviceBvhStorage {
     HostBvh host;
@@ -443,7 +397,7 @@ int solveRange(zb_scene *scene, SolveArgs& a, int n, bool anyGradient)
 
 extern "C" {
 
-const char *zb_last_error(void) { return g_lastError.c_str(); }
+const char *zb_last_error(void) { return lastErrorRef().c_str(); }
 int zb_abi_version(void) { return ZB_ABI_VERSION; }
 
 int zb_device_count(void)
@@ -474,6 +428,7 @@ int zb_context_create(int device, zb_context **out)
     ZB_CUDA(cudaMemset(ctx->counters.ptr, 0, 256));
     ZB_CUDA(cudaMallocHost(&ctx->hostStatus, 64));
     for (int k = 0; k < 4; k++) ZB_CUDA(cudaEventCreate(&ctx->ev[k]));
+    for (int k = 0; k < 2; k++) ZB_CUDA(cudaEventCreate(&ctx->evSplat[k]));
     *out = ctx;
     return ZB_OK;
 }
@@ -486,6 +441,7 @@ void zb_context_destroy(zb_context *ctx)
     if (ctx->ownsStream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->hostStatus) cudaFreeHost(ctx->hostStatus);
     for (int k = 0; k < 4; k++) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+    for (int k = 0; k < 2; k++) if (ctx->evSplat[k]) cudaEventDestroy(ctx->evSplat[k]);
     delete ctx;
 }
 

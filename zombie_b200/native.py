@@ -9,6 +9,7 @@ import os
 import numpy as np
 
 from . import abi
+from .abi import FLT_MAX
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ZOMBIE_B200_LIB", os.path.join(_HERE, "libzombie_b200.so"))
@@ -20,7 +21,8 @@ SYMBOLS = ["zb_last_error", "zb_abi_version", "zb_device_count", "zb_context_cre
            "zb_context_last_solve_profile",
            "zb_host_bvh_check", "zb_scene_create", "zb_scene_destroy", "zb_scene_update_robin_coefficients", "zb_scene_stats",
            "zb_closest_point", "zb_intersect_ray", "zb_occluded", "zb_sample_sphere", "zb_star_radius",
-           "zb_solve", "zb_solve_dev", "zb_pcg32_kat", "zb_pcg32_demo", "zb_pcg32_floats"]
+           "zb_solve", "zb_solve_dev", "zb_bvc_splat", "zb_bvc_splat_dev", "zb_context_last_splat_ms",
+           "zb_pcg32_kat", "zb_pcg32_demo", "zb_pcg32_floats"]
 
 
 class ZombieError(RuntimeError):
@@ -59,6 +61,9 @@ def lib():
         l.zb_solve_dev.argtypes = [vp, i, vp, vp, vp, vp, vp]
         l.zb_host_bvh_check.argtypes = [i, vp, i, vp, i, i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                         C.POINTER(C.c_int64)]
+        l.zb_bvc_splat.argtypes = [vp, i, f, vp, f, f, f, f, f, vp, C.POINTER(C.c_int64)]
+        l.zb_bvc_splat_dev.argtypes = [vp, i, f, vp, f, f, f, f, f, vp, C.POINTER(C.c_int64)]
+        l.zb_context_last_splat_ms.argtypes = [vp, C.POINTER(C.c_float)]
         l.zb_pcg32_kat.argtypes = [vp, C.c_uint64, C.c_uint64, i, vp]
         l.zb_pcg32_demo.argtypes = [vp, C.c_uint64, C.c_uint64, i, vp, vp, vp, vp]
         l.zb_pcg32_floats.argtypes = [vp, C.c_uint64, C.c_uint64, i, vp]
@@ -128,6 +133,28 @@ class Context:
                                                    C.byref(grid), C.byref(launches)), "zb_context_last_solve_profile")
         return {"prepare_ms": p.value, "walk_ms": w.value, "reduce_ms": r.value, "walks": walks.value,
                 "walk_grid": grid.value, "launches": launches.value}
+
+    def bvc_splat(self, dim, absorption_coeff, samples, eval_pts, radius_clamp=1e-3, kernel_regularization=0.0,
+                  robin_cutoff=FLT_MAX, cutoff_a=0.0, cutoff_r=0.0, device_eval_struct=None):
+        """BoundaryValueCaching::splat (boundary_value_caching.h:482-502): samples = abi.HostBvcSamples, eval_pts =
+        abi.HostBvcEvalPoints (updated in place). With device_eval_struct (an abi.BvcEvalPoints of device pointers)
+        the evaluation points stay resident on the device. Returns the number of pairs evaluated."""
+        pairs = C.c_int64(0)
+        ss = samples.as_struct()
+        if device_eval_struct is not None:
+            _check(lib().zb_bvc_splat_dev(self._h, dim, absorption_coeff, C.byref(ss), radius_clamp, kernel_regularization,
+                                          robin_cutoff, cutoff_a, cutoff_r, C.byref(device_eval_struct), C.byref(pairs)),
+                   "zb_bvc_splat_dev")
+        else:
+            es = eval_pts.as_struct()
+            _check(lib().zb_bvc_splat(self._h, dim, absorption_coeff, C.byref(ss), radius_clamp, kernel_regularization,
+                                      robin_cutoff, cutoff_a, cutoff_r, C.byref(es), C.byref(pairs)), "zb_bvc_splat")
+        return pairs.value
+
+    def last_splat_ms(self):
+        ms = C.c_float()
+        _check(lib().zb_context_last_splat_ms(self._h, C.byref(ms)), "zb_context_last_splat_ms")
+        return ms.value
 
     def pcg32(self, initstate, initseq, n):
         out = np.zeros(n, np.uint32)
