@@ -15,6 +15,7 @@ BVH is replicated), there is no data-path collective, timing is the max over ran
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -156,13 +157,8 @@ def run_native(args, rank, world, local_rank):
     # boundaries are part of SamplePoint construction in the reference (demo.cpp:9-46) -> setup, untimed
     shard = np.arange(rank, len(w.points), world)
     n_steps = args.warmup + args.steps
-    batch = min(args.batch, len(shard))
     _, dist_a, _, _ = scene.closest_point(abi.ABSORBING, w.points, want_normal=False)
     _, dist_r, _, _ = scene.closest_point(abi.REFLECTING, w.points, want_normal=False)
-
-    def batch_indices(s):
-        start = (s*batch) % max(1, len(shard) - batch + 1)
-        return shard[start:start + batch]
 
     def to_dev(a):
         return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
@@ -172,28 +168,53 @@ def run_native(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident arm --------------------------------------------------------------------
-    dev_steps = []
-    for s in range(n_steps):
-        hp = make_points(w, batch_indices(s), dist_a, dist_r, 0)
+    STAT_KEYS = ("solutionMean", "solutionM2", "gradientMean", "gradientM2", "totalFirstSourceContribution",
+                 "totalDerivativeContribution", "nSolutionEstimates", "nGradientEstimates", "totalWalkLength", "totalSplits")
+    POINT_KEYS = ("pt", "normal", "directionForDerivative", "type", "estimationQuantity", "distToAbsorbingBoundary",
+                  "distToReflectingBoundary", "estimateBoundaryNormalAligned", "nWalks", "rngState", "rngInc", "firstSphereRadius")
+
+    def device_set(idx, seed_base):
+        hp = make_points(w, idx, dist_a, dist_r, seed_base)
         hs = abi.HostStatistics(hp.n, 3)
         tensors = {}
-        for k in ("pt", "normal", "directionForDerivative", "type", "estimationQuantity", "distToAbsorbingBoundary",
-                  "distToReflectingBoundary", "estimateBoundaryNormalAligned", "nWalks", "firstSphereRadius"):
-            tensors[k] = to_dev(getattr(hp, k))
-        tensors["rngState"] = to_dev(hp.rngState.view(np.int64))
-        tensors["rngInc"] = to_dev(hp.rngInc.view(np.int64))
-        for k in ("solutionMean", "solutionM2", "gradientMean", "gradientM2", "totalFirstSourceContribution",
-                  "totalDerivativeContribution", "nSolutionEstimates", "nGradientEstimates", "totalWalkLength", "totalSplits"):
+        for k in POINT_KEYS:
+            a = getattr(hp, k)
+            tensors[k] = to_dev(a.view(np.int64) if a.dtype == np.uint64 else a)
+        for k in STAT_KEYS:
             tensors[k] = to_dev(getattr(hs, k))
         tensors["steps"] = torch.zeros(1, dtype=torch.int64, device=dev)
-        ps = abi.SamplePoints(hp.n, *[tensors[k].data_ptr() for k in (
-            "pt", "normal", "directionForDerivative", "type", "estimationQuantity", "distToAbsorbingBoundary",
-            "distToReflectingBoundary", "estimateBoundaryNormalAligned", "nWalks", "rngState", "rngInc", "firstSphereRadius")])
-        ss = abi.Statistics(*[tensors[k].data_ptr() for k in (
-            "solutionMean", "solutionM2", "gradientMean", "gradientM2", "totalFirstSourceContribution",
-            "totalDerivativeContribution", "nSolutionEstimates", "nGradientEstimates", "totalWalkLength", "totalSplits")])
-        dev_steps.append((ps, ss, tensors))
+        ps = abi.SamplePoints(hp.n, *[tensors[k].data_ptr() for k in POINT_KEYS])
+        ss = abi.Statistics(*[tensors[k].data_ptr() for k in STAT_KEYS])
+        return ps, ss, tensors
+
+    # ---- batch size: the points one step solves. --batch 0 sizes it with a pilot solve so that a step takes
+    # about --step-seconds on this device (the persistent walk kernel wants >> 1 walk per lane, but the default
+    # run has to end within minutes whatever the kernel's speed)
+    batch = args.batch
+    pilot = None
+    if batch <= 0:
+        n_pilot = min(2048, len(shard))
+        ps, ss, tensors = device_set(shard[-n_pilot:], 7 << 40)
+        t0 = time.perf_counter()
+        scene.solve_dev(w.estimator, w.pde, w.settings, ps, ss, tensors["steps"].data_ptr())
+        torch.cuda.synchronize()
+        pilot_s = time.perf_counter() - t0
+        per_point_s = pilot_s/n_pilot
+        batch = int(args.step_seconds/max(per_point_s, 1e-9))
+        batch = 1 << max(11, min(16, int(math.floor(math.log2(max(batch, 1))))))
+        pilot = {"points": n_pilot, "seconds": pilot_s}
+    if dist is not None:  # every rank must use the same batch
+        t = torch.tensor([batch], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        batch = int(t.item())
+    batch = min(batch, len(shard))
+
+    def batch_indices(s):
+        start = (s*batch) % max(1, len(shard) - batch + 1)
+        return shard[start:start + batch]
+
+    # ---- device-resident arm --------------------------------------------------------------------
+    dev_steps = [device_set(batch_indices(s), 0) for s in range(n_steps)]
 
     def run_dev(s):
         ps, ss, tensors = dev_steps[s]
@@ -206,30 +227,23 @@ def run_native(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    walk_ms, walk_tasks = 0.0, 0
+    walk_ms, walk_tasks, grid = 0.0, 0, 0
     ev0.record(stream)
     for s in range(args.warmup, n_steps):
         run_dev(s)
+        # the library brackets the walk kernel of every solve with CUDA events on the launching stream; reading
+        # them costs nothing here because zb_solve_dev has already waited for the solve's task count
+        prof = ctx.last_solve_profile()
+        walk_ms += prof["walk_ms"]
+        walk_tasks += prof["walks"]
+        grid = prof["walk_grid"]
     ev1.record(stream)
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     clocks = sampler.summary()
     launches_timed = ctx.last_solve_profile()["launches"] - launches_before
     steps_dev = int(sum(int(dev_steps[s][2]["steps"].item()) for s in range(args.warmup, n_steps)))
-
-    # kernel time of the dominant (walk) kernel, measured live with CUDA events on the launching stream:
-    # the library brackets every walk-kernel launch; read it for one extra pass per timed step
-    prof_steps = 0
-    for s in range(args.warmup, n_steps):
-        for k in ("solutionMean", "solutionM2", "gradientMean", "gradientM2", "totalFirstSourceContribution",
-                  "totalDerivativeContribution", "nSolutionEstimates", "nGradientEstimates", "totalWalkLength", "totalSplits"):
-            dev_steps[s][2][k].zero_()
-        run_dev(s)
-        prof = ctx.last_solve_profile()
-        walk_ms += prof["walk_ms"]
-        walk_tasks += prof["walks"]
-        prof_steps += int(dev_steps[s][2]["steps"].item())
-    grid = ctx.last_solve_profile()["walk_grid"]
+    prof_steps, local_walk_ms = steps_dev, walk_ms  # this rank's kernel: its steps / its kernel time
 
     # ---- end-to-end arm: host buffers through zb_solve --------------------------------------------
     host_sets = []
@@ -283,13 +297,13 @@ def run_native(args, rank, world, local_rank):
         peak, peak_kind = measured_peaks()
         bytes_per_step = w.algorithmic_bytes_per_step()
         # per-rank kernel: this rank's steps / this rank's kernel time
-        achieved = prof_steps*bytes_per_step/(walk_ms*1e-3)/1e9 if walk_ms > 0 else 0.0
+        achieved = prof_steps*bytes_per_step/(local_walk_ms*1e-3)/1e9 if local_walk_ms > 0 else 0.0
         value = steps_dev/(dev_ms*1e-3)
         line = {
             "metric": "walk steps/sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms/args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": w.name, "points_per_step_per_gpu": batch, "walks_per_point": w.n_walks,
+            "config": {"workload": w.name, "points_per_step_per_gpu": batch, "batch_pilot": pilot, "walks_per_point": w.n_walks,
                        "sharding": "evaluation points interleaved over ranks, BVH replicated, no data-path collective",
                        "l2": "inputs larger than L2: BVH %.0f MB + %.0f MB of per-walk records per step"
                              % ((scene.stats(0)["bytes"] + scene.stats(1)["bytes"])/1e6, walk_tasks/max(1, args.steps)*40/1e6),
@@ -327,10 +341,11 @@ def cpu_baseline(args, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--batch", type=int, default=65536, help="evaluation points per step per GPU")
+    ap.add_argument("--batch", type=int, default=0, help="evaluation points per step per GPU (0: sized by a pilot solve)")
+    ap.add_argument("--step-seconds", type=float, default=1.5, help="target duration of one step when --batch is 0")
     ap.add_argument("--subdiv", type=int, default=8, help="icosphere subdivisions (8 -> 1,310,720 triangles)")
     ap.add_argument("--points", type=int, default=1 << 20)
     ap.add_argument("--walks", type=int, default=64)

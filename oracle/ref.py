@@ -38,6 +38,9 @@ def lib():
         _lib.zref_solve.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_int, C.c_void_p]
         _lib.zref_bvc_splat.argtypes = [C.c_int, C.c_float, C.c_void_p] + [C.c_float]*5 + [C.c_int] + [C.c_void_p]*9
+        _lib.zref_kelvin_transform_points.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        _lib.zref_kelvin_robin_coefficients.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p]*5
+        _lib.zref_kelvin_back_transform.argtypes = [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p]*5
         _lib.zref_pcg32.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
         _lib.zref_pcg32_demo.argtypes = [C.c_uint64, C.c_uint64, C.c_int] + [C.c_void_p]*4
         _lib.zref_pcg32_floats.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
@@ -91,6 +94,29 @@ def bvc_splat(dim, absorption_coeff, samples, eval_pts, radius_clamp=1e-3, kerne
                               abi.ptr(sol), abi.ptr(grad), abi.ptr(cnt), abi.ptr(mean), C.byref(secs))
     assert rc == 0
     return sol, grad, cnt, mean, secs.value
+
+
+def kelvin_transform_points(x, origin):
+    x, origin = _f32(x), _f32(origin)
+    y = np.zeros_like(x)
+    lib().zref_kelvin_transform_points(x.shape[1], abi.ptr(origin), len(x), abi.ptr(x), abi.ptr(y))
+    return y
+
+
+def kelvin_robin_coefficients(transformed_points, indices, min_coeff, max_coeff, origin):
+    p, mn, mx, origin = _f32(transformed_points), _f32(min_coeff), _f32(max_coeff), _f32(origin)
+    idx = np.ascontiguousarray(indices, np.int32)
+    omn, omx = np.zeros(len(idx), np.float32), np.zeros(len(idx), np.float32)
+    lib().zref_kelvin_robin_coefficients(p.shape[1], abi.ptr(origin), len(p), abi.ptr(p), len(idx), abi.ptr(idx),
+                                         abi.ptr(mn), abi.ptr(mx), abi.ptr(omn), abi.ptr(omx))
+    return omn, omx
+
+
+def kelvin_back_transform(V, dV, y, origin):
+    y, V, dV, origin = _f32(y), _f32(V), _f32(dV), _f32(origin)
+    u, du = np.zeros(len(y), np.float32), np.zeros_like(y)
+    lib().zref_kelvin_back_transform(y.shape[1], abi.ptr(origin), len(y), abi.ptr(y), abi.ptr(V), abi.ptr(dV), abi.ptr(u), abi.ptr(du))
+    return u, du
 
 
 class RefScene:

@@ -260,6 +260,14 @@ int solve(RefScene<DIM>& s, int estimator, const zb_pde_desc *pdeDesc, const zb_
 {
     PDE<float, DIM> pde;
     buildPde<DIM>(*pdeDesc, pde);
+    // exterior problems: pdeDesc describes the PDE on the exterior domain, the walk runs on the inverted domain
+    // with the callbacks wrapped by KelvinTransform::transformPde (kelvin_transform.h:282-348)
+    float zeroOrigin[3] = {0.0f, 0.0f, 0.0f};
+    KelvinTransform<float, DIM> kelvin(toVec<DIM>(pdeDesc->kelvin ? pdeDesc->kelvinOrigin : zeroOrigin));
+    if (pdeDesc->kelvin) {
+        PDE<float, DIM> exterior = pde;
+        kelvin.transformPde(exterior, pde);
+    }
     WalkSettings settings = toSettings(*ws);
     int n = pts->n;
     std::vector<SamplePoint<float, DIM>> samplePts;
@@ -389,6 +397,36 @@ int bvcSplat(float absorptionCoeff, const zb_bvc_samples *s, float radiusClamp, 
 
 } // namespace
 
+namespace {
+template <size_t DIM>
+void kelvinRobin(const float *origin, int nV, const float *tp, int nP, const int32_t *idx, const float *mn, const float *mx,
+                 float *outMin, float *outMax)
+{
+    KelvinTransform<float, DIM> k(toVec<DIM>(origin));
+    std::vector<Vec<DIM>> pts;
+    std::vector<Veci<DIM>> ind;
+    for (int i = 0; i < nV; i++) pts.push_back(toVec<DIM>(tp + DIM*i));
+    for (int i = 0; i < nP; i++) { Veci<DIM> t; for (size_t j = 0; j < DIM; j++) t[j] = idx[DIM*i + j]; ind.push_back(t); }
+    std::vector<float> a(mn, mn + nP), b(mx, mx + nP), oa, ob;
+    k.computeRobinCoefficients(pts, ind, a, b, oa, ob);
+    for (int i = 0; i < nP; i++) { outMin[i] = oa[i]; outMax[i] = ob[i]; }
+}
+
+template <size_t DIM>
+void kelvinBack(const float *origin, int n, const float *y, const float *V, const float *dV, float *u, float *du)
+{
+    KelvinTransform<float, DIM> k(toVec<DIM>(origin));
+    for (int i = 0; i < n; i++) {
+        Vec<DIM> yy = toVec<DIM>(y + DIM*i);
+        u[i] = k.transformSolutionEstimate(V[i], yy);
+        std::vector<float> g(dV + DIM*i, dV + DIM*i + DIM), out;
+        k.transformGradientEstimate(V[i], g, yy, out);
+        for (size_t j = 0; j < DIM; j++) du[DIM*i + j] = out[j];
+    }
+}
+
+} // namespace
+
 #define DISPATCH(scene, expr2, expr3) \
     (((AnyScene *)(scene))->dim == 2 ? (expr2) : (expr3))
 
@@ -505,6 +543,30 @@ int zref_bvc_splat(int dim, float absorptionCoeff, const zb_bvc_samples *s, floa
                                     evalPt, evalType, distA, distR, solution, gradient, bucketCount, bucketMean);
     if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return rc;
+}
+
+// KelvinTransform host helpers (kelvin_transform.h:109-121, 244-279, 351-388) for the parity tests of
+// zombie_b200/kelvin.py
+int zref_kelvin_transform_points(int dim, const float *origin, int n, const float *x, float *y)
+{
+    if (dim == 2) { KelvinTransform<float, 2> k(toVec<2>(origin)); for (int i = 0; i < n; i++) fromVec<2>(k.transformPoint(toVec<2>(x + 2*i)), y + 2*i); }
+    else { KelvinTransform<float, 3> k(toVec<3>(origin)); for (int i = 0; i < n; i++) fromVec<3>(k.transformPoint(toVec<3>(x + 3*i)), y + 3*i); }
+    return 0;
+}
+
+int zref_kelvin_robin_coefficients(int dim, const float *origin, int nV, const float *transformedPoints, int nP,
+                                   const int32_t *indices, const float *minCoeff, const float *maxCoeff, float *outMin, float *outMax)
+{
+    if (dim == 2) kelvinRobin<2>(origin, nV, transformedPoints, nP, indices, minCoeff, maxCoeff, outMin, outMax);
+    else kelvinRobin<3>(origin, nV, transformedPoints, nP, indices, minCoeff, maxCoeff, outMin, outMax);
+    return 0;
+}
+
+int zref_kelvin_back_transform(int dim, const float *origin, int n, const float *y, const float *V, const float *dV, float *u, float *du)
+{
+    if (dim == 2) kelvinBack<2>(origin, n, y, V, dV, u, du);
+    else kelvinBack<3>(origin, n, y, V, dV, u, du);
+    return 0;
 }
 
 } // extern "C"

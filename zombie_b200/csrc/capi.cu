@@ -736,7 +736,8 @@ int zb_solve_dev(zb_scene *scene, int estimator, const zb_pde_desc *pde, const z
         !pts->distToReflectingBoundary || !pts->nWalks || !pts->rngState || !pts->rngInc || !pts->firstSphereRadius)
         return fail(ZB_ERR_INVALID_ARGUMENT, "zb_solve_dev: a required sample-point array is NULL");
     if (pde->mode != ZB_PDE_MANUFACTURED && pde->mode != ZB_PDE_CONSTANT) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_solve_dev: unknown pde mode");
-    if (pde->kelvin) return fail(ZB_ERR_UNSUPPORTED, "zb_solve_dev: Kelvin-transformed PDEs are not implemented yet");
+    if (pde->kelvin && pde->absorptionCoeff > 0.0f) // kelvin_transform.h:285-288
+        return fail(ZB_ERR_UNSUPPORTED, "zb_solve_dev: the Kelvin transform does not support non-zero absorption coefficients");
     if (settings->printLogs) return fail(ZB_ERR_UNSUPPORTED, "zb_solve_dev: printLogs is not supported on the device");
     zb_context *ctx = scene->ctx;
     ZB_CUDA(cudaSetDevice(ctx->device));
@@ -746,6 +747,11 @@ int zb_solve_dev(zb_scene *scene, int estimator, const zb_pde_desc *pde, const z
     a.estimator = estimator;
     a.ws = *settings;
     a.pde = *pde;
+    if (pde->kelvin) { // flags of the wrapped PDE (kelvin_transform.h:340-347)
+        a.pde.isSourceConstant = 0;
+        a.pde.absorptionCoeff = 0.0f;
+        if (scene->dim == 3) { a.pde.areRobinConditionsPureNeumann = 0; a.pde.areRobinCoeffsNonnegative = 0; }
+    }
     a.pts = *pts;
     a.stats = *stats;
     a.walkSteps = ctx->counters.as<long long>() + 1;

@@ -17,29 +17,67 @@ struct PdeEval {
         float xx[3] = {x[0], x[1], DIM == 3 ? x[DIM - 1] : 0.0f};
         return zb_eval_solution(d.family, d.params, xx);
     }
+    // ---- the callbacks of the PDE as the caller described it --------------------------------------
     // pde.source: the estimator solves lap u - sigma u = -f
-    ZB_HOSTDEV float source(const Vec<DIM>& x) const {
+    ZB_HOSTDEV float baseSource(const Vec<DIM>& x) const {
         if (d.mode == ZB_PDE_CONSTANT) return d.sourceValue;
         zb_jet j = jet(x);
         return d.absorptionCoeff*j.u - j.lap;
     }
-    // pde.dirichlet
-    ZB_HOSTDEV float dirichlet(const Vec<DIM>& x) const {
+    ZB_HOSTDEV float baseDirichlet(const Vec<DIM>& x) const {
         if (d.mode == ZB_PDE_CONSTANT) return d.dirichletValue;
         return jet(x).u;
     }
-    // pde.robin: du/dn + mu u with n the boundary normal handed to the callback
-    ZB_HOSTDEV float robin(const Vec<DIM>& x, const Vec<DIM>& n) const {
+    // du/dn + mu u with n the boundary normal handed to the callback
+    ZB_HOSTDEV float baseRobin(const Vec<DIM>& x, const Vec<DIM>& n) const {
         if (d.mode == ZB_PDE_CONSTANT) return d.robinValue;
         zb_jet j = jet(x);
         float dn = 0.0f;
         for (int k = 0; k < DIM; k++) dn += n[k]*j.g[k];
         return dn + d.robinCoeff*j.u;
     }
-    ZB_HOSTDEV float robinCoeff() const { return d.robinCoeff; }
-    // PDE::hasNonZeroRobinCoeff (pde.h:59-76)
-    ZB_HOSTDEV bool hasNonZeroRobinCoeff() const {
-        return !d.areRobinConditionsPureNeumann && fabsf(d.robinCoeff) > 0.0f;
+    // y on the inverted domain -> x on the exterior domain (kelvin_transform.h:288-289)
+    ZB_HOSTDEV Vec<DIM> exteriorPoint(const Vec<DIM>& y, float r2) const {
+        Vec<DIM> x;
+        for (int k = 0; k < DIM; k++) x[k] = y[k]/r2 + d.kelvinOrigin[k];
+        return x;
+    }
+    // ---- what the walk calls: wrapped like KelvinTransform::transformPde (kelvin_transform.h:282-348)
+    // when d.kelvin is set, the plain callbacks otherwise
+    ZB_HOSTDEV float source(const Vec<DIM>& y) const {
+        if (!d.kelvin) return baseSource(y);
+        float r2 = dot(y, y);
+        float rPow = r2*r2;
+        if (DIM == 3) rPow *= sqrtf(r2);
+        return baseSource(exteriorPoint(y, r2))/rPow;
+    }
+    ZB_HOSTDEV float dirichlet(const Vec<DIM>& y) const {
+        if (!d.kelvin) return baseDirichlet(y);
+        float r2 = dot(y, y);
+        float rPow = DIM == 3 ? sqrtf(r2) : 1.0f;
+        return baseDirichlet(exteriorPoint(y, r2))/rPow;
+    }
+    ZB_HOSTDEV float robin(const Vec<DIM>& y, const Vec<DIM>& N) const {
+        if (!d.kelvin) return baseRobin(y, N);
+        float r2 = dot(y, y);
+        Vec<DIM> n = N - y*(2.0f*dot(N, y))/r2;
+        float rPow = r2;
+        if (DIM == 3) rPow *= sqrtf(r2);
+        return baseRobin(exteriorPoint(y, r2), n)/rPow;
+    }
+    ZB_HOSTDEV float robinCoeff(const Vec<DIM>& y, const Vec<DIM>& N) const {
+        if (!d.kelvin) return d.robinCoeff;
+        float r2 = dot(y, y);
+        float P = dot(N, y)/r2;
+        float shift = DIM == 3 ? P : 0.0f;
+        return d.robinCoeff/r2 + shift;
+    }
+    // PDE::hasNonZeroRobinCoeff (pde.h:59-76): probes robinCoeff with the normal e_0
+    ZB_HOSTDEV bool hasNonZeroRobinCoeff(const Vec<DIM>& y) const {
+        if (d.areRobinConditionsPureNeumann) return false;
+        Vec<DIM> n = vzero<DIM>();
+        n[0] = 1.0f;
+        return fabsf(robinCoeff(y, n)) > 0.0f;
     }
 };
 

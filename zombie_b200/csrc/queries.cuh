@@ -32,10 +32,15 @@ struct BvhView {
 #define ZB_COUNT_FLUSH(q)
 #else
 void zbHostRecord(int query, int nodes, int prims);
+extern long long g_zbClass[8]; // star query: [0] items with silhouette tests, [1] without, [2] prims early-out by distance, [3] prims fully tested
+#define ZB_CLASS(i) g_zbClass[i]++;
 #define ZB_COUNT_DECL int zbNodes = 0, zbPrims = 0;
 #define ZB_COUNT_NODE zbNodes++;
 #define ZB_COUNT_PRIM zbPrims++;
 #define ZB_COUNT_FLUSH(q) zbHostRecord((q), zbNodes, zbPrims);
+#endif
+#if !defined(ZB_CLASS)
+#define ZB_CLASS(i)
 #endif
 #elif defined(ZB_STATS)
 __device__ unsigned long long g_zbCounters[16];
@@ -48,6 +53,9 @@ __device__ unsigned long long g_zbCounters[16];
 #define ZB_COUNT_NODE
 #define ZB_COUNT_PRIM
 #define ZB_COUNT_FLUSH(q)
+#endif
+#if !defined(ZB_CLASS)
+#define ZB_CLASS(i)
 #endif
 
 constexpr int kStackSize = 64;
@@ -706,7 +714,8 @@ ZB_DEV void primStarRadius2(const BvhView& bvh, uint32_t primIdx, const Vec<DIM>
     float bu, bv;
     float closestDist = prim.closest(x, closestPt, bu, bv);
     float closestDist2 = closestDist*closestDist;
-    if (closestDist2 > r2) return;
+    if (closestDist2 > r2) { ZB_CLASS(2) return; }
+    ZB_CLASS(3)
 
     // PrimAdjacency: n[3][3], minCoeff, maxCoeff, flags
     float4 a0 = zb_ldg(bvh.adjacency + (size_t)3*primIdx), a1 = zb_ldg(bvh.adjacency + (size_t)3*primIdx + 1),
@@ -864,6 +873,7 @@ ZB_DEV float starRadius2(const BvhView& bvh, const Vec<DIM>& x, float r2, bool f
         // bit 2 of the key marks "no silhouette inside this subtree" (reflectance bvh.h:474-476 sign trick)
         bool silhouetteTests = !(e.x & 4u);
         if (zb_uint_as_float(e.x & ~7u) > r2) continue;
+        ZB_CLASS(silhouetteTests ? 0 : 1)
         if (e.y & kLeafFlag) {
             uint32_t first = e.y & 0x0fffffffu, count = (e.y >> 28) & 7u;
             for (uint32_t i = 0; i < count; i++) { ZB_COUNT_PRIM primStarRadius2<DIM>(bvh, first + i, x, r2, flip, precision, silhouetteTests); }

@@ -299,7 +299,7 @@ ZB_DEV bool preparePointNoQuery(const SolveArgs& a, int i, bool& flip)
                 radius = distA;
             } else {
                 PdeEval<DIM> pde{a.pde};
-                if (a.pts.type[i] == ZB_ON_REFLECTING_BOUNDARY && pde.hasNonZeroRobinCoeff()) {
+                if (a.pts.type[i] == ZB_ON_REFLECTING_BOUNDARY && pde.hasNonZeroRobinCoeff(loadVec<DIM>(a.pts.pt + (size_t)DIM*i))) {
                     radius = a.ws.epsilonShellForReflectingBoundary;
                 } else {
                     flip = a.ws.solveDoubleSided && a.pts.type[i] == ZB_ON_REFLECTING_BOUNDARY &&
@@ -573,7 +573,7 @@ ZB_DEV bool stepStarPrologue(const SolveArgs& a, Lane<DIM>& L, float& starRadius
         starRadius = L.distA;
         return false;
     }
-    if (st.onRefl && pde.hasNonZeroRobinCoeff()) {
+    if (st.onRefl && pde.hasNonZeroRobinCoeff(st.pt)) {
         starRadius = a.ws.epsilonShellForReflectingBoundary;
         return false;
     }
@@ -701,7 +701,7 @@ ZB_DEV StepResult stepBody(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *que
             Vec<DIM> n = st.normal;
             if (!a.pde.areRobinConditionsPureNeumann) {
                 if (a.ws.solveDoubleSided && dot(st.prevDir, st.normal) < 0.0f) n = -n;
-                mu = pde.robinCoeff();
+                mu = pde.robinCoeff(st.pt, st.normal);
             }
             float reflectance = L.g.reflectance(st.prevDist, st.prevDir, n, mu);
             float maxReflectance = a.pde.areRobinCoeffsNonnegative ? 1.0f : 2.0f;
