@@ -23,18 +23,22 @@ def check_closest(ref_out, gpu_out, x, allow_tie_fraction=0.5):
     found = rprim >= 0
     assert rel_err(rd, gd)[found].max() <= TOL
     mism = (rprim != gprim) & found
-    # A different index is only acceptable for an EXACT tie: the query is equidistant (bit-equal distance) from
-    # two primitives sharing the closest edge/vertex and both report the same closest point (checked below).
+    # A different index is only acceptable for an EXACT tie: the query is bit-exactly equidistant from two
+    # primitives — almost always two primitives sharing the closest edge/vertex (same closest point), rarely two
+    # unrelated ones whose float distances coincide (queries near the centre of curvature of a smooth boundary).
     # FCPW keeps whichever primitive its own binary tree happens to visit last (bvh.inl:1331-1335: `found` on
     # d*d <= r2 overwrites); the cooperative traversal has no visit order and keeps the smaller leaf index. On the
     # coarse test meshes 25-40 % of random queries are such ties (closest point on a mesh edge or vertex), of
-    # which about half pick the other primitive. Anything that is not a bit-exact tie fails.
+    # which about half pick the other primitive. Anything that is not a bit-exact tie fails, and the point
+    # returned with the other primitive must be at exactly the returned distance.
     assert np.array_equal(rd[mism], gd[mism]), "primitive index differs without an exact distance tie"
     assert mism.mean() <= allow_tie_fraction
     ok = found & ~mism
     scale = np.maximum(1.0, np.abs(rpt).max())
     assert np.abs(rpt - gpt)[ok].max() <= TOL*scale
-    assert np.abs(rpt - gpt)[mism].max(initial=0.0) <= 2e-6*scale   # same closest point on the shared edge
+    same_point = np.abs(rpt - gpt)[mism].max(axis=1, initial=0.0) <= 2e-6*scale
+    assert same_point.mean() >= 0.97 if mism.any() else True        # shared edge / vertex: same closest point
+    assert np.abs(np.linalg.norm(x - gpt, axis=1) - gd)[mism].max(initial=0.0) <= 2e-6*scale
     if rn is not None and gn is not None:
         assert np.abs(rn - gn)[ok].max() <= 1e-5
 
@@ -140,7 +144,14 @@ def test_sphere_sampling_is_a_valid_importance_sampler(ctx, ref, dim):
     # (how often the single-path descent dead-ends depends on the tree; the pdf accounts for it)
     f = gprim >= 0
     assert (gpdf[f] > 0).all()
-    assert (np.linalg.norm(gpt - x, axis=1)[f] <= 0.6*(1 + 1e-5)).mean() > 0.995
+    # a sample is a uniform point of a primitive that touches the sphere, so it may lie a primitive's diameter
+    # outside it (the estimator rejects those, walk_on_stars.h:222); both trees put the same mass inside
+    rf = rprim >= 0
+    edge = np.linalg.norm(reflecting[0][reflecting[1][:, 0]] - reflecting[0][reflecting[1][:, 1]], axis=1).max()
+    assert (np.linalg.norm(gpt - x, axis=1)[f] <= 0.6 + 1.01*edge).all()
+    inside_g = (np.linalg.norm(gpt - x, axis=1)[f] <= 0.6).mean()
+    inside_r = (np.linalg.norm(rpt - x, axis=1)[rf] <= 0.6).mean()
+    assert abs(inside_g - inside_r) < 0.05, (inside_g, inside_r)
     # per query point: area estimates agree within 4 standard errors
     bad = 0
     for j in range(50):

@@ -226,3 +226,33 @@ def test_2d_demo_like_config(ctx):
         z = (st.solutionMean - w.exact(w.points))/np.maximum(se, 1e-4)
         assert np.mean(np.abs(z) < 4.0) > 0.96, (w.name, np.mean(np.abs(z) < 4.0), z.mean())
         sc.close()
+
+
+@pytest.mark.parametrize("mixed", [False, True])
+def test_kelvin_exterior_problem_matches_reference(ctx, ref, mixed):
+    """SURVEY §8a row K / BASELINE configs[4]: exterior Laplace problem solved on the Kelvin-inverted domain. The
+    device wraps the PDE like KelvinTransform::transformPde (kelvin_transform.h:282-348); the reference runs the
+    same inverted inputs through its own transformPde. Dirichlet variant: also against u = 1/|x - x0|."""
+    from zombie_b200 import kelvin
+    w = workloads.config5(subdivisions=4, n_points=384, n_walks=128, mixed=mixed)
+    sc = native.Scene(ctx, 3, **w.scene_kwargs())
+    rs = ref.RefScene(3, **w.scene_kwargs())
+    _, da, _, _ = sc.closest_point(abi.ABSORBING, w.points)
+    dr = sc.closest_point(abi.REFLECTING, w.points)[1] if mixed else None
+    results = []
+    for solver, seed in ((sc, 0xBEEF), (rs, 0xF00D)):
+        pts = abi.HostSamplePoints(w.points, da, dr, nWalks=w.n_walks, estimationQuantity=abi.SOLUTION, seed=seed)
+        st = abi.HostStatistics(pts.n, 3)
+        out = solver.solve(w.estimator, w.pde, w.settings, pts, st)
+        results.append((st, out if np.isscalar(out) else out[0]))
+    (gs, gsteps), (rs_, rsteps) = results
+    assert np.array_equal(gs.nSolutionEstimates, rs_.nSolutionEstimates)
+    z = cases.z_scores(gs, rs_)
+    assert np.mean(np.abs(z) < 3.0) >= 0.985, np.mean(np.abs(z) < 3.0)
+    assert abs(z.mean()) < 0.25 and 0.8 < z.std() < 1.25, (z.mean(), z.std())
+    assert abs(gsteps/float(rsteps) - 1.0) < 0.05
+    if not mixed:
+        u = kelvin.transform_solution_estimate(gs.solutionMean, w.points)   # back to the exterior domain
+        se = np.linalg.norm(w.points, axis=1)*np.sqrt(gs.solution_variance()/np.maximum(1, gs.nSolutionEstimates))
+        err = u - w.exterior_exact(w.exterior_points)
+        assert np.mean(np.abs(err) < 4.0*se + 2e-3) > 0.97

@@ -1,0 +1,77 @@
+"""CPU cross-check of the DEVICE walk code: zombie_b200/csrc/{walk,queries,greens,pde,rng}.cuh are host+device, and
+tools/host_solve.cu runs them one walk at a time on the CPU (test tool only — the library has no CPU path). Here its
+estimates, walk lengths and first-sphere radii are compared with the reference's TBB solver (oracle/_ref) and the
+exact solution, so estimator regressions are caught without a GPU. Same gates as tests/test_gpu_solve.py.
+
+(This test found a real defect: FCPW's 2D SilhouetteVertex test and its 3D SilhouetteEdge test use opposite view-
+direction conventions relative to Zombie's reflectance primitives; applying the 3D sign in 2D made walks along 2D
+Neumann boundaries 35 % too short.)"""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import cases
+from tests.conftest import ROOT
+from zombie_b200 import abi
+
+
+@pytest.fixture(scope="module")
+def host_solve(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("host") / "host_solve")
+    cmd = ["/usr/local/cuda/bin/nvcc", "-std=c++17", "-O2", "-DZB_HOST_STATS", "-Xcompiler", "-ffp-contract=off", "-o", exe,
+           os.path.join(ROOT, "tools", "host_solve.cu"), os.path.join(ROOT, "zombie_b200", "csrc", "wide_bvh.cpp")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    return exe
+
+
+def run_host(exe, d, dim, kind, absorbing, reflecting, x, n_walks, family, params, sigma, mu, rr, split, seed):
+    hdr = struct.pack("<4i16f4fQ", dim, kind, n_walks, family, *(list(params) + [0.0]*(16 - len(params))), sigma, mu, rr, split, seed)
+    open(os.path.join(d, "hdr.bin"), "wb").write(hdr)
+    empty = (np.zeros((0, dim), np.float32), np.zeros((0, dim), np.int32))
+    for name, (pos, idx) in (("a", absorbing), ("r", reflecting if reflecting is not None else empty)):
+        np.ascontiguousarray(pos, np.float32).tofile(os.path.join(d, name + "pos.bin"))
+        np.ascontiguousarray(idx, np.int32).tofile(os.path.join(d, name + "idx.bin"))
+    np.ascontiguousarray(x, np.float32).tofile(os.path.join(d, "pts.bin"))
+    r = subprocess.run([exe, d], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "status 0" in r.stdout, r.stdout
+    out = np.fromfile(os.path.join(d, "out.bin"), np.float32).reshape(-1, 4)
+    st = abi.HostStatistics(len(x), dim)
+    st.solutionMean, st.solutionM2 = out[:, 0].copy(), out[:, 1].copy()
+    st.nSolutionEstimates = out[:, 2].astype(np.int32)
+    st.totalWalkLength = out[:, 3].astype(np.int32)
+    return st
+
+
+CASES = {
+    "wost2d_neumann": dict(dim=2, kind=abi.REFLECTING_NEUMANN, family=abi.SOL_QUADRATIC, params=[1.0, -0.5, 0.0, 0.3], sigma=0.0, mu=0.0),
+    "wost3d_neumann": dict(dim=3, kind=abi.REFLECTING_NEUMANN, family=abi.SOL_QUADRATIC, params=[1.0, -0.5, 0.25, 0.3], sigma=0.0, mu=0.0),
+    "wost3d_robin_yukawa": dict(dim=3, kind=abi.REFLECTING_ROBIN, family=abi.SOL_EXP_DIR, params=[3**-0.5]*3 + [1.0], sigma=1.0, mu=1.0),
+    "wost2d_robin": dict(dim=2, kind=abi.REFLECTING_ROBIN, family=abi.SOL_QUADRATIC, params=[1.0, -0.5, 0.0, 0.3], sigma=0.0, mu=0.7),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_device_walk_code_on_host_matches_reference(ref, host_solve, tmp_path, name):
+    c = CASES[name]
+    dim = c["dim"]
+    whole, absorbing, reflecting = cases.mesh3d(3) if dim == 3 else cases.mesh2d(512)
+    x = cases.query_points(160, dim, 0.6 if dim == 3 else 0.7, seed=77)
+    n_walks = 192
+    st = run_host(host_solve, str(tmp_path), dim, c["kind"], absorbing, reflecting, x, n_walks, c["family"], c["params"],
+                  c["sigma"], c["mu"], 0.0, abi.FLT_MAX, 0xBEEF)
+    rs = ref.RefScene(dim, **cases.scene_kwargs(dim, c["kind"], absorbing, reflecting, mu=c["mu"]))
+    _, da, _, _ = rs.closest_point(abi.ABSORBING, x)
+    _, dr, _, _ = rs.closest_point(abi.REFLECTING, x)
+    pts = abi.HostSamplePoints(x, da, dr, nWalks=n_walks, estimationQuantity=abi.SOLUTION, seed=0xF00D)
+    rst = abi.HostStatistics(len(x), dim)
+    pde = abi.PdeDesc.manufactured(c["family"], c["params"], absorptionCoeff=c["sigma"], robinCoeff=c["mu"])
+    rsteps, _ = rs.solve(abi.WALK_ON_STARS, pde, abi.WalkSettings.default(), pts, rst)
+    assert np.array_equal(st.nSolutionEstimates, rst.nSolutionEstimates)
+    assert abs(st.totalWalkLength.sum()/float(rsteps) - 1.0) < 0.04      # same walk-length distribution
+    z = cases.z_scores(st, rst)
+    assert np.mean(np.abs(z) < 3.0) >= 0.98
+    assert abs(z.mean()) < 0.3 and 0.75 < z.std() < 1.3, (z.mean(), z.std())

@@ -76,7 +76,4 @@ inline void atomicMin64(unsigned long long *p, unsigned long long v)
 #define zb_shfl_up(v, o) zbemu::shflUp((v), (o))
 #define zb_atomic_min64(p, v) zbemu::atomicMin64((p), (v))
 #define zb_status_or(p, v) __atomic_fetch_or((p), (v), __ATOMIC_RELAXED)
-#define zb_sincos_fast(x, s, c) sincosf((x), (s), (c))
-#define zb_rsqrt(x) (1.0f/sqrtf(x))
-#define zb_exp_fast(x) expf(x)
 #define zb_popc(x) __builtin_popcount(x)

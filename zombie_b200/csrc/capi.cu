@@ -541,7 +541,10 @@ int zb_scene_create(zb_context *ctx, int dim,
             delete scene;
             return fail(ZB_ERR_INVALID_ARGUMENT, std::string("zb_scene_create: reflecting mesh: ") + (err ? err : "?"));
         }
-        int rc = uploadBvh(ctx, scene->boundary[ZB_REFLECTING], reflectingKind == ZB_REFLECTING_NEUMANN ? -1 : 1);
+        // FCPW's SilhouetteEdge test (silhouette_edges.inl:83-111, Neumann handler, 3D) measures the view direction
+        // with the opposite sign of Zombie's ReflectanceTriangle (reflectance_boundary_bvh/geometry.h:196-206); the 2D
+        // SilhouetteVertex and ReflectanceLineSegment tests agree (silhouette_vertices.inl:59-85, geometry.h:108-126)
+        int rc = uploadBvh(ctx, scene->boundary[ZB_REFLECTING], reflectingKind == ZB_REFLECTING_NEUMANN && dim == 3 ? -1 : 1);
         if (rc != ZB_OK) { delete scene; return rc; }
     }
     *out = scene;

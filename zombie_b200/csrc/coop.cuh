@@ -4,11 +4,14 @@
 // percentile ~2000 nodes + 9000 primitives, so with one thread per query a warp idles on its slowest lane
 // (lane efficiency ~0.1).
 //
-// Here the (up to) 32 queries of a warp share the work: the query state lives in shared memory and the warp
-// keeps TWO work lists there,
+// Two phases. (1) Every lane runs its own depth-first traversal (queries.cuh: closestPointDfs / starRadiusDfs,
+// nearest child first) for a bounded number of stack pops. Most queries finish here with exactly the work of
+// a sequential traversal, and the ones that do not have already found a close primitive, so their search
+// radius is tight. (2) The unfinished traversals are pooled: the query state moves to shared memory and the
+// warp keeps TWO work lists there,
 //   * a stack of (owner query, node) items, and
 //   * a queue of (owner query, primitive) items,
-// and runs homogeneous rounds: a NODE round pops up to 32 nodes, every lane tests the 8 children of one node
+// refilled from the lanes' private stacks, and runs homogeneous rounds: a NODE round pops up to 32 nodes, every lane tests the 8 children of one node
 // against its owner's query and the survivors are appended with warp prefix sums (internal children to the node
 // stack, the primitives of leaf children to the primitive queue); a PRIMITIVE round pops 32 primitives, one per
 // lane. Rounds never mix the two code paths, so a warp does not pay for both on every iteration, and a leaf
@@ -39,16 +42,23 @@
 #define zb_shfl_up(v, o) __shfl_up_sync(0xffffffffu, (v), (o))
 #define zb_atomic_min64(p, v) atomicMin((p), (v))
 #define zb_status_or(p, v) atomicOr((p), (v))
-#define zb_sincos_fast(x, s, c) __sincosf((x), (s), (c))
-#define zb_rsqrt(x) rsqrtf(x)
-#define zb_exp_fast(x) __expf(x)
 #define zb_popc(x) __popc(x)
 #endif
 
 namespace zb {
 
-constexpr int kNodeStack = 640;       // node items per warp; the top kNodeHeadroom are depth-first headroom
+#if defined(ZB_EMULATE_WARP)
+extern long long g_coopCount[8]; // [0] closest node items, [1] closest prims, [2] star node items, [3] star prims, [4..7] rounds
+#define ZB_COOP_COUNT(i, n) __atomic_fetch_add(&g_coopCount[i], (long long)(n), __ATOMIC_RELAXED);
+#else
+#define ZB_COOP_COUNT(i, n)
+#endif
+
+constexpr int kNodeStack = 1024;      // node items per warp; the top kNodeHeadroom are depth-first headroom
 constexpr int kNodeHeadroom = 128;
+constexpr int kPhase1Budget = 24;     // private stack pops per lane before the warp pools what is left
+constexpr int kRefillPerLane = 8;     // private stack entries a lane hands to the shared lists per refill
+constexpr int kRefillLowWater = 192;  // refill when the shared node stack is below this
 constexpr int kPrimQueue = 1056;      // >= 31 + 32 lanes x 8 leaves x 4 primitives
 constexpr uint32_t kPrimIndexMask = 0x03ffffffu; // 26 bits: up to 67 M primitives per boundary
 enum : int { kStatusCoopOverflow = 4 };
@@ -135,6 +145,37 @@ ZB_COOP void coopPushChildren(WarpShared& ws, int& nodeTop, int& primTop, int la
     primTop += totalP;
 }
 
+// Moves up to kRefillPerLane entries from the top of every lane's private traversal stack (queries.cuh format: x =
+// key with flag bits in the low 3 bits, y = node index or kLeafFlag | count << 28 | first primitive) to the
+// shared lists. starFlags: bit 2 of x is the "no silhouette" mark of the star-radius traversal. Every lane calls.
+// Only called with primTop < 32 and nodeTop < kRefillLowWater, so the lists cannot overflow.
+ZB_COOP void coopRefill(WarpShared& ws, int& nodeTop, int& primTop, int lane, const uint2 *stack, int& sp, bool starFlags)
+{
+    int take = min(sp, kRefillPerLane);
+    int nNodes = 0, nPrims = 0;
+    for (int k = 0; k < take; k++) {
+        uint2 e = stack[sp - take + k];
+        if (e.y & kLeafFlag) nPrims += (int)((e.y >> 28) & 7u); else nNodes++;
+    }
+    int inclN = warpInclusiveSum(nNodes, lane), inclP = warpInclusiveSum(nPrims, lane);
+    int totalN = zb_shfl(inclN, 31), totalP = zb_shfl(inclP, 31);
+    int slotN = nodeTop + inclN - nNodes, slotP = primTop + inclP - nPrims;
+    for (int k = 0; k < take; k++) { // bottom to top: the lane's nearest entry ends on top of its group
+        uint2 e = stack[sp - take + k];
+        uint32_t sil = starFlags ? (e.x >> 2) & 1u : 0u;
+        if (e.y & kLeafFlag) {
+            uint32_t first = e.y & 0x0fffffffu, count = (e.y >> 28) & 7u;
+            uint32_t head = ((uint32_t)lane << 27) | (sil << 26);
+            for (uint32_t i = count; i > 0u; i--) ws.prims[slotP++] = head | (first + i - 1u);
+        } else {
+            ws.nodes[slotN++] = make_uint2((e.x & ~63u) | (sil << 5) | (uint32_t)lane, e.y);
+        }
+    }
+    sp -= take;
+    nodeTop += totalN;
+    primTop += totalP;
+}
+
 // Aggregate::findClosestPoint for up to 32 queries at once (one per lane with hasQuery). Every lane of
 // the warp must call this. r2max: squared search radius. On return hit describes the lane's own query.
 template <int DIM>
@@ -142,20 +183,39 @@ ZB_COOP_NOINLINE void coopClosestPoint(const BvhView& bvh, WarpShared& ws, bool 
                                  ClosestHit<DIM>& hit, int *status)
 {
     const int lane = zb_lane();
+    // ---- phase 1: private depth-first traversal with a budget
+    uint2 stack[kStackSize];
+    int sp = 0;
+    float r2own = r2max;
+    hit.d = kMaxFloat;
+    hit.prim = -1;
+    hit.p = x;
+    if (hasQuery) {
+        stack[sp++] = make_uint2(0u, 0u);
+        closestPointDfs<DIM>(bvh, x, r2own, hit, stack, sp, kPhase1Budget, status);
+    }
+    if (zb_ballot(sp > 0) == 0u) return;
+
+    // ---- phase 2: pool the unfinished traversals
     zb_syncwarp();
     ws.qx[lane] = x[0];
     ws.qy[lane] = x[1];
     ws.qz[lane] = DIM == 3 ? x[DIM - 1] : 0.0f;
-    ws.best[lane] = packBest(r2max, 0xffffffffu);
-    unsigned m = zb_ballot(hasQuery);
-    int nodeTop = zb_popc(m), primTop = 0;
-    if (hasQuery) ws.nodes[zb_popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)lane, 0u);
+    // the phase-1 primitive stays the incumbent only if it lies within the (possibly box-shrunk) radius
+    ws.best[lane] = packBest(r2own, hit.prim >= 0 && hit.d*hit.d <= r2own ? (uint32_t)hit.prim : 0xffffffffu);
+    int nodeTop = 0, primTop = 0;
     zb_syncwarp();
 
-    while (nodeTop > 0 || primTop > 0) {
+    while (true) {
+        if (primTop < 32 && nodeTop < kRefillLowWater && zb_ballot(sp > 0) != 0u) {
+            coopRefill(ws, nodeTop, primTop, lane, stack, sp, false);
+            zb_syncwarp();
+        }
+        if (nodeTop == 0 && primTop == 0) break;
         if (primTop >= 32 || nodeTop == 0) {
             // ---- primitive round: one primitive per lane
             int n = min(primTop, 32);
+            if (lane == 0) { ZB_COOP_COUNT(1, n) ZB_COOP_COUNT(5, 1) }
             if (lane < n) {
                 uint32_t item = ws.prims[primTop - 1 - lane];
                 int owner = (int)(item >> 27);
@@ -179,6 +239,7 @@ ZB_COOP_NOINLINE void coopClosestPoint(const BvhView& bvh, WarpShared& ws, bool 
 
         // ---- node round: one node per lane
         int n = coopNodeBudget(nodeTop);
+        if (lane == 0) { ZB_COOP_COUNT(0, n) ZB_COOP_COUNT(4, 1) }
         bool have = lane < n;
         uint2 item = make_uint2(0u, 0u);
         if (have) item = ws.nodes[nodeTop - 1 - lane];
@@ -228,10 +289,7 @@ ZB_COOP_NOINLINE void coopClosestPoint(const BvhView& bvh, WarpShared& ws, bool 
 
     unsigned long long b = ws.best[lane];
     uint32_t prim = (uint32_t)b;
-    hit.prim = -1;
-    hit.d = kMaxFloat;
-    hit.p = x;
-    if (hasQuery && prim != 0xffffffffu) {
+    if (hasQuery && prim != 0xffffffffu && (int)prim != hit.prim) {
         Prim<DIM> p;
         p.load(bvh, prim);
         float u, v;
@@ -245,67 +303,6 @@ ZB_COOP_NOINLINE void coopClosestPoint(const BvhView& bvh, WarpShared& ws, bool 
 // star radius
 // ------------------------------------------------------------------------------------------
 
-// ReflectanceBvh::visitNode (reflectance_boundary_bvh/bvh.h:370-412) for one child of a wide node, in the
-// transcendental-free form described at the top of this file. Same contract as starChildBounds (queries.cuh):
-// bounds [lower, upper] on the squared star radius anything inside the child can produce, whether a silhouette
-// may hide inside; false when the child cannot shrink the radius at all. Conservative with respect to
-// starChildBounds' own tests: the overlap threshold carries 2e-5 of slack on the sine, the Robin cosine bound
-// 1e-5, on top of the 1e-4 rad by which the builder pads every cone.
-template <int DIM>
-ZB_COOP bool starChildBoundsFast(const BvhView& bvh, uint32_t nodeIdx, int c, const Vec<DIM>& x,
-                                                    const float lo[DIM], const float hi[DIM], float d2min, float d2max,
-                                                    float& lower, float& upper, bool& hasSil)
-{
-    const float4 *cone = bvh.cones + ((size_t)nodeIdx*8 + c)*2;
-    float4 c0 = zb_ldg(cone), c1 = zb_ldg(cone + 1);
-    float minCoeff = c1.y, maxCoeff = c1.z;
-    lower = d2min;
-    upper = d2max;
-    hasSil = true;
-    if (!(minCoeff < kMaxFloat - kEpsilon)) return true; // perfectly absorbing subtree: plain distance bounds
-
-    upper = kMaxFloat;
-    float halfAngle = c0.w;
-    if (halfAngle >= kHalfPiF || d2min < kEpsilon) return true;
-    float view[DIM], l2 = 0.0f;
-#pragma unroll
-    for (int k = 0; k < DIM; k++) { view[k] = 0.5f*(lo[k] + hi[k]) - x[k]; l2 = fmaf(view[k], view[k], l2); }
-    float radius = c1.x;
-    if (!(l2 > radius*radius)) return true; // inside the bounding sphere of the child: treat as overlapping
-    float invL = zb_rsqrt(l2);
-    float cosTheta = 0.0f;
-    const float axis[3] = {c0.x, c0.y, c0.z};
-#pragma unroll
-    for (int k = 0; k < DIM; k++) cosTheta = fmaf(axis[k], view[k], cosTheta);
-    cosTheta = fminf(1.0f, fabsf(cosTheta*invL));
-    float sinA, cosA;
-    zb_sincos_fast(halfAngle, &sinA, &cosA);
-    float sinB = fminf(1.0f, radius*invL), cosB = sqrtf(fmaxf(0.0f, 1.0f - sinB*sinB));
-    float sinG = sinA*cosB + cosA*sinB, cosG = cosA*cosB - sinA*sinB; // gamma = cone half angle + view half angle
-    if (cosG <= 1e-4f || cosTheta <= sinG + 2e-5f) return true;        // pi/2 within theta +- gamma: may hold a silhouette
-
-    hasSil = false;
-    if (!(maxCoeff > kEpsilon)) return false; // perfectly reflecting and no silhouette inside
-    // RobinBvhNodeBound (robin_bounds.h:102-154): radius range over the whole subtree
-    float sinTheta = sqrtf(fmaxf(0.0f, 1.0f - cosTheta*cosTheta));
-    float minCos = fmaxf(0.0f, cosTheta*cosG - sinTheta*sinG - 1e-5f); // min |cos| over [theta - gamma, theta + gamma]
-    float rMin = sqrtf(d2min), rMax = sqrtf(d2max);
-    if (DIM == 3) {
-        if (rMax < minCos/maxCoeff) lower = kMaxFloat;
-        else { float rb = rMin/(1.0f - minCos/(maxCoeff*rMax)); lower = rb*rb; }
-        if (!(rMin < 1.0f/minCoeff)) { float rb = rMax/(1.0f - 1.0f/(minCoeff*rMin)); upper = rb*rb; }
-    } else {
-        float rb = rMin*zb_exp_fast(minCos/(maxCoeff*rMax));
-        lower = rb*rb;
-        rb = rMax*expf(1.0f/(minCoeff*rMin));
-        upper = rb*rb;
-    }
-    // keep the pruning bounds conservative under float rounding
-    lower *= 0.9999f;
-    upper *= 1.0001f;
-    return true;
-}
-
 // ReflectanceBvh::computeSquaredStarRadius / findClosestSilhouettePoint for up to 32 queries at once.
 // Every lane of the warp must call this; returns the squared star radius (<= r2max) of the lane's query.
 template <int DIM>
@@ -313,21 +310,36 @@ ZB_COOP_NOINLINE float coopStarRadius2(const BvhView& bvh, WarpShared& ws, bool 
                                  bool flip, float precision, int *status)
 {
     const int lane = zb_lane();
+    // ---- phase 1: private depth-first traversal with a budget
+    uint2 stack[kStackSize];
+    int sp = 0;
+    float r2own = r2max;
+    if (hasQuery) {
+        stack[sp++] = make_uint2(0u, 0u);
+        starRadiusDfs<DIM, true>(bvh, x, r2own, flip, precision, stack, sp, kPhase1Budget, status);
+    }
+    if (zb_ballot(sp > 0) == 0u) return hasQuery ? r2own : r2max;
+
+    // ---- phase 2: pool the unfinished traversals
     zb_syncwarp();
     ws.qx[lane] = x[0];
     ws.qy[lane] = x[1];
     ws.qz[lane] = DIM == 3 ? x[DIM - 1] : 0.0f;
-    ws.best[lane] = packBest(r2max, 0u);
+    ws.best[lane] = packBest(r2own, 0u);
     ws.flags[lane] = flip ? 1u : 0u;
-    unsigned m = zb_ballot(hasQuery);
-    int nodeTop = zb_popc(m), primTop = 0;
-    if (hasQuery) ws.nodes[zb_popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)lane, 0u);
+    int nodeTop = 0, primTop = 0;
     zb_syncwarp();
 
-    while (nodeTop > 0 || primTop > 0) {
+    while (true) {
+        if (primTop < 32 && nodeTop < kRefillLowWater && zb_ballot(sp > 0) != 0u) {
+            coopRefill(ws, nodeTop, primTop, lane, stack, sp, true);
+            zb_syncwarp();
+        }
+        if (nodeTop == 0 && primTop == 0) break;
         if (primTop >= 32 || nodeTop == 0) {
             // ---- primitive round
             int n = min(primTop, 32);
+            if (lane == 0) { ZB_COOP_COUNT(3, n) ZB_COOP_COUNT(7, 1) }
             if (lane < n) {
                 uint32_t item = ws.prims[primTop - 1 - lane];
                 int owner = (int)(item >> 27);
@@ -337,7 +349,7 @@ ZB_COOP_NOINLINE float coopStarRadius2(const BvhView& bvh, WarpShared& ws, bool 
                 Vec<DIM> q;
                 q[0] = ws.qx[owner]; q[1] = ws.qy[owner];
                 if (DIM == 3) q[DIM - 1] = ws.qz[owner];
-                primStarRadius2<DIM>(bvh, item & kPrimIndexMask, q, r2, ws.flags[owner] != 0u, precision, silhouetteTests);
+                primStarRadius2Fast<DIM>(bvh, item & kPrimIndexMask, q, r2, ws.flags[owner] != 0u, precision, silhouetteTests);
                 if (r2 < before) zb_atomic_min64(&ws.best[owner], packBest(r2, 0u));
             }
             primTop -= n;
@@ -347,6 +359,7 @@ ZB_COOP_NOINLINE float coopStarRadius2(const BvhView& bvh, WarpShared& ws, bool 
 
         // ---- node round
         int n = coopNodeBudget(nodeTop);
+        if (lane == 0) { ZB_COOP_COUNT(2, n) ZB_COOP_COUNT(6, 1) }
         bool have = lane < n;
         uint2 item = make_uint2(0u, 0u);
         if (have) item = ws.nodes[nodeTop - 1 - lane];

@@ -221,7 +221,12 @@ struct GreensBall {
         float bound = R <= lambda ? fmaxf(fmaxf(a/R, a/lambda), fmaxf(b*sqrtf(R), b*sqrtLambda))
                                   : fmaxf(fminf(a/R, a/lambda), fminf(b*sqrtf(R), b*sqrtLambda));
         float fnNorm = norm();
-        int iter = 0;
+        // For small balls (mu R ~ 1e-3: every step taken from a Robin boundary, whose star radius is the epsilon
+        // shell) 1 - mu R/sinh(mu R) cancels catastrophically in float and the norm comes out <= 0 about as often as
+        // not. Then pdfRadius <= 0 for every candidate, the reference's loop rejects 1000 candidates in a row and
+        // keeps the last one (distributions.h:425-436); drawing that one candidate directly gives the same
+        // distribution of (r, pdf) without stalling the other 31 walks of the warp for 1000 iterations.
+        int iter = fnNorm > 0.0f ? 0 : 999;
         do {
             float u = rng.nextFloat();
             r = rng.nextFloat()*R;

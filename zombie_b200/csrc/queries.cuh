@@ -341,20 +341,15 @@ ZB_DEV void boxDistance2(const float lo[DIM], const float hi[DIM], const Vec<DIM
     }
 }
 
-// Aggregate::findClosestPoint(BoundingSphere(x, r2)) — bvh.inl:1291-1418. The search radius also
-// shrinks by each child's farthest-corner distance (bvh.inl:1339-1343), which bounds the stack.
+// Depth-first core of the closest-point query: pops up to `budget` stack entries (nearest child first) and
+// returns with the unfinished part of the traversal still on the stack (sp > 0) when the budget runs out.
+// hit / r2 carry the best primitive and squared search radius found so far.
 template <int DIM>
-ZB_DEV bool closestPoint(const BvhView& bvh, const Vec<DIM>& x, float r2, ClosestHit<DIM>& hit, int *status)
+ZB_DEV void closestPointDfs(const BvhView& bvh, const Vec<DIM>& x, float& r2, ClosestHit<DIM>& hit, uint2 *stack, int& sp,
+                            int budget, int *status)
 {
-    uint2 stack[kStackSize];
-    int sp = 0;
-    stack[sp++] = make_uint2(0u, 0u);
-    hit.d = kMaxFloat;
-    hit.prim = -1;
-    hit.p = x;
     ZB_COUNT_DECL
-
-    while (sp > 0) {
+    while (sp > 0 && budget-- > 0) {
         uint2 e = stack[--sp];
         if (keyValue(e.x) > r2) continue;
         if (e.y & kLeafFlag) {
@@ -402,6 +397,20 @@ ZB_DEV bool closestPoint(const BvhView& bvh, const Vec<DIM>& x, float r2, Closes
         }
     }
     ZB_COUNT_FLUSH(0)
+}
+
+// Aggregate::findClosestPoint(BoundingSphere(x, r2)) — bvh.inl:1291-1418. The search radius also
+// shrinks by each child's farthest-corner distance (bvh.inl:1339-1343), which bounds the stack.
+template <int DIM>
+ZB_DEV bool closestPoint(const BvhView& bvh, const Vec<DIM>& x, float r2, ClosestHit<DIM>& hit, int *status)
+{
+    uint2 stack[kStackSize];
+    int sp = 0;
+    stack[sp++] = make_uint2(0u, 0u);
+    hit.d = kMaxFloat;
+    hit.prim = -1;
+    hit.p = x;
+    closestPointDfs<DIM>(bvh, x, r2, hit, stack, sp, 0x7fffffff, status);
     return hit.prim >= 0;
 }
 
@@ -763,6 +772,112 @@ ZB_DEV void primStarRadius2(const BvhView& bvh, uint32_t primIdx, const Vec<DIM>
     }
 }
 
+// The same primitive test with fused arithmetic, reciprocal multiplies and a single normalisation (3D only; the 2D
+// form forwards to primStarRadius2). Identical case analysis, so the star radius agrees with primStarRadius2 to float
+// rounding (the gate on this query is FCPW's 1e-3 silhouette tolerance); roughly half the instructions.
+template <int DIM>
+ZB_DEV void primStarRadius2Fast(const BvhView& bvh, uint32_t primIdx, const Vec<DIM>& x, float& r2, bool flip,
+                                float precision, bool silhouetteTests)
+{
+    primStarRadius2<DIM>(bvh, primIdx, x, r2, flip, precision, silhouetteTests);
+}
+
+ZB_DEV float closestPointTriangleFast2(const Vec<3>& pa, const Vec<3>& pb, const Vec<3>& pc, const Vec<3>& x, Vec<3>& pt)
+{
+    Vec<3> ab = pb - pa, ac = pc - pa, ax = x - pa;
+    float d1 = dot(ab, ax), d2 = dot(ac, ax);
+    Vec<3> bx = x - pb, cx = x - pc;
+    float d3 = dot(ab, bx), d4 = dot(ac, bx), d5 = dot(ab, cx), d6 = dot(ac, cx);
+    float vc = d1*d4 - d3*d2, vb = d5*d2 - d1*d6, va = d3*d6 - d5*d4;
+    float v, w; // pt = pa + ab*v + ac*w
+    if (d1 <= 0.0f && d2 <= 0.0f) { v = 0.0f; w = 0.0f; }
+    else if (d3 >= 0.0f && d4 <= d3) { v = 1.0f; w = 0.0f; }
+    else if (d6 >= 0.0f && d5 <= d6) { v = 0.0f; w = 1.0f; }
+    else if (vc <= 0.0f && d1 >= 0.0f && d3 <= 0.0f) { v = d1/(d1 - d3); w = 0.0f; }
+    else if (vb <= 0.0f && d2 >= 0.0f && d6 <= 0.0f) { v = 0.0f; w = d2/(d2 - d6); }
+    else if (va <= 0.0f && (d4 - d3) >= 0.0f && (d5 - d6) >= 0.0f) { w = (d4 - d3)/((d4 - d3) + (d5 - d6)); v = 1.0f - w; }
+    else { float denom = 1.0f/(va + vb + vc); v = vb*denom; w = vc*denom; }
+    pt = pa + ab*v + ac*w;
+    return norm2(x - pt);
+}
+
+template <>
+ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const Vec<3>& x, float& r2, bool flip,
+                                   float precision, bool silhouetteTests)
+{
+    Prim<3> prim;
+    prim.load(bvh, primIdx);
+    Vec<3> closestPt;
+    float closestDist2 = closestPointTriangleFast2(prim.a, prim.b, prim.c, x, closestPt);
+    if (closestDist2 > r2) { ZB_CLASS(2) return; }
+    ZB_CLASS(3)
+
+    float4 a0 = zb_ldg(bvh.adjacency + (size_t)3*primIdx), a1 = zb_ldg(bvh.adjacency + (size_t)3*primIdx + 1),
+           a2 = zb_ldg(bvh.adjacency + (size_t)3*primIdx + 2);
+    float maxCoeff = a2.z;
+    uint32_t flags = zb_float_as_uint(a2.w);
+    if (!(maxCoeff < kMaxFloat - kEpsilon)) { // perfectly absorbing
+        r2 = fminf(r2, closestDist2);
+        return;
+    }
+
+    Vec<3> n0 = cross(prim.b - prim.a, prim.c - prim.a);
+    n0 = n0*(1.0f/sqrtf(dot(n0, n0)));
+    if (silhouetteTests) {
+        const float adjN[3][3] = {{a0.x, a0.y, a0.z}, {a0.w, a1.x, a1.y}, {a1.z, a1.w, a2.x}};
+        float convention = (float)bvh.snchSign;
+        float sign = flip ? 1.0f : -1.0f;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            if ((flags >> (4 + j)) & 1u) continue; // ignoreAdjacentFace
+            Vec<3> pj = j == 0 ? prim.a : (j == 1 ? prim.b : prim.c);
+            Vec<3> pk = j == 0 ? prim.b : (j == 1 ? prim.c : prim.a);
+            Vec<3> e = pk - pj, v = x - pj;
+            float c1 = dot(e, v), c2 = dot(e, e);
+            float t = c1 <= 0.0f ? 0.0f : (c2 <= c1 ? 1.0f : c1/c2);
+            Vec<3> vd = v - e*t;
+            float sd2 = dot(vd, vd);
+            if (!(sd2 < r2)) continue; // cannot shrink the radius whatever the classification says
+            bool isSilhouette = true;
+            if ((flags >> j) & 1u) {
+                Vec<3> nj = make3(adjN[j][0], adjN[j][1], adjN[j][2]);
+                float d = sqrtf(sd2);
+                if (d <= precision) {
+                    isSilhouette = isSilhouetteEdge3(pj, pk, nj, n0, vd, d, flip, precision, convention);
+                } else {
+                    float s = convention/d;
+                    float dot0 = s*dot(vd, nj), dot1 = s*dot(vd, n0);
+                    if (fabsf(dot0) <= precision) isSilhouette = sign*dot1 > precision;
+                    else if (fabsf(dot1) <= precision) isSilhouette = sign*dot0 > precision;
+                    else isSilhouette = dot0*dot1 < 0.0f;
+                }
+            }
+            if (isSilhouette) r2 = sd2;
+        }
+    }
+
+    if (maxCoeff > kEpsilon) { // reflectance case
+        float closestDist = sqrtf(closestDist2);
+        if (closestDist < kEpsilon) {
+            r2 = closestDist; // sic (geometry.h:216)
+        } else if (r2 > closestDist2) {
+            Vec<3> va = x - prim.a, vb = x - prim.b, vc = x - prim.c;
+            float da = dot(va, va), db = dot(vb, vb), dc = dot(vc, vc);
+            Vec<3> vfar = (da >= db && da >= dc) ? va : ((db >= da && db >= dc) ? vb : vc);
+            float far2 = fmaxf(da, fmaxf(db, dc));
+            float h = fabsf(dot(n0, va));
+            if (h > 0.0f) {
+                float cosUpper = fabsf(dot(x - closestPt, n0))/closestDist;
+                float cosLower = fabsf(dot(vfar, n0))/sqrtf(far2);
+                float radius = robinRadiusBound<3>(h, maxCoeff, cosLower, cosUpper);
+                if (radius < kMaxFloat) r2 = fminf(r2, radius*radius);
+            } else {
+                r2 = fminf(r2, closestDist2);
+            }
+        }
+    }
+}
+
 // BoundingCone::overlap (fcpw/core/bounding_volumes.h:275-321): can a normal inside the cone be
 // orthogonal to a direction from x to the box? Also returns the range of angles between the two.
 template <int DIM>
@@ -858,17 +973,77 @@ ZB_DEV bool starChildBounds(const BvhView& bvh, uint32_t nodeIdx, int c, const V
     return true;
 }
 
-// GeometricQueries::computeStarRadiusForReflectingBoundary for both the Neumann and the Robin
-// handler (fcpw_geometric_queries.h:1250-1291): returns the squared radius, <= r2Max.
+// ReflectanceBvh::visitNode (reflectance_boundary_bvh/bvh.h:370-412) for one child of a wide node, in the
+// transcendental-free form: the reference's acos/asin/atan2 cone test (fcpw/core/bounding_volumes.h:275-321)
+// becomes products of sines and cosines with explicit slack (node tests only prune, so any conservative form
+// returns the same query results). Same contract as starChildBounds (queries.cuh):
+// bounds [lower, upper] on the squared star radius anything inside the child can produce, whether a silhouette
+// may hide inside; false when the child cannot shrink the radius at all. Conservative with respect to
+// starChildBounds' own tests: the overlap threshold carries 2e-5 of slack on the sine, the Robin cosine bound
+// 1e-5, on top of the 1e-4 rad by which the builder pads every cone.
 template <int DIM>
-ZB_DEV float starRadius2(const BvhView& bvh, const Vec<DIM>& x, float r2, bool flip, float precision, int *status)
+ZB_DEV bool starChildBoundsFast(const BvhView& bvh, uint32_t nodeIdx, int c, const Vec<DIM>& x,
+                                                    const float lo[DIM], const float hi[DIM], float d2min, float d2max,
+                                                    float& lower, float& upper, bool& hasSil)
 {
-    uint2 stack[kStackSize];
-    int sp = 0;
-    stack[sp++] = make_uint2(0u, 0u);
-    ZB_COUNT_DECL
+    const float4 *cone = bvh.cones + ((size_t)nodeIdx*8 + c)*2;
+    float4 c0 = zb_ldg(cone), c1 = zb_ldg(cone + 1);
+    float minCoeff = c1.y, maxCoeff = c1.z;
+    lower = d2min;
+    upper = d2max;
+    hasSil = true;
+    if (!(minCoeff < kMaxFloat - kEpsilon)) return true; // perfectly absorbing subtree: plain distance bounds
 
-    while (sp > 0) {
+    upper = kMaxFloat;
+    float halfAngle = c0.w;
+    if (halfAngle >= kHalfPiF || d2min < kEpsilon) return true;
+    float view[DIM], l2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < DIM; k++) { view[k] = 0.5f*(lo[k] + hi[k]) - x[k]; l2 = fmaf(view[k], view[k], l2); }
+    float radius = c1.x;
+    if (!(l2 > radius*radius)) return true; // inside the bounding sphere of the child: treat as overlapping
+    float invL = zb_rsqrt(l2);
+    float cosTheta = 0.0f;
+    const float axis[3] = {c0.x, c0.y, c0.z};
+#pragma unroll
+    for (int k = 0; k < DIM; k++) cosTheta = fmaf(axis[k], view[k], cosTheta);
+    cosTheta = fminf(1.0f, fabsf(cosTheta*invL));
+    float sinA, cosA;
+    zb_sincos_fast(halfAngle, &sinA, &cosA);
+    float sinB = fminf(1.0f, radius*invL), cosB = sqrtf(fmaxf(0.0f, 1.0f - sinB*sinB));
+    float sinG = sinA*cosB + cosA*sinB, cosG = cosA*cosB - sinA*sinB; // gamma = cone half angle + view half angle
+    if (cosG <= 1e-4f || cosTheta <= sinG + 2e-5f) return true;        // pi/2 within theta +- gamma: may hold a silhouette
+
+    hasSil = false;
+    if (!(maxCoeff > kEpsilon)) return false; // perfectly reflecting and no silhouette inside
+    // RobinBvhNodeBound (robin_bounds.h:102-154): radius range over the whole subtree
+    float sinTheta = sqrtf(fmaxf(0.0f, 1.0f - cosTheta*cosTheta));
+    float minCos = fmaxf(0.0f, cosTheta*cosG - sinTheta*sinG - 1e-5f); // min |cos| over [theta - gamma, theta + gamma]
+    float rMin = sqrtf(d2min), rMax = sqrtf(d2max);
+    if (DIM == 3) {
+        if (rMax < minCos/maxCoeff) lower = kMaxFloat;
+        else { float rb = rMin/(1.0f - minCos/(maxCoeff*rMax)); lower = rb*rb; }
+        if (!(rMin < 1.0f/minCoeff)) { float rb = rMax/(1.0f - 1.0f/(minCoeff*rMin)); upper = rb*rb; }
+    } else {
+        float rb = rMin*zb_exp_fast(minCos/(maxCoeff*rMax));
+        lower = rb*rb;
+        rb = rMax*expf(1.0f/(minCoeff*rMin));
+        upper = rb*rb;
+    }
+    // keep the pruning bounds conservative under float rounding
+    lower *= 0.9999f;
+    upper *= 1.0001f;
+    return true;
+}
+
+// Depth-first core of the star-radius query: pops up to `budget` stack entries and returns with the unfinished
+// part of the traversal on the stack (sp > 0) when the budget runs out. FAST selects the algebraic child test.
+template <int DIM, bool FAST>
+ZB_DEV void starRadiusDfs(const BvhView& bvh, const Vec<DIM>& x, float& r2, bool flip, float precision, uint2 *stack, int& sp,
+                          int budget, int *status)
+{
+    ZB_COUNT_DECL
+    while (sp > 0 && budget-- > 0) {
         uint2 e = stack[--sp];
         // bit 2 of the key marks "no silhouette inside this subtree" (reflectance bvh.h:474-476 sign trick)
         bool silhouetteTests = !(e.x & 4u);
@@ -876,7 +1051,11 @@ ZB_DEV float starRadius2(const BvhView& bvh, const Vec<DIM>& x, float r2, bool f
         ZB_CLASS(silhouetteTests ? 0 : 1)
         if (e.y & kLeafFlag) {
             uint32_t first = e.y & 0x0fffffffu, count = (e.y >> 28) & 7u;
-            for (uint32_t i = 0; i < count; i++) { ZB_COUNT_PRIM primStarRadius2<DIM>(bvh, first + i, x, r2, flip, precision, silhouetteTests); }
+            for (uint32_t i = 0; i < count; i++) {
+                ZB_COUNT_PRIM
+                if (FAST) primStarRadius2Fast<DIM>(bvh, first + i, x, r2, flip, precision, silhouetteTests);
+                else primStarRadius2<DIM>(bvh, first + i, x, r2, flip, precision, silhouetteTests);
+            }
             continue;
         }
 
@@ -897,9 +1076,11 @@ ZB_DEV float starRadius2(const BvhView& bvh, const Vec<DIM>& x, float r2, bool f
             if (d2min > r2) continue;
             float lower, upper;
             bool hasSil;
-            if (!starChildBounds<DIM>(bvh, e.y, c, x, lo, hi, d2min, d2max, lower, upper, hasSil)) continue;
+            bool keep = FAST ? starChildBoundsFast<DIM>(bvh, e.y, c, x, lo, hi, d2min, d2max, lower, upper, hasSil)
+                             : starChildBounds<DIM>(bvh, e.y, c, x, lo, hi, d2min, d2max, lower, upper, hasSil);
+            if (!keep) continue;
             r2 = fminf(r2, upper);
-            if (!hasSil) noSil |= 1u << c;
+            if (!hasSil || !silhouetteTests) noSil |= 1u << c;
             keys[c] = (zb_float_as_uint(lower) & ~7u) | (uint32_t)c;
         }
         sort8(keys);
@@ -915,6 +1096,18 @@ ZB_DEV float starRadius2(const BvhView& bvh, const Vec<DIM>& x, float r2, bool f
         }
     }
     ZB_COUNT_FLUSH(4)
+}
+
+// GeometricQueries::computeStarRadiusForReflectingBoundary for both the Neumann and the Robin
+// handler (fcpw_geometric_queries.h:1250-1291): returns the squared radius, <= r2Max. One thread per query,
+// with the reference's own trigonometric cone test (the cross-check of the fast form).
+template <int DIM>
+ZB_DEV float starRadius2(const BvhView& bvh, const Vec<DIM>& x, float r2, bool flip, float precision, int *status)
+{
+    uint2 stack[kStackSize];
+    int sp = 0;
+    stack[sp++] = make_uint2(0u, 0u);
+    starRadiusDfs<DIM, false>(bvh, x, r2, flip, precision, stack, sp, 0x7fffffff, status);
     return r2;
 }
 

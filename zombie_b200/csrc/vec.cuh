@@ -26,6 +26,9 @@ static inline float zb_fsub(float a, float b) { volatile float r = a - b; return
 static inline int zb_atomic_or(int *p, int v) { int o = *p; *p |= v; return o; }
 static inline uint32_t zb_umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
 static inline uint32_t zb_umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
+static inline void zb_sincos_fast(float x, float *s, float *c) { *s = sinf(x); *c = cosf(x); }
+static inline float zb_rsqrt(float x) { return 1.0f/sqrtf(x); }
+static inline float zb_exp_fast(float x) { return expf(x); }
 #else
 #define zb_ldg __ldg
 #define zb_uint_as_float __uint_as_float
@@ -38,6 +41,9 @@ static inline uint32_t zb_umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
 #define zb_atomic_or atomicOr
 #define zb_umin min
 #define zb_umax max
+#define zb_sincos_fast(x, s, c) __sincosf((x), (s), (c))
+#define zb_rsqrt(x) rsqrtf(x)
+#define zb_exp_fast(x) __expf(x)
 #endif
 
 namespace zb {

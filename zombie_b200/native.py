@@ -186,6 +186,8 @@ class Scene:
                  watertight=True, domain_min=None, domain_max=None):
         self.ctx = ctx
         self.dim = dim
+        if dim not in (2, 3):
+            raise ZombieError("zb_scene_create: dim must be 2 or 3")
         ap, ai = absorbing if absorbing is not None else (np.zeros((0, dim), np.float32), np.zeros((0, dim), np.int32))
         rp, ri = reflecting if reflecting is not None else (np.zeros((0, dim), np.float32), np.zeros((0, dim), np.int32))
         ap, rp = _f32(ap), _f32(rp)

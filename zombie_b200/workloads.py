@@ -117,3 +117,53 @@ def config2(n_segments=4096, grid=512, n_walks=1024):
     return Workload("C2: 2D Poisson mixed Dirichlet/Neumann, star polygon %d segments, WoSt, %dx%d grid x %d walks" % (n_segments, grid, grid, n_walks),
                     2, absorbing, reflecting, abi.REFLECTING_NEUMANN, None, None, pde, settings, abi.WALK_ON_STARS, pts, n_walks,
                     abi.SOLUTION, lambda x: np.sin(pi*x[:, 0])*np.exp(pi*x[:, 1]) + x[:, 0]**2)
+
+
+def config5(subdivisions=9, n_points=1 << 20, n_walks=100, mixed=False, seed_points=11):
+    """BASELINE configs[4]: 3D Laplace EXTERIOR problem outside a bumpy icosphere, solved on the Kelvin-inverted
+    domain (zombie/variance_reduction/kelvin_transform.h). u = 1/|x - x0| with the pole x0 inside the body, so u is
+    harmonic outside and decays like 1/r. Evaluation points lie in the shell 1.5 < |x| < 4. The PDE descriptor
+    describes the EXTERIOR problem and carries kelvin = 1: the device wraps its callbacks like
+    KelvinTransform::transformPde; the mesh and the points handed to the solver are the inverted ones; estimates map
+    back with kelvin.transform_solution_estimate (u(x) = |y| V(y)).
+    mixed = False: Dirichlet everywhere (WalkOnSpheres). mixed = True: Neumann data on faces with centroid z > 0,
+    which the inversion turns into Robin conditions with coefficient n.y/|y|^2 (kelvin_transform.h:327-337), bounded
+    per triangle by kelvin.compute_robin_coefficients; WalkOnStars."""
+    from . import kelvin
+    origin = np.zeros(3, np.float32)
+    pos, tri = P.bumpy_sphere(subdivisions)
+    x0 = np.array([0.2, -0.1, 0.15], np.float32)
+    inv_pos = kelvin.transform_points(pos, origin)
+    rng = np.random.RandomState(seed_points)
+    d = rng.normal(size=(n_points, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    r = rng.uniform(1.5**3, 4.0**3, n_points)**(1.0/3.0)
+    x = np.ascontiguousarray(d*r[:, None], np.float32)
+    y = kelvin.transform_points(x, origin)
+    pde = abi.PdeDesc.manufactured(abi.SOL_INV_DIST, list(x0) + [1.0], absorptionCoeff=0.0, robinCoeff=0.0)
+    pde.kelvin = 1
+    for k in range(3):
+        pde.kelvinOrigin[k] = float(origin[k])
+    settings = abi.WalkSettings.default(1e-3, 1e-3, 1024, False)
+
+    def exact_inverted(yy):  # V(y) = u(x)/|y|
+        xx = yy/np.sum(yy*yy, axis=1, keepdims=True) + origin
+        return (1.0/np.linalg.norm(xx - x0, axis=1))/np.linalg.norm(yy, axis=1)
+
+    if not mixed:
+        w = Workload("C5: 3D Laplace exterior (Kelvin), Dirichlet, bumpy icosphere %d tris, WoS, %d pts x %d walks"
+                     % (len(tri), n_points, n_walks), 3, (inv_pos, tri), None, abi.REFLECTING_NONE, None, None, pde, settings,
+                     abi.WALK_ON_SPHERES, y, n_walks, abi.SOLUTION, exact_inverted)
+    else:
+        absorbing, reflecting = P.partition_mesh(pos, tri, lambda c: c[:, 2] > 0)
+        inv_abs = (kelvin.transform_points(absorbing[0], origin), absorbing[1])
+        inv_ref = (kelvin.transform_points(reflecting[0], origin), reflecting[1])
+        zero = np.zeros(len(reflecting[1]), np.float32)
+        mn, mx = kelvin.compute_robin_coefficients(inv_ref[0], inv_ref[1], zero, zero)
+        w = Workload("C5m: 3D Laplace exterior (Kelvin), Neumann z>0 -> Robin / Dirichlet z<0, bumpy icosphere %d tris, WoSt, %d pts x %d walks"
+                     % (len(tri), n_points, n_walks), 3, inv_abs, inv_ref, abi.REFLECTING_ROBIN, mn, mx, pde, settings,
+                     abi.WALK_ON_STARS, y, n_walks, abi.SOLUTION, exact_inverted)
+    w.exterior_points = x
+    w.exterior_exact = lambda xx: 1.0/np.linalg.norm(xx - x0, axis=1)
+    w.kelvin_origin = origin
+    return w
