@@ -201,7 +201,7 @@ def run_native(args, rank, world, local_rank):
         pilot_s = time.perf_counter() - t0
         per_point_s = pilot_s/n_pilot
         batch = int(args.step_seconds/max(per_point_s, 1e-9))
-        batch = 1 << max(11, min(16, int(math.floor(math.log2(max(batch, 1))))))
+        batch = 1 << max(13, min(16, int(math.floor(math.log2(max(batch, 1))))))
         pilot = {"points": n_pilot, "seconds": pilot_s}
     if dist is not None:  # every rank must use the same batch
         t = torch.tensor([batch], dtype=torch.int64, device=dev)
@@ -341,11 +341,11 @@ def cpu_baseline(args, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="evaluation points per step per GPU (0: sized by a pilot solve)")
-    ap.add_argument("--step-seconds", type=float, default=1.5, help="target duration of one step when --batch is 0")
+    ap.add_argument("--step-seconds", type=float, default=8.0, help="target duration of one step when --batch is 0")
     ap.add_argument("--subdiv", type=int, default=8, help="icosphere subdivisions (8 -> 1,310,720 triangles)")
     ap.add_argument("--points", type=int, default=1 << 20)
     ap.add_argument("--walks", type=int, default=64)

@@ -12,7 +12,7 @@ ctx = native.Context(0)
 scene = native.Scene(ctx, 3, **w.scene_kwargs())
 _, da, _, _ = scene.closest_point(abi.ABSORBING, w.points)
 _, dr, _, _ = scene.closest_point(abi.REFLECTING, w.points)
-for rep in range(2):
+for rep in range(int(os.environ.get('ZB_REPS', '2'))):
     pts = abi.HostSamplePoints(w.points, da, dr, nWalks=W, estimationQuantity=w.quantity)
     st = abi.HostStatistics(n, 3)
     steps = scene.solve(w.estimator, w.pde, w.settings, pts, st)

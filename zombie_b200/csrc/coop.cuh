@@ -54,9 +54,15 @@ extern long long g_coopCount[8]; // [0] closest node items, [1] closest prims, [
 #define ZB_COOP_COUNT(i, n)
 #endif
 
-constexpr int kNodeStack = 1024;      // node items per warp; the top kNodeHeadroom are depth-first headroom
+#ifndef ZB_NODE_STACK
+#define ZB_NODE_STACK 1024
+#endif
+#ifndef ZB_PHASE1_BUDGET
+#define ZB_PHASE1_BUDGET 8
+#endif
+constexpr int kNodeStack = ZB_NODE_STACK; // node items per warp; the top kNodeHeadroom are depth-first headroom
 constexpr int kNodeHeadroom = 128;
-constexpr int kPhase1Budget = 24;     // private stack pops per lane before the warp pools what is left
+constexpr int kPhase1Budget = ZB_PHASE1_BUDGET; // private stack pops per lane before the warp pools what is left
 constexpr int kRefillPerLane = 8;     // private stack entries a lane hands to the shared lists per refill
 constexpr int kRefillLowWater = 192;  // refill when the shared node stack is below this
 constexpr int kPrimQueue = 1056;      // >= 31 + 32 lanes x 8 leaves x 4 primitives

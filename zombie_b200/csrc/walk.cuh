@@ -783,8 +783,11 @@ ZB_DEV void finishState(const SolveArgs& a, Lane<DIM>& L, StepResult code, WalkS
     L.active = false;
 }
 
+#ifndef ZB_WALK_MIN_BLOCKS
+#define ZB_WALK_MIN_BLOCKS 4
+#endif
 template <int DIM, bool WOST>
-__global__ void __launch_bounds__(128) walkKernel(SolveArgs a)
+__global__ void __launch_bounds__(128, ZB_WALK_MIN_BLOCKS) walkKernel(SolveArgs a)
 {
 #if defined(__CUDA_ARCH__)
     extern __shared__ __align__(16) unsigned char zbShared[];
