@@ -75,3 +75,74 @@ def test_device_walk_code_on_host_matches_reference(ref, host_solve, tmp_path, n
     z = cases.z_scores(st, rst)
     assert np.mean(np.abs(z) < 3.0) >= 0.98
     assert abs(z.mean()) < 0.3 and 0.75 < z.std() < 1.3, (z.mean(), z.std())
+
+
+def test_cooperative_traversal_on_emulated_warps(tmp_path):
+    """zombie_b200/csrc/coop.cuh (the warp-cooperative closest-point / star-radius traversal the walk kernel runs) on
+    a CPU: tools/coop_check.cu emulates each warp with 32 host threads (tools/warp_emu.h) and compares every query
+    with the one-thread-per-query traversal: bit-identical distances, star radii equal to float rounding, no
+    work-list overflow — for a Robin and a Neumann boundary."""
+    exe = str(tmp_path / "coop_check")
+    cmd = ["/usr/local/cuda/bin/nvcc", "-std=c++17", "-O2", "-DZB_EMULATE_WARP", "-Xcompiler", "-ffp-contract=off", "-Xcompiler",
+           "-pthread", "-o", exe, os.path.join(ROOT, "tools", "coop_check.cu"), os.path.join(ROOT, "zombie_b200", "csrc", "wide_bvh.cpp")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    for mu in ("1.0", "0"):
+        r = subprocess.run([exe, "5", "1024", mu], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert "distance mismatches 0" in r.stdout and "cooperative status 0" in r.stdout, r.stdout
+        worst = float(r.stdout.split("worst rel ")[1].split(")")[0])
+        assert worst < 5e-3, r.stdout   # squared radius; fast vs exact primitive arithmetic in the ill-conditioned Robin bound
+
+
+@pytest.fixture(scope="module")
+def host_query(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("hostq") / "host_query")
+    cmd = ["/usr/local/cuda/bin/nvcc", "-std=c++17", "-O2", "-DZB_HOST_STATS", "-Xcompiler", "-ffp-contract=off", "-o", exe,
+           os.path.join(ROOT, "tools", "host_query.cu"), os.path.join(ROOT, "zombie_b200", "csrc", "wide_bvh.cpp")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    return exe
+
+
+@pytest.mark.parametrize("dim,kind,mu", [(2, abi.REFLECTING_NEUMANN, 0.0), (2, abi.REFLECTING_ROBIN, 2.0),
+                                         (3, abi.REFLECTING_NEUMANN, 0.0), (3, abi.REFLECTING_ROBIN, 2.0)])
+def test_device_star_radius_code_on_host_matches_reference(ref, host_query, tmp_path, dim, kind, mu):
+    """GeometricQueries::computeStarRadiusForReflectingBoundary (fcpw_geometric_queries.h:1250-1291): the device
+    traversals compiled for the host against the reference's BVH on interior points and on points ON the boundary
+    (where walks continue after a reflection). Where the reference's BVH and its own brute-force Baseline disagree by
+    more than FCPW's 1e-3 tolerance (a few queries in 10^5), the device code must side with the Baseline."""
+    whole, absorbing, reflecting = cases.mesh3d(4) if dim == 3 else cases.mesh2d(2048)
+    rp, ri = reflecting
+    rng = np.random.RandomState(3)
+    n_b = 6000
+    k = rng.randint(0, len(ri), n_b)
+    w = rng.dirichlet([1.0]*dim, n_b).astype(np.float32)
+    on_boundary = sum(rp[ri[k, j]]*w[:, j:j + 1] for j in range(dim)).astype(np.float32)
+    x = np.concatenate([cases.query_points(30000, dim, 0.99, seed=41), on_boundary])
+    kw = cases.scene_kwargs(dim, kind, absorbing, reflecting, mu=mu)
+    rs = ref.RefScene(dim, **kw)
+    _, da, _, _ = rs.closest_point(abi.ABSORBING, x)
+    _, dr, _, _ = rs.closest_point(abi.REFLECTING, x)
+    d = str(tmp_path)
+    x.tofile(os.path.join(d, "pts.bin"))
+    da.astype(np.float32).tofile(os.path.join(d, "maxr.bin"))
+    np.ascontiguousarray(rp, np.float32).tofile(os.path.join(d, "rpos.bin"))
+    np.ascontiguousarray(ri, np.int32).tofile(os.path.join(d, "ridx.bin"))
+    r = subprocess.run([host_query, d, str(dim), str(kind), str(mu)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    out = np.fromfile(os.path.join(d, "query_out.bin"), np.float32).reshape(-1, 3)
+    assert np.array_equal(out[:, 0], dr)                         # closest-point distance: bit-identical to FCPW
+    rr = rs.star_radius(x, np.full(len(x), 1e-3, np.float32), da)
+    for col, name in ((1, "trigonometric node test"), (2, "algebraic node test + fast primitive test")):
+        g = out[:, col]
+        bad = np.abs(rr - g) > 1e-3
+        assert bad.mean() <= 2e-4, name
+        if bad.any():
+            rb = ref.RefScene(dim, use_baseline=True, **kw)
+            base = rb.star_radius(x[bad], np.full(int(bad.sum()), 1e-3, np.float32), da[bad])
+            # ... or it is the Robin radius bound of a triangle the query is almost coplanar with: h -> 0 makes
+            # h^2 mu/(c(h mu - c^2)) cancel, and two float evaluations of it agree to about a percent only
+            ok = (np.abs(base - g[bad]) <= 1e-5) | (np.abs(rr[bad] - g[bad]) <= 2e-2*rr[bad])
+            assert ok.all(), (name, rr[bad], g[bad], base)
+        assert np.mean(np.abs(rr - g)[~bad] <= 1e-5*np.maximum(rr[~bad], 1e-3) + 1e-7) > 0.99, name
+    assert (rr < 0.999*da).mean() > 0.05

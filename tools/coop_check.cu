@@ -122,7 +122,25 @@ int main(int argc, char **argv)
         if (seqStar[i] < r2max[i]) shrunk++;
         double rel = std::fabs((double)coopStar[i] - seqStar[i])/std::max(1e-30, (double)std::max(coopStar[i], seqStar[i]));
         worstStar = std::max(worstStar, rel);
-        if (rel > 2e-5) { if (badStar < 5) printf("  star mismatch q %d: seq %.9g coop %.9g r2max %.9g\n", i, seqStar[i], coopStar[i], r2max[i]); badStar++; }
+        if (rel > 2e-5) {
+            if (badStar < 5) {
+                // which part differs: the traversal (coop vs one thread) or the arithmetic (fast vs reference-ordered)?
+                uint2 stack[kStackSize]; int sp = 0; stack[sp++] = make_uint2(0u, 0u);
+                float r2f = r2max[i];
+                Vec<3> q = loadVec<3>(&x[3*i]);
+                starRadiusDfs<3, true>(vr, q, r2f, i%7 != 3, 1e-3f, stack, sp, 0x7fffffff, &status);
+                // brute force over all primitives with both primitive tests
+                float be = r2max[i], bf = r2max[i]; int ie = -1, jf = -1;
+                for (int p = 0; p < vr.nPrims; p++) {
+                    float a = be, b = bf;
+                    primStarRadius2<3>(vr, p, q, a, i%7 != 3, 1e-3f, true); if (a < be) { be = a; ie = p; }
+                    primStarRadius2Fast<3>(vr, p, q, b, i%7 != 3, 1e-3f, true); if (b < bf) { bf = b; jf = p; }
+                }
+                printf("  star mismatch q %d: seq %.9g coop %.9g (one-thread fast %.9g) r2max %.9g | brute exact %.9g (prim %d) brute fast %.9g (prim %d)\n",
+                       i, seqStar[i], coopStar[i], r2f, r2max[i], be, ie, bf, jf);
+            }
+            badStar++;
+        }
     }
     printf("closest: distance mismatches %d, primitive differs (ties) %d | star: mismatches %d (worst rel %.3g), %d of %d queries shrunk below r2max\n",
            badDist, primDiff, badStar, worstStar, shrunk, nQ);

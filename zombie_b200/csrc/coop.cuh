@@ -399,7 +399,7 @@ ZB_COOP_NOINLINE float coopStarRadius2(const BvhView& bvh, WarpShared& ws, bool 
                     if (d2min > r2) continue;
                     float lower, upper;
                     bool hasSil;
-                    if (!starChildBoundsFast<DIM>(bvh, item.y, c, q, lo, hi, d2min, d2max, lower, upper, hasSil)) continue;
+                    if (!starChildBoundsFast<DIM>(bvh, item.y, c, q, lo, hi, d2min, d2max, lower, upper, hasSil, precision)) continue;
                     shrink = fminf(shrink, upper);
                     if (!hasSil || parentNoSil) noSil |= 1u << c;
                     keys[c] = (zb_float_as_uint(lower) & ~63u) | (uint32_t)c;

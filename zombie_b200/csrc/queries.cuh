@@ -811,6 +811,12 @@ ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const V
     float closestDist2 = closestPointTriangleFast2(prim.a, prim.b, prim.c, x, closestPt);
     if (closestDist2 > r2) { ZB_CLASS(2) return; }
     ZB_CLASS(3)
+    // Discrete decisions (is this edge a silhouette? does the reflectance bound apply?) are taken with fused
+    // arithmetic; whenever one of them falls within rounding distance of its threshold, or the bound formula is
+    // ill-conditioned, the primitive is redone with the reference-ordered arithmetic of primStarRadius2, so the
+    // two never disagree by more than float rounding.
+    const float r2in = r2;
+    bool redo = false;
 
     float4 a0 = zb_ldg(bvh.adjacency + (size_t)3*primIdx), a1 = zb_ldg(bvh.adjacency + (size_t)3*primIdx + 1),
            a2 = zb_ldg(bvh.adjacency + (size_t)3*primIdx + 2);
@@ -821,8 +827,7 @@ ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const V
         return;
     }
 
-    Vec<3> n0 = cross(prim.b - prim.a, prim.c - prim.a);
-    n0 = n0*(1.0f/sqrtf(dot(n0, n0)));
+    Vec<3> n0 = unitNormal<3>(prim); // reference-ordered: the plane distance below cancels and must round the same way
     if (silhouetteTests) {
         const float adjN[3][3] = {{a0.x, a0.y, a0.z}, {a0.w, a1.x, a1.y}, {a1.z, a1.w, a2.x}};
         float convention = (float)bvh.snchSign;
@@ -847,6 +852,7 @@ ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const V
                 } else {
                     float s = convention/d;
                     float dot0 = s*dot(vd, nj), dot1 = s*dot(vd, n0);
+                    redo = redo || fabsf(fabsf(dot0) - precision) < 4e-6f || fabsf(fabsf(dot1) - precision) < 4e-6f;
                     if (fabsf(dot0) <= precision) isSilhouette = sign*dot1 > precision;
                     else if (fabsf(dot1) <= precision) isSilhouette = sign*dot0 > precision;
                     else isSilhouette = dot0*dot1 < 0.0f;
@@ -865,16 +871,26 @@ ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const V
             float da = dot(va, va), db = dot(vb, vb), dc = dot(vc, vc);
             Vec<3> vfar = (da >= db && da >= dc) ? va : ((db >= da && db >= dc) ? vb : vc);
             float far2 = fmaxf(da, fmaxf(db, dc));
-            float h = fabsf(dot(n0, va));
+            float h = fabsf(dot(n0, prim.a - x)/dot(n0, n0)); // findClosestPointPlane (geometry.h:62-70)
             if (h > 0.0f) {
-                float cosUpper = fabsf(dot(x - closestPt, n0))/closestDist;
-                float cosLower = fabsf(dot(vfar, n0))/sqrtf(far2);
+                float cosUpper = fabsf(dot((x - closestPt)/closestDist, n0));
+                float farDist = sqrtf(far2);
+                float cosLower = fabsf(dot(vfar/farDist, n0));
                 float radius = robinRadiusBound<3>(h, maxCoeff, cosLower, cosUpper);
                 if (radius < kMaxFloat) r2 = fminf(r2, radius*radius);
+                // threshold maxCos >= cosLower, the conditioning h mu/(h mu - c^2) of the bound (robin_bounds.h:48-74), and the
+                // cancellation in cosUpper when x is nearly coplanar with the triangle (its value then sets the radius)
+                float hmu = h*maxCoeff, maxCos = sqrtf(hmu);
+                float c = clampLikeStd(maxCos/1.7320508075688772935f, cosLower, cosUpper);
+                redo = redo || fabsf(maxCos - cosLower) < 1e-5f || (maxCos >= cosLower && ((hmu - c*c) < 0.3f*hmu || (c == cosUpper && cosUpper < 0.05f)));
             } else {
                 r2 = fminf(r2, closestDist2);
             }
         }
+    }
+    if (redo) {
+        r2 = r2in;
+        primStarRadius2<3>(bvh, primIdx, x, r2, flip, precision, silhouetteTests);
     }
 }
 
@@ -936,7 +952,7 @@ ZB_DEV bool coneOverlap(const float axis[3], float halfAngle, float radius, cons
 // the child cannot shrink the radius at all.
 template <int DIM>
 ZB_DEV bool starChildBounds(const BvhView& bvh, uint32_t nodeIdx, int c, const Vec<DIM>& x, const float lo[DIM], const float hi[DIM],
-                            float d2min, float d2max, float& lower, float& upper, bool& hasSil)
+                            float d2min, float d2max, float& lower, float& upper, bool& hasSil, float precision)
 {
     float4 c0 = zb_ldg(bvh.cones + ((size_t)nodeIdx*8 + c)*2), c1 = zb_ldg(bvh.cones + ((size_t)nodeIdx*8 + c)*2 + 1);
     float minCoeff = c1.y, maxCoeff = c1.z;
@@ -946,7 +962,10 @@ ZB_DEV bool starChildBounds(const BvhView& bvh, uint32_t nodeIdx, int c, const V
     if (minCoeff < kMaxFloat - kEpsilon) {
         float axis[3] = {c0.x, c0.y, c0.z};
         float minAngle, maxAngle;
-        if (coneOverlap<DIM>(axis, c0.w, c1.x, x, lo, hi, d2min, minAngle, maxAngle)) {
+        // A query within `precision` of an edge / vertex classifies it by its dihedral angle alone, whatever the view
+        // direction (silhouette_edges.inl:88-95, silhouette_vertices.inl:64-68), which the view-cone test cannot see:
+        // such children always count as possible silhouettes, so the traversal equals a brute-force scan there too.
+        if (d2min <= precision*precision || coneOverlap<DIM>(axis, c0.w, c1.x, x, lo, hi, d2min, minAngle, maxAngle)) {
             upper = kMaxFloat;
         } else {
             hasSil = false;
@@ -984,7 +1003,7 @@ ZB_DEV bool starChildBounds(const BvhView& bvh, uint32_t nodeIdx, int c, const V
 template <int DIM>
 ZB_DEV bool starChildBoundsFast(const BvhView& bvh, uint32_t nodeIdx, int c, const Vec<DIM>& x,
                                                     const float lo[DIM], const float hi[DIM], float d2min, float d2max,
-                                                    float& lower, float& upper, bool& hasSil)
+                                                    float& lower, float& upper, bool& hasSil, float precision)
 {
     const float4 *cone = bvh.cones + ((size_t)nodeIdx*8 + c)*2;
     float4 c0 = zb_ldg(cone), c1 = zb_ldg(cone + 1);
@@ -996,7 +1015,7 @@ ZB_DEV bool starChildBoundsFast(const BvhView& bvh, uint32_t nodeIdx, int c, con
 
     upper = kMaxFloat;
     float halfAngle = c0.w;
-    if (halfAngle >= kHalfPiF || d2min < kEpsilon) return true;
+    if (halfAngle >= kHalfPiF || d2min < kEpsilon || d2min <= precision*precision) return true; // see starChildBounds
     float view[DIM], l2 = 0.0f;
 #pragma unroll
     for (int k = 0; k < DIM; k++) { view[k] = 0.5f*(lo[k] + hi[k]) - x[k]; l2 = fmaf(view[k], view[k], l2); }
@@ -1076,8 +1095,8 @@ ZB_DEV void starRadiusDfs(const BvhView& bvh, const Vec<DIM>& x, float& r2, bool
             if (d2min > r2) continue;
             float lower, upper;
             bool hasSil;
-            bool keep = FAST ? starChildBoundsFast<DIM>(bvh, e.y, c, x, lo, hi, d2min, d2max, lower, upper, hasSil)
-                             : starChildBounds<DIM>(bvh, e.y, c, x, lo, hi, d2min, d2max, lower, upper, hasSil);
+            bool keep = FAST ? starChildBoundsFast<DIM>(bvh, e.y, c, x, lo, hi, d2min, d2max, lower, upper, hasSil, precision)
+                             : starChildBounds<DIM>(bvh, e.y, c, x, lo, hi, d2min, d2max, lower, upper, hasSil, precision);
             if (!keep) continue;
             r2 = fminf(r2, upper);
             if (!hasSil || !silhouetteTests) noSil |= 1u << c;
