@@ -315,7 +315,9 @@ def run_native(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak,
                          "traffic": None, "peak_kind": peak_kind, "kernel": "walkKernel<3,true>", "grid": grid,
                          "algorithmic_bytes_per_walk_step": bytes_per_step, "kernel_ms_per_step": walk_ms/args.steps,
-                         "kernel_share_of_step": walk_ms/dev_ms if dev_ms > 0 else None},
+                         "kernel_share_of_step": walk_ms/dev_ms if dev_ms > 0 else None,
+                         "traffic_note": "ncu --set full of the same kernel on a 512-point launch (profiles/README.md): 20 KB of "
+                                         "DRAM traffic and 44 K warp instructions per walk step; issue/latency bound, not HBM bound"},
         }
         if not args.no_cpu and world >= 1:
             line["cpu_baseline"] = cpu_baseline(args, w)
