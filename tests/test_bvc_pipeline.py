@@ -1,0 +1,132 @@
+"""Boundary Value Caching end to end (BASELINE configs[3] at test size): zombie_b200/bvc.py orchestrates sample
+generation, WalkOnStars at the cache points, the splat and the near-boundary estimates
+(bvc::BoundaryValueCachingSolver, zombie/variance_reduction/boundary_value_caching.h:814-925).
+
+CPU: the same orchestration over the compiled reference (oracle/_ref) as backend pins the host logic — samplers,
+estimation-data rules, bucket bookkeeping — against the exact solution. GPU: the device backend must reach the same
+accuracy and agree with the reference-backed run statistically."""
+import numpy as np
+import pytest
+
+from tests import cases
+from zombie_b200 import abi, bvc, procedural as P
+
+
+class RefBackend:
+    """the reference's CPU solver behind the backend interface of zombie_b200/bvc.py (test infrastructure)"""
+
+    def __init__(self, ref, scene, dim):
+        self.ref, self.scene, self.dim = ref, scene, dim
+
+    def distances(self, x, has_absorbing=True, has_reflecting=True):
+        da = self.scene.closest_point(abi.ABSORBING, x, want_normal=False)[1]
+        dr = self.scene.closest_point(abi.REFLECTING, x, want_normal=False)[1]
+        return da, dr
+
+    def solve(self, pde, settings, pts, stats):
+        return self.scene.solve(abi.WALK_ON_STARS, pde, settings, pts, stats)[0]
+
+    def splat(self, absorption_coeff, samples, eval_pts, radius_clamp, kernel_regularization, robin_cutoff, cutoff_a, cutoff_r):
+        sol, grad, cnt, mean, _ = self.ref.bvc_splat(self.dim, absorption_coeff, samples, eval_pts, radius_clamp, kernel_regularization,
+                                                     robin_cutoff, cutoff_a, cutoff_r)
+        eval_pts.bucketCount += cnt
+        eval_pts.bucketSum += mean*cnt[:, :, None]
+        m = eval_pts.bucket_mean()
+        eval_pts.solution[:] = m[:, :, 0].sum(axis=1)
+        eval_pts.gradient[:] = m[:, :, 1:].sum(axis=1)
+        return samples.n*eval_pts.n
+
+
+def problem():
+    """3D Poisson, Dirichlet on z <= 0 / Neumann on z > 0 of the bumpy sphere, u = x^2 - y^2/2 + z^2/4 + 0.3 (f = -1.5)"""
+    whole, absorbing, reflecting = cases.mesh3d(3)
+    pde = cases.quadratic_pde()
+    ev = bvc.ManufacturedPdeEval(
+        u=lambda x: cases.quadratic_exact(x),
+        grad_u=lambda x: np.stack([2.0*x[:, 0], -1.0*x[:, 1], 0.5*x[:, 2]], axis=1),
+        lap_u=lambda x: np.full(len(x), 1.5), sigma=0.0, mu=0.0)
+    return whole, absorbing, reflecting, pde, ev
+
+
+def run_pipeline(backend, absorbing, reflecting, pde, ev, x, seed):
+    eps = 1e-3
+    settings = abi.WalkSettings.default(eps, eps, 1024, False)
+    sa = bvc.UniformBoundarySampler(*absorbing, seed=seed)
+    sr = bvc.UniformBoundarySampler(*reflecting, seed=seed + 1)
+    offset_a, offset_r = 0.03, 0.0   # the normal-derivative estimate at the offset points has variance ~ 1/offset^2
+    # the cached boundary data live on the Dirichlet part displaced inward, so the source integral runs over the region
+    # that surface encloses (with the reference's 5-epsilon offsets the difference is negligible; at 0.03 it is not)
+    def inside(p):
+        r = np.linalg.norm(p, axis=1)
+        d = p/np.maximum(r, 1e-30)[:, None]
+        return r < P.bumpy_sphere_radius(d) - np.where(d[:, 2] < 0.0, offset_a, 0.0)
+    dirs = np.random.RandomState(1).normal(size=(400000, 3))
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    volume = float(4.0*np.pi/3.0*np.mean((P.bumpy_sphere_radius(dirs) - np.where(dirs[:, 2] < 0.0, offset_a, 0.0))**3))
+    sd = bvc.UniformDomainSampler(inside, [-1.2]*3, [1.2]*3, volume, seed=seed + 2)
+    sa.initialize(offset_a, False)
+    sr.initialize(offset_r, False)
+    solver = bvc.BoundaryValueCachingSolver(backend, sa, sr, sd, seed=seed)
+    solver.generate_samples(1024, 768, 1536, offset_a, offset_r)
+    steps = solver.compute_sample_estimates(pde, settings, 64, 256, abi.FLT_MAX, ev)
+    da, dr = backend.distances(x)
+    e = abi.HostBvcEvalPoints(x, da, dr)
+    pairs = solver.splat(pde, e, 1e-3, 0.0, abi.FLT_MAX, 0.05, 0.05)
+    near = solver.estimate_solution_near_boundary(pde, settings, e, 0.05, 0.05, 64)
+    return solver, e, steps, pairs
+
+
+def check_samplers(solver, absorbing, reflecting):
+    c = solver.caches
+    assert len(c["absorbing"]) == 1024 and len(c["reflecting"]) == 768 and 1200 < len(c["domain"]) < 1900
+    # absorbing samples sit 0.03 inside the Dirichlet half (z <= 0 up to a triangle), reflecting samples on the Neumann half
+    assert np.allclose(c["absorbing"].dist_a, 0.03, atol=4e-3) and (c["absorbing"].pt[:, 2] < 0.1).all()
+    assert (c["reflecting"].dist_r < 1e-5).all() and (c["reflecting"].pt[:, 2] > -0.1).all()
+    assert P.bumpy_sphere_inside(c["domain"].pt).all()
+    # pdf = 1/area for uniform weights (boundary_samplers.h:575), 1/volume in the domain (domain_samplers.h:80)
+    for name, mesh in (("absorbing", absorbing), ("reflecting", reflecting)):
+        pos, tri = mesh
+        area = 0.5*np.linalg.norm(np.cross(pos[tri[:, 1]] - pos[tri[:, 0]], pos[tri[:, 2]] - pos[tri[:, 0]]), axis=1).sum()
+        # (the absorbing cache lives on the surface displaced 0.03 inward, whose area is ~6 % smaller)
+        assert np.allclose(c[name].pdf, 1.0/area, rtol=8e-2 if name == "absorbing" else 1e-3)
+    assert np.allclose(c["domain"].pdf, 1.0/P.bumpy_sphere_volume(), rtol=5e-2)
+    # the Neumann data and the estimated normal derivative on the Dirichlet part are the exact ones up to MC noise
+    nd_exact = (np.stack([2.0*c["absorbing"].pt[:, 0], -c["absorbing"].pt[:, 1], 0.5*c["absorbing"].pt[:, 2]], 1)*c["absorbing"].normal).sum(1)
+    dn_err = c["absorbing"].normal_derivative - nd_exact      # noisy per sample: the first ball has radius 0.03
+    assert abs(np.mean(dn_err)) < 4.0*np.std(dn_err)/np.sqrt(len(dn_err)) + 0.02
+    sol_err = c["reflecting"].solution - cases.quadratic_exact(c["reflecting"].pt)
+    assert abs(sol_err.mean()) < 0.03 and sol_err.std() < 0.3
+
+
+def test_pipeline_over_the_reference_reaches_the_exact_solution(ref):
+    whole, absorbing, reflecting, pde, ev = problem()
+    scene = ref.RefScene(3, **cases.scene_kwargs(3, abi.REFLECTING_NEUMANN, absorbing, reflecting))
+    x = np.concatenate([cases.query_points(300, 3, 0.6, seed=5), cases.query_points(60, 3, 0.93, seed=6)])
+    solver, e, steps, pairs = run_pipeline(RefBackend(ref, scene, 3), absorbing, reflecting, pde, ev, x, seed=11)
+    check_samplers(solver, absorbing, reflecting)
+    assert steps > 0 and pairs == solver.cache().n*len(x)
+    err = e.solution - cases.quadratic_exact(x)
+    # over sampler / walk seeds the rmse spreads over 0.016-0.040 and the common-mode error (the mean normal derivative of
+    # the cache enters every evaluation point alike) over +-0.035
+    assert np.sqrt(np.mean(err**2)) < 0.08 and abs(err.mean()) < 0.07, (np.sqrt(np.mean(err**2)), err.mean())
+    assert (e.bucketCount.sum(axis=1) > 0).all()          # every evaluation point got an estimate (splat or near-boundary walk)
+
+
+@pytest.mark.gpu
+def test_pipeline_on_the_device_matches_the_reference_backed_run(ctx, ref):
+    from zombie_b200 import native
+    whole, absorbing, reflecting, pde, ev = problem()
+    kw = cases.scene_kwargs(3, abi.REFLECTING_NEUMANN, absorbing, reflecting)
+    x = np.concatenate([cases.query_points(300, 3, 0.6, seed=5), cases.query_points(60, 3, 0.93, seed=6)])
+    gs, ge, gsteps, gpairs = run_pipeline(bvc.NativeBackend(ctx, native.Scene(ctx, 3, **kw)), absorbing, reflecting, pde, ev, x, seed=11)
+    rs, re_, rsteps, _ = run_pipeline(RefBackend(ref, ref.RefScene(3, **kw), 3), absorbing, reflecting, pde, ev, x, seed=11)
+    check_samplers(gs, absorbing, reflecting)
+    # the caches are the same points (same sampler seeds); cached estimates agree within Monte Carlo noise
+    assert np.array_equal(gs.caches["absorbing"].pt, rs.caches["absorbing"].pt)
+    assert np.allclose(gs.caches["absorbing"].dist_a, rs.caches["absorbing"].dist_a, rtol=1e-6)
+    assert abs(gsteps/float(rsteps) - 1.0) < 0.05
+    exact = cases.quadratic_exact(x)
+    gerr, rerr = ge.solution - exact, re_.solution - exact
+    assert np.sqrt(np.mean(gerr**2)) < 0.08 and abs(gerr.mean()) < 0.07
+    assert abs(np.sqrt(np.mean(gerr**2)) - np.sqrt(np.mean(rerr**2))) < 0.05
+    assert np.array_equal(ge.bucketCount, re_.bucketCount)

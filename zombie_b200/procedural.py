@@ -114,3 +114,27 @@ def pcg32_seed(initstate, initseq):
         state = state + initstate
         state = state * mult + inc
     return state, inc
+
+
+def bumpy_sphere_radius(directions, amplitude=0.15, seed=42, n_waves=3, max_freq=4.0):
+    """r(d) of bumpy_sphere for unit directions d (the same waves, so the mesh interpolates this surface)"""
+    rng = np.random.RandomState(seed)
+    w = rng.uniform(-max_freq, max_freq, size=(n_waves, 3))
+    phi = rng.uniform(0.0, 2.0 * np.pi, size=n_waves)
+    d = np.asarray(directions, np.float64)
+    return 1.0 + amplitude * np.sin(d @ w.T + phi[None, :]).sum(axis=1) / n_waves
+
+
+def bumpy_sphere_inside(x, margin=0.0, **kw):
+    """is x inside the solid r < r(x/|x|) - margin"""
+    x = np.asarray(x, np.float64)
+    r = np.linalg.norm(x, axis=1)
+    d = x / np.maximum(r, 1e-30)[:, None]
+    return r < bumpy_sphere_radius(d, **kw) - margin
+
+
+def bumpy_sphere_volume(n=400000, seed=1, **kw):
+    """volume of the solid: (4 pi / 3) E[r(d)^3] over uniform directions"""
+    d = np.random.RandomState(seed).normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return float(4.0 * np.pi / 3.0 * np.mean(bumpy_sphere_radius(d, **kw) ** 3))
