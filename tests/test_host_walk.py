@@ -28,7 +28,8 @@ def host_solve(tmp_path_factory):
     return exe
 
 
-def run_host(exe, d, dim, kind, absorbing, reflecting, x, n_walks, family, params, sigma, mu, rr, split, seed):
+def run_host(exe, d, dim, kind, absorbing, reflecting, x, n_walks, family, params, sigma, mu, rr, split, seed,
+             types=None, quantities=None, normals=None, directions=None):
     hdr = struct.pack("<4i16f4fQ", dim, kind, n_walks, family, *(list(params) + [0.0]*(16 - len(params))), sigma, mu, rr, split, seed)
     open(os.path.join(d, "hdr.bin"), "wb").write(hdr)
     empty = (np.zeros((0, dim), np.float32), np.zeros((0, dim), np.int32))
@@ -36,13 +37,22 @@ def run_host(exe, d, dim, kind, absorbing, reflecting, x, n_walks, family, param
         np.ascontiguousarray(pos, np.float32).tofile(os.path.join(d, name + "pos.bin"))
         np.ascontiguousarray(idx, np.int32).tofile(os.path.join(d, name + "idx.bin"))
     np.ascontiguousarray(x, np.float32).tofile(os.path.join(d, "pts.bin"))
+    for name, arr, dt in (("type", types, np.int32), ("quantity", quantities, np.int32), ("normal", normals, np.float32),
+                          ("dir", directions, np.float32)):
+        path = os.path.join(d, name + ".bin")
+        if arr is not None:
+            np.ascontiguousarray(arr, dt).tofile(path)
+        elif os.path.exists(path):
+            os.remove(path)
     r = subprocess.run([exe, d], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0 and "status 0" in r.stdout, r.stdout
-    out = np.fromfile(os.path.join(d, "out.bin"), np.float32).reshape(-1, 4)
+    out = np.fromfile(os.path.join(d, "out.bin"), np.float32).reshape(-1, 6)
     st = abi.HostStatistics(len(x), dim)
     st.solutionMean, st.solutionM2 = out[:, 0].copy(), out[:, 1].copy()
     st.nSolutionEstimates = out[:, 2].astype(np.int32)
     st.totalWalkLength = out[:, 3].astype(np.int32)
+    st.totalDerivativeContribution = out[:, 4].copy()
+    st.firstSphereRadius = out[:, 5].copy()
     return st
 
 
@@ -146,3 +156,43 @@ def test_device_star_radius_code_on_host_matches_reference(ref, host_query, tmp_
             assert ok.all(), (name, rr[bad], g[bad], base)
         assert np.mean(np.abs(rr - g)[~bad] <= 1e-5*np.maximum(rr[~bad], 1e-3) + 1e-7) > 0.99, name
     assert (rr < 0.999*da).mean() > 0.05
+
+
+def test_device_walk_code_on_host_at_cache_points(ref, host_solve, tmp_path):
+    """The sample points Boundary Value Caching solves at (boundary_value_caching.h:567-626): points ON the reflecting
+    boundary (walks start with a hemispherical step, walk_on_stars.h:410-416) and points displaced inward from the
+    absorbing boundary whose normal derivative is estimated as a directional derivative (walk_on_stars.h:665-848)."""
+    from zombie_b200 import bvc
+    whole, absorbing, reflecting = cases.mesh3d(3)
+    sa, sr = bvc.UniformBoundarySampler(*absorbing, seed=3), bvc.UniformBoundarySampler(*reflecting, seed=4)
+    sa.initialize(0.03, False)
+    sr.initialize(0.0, False)
+    a = sa.generate_samples(96, abi.ON_ABSORBING_BOUNDARY, 0.03)
+    r = sr.generate_samples(96, abi.ON_REFLECTING_BOUNDARY, 0.0)
+    x = np.concatenate([a.pt, r.pt])
+    normals = np.concatenate([a.normal, r.normal])
+    types = np.concatenate([a.type, r.type])
+    quantities = np.concatenate([np.full(96, abi.SOLUTION_AND_GRADIENT, np.int32), np.full(96, abi.SOLUTION, np.int32)])
+    n_walks = 256
+    st = run_host(host_solve, str(tmp_path), 3, abi.REFLECTING_NEUMANN, absorbing, reflecting, x, n_walks, abi.SOL_QUADRATIC,
+                  [1.0, -0.5, 0.25, 0.3], 0.0, 0.0, 0.0, abi.FLT_MAX, 0xBEEF, types=types, quantities=quantities,
+                  normals=normals, directions=normals)
+    rs = ref.RefScene(3, **cases.scene_kwargs(3, abi.REFLECTING_NEUMANN, absorbing, reflecting))
+    _, da, _, _ = rs.closest_point(abi.ABSORBING, x)
+    _, dr, _, _ = rs.closest_point(abi.REFLECTING, x)
+    pts = abi.HostSamplePoints(x, da, dr, nWalks=n_walks, estimationQuantity=quantities, type=types, normal=normals, seed=0xF00D)
+    pts.directionForDerivative = np.ascontiguousarray(normals)
+    rst = abi.HostStatistics(len(x), 3)
+    rsteps, _ = rs.solve(abi.WALK_ON_STARS, cases.quadratic_pde(), abi.WalkSettings.default(), pts, rst)
+    assert np.array_equal(st.nSolutionEstimates, rst.nSolutionEstimates)
+    assert abs(st.totalWalkLength.sum()/float(rsteps) - 1.0) < 0.04
+    assert np.allclose(st.firstSphereRadius, pts.firstSphereRadius, rtol=1e-5, atol=1e-7)
+    z = cases.z_scores(st, rst)
+    assert np.mean(np.abs(z) < 3.0) >= 0.97 and abs(z.mean()) < 0.3 and 0.75 < z.std() < 1.3, (z.mean(), z.std())
+    # getEstimatedDerivative (common.h:341-345) at the displaced absorbing points: same mean over the batch
+    dh = st.totalDerivativeContribution[:96]/np.maximum(1, st.nSolutionEstimates[:96])
+    dref = rst.totalDerivativeContribution[:96]/np.maximum(1, rst.nSolutionEstimates[:96])
+    exact = (np.stack([2.0*x[:96, 0], -x[:96, 1], 0.5*x[:96, 2]], 1)*normals[:96]).sum(1)
+    se = np.sqrt(np.var(dh - exact)/96 + np.var(dref - exact)/96)
+    assert abs(np.mean(dh - exact) - np.mean(dref - exact)) < 4.0*se + 0.02
+    assert abs(np.mean(dh - exact)) < 4.0*np.std(dh - exact)/np.sqrt(96) + 0.02

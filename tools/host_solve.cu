@@ -2,7 +2,9 @@
 // one walk at a time, thread-per-query traversals) on a problem dumped by a Python script, so that estimator
 // questions (bias vs the exact solution / the reference) can be studied without a GPU.
 //   nvcc -std=c++17 -O2 -DZB_HOST_STATS -Xcompiler -ffp-contract=off -o /tmp/host_solve tools/host_solve.cu zombie_b200/csrc/wide_bvh.cpp
-//   /tmp/host_solve <dir>   reads <dir>/{hdr,apos,aidx,rpos,ridx,pts}.bin, writes <dir>/out.bin (mean, m2, n, length per point)
+//   /tmp/host_solve <dir>   reads <dir>/{hdr,apos,aidx,rpos,ridx,pts}.bin and, when present, per-point
+//   {type,quantity}.bin (int32) and {normal,dir}.bin (float, dim per point); writes <dir>/out.bin
+//   (mean, m2, n, total walk length, derivative sum, firstSphereRadius per point)
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -14,9 +16,10 @@
 using namespace zb;
 namespace zb { long long g_zbClass[8] = {0}; void zbHostRecord(int, int, int) {} }
 
-template <typename T> static std::vector<T> rd(const std::string& p)
+template <typename T> static std::vector<T> rd(const std::string& p, bool optional = false)
 {
     FILE *f = fopen(p.c_str(), "rb");
+    if (!f && optional) return std::vector<T>();
     if (!f) { printf("cannot open %s\n", p.c_str()); exit(2); }
     fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET);
     std::vector<T> v(n/sizeof(T));
@@ -80,6 +83,11 @@ int run(const std::string& dir, const Header& h)
 
     std::vector<float> nrm(DIM*nPts, 0.0f), dA(nPts), dR(nPts, kMaxFloat), fsr(nPts, 0.0f);
     std::vector<int> type(nPts, 0), quantity(nPts, ZB_SOLUTION), nWalks(nPts, h.nWalks);
+    auto typeIn = rd<int>(dir + "/type.bin", true), quantityIn = rd<int>(dir + "/quantity.bin", true);
+    auto normalIn = rd<float>(dir + "/normal.bin", true), dirIn = rd<float>(dir + "/dir.bin", true);
+    if ((int)typeIn.size() == nPts) type = typeIn;
+    if ((int)quantityIn.size() == nPts) quantity = quantityIn;
+    if ((int)normalIn.size() == DIM*nPts) nrm = normalIn;
     std::vector<uint64_t> rs(nPts), ri(nPts);
     for (int i = 0; i < nPts; i++) {
         Pcg32 r; r.seed(h.seed, i); rs[i] = r.state; ri[i] = r.inc;
@@ -89,7 +97,7 @@ int run(const std::string& dir, const Header& h)
     }
     std::vector<float> mean(nPts, 0), m2(nPts, 0), gm(DIM*nPts, 0), gm2(DIM*nPts, 0), fs(nPts, 0), dc(nPts, 0);
     std::vector<int> ns(nPts, 0), ng(nPts, 0), wl(nPts, 0), sp(nPts, 0);
-    a.pts = zb_sample_points{nPts, pt.data(), nrm.data(), nullptr, type.data(), quantity.data(), dA.data(), dR.data(), nullptr, nWalks.data(), rs.data(), ri.data(), fsr.data()};
+    a.pts = zb_sample_points{nPts, pt.data(), nrm.data(), (int)dirIn.size() == DIM*nPts ? dirIn.data() : nullptr, type.data(), quantity.data(), dA.data(), dR.data(), nullptr, nWalks.data(), rs.data(), ri.data(), fsr.data()};
     a.stats = zb_statistics{mean.data(), m2.data(), gm.data(), gm2.data(), fs.data(), dc.data(), ns.data(), ng.data(), wl.data(), sp.data()};
     std::vector<int> taskCount(nPts), stratCount(nPts);
     std::vector<long long> taskOffset(nPts + 1, 0), stratOffset(nPts + 1, 0);
@@ -123,7 +131,7 @@ int run(const std::string& dir, const Header& h)
     for (int i = 0; i < nPts; i++) steps += reducePoint<DIM>(a, i);
     printf("points %d walks %lld steps %lld status %d\n", nPts, total, steps, status);
     FILE *f = fopen((dir + "/out.bin").c_str(), "wb");
-    for (int i = 0; i < nPts; i++) { float rec[4] = {mean[i], m2[i], (float)ns[i], (float)wl[i]}; fwrite(rec, 4, 4, f); }
+    for (int i = 0; i < nPts; i++) { float rec[6] = {mean[i], m2[i], (float)ns[i], (float)wl[i], dc[i], fsr[i]}; fwrite(rec, 4, 6, f); }
     fclose(f);
     return 0;
 }
