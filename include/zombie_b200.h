@@ -251,6 +251,43 @@ int zb_bvc_splat_dev(zb_context *ctx, int dim, float absorptionCoeff, const zb_b
 /* CUDA-event duration of the last zb_bvc_splat(_dev) kernel on this context (measurement hook) */
 int zb_context_last_splat_ms(zb_context *ctx, float *ms);
 
+/* ---- Reverse Walk on Stars: replaces rws::ReverseWalkOnStarsSolver::solve
+ * (zombie/variance_reduction/reverse_walk_solver.h:287-330) = ReverseWalkOnStars::solve at every sample point
+ * (zombie/point_estimation/reverse_walk_on_stars.h:89-195) + rws::splatContribution at every step (:233-283). ---- */
+/* SoA of the zombie::SamplePoint fields a reverse walk reads (common.h:182-194). type: ZB_ON_ABSORBING_BOUNDARY (sample
+ * displaced inward by normalOffsetForAbsorbingBoundary), ZB_ON_REFLECTING_BOUNDARY, ZB_IN_DOMAIN (source sample). The
+ * contribution of every sample (Dirichlet / Robin / source value) is evaluated from the PDE like the reference does.
+ * rngState is in/out. Host arrays. */
+typedef struct zb_rws_samples {
+    int32_t n;
+    const float *pt;                              /* n*dim */
+    const float *normal;                          /* n*dim */
+    const int32_t *type;                          /* zb_sample_type */
+    const uint8_t *estimateBoundaryNormalAligned; /* or NULL */
+    const float *pdf;
+    const float *distToAbsorbingBoundary;
+    const float *distToReflectingBoundary;
+    uint64_t *rngState;                           /* in/out */
+    uint64_t *rngInc;
+} zb_rws_samples;
+
+/* SoA of rws::EvaluationPoint (reverse_walk_solver.h:20-52). totals: 6 running sums per point — totalPoissonKernel-
+ * Contribution, totalAbsorbingBoundary-, -NormalAligned-, totalReflectingBoundary-, -NormalAligned-, totalSource-
+ * Contribution — in/out, so repeated solves accumulate like the reference's; EvaluationPoint::getEstimatedSolution
+ * (:129-166) divides them by the sample counts. */
+typedef struct zb_rws_eval_points {
+    int32_t n;
+    const float *pt;      /* n*dim */
+    const float *normal;  /* n*dim or NULL */
+    const int32_t *type;  /* zb_sample_type; points on the absorbing boundary take no splats (:251) */
+    float *totals;        /* n*6, in/out */
+} zb_rws_eval_points;
+
+/* walkSteps / splatRecords (optional): walk steps taken and splat records (= ball visits) gathered. */
+int zb_rws_solve(zb_scene *scene, const zb_pde_desc *pde, const zb_walk_settings *settings, const zb_rws_samples *samples,
+                 float normalOffsetForAbsorbingBoundary, float radiusClamp, float kernelRegularization,
+                 zb_rws_eval_points *evalPts, int64_t *walkSteps, int64_t *splatRecords);
+
 /* pcg32 known-answer hook (deps/pcg32/pcg32.h:53-100): seeds a device generator with
  * (initstate, initseq) and returns n successive nextUInt() values */
 int zb_pcg32_kat(zb_context *ctx, uint64_t initstate, uint64_t initseq, int n, uint32_t *out);

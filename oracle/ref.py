@@ -41,6 +41,8 @@ def lib():
         _lib.zref_kelvin_transform_points.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _lib.zref_kelvin_robin_coefficients.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p]*5
         _lib.zref_kelvin_back_transform.argtypes = [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p]*5
+        _lib.zref_rws_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p,
+                                        C.c_int, C.c_void_p, C.c_void_p]
         _lib.zref_pcg32.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
         _lib.zref_pcg32_demo.argtypes = [C.c_uint64, C.c_uint64, C.c_int] + [C.c_void_p]*4
         _lib.zref_pcg32_floats.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
@@ -208,6 +210,17 @@ class RefScene:
                                     abi.ptr(fl), abi.ptr(out), threads)
         assert rc == 0
         return out
+
+    def rws_solve(self, pde, settings, samples, eval_pts, normal_offset, radius_clamp=0.0, kernel_regularization=0.0, threads=0):
+        """rws::ReverseWalkOnStarsSolver::solve on abi.HostRwsSamples / abi.HostRwsEvalPoints (totals accumulate).
+        Returns (group counts [5], seconds)."""
+        counts = np.zeros(5, np.int32)
+        secs = C.c_double(0.0)
+        ss, es = samples.as_struct(), eval_pts.as_struct()
+        rc = lib().zref_rws_solve(self._h, C.byref(pde), C.byref(settings), C.byref(ss), normal_offset, radius_clamp,
+                                  kernel_regularization, C.byref(es), threads, abi.ptr(counts), C.byref(secs))
+        assert rc == 0
+        return counts, secs.value
 
     def solve(self, estimator, pde, settings, pts, stats, threads=0):
         """WalkOnSpheres/WalkOnStars::solve; threads: 0 = TBB default arena, 1 = runSingleThreaded.

@@ -15,6 +15,8 @@
 #include <zombie/utils/fcpw_geometric_queries.h>
 #include <zombie/variance_reduction/kelvin_transform.h>
 #include <zombie/variance_reduction/boundary_value_caching.h>
+#include <zombie/variance_reduction/reverse_walk_solver.h>
+#include <zombie/utils/nearest_neighbor_finder.h>
 #include "oneapi/tbb/global_control.h"
 #include "oneapi/tbb/task_arena.h"
 
@@ -425,6 +427,74 @@ void kelvinBack(const float *origin, int n, const float *y, const float *V, cons
     }
 }
 
+// rws::ReverseWalkOnStarsSolver with caller-made sample points instead of its samplers' (reverse_walk_solver.h:54-108)
+template <size_t DIM>
+struct RwsAccess: public rws::ReverseWalkOnStarsSolver<float, DIM, NearestNeighborFinder<DIM>> {
+    using Base = rws::ReverseWalkOnStarsSolver<float, DIM, NearestNeighborFinder<DIM>>;
+    RwsAccess(const GeometricQueries<DIM>& q): Base(q, nullptr, nullptr, nullptr) {}
+    std::vector<SamplePoint<float, DIM>>& group(int type, bool aligned) {
+        if (type == ZB_ON_ABSORBING_BOUNDARY) return aligned ? this->absorbingBoundaryNormalAlignedSamplePts : this->absorbingBoundarySamplePts;
+        if (type == ZB_ON_REFLECTING_BOUNDARY) return aligned ? this->reflectingBoundaryNormalAlignedSamplePts : this->reflectingBoundarySamplePts;
+        return this->domainSamplePts;
+    }
+};
+
+template <size_t DIM>
+int rwsSolve(RefScene<DIM>& s, const zb_pde_desc *pdeDesc, const zb_walk_settings *ws, const zb_rws_samples *smp,
+             float normalOffset, float radiusClamp, float kernelRegularization, zb_rws_eval_points *ev, int nThreads,
+             int32_t *groupCounts, double *seconds)
+{
+    PDE<float, DIM> pde;
+    buildPde<DIM>(*pdeDesc, pde);
+    WalkSettings settings = toSettings(*ws);
+    RwsAccess<DIM> solver(*s.queries);
+    for (int i = 0; i < smp->n; i++) {
+        bool aligned = smp->estimateBoundaryNormalAligned && smp->estimateBoundaryNormalAligned[i];
+        SamplePoint<float, DIM> p(toVec<DIM>(smp->pt + DIM*i), toVec<DIM>(smp->normal + DIM*i), (SampleType)smp->type[i],
+                                  EstimationQuantity::Solution, smp->pdf[i], smp->distToAbsorbingBoundary[i],
+                                  smp->distToReflectingBoundary[i]);
+        p.rng.state = smp->rngState[i];
+        p.rng.inc = smp->rngInc[i];
+        p.estimateBoundaryNormalAligned = aligned;
+        solver.group(smp->type[i], aligned).push_back(p);
+    }
+    std::vector<rws::EvaluationPoint<float, DIM>> evalPts;
+    Vec<DIM> zero = Vec<DIM>::Zero();
+    for (int i = 0; i < ev->n; i++) {
+        evalPts.emplace_back(toVec<DIM>(ev->pt + DIM*i), ev->normal ? toVec<DIM>(ev->normal + DIM*i) : zero,
+                             (SampleType)ev->type[i], 0.0f, 0.0f);
+        rws::EvaluationPoint<float, DIM>& e = evalPts.back();
+        e.totalPoissonKernelContribution = ev->totals[6*i];
+        e.totalAbsorbingBoundaryContribution = ev->totals[6*i + 1];
+        e.totalAbsorbingBoundaryNormalAlignedContribution = ev->totals[6*i + 2];
+        e.totalReflectingBoundaryContribution = ev->totals[6*i + 3];
+        e.totalReflectingBoundaryNormalAlignedContribution = ev->totals[6*i + 4];
+        e.totalSourceContribution = ev->totals[6*i + 5];
+    }
+    std::unique_ptr<tbb::global_control> gc;
+    if (nThreads > 0) gc.reset(new tbb::global_control(tbb::global_control::max_allowed_parallelism, (size_t)nThreads));
+    auto t0 = std::chrono::steady_clock::now();
+    solver.solve(pde, settings, normalOffset, radiusClamp, kernelRegularization, evalPts, true, nThreads == 1);
+    if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    for (int i = 0; i < ev->n; i++) {
+        const rws::EvaluationPoint<float, DIM>& e = evalPts[i];
+        ev->totals[6*i] = e.totalPoissonKernelContribution;
+        ev->totals[6*i + 1] = e.totalAbsorbingBoundaryContribution;
+        ev->totals[6*i + 2] = e.totalAbsorbingBoundaryNormalAlignedContribution;
+        ev->totals[6*i + 3] = e.totalReflectingBoundaryContribution;
+        ev->totals[6*i + 4] = e.totalReflectingBoundaryNormalAlignedContribution;
+        ev->totals[6*i + 5] = e.totalSourceContribution;
+    }
+    if (groupCounts) {
+        groupCounts[0] = solver.getAbsorbingBoundarySampleCount(false);
+        groupCounts[1] = solver.getAbsorbingBoundarySampleCount(true);
+        groupCounts[2] = solver.getReflectingBoundarySampleCount(false);
+        groupCounts[3] = solver.getReflectingBoundarySampleCount(true);
+        groupCounts[4] = solver.getDomainSampleCount();
+    }
+    return ZB_OK;
+}
+
 } // namespace
 
 #define DISPATCH(scene, expr2, expr3) \
@@ -567,6 +637,15 @@ int zref_kelvin_back_transform(int dim, const float *origin, int n, const float 
     if (dim == 2) kelvinBack<2>(origin, n, y, V, dV, u, du);
     else kelvinBack<3>(origin, n, y, V, dV, u, du);
     return 0;
+}
+
+// rws::ReverseWalkOnStarsSolver::solve on caller-made samples; totals (n*6) are in/out
+int zref_rws_solve(void *scene, const zb_pde_desc *pde, const zb_walk_settings *ws, const zb_rws_samples *samples,
+                   float normalOffset, float radiusClamp, float kernelRegularization, zb_rws_eval_points *evalPts,
+                   int nThreads, int32_t *groupCounts, double *seconds)
+{
+    return DISPATCH(scene, rwsSolve<2>(*((AnyScene *)scene)->s2, pde, ws, samples, normalOffset, radiusClamp, kernelRegularization, evalPts, nThreads, groupCounts, seconds),
+                           rwsSolve<3>(*((AnyScene *)scene)->s3, pde, ws, samples, normalOffset, radiusClamp, kernelRegularization, evalPts, nThreads, groupCounts, seconds));
 }
 
 } // extern "C"

@@ -245,3 +245,72 @@ class HostBvcEvalPoints:
     def bucket_mean(self):
         """per-bucket Welford means [n, 5, 1 + dim] (0 where a bucket is empty)"""
         return self.bucketSum/np.maximum(1, self.bucketCount)[:, :, None]
+
+
+class RwsSamples(C.Structure):
+    """zb_rws_samples: SoA of the zombie::SamplePoint fields a reverse walk reads."""
+    _fields_ = [("n", C.c_int32), ("pt", C.c_void_p), ("normal", C.c_void_p), ("type", C.c_void_p),
+                ("estimateBoundaryNormalAligned", C.c_void_p), ("pdf", C.c_void_p), ("distToAbsorbingBoundary", C.c_void_p),
+                ("distToReflectingBoundary", C.c_void_p), ("rngState", C.c_void_p), ("rngInc", C.c_void_p)]
+
+
+class RwsEvalPoints(C.Structure):
+    """zb_rws_eval_points: SoA of rws::EvaluationPoint; totals = 6 running sums per point."""
+    _fields_ = [("n", C.c_int32), ("pt", C.c_void_p), ("normal", C.c_void_p), ("type", C.c_void_p), ("totals", C.c_void_p)]
+
+
+class HostRwsSamples:
+    def __init__(self, pt, normal, type, pdf, distToAbsorbingBoundary, distToReflectingBoundary, aligned=None, seed=0xC0FFEE,
+                 streams=None):
+        from .procedural import pcg32_seed
+        self.pt = np.ascontiguousarray(pt, np.float32)
+        self.n, self.dim = self.pt.shape
+        self.normal = np.ascontiguousarray(normal, np.float32)
+        self.type = np.ascontiguousarray(type, np.int32)
+        self.estimateBoundaryNormalAligned = np.zeros(self.n, np.uint8) if aligned is None else np.ascontiguousarray(aligned, np.uint8)
+        self.pdf = np.ascontiguousarray(pdf, np.float32)
+        self.distToAbsorbingBoundary = np.ascontiguousarray(distToAbsorbingBoundary, np.float32)
+        self.distToReflectingBoundary = np.ascontiguousarray(distToReflectingBoundary, np.float32)
+        if streams is None:
+            streams = np.arange(self.n, dtype=np.uint64)
+        st, inc = pcg32_seed(np.full(self.n, seed, np.uint64), np.asarray(streams, np.uint64))
+        self.rngState, self.rngInc = np.ascontiguousarray(st), np.ascontiguousarray(inc)
+
+    def as_struct(self):
+        return RwsSamples(self.n, ptr(self.pt), ptr(self.normal), ptr(self.type), ptr(self.estimateBoundaryNormalAligned),
+                          ptr(self.pdf), ptr(self.distToAbsorbingBoundary), ptr(self.distToReflectingBoundary),
+                          ptr(self.rngState), ptr(self.rngInc))
+
+    def group_counts(self):
+        """sample counts per statistics group: absorbing, absorbing aligned, reflecting, reflecting aligned, domain"""
+        al = self.estimateBoundaryNormalAligned != 0
+        a, r = self.type == ON_ABSORBING_BOUNDARY, self.type == ON_REFLECTING_BOUNDARY
+        return np.array([np.sum(a & ~al), np.sum(a & al), np.sum(r & ~al), np.sum(r & al), np.sum(self.type == IN_DOMAIN)], np.int64)
+
+
+class HostRwsEvalPoints:
+    def __init__(self, pt, type=IN_DOMAIN, normal=None):
+        self.pt = np.ascontiguousarray(pt, np.float32)
+        self.n, self.dim = self.pt.shape
+        self.normal = np.zeros_like(self.pt) if normal is None else np.ascontiguousarray(normal, np.float32)
+        self.type = np.full(self.n, type, np.int32) if np.isscalar(type) else np.ascontiguousarray(type, np.int32)
+        self.totals = np.zeros((self.n, 6), np.float32)
+
+    def as_struct(self):
+        return RwsEvalPoints(self.n, ptr(self.pt), ptr(self.normal), ptr(self.type), ptr(self.totals))
+
+    def estimated_solution(self, group_counts, dirichlet=None):
+        """rws::EvaluationPoint::getEstimatedSolution (reverse_walk_solver.h:129-166); points on the absorbing boundary
+        take `dirichlet` (the solver assigns pde.dirichlet there, :324-329)"""
+        t = self.totals.astype(np.float64)
+        n = np.asarray(group_counts, np.float64)
+        sol = np.zeros(self.n)
+        if n[0] > 0:
+            sol += np.where(t[:, 0] > 0.0, t[:, 1]/np.where(t[:, 0] > 0.0, t[:, 0], 1.0), t[:, 1]/n[0])
+        for k, col in ((1, 2), (2, 3), (3, 4), (4, 5)):
+            if n[k] > 0:
+                sol += t[:, col]/n[k]
+        on_abs = self.type == ON_ABSORBING_BOUNDARY
+        if dirichlet is not None:
+            sol = np.where(on_abs, dirichlet, sol)
+        return sol.astype(np.float32)

@@ -11,6 +11,7 @@
 #include "../../include/zombie_b200.h"
 #include "capi_common.h"
 #include "walk.cuh"
+#include "rws.cuh"
 #include "wide_bvh.h"
 
 using namespace zb;
@@ -386,7 +387,8 @@ int solveRange(zb_scene *scene, SolveArgs& a, int n, bool anyGradient)
     }
     ZB_CUDA(cudaEventRecord(ctx->ev[2], stream));
 
-    reducePointsKernel<DIM><<<blocksFor(n, threads), threads, 0, stream>>>(a);
+    if (a.rwsRecords) rwsFinishKernel<DIM><<<blocksFor(n, threads), threads, 0, stream>>>(a);
+    else reducePointsKernel<DIM><<<blocksFor(n, threads), threads, 0, stream>>>(a);
     ZB_CUDA(cudaGetLastError());
     ZB_CUDA(cudaEventRecord(ctx->ev[3], stream));
     ctx->profiled = true;
@@ -849,6 +851,148 @@ int zb_solve(zb_scene *scene, int estimator, const zb_pde_desc *pde, const zb_wa
     if (rc != ZB_OK) return rc;
     if (walkSteps) ZB_CUDA(cudaMemcpyAsync(walkSteps, base + stepsOff, 8, cudaMemcpyDeviceToHost, ctx->stream));
     return stageOut(ctx, plan);
+}
+
+int zb_rws_solve(zb_scene *scene, const zb_pde_desc *pde, const zb_walk_settings *settings, const zb_rws_samples *smp,
+                 float normalOffsetForAbsorbingBoundary, float radiusClamp, float kernelRegularization,
+                 zb_rws_eval_points *ev, int64_t *walkSteps, int64_t *splatRecords)
+{
+    if (!scene || !pde || !settings || !smp || !ev) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_rws_solve: NULL argument");
+    if (smp->n < 0 || ev->n < 0) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_rws_solve: negative count");
+    if (walkSteps) *walkSteps = 0;
+    if (splatRecords) *splatRecords = 0;
+    if (smp->n == 0 || ev->n == 0) return ZB_OK;
+    if (!smp->pt || !smp->normal || !smp->type || !smp->pdf || !smp->distToAbsorbingBoundary || !smp->distToReflectingBoundary ||
+        !smp->rngState || !smp->rngInc) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_rws_solve: a sample array is NULL");
+    if (!ev->pt || !ev->type || !ev->totals) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_rws_solve: an evaluation-point array is NULL");
+    if (pde->kelvin) return fail(ZB_ERR_UNSUPPORTED, "zb_rws_solve: Kelvin-transformed PDEs are not supported");
+    if (!(normalOffsetForAbsorbingBoundary > 0.0f)) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_rws_solve: normalOffsetForAbsorbingBoundary must be > 0");
+    zb_context *ctx = scene->ctx;
+    ZB_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)smp->n, m = (size_t)ev->n, dim = (size_t)scene->dim;
+
+    // samples whose contribution the settings switch off take no walk (reverse_walk_on_stars.h:95-124)
+    std::vector<int32_t> quantity(n);
+    for (size_t i = 0; i < n; i++) {
+        int t = smp->type[i];
+        bool off = t == ZB_IN_DOMAIN ? settings->ignoreSourceContribution != 0
+                 : (t == ZB_ON_ABSORBING_BOUNDARY ? settings->ignoreAbsorbingBoundaryContribution != 0
+                                                  : settings->ignoreReflectingBoundaryContribution != 0);
+        quantity[i] = off ? ZB_SKIP : ZB_SOLUTION;
+    }
+
+    IoPlan plan;
+    size_t ptOff = plan.addIn(smp->pt, 4*dim*n), nOff = plan.addIn(smp->normal, 4*dim*n), tyOff = plan.addIn(smp->type, 4*n),
+           qOff = plan.addIn(quantity.data(), 4*n), alOff = plan.addIn(smp->estimateBoundaryNormalAligned, smp->estimateBoundaryNormalAligned ? n : 0),
+           pdfOff = plan.addIn(smp->pdf, 4*n), daOff = plan.addIn(smp->distToAbsorbingBoundary, 4*n),
+           drOff = plan.addIn(smp->distToReflectingBoundary, 4*n), incOff = plan.addIn(smp->rngInc, 8*n);
+    size_t stOff = plan.addIn(smp->rngState, 8*n);
+    plan.outputs.push_back({(void *)smp->rngState, 8*n}); plan.outOffsets.push_back(stOff);
+    size_t ePtOff = plan.addIn(ev->pt, 4*dim*m), eNOff = plan.addIn(ev->normal, ev->normal ? 4*dim*m : 0), eTyOff = plan.addIn(ev->type, 4*m);
+    size_t totOff = plan.addIn(ev->totals, 4*6*m);
+    plan.outputs.push_back({(void *)ev->totals, 4*6*m}); plan.outOffsets.push_back(totOff);
+    // scratch: nWalks (all 1), firstSphereRadius, contribution, record count
+    auto scratch = [&](size_t bytes) { plan.total = (plan.total + 255) & ~size_t(255); size_t o = plan.total; plan.total += bytes; return o; };
+    size_t nwOff = scratch(4*n), fsrOff = scratch(4*n), conOff = scratch(4*n), cntOff = scratch(8), stepsOff = scratch(8);
+
+    long long capacity = std::max<long long>((long long)n*64, 1 << 18);
+    for (int attempt = 0; attempt < 3; attempt++) {
+        int rc = stageIn(ctx, plan);
+        if (rc != ZB_OK) return rc;
+        char *base = ctx->io.as<char>();
+        ZB_CUDA(ctx->rwsRecords.reserve((size_t)capacity*48 + 256));
+        ZB_CUDA(cudaMemsetAsync(base + cntOff, 0, 8, ctx->stream));
+        ZB_CUDA(cudaMemsetAsync(base + stepsOff, 0, 8, ctx->stream));
+        ZB_CUDA(cudaMemsetAsync(base + fsrOff, 0, 4*n, ctx->stream));
+        std::vector<int32_t> ones(n, 1);
+        ZB_CUDA(cudaMemcpyAsync(base + nwOff, ones.data(), 4*n, cudaMemcpyHostToDevice, ctx->stream));
+
+        SolveArgs a;
+        fillSceneArgs(scene, a);
+        a.estimator = ZB_WALK_ON_STARS;
+        a.ws = *settings;
+        a.pde = *pde;
+        a.pts.n = (int32_t)n;
+        a.pts.pt = (const float *)(base + ptOff);
+        a.pts.normal = (const float *)(base + nOff);
+        a.pts.directionForDerivative = nullptr;
+        a.pts.type = (const int32_t *)(base + tyOff);
+        a.pts.estimationQuantity = (const int32_t *)(base + qOff);
+        a.pts.distToAbsorbingBoundary = (const float *)(base + daOff);
+        a.pts.distToReflectingBoundary = (const float *)(base + drOff);
+        a.pts.estimateBoundaryNormalAligned = smp->estimateBoundaryNormalAligned ? (const uint8_t *)(base + alOff) : nullptr;
+        a.pts.nWalks = (const int32_t *)(base + nwOff);
+        a.pts.rngState = (uint64_t *)(base + stOff);
+        a.pts.rngInc = (uint64_t *)(base + incOff);
+        a.pts.firstSphereRadius = (float *)(base + fsrOff);
+        a.walkSteps = (long long *)(base + stepsOff);
+
+        // 1. what every sample carries (needs the caller's ignore flags)
+        const int threads = 128;
+        if (scene->dim == 3) {
+            ZB_CUDA(cudaFuncSetAttribute(rwsContributionKernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
+            rwsContributionKernel<3><<<blocksFor((int)n, threads), threads, kCoopSmem, ctx->stream>>>(a, (float *)(base + conOff));
+        } else {
+            ZB_CUDA(cudaFuncSetAttribute(rwsContributionKernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
+            rwsContributionKernel<2><<<blocksFor((int)n, threads), threads, kCoopSmem, ctx->stream>>>(a, (float *)(base + conOff));
+        }
+        ZB_CUDA(cudaGetLastError());
+        ctx->launches += 1;
+
+        // 2. the walks: forward WoSt steps without boundary / source terms, one splat record per step
+        a.ws.ignoreReflectingBoundaryContribution = 1;
+        a.ws.ignoreSourceContribution = 1;
+        a.rwsRecords = ctx->rwsRecords.as<float4>();
+        a.rwsCount = (unsigned long long *)(base + cntOff);
+        a.rwsCapacity = capacity;
+        a.rwsPdf = (const float *)(base + pdfOff);
+        a.rwsContribution = (const float *)(base + conOff);
+        a.rwsNormalOffset = normalOffsetForAbsorbingBoundary;
+        rc = scene->dim == 3 ? solveRange<3>(scene, a, (int)n, false) : solveRange<2>(scene, a, (int)n, false);
+        if (rc != ZB_OK) return rc;
+        unsigned long long count = 0;
+        long long steps = 0;
+        ZB_CUDA(cudaMemcpyAsync(&count, base + cntOff, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        ZB_CUDA(cudaMemcpyAsync(&steps, base + stepsOff, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        ZB_CUDA(cudaStreamSynchronize(ctx->stream));
+        rc = checkStatus(ctx, "zb_rws_solve");
+        if (rc != ZB_OK) return rc;
+        if ((long long)count > capacity) { // the record buffer was too small: run the same walks again with room for all of them
+            capacity = (long long)count + (long long)count/8 + 1024;
+            continue;
+        }
+
+        // 3. gather
+        RwsGatherArgs g;
+        std::memset(&g, 0, sizeof(g));
+        g.reflecting = scene->boundary[ZB_REFLECTING].view;
+        g.hasReflecting = scene->boundary[ZB_REFLECTING].present ? 1 : 0;
+        g.records = ctx->rwsRecords.as<float4>();
+        g.nRecords = (long long)count;
+        g.nEval = (int)m;
+        g.evalPt = (const float *)(base + ePtOff);
+        g.evalNormal = ev->normal ? (const float *)(base + eNOff) : nullptr;
+        g.evalType = (const int *)(base + eTyOff);
+        g.totals = (float *)(base + totOff);
+        g.sqrtLambda = pde->absorptionCoeff > 0.0f ? std::sqrt(pde->absorptionCoeff) : 0.0f;
+        g.radiusClamp = radiusClamp;
+        g.kernelRegularization = kernelRegularization;
+        // reverse_walk_solver.h:244-245
+        bool selfNorm = scene->watertight != 0 && pde->absorptionCoeff == 0.0f;
+        if (g.hasReflecting && selfNorm) selfNorm = pde->areRobinConditionsPureNeumann != 0;
+        g.useSelfNormalization = selfNorm ? 1 : 0;
+        g.status = ctx->status.as<int>();
+        if (scene->dim == 3) rwsGatherKernel<3><<<blocksFor((int)m, kRwsThreads), kRwsThreads, 0, ctx->stream>>>(g);
+        else rwsGatherKernel<2><<<blocksFor((int)m, kRwsThreads), kRwsThreads, 0, ctx->stream>>>(g);
+        ZB_CUDA(cudaGetLastError());
+        ctx->launches += 1;
+        rc = stageOut(ctx, plan);
+        if (rc != ZB_OK) return rc;
+        if (walkSteps) *walkSteps = steps;
+        if (splatRecords) *splatRecords = (int64_t)count;
+        return checkStatus(ctx, "zb_rws_solve");
+    }
+    return fail(ZB_ERR_OUT_OF_MEMORY, "zb_rws_solve: the splat-record buffer kept overflowing");
 }
 
 #ifdef ZB_STATS

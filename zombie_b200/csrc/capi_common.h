@@ -55,7 +55,7 @@ struct zb_context {
     cudaStream_t stream = nullptr;
     bool ownsStream = false;
     zb::DeviceBuffer status, counters, perPoint, strat, records, scanTemp, io;
-    zb::DeviceBuffer bvcSamples, bvcIo;
+    zb::DeviceBuffer bvcSamples, bvcIo, rwsRecords;
     int *hostStatus = nullptr; // pinned
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; // solve start | walk start | walk end | solve end
     cudaEvent_t evSplat[2] = {nullptr, nullptr};

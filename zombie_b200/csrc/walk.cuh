@@ -51,6 +51,14 @@ struct SolveArgs {
     long long *walkSteps;
     long long totalTasks;
     int anyGradient;
+    // Reverse Walk on Stars (rws.cuh): when rwsRecords is set the walks are reverse walks started at sample points,
+    // one per point, and every step appends one splat record (the ball and the weight carried by the walk)
+    float4 *rwsRecords;               // 3 float4 per record
+    unsigned long long *rwsCount;     // records appended so far
+    long long rwsCapacity;
+    const float *rwsPdf;              // per sample point
+    const float *rwsContribution;     // per sample point
+    float rwsNormalOffset;            // normalOffsetForAbsorbingBoundary
 };
 
 template <int DIM>
@@ -225,7 +233,10 @@ ZB_DEV void countTasksPoint(const SolveArgs& a, int i)
     int type = a.pts.type[i];
     int nWalks = a.pts.nWalks[i];
     int tasks = 0, strat = 0;
-    if (quantity == ZB_SOLUTION_AND_GRADIENT) {
+    if (a.rwsRecords) {
+        // ReverseWalkOnStars::solve (reverse_walk_on_stars.h:89-166): one walk per sample point
+        tasks = quantity == ZB_SKIP ? 0 : 1;
+    } else if (quantity == ZB_SOLUTION_AND_GRADIENT) {
         int nAnti = 1;
         if (a.ws.useGradientAntitheticVariates) { nWalks = max(1, nWalks/2); nAnti = 2; }
         nWalks = max(0, nWalks);
@@ -264,7 +275,9 @@ ZB_DEV bool preparePointNoQuery(const SolveArgs& a, int i, bool& flip)
     float distA = a.pts.distToAbsorbingBoundary[i];
     bool wost = a.estimator == ZB_WALK_ON_STARS;
 
-    if (quantity == ZB_SOLUTION_AND_GRADIENT) {
+    if (a.rwsRecords) {
+        a.pts.firstSphereRadius[i] = 0.0f; // a reverse walk queries its first star like any other (reverse_walk_on_stars.h:283-309)
+    } else if (quantity == ZB_SOLUTION_AND_GRADIENT) {
         float boundaryDist = wost ? fminf(distA, a.pts.distToReflectingBoundary[i]) : distA;
         a.pts.firstSphereRadius[i] = 0.99f*boundaryDist;
         // generateStratifiedSamples<DIM-1>(2*nWalks) (sampling.h:436-458): jittered diagonal, then one
@@ -365,6 +378,7 @@ struct Lane {
     float firstSource;
     Vec<DIM> gradBoundary, gradSource;
     long long task;
+    int point;             // index of the sample point the task belongs to
     int totalLength;
     int splits;
     int nQueued;
@@ -393,6 +407,7 @@ ZB_DEV void beginTask(const SolveArgs& a, Lane<DIM>& L, long long task)
     Vec<DIM> x = loadVec<DIM>(a.pts.pt + (size_t)DIM*i);
     bool yukawa = a.pde.absorptionCoeff > 0.0f && a.ws.stepsBeforeApplyingTikhonov == 0;
     L.task = task;
+    L.point = i;
     L.active = true;
     L.total = 0.0f;
     L.totalLength = 0;
@@ -408,7 +423,7 @@ ZB_DEV void beginTask(const SolveArgs& a, Lane<DIM>& L, long long task)
     L.st.throughput = 1.0f;
     L.st.walkLength = 0;
     L.firstStep = true;
-    L.gradient = a.pts.estimationQuantity[i] == ZB_SOLUTION_AND_GRADIENT;
+    L.gradient = !a.rwsRecords && a.pts.estimationQuantity[i] == ZB_SOLUTION_AND_GRADIENT;
     L.needClosest = false;
     L.keepDistA = false;
 
@@ -584,6 +599,37 @@ ZB_DEV bool stepStarPrologue(const SolveArgs& a, Lane<DIM>& L, float& starRadius
     return true;
 }
 
+// One splat record of a reverse walk: the current ball and the weight the walk carries into it
+// (rws::splatContribution, zombie/variance_reduction/reverse_walk_solver.h:233-283, evaluation-point independent part):
+//   q0 = (centre, R)   q1 = (current normal, v)   q2 = (v * contribution, flags, 0, 0)
+// v = alpha * throughput / pdf (/ normalOffset for samples of the absorbing boundary); flags: bits 0-2 the statistics
+// bucket (0 absorbing, 1 absorbing normal-aligned, 2 reflecting, 3 reflecting normal-aligned, 4 source), bit 3 walk is on
+// the reflecting boundary, bit 4 the ball uses the Yukawa Green's function.
+template <int DIM>
+ZB_DEV void rwsEmit(const SolveArgs& a, const Lane<DIM>& L)
+{
+#if defined(__CUDA_ARCH__)
+    unsigned long long slot = atomicAdd(a.rwsCount, 1ull);
+#else
+    unsigned long long slot = (*a.rwsCount)++;
+#endif
+    if ((long long)slot >= a.rwsCapacity) return; // counted, not stored: the host sees count > capacity and retries
+    int i = L.point;
+    int type = a.pts.type[i];
+    bool aligned = a.pts.estimateBoundaryNormalAligned && a.pts.estimateBoundaryNormalAligned[i];
+    uint32_t bucket = type == ZB_ON_ABSORBING_BOUNDARY ? (aligned ? 1u : 0u) : (type == ZB_ON_REFLECTING_BOUNDARY ? (aligned ? 3u : 2u) : 4u);
+    float v = (L.st.onRefl ? 2.0f : 1.0f)*L.st.throughput/a.rwsPdf[i];
+    if (type == ZB_ON_ABSORBING_BOUNDARY) v /= a.rwsNormalOffset;
+    uint32_t flags = bucket | (L.st.onRefl ? 8u : 0u) | (L.g.yukawa ? 16u : 0u);
+    float4 q0, q1, q2;
+    q0.x = L.st.pt[0]; q0.y = L.st.pt[1]; q0.z = DIM == 3 ? L.st.pt[DIM - 1] : 0.0f; q0.w = L.g.R;
+    q1.x = L.st.normal[0]; q1.y = L.st.normal[1]; q1.z = DIM == 3 ? L.st.normal[DIM - 1] : 0.0f; q1.w = v;
+    q2.x = v*a.rwsContribution[i]; q2.y = zb_uint_as_float(flags); q2.z = 0.0f; q2.w = 0.0f;
+    a.rwsRecords[3*slot] = q0;
+    a.rwsRecords[3*slot + 1] = q1;
+    a.rwsRecords[3*slot + 2] = q2;
+}
+
 // The rest of one iteration of the while loop of WalkOnStars::walk (walk_on_stars.h:401-487) given the
 // star radius, or the whole iteration of WalkOnSpheres::walk (walk_on_spheres.h:237-288). The distance
 // to the absorbing boundary at the new position is left pending (L.needClosest).
@@ -613,6 +659,7 @@ ZB_DEV StepResult stepBody(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *que
         if (outsideDomain<DIM>(a, st.pt)) return kEscaped;
     } else {
         L.g.updateBall(st.pt, starRadius);
+        if (a.rwsRecords) rwsEmit<DIM>(a, L); // splatContribution (reverse_walk_on_stars.h:319)
 
         // --- direction, hemispherical on the reflecting boundary (:410-416)
         Vec<DIM> dir = uniformDirection<DIM>(L.rng);

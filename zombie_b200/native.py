@@ -21,7 +21,7 @@ SYMBOLS = ["zb_last_error", "zb_abi_version", "zb_device_count", "zb_context_cre
            "zb_context_last_solve_profile",
            "zb_host_bvh_check", "zb_scene_create", "zb_scene_destroy", "zb_scene_update_robin_coefficients", "zb_scene_stats",
            "zb_closest_point", "zb_intersect_ray", "zb_occluded", "zb_sample_sphere", "zb_star_radius",
-           "zb_solve", "zb_solve_dev", "zb_bvc_splat", "zb_bvc_splat_dev", "zb_context_last_splat_ms",
+           "zb_solve", "zb_solve_dev", "zb_bvc_splat", "zb_bvc_splat_dev", "zb_context_last_splat_ms", "zb_rws_solve",
            "zb_pcg32_kat", "zb_pcg32_demo", "zb_pcg32_floats"]
 
 
@@ -64,6 +64,7 @@ def lib():
         l.zb_bvc_splat.argtypes = [vp, i, f, vp, f, f, f, f, f, vp, C.POINTER(C.c_int64)]
         l.zb_bvc_splat_dev.argtypes = [vp, i, f, vp, f, f, f, f, f, vp, C.POINTER(C.c_int64)]
         l.zb_context_last_splat_ms.argtypes = [vp, C.POINTER(C.c_float)]
+        l.zb_rws_solve.argtypes = [vp, vp, vp, vp, f, f, f, vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         l.zb_pcg32_kat.argtypes = [vp, C.c_uint64, C.c_uint64, i, vp]
         l.zb_pcg32_demo.argtypes = [vp, C.c_uint64, C.c_uint64, i, vp, vp, vp, vp]
         l.zb_pcg32_floats.argtypes = [vp, C.c_uint64, C.c_uint64, i, vp]
@@ -284,6 +285,15 @@ class Scene:
         _check(lib().zb_solve(self._h, estimator, C.byref(pde), C.byref(settings), C.byref(ps), C.byref(ss),
                               C.byref(steps)), "zb_solve")
         return steps.value
+
+    def rws_solve(self, pde, settings, samples, eval_pts, normal_offset, radius_clamp=0.0, kernel_regularization=0.0):
+        """rws::ReverseWalkOnStarsSolver::solve (reverse_walk_solver.h:287-330): samples = abi.HostRwsSamples (rngState
+        advances), eval_pts = abi.HostRwsEvalPoints (totals accumulate). Returns (walk steps, splat records)."""
+        steps, records = C.c_int64(0), C.c_int64(0)
+        ss, es = samples.as_struct(), eval_pts.as_struct()
+        _check(lib().zb_rws_solve(self._h, C.byref(pde), C.byref(settings), C.byref(ss), normal_offset, radius_clamp,
+                                  kernel_regularization, C.byref(es), C.byref(steps), C.byref(records)), "zb_rws_solve")
+        return steps.value, records.value
 
     def solve_dev(self, estimator, pde, settings, pts_struct, stats_struct, steps_dev_ptr=None):
         """Same with every array already resident on the device (abi.SamplePoints / abi.Statistics of
