@@ -246,8 +246,11 @@ def run_native(args, rank, world, local_rank):
     prof_steps, local_walk_ms = steps_dev, walk_ms  # this rank's kernel: its steps / its kernel time
 
     # ---- end-to-end arm: host buffers through zb_solve --------------------------------------------
+    # (at most 3 timed steps after 1 warm-up: the end-to-end arm repeats the device arm's work plus the copies, and the
+    # whole default run has to end within minutes)
+    e2e_warmup, e2e_steps = min(1, args.warmup), min(3, args.steps)
     host_sets = []
-    for s in range(n_steps):
+    for s in range(e2e_warmup + e2e_steps):
         hp = make_points(w, batch_indices(s), dist_a, dist_r, 1 << 40)
         hs = abi.HostStatistics(hp.n, 3)
         # pinned host memory
@@ -268,12 +271,12 @@ def run_native(args, rank, world, local_rank):
     n, dim = host_sets[0][0].n, 3
     h2d = n*(4*dim*3 + 4*6 + 1 + 8*2) + n*(4*2 + 4*dim*2 + 4*2 + 4*4)
     d2h = n*(8 + 4) + n*(4*2 + 4*dim*2 + 4*2 + 4*4) + 8
-    for s in range(args.warmup):
+    for s in range(e2e_warmup):
         scene.solve(w.estimator, w.pde, w.settings, *host_sets[s])
     barrier()
     t0 = time.perf_counter()
     steps_e2e = 0
-    for s in range(args.warmup, n_steps):
+    for s in range(e2e_warmup, e2e_warmup + e2e_steps):
         steps_e2e += scene.solve(w.estimator, w.pde, w.settings, *host_sets[s])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
@@ -290,7 +293,7 @@ def run_native(args, rank, world, local_rank):
         prof_steps_all = prof_steps
 
     # ---- parity smoke on the estimates of the last timed batch (exact solution is known) ----------
-    hp, hs = host_sets[n_steps - 1]
+    hp, hs = host_sets[-1]
     rmse = float(np.sqrt(np.mean((hs.solutionMean - w.exact(hp.pt))**2)))
 
     if rank == 0:
@@ -309,7 +312,7 @@ def run_native(args, rank, world, local_rank):
                              % ((scene.stats(0)["bytes"] + scene.stats(1)["bytes"])/1e6, walk_tasks/max(1, args.steps)*40/1e6),
                        "bvh_build_s": build_s, "rmse_vs_exact_last_batch": rmse},
             "e2e": {"value": steps_e2e/e2e_s, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3*e2e_s/args.steps},
+                    "ms_per_step": 1e3*e2e_s/max(1, e2e_steps), "steps": e2e_steps},
             "gpu_launches": int(launches_timed),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak,
@@ -319,7 +322,7 @@ def run_native(args, rank, world, local_rank):
                          "traffic_note": "ncu --set full of the same kernel on a 512-point launch (profiles/README.md): 20 KB of "
                                          "DRAM traffic and 44 K warp instructions per walk step; issue/latency bound, not HBM bound"},
         }
-        if not args.no_cpu and world >= 1:
+        if not args.no_cpu and world == 1:   # the CPU baseline is reported at N = 1 only
             line["cpu_baseline"] = cpu_baseline(args, w)
         print(json.dumps(line))
     if dist is not None:
