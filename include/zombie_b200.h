@@ -236,9 +236,8 @@ typedef struct zb_bvc_eval_points {
 
 /* BoundaryValueCaching::splat(pde, samplePts, radiusClamp, kernelRegularization,
  * robinCoeffCutoffForNormalDerivative, cutoffDistToAbsorbingBoundary, cutoffDistToReflectingBoundary,
- * evalPts) (:482-502). absorptionCoeff = pde.absorptionCoeff selects Yukawa (> 0) or harmonic kernels.
- * 2D Yukawa (modified Bessel functions) is not implemented: ZB_ERR_UNSUPPORTED. pairs (optional) receives the
- * number of (sample, evaluation point) pairs evaluated. Evaluation-point arrays are host pointers. */
+ * evalPts) (:482-502). absorptionCoeff = pde.absorptionCoeff selects Yukawa (> 0) or harmonic kernels. pairs
+ * (optional) receives the number of (sample, evaluation point) pairs evaluated. Evaluation-point arrays are host pointers. */
 int zb_bvc_splat(zb_context *ctx, int dim, float absorptionCoeff, const zb_bvc_samples *samples,
                  float radiusClamp, float kernelRegularization, float robinCoeffCutoffForNormalDerivative,
                  float cutoffDistToAbsorbingBoundary, float cutoffDistToReflectingBoundary,

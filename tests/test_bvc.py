@@ -61,6 +61,17 @@ def numpy_splat(dim, sigma, s, e, radius_clamp, reg, robin_cutoff, cutoff_a, cut
             Pk = ndot*c/r**3
             dG = -xy*(c/r**3)[..., None]
             dP = (nrm[None] - (3*ndot/(r*r))[..., None]*xy)*(c/r**3)[..., None]
+    elif sigma > 0:
+        from scipy.special import kv
+        c = f(1.0/(2.0*math.pi))
+        mu = f(math.sqrt(sigma))
+        mur = (r*mu).astype(np.float64)
+        K0, K1, K2 = kv(0, mur).astype(f), kv(1, mur).astype(f), kv(2, mur).astype(f)
+        q1, q2 = mu*K1, f(sigma)*(K0 + K2)/2
+        G = K0*c
+        Pk = ndot*q1*c/r
+        dG = -xy*(q1*c/r)[..., None]
+        dP = (nrm[None]*q1[..., None] - ((ndot/(r*r))*(q1 + r*q2))[..., None]*xy)*(c/r)[..., None]
     else:
         c = f(1.0/(2.0*math.pi))
         G = -np.log(r)*c
@@ -121,9 +132,10 @@ CASES = [
     dict(dim=2, sigma=0.0, reg=0.0, robin_cutoff=1.0),
     dict(dim=2, sigma=0.0, reg=0.05, robin_cutoff=1.0),
 ]
+CPU_ONLY_CASES = [dict(dim=2, sigma=3.0, reg=0.0, robin_cutoff=1.0)]   # its GPU run lives in tests/test_z_rws.py
 
 
-@pytest.mark.parametrize("c", CASES, ids=lambda c: "dim%d_sigma%g_reg%g" % (c["dim"], c["sigma"], c["reg"]))
+@pytest.mark.parametrize("c", CASES + CPU_ONLY_CASES, ids=lambda c: "dim%d_sigma%g_reg%g" % (c["dim"], c["sigma"], c["reg"]))
 def test_reference_splat_matches_formula_restatement(ref, c):
     """CPU: pins the oracle wrapper (oracle/ref_capi.cpp: zref_bvc_splat) and the restated formulas the kernel
     implements against each other, including the cutoff-distance rule and boundary evaluation points."""
@@ -140,6 +152,10 @@ def test_reference_splat_matches_formula_restatement(ref, c):
 @pytest.mark.gpu
 @pytest.mark.parametrize("c", CASES, ids=lambda c: "dim%d_sigma%g_reg%g" % (c["dim"], c["sigma"], c["reg"]))
 def test_gpu_splat_matches_reference(ctx, ref, c):
+    check_gpu_splat(ctx, ref, c)
+
+
+def check_gpu_splat(ctx, ref, c):
     s, e = make_problem(c["dim"], 3000, 5000, seed=23, on_boundary_eval=True)
     sol, grad, cnt, mean, _ = ref.bvc_splat(c["dim"], c["sigma"], s, e, 1e-3, c["reg"], c["robin_cutoff"], 0.12, 0.0)
     pairs = ctx.bvc_splat(c["dim"], c["sigma"], s, e, 1e-3, c["reg"], c["robin_cutoff"], 0.12, 0.0)
@@ -176,4 +192,4 @@ def test_gpu_splat_edge_cases(ctx):
     assert not e0.solution.any() and not e0.bucketCount.any()
     with pytest.raises(native.ZombieError):
         s2, e2 = make_problem(2, 10, 10, seed=1)
-        ctx.bvc_splat(2, 1.0, s2, e2)                              # 2D Yukawa is reported, not silently wrong
+        ctx.bvc_splat(2, -1.0, s2, e2)                             # a negative absorption coefficient is an error, not a crash

@@ -113,3 +113,11 @@ def test_gpu_reverse_walk_matches_reference(ctx, ref):
     ev2 = abi.HostRwsEvalPoints(x[:8], type=abi.ON_ABSORBING_BOUNDARY)
     sc.rws_solve(cases.quadratic_pde(), abi.WalkSettings.default(), smp, ev2, OFFSET)
     assert not ev2.totals.any()
+
+
+@pytest.mark.gpu
+def test_gpu_bvc_splat_2d_yukawa(ctx, ref):
+    """the 2D screened-Poisson free-space kernels (modified Bessel functions, distributions.h:215-262) of zb_bvc_splat;
+    here, after the longer-standing GPU tests, because it first runs on a GPU at the end of round 1"""
+    from tests import test_bvc
+    test_bvc.check_gpu_splat(ctx, ref, dict(dim=2, sigma=3.0, reg=0.0, robin_cutoff=1.0))

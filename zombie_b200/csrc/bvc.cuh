@@ -17,7 +17,7 @@
 // FP32-compute-bound: ~100 flop per pair against 48 B of sample data amortised over the whole CTA.
 #pragma once
 
-#include "vec.cuh"
+#include "greens.cuh"
 
 namespace zb {
 
@@ -81,7 +81,7 @@ __device__ __forceinline__ void freeSpaceKernels(const Vec<DIM>& xy, float r, co
                 dP[k] = (n[k]*Qr1 - s*xy[k])*inv4pir2;
             }
         }
-    } else {
+    } else if (!YUKAWA) {
         const float inv2pi = 1.0f/(2.0f*kPiF);
         float r2 = r*r;
         float inv2pir2 = inv2pi/r2;
@@ -91,6 +91,24 @@ __device__ __forceinline__ void freeSpaceKernels(const Vec<DIM>& xy, float r, co
         for (int k = 0; k < DIM; k++) {
             dG[k] = -xy[k]*inv2pir2;
             dP[k] = (n[k] - s*xy[k])*inv2pir2;
+        }
+    } else {
+        // YukawaGreensFnFreeSpace<2> (distributions.h:215-262): modified Bessel functions K0, K1, K2 evaluated in double like
+        // zombie/core/bessel.h, K2 by the recurrence bessk(2, x) uses (bessel.h:345-360)
+        const float inv2pi = 1.0f/(2.0f*kPiF);
+        float r2 = r*r;
+        float mur = r*sqrtLambda;
+        float K0 = (float)bessel::k0((double)mur), K1 = (float)bessel::k1((double)mur);
+        float K2 = (float)(bessel::k0((double)mur) + (2.0/(double)mur)*bessel::k1((double)mur));
+        float lambda = sqrtLambda*sqrtLambda;
+        float Qr1 = sqrtLambda*K1, Qr2 = lambda*(K0 + K2)/2.0f;
+        float inv2pir = inv2pi/r;
+        G = K0*inv2pi;
+        P = ndotxy*Qr1*inv2pir;
+        float s = (ndotxy/r2)*(Qr1 + r*Qr2);
+        for (int k = 0; k < DIM; k++) {
+            dG[k] = -xy[k]*Qr1*inv2pir;
+            dP[k] = (n[k]*Qr1 - s*xy[k])*inv2pir;
         }
     }
 }

@@ -58,7 +58,8 @@ int launchSplat(zb_context *ctx, int dim, bool yukawa, const BvcArgs& a)
         if (yukawa) bvcSplatKernel<3, true><<<blocks, kBvcThreads, 0, ctx->stream>>>(a);
         else bvcSplatKernel<3, false><<<blocks, kBvcThreads, 0, ctx->stream>>>(a);
     } else {
-        bvcSplatKernel<2, false><<<blocks, kBvcThreads, 0, ctx->stream>>>(a);
+        if (yukawa) bvcSplatKernel<2, true><<<blocks, kBvcThreads, 0, ctx->stream>>>(a);
+        else bvcSplatKernel<2, false><<<blocks, kBvcThreads, 0, ctx->stream>>>(a);
     }
     ZB_CUDA(cudaGetLastError());
     ZB_CUDA(cudaEventRecord(ctx->evSplat[1], ctx->stream));
@@ -73,8 +74,6 @@ int validate(const char *name, zb_context *ctx, int dim, float absorptionCoeff, 
     if (dim != 2 && dim != 3) return fail(ZB_ERR_INVALID_ARGUMENT, std::string(name) + ": dim must be 2 or 3");
     if (s->n < 0 || e->n < 0) return fail(ZB_ERR_INVALID_ARGUMENT, std::string(name) + ": negative count");
     if (absorptionCoeff < 0.0f) return fail(ZB_ERR_INVALID_ARGUMENT, std::string(name) + ": absorptionCoeff must be >= 0");
-    if (dim == 2 && absorptionCoeff > 0.0f)
-        return fail(ZB_ERR_UNSUPPORTED, std::string(name) + ": the 2D Yukawa free-space kernel (modified Bessel functions) is not implemented");
     if (s->n > 0 && (!s->pt || !s->normal || !s->type || !s->pdf || !s->solution || !s->normalDerivative || !s->contribution || !s->robinCoeff))
         return fail(ZB_ERR_INVALID_ARGUMENT, std::string(name) + ": a sample array is NULL");
     if (e->n > 0 && (!e->pt || !e->type || !e->distToAbsorbingBoundary || !e->distToReflectingBoundary || !e->bucketCount ||
