@@ -951,6 +951,192 @@ protected:
     const GeometricQueries<DIM>& queries;
 };
 
+// ------------------------------------------------------------------------------------------------
+// Boundary Value Caching: the splat (zombie/variance_reduction/boundary_value_caching.h)
+// ------------------------------------------------------------------------------------------------
+namespace bvc {
+
+template <typename T, size_t DIM> class BoundaryValueCaching;
+
+template <typename T, size_t DIM>
+struct EvaluationPoint { // boundary_value_caching.h:18-56. The five SampleStatistics are kept as (count, sums): a Welford mean is sum/N
+    EvaluationPoint(const Vector<DIM>& pt_, const Vector<DIM>& normal_, SampleType type_, float distToAbsorbingBoundary_,
+                    float distToReflectingBoundary_):
+        pt(pt_), normal(normal_), type(type_), distToAbsorbingBoundary(distToAbsorbingBoundary_),
+        distToReflectingBoundary(distToReflectingBoundary_) { reset(); }
+    T getEstimatedSolution() const { T s = T(0.0f); for (int b = 0; b < ZB_BVC_BUCKETS; b++) s += mean(b, 0); return s; }
+    void getEstimatedGradient(std::vector<T>& gradient) const {
+        gradient.resize(DIM);
+        for (size_t k = 0; k < DIM; k++) gradient[k] = getEstimatedGradient((int)k);
+    }
+    T getEstimatedGradient(int channel) const { T s = T(0.0f); for (int b = 0; b < ZB_BVC_BUCKETS; b++) s += mean(b, 1 + channel); return s; }
+    void reset() { for (int b = 0; b < ZB_BVC_BUCKETS; b++) { count[b] = 0; for (size_t k = 0; k < 1 + DIM; k++) sums[b][k] = 0.0f; } }
+
+    Vector<DIM> pt;
+    Vector<DIM> normal;
+    SampleType type;
+    float distToAbsorbingBoundary;
+    float distToReflectingBoundary;
+
+protected:
+    T mean(int b, int k) const { return count[b] > 0 ? sums[b][k]/(float)count[b] : T(0.0f); }
+    int32_t count[ZB_BVC_BUCKETS];
+    float sums[ZB_BVC_BUCKETS][1 + DIM];
+    template <typename A, size_t B> friend class BoundaryValueCaching;
+};
+
+template <typename T, size_t DIM>
+class BoundaryValueCaching { // boundary_value_caching.h:58-193 (the splat overloads)
+public:
+    BoundaryValueCaching(const GeometricQueries<DIM>& queries_, const WalkOnStars<T, DIM>& walkOnStars_):
+        queries(queries_), walkOnStars(walkOnStars_) {}
+
+    // splats sample pt data to the input evaluation pts (:482-502): one zb_bvc_splat
+    void splat(const PDE<T, DIM>& pde, const std::vector<SamplePoint<T, DIM>>& samplePts, float radiusClamp,
+               float kernelRegularization, float robinCoeffCutoffForNormalDerivative, float cutoffDistToAbsorbingBoundary,
+               float cutoffDistToReflectingBoundary, std::vector<EvaluationPoint<T, DIM>>& evalPts,
+               std::function<void(int, int)> reportProgress = {}) const {
+        size_t n = samplePts.size(), m = evalPts.size();
+        if (n == 0 || m == 0) return;
+        std::vector<float> spt(n*DIM), snormal(n*DIM), pdf(n), solution(n), normalDerivative(n), contribution(n), robinCoeff(n);
+        std::vector<int32_t> stype(n);
+        std::vector<uint8_t> aligned(n);
+        for (size_t i = 0; i < n; i++) {
+            const SamplePoint<T, DIM>& p = samplePts[i];
+            for (size_t k = 0; k < DIM; k++) { spt[i*DIM + k] = p.pt[k]; snormal[i*DIM + k] = p.normal[k]; }
+            stype[i] = (int32_t)p.type; aligned[i] = p.estimateBoundaryNormalAligned ? 1 : 0;
+            pdf[i] = p.pdf; solution[i] = p.solution; normalDerivative[i] = p.normalDerivative; contribution[i] = p.contribution;
+            robinCoeff[i] = p.robinCoeff;
+        }
+        zb_bvc_samples s{(int32_t)n, spt.data(), snormal.data(), stype.data(), aligned.data(), pdf.data(), solution.data(),
+                         normalDerivative.data(), contribution.data(), robinCoeff.data()};
+        std::vector<float> ept(m*DIM), da(m), dr(m), bucketSum(m*ZB_BVC_BUCKETS*(1 + DIM)), sol(m), grad(m*DIM);
+        std::vector<int32_t> etype(m), bucketCount(m*ZB_BVC_BUCKETS);
+        for (size_t i = 0; i < m; i++) {
+            const EvaluationPoint<T, DIM>& e = evalPts[i];
+            for (size_t k = 0; k < DIM; k++) ept[i*DIM + k] = e.pt[k];
+            etype[i] = (int32_t)e.type; da[i] = e.distToAbsorbingBoundary; dr[i] = e.distToReflectingBoundary;
+            for (int b = 0; b < ZB_BVC_BUCKETS; b++) {
+                bucketCount[i*ZB_BVC_BUCKETS + b] = e.count[b];
+                for (size_t k = 0; k < 1 + DIM; k++) bucketSum[(i*ZB_BVC_BUCKETS + b)*(1 + DIM) + k] = e.sums[b][k];
+            }
+        }
+        zb_bvc_eval_points ev{(int32_t)m, ept.data(), etype.data(), da.data(), dr.data(), bucketCount.data(), bucketSum.data(),
+                              sol.data(), grad.data()};
+        detail::check(zb_bvc_splat(detail::context()->ctx, (int)DIM, pde.absorptionCoeff, &s, radiusClamp, kernelRegularization,
+                                   robinCoeffCutoffForNormalDerivative, cutoffDistToAbsorbingBoundary, cutoffDistToReflectingBoundary,
+                                   &ev, nullptr));
+        for (size_t i = 0; i < m; i++) {
+            EvaluationPoint<T, DIM>& e = evalPts[i];
+            for (int b = 0; b < ZB_BVC_BUCKETS; b++) {
+                e.count[b] = bucketCount[i*ZB_BVC_BUCKETS + b];
+                for (size_t k = 0; k < 1 + DIM; k++) e.sums[b][k] = bucketSum[(i*ZB_BVC_BUCKETS + b)*(1 + DIM) + k];
+            }
+        }
+        if (reportProgress) reportProgress((int)n, 0);
+    }
+
+protected:
+    const GeometricQueries<DIM>& queries;
+    const WalkOnStars<T, DIM>& walkOnStars;
+};
+
+} // namespace bvc
+
+// ------------------------------------------------------------------------------------------------
+// Reverse Walk on Stars (zombie/variance_reduction/reverse_walk_solver.h)
+// ------------------------------------------------------------------------------------------------
+namespace rws {
+
+template <typename T, size_t DIM>
+struct EvaluationPoint { // reverse_walk_solver.h:20-52 (no mutex: the device gather needs none)
+    EvaluationPoint(const Vector<DIM>& pt_, const Vector<DIM>& normal_, SampleType type_, float distToAbsorbingBoundary_,
+                    float distToReflectingBoundary_):
+        pt(pt_), normal(normal_), type(type_), distToAbsorbingBoundary(distToAbsorbingBoundary_),
+        distToReflectingBoundary(distToReflectingBoundary_) { reset(); }
+    T getEstimatedSolution(int nAbsorbingBoundarySamples, int nAbsorbingBoundaryNormalAlignedSamples, int nReflectingBoundarySamples,
+                           int nReflectingBoundaryNormalAlignedSamples, int nSourceSamples) const { // :129-166
+        if (type == SampleType::OnAbsorbingBoundary) return totalAbsorbingBoundaryContribution;
+        T solution(0.0f);
+        if (nAbsorbingBoundarySamples > 0) {
+            if (totalPoissonKernelContribution > 0.0f) solution += totalAbsorbingBoundaryContribution/totalPoissonKernelContribution;
+            else solution += totalAbsorbingBoundaryContribution/(float)nAbsorbingBoundarySamples;
+        }
+        if (nAbsorbingBoundaryNormalAlignedSamples > 0) solution += totalAbsorbingBoundaryNormalAlignedContribution/(float)nAbsorbingBoundaryNormalAlignedSamples;
+        if (nReflectingBoundarySamples > 0) solution += totalReflectingBoundaryContribution/(float)nReflectingBoundarySamples;
+        if (nReflectingBoundaryNormalAlignedSamples > 0) solution += totalReflectingBoundaryNormalAlignedContribution/(float)nReflectingBoundaryNormalAlignedSamples;
+        if (nSourceSamples > 0) solution += totalSourceContribution/(float)nSourceSamples;
+        return solution;
+    }
+    void reset() {
+        totalPoissonKernelContribution = 0.0f;
+        totalAbsorbingBoundaryContribution = totalAbsorbingBoundaryNormalAlignedContribution = T(0.0f);
+        totalReflectingBoundaryContribution = totalReflectingBoundaryNormalAlignedContribution = totalSourceContribution = T(0.0f);
+    }
+
+    Vector<DIM> pt;
+    Vector<DIM> normal;
+    SampleType type;
+    float distToAbsorbingBoundary;
+    float distToReflectingBoundary;
+    float totalPoissonKernelContribution;
+    T totalAbsorbingBoundaryContribution;
+    T totalAbsorbingBoundaryNormalAlignedContribution;
+    T totalReflectingBoundaryContribution;
+    T totalReflectingBoundaryNormalAlignedContribution;
+    T totalSourceContribution;
+};
+
+// rws::ReverseWalkOnStarsSolver::solve (:287-330) on caller-made sample points (the reference draws them with its
+// BoundarySampler / DomainSampler; zombie_b200/bvc.py has those samplers): one zb_rws_solve. samplePts' rng advances.
+template <typename T, size_t DIM>
+void solve(const GeometricQueries<DIM>& queries, const PDE<T, DIM>& pde, const WalkSettings& walkSettings,
+           std::vector<SamplePoint<T, DIM>>& samplePts, float normalOffsetForAbsorbingBoundary, float radiusClamp,
+           float kernelRegularization, std::vector<EvaluationPoint<T, DIM>>& evalPts)
+{
+    size_t n = samplePts.size(), m = evalPts.size();
+    if (n == 0 || m == 0) return;
+    std::vector<float> spt(n*DIM), snormal(n*DIM), pdf(n), da(n), dr(n);
+    std::vector<int32_t> stype(n);
+    std::vector<uint8_t> aligned(n);
+    std::vector<uint64_t> state(n), inc(n);
+    for (size_t i = 0; i < n; i++) {
+        const SamplePoint<T, DIM>& p = samplePts[i];
+        for (size_t k = 0; k < DIM; k++) { spt[i*DIM + k] = p.pt[k]; snormal[i*DIM + k] = p.normal[k]; }
+        stype[i] = (int32_t)p.type; aligned[i] = p.estimateBoundaryNormalAligned ? 1 : 0; pdf[i] = p.pdf;
+        da[i] = p.distToAbsorbingBoundary; dr[i] = p.distToReflectingBoundary; state[i] = p.rng.state; inc[i] = p.rng.inc;
+    }
+    zb_rws_samples s{(int32_t)n, spt.data(), snormal.data(), stype.data(), aligned.data(), pdf.data(), da.data(), dr.data(),
+                     state.data(), inc.data()};
+    std::vector<float> ept(m*DIM), enormal(m*DIM), totals(m*6);
+    std::vector<int32_t> etype(m);
+    for (size_t i = 0; i < m; i++) {
+        const EvaluationPoint<T, DIM>& e = evalPts[i];
+        for (size_t k = 0; k < DIM; k++) { ept[i*DIM + k] = e.pt[k]; enormal[i*DIM + k] = e.normal[k]; }
+        etype[i] = (int32_t)e.type;
+        totals[6*i] = e.totalPoissonKernelContribution; totals[6*i + 1] = e.totalAbsorbingBoundaryContribution;
+        totals[6*i + 2] = e.totalAbsorbingBoundaryNormalAlignedContribution; totals[6*i + 3] = e.totalReflectingBoundaryContribution;
+        totals[6*i + 4] = e.totalReflectingBoundaryNormalAlignedContribution; totals[6*i + 5] = e.totalSourceContribution;
+    }
+    zb_rws_eval_points ev{(int32_t)m, ept.data(), enormal.data(), etype.data(), totals.data()};
+    zb_pde_desc desc = pde.descriptor();
+    zb_walk_settings ws = walkSettings.toAbi();
+    detail::check(zb_rws_solve(queries.scene(), &desc, &ws, &s, normalOffsetForAbsorbingBoundary, radiusClamp, kernelRegularization,
+                               &ev, nullptr, nullptr));
+    for (size_t i = 0; i < n; i++) samplePts[i].rng.state = state[i];
+    for (size_t i = 0; i < m; i++) {
+        EvaluationPoint<T, DIM>& e = evalPts[i];
+        e.totalPoissonKernelContribution = totals[6*i]; e.totalAbsorbingBoundaryContribution = totals[6*i + 1];
+        e.totalAbsorbingBoundaryNormalAlignedContribution = totals[6*i + 2]; e.totalReflectingBoundaryContribution = totals[6*i + 3];
+        e.totalReflectingBoundaryNormalAlignedContribution = totals[6*i + 4]; e.totalSourceContribution = totals[6*i + 5];
+        // evaluation points on the absorbing boundary take the Dirichlet data (:324-329)
+        if (e.type == SampleType::OnAbsorbingBoundary)
+            e.totalAbsorbingBoundaryContribution = !walkSettings.ignoreAbsorbingBoundaryContribution ? pde.dirichlet(e.pt, false) : T(0.0f);
+    }
+}
+
+} // namespace rws
+
 } // namespace zombie_b200
 
 #if !defined(ZOMBIE_B200_NO_ALIAS)

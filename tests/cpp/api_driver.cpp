@@ -107,9 +107,35 @@ static int run(const Header& h, FILE *f, const char *outPath)
     float d0 = queries.computeDistToAbsorbingBoundary(x[0], false);
     if (h.nPa > 0 && d0 != distA[0]) { fprintf(stderr, "single/batched distance mismatch %g %g\n", d0, distA[0]); return 4; }
 
+    // Boundary Value Caching splat and Reverse Walk on Stars through the same surface: a cache made of the solved
+    // points themselves (solution = estimate, no flux), splatted onto / walked towards two interior points
+    float bvcSolution = 0.0f, rwsSolution = 0.0f;
+    if (DIM == 3 || h.absorptionCoeff == 0.0f) {
+        std::vector<SamplePoint<float, DIM>> cache;
+        for (int i = 0; i < h.nPts && i < 32; i++) {
+            SamplePoint<float, DIM> c = samplePts[i];
+            c.type = SampleType::InDomain;       // treated as source samples by both solvers
+            c.pdf = 1.0f;
+            c.contribution = statistics[i].getEstimatedSolution();
+            cache.push_back(c);
+        }
+        WalkOnStars<float, DIM> wostForCache(queries);
+        bvc::BoundaryValueCaching<float, DIM> caching(queries, wostForCache);
+        std::vector<bvc::EvaluationPoint<float, DIM>> bvcPts;
+        bvcPts.emplace_back(x[0], Vector<DIM>::Zero(), SampleType::InDomain, distA[0], distR[0]);
+        caching.splat(pde, cache, 1e-3f, 0.0f, std::numeric_limits<float>::max(), 0.0f, 0.0f, bvcPts);
+        bvcSolution = bvcPts[0].getEstimatedSolution();
+        std::vector<rws::EvaluationPoint<float, DIM>> rwsPts;
+        rwsPts.emplace_back(x[0], Vector<DIM>::Zero(), SampleType::InDomain, distA[0], distR[0]);
+        rws::solve<float, DIM>(queries, pde, settings, cache, 0.01f, 1e-3f, 0.0f, rwsPts);
+        rwsSolution = rwsPts[0].getEstimatedSolution(0, 0, 0, 0, (int)cache.size());
+    }
+
     FILE *o = fopen(outPath, "wb");
     if (!o) return 2;
     fwrite(&steps, sizeof(steps), 1, o);
+    fwrite(&bvcSolution, sizeof(float), 1, o);
+    fwrite(&rwsSolution, sizeof(float), 1, o);
     for (int i = 0; i < h.nPts; i++) {
         const SampleStatistics<float, DIM>& s = statistics[i];
         float rec[8] = {s.getEstimatedSolution(), s.getEstimatedSolutionVariance(), (float)s.getSolutionEstimateCount(),

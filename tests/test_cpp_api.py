@@ -48,7 +48,9 @@ def write_problem(path, dim, estimator, kind, absorbing, reflecting, pts, n_walk
 def read_result(path, n):
     raw = open(path, "rb").read()
     steps = struct.unpack("<q", raw[:8])[0]
-    rec = np.frombuffer(raw[8:], np.float32).reshape(n, 8)
+    extras = struct.unpack("<2f", raw[8:16])     # BVC / RWS estimates at the first point (finite when the calls ran)
+    rec = np.frombuffer(raw[16:], np.float32).reshape(n, 8)
+    assert np.isfinite(extras).all()
     return steps, rec
 
 
