@@ -25,7 +25,7 @@ struct Header {
 };
 
 template <size_t DIM>
-static int run(const Header& h, FILE *f, const char *outPath)
+static int run(const Header& h, FILE *f, const char *outPath, bool extras)
 {
     using namespace zombie; // = zombie_b200: the same names user code uses with the reference
     std::vector<float> ap, rp, mn, mx, pts;
@@ -110,7 +110,7 @@ static int run(const Header& h, FILE *f, const char *outPath)
     // Boundary Value Caching splat and Reverse Walk on Stars through the same surface: a cache made of the solved
     // points themselves (solution = estimate, no flux), splatted onto / walked towards two interior points
     float bvcSolution = 0.0f, rwsSolution = 0.0f;
-    if (DIM == 3 || h.absorptionCoeff == 0.0f) {
+    if (extras) {
         std::vector<SamplePoint<float, DIM>> cache;
         for (int i = 0; i < h.nPts && i < 32; i++) {
             SamplePoint<float, DIM> c = samplePts[i];
@@ -150,13 +150,14 @@ static int run(const Header& h, FILE *f, const char *outPath)
 
 int main(int argc, char **argv)
 {
-    if (argc < 3) { fprintf(stderr, "usage: api_driver <problem.bin> <out.bin>\n"); return 2; }
+    if (argc < 3) { fprintf(stderr, "usage: api_driver <problem.bin> <out.bin> [extras]\n"); return 2; }
     FILE *f = fopen(argv[1], "rb");
     if (!f) return 2;
     Header h;
     if (fread(&h, sizeof(h), 1, f) != 1) return 2;
     try {
-        int rc = h.dim == 2 ? run<2>(h, f, argv[2]) : run<3>(h, f, argv[2]);
+        bool extras = argc > 3; // also run the BVC splat and the reverse walks
+        int rc = h.dim == 2 ? run<2>(h, f, argv[2], extras) : run<3>(h, f, argv[2], extras);
         fclose(f);
         return rc;
     } catch (const zombie_b200::Error& e) {
