@@ -267,22 +267,21 @@ ZB_COOP_NOINLINE void coopClosestPoint(const BvhView& bvh, WarpShared& ws, bool 
                 loadNode(bvh.nodes, item.y, node);
                 NodeFrame<DIM> f = nodeFrame<DIM>(node);
                 float shrink = r2;
-#pragma unroll
+                ZB_CHILD_LOOP
                 for (int c = 0; c < 8; c++) {
+                    if (childMeta(node, c) == 0u) continue;
                     float lo[DIM], hi[DIM], d2min, d2max;
                     childBox<DIM>(node, f, c, lo, hi);
                     boxDistance2<DIM>(lo, hi, q, d2min, d2max);
-                    bool valid = childMeta(node, c) != 0u;
-                    if (valid) shrink = fminf(shrink, d2max);
+                    shrink = fminf(shrink, d2max);
                     // keys are rounded DOWN to a multiple of 64 ulps: still a lower bound of the child's distance
-                    keys[c] = valid ? ((zb_float_as_uint(d2min) & ~63u) | (uint32_t)c) : 0xffffffffu;
+                    insertKey(keys, (zb_float_as_uint(d2min) & ~63u) | (uint32_t)c);
                 }
                 if (shrink < r2) {
                     // the search radius also shrinks by each child's farthest-corner distance (bvh.inl:1339-1343)
                     zb_atomic_min64(&ws.best[owner], packBest(shrink, 0xffffffffu));
                     r2 = shrink;
                 }
-                sort8(keys);
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
                     if (keys[c] != 0xffffffffu && zb_uint_as_float(keys[c] & ~63u) <= r2) nKeep = c + 1;
@@ -355,7 +354,8 @@ ZB_COOP_NOINLINE float coopStarRadius2(const BvhView& bvh, WarpShared& ws, bool 
                 Vec<DIM> q;
                 q[0] = ws.qx[owner]; q[1] = ws.qy[owner];
                 if (DIM == 3) q[DIM - 1] = ws.qz[owner];
-                primStarRadius2Fast<DIM>(bvh, item & kPrimIndexMask, q, r2, ws.flags[owner] != 0u, precision, silhouetteTests);
+                r2 = primStarRadius2Call<DIM>(bvh.prims, bvh.adjacency, bvh.snchSign, item & kPrimIndexMask, q, r2, ws.flags[owner] != 0u,
+                                              precision, silhouetteTests);
                 if (r2 < before) zb_atomic_min64(&ws.best[owner], packBest(r2, 0u));
             }
             primTop -= n;
@@ -389,7 +389,7 @@ ZB_COOP_NOINLINE float coopStarRadius2(const BvhView& bvh, WarpShared& ws, bool 
                 loadNode(bvh.nodes, item.y, node);
                 NodeFrame<DIM> f = nodeFrame<DIM>(node);
                 float shrink = r2;
-#pragma unroll
+                ZB_CHILD_LOOP
                 for (int c = 0; c < 8; c++) {
                     uint32_t meta = childMeta(node, c);
                     if (meta == 0u) continue;
@@ -402,13 +402,12 @@ ZB_COOP_NOINLINE float coopStarRadius2(const BvhView& bvh, WarpShared& ws, bool 
                     if (!starChildBoundsFast<DIM>(bvh, item.y, c, q, lo, hi, d2min, d2max, lower, upper, hasSil, precision)) continue;
                     shrink = fminf(shrink, upper);
                     if (!hasSil || parentNoSil) noSil |= 1u << c;
-                    keys[c] = (zb_float_as_uint(lower) & ~63u) | (uint32_t)c;
+                    insertKey(keys, (zb_float_as_uint(lower) & ~63u) | (uint32_t)c);
                 }
                 if (shrink < r2) {
                     zb_atomic_min64(&ws.best[owner], packBest(shrink, 0u));
                     r2 = shrink;
                 }
-                sort8(keys);
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
                     if (keys[c] != 0xffffffffu && zb_uint_as_float(keys[c] & ~63u) <= r2) nKeep = c + 1;

@@ -77,6 +77,25 @@ ZB_DEV void loadNode(const uint4 *nodes, uint32_t idx, NodeRegs& n)
 
 ZB_DEV float byteF(uint32_t w, int i) { return (float)((w >> (8*i)) & 0xffu); }
 
+// byte c (0..7) of the word pair (w0: children 0..3, w1: children 4..7) for a child slot only known at run time: the
+// child loops of the traversals are NOT unrolled (one copy of the child test instead of eight — the walk kernel is
+// bound by instruction fetch, see profiles/README.md), so the slot is a loop variable
+ZB_DEV uint32_t byte8(uint32_t w0, uint32_t w1, int c)
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(w0, w1, (uint32_t)c) & 0xffu;
+#else
+    return ((c < 4 ? w0 : w1) >> (8*(c & 3))) & 0xffu;
+#endif
+}
+
+// child loops: "unroll 1" keeps one copy of the body; build with -DZB_UNROLL_CHILD_LOOPS to compare against full unrolling
+#if defined(ZB_UNROLL_CHILD_LOOPS)
+#define ZB_CHILD_LOOP _Pragma("unroll")
+#else
+#define ZB_CHILD_LOOP _Pragma("unroll 1")
+#endif
+
 // word holding the quantised coordinate bytes of children 0..3 / 4..7: axis 0..2, side 0 = lo, 1 = hi
 ZB_DEV uint32_t qword(const NodeRegs& n, int axis, int side, int half)
 {
@@ -109,16 +128,12 @@ ZB_DEV void childBox(const NodeRegs& n, const NodeFrame<DIM>& f, int c, float lo
 {
 #pragma unroll
     for (int k = 0; k < DIM; k++) {
-        lo[k] = fmaf(f.s[k], byteF(qword(n, k, 0, c >> 2), c & 3), f.o[k]);
-        hi[k] = fmaf(f.s[k], byteF(qword(n, k, 1, c >> 2), c & 3), f.o[k]);
+        lo[k] = fmaf(f.s[k], (float)byte8(qword(n, k, 0, 0), qword(n, k, 0, 1), c), f.o[k]);
+        hi[k] = fmaf(f.s[k], (float)byte8(qword(n, k, 1, 0), qword(n, k, 1, 1), c), f.o[k]);
     }
 }
 
-ZB_DEV uint32_t childMeta(const NodeRegs& n, int c)
-{
-    uint32_t w = c < 4 ? n.q[1].z : n.q[1].w;
-    return (w >> (8*(c & 3))) & 0xffu;
-}
+ZB_DEV uint32_t childMeta(const NodeRegs& n, int c) { return byte8(n.q[1].z, n.q[1].w, c); }
 
 // stack reference of child slot c: internal -> node index; leaf -> flag | count << 28 | first primitive
 ZB_DEV uint32_t childRef(const NodeRegs& n, uint32_t meta)
@@ -140,6 +155,13 @@ ZB_DEV void sort8(uint32_t k[8])
     cswap(k[1], k[4]); cswap(k[3], k[6]);
     cswap(k[2], k[4]); cswap(k[3], k[5]);
     cswap(k[3], k[4]);
+}
+
+// inserts key t into the ascending list k[0..8) (padded with 0xffffffff; the largest entry falls off the end)
+ZB_DEV void insertKey(uint32_t k[8], uint32_t t)
+{
+#pragma unroll
+    for (int i = 0; i < 8; i++) cswap(k[i], t);
 }
 
 ZB_DEV float keyValue(uint32_t key) { return zb_uint_as_float(key & ~7u); }
@@ -378,15 +400,16 @@ ZB_DEV void closestPointDfs(const BvhView& bvh, const Vec<DIM>& x, float& r2, Cl
         NodeFrame<DIM> f = nodeFrame<DIM>(n);
         uint32_t keys[8];
 #pragma unroll
+        for (int c = 0; c < 8; c++) keys[c] = 0xffffffffu;
+        ZB_CHILD_LOOP
         for (int c = 0; c < 8; c++) {
+            if (childMeta(n, c) == 0u) continue;
             float lo[DIM], hi[DIM], d2min, d2max;
             childBox<DIM>(n, f, c, lo, hi);
             boxDistance2<DIM>(lo, hi, x, d2min, d2max);
-            bool valid = childMeta(n, c) != 0u;
-            if (valid) r2 = fminf(r2, d2max);
-            keys[c] = valid ? ((zb_float_as_uint(d2min) & ~7u) | (uint32_t)c) : 0xffffffffu;
+            r2 = fminf(r2, d2max);
+            insertKey(keys, (zb_float_as_uint(d2min) & ~7u) | (uint32_t)c);
         }
-        sort8(keys);
 #pragma unroll
         for (int c = 7; c >= 0; c--) {
             uint32_t key = keys[c];
@@ -772,6 +795,20 @@ ZB_DEV void primStarRadius2(const BvhView& bvh, uint32_t primIdx, const Vec<DIM>
     }
 }
 
+// Out-of-line copy of the reference-ordered test for primStarRadius2Fast's rare redo (arguments by value: a noinline
+// device function taking references would pin them in local memory at every call site).
+template <int DIM>
+ZB_DEV_COLD float primStarRadius2Redo(const float4 *prims, const float4 *adjacency, int snchSign, uint32_t primIdx, Vec<DIM> x,
+                                      float r2, bool flip, float precision, bool silhouetteTests)
+{
+    BvhView bvh{};
+    bvh.prims = prims;
+    bvh.adjacency = adjacency;
+    bvh.snchSign = snchSign;
+    primStarRadius2<DIM>(bvh, primIdx, x, r2, flip, precision, silhouetteTests);
+    return r2;
+}
+
 // The same primitive test with fused arithmetic, reciprocal multiplies and a single normalisation (3D only; the 2D
 // form forwards to primStarRadius2). Identical case analysis, so the star radius agrees with primStarRadius2 to float
 // rounding (the gate on this query is FCPW's 1e-3 silhouette tolerance); roughly half the instructions.
@@ -888,10 +925,27 @@ ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const V
             }
         }
     }
-    if (redo) {
-        r2 = r2in;
-        primStarRadius2<3>(bvh, primIdx, x, r2, flip, precision, silhouetteTests);
-    }
+    if (redo) r2 = primStarRadius2Redo<3>(bvh.prims, bvh.adjacency, bvh.snchSign, primIdx, x, r2in, flip, precision, silhouetteTests);
+}
+
+// One out-of-line copy of the fast primitive test for all the traversals of a kernel (the private depth-first phase and
+// the pooled primitive rounds of coop.cuh both call it): ~1300 instructions that would otherwise be resident twice.
+// Build with -DZB_INLINE_PRIM_TESTS to inline it at every call site instead.
+template <int DIM>
+#if defined(ZB_INLINE_PRIM_TESTS)
+ZB_DEV
+#else
+ZB_DEV_COLD
+#endif
+float primStarRadius2Call(const float4 *prims, const float4 *adjacency, int snchSign, uint32_t primIdx, Vec<DIM> x, float r2,
+                          bool flip, float precision, bool silhouetteTests)
+{
+    BvhView bvh{};
+    bvh.prims = prims;
+    bvh.adjacency = adjacency;
+    bvh.snchSign = snchSign;
+    primStarRadius2Fast<DIM>(bvh, primIdx, x, r2, flip, precision, silhouetteTests);
+    return r2;
 }
 
 // BoundingCone::overlap (fcpw/core/bounding_volumes.h:275-321): can a normal inside the cone be
@@ -1072,7 +1126,7 @@ ZB_DEV void starRadiusDfs(const BvhView& bvh, const Vec<DIM>& x, float& r2, bool
             uint32_t first = e.y & 0x0fffffffu, count = (e.y >> 28) & 7u;
             for (uint32_t i = 0; i < count; i++) {
                 ZB_COUNT_PRIM
-                if (FAST) primStarRadius2Fast<DIM>(bvh, first + i, x, r2, flip, precision, silhouetteTests);
+                if (FAST) r2 = primStarRadius2Call<DIM>(bvh.prims, bvh.adjacency, bvh.snchSign, first + i, x, r2, flip, precision, silhouetteTests);
                 else primStarRadius2<DIM>(bvh, first + i, x, r2, flip, precision, silhouetteTests);
             }
             continue;
@@ -1085,8 +1139,9 @@ ZB_DEV void starRadiusDfs(const BvhView& bvh, const Vec<DIM>& x, float& r2, bool
         uint32_t keys[8];
         uint32_t noSil = 0u;
 #pragma unroll
+        for (int c = 0; c < 8; c++) keys[c] = 0xffffffffu;
+        ZB_CHILD_LOOP
         for (int c = 0; c < 8; c++) {
-            keys[c] = 0xffffffffu;
             uint32_t meta = childMeta(n, c);
             if (meta == 0u) continue;
             float lo[DIM], hi[DIM], d2min, d2max;
@@ -1100,9 +1155,8 @@ ZB_DEV void starRadiusDfs(const BvhView& bvh, const Vec<DIM>& x, float& r2, bool
             if (!keep) continue;
             r2 = fminf(r2, upper);
             if (!hasSil || !silhouetteTests) noSil |= 1u << c;
-            keys[c] = (zb_float_as_uint(lower) & ~7u) | (uint32_t)c;
+            insertKey(keys, (zb_float_as_uint(lower) & ~7u) | (uint32_t)c);
         }
-        sort8(keys);
 #pragma unroll
         for (int c = 7; c >= 0; c--) {
             uint32_t key = keys[c];
