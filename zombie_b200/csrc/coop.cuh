@@ -130,21 +130,29 @@ ZB_COOP void coopPushChildren(WarpShared& ws, int& nodeTop, int& primTop, int la
         if (lane == 0 && status) zb_status_or(status, kStatusCoopOverflow);
         return;
     }
-    int slotN = nodeTop + inclN - nNodes, slotP = primTop + inclP - nPrims;
+    // the lane's group is filled from its END while the keys are walked nearest first: one rolled loop of nKeep
+    // iterations (the keys rotate through their registers, so none is indexed with a run-time value) instead of eight
+    // unrolled copies of the body
+    int endN = nodeTop + inclN, endP = primTop + inclP;
+    uint32_t k[8];
 #pragma unroll
-    for (int c = 7; c >= 0; c--) {
-        if (c < nKeep) {
-            uint32_t key = keys[c], slot = key & 7u;
-            uint32_t meta = childMeta(node, slot);
-            uint32_t count = meta >> 5;
-            uint32_t sil = (noSil >> slot) & 1u;
-            if (count == 0u) {
-                ws.nodes[slotN++] = make_uint2((key & ~63u) | (sil << 5) | (uint32_t)owner, node.q[1].x + (meta & 31u) - 1u);
-            } else {
-                uint32_t first = node.q[1].y + (meta & 31u);
-                uint32_t head = ((uint32_t)owner << 27) | (sil << 26);
-                for (uint32_t i = count; i > 0u; i--) ws.prims[slotP++] = head | (first + i - 1u);
-            }
+    for (int c = 0; c < 8; c++) k[c] = keys[c];
+#pragma unroll 1
+    for (int c = 0; c < nKeep; c++) {
+        uint32_t key = k[0];
+#pragma unroll
+        for (int i = 0; i < 7; i++) k[i] = k[i + 1];
+        uint32_t slot = key & 7u;
+        uint32_t meta = childMeta(node, slot);
+        uint32_t count = meta >> 5;
+        uint32_t sil = (noSil >> slot) & 1u;
+        if (count == 0u) {
+            ws.nodes[--endN] = make_uint2((key & ~63u) | (sil << 5) | (uint32_t)owner, node.q[1].x + (meta & 31u) - 1u);
+        } else {
+            uint32_t first = node.q[1].y + (meta & 31u);
+            uint32_t head = ((uint32_t)owner << 27) | (sil << 26);
+            endP -= (int)count;
+            for (uint32_t i = 0; i < count; i++) ws.prims[endP + i] = head | (first + count - 1u - i);
         }
     }
     nodeTop += totalN;
@@ -159,13 +167,15 @@ ZB_COOP void coopRefill(WarpShared& ws, int& nodeTop, int& primTop, int lane, co
 {
     int take = min(sp, kRefillPerLane);
     int nNodes = 0, nPrims = 0;
+#pragma unroll 1
     for (int k = 0; k < take; k++) {
-        uint2 e = stack[sp - take + k];
-        if (e.y & kLeafFlag) nPrims += (int)((e.y >> 28) & 7u); else nNodes++;
+        uint32_t y = stack[sp - take + k].y;
+        if (y & kLeafFlag) nPrims += (int)((y >> 28) & 7u); else nNodes++;
     }
     int inclN = warpInclusiveSum(nNodes, lane), inclP = warpInclusiveSum(nPrims, lane);
     int totalN = zb_shfl(inclN, 31), totalP = zb_shfl(inclP, 31);
     int slotN = nodeTop + inclN - nNodes, slotP = primTop + inclP - nPrims;
+#pragma unroll 1
     for (int k = 0; k < take; k++) { // bottom to top: the lane's nearest entry ends on top of its group
         uint2 e = stack[sp - take + k];
         uint32_t sil = starFlags ? (e.x >> 2) & 1u : 0u;
@@ -230,11 +240,7 @@ ZB_COOP_NOINLINE void coopClosestPoint(const BvhView& bvh, WarpShared& ws, bool 
                 Vec<DIM> q;
                 q[0] = ws.qx[owner]; q[1] = ws.qy[owner];
                 if (DIM == 3) q[DIM - 1] = ws.qz[owner];
-                Prim<DIM> prim;
-                prim.load(bvh, idx);
-                Vec<DIM> pt;
-                float u, v;
-                float d = prim.closest(q, pt, u, v);
+                float d = primClosestCall<DIM>(bvh.prims, idx, q).w;
                 float d2 = d*d;
                 if (d2 <= r2) zb_atomic_min64(&ws.best[owner], packBest(d2, idx));
             }
@@ -295,10 +301,10 @@ ZB_COOP_NOINLINE void coopClosestPoint(const BvhView& bvh, WarpShared& ws, bool 
     unsigned long long b = ws.best[lane];
     uint32_t prim = (uint32_t)b;
     if (hasQuery && prim != 0xffffffffu && (int)prim != hit.prim) {
-        Prim<DIM> p;
-        p.load(bvh, prim);
-        float u, v;
-        hit.d = p.closest(x, hit.p, u, v);
+        float4 cp = primClosestCall<DIM>(bvh.prims, prim, x);
+        hit.d = cp.w;
+        hit.p[0] = cp.x; hit.p[1] = cp.y;
+        if (DIM == 3) hit.p[DIM - 1] = cp.z;
         hit.prim = (int)prim;
     }
     zb_syncwarp();

@@ -334,8 +334,41 @@ template <> struct Prim<2> {
     }
 };
 
+ZB_DEV void setThird(Prim<3>& p, const float4& v) { p.c = make3(v.x, v.y, v.z); }
+ZB_DEV void setThird(Prim<2>&, const float4&) {}
+
 template <int DIM>
 ZB_DEV Vec<DIM> unitNormal(const Prim<DIM>& p) { Vec<DIM> n = p.rawNormal(); return n/xnorm(n); }
+
+// Closest point on primitive i (leaf order): ONE out-of-line copy per kernel, shared by the private depth-first phase,
+// the pooled primitive rounds and the final re-evaluation of the winner (coop.cuh) and by sampleSphere. Returns
+// (pt, distance) packed in a float4. Build with -DZB_INLINE_PRIM_TESTS to inline it at every call site instead.
+template <int DIM>
+#if defined(ZB_INLINE_PRIM_TESTS)
+ZB_DEV
+#else
+ZB_DEV_COLD
+#endif
+float4 primClosestCall(const float4 *prims, uint32_t i, Vec<DIM> x)
+{
+    Vec<DIM> pa, pb, pt;
+    float d, u, v;
+    if (DIM == 3) {
+        float4 v0 = zb_ldg(prims + (size_t)3*i), v1 = zb_ldg(prims + (size_t)3*i + 1), v2 = zb_ldg(prims + (size_t)3*i + 2);
+        Prim<DIM> prim;
+        prim.a[0] = v0.x; prim.a[1] = v0.y; prim.a[DIM - 1] = v0.z;
+        prim.b[0] = v1.x; prim.b[1] = v1.y; prim.b[DIM - 1] = v1.z;
+        setThird(prim, v2);
+        d = prim.closest(x, pt, u, v);
+    } else {
+        float4 v0 = zb_ldg(prims + i);
+        Prim<DIM> prim;
+        prim.a[0] = v0.x; prim.a[1] = v0.y;
+        prim.b[0] = v0.z; prim.b[1] = v0.w;
+        d = prim.closest(x, pt, u, v);
+    }
+    return make_float4(pt[0], pt[1], DIM == 3 ? pt[DIM - 1] : 0.0f, d);
+}
 
 // ------------------------------------------------------------------------------------------
 // closest point
@@ -377,18 +410,15 @@ ZB_DEV void closestPointDfs(const BvhView& bvh, const Vec<DIM>& x, float& r2, Cl
         if (e.y & kLeafFlag) {
             uint32_t first = e.y & 0x0fffffffu, count = (e.y >> 28) & 7u;
             for (uint32_t i = 0; i < count; i++) {
-                Prim<DIM> prim;
-                prim.load(bvh, first + i);
-                Vec<DIM> pt;
-                float u, v;
-                float d = prim.closest(x, pt, u, v);
+                float4 cp = primClosestCall<DIM>(bvh.prims, first + i, x);
                 ZB_COUNT_PRIM
-                float d2 = d*d;
+                float d = cp.w, d2 = d*d;
                 if (d2 <= r2) { // triangles.inl:479: inclusive, later primitives replace equal distances
                     r2 = d2;
                     hit.d = d;
                     hit.prim = (int)(first + i);
-                    hit.p = pt;
+                    hit.p[0] = cp.x; hit.p[1] = cp.y;
+                    if (DIM == 3) hit.p[DIM - 1] = cp.z;
                 }
             }
             continue;
@@ -489,7 +519,10 @@ ZB_DEV bool intersectRay(const BvhView& bvh, const Vec<DIM>& o, const Vec<DIM>& 
         NodeFrame<DIM> f = nodeFrame<DIM>(n);
         uint32_t keys[8];
 #pragma unroll
+        for (int c = 0; c < 8; c++) keys[c] = 0xffffffffu;
+        ZB_CHILD_LOOP
         for (int c = 0; c < 8; c++) {
+            if (childMeta(n, c) == 0u) continue;
             float lo[DIM], hi[DIM];
             childBox<DIM>(n, f, c, lo, hi);
             float tNear = 0.0f, tFar = tMax;
@@ -499,10 +532,8 @@ ZB_DEV bool intersectRay(const BvhView& bvh, const Vec<DIM>& o, const Vec<DIM>& 
                 tNear = fmaxf(tNear, fminf(t0, t1));
                 tFar = fminf(tFar, fmaxf(t0, t1));
             }
-            bool valid = childMeta(n, c) != 0u && tNear <= tFar;
-            keys[c] = valid ? ((zb_float_as_uint(tNear) & ~7u) | (uint32_t)c) : 0xffffffffu;
+            if (tNear <= tFar) insertKey(keys, (zb_float_as_uint(tNear) & ~7u) | (uint32_t)c);
         }
-        sort8(keys);
 #pragma unroll
         for (int c = 7; c >= 0; c--) {
             uint32_t key = keys[c];
@@ -553,47 +584,60 @@ ZB_DEV bool sampleSphere(const BvhView& bvh, const Vec<DIM>& x, float r2, const 
         NodeRegs n;
         loadNode(bvh.nodes, nodeIdx, n);
         NodeFrame<DIM> f = nodeFrame<DIM>(n);
-        float weight[8], d2far[8];
+        // the child loop is not unrolled (ZB_CHILD_LOOP); the weights rotate through eight registers, so child c ends
+        // up in weight[7 - c] and no array is indexed with a run-time value
+        float weight[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) weight[c] = 0.0f;
         float total = 0.0f;
-#pragma unroll
+        ZB_CHILD_LOOP
         for (int c = 0; c < 8; c++) {
-            float lo[DIM], hi[DIM], d2min, d2max;
-            childBox<DIM>(n, f, c, lo, hi);
-            boxDistance2<DIM>(lo, hi, x, d2min, d2max);
             float w = 0.0f;
-            if (childMeta(n, c) != 0u && d2min <= r2) {
-                float c2 = 0.0f;
+            if (childMeta(n, c) != 0u) {
+                float lo[DIM], hi[DIM], d2min, d2max;
+                childBox<DIM>(n, f, c, lo, hi);
+                boxDistance2<DIM>(lo, hi, x, d2min, d2max);
+                if (d2min <= r2) {
+                    float c2 = 0.0f;
 #pragma unroll
-                for (int k = 0; k < DIM; k++) { float dc = x[k] - 0.5f*(lo[k] + hi[k]); c2 = fmaf(dc, dc, c2); }
-                w = branchWeight(c2);
+                    for (int k = 0; k < DIM; k++) { float dc = x[k] - 0.5f*(lo[k] + hi[k]); c2 = fmaf(dc, dc, c2); }
+                    w = branchWeight(c2);
+                }
             }
-            weight[c] = w;
-            d2far[c] = d2max;
+#pragma unroll
+            for (int i = 7; i > 0; i--) weight[i] = weight[i - 1];
+            weight[0] = w;
             total += w;
         }
         if (!(total > 0.0f)) return false;
 
         // select a child: u is rescaled to [0,1) after each decision, as in bvh.inl:1237-1247
         int chosen = -1;
-        float d2NodeMax = 0.0f, prob = 0.0f;
+        float prob = 0.0f;
         float remaining = total;
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-            if (chosen < 0 && weight[c] > 0.0f) {
-                float p = weight[c]/remaining;
-                if (u < p || weight[c] >= remaining) {
+            float wc = weight[7 - c];
+            if (chosen < 0 && wc > 0.0f) {
+                float p = wc/remaining;
+                if (u < p || wc >= remaining) {
                     chosen = c;
                     u = fminf(u/p, 0.99999994f);
-                    prob = weight[c]/total;
-                    d2NodeMax = d2far[c];
+                    prob = wc/total;
                 } else {
                     u = (u - p)/(1.0f - p);
-                    remaining -= weight[c];
+                    remaining -= wc;
                 }
             }
         }
         if (chosen < 0) return false;
         traversalPdf *= prob;
+        float d2NodeMax;
+        {
+            float lo[DIM], hi[DIM], d2min;
+            childBox<DIM>(n, f, chosen, lo, hi);
+            boxDistance2<DIM>(lo, hi, x, d2min, d2NodeMax);
+        }
         uint32_t meta = childMeta(n, chosen);
         uint32_t count = meta >> 5;
         if (count == 0u) {
@@ -610,9 +654,7 @@ ZB_DEV bool sampleSphere(const BvhView& bvh, const Vec<DIM>& x, float r2, const 
             prim.load(bvh, first + i);
             bool inside = d2NodeMax <= r2;
             if (!inside) {
-                Vec<DIM> pt;
-                float a, b;
-                float d = prim.closest(x, pt, a, b);
+                float d = primClosestCall<DIM>(bvh.prims, first + i, x).w;
                 inside = d*d <= r2;
             }
             if (inside) {
@@ -809,6 +851,13 @@ ZB_DEV_COLD float primStarRadius2Redo(const float4 *prims, const float4 *adjacen
     return r2;
 }
 
+// the on-the-edge branch of isSilhouetteEdge3 (atan2 of the dihedral angle): rare, kept out of line
+ZB_DEV_COLD bool isSilhouetteEdge3Cold(Vec<3> pa, Vec<3> pb, Vec<3> n0, Vec<3> n1, Vec<3> viewDir, float d, bool flip,
+                                       float precision, float convention)
+{
+    return isSilhouetteEdge3(pa, pb, n0, n1, viewDir, d, flip, precision, convention);
+}
+
 // The same primitive test with fused arithmetic, reciprocal multiplies and a single normalisation (3D only; the 2D
 // form forwards to primStarRadius2). Identical case analysis, so the star radius agrees with primStarRadius2 to float
 // rounding (the gate on this query is FCPW's 1e-3 silhouette tolerance); roughly half the instructions.
@@ -866,36 +915,40 @@ ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const V
 
     Vec<3> n0 = unitNormal<3>(prim); // reference-ordered: the plane distance below cancels and must round the same way
     if (silhouetteTests) {
-        const float adjN[3][3] = {{a0.x, a0.y, a0.z}, {a0.w, a1.x, a1.y}, {a1.z, a1.w, a2.x}};
         float convention = (float)bvh.snchSign;
         float sign = flip ? 1.0f : -1.0f;
-#pragma unroll
+        // ONE copy of the edge test: the loop is not unrolled; vertices and neighbour normals rotate through their
+        // registers instead (edge j runs from the current pj to pk), so nothing is indexed with a run-time value
+        Vec<3> pj = prim.a, pk = prim.b, pl = prim.c;
+        Vec<3> nj = make3(a0.x, a0.y, a0.z), nk = make3(a0.w, a1.x, a1.y), nl = make3(a1.z, a1.w, a2.x);
+#pragma unroll 1
         for (int j = 0; j < 3; j++) {
-            if ((flags >> (4 + j)) & 1u) continue; // ignoreAdjacentFace
-            Vec<3> pj = j == 0 ? prim.a : (j == 1 ? prim.b : prim.c);
-            Vec<3> pk = j == 0 ? prim.b : (j == 1 ? prim.c : prim.a);
-            Vec<3> e = pk - pj, v = x - pj;
-            float c1 = dot(e, v), c2 = dot(e, e);
-            float t = c1 <= 0.0f ? 0.0f : (c2 <= c1 ? 1.0f : c1/c2);
-            Vec<3> vd = v - e*t;
-            float sd2 = dot(vd, vd);
-            if (!(sd2 < r2)) continue; // cannot shrink the radius whatever the classification says
-            bool isSilhouette = true;
-            if ((flags >> j) & 1u) {
-                Vec<3> nj = make3(adjN[j][0], adjN[j][1], adjN[j][2]);
-                float d = sqrtf(sd2);
-                if (d <= precision) {
-                    isSilhouette = isSilhouetteEdge3(pj, pk, nj, n0, vd, d, flip, precision, convention);
-                } else {
-                    float s = convention/d;
-                    float dot0 = s*dot(vd, nj), dot1 = s*dot(vd, n0);
-                    redo = redo || fabsf(fabsf(dot0) - precision) < 4e-6f || fabsf(fabsf(dot1) - precision) < 4e-6f;
-                    if (fabsf(dot0) <= precision) isSilhouette = sign*dot1 > precision;
-                    else if (fabsf(dot1) <= precision) isSilhouette = sign*dot0 > precision;
-                    else isSilhouette = dot0*dot1 < 0.0f;
+            if (!((flags >> (4 + j)) & 1u)) { // else: ignoreAdjacentFace
+                Vec<3> e = pk - pj, v = x - pj;
+                float c1 = dot(e, v), c2 = dot(e, e);
+                float t = c1 <= 0.0f ? 0.0f : (c2 <= c1 ? 1.0f : c1/c2);
+                Vec<3> vd = v - e*t;
+                float sd2 = dot(vd, vd);
+                if (sd2 < r2) { // else: cannot shrink the radius whatever the classification says
+                    bool isSilhouette = true;
+                    if ((flags >> j) & 1u) {
+                        float d = sqrtf(sd2);
+                        if (d <= precision) {
+                            isSilhouette = isSilhouetteEdge3Cold(pj, pk, nj, n0, vd, d, flip, precision, convention);
+                        } else {
+                            float s = convention/d;
+                            float dot0 = s*dot(vd, nj), dot1 = s*dot(vd, n0);
+                            redo = redo || fabsf(fabsf(dot0) - precision) < 4e-6f || fabsf(fabsf(dot1) - precision) < 4e-6f;
+                            if (fabsf(dot0) <= precision) isSilhouette = sign*dot1 > precision;
+                            else if (fabsf(dot1) <= precision) isSilhouette = sign*dot0 > precision;
+                            else isSilhouette = dot0*dot1 < 0.0f;
+                        }
+                    }
+                    if (isSilhouette) r2 = sd2;
                 }
             }
-            if (isSilhouette) r2 = sd2;
+            Vec<3> tp = pj; pj = pk; pk = pl; pl = tp;
+            Vec<3> tn = nj; nj = nk; nk = nl; nl = tn;
         }
     }
 
