@@ -9,13 +9,21 @@
 
 namespace zb {
 
+// One out-of-line copy of the solution families per kernel: the switch over eight families (with the slow paths of
+// sinf / cosf / expf) is ~1000 instructions, and source / dirichlet / robin are evaluated at six places of the walk
+// kernel. Every family reads p[0..3] only.
+ZB_DEV_COLD zb_jet evalSolutionCall(int family, float p0, float p1, float p2, float p3, float x0, float x1, float x2)
+{
+    float p[4] = {p0, p1, p2, p3}, x[3] = {x0, x1, x2};
+    return zb_eval_solution(family, p, x);
+}
+
 template <int DIM>
 struct PdeEval {
     const zb_pde_desc& d; // lives in the kernel parameter block
 
     ZB_HOSTDEV zb_jet jet(const Vec<DIM>& x) const {
-        float xx[3] = {x[0], x[1], DIM == 3 ? x[DIM - 1] : 0.0f};
-        return zb_eval_solution(d.family, d.params, xx);
+        return evalSolutionCall(d.family, d.params[0], d.params[1], d.params[2], d.params[3], x[0], x[1], DIM == 3 ? x[DIM - 1] : 0.0f);
     }
     // ---- the callbacks of the PDE as the caller described it --------------------------------------
     // pde.source: the estimator solves lap u - sigma u = -f
