@@ -70,6 +70,35 @@ def build(force=False, verbose=False, extra=()):
     return LIB
 
 
+def build_variant(name, extra):
+    """A/B builds for GPU measurements: zombie_b200/variants/lib<name>.so compiled with extra nvcc flags
+    (e.g. -DZB_UNROLL_CHILD_LOOPS); select one at run time with ZOMBIE_B200_LIB (scripts/gpu_variants.sh)."""
+    srcs, _ = _sources()
+    out_dir = os.path.join(HERE, "variants")
+    obj_dir = os.path.join(OBJ, "variant_" + name)
+    os.makedirs(out_dir, exist_ok=True)
+    os.makedirs(obj_dir, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, os.path.basename(src) + ".o")
+        r = subprocess.run([NVCC] + ARCH + COMMON + list(extra) + ["-c", src, "-o", obj], stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(r.stdout)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=max(1, min(len(srcs), os.cpu_count() or 1))) as pool:
+        objs = list(pool.map(compile_one, srcs))
+    lib = os.path.join(out_dir, "lib%s.so" % name)
+    r = subprocess.run([NVCC] + ARCH + ["-shared", "-o", lib] + objs, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(r.stdout)
+    return lib
+
+
 if __name__ == "__main__":
-    build(force="-f" in sys.argv, verbose="-v" in sys.argv)
-    print(LIB)
+    if len(sys.argv) > 2 and sys.argv[1] == "--variant":  # python -m zombie_b200.build --variant NAME [nvcc flags...]
+        print(build_variant(sys.argv[2], sys.argv[3:]))
+    else:
+        build(force="-f" in sys.argv, verbose="-v" in sys.argv)
+        print(LIB)
