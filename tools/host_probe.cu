@@ -143,7 +143,9 @@ int main(int argc, char **argv)
         }
     }
     printf("walks %lld steps %lld status %d\n", total, nSteps, status);
-    printf("star items: with silhouette tests %lld, robin-only %lld | prims rejected by distance %lld, fully tested %lld\n", g_zbClass[0], g_zbClass[1], g_zbClass[2], g_zbClass[3]);
+    printf("star items: with silhouette tests %lld, robin-only %lld | prims rejected by distance %lld, by the plane-distance bound %lld, fully tested %lld\n", g_zbClass[0], g_zbClass[1], g_zbClass[2], g_zbClass[4], g_zbClass[3]);
+    printf("star prims (fast test): robin-only skipped by the plane bound %lld, robin-only evaluated %lld, silhouette prims without / with the reflectance part %lld / %lld\n",
+           g_zbClass[4], g_zbClass[7], g_zbClass[5], g_zbClass[6]);
     const char *names[5] = {"closest", "ray", "occlusion", "sample", "star"};
     for (int q = 0; q < 5; q++) {
         std::vector<int> n, p;

@@ -858,6 +858,10 @@ ZB_DEV_COLD bool isSilhouetteEdge3Cold(Vec<3> pa, Vec<3> pb, Vec<3> n0, Vec<3> n
     return isSilhouetteEdge3(pa, pb, n0, n1, viewDir, d, flip, precision, convention);
 }
 
+#ifndef ZB_ROBIN_PLANE_BOUND
+#define ZB_ROBIN_PLANE_BOUND 1 // 0: evaluate every reflectance bound in full (A/B builds)
+#endif
+
 // The same primitive test with fused arithmetic, reciprocal multiplies and a single normalisation (3D only; the 2D
 // form forwards to primStarRadius2). Identical case analysis, so the star radius agrees with primStarRadius2 to float
 // rounding (the gate on this query is FCPW's 1e-3 silhouette tolerance); roughly half the instructions.
@@ -893,9 +897,32 @@ ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const V
 {
     Prim<3> prim;
     prim.load(bvh, primIdx);
-    Vec<3> closestPt;
-    float closestDist2 = closestPointTriangleFast2(prim.a, prim.b, prim.c, x, closestPt);
-    if (closestDist2 > r2) { ZB_CLASS(2) return; }
+    float4 a2 = zb_ldg(bvh.adjacency + (size_t)3*primIdx + 2);
+    float maxCoeff = a2.z;
+    uint32_t flags = zb_float_as_uint(a2.w);
+    // Can the reflectance bound of this triangle shrink the radius at all? With h the distance from x to the triangle's
+    // plane, the bound h^2 mu/(c (h mu - c^2)) (robin_bounds.h:48-74) is smallest at c = sqrt(h mu/3), whatever the
+    // clamping cosines are, where its square is (27/4) h/mu. So 6.7 h >= mu r^2 (0.7 % of slack for rounding) means the
+    // reflectance part of the test cannot lower r2, and neither the closest nor the farthest point is needed.
+    bool robinCannotShrink = false;
+    if (ZB_ROBIN_PLANE_BOUND && maxCoeff < kMaxFloat - kEpsilon) {
+        if (!(maxCoeff > kEpsilon)) {
+            robinCannotShrink = true; // perfectly reflecting: the reference skips the reflectance part (geometry.h:215)
+        } else {
+            Vec<3> nRaw = cross(prim.b - prim.a, prim.c - prim.a);
+            float s = dot(nRaw, prim.a - x), nn = dot(nRaw, nRaw);
+            float t = fmaxf(r2*maxCoeff*(1.0f/6.7f), 1e-6f); // h > 1e-6 also keeps clear of the closestDist < epsilon case
+            robinCannotShrink = nn > 0.0f && s*s >= nn*(t*t);
+        }
+        if (robinCannotShrink && !silhouetteTests) { ZB_CLASS(4) return; }
+        if (robinCannotShrink) { ZB_CLASS(5) } else if (silhouetteTests) { ZB_CLASS(6) } else { ZB_CLASS(7) }
+    }
+    Vec<3> closestPt = x;
+    float closestDist2 = 0.0f;
+    if (!robinCannotShrink) {
+        closestDist2 = closestPointTriangleFast2(prim.a, prim.b, prim.c, x, closestPt);
+        if (closestDist2 > r2) { ZB_CLASS(2) return; }
+    }
     ZB_CLASS(3)
     // Discrete decisions (is this edge a silhouette? does the reflectance bound apply?) are taken with fused
     // arithmetic; whenever one of them falls within rounding distance of its threshold, or the bound formula is
@@ -904,10 +931,7 @@ ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const V
     const float r2in = r2;
     bool redo = false;
 
-    float4 a0 = zb_ldg(bvh.adjacency + (size_t)3*primIdx), a1 = zb_ldg(bvh.adjacency + (size_t)3*primIdx + 1),
-           a2 = zb_ldg(bvh.adjacency + (size_t)3*primIdx + 2);
-    float maxCoeff = a2.z;
-    uint32_t flags = zb_float_as_uint(a2.w);
+    float4 a0 = zb_ldg(bvh.adjacency + (size_t)3*primIdx), a1 = zb_ldg(bvh.adjacency + (size_t)3*primIdx + 1);
     if (!(maxCoeff < kMaxFloat - kEpsilon)) { // perfectly absorbing
         r2 = fminf(r2, closestDist2);
         return;
@@ -952,7 +976,7 @@ ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const V
         }
     }
 
-    if (maxCoeff > kEpsilon) { // reflectance case
+    if (maxCoeff > kEpsilon && !robinCannotShrink) { // reflectance case
         float closestDist = sqrtf(closestDist2);
         if (closestDist < kEpsilon) {
             r2 = closestDist; // sic (geometry.h:216)
@@ -1150,6 +1174,9 @@ ZB_DEV bool starChildBoundsFast(const BvhView& bvh, uint32_t nodeIdx, int c, con
         if (rMax < minCos/maxCoeff) lower = kMaxFloat;
         else { float rb = rMin/(1.0f - minCos/(maxCoeff*rMax)); lower = rb*rb; }
         if (!(rMin < 1.0f/minCoeff)) { float rb = rMax/(1.0f - 1.0f/(minCoeff*rMin)); upper = rb*rb; }
+        // every triangle below has plane distance h >= rMin minCos, and no triangle's bound is below (27/4) h/mu
+        // (see primStarRadius2Fast): a second lower bound that does not degrade when the subtree is far and large
+        if (ZB_ROBIN_PLANE_BOUND) lower = fmaxf(lower, 6.7f*rMin*minCos/maxCoeff);
     } else {
         float rb = rMin*zb_exp_fast(minCos/(maxCoeff*rMax));
         lower = rb*rb;
@@ -1233,7 +1260,11 @@ ZB_DEV float starRadius2(const BvhView& bvh, const Vec<DIM>& x, float r2, bool f
     uint2 stack[kStackSize];
     int sp = 0;
     stack[sp++] = make_uint2(0u, 0u);
+#if defined(ZB_SEQUENTIAL_FAST) // host tools: measure the kernels' (fast) node and primitive tests one thread per query
+    starRadiusDfs<DIM, true>(bvh, x, r2, flip, precision, stack, sp, 0x7fffffff, status);
+#else
     starRadiusDfs<DIM, false>(bvh, x, r2, flip, precision, stack, sp, 0x7fffffff, status);
+#endif
     return r2;
 }
 
