@@ -17,7 +17,7 @@ using namespace zb;
 
 struct Rec { int q, nodes, prims; };
 static std::vector<Rec> g_recs;
-namespace zb { long long g_zbClass[8] = {0}; }
+namespace zb { long long g_zbClass[12] = {0}; }
 namespace zb { void zbHostRecord(int query, int nodes, int prims) { g_recs.push_back({query, nodes, prims}); } }
 
 static BvhView viewOf(const HostBvh& h, int sign)
@@ -120,7 +120,7 @@ int main(int argc, char **argv)
     a.recLength = recLen.data(); a.recFlags = recFlags.data(); a.anyGradient = 1;
     for (int i = 0; i < nPts; i++) preparePoint<3>(a, i);
     g_recs.clear();
-    for (int k = 0; k < 8; k++) g_zbClass[k] = 0;
+    for (int k = 0; k < 12; k++) g_zbClass[k] = 0;
 
     // run the walks; per step, collect the cost of each query
     struct StepCost { int nodes[5], prims[5]; int stepIndex; bool onRefl; float distA; };
@@ -146,6 +146,7 @@ int main(int argc, char **argv)
     printf("star items: with silhouette tests %lld, robin-only %lld | prims rejected by distance %lld, by the plane-distance bound %lld, fully tested %lld\n", g_zbClass[0], g_zbClass[1], g_zbClass[2], g_zbClass[4], g_zbClass[3]);
     printf("star prims (fast test): robin-only skipped by the plane bound %lld, robin-only evaluated %lld, silhouette prims without / with the reflectance part %lld / %lld\n",
            g_zbClass[4], g_zbClass[7], g_zbClass[5], g_zbClass[6]);
+    printf("star edges (fast test): skipped by the sign shortcut %lld, tested in full %lld\n", g_zbClass[8], g_zbClass[9]);
     const char *names[5] = {"closest", "ray", "occlusion", "sample", "star"};
     for (int q = 0; q < 5; q++) {
         std::vector<int> n, p;

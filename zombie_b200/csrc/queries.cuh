@@ -32,7 +32,7 @@ struct BvhView {
 #define ZB_COUNT_FLUSH(q)
 #else
 void zbHostRecord(int query, int nodes, int prims);
-extern long long g_zbClass[8]; // star query: [0] items with silhouette tests, [1] without, [2] prims early-out by distance, [3] prims fully tested
+extern long long g_zbClass[12]; // star query: [0] items with silhouette tests, [1] without, [2] prims early-out by distance, [3] prims fully tested
 #define ZB_CLASS(i) g_zbClass[i]++;
 #define ZB_COUNT_DECL int zbNodes = 0, zbPrims = 0;
 #define ZB_COUNT_NODE zbNodes++;
@@ -858,6 +858,9 @@ ZB_DEV_COLD bool isSilhouetteEdge3Cold(Vec<3> pa, Vec<3> pb, Vec<3> n0, Vec<3> n
     return isSilhouetteEdge3(pa, pb, n0, n1, viewDir, d, flip, precision, convention);
 }
 
+#ifndef ZB_SILHOUETTE_SIGN_SHORTCUT
+#define ZB_SILHOUETTE_SIGN_SHORTCUT 1 // 0: run the full edge test on every edge (A/B builds)
+#endif
 #ifndef ZB_ROBIN_PLANE_BOUND
 #define ZB_ROBIN_PLANE_BOUND 1 // 0: evaluate every reflectance bound in full (A/B builds)
 #endif
@@ -914,7 +917,9 @@ ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const V
             float t = fmaxf(r2*maxCoeff*(1.0f/6.7f), 1e-6f); // h > 1e-6 also keeps clear of the closestDist < epsilon case
             robinCannotShrink = nn > 0.0f && s*s >= nn*(t*t);
         }
-        if (robinCannotShrink && !silhouetteTests) { ZB_CLASS(4) return; }
+        // ... and when, on top of that, every edge is marked ignoreAdjacentFace (convex edges of a single-sided solve,
+        // fcpw_geometric_queries.h:1029-1038) or the subtree holds no silhouette, the triangle has nothing to say
+        if (robinCannotShrink && !(silhouetteTests && ((flags >> 4) & 7u) != 7u)) { ZB_CLASS(4) return; }
         if (robinCannotShrink) { ZB_CLASS(5) } else if (silhouetteTests) { ZB_CLASS(6) } else { ZB_CLASS(7) }
     }
     Vec<3> closestPt = x;
@@ -945,9 +950,25 @@ ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const V
         // registers instead (edge j runs from the current pj to pk), so nothing is indexed with a run-time value
         Vec<3> pj = prim.a, pk = prim.b, pl = prim.c;
         Vec<3> nj = make3(a0.x, a0.y, a0.z), nk = make3(a0.w, a1.x, a1.y), nl = make3(a1.z, a1.w, a2.x);
+        // Sign shortcut. The closest point of an edge lies in the planes of both faces that share it, so the two dot
+        // products of the silhouette test are the signed distances s0, sj of x from those planes over the distance d
+        // to the edge. If both exceed precision times an upper bound of d (the distance to a vertex of the edge) and
+        // have the same sign, the edge is no silhouette (silhouette_edges.inl:97-110) whatever d is — and one of them
+        // above precision in absolute terms rules out the on-the-edge branch (d <= precision) since d >= |s|. 10 % of
+        // slack covers the rounding of s against the reference's normalised dot products.
+        const float s0 = dot(n0, x - prim.a);
+        const float p2 = 1.21f*precision*precision;
 #pragma unroll 1
         for (int j = 0; j < 3; j++) {
-            if (!((flags >> (4 + j)) & 1u)) { // else: ignoreAdjacentFace
+            bool skip = ((flags >> (4 + j)) & 1u) != 0u; // ignoreAdjacentFace
+            if (ZB_SILHOUETTE_SIGN_SHORTCUT && !skip && ((flags >> j) & 1u)) {
+                Vec<3> v = x - pj;
+                float sj = dot(nj, v), lim = p2*dot(v, v);
+                skip = s0*s0 > lim && sj*sj > lim && (s0 > 0.0f) == (sj > 0.0f) && fmaxf(s0*s0, sj*sj) > p2;
+                if (skip) { ZB_CLASS(8) }
+            }
+            if (!skip) {
+                ZB_CLASS(9)
                 Vec<3> e = pk - pj, v = x - pj;
                 float c1 = dot(e, v), c2 = dot(e, e);
                 float t = c1 <= 0.0f ? 0.0f : (c2 <= c1 ? 1.0f : c1/c2);
