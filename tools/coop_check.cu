@@ -14,7 +14,7 @@
 #include "probe_mesh.h"
 
 using namespace zb;
-namespace zb { long long g_coopCount[8] = {0}; }
+namespace zb { long long g_coopCount[10] = {0}; }
 #if defined(ZB_HOST_STATS)
 static long long g_seq[5][2] = {{0}};
 namespace zb { long long g_zbClass[12] = {0}; void zbHostRecord(int q, int nodes, int prims) { __atomic_fetch_add(&g_seq[q][0], (long long)nodes, __ATOMIC_RELAXED); __atomic_fetch_add(&g_seq[q][1], (long long)prims, __ATOMIC_RELAXED); } }
@@ -113,6 +113,7 @@ int main(int argc, char **argv)
     printf("phase-1 (private DFS) work per query: closest %.1f nodes %.1f prims | star %.1f nodes %.1f prims\n", g_seq[0][0]/(double)nQ, g_seq[0][1]/(double)nQ, g_seq[4][0]/(double)nQ, g_seq[4][1]/(double)nQ);
 #endif
     printf("coop work per query: closest %.1f node items %.1f prims (%.1f + %.1f rounds/warp) | star %.1f node items %.1f prims (%.1f + %.1f rounds/warp)\n", g_coopCount[0]/(double)nQ, g_coopCount[1]/(double)nQ, g_coopCount[4]*32.0/nQ, g_coopCount[5]*32.0/nQ, g_coopCount[2]/(double)nQ, g_coopCount[3]/(double)nQ, g_coopCount[6]*32.0/nQ, g_coopCount[7]*32.0/nQ);
+    printf("star filter stage: %.1f prims per query in %.1f filter rounds/warp\n", g_coopCount[8]/(double)nQ, g_coopCount[9]*32.0/nQ);
 
     int badDist = 0, primDiff = 0, badStar = 0, shrunk = 0;
     double worstStar = 0;

@@ -48,7 +48,7 @@
 namespace zb {
 
 #if defined(ZB_EMULATE_WARP)
-extern long long g_coopCount[8]; // [0] closest node items, [1] closest prims, [2] star node items, [3] star prims, [4..7] rounds
+extern long long g_coopCount[10]; // [0] closest node items, [1] closest prims, [2] star node items, [3] star prims (full test), [4..7] rounds, [8] star prims through the filter stage, [9] filter rounds
 #define ZB_COOP_COUNT(i, n) __atomic_fetch_add(&g_coopCount[i], (long long)(n), __ATOMIC_RELAXED);
 #else
 #define ZB_COOP_COUNT(i, n)
@@ -56,6 +56,9 @@ extern long long g_coopCount[8]; // [0] closest node items, [1] closest prims, [
 
 #ifndef ZB_NODE_STACK
 #define ZB_NODE_STACK 1024
+#endif
+#ifndef ZB_STAR_TWO_STAGE
+#define ZB_STAR_TWO_STAGE 1 // 0: every pooled primitive round runs the full star test (A/B builds)
 #endif
 #ifndef ZB_PHASE1_BUDGET
 #define ZB_PHASE1_BUDGET 8
@@ -65,7 +68,7 @@ constexpr int kNodeHeadroom = 128;
 constexpr int kPhase1Budget = ZB_PHASE1_BUDGET; // private stack pops per lane before the warp pools what is left
 constexpr int kRefillPerLane = 8;     // private stack entries a lane hands to the shared lists per refill
 constexpr int kRefillLowWater = 192;  // refill when the shared node stack is below this
-constexpr int kPrimQueue = 1056;      // >= 31 + 32 lanes x 8 leaves x 4 primitives
+constexpr int kPrimQueue = 1120;      // >= 31 + 32 lanes x 8 leaves x 4 primitives, + 63 survivors of the cheap stage (from the end)
 constexpr uint32_t kPrimIndexMask = 0x03ffffffu; // 26 bits: up to 67 M primitives per boundary
 enum : int { kStatusCoopOverflow = 4 };
 
@@ -76,6 +79,10 @@ struct WarpShared {
     float qx[32], qy[32], qz[32];
     unsigned int flags[32];
 };
+
+// four 128-thread CTAs per SM (the register budget of the walk kernel) must also fit in the 227 KB of shared memory,
+// 1 KB of which the system reserves per CTA
+static_assert(4*(4*sizeof(WarpShared) + 1024) <= 227*1024, "WarpShared too large for 4 CTAs per SM");
 
 ZB_COOP unsigned long long packBest(float d2, uint32_t payload)
 {
@@ -112,7 +119,8 @@ ZB_COOP int coopNodeBudget(int nodeTop)
 // the primitives of leaf children far-to-near on the primitive queue. tag = noSil bits (per slot) for the
 // star-radius query, 0 for closest point. Every lane must call this (lanes without a node pass nKeep = 0).
 ZB_COOP void coopPushChildren(WarpShared& ws, int& nodeTop, int& primTop, int lane, int owner,
-                                                 const NodeRegs& node, const uint32_t keys[8], int nKeep, uint32_t noSil, int *status)
+                                                 const NodeRegs& node, const uint32_t keys[8], int nKeep, uint32_t noSil, int *status,
+                                                 int primReserved = 0)
 {
     int nNodes = 0, nPrims = 0;
 #pragma unroll
@@ -126,7 +134,7 @@ ZB_COOP void coopPushChildren(WarpShared& ws, int& nodeTop, int& primTop, int la
     }
     int inclN = warpInclusiveSum(nNodes, lane), inclP = warpInclusiveSum(nPrims, lane);
     int totalN = zb_shfl(inclN, 31), totalP = zb_shfl(inclP, 31);
-    if (nodeTop + totalN > kNodeStack || primTop + totalP > kPrimQueue) { // warp-uniform; cannot happen for trees of depth <= 18
+    if (nodeTop + totalN > kNodeStack || primTop + totalP + primReserved > kPrimQueue) { // warp-uniform; cannot happen for trees of depth <= 18
         if (lane == 0 && status) zb_status_or(status, kStatusCoopOverflow);
         return;
     }
@@ -339,6 +347,11 @@ ZB_COOP_NOINLINE float coopStarRadius2(const BvhView& bvh, WarpShared& ws, bool 
     ws.best[lane] = packBest(r2own, 0u);
     ws.flags[lane] = flip ? 1u : 0u;
     int nodeTop = 0, primTop = 0;
+    // Two-stage primitive rounds (3D): a FILTER round pops 32 primitives and runs the cheap first stage of the test
+    // (primStarNeedsFullTest); the survivors are compacted into a second list, kept at the END of ws.prims, and a FULL
+    // round runs the whole test on 32 of them. fullTop counts that list (entries ws.prims[kPrimQueue - 1 - k]).
+    constexpr bool kTwoStage = DIM == 3 && ZB_STAR_TWO_STAGE;
+    int fullTop = 0;
     zb_syncwarp();
 
     while (true) {
@@ -346,15 +359,14 @@ ZB_COOP_NOINLINE float coopStarRadius2(const BvhView& bvh, WarpShared& ws, bool 
             coopRefill(ws, nodeTop, primTop, lane, stack, sp, true);
             zb_syncwarp();
         }
-        if (nodeTop == 0 && primTop == 0) break;
-        if (primTop >= 32 || nodeTop == 0) {
-            // ---- primitive round
-            int n = min(primTop, 32);
+        if (nodeTop == 0 && primTop == 0 && fullTop == 0) break;
+        if (kTwoStage && (fullTop >= 32 || (nodeTop == 0 && primTop == 0))) {
+            // ---- full round on the survivors
+            int n = min(fullTop, 32);
             if (lane == 0) { ZB_COOP_COUNT(3, n) ZB_COOP_COUNT(7, 1) }
             if (lane < n) {
-                uint32_t item = ws.prims[primTop - 1 - lane];
+                uint32_t item = ws.prims[kPrimQueue - fullTop + lane];
                 int owner = (int)(item >> 27);
-                // bit 26: "no silhouette inside this subtree" (reflectance bvh.h:474-476 sign trick)
                 bool silhouetteTests = !((item >> 26) & 1u);
                 float r2 = coopRadius2(ws, owner), before = r2;
                 Vec<DIM> q;
@@ -364,7 +376,39 @@ ZB_COOP_NOINLINE float coopStarRadius2(const BvhView& bvh, WarpShared& ws, bool 
                                               precision, silhouetteTests);
                 if (r2 < before) zb_atomic_min64(&ws.best[owner], packBest(r2, 0u));
             }
+            fullTop -= n;
+            zb_syncwarp();
+            continue;
+        }
+        if (primTop >= 32 || nodeTop == 0) {
+            // ---- primitive round (two-stage: filter round)
+            int n = min(primTop, 32);
+            uint32_t item = 0u;
+            bool survivor = false;
+            if (lane < n) {
+                item = ws.prims[primTop - 1 - lane];
+                int owner = (int)(item >> 27);
+                // bit 26: "no silhouette inside this subtree" (reflectance bvh.h:474-476 sign trick)
+                bool silhouetteTests = !((item >> 26) & 1u);
+                float r2 = coopRadius2(ws, owner), before = r2;
+                Vec<DIM> q;
+                q[0] = ws.qx[owner]; q[1] = ws.qy[owner];
+                if (DIM == 3) q[DIM - 1] = ws.qz[owner];
+                if (kTwoStage) {
+                    survivor = primStarNeedsFullTest<DIM>(bvh, item & kPrimIndexMask, q, r2, silhouetteTests);
+                } else {
+                    r2 = primStarRadius2Call<DIM>(bvh.prims, bvh.adjacency, bvh.snchSign, item & kPrimIndexMask, q, r2,
+                                                  ws.flags[owner] != 0u, precision, silhouetteTests);
+                    if (r2 < before) zb_atomic_min64(&ws.best[owner], packBest(r2, 0u));
+                }
+            }
             primTop -= n;
+            if (kTwoStage) {
+                if (lane == 0) { ZB_COOP_COUNT(8, n) ZB_COOP_COUNT(9, 1) }
+                unsigned int m = zb_ballot(survivor);
+                if (survivor) ws.prims[kPrimQueue - 1 - (fullTop + zb_popc(m & ((1u << lane) - 1u)))] = item;
+                fullTop += zb_popc(m);
+            } else if (lane == 0) { ZB_COOP_COUNT(3, n) ZB_COOP_COUNT(7, 1) }
             zb_syncwarp();
             continue;
         }
@@ -420,7 +464,7 @@ ZB_COOP_NOINLINE float coopStarRadius2(const BvhView& bvh, WarpShared& ws, bool 
                 }
             }
         }
-        coopPushChildren(ws, nodeTop, primTop, lane, owner, node, keys, nKeep, noSil, status);
+        coopPushChildren(ws, nodeTop, primTop, lane, owner, node, keys, nKeep, noSil, status, fullTop);
         zb_syncwarp();
     }
     float r2 = coopRadius2(ws, lane);

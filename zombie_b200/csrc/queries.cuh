@@ -1026,6 +1026,33 @@ ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const V
     if (redo) r2 = primStarRadius2Redo<3>(bvh.prims, bvh.adjacency, bvh.snchSign, primIdx, x, r2in, flip, precision, silhouetteTests);
 }
 
+// Cheap first stage of primStarRadius2Fast for the pooled primitive rounds of coop.cuh: false when the triangle cannot
+// lower r2 (its reflectance bound is cut off by the plane distance and it has no edge to test), so that only the
+// survivors of a round are compacted into rounds of the full test — in a warp the full test costs the same whether
+// one lane needs it or all 32 do.
+template <int DIM>
+ZB_DEV bool primStarNeedsFullTest(const BvhView& bvh, uint32_t primIdx, const Vec<DIM>& x, float r2, bool silhouetteTests)
+{
+    return true;
+}
+
+template <>
+ZB_DEV bool primStarNeedsFullTest<3>(const BvhView& bvh, uint32_t primIdx, const Vec<3>& x, float r2, bool silhouetteTests)
+{
+    float4 a2 = zb_ldg(bvh.adjacency + (size_t)3*primIdx + 2);
+    float maxCoeff = a2.z;
+    uint32_t flags = zb_float_as_uint(a2.w);
+    if (!ZB_ROBIN_PLANE_BOUND || !(maxCoeff < kMaxFloat - kEpsilon)) return true;
+    if (silhouetteTests && ((flags >> 4) & 7u) != 7u) return true;
+    if (!(maxCoeff > kEpsilon)) return false;
+    Prim<3> prim;
+    prim.load(bvh, primIdx);
+    Vec<3> nRaw = cross(prim.b - prim.a, prim.c - prim.a);
+    float s = dot(nRaw, prim.a - x), nn = dot(nRaw, nRaw);
+    float t = fmaxf(r2*maxCoeff*(1.0f/6.7f), 1e-6f);
+    return !(nn > 0.0f && s*s >= nn*(t*t));
+}
+
 // One out-of-line copy of the fast primitive test for all the traversals of a kernel (the private depth-first phase and
 // the pooled primitive rounds of coop.cuh both call it): ~1300 instructions that would otherwise be resident twice.
 // Build with -DZB_INLINE_PRIM_TESTS to inline it at every call site instead.
