@@ -1208,23 +1208,26 @@ ZB_DEV bool starChildBoundsFast(const BvhView& bvh, uint32_t nodeIdx, int c, con
     cosTheta = fminf(1.0f, fabsf(cosTheta*invL));
     float sinA, cosA;
     zb_sincos_fast(halfAngle, &sinA, &cosA);
-    float sinB = fminf(1.0f, radius*invL), cosB = sqrtf(fmaxf(0.0f, 1.0f - sinB*sinB));
+    float sinB = fminf(1.0f, radius*invL), cosB = zb_sqrt_fast(fmaxf(0.0f, 1.0f - sinB*sinB));
     float sinG = sinA*cosB + cosA*sinB, cosG = cosA*cosB - sinA*sinB; // gamma = cone half angle + view half angle
     if (cosG <= 1e-4f || cosTheta <= sinG + 2e-5f) return true;        // pi/2 within theta +- gamma: may hold a silhouette
 
     hasSil = false;
     if (!(maxCoeff > kEpsilon)) return false; // perfectly reflecting and no silhouette inside
     // RobinBvhNodeBound (robin_bounds.h:102-154): radius range over the whole subtree
-    float sinTheta = sqrtf(fmaxf(0.0f, 1.0f - cosTheta*cosTheta));
+    float sinTheta = zb_sqrt_fast(fmaxf(0.0f, 1.0f - cosTheta*cosTheta));
     float minCos = fmaxf(0.0f, cosTheta*cosG - sinTheta*sinG - 1e-5f); // min |cos| over [theta - gamma, theta + gamma]
-    float rMin = sqrtf(d2min), rMax = sqrtf(d2max);
+    float rMin = zb_sqrt_fast(d2min), rMax = zb_sqrt_fast(d2max);
     if (DIM == 3) {
-        if (rMax < minCos/maxCoeff) lower = kMaxFloat;
-        else { float rb = rMin/(1.0f - minCos/(maxCoeff*rMax)); lower = rb*rb; }
-        if (!(rMin < 1.0f/minCoeff)) { float rb = rMax/(1.0f - 1.0f/(minCoeff*rMin)); upper = rb*rb; }
-        // every triangle below has plane distance h >= rMin minCos, and no triangle's bound is below (27/4) h/mu
-        // (see primStarRadius2Fast): a second lower bound that does not degrade when the subtree is far and large
-        if (ZB_ROBIN_PLANE_BOUND) lower = fmaxf(lower, 6.7f*rMin*minCos/maxCoeff);
+        // r_min/(1 - cos/(mu r_max)) and r_max/(1 - 1/(mu r_min)) with approximate reciprocals: the denominators are
+        // padded by 1e-6 (>> the 2-ulp error of their operands, also where they cancel) on the conservative side
+        float a = minCos*zb_rcp_fast(maxCoeff*rMax);
+        if (a > 1.00001f) lower = kMaxFloat; // r_max < cos/mu
+        else { float rb = rMin*zb_rcp_fast(fmaxf(1.0f - a, 0.0f) + 1e-6f); lower = rb*rb; }
+        if (!(rMin*minCoeff < 1.0f)) {
+            float den = 1.0f - zb_rcp_fast(minCoeff*rMin) - 1e-6f;
+            if (den > 0.0f) { float rb = rMax*zb_rcp_fast(den); upper = rb*rb; }
+        }
     } else {
         float rb = rMin*zb_exp_fast(minCos/(maxCoeff*rMax));
         lower = rb*rb;

@@ -36,6 +36,8 @@ static inline uint32_t zb_umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
 static inline void zb_sincos_fast(float x, float *s, float *c) { *s = sinf(x); *c = cosf(x); }
 static inline float zb_rsqrt(float x) { return 1.0f/sqrtf(x); }
 static inline float zb_exp_fast(float x) { return expf(x); }
+static inline float zb_rcp_fast(float x) { return 1.0f/x; }
+static inline float zb_sqrt_fast(float x) { return sqrtf(x); }
 #else
 #define zb_ldg __ldg
 #define zb_uint_as_float __uint_as_float
@@ -51,6 +53,10 @@ static inline float zb_exp_fast(float x) { return expf(x); }
 #define zb_sincos_fast(x, s, c) __sincosf((x), (s), (c))
 #define zb_rsqrt(x) rsqrtf(x)
 #define zb_exp_fast(x) __expf(x)
+// 2-ulp reciprocal / square root for PRUNING bounds only (they carry explicit slack); values a query returns never
+// go through these
+#define zb_rcp_fast(x) __fdividef(1.0f, (x))
+static __device__ __forceinline__ float zb_sqrt_fast(float x) { return x > 0.0f ? x*rsqrtf(x) : 0.0f; }
 #endif
 
 namespace zb {
