@@ -147,6 +147,7 @@ int main(int argc, char **argv)
     printf("star prims (fast test): robin-only skipped by the plane bound %lld, robin-only evaluated %lld, silhouette prims without / with the reflectance part %lld / %lld\n",
            g_zbClass[4], g_zbClass[7], g_zbClass[5], g_zbClass[6]);
     printf("star edges (fast test): skipped by the sign shortcut %lld, tested in full %lld\n", g_zbClass[8], g_zbClass[9]);
+    printf("star children: %lld passed the box test, %lld of them went on to the reflectance bounds\n", g_zbClass[10], g_zbClass[11]);
     const char *names[5] = {"closest", "ray", "occlusion", "sample", "star"};
     for (int q = 0; q < 5; q++) {
         std::vector<int> n, p;

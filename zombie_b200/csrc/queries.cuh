@@ -1215,6 +1215,7 @@ ZB_DEV bool starChildBoundsFast(const BvhView& bvh, uint32_t nodeIdx, int c, con
     hasSil = false;
     if (!(maxCoeff > kEpsilon)) return false; // perfectly reflecting and no silhouette inside
     // RobinBvhNodeBound (robin_bounds.h:102-154): radius range over the whole subtree
+    ZB_CLASS(11)
     float sinTheta = zb_sqrt_fast(fmaxf(0.0f, 1.0f - cosTheta*cosTheta));
     float minCos = fmaxf(0.0f, cosTheta*cosG - sinTheta*sinG - 1e-5f); // min |cos| over [theta - gamma, theta + gamma]
     float rMin = zb_sqrt_fast(d2min), rMax = zb_sqrt_fast(d2max);
@@ -1279,6 +1280,7 @@ ZB_DEV void starRadiusDfs(const BvhView& bvh, const Vec<DIM>& x, float& r2, bool
             childBox<DIM>(n, f, c, lo, hi);
             boxDistance2<DIM>(lo, hi, x, d2min, d2max);
             if (d2min > r2) continue;
+            ZB_CLASS(10)
             float lower, upper;
             bool hasSil;
             bool keep = FAST ? starChildBoundsFast<DIM>(bvh, e.y, c, x, lo, hi, d2min, d2max, lower, upper, hasSil, precision)
