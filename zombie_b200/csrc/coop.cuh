@@ -228,6 +228,10 @@ ZB_COOP_NOINLINE void coopClosestPoint(const BvhView& bvh, WarpShared& ws, bool 
     // the phase-1 primitive stays the incumbent only if it lies within the (possibly box-shrunk) radius
     ws.best[lane] = packBest(r2own, hit.prim >= 0 && hit.d*hit.d <= r2own ? (uint32_t)hit.prim : 0xffffffffu);
     int nodeTop = 0, primTop = 0;
+    // two-stage primitive rounds as in coopStarRadius2 below: a filter round keeps the triangles whose plane is within
+    // the search radius (primClosestNeedsFullTest), full rounds run the closest-point test on 32 survivors
+    constexpr bool kTwoStage = DIM == 3 && ZB_CLOSEST_PLANE_FILTER && ZB_STAR_TWO_STAGE;
+    int fullTop = 0;
     zb_syncwarp();
 
     while (true) {
@@ -235,24 +239,40 @@ ZB_COOP_NOINLINE void coopClosestPoint(const BvhView& bvh, WarpShared& ws, bool 
             coopRefill(ws, nodeTop, primTop, lane, stack, sp, false);
             zb_syncwarp();
         }
-        if (nodeTop == 0 && primTop == 0) break;
-        if (primTop >= 32 || nodeTop == 0) {
+        if (nodeTop == 0 && primTop == 0 && fullTop == 0) break;
+        const bool fullRound = kTwoStage && (fullTop >= 32 || (nodeTop == 0 && primTop == 0));
+        if (fullRound || primTop >= 32 || nodeTop == 0) {
             // ---- primitive round: one primitive per lane
-            int n = min(primTop, 32);
-            if (lane == 0) { ZB_COOP_COUNT(1, n) ZB_COOP_COUNT(5, 1) }
+            int n = fullRound ? min(fullTop, 32) : min(primTop, 32);
+            uint32_t item = 0u;
+            bool survivor = false;
             if (lane < n) {
-                uint32_t item = ws.prims[primTop - 1 - lane];
+                item = fullRound ? ws.prims[kPrimQueue - fullTop + lane] : ws.prims[primTop - 1 - lane];
                 int owner = (int)(item >> 27);
                 uint32_t idx = item & kPrimIndexMask;
                 float r2 = coopRadius2(ws, owner);
                 Vec<DIM> q;
                 q[0] = ws.qx[owner]; q[1] = ws.qy[owner];
                 if (DIM == 3) q[DIM - 1] = ws.qz[owner];
-                float d = primClosestCall<DIM>(bvh.prims, idx, q).w;
-                float d2 = d*d;
-                if (d2 <= r2) zb_atomic_min64(&ws.best[owner], packBest(d2, idx));
+                if (kTwoStage && !fullRound) {
+                    survivor = primClosestNeedsFullTest<DIM>(bvh.prims, idx, q, r2);
+                } else {
+                    float d = primClosestCall<DIM>(bvh.prims, idx, q).w;
+                    float d2 = d*d;
+                    if (d2 <= r2) zb_atomic_min64(&ws.best[owner], packBest(d2, idx));
+                }
             }
-            primTop -= n;
+            if (fullRound) {
+                if (lane == 0) { ZB_COOP_COUNT(1, n) ZB_COOP_COUNT(5, 1) }
+                fullTop -= n;
+            } else {
+                primTop -= n;
+                if (kTwoStage) {
+                    unsigned int m = zb_ballot(survivor);
+                    if (survivor) ws.prims[kPrimQueue - 1 - (fullTop + zb_popc(m & ((1u << lane) - 1u)))] = item;
+                    fullTop += zb_popc(m);
+                } else if (lane == 0) { ZB_COOP_COUNT(1, n) ZB_COOP_COUNT(5, 1) }
+            }
             zb_syncwarp();
             continue;
         }
@@ -302,7 +322,7 @@ ZB_COOP_NOINLINE void coopClosestPoint(const BvhView& bvh, WarpShared& ws, bool 
                 }
             }
         }
-        coopPushChildren(ws, nodeTop, primTop, lane, owner, node, keys, nKeep, 0u, status);
+        coopPushChildren(ws, nodeTop, primTop, lane, owner, node, keys, nKeep, 0u, status, fullTop);
         zb_syncwarp();
     }
 

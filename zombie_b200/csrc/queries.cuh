@@ -340,6 +340,25 @@ ZB_DEV void setThird(Prim<2>&, const float4&) {}
 template <int DIM>
 ZB_DEV Vec<DIM> unitNormal(const Prim<DIM>& p) { Vec<DIM> n = p.rawNormal(); return n/xnorm(n); }
 
+#ifndef ZB_CLOSEST_PLANE_FILTER
+#define ZB_CLOSEST_PLANE_FILTER 1 // 0: run the closest-point test on every primitive of a visited leaf (A/B builds)
+#endif
+
+// Cheap first stage of the closest-point test (3D): a triangle whose PLANE is farther than the search radius cannot
+// hold a closer point. False = skip it. 1e-5 of slack keeps exact ties (which the reference resolves by primitive
+// order, triangles.inl:479) inside the full test.
+template <int DIM>
+ZB_DEV bool primClosestNeedsFullTest(const float4 *prims, uint32_t i, const Vec<DIM>& x, float r2)
+{
+    if (DIM != 3 || !ZB_CLOSEST_PLANE_FILTER) return true;
+    float4 v0 = zb_ldg(prims + (size_t)3*i), v1 = zb_ldg(prims + (size_t)3*i + 1), v2 = zb_ldg(prims + (size_t)3*i + 2);
+    float e1[3] = {v1.x - v0.x, v1.y - v0.y, v1.z - v0.z}, e2[3] = {v2.x - v0.x, v2.y - v0.y, v2.z - v0.z};
+    float n[3] = {e1[1]*e2[2] - e1[2]*e2[1], e1[2]*e2[0] - e1[0]*e2[2], e1[0]*e2[1] - e1[1]*e2[0]};
+    float s = n[0]*(x[0] - v0.x) + n[1]*(x[1] - v0.y) + n[2]*(x[DIM - 1] - v0.z);
+    float nn = n[0]*n[0] + n[1]*n[1] + n[2]*n[2];
+    return !(s*s > nn*(r2*1.00001f));
+}
+
 // Closest point on primitive i (leaf order): ONE out-of-line copy per kernel, shared by the private depth-first phase,
 // the pooled primitive rounds and the final re-evaluation of the winner (coop.cuh) and by sampleSphere. Returns
 // (pt, distance) packed in a float4. Build with -DZB_INLINE_PRIM_TESTS to inline it at every call site instead.
@@ -410,8 +429,9 @@ ZB_DEV void closestPointDfs(const BvhView& bvh, const Vec<DIM>& x, float& r2, Cl
         if (e.y & kLeafFlag) {
             uint32_t first = e.y & 0x0fffffffu, count = (e.y >> 28) & 7u;
             for (uint32_t i = 0; i < count; i++) {
-                float4 cp = primClosestCall<DIM>(bvh.prims, first + i, x);
                 ZB_COUNT_PRIM
+                if (!primClosestNeedsFullTest<DIM>(bvh.prims, first + i, x, r2)) continue;
+                float4 cp = primClosestCall<DIM>(bvh.prims, first + i, x);
                 float d = cp.w, d2 = d*d;
                 if (d2 <= r2) { // triangles.inl:479: inclusive, later primitives replace equal distances
                     r2 = d2;
