@@ -459,8 +459,12 @@ ZB_COOP_NOINLINE float coopStarRadius2(const BvhView& bvh, WarpShared& ws, bool 
                 loadNode(bvh.nodes, item.y, node);
                 NodeFrame<DIM> f = nodeFrame<DIM>(node);
                 float shrink = r2;
+                ConePrefetch cones;
+                cones.start(bvh, item.y);
                 ZB_CHILD_LOOP
                 for (int c = 0; c < 8; c++) {
+                    float4 c0, c1;
+                    cones.next(c, c0, c1);
                     uint32_t meta = childMeta(node, c);
                     if (meta == 0u) continue;
                     float lo[DIM], hi[DIM], d2min, d2max;
@@ -469,7 +473,7 @@ ZB_COOP_NOINLINE float coopStarRadius2(const BvhView& bvh, WarpShared& ws, bool 
                     if (d2min > r2) continue;
                     float lower, upper;
                     bool hasSil;
-                    if (!starChildBoundsFast<DIM>(bvh, item.y, c, q, lo, hi, d2min, d2max, lower, upper, hasSil, precision)) continue;
+                    if (!starChildBoundsFast<DIM>(c0, c1, q, lo, hi, d2min, d2max, lower, upper, hasSil, precision)) continue;
                     shrink = fminf(shrink, upper);
                     if (!hasSil || parentNoSil) noSil |= 1u << c;
                     insertKey(keys, (zb_float_as_uint(lower) & ~63u) | (uint32_t)c);

@@ -1200,12 +1200,13 @@ ZB_DEV bool starChildBounds(const BvhView& bvh, uint32_t nodeIdx, int c, const V
 // starChildBounds' own tests: the overlap threshold carries 2e-5 of slack on the sine, the Robin cosine bound
 // 1e-5, on top of the 1e-4 rad by which the builder pads every cone.
 template <int DIM>
-ZB_DEV bool starChildBoundsFast(const BvhView& bvh, uint32_t nodeIdx, int c, const Vec<DIM>& x,
+ZB_DEV bool starChildBoundsFast(const float4& c0, const float4& c1, const Vec<DIM>& x,
                                                     const float lo[DIM], const float hi[DIM], float d2min, float d2max,
                                                     float& lower, float& upper, bool& hasSil, float precision)
 {
-    const float4 *cone = bvh.cones + ((size_t)nodeIdx*8 + c)*2;
-    float4 c0 = zb_ldg(cone), c1 = zb_ldg(cone + 1);
+    // c0, c1: the child's ChildCone (axis | half angle, radius | coefficient range), loaded by the caller one child
+    // ahead (ConePrefetch below) — the child loop is rolled, and a load issued where its value is needed would put
+    // one full memory latency into every iteration
     float minCoeff = c1.y, maxCoeff = c1.z;
     lower = d2min;
     upper = d2max;
@@ -1261,6 +1262,26 @@ ZB_DEV bool starChildBoundsFast(const BvhView& bvh, uint32_t nodeIdx, int c, con
     return true;
 }
 
+// One-child-ahead loads of a node's eight ChildCones for the rolled child loops of the star-radius traversals.
+struct ConePrefetch {
+    const float4 *base;
+    float4 n0, n1;
+    ZB_DEV void start(const BvhView& bvh, uint32_t nodeIdx) {
+        base = bvh.cones + (size_t)nodeIdx*16;
+        n0 = zb_ldg(base);
+        n1 = zb_ldg(base + 1);
+    }
+    // returns child c's cone and issues the loads of child c + 1 (every node owns eight entries, empty slots included)
+    ZB_DEV void next(int c, float4& c0, float4& c1) {
+        c0 = n0;
+        c1 = n1;
+        if (c < 7) {
+            n0 = zb_ldg(base + 2*(c + 1));
+            n1 = zb_ldg(base + 2*(c + 1) + 1);
+        }
+    }
+};
+
 // Depth-first core of the star-radius query: pops up to `budget` stack entries and returns with the unfinished
 // part of the traversal on the stack (sp > 0) when the budget runs out. FAST selects the algebraic child test.
 template <int DIM, bool FAST>
@@ -1292,8 +1313,12 @@ ZB_DEV void starRadiusDfs(const BvhView& bvh, const Vec<DIM>& x, float& r2, bool
         uint32_t noSil = 0u;
 #pragma unroll
         for (int c = 0; c < 8; c++) keys[c] = 0xffffffffu;
+        ConePrefetch cones;
+        if (FAST) cones.start(bvh, e.y);
         ZB_CHILD_LOOP
         for (int c = 0; c < 8; c++) {
+            float4 c0, c1;
+            if (FAST) cones.next(c, c0, c1);
             uint32_t meta = childMeta(n, c);
             if (meta == 0u) continue;
             float lo[DIM], hi[DIM], d2min, d2max;
@@ -1303,7 +1328,7 @@ ZB_DEV void starRadiusDfs(const BvhView& bvh, const Vec<DIM>& x, float& r2, bool
             ZB_CLASS(10)
             float lower, upper;
             bool hasSil;
-            bool keep = FAST ? starChildBoundsFast<DIM>(bvh, e.y, c, x, lo, hi, d2min, d2max, lower, upper, hasSil, precision)
+            bool keep = FAST ? starChildBoundsFast<DIM>(c0, c1, x, lo, hi, d2min, d2max, lower, upper, hasSil, precision)
                              : starChildBounds<DIM>(bvh, e.y, c, x, lo, hi, d2min, d2max, lower, upper, hasSil, precision);
             if (!keep) continue;
             r2 = fminf(r2, upper);
