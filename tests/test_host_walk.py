@@ -108,6 +108,21 @@ def test_cooperative_traversal_on_emulated_warps(tmp_path):
         assert worst < 2e-5, r.stdout   # squared radius; fused vs reference-ordered primitive arithmetic
 
 
+def test_cooperative_traversal_2d_on_emulated_warps(tmp_path):
+    """The DIM = 2 instantiation of coop.cuh (line segments, silhouette vertices; configs C1 / C2) on emulated warps
+    (tools/coop_check2d.cu): identical distances and star radii to the one-thread traversal on a star-shaped polygon,
+    Robin and Neumann, coarse and fine."""
+    exe = str(tmp_path / "coop_check2d")
+    cmd = ["/usr/local/cuda/bin/nvcc", "-std=c++17", "-O2", "-DZB_EMULATE_WARP", "-Xcompiler", "-ffp-contract=off", "-Xcompiler",
+           "-pthread", "-o", exe, os.path.join(ROOT, "tools", "coop_check2d.cu"), os.path.join(ROOT, "zombie_b200", "csrc", "wide_bvh.cpp")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    for args in (("4096", "1024", "1"), ("4096", "1024", "0"), ("512", "512", "5")):
+        r = subprocess.run([exe, *args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0 and "distance mismatches 0" in r.stdout and "star: mismatches 0" in r.stdout, r.stdout
+        assert "cooperative status 0" in r.stdout, r.stdout
+
+
 @pytest.fixture(scope="module")
 def host_query(tmp_path_factory):
     exe = str(tmp_path_factory.mktemp("hostq") / "host_query")
