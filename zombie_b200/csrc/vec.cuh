@@ -12,11 +12,7 @@
 #define ZB_HOSTDEV __host__ __device__ __forceinline__
 // rarely executed paths that must stay OUT of the hot loops' instruction footprint: the walk kernel is bound by
 // instruction fetch (profiles/README.md), so what is cold is kept out of line on the device
-#if defined(__CUDA_ARCH__)
-#define ZB_DEV_COLD __device__ __noinline__
-#else
-#define ZB_DEV_COLD __host__ __device__ inline
-#endif
+#define ZB_DEV_COLD __host__ __device__ __noinline__ inline
 
 #if !defined(__CUDA_ARCH__)
 #include <string.h>
