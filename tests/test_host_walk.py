@@ -266,3 +266,56 @@ def test_device_walk_code_on_host_at_cache_points(ref, host_solve, tmp_path):
     se = np.sqrt(np.var(dh - exact)/96 + np.var(dref - exact)/96)
     assert abs(np.mean(dh - exact) - np.mean(dref - exact)) < 4.0*se + 0.02
     assert abs(np.mean(dh - exact)) < 4.0*np.std(dh - exact)/np.sqrt(96) + 0.02
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_device_ray_and_sampling_code_on_host_matches_reference(ref, tmp_path, dim):
+    """Aggregate::intersect(Ray) closest hit / occlusion (bvh.inl:656-771) and the stochastic sphere-sampling descent
+    (bvh.inl:1141-1288) as the kernels run them, compiled for the host (tools/host_rays.cu): hits against the compiled
+    reference under the gates of the GPU test (primitive identical or an exact tie in t, t and point to 1e-6, normal to
+    1e-5, occlusion flags identical), sampling as an importance sampler (E[1/pdf] per query within 4 standard errors of
+    the reference's own sampler; the pdf depends on the tree, so nothing finer is comparable)."""
+    from tests.test_gpu_queries import check_rays
+    exe = str(tmp_path / "host_rays")
+    cmd = ["/usr/local/cuda/bin/nvcc", "-std=c++17", "-O2", "-Xcompiler", "-ffp-contract=off", "-o", exe,
+           os.path.join(ROOT, "tools", "host_rays.cu"), os.path.join(ROOT, "zombie_b200", "csrc", "wide_bvh.cpp")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    whole, absorbing, reflecting = cases.mesh3d(4) if dim == 3 else cases.mesh2d(2048)
+    pos, idx = reflecting
+    nq = 20000
+    o, d, tmax = cases.rays(nq, dim, 0.9, seed=5)
+    n = 100000
+    sx = np.repeat(cases.query_points(50, dim, 0.8, seed=51), n//50, axis=0)
+    rad = np.full(n, 0.6, np.float32)
+    u = np.random.RandomState(5).uniform(size=(n, dim)).astype(np.float32)
+    dd = str(tmp_path)
+    for name, a, t in (("pos", pos, np.float32), ("idx", idx, np.int32), ("o", o, np.float32), ("d", d, np.float32),
+                       ("tmax", tmax, np.float32), ("sx", sx, np.float32), ("srad", rad, np.float32), ("su", u, np.float32)):
+        np.ascontiguousarray(a, t).tofile(os.path.join(dd, name + ".bin"))
+    r = subprocess.run([exe, dd, str(dim)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    rays = np.fromfile(os.path.join(dd, "rays_out.bin"), np.float32).reshape(nq, 3 + 2*dim)
+    smp = np.fromfile(os.path.join(dd, "samples_out.bin"), np.float32).reshape(n, 2 + 2*dim)
+
+    rs = ref.RefScene(dim, **cases.scene_kwargs(dim, abi.REFLECTING_NEUMANN, absorbing, reflecting))
+    ref_hits = rs.intersect_ray(abi.REFLECTING, o, d, tmax)
+    assert (ref_hits[0] >= 0).mean() > 0.1 and (ref_hits[0] < 0).mean() > 0.1
+    check_rays(ref_hits, (rays[:, 0].astype(np.int32), rays[:, 1], rays[:, 2:2 + dim], rays[:, 2 + dim:2 + 2*dim]))
+    assert np.array_equal(rs.occluded(abi.REFLECTING, o, o + d*tmax[:, None]).astype(bool), rays[:, 2 + 2*dim] > 0.5)
+
+    rprim, rpt, rn, rpdf = rs.sample_sphere(sx, rad, u)
+    gprim, gpdf, gpt, gn = smp[:, 0].astype(np.int32), smp[:, 1], smp[:, 2:2 + dim], smp[:, 2 + dim:]
+    f = gprim >= 0
+    assert f.mean() > 0.2 and (gpdf[f] > 0).all()
+    bad = 0
+    for j in range(50):
+        sl = slice(j*(n//50), (j + 1)*(n//50))
+        wr = np.where(rprim[sl] >= 0, 1.0/np.maximum(rpdf[sl], 1e-30), 0.0)
+        wg = np.where(gprim[sl] >= 0, 1.0/np.maximum(gpdf[sl], 1e-30), 0.0)
+        se = np.sqrt(wr.var()/len(wr) + wg.var()/len(wg))
+        bad += abs(wr.mean() - wg.mean()) > 4.0*se + 1e-6
+    assert bad <= 2
+    a = pos[idx[gprim[f], 0]]
+    assert np.abs(((gpt[f] - a)*gn[f]).sum(axis=1)).max() < 1e-5   # the sample lies on the primitive it names
+    rs.close()
