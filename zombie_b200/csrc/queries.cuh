@@ -878,6 +878,9 @@ ZB_DEV_COLD bool isSilhouetteEdge3Cold(Vec<3> pa, Vec<3> pb, Vec<3> n0, Vec<3> n
     return isSilhouetteEdge3(pa, pb, n0, n1, viewDir, d, flip, precision, convention);
 }
 
+#ifndef ZB_NO_EDGE_FLAG
+#define ZB_NO_EDGE_FLAG 1 // 0: ignore the builder's "no testable edge below" mark (A/B builds)
+#endif
 #ifndef ZB_SILHOUETTE_SIGN_SHORTCUT
 #define ZB_SILHOUETTE_SIGN_SHORTCUT 1 // 0: run the full edge test on every edge (A/B builds)
 #endif
@@ -1214,13 +1217,19 @@ ZB_DEV bool starChildBoundsFast(const float4& c0, const float4& c1, const Vec<DI
     if (!(minCoeff < kMaxFloat - kEpsilon)) return true; // perfectly absorbing subtree: plain distance bounds
 
     upper = kMaxFloat;
+    // The builder marks subtrees in which every edge carries the reference's ignore mark (convex edges of a single-sided
+    // solve, fcpw_geometric_queries.h:1029-1038): their primitive tests skip every edge, so wherever the cone test below
+    // would have to answer "may hold a silhouette" such a subtree holds none — a perfectly reflecting one (Neumann) is
+    // pruned, a Robin one is kept for its reflectance bounds only (no radius bound is derived for it: lower = d2min).
+    const bool noEdges = ZB_NO_EDGE_FLAG && c1.w != 0.0f;
+#define ZB_MAY_HOLD_SILHOUETTE { if (!noEdges) return true; hasSil = false; return maxCoeff > kEpsilon; }
     float halfAngle = c0.w;
-    if (halfAngle >= kHalfPiF || d2min < kEpsilon || d2min <= precision*precision) return true; // see starChildBounds
+    if (halfAngle >= kHalfPiF || d2min < kEpsilon || d2min <= precision*precision) ZB_MAY_HOLD_SILHOUETTE // see starChildBounds
     float view[DIM], l2 = 0.0f;
 #pragma unroll
     for (int k = 0; k < DIM; k++) { view[k] = 0.5f*(lo[k] + hi[k]) - x[k]; l2 = fmaf(view[k], view[k], l2); }
     float radius = c1.x;
-    if (!(l2 > radius*radius)) return true; // inside the bounding sphere of the child: treat as overlapping
+    if (!(l2 > radius*radius)) ZB_MAY_HOLD_SILHOUETTE // inside the bounding sphere of the child: treat as overlapping
     float invL = zb_rsqrt(l2);
     float cosTheta = 0.0f;
     const float axis[3] = {c0.x, c0.y, c0.z};
@@ -1231,7 +1240,8 @@ ZB_DEV bool starChildBoundsFast(const float4& c0, const float4& c1, const Vec<DI
     zb_sincos_fast(halfAngle, &sinA, &cosA);
     float sinB = fminf(1.0f, radius*invL), cosB = zb_sqrt_fast(fmaxf(0.0f, 1.0f - sinB*sinB));
     float sinG = sinA*cosB + cosA*sinB, cosG = cosA*cosB - sinA*sinB; // gamma = cone half angle + view half angle
-    if (cosG <= 1e-4f || cosTheta <= sinG + 2e-5f) return true;        // pi/2 within theta +- gamma: may hold a silhouette
+    if (cosG <= 1e-4f || cosTheta <= sinG + 2e-5f) ZB_MAY_HOLD_SILHOUETTE // pi/2 within theta +- gamma
+#undef ZB_MAY_HOLD_SILHOUETTE
 
     hasSil = false;
     if (!(maxCoeff > kEpsilon)) return false; // perfectly reflecting and no silhouette inside

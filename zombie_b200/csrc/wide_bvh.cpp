@@ -294,7 +294,7 @@ ChildCone computeCone(const Geometry& g, const std::vector<PrimAdjacency>& adj, 
     cone.minCoeff = FLT_MAX;
     cone.maxCoeff = -FLT_MAX;
     float axis[3] = {0, 0, 0};
-    bool allAdjacent = true;
+    bool allAdjacent = true, anyTestableEdge = false;
     int nEdges = g.dim;
     for (int i = 0; i < count; i++) {
         int p = prims[i];
@@ -314,8 +314,12 @@ ChildCone computeCone(const Geometry& g, const std::vector<PrimAdjacency>& adj, 
             float d[3] = {q[0]-centroid[0], q[1]-centroid[1], q[2]-centroid[2]};
             cone.radius = std::max(cone.radius, norm3(d));
             allAdjacent = allAdjacent && ((adj[p].flags >> k) & 1u);
+            anyTestableEdge = anyTestableEdge || !((adj[p].flags >> (4 + k)) & 1u);
         }
     }
+    // every edge (vertex in 2D) below carries the ignore mark: no primitive test in this subtree can ever report a
+    // silhouette, whatever the normal cone says
+    cone.noTestableEdge = anyTestableEdge ? 0.0f : 1.0f;
     if (allAdjacent) {
         float l = norm3(axis);
         if (l > FLT_EPSILON) {

@@ -43,7 +43,7 @@ struct ChildCone {
     float radius;        // max distance from the (decoded) box centroid to an edge midpoint / vertex
     float minCoeff;
     float maxCoeff;
-    float pad;
+    float noTestableEdge; // 1: every edge below is marked ignoreAdjacentFace (single-sided solves: convex edges), else 0
 };
 static_assert(sizeof(ChildCone) == 32, "ChildCone must be 32 bytes");
 
