@@ -319,8 +319,9 @@ def run_native(args, rank, world, local_rank):
                          "traffic": None, "peak_kind": peak_kind, "kernel": "walkKernel<3,true>", "grid": grid,
                          "algorithmic_bytes_per_walk_step": bytes_per_step, "kernel_ms_per_step": walk_ms/args.steps,
                          "kernel_share_of_step": walk_ms/dev_ms if dev_ms > 0 else None,
-                         "traffic_note": "ncu --set full of the same kernel on a 512-point launch (profiles/README.md): 20 KB of "
-                                         "DRAM traffic and 44 K warp instructions per walk step; issue/latency bound, not HBM bound"},
+                         "traffic_note": "ncu --set full of the round-1 kernel on a 512-point launch (profiles/README.md): 20 KB of "
+                                         "DRAM traffic and 44 K warp instructions per walk step, 54 % of stalls on instruction "
+                                         "fetch; issue/latency bound, not HBM bound (kernel reshaped since, not re-profiled)"},
         }
         if not args.no_cpu and world == 1:   # the CPU baseline is reported at N = 1 only
             line["cpu_baseline"] = cpu_baseline(args, w)
