@@ -345,7 +345,7 @@ ZB_DEV Vec<DIM> unitNormal(const Prim<DIM>& p) { Vec<DIM> n = p.rawNormal(); ret
 #endif
 
 // Cheap first stage of the closest-point test (3D): a triangle whose PLANE is farther than the search radius cannot
-// hold a closer point. False = skip it. 1e-5 of slack keeps exact ties (which the reference resolves by primitive
+// hold a closer point, nor can one whose bounding sphere is. False = skip it. 1e-5 of slack keeps exact ties (which the reference resolves by primitive
 // order, triangles.inl:479) inside the full test.
 template <int DIM>
 ZB_DEV bool primClosestNeedsFullTest(const float4 *prims, uint32_t i, const Vec<DIM>& x, float r2)
@@ -356,7 +356,16 @@ ZB_DEV bool primClosestNeedsFullTest(const float4 *prims, uint32_t i, const Vec<
     float n[3] = {e1[1]*e2[2] - e1[2]*e2[1], e1[2]*e2[0] - e1[0]*e2[2], e1[0]*e2[1] - e1[1]*e2[0]};
     float s = n[0]*(x[0] - v0.x) + n[1]*(x[1] - v0.y) + n[2]*(x[DIM - 1] - v0.z);
     float nn = n[0]*n[0] + n[1]*n[1] + n[2]*n[2];
-    return !(s*s > nn*(r2*1.00001f));
+    if (s*s > nn*(r2*1.00001f)) return false;
+    // ... nor can one whose bounding sphere (about the centroid) lies beyond it: |x - c| > R + r, squared
+    float c[3] = {(v0.x + v1.x + v2.x)*(1.0f/3.0f), (v0.y + v1.y + v2.y)*(1.0f/3.0f), (v0.z + v1.z + v2.z)*(1.0f/3.0f)};
+    float a0 = v0.x - c[0], a1 = v0.y - c[1], a2 = v0.z - c[2], b0 = v1.x - c[0], b1 = v1.y - c[1], b2 = v1.z - c[2];
+    float g0 = v2.x - c[0], g1 = v2.y - c[1], g2 = v2.z - c[2];
+    float R2 = fmaxf(fmaxf(a0*a0 + a1*a1 + a2*a2, b0*b0 + b1*b1 + b2*b2), g0*g0 + g1*g1 + g2*g2)*1.00001f;
+    float dx = x[0] - c[0], dy = x[1] - c[1], dz = x[DIM - 1] - c[2];
+    float dc2 = dx*dx + dy*dy + dz*dz, rr = r2*1.00001f;
+    // r2 may be +inf (unbounded search): inf*0 = NaN and inf compare false either way -> kept
+    return !(dc2 > (R2 + rr + 2.0f*zb_sqrt_fast(R2*rr))*1.00001f);
 }
 
 // Closest point on primitive i (leaf order): ONE out-of-line copy per kernel, shared by the private depth-first phase,
