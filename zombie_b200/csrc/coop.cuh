@@ -132,8 +132,9 @@ ZB_COOP void coopPushChildren(WarpShared& ws, int& nodeTop, int& primTop, int la
             nPrims += (int)count;
         }
     }
-    int inclN = warpInclusiveSum(nNodes, lane), inclP = warpInclusiveSum(nPrims, lane);
-    int totalN = zb_shfl(inclN, 31), totalP = zb_shfl(inclP, 31);
+    // one scan for both counts (nodes in the low half-word, primitives in the high one: totals stay below 2^16)
+    int incl = warpInclusiveSum(nNodes | (nPrims << 16), lane), total = zb_shfl(incl, 31);
+    int inclN = incl & 0xffff, inclP = incl >> 16, totalN = total & 0xffff, totalP = total >> 16;
     if (nodeTop + totalN > kNodeStack || primTop + totalP + primReserved > kPrimQueue) { // warp-uniform; cannot happen for trees of depth <= 18
         if (lane == 0 && status) zb_status_or(status, kStatusCoopOverflow);
         return;
@@ -180,8 +181,8 @@ ZB_COOP void coopRefill(WarpShared& ws, int& nodeTop, int& primTop, int lane, co
         uint32_t y = stack[sp - take + k].y;
         if (y & kLeafFlag) nPrims += (int)((y >> 28) & 7u); else nNodes++;
     }
-    int inclN = warpInclusiveSum(nNodes, lane), inclP = warpInclusiveSum(nPrims, lane);
-    int totalN = zb_shfl(inclN, 31), totalP = zb_shfl(inclP, 31);
+    int incl = warpInclusiveSum(nNodes | (nPrims << 16), lane), total = zb_shfl(incl, 31);
+    int inclN = incl & 0xffff, inclP = incl >> 16, totalN = total & 0xffff, totalP = total >> 16;
     int slotN = nodeTop + inclN - nNodes, slotP = primTop + inclP - nPrims;
 #pragma unroll 1
     for (int k = 0; k < take; k++) { // bottom to top: the lane's nearest entry ends on top of its group
