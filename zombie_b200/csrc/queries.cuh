@@ -1239,7 +1239,7 @@ ZB_DEV bool starChildBoundsFast(const float4& c0, const float4& c1, const Vec<DI
     for (int k = 0; k < DIM; k++) { view[k] = 0.5f*(lo[k] + hi[k]) - x[k]; l2 = fmaf(view[k], view[k], l2); }
     float radius = c1.x;
     if (!(l2 > radius*radius)) ZB_MAY_HOLD_SILHOUETTE // inside the bounding sphere of the child: treat as overlapping
-    float invL = zb_rsqrt(l2);
+    float invL = zb_rsqrt_fast(l2);
     float cosTheta = 0.0f;
     const float axis[3] = {c0.x, c0.y, c0.z};
 #pragma unroll

@@ -34,6 +34,7 @@ static inline float zb_rsqrt(float x) { return 1.0f/sqrtf(x); }
 static inline float zb_exp_fast(float x) { return expf(x); }
 static inline float zb_rcp_fast(float x) { return 1.0f/x; }
 static inline float zb_sqrt_fast(float x) { return sqrtf(x); }
+static inline float zb_rsqrt_fast(float x) { return 1.0f/sqrtf(x); }
 #else
 #define zb_ldg __ldg
 #define zb_uint_as_float __uint_as_float
@@ -51,8 +52,11 @@ static inline float zb_sqrt_fast(float x) { return sqrtf(x); }
 #define zb_exp_fast(x) __expf(x)
 // 2-ulp reciprocal / square root for PRUNING bounds only (they carry explicit slack); values a query returns never
 // go through these
-#define zb_rcp_fast(x) __fdividef(1.0f, (x))
-static __device__ __forceinline__ float zb_sqrt_fast(float x) { return x > 0.0f ? x*rsqrtf(x) : 0.0f; }
+// (single MUFU instructions: the library forms rsqrtf / __fdividef add denormal and range handling these operands —
+// distances and cosines of order 1e-6 .. 1e3 — never need)
+static __device__ __forceinline__ float zb_rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+static __device__ __forceinline__ float zb_sqrt_fast(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+static __device__ __forceinline__ float zb_rsqrt_fast(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 #endif
 
 namespace zb {
