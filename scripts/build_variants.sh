@@ -9,6 +9,8 @@ python -m zombie_b200.build --variant unrolled -DZB_UNROLL_CHILD_LOOPS
 python -m zombie_b200.build --variant inlined -DZB_INLINE_PRIM_TESTS
 python -m zombie_b200.build --variant no_plane_bound -DZB_ROBIN_PLANE_BOUND=0 -DZB_STAR_TWO_STAGE=0
 python -m zombie_b200.build --variant one_stage -DZB_STAR_TWO_STAGE=0
+python -m zombie_b200.build --variant no_closest_filter -DZB_CLOSEST_PLANE_FILTER=0
+python -m zombie_b200.build --variant no_edge_flag -DZB_NO_EDGE_FLAG=0
 python -m zombie_b200.build --variant budget4 -DZB_PHASE1_BUDGET=4
 python -m zombie_b200.build --variant budget16 -DZB_PHASE1_BUDGET=16
 ls -la zombie_b200/variants/
