@@ -158,6 +158,12 @@ int main(int argc, char **argv)
         printf("%-10s nodes mean %8.1f p50 %6d p90 %6d p99 %6d p99.9 %6d max %7d | prims mean %8.1f p50 %6d p90 %6d p99 %6d p99.9 %6d max %7d\n", names[q],
                mn/n.size(), pct(n, .5), pct(n, .9), pct(n, .99), pct(n, .999), n.back(), mp/p.size(), pct(p, .5), pct(p, .9), pct(p, .99), pct(p, .999), p.back());
     }
+    {   // steps that start ON the reflecting boundary: their share of the steps and of the closest-point work
+        long long nOn = 0, cn = 0, cp = 0, an = 0, ap = 0;
+        for (auto& s : steps) { an += s.nodes[0]; ap += s.prims[0]; if (s.onRefl) { nOn++; cn += s.nodes[0]; cp += s.prims[0]; } }
+        printf("steps starting on the reflecting boundary: %.1f %% of the steps, %.1f %% of the closest-point nodes, %.1f %% of its primitives\n",
+               100.0*nOn/std::max<size_t>(1, steps.size()), 100.0*cn/std::max(1LL, an), 100.0*cp/std::max(1LL, ap));
+    }
     // the worst star-radius steps
     std::sort(steps.begin(), steps.end(), [](const StepCost& x, const StepCost& y) { return x.prims[4] > y.prims[4]; });
     for (int i = 0; i < 8 && i < (int)steps.size(); i++)

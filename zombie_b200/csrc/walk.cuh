@@ -154,7 +154,7 @@ ZB_DEV bool outsideDomain(const SolveArgs& a, const Vec<DIM>& x)
 
 // GeometricQueries::computeDistToAbsorbingBoundary (+ the closest point, reused at termination)
 template <int DIM>
-ZB_DEV float distToAbsorbing(const SolveArgs& a, const Vec<DIM>& x, Vec<DIM>& proj, int& projPrim)
+ZB_DEV float distToAbsorbing(const SolveArgs& a, const Vec<DIM>& x, Vec<DIM>& proj, int& projPrim, float r2max = kMaxFloat)
 {
     if (!a.hasAbsorbing) {
         // default of GeometricQueries::populate (geometric_queries.h:213-218)
@@ -166,7 +166,7 @@ ZB_DEV float distToAbsorbing(const SolveArgs& a, const Vec<DIM>& x, Vec<DIM>& pr
         return sqrtf(s);
     }
     ClosestHit<DIM> hit;
-    closestPoint<DIM>(a.absorbing, x, kMaxFloat, hit, a.status);
+    closestPoint<DIM>(a.absorbing, x, r2max, hit, a.status);
     proj = hit.p;
     projPrim = hit.prim;
     return hit.d;
@@ -522,12 +522,33 @@ ZB_DEV void beginTask(const SolveArgs& a, Lane<DIM>& L, long long task)
     L.needClosest = true;
 }
 
+#ifndef ZB_BOUNDED_CLOSEST
+#define ZB_BOUNDED_CLOSEST 1 // 0: every distance query searches without a radius bound (A/B builds)
+#endif
+
+// Squared search radius of a pending distance-to-absorbing-boundary query. A Walk on Stars step that starts ON a boundary
+// with a non-zero Robin coefficient takes an epsilon-sized ball whatever that distance is (walk_on_stars.h:377-381,
+// stepStarPrologue below), so all the walk needs to learn is whether it stands inside the absorbing epsilon shell:
+// the search stops at that radius ("nothing found" leaves distA at +inf, the projection unused). 17 % of the steps
+// of a C3-like solve and a tenth of its closest-point work (tools/host_probe.cu).
+template <int DIM, bool WOST>
+ZB_DEV float closestSearchRadius2(const SolveArgs& a, const Lane<DIM>& L)
+{
+    if (!WOST || !ZB_BOUNDED_CLOSEST || !a.hasReflecting) return kMaxFloat;
+    if (L.keepDistA || L.firstStep || !L.st.onRefl) return kMaxFloat;
+    if (!(a.ws.stepsBeforeUsingMaximalSpheres > L.st.walkLength)) return kMaxFloat; // the maximal-sphere step reads distA
+    PdeEval<DIM> pde{a.pde};
+    if (!pde.hasNonZeroRobinCoeff(L.st.pt)) return kMaxFloat;
+    float e = a.ws.epsilonShellForAbsorbingBoundary;
+    return e*e*1.0001f;
+}
+
 // thread-per-query resolution of a pending distance query (host probe; the kernel does it cooperatively)
-template <int DIM>
+template <int DIM, bool WOST = true>
 ZB_DEV void resolveClosest(const SolveArgs& a, Lane<DIM>& L)
 {
     int projPrim;
-    float d = distToAbsorbing<DIM>(a, L.st.pt, L.proj, projPrim);
+    float d = distToAbsorbing<DIM>(a, L.st.pt, L.proj, projPrim, closestSearchRadius2<DIM, WOST>(a, L));
     if (!L.keepDistA) L.distA = d;
     L.needClosest = false;
     L.keepDistA = false;
@@ -775,7 +796,7 @@ ZB_DEV StepResult stepBody(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *que
 template <int DIM, bool WOST>
 ZB_DEV StepResult walkStep(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *queue)
 {
-    if (L.needClosest) resolveClosest<DIM>(a, L);
+    if (L.needClosest) resolveClosest<DIM, WOST>(a, L);
     if (!(L.distA > a.ws.epsilonShellForAbsorbingBoundary)) return kReached;
     float starRadius = 0.0f, r2max = 0.0f;
     if (WOST && stepStarPrologue<DIM>(a, L, starRadius, r2max)) {
@@ -881,7 +902,7 @@ __global__ void __launch_bounds__(128, ZB_WALK_MIN_BLOCKS) walkKernel(SolveArgs 
         if (__any_sync(full, qc)) {
             if (a.hasAbsorbing) {
                 ClosestHit<DIM> hit;
-                coopClosestPoint<DIM>(a.absorbing, ws, qc, L.st.pt, kMaxFloat, hit, a.status);
+                coopClosestPoint<DIM>(a.absorbing, ws, qc, L.st.pt, closestSearchRadius2<DIM, WOST>(a, L), hit, a.status);
                 if (qc) {
                     if (!L.keepDistA) L.distA = hit.d;
                     L.proj = hit.p;
@@ -889,7 +910,7 @@ __global__ void __launch_bounds__(128, ZB_WALK_MIN_BLOCKS) walkKernel(SolveArgs 
                     L.keepDistA = false;
                 }
             } else if (qc) {
-                resolveClosest<DIM>(a, L);
+                resolveClosest<DIM, WOST>(a, L);
             }
         }
 
