@@ -123,7 +123,7 @@ int main(int argc, char **argv)
     for (int k = 0; k < 12; k++) g_zbClass[k] = 0;
 
     // run the walks; per step, collect the cost of each query
-    struct StepCost { int nodes[5], prims[5]; int stepIndex; bool onRefl; float distA; };
+    struct StepCost { int nodes[5], prims[5]; int stepIndex; bool onRefl; float distA; float ballR, distNow; };
     std::vector<StepCost> steps;
     long long nSteps = 0;
     for (long long t = 0; t < total; t++) {
@@ -135,7 +135,7 @@ int main(int argc, char **argv)
             bool onRefl = L.st.onRefl; float distA = L.distA; int idx = L.st.walkLength;
             StepResult r = walkStep<3, true>(a, L, queue);
             StepCost c{};
-            c.stepIndex = idx; c.onRefl = onRefl; c.distA = distA;
+            c.stepIndex = idx; c.onRefl = onRefl; c.distA = distA; c.ballR = L.g.R; c.distNow = L.distA;
             for (auto& rec : g_recs) { c.nodes[rec.q] += rec.nodes; c.prims[rec.q] += rec.prims; }
             g_recs.clear();
             steps.push_back(c);
@@ -163,6 +163,16 @@ int main(int argc, char **argv)
         for (auto& s : steps) { an += s.nodes[0]; ap += s.prims[0]; if (s.onRefl) { nOn++; cn += s.nodes[0]; cp += s.prims[0]; } }
         printf("steps starting on the reflecting boundary: %.1f %% of the steps, %.1f %% of the closest-point nodes, %.1f %% of its primitives\n",
                100.0*nOn/std::max<size_t>(1, steps.size()), 100.0*cn/std::max(1LL, an), 100.0*cp/std::max(1LL, ap));
+    }
+    {   // steps whose ball is set by the reflecting boundary (radius well below the absorbing distance): the distance query
+        // of such a step could be bounded by the star radius if the star query ran first
+        long long n = 0, cn = 0, cp = 0, an = 0, ap = 0;
+        for (auto& s : steps) {
+            an += s.nodes[0]; ap += s.prims[0];
+            if (!s.onRefl && s.distNow < 1e30f && s.ballR < 0.5f*s.distNow) { n++; cn += s.nodes[0]; cp += s.prims[0]; }
+        }
+        printf("steps (not on the boundary) with ball radius < half the absorbing distance: %.1f %% of the steps, %.1f %% of the closest-point nodes, %.1f %% of its primitives\n",
+               100.0*n/std::max<size_t>(1, steps.size()), 100.0*cn/std::max(1LL, an), 100.0*cp/std::max(1LL, ap));
     }
     // the worst star-radius steps
     std::sort(steps.begin(), steps.end(), [](const StepCost& x, const StepCost& y) { return x.prims[4] > y.prims[4]; });
