@@ -61,6 +61,8 @@ CASES = {
     "wost3d_neumann": dict(dim=3, kind=abi.REFLECTING_NEUMANN, family=abi.SOL_QUADRATIC, params=[1.0, -0.5, 0.25, 0.3], sigma=0.0, mu=0.0),
     "wost3d_robin_yukawa": dict(dim=3, kind=abi.REFLECTING_ROBIN, family=abi.SOL_EXP_DIR, params=[3**-0.5]*3 + [1.0], sigma=1.0, mu=1.0),
     "wost2d_robin": dict(dim=2, kind=abi.REFLECTING_ROBIN, family=abi.SOL_QUADRATIC, params=[1.0, -0.5, 0.0, 0.3], sigma=0.0, mu=0.7),
+    # screened Poisson in 2D: the Bessel-function ball Green's function (distributions.h:678-833)
+    "wost2d_neumann_yukawa": dict(dim=2, kind=abi.REFLECTING_NEUMANN, family=abi.SOL_EXP_DIR, params=[0.6, 0.8, 0.0, 1.0], sigma=1.0, mu=0.0),
 }
 
 
