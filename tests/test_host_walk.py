@@ -29,7 +29,7 @@ def host_solve(tmp_path_factory):
 
 
 def run_host(exe, d, dim, kind, absorbing, reflecting, x, n_walks, family, params, sigma, mu, rr, split, seed,
-             types=None, quantities=None, normals=None, directions=None):
+             types=None, quantities=None, normals=None, directions=None, double_sided=False):
     hdr = struct.pack("<4i16f4fQ", dim, kind, n_walks, family, *(list(params) + [0.0]*(16 - len(params))), sigma, mu, rr, split, seed)
     open(os.path.join(d, "hdr.bin"), "wb").write(hdr)
     empty = (np.zeros((0, dim), np.float32), np.zeros((0, dim), np.int32))
@@ -44,6 +44,7 @@ def run_host(exe, d, dim, kind, absorbing, reflecting, x, n_walks, family, param
             np.ascontiguousarray(arr, dt).tofile(path)
         elif os.path.exists(path):
             os.remove(path)
+    np.array([1 if double_sided else 0], np.int32).tofile(os.path.join(d, "double_sided.bin"))
     r = subprocess.run([exe, d], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0 and "status 0" in r.stdout, r.stdout
     out = np.fromfile(os.path.join(d, "out.bin"), np.float32).reshape(-1, 6)
@@ -87,6 +88,43 @@ def test_device_walk_code_on_host_matches_reference(ref, host_solve, tmp_path, n
     z = cases.z_scores(st, rst)
     assert np.mean(np.abs(z) < 3.0) >= 0.98
     assert abs(z.mean()) < 0.3 and 0.75 < z.std() < 1.3, (z.mean(), z.std())
+
+
+def test_device_walk_code_on_host_double_sided(ref, host_solve, tmp_path):
+    """WalkSettings::solveDoubleSided (walk_on_stars.h:357-376, 419-436; fcpw_geometric_queries.h:1029-1038): an open
+    reflecting plate inside a Dirichlet sphere, walks passing on both of its sides; no edge is ignored as convex, the
+    plate's rim consists of edges without an adjacent face (always silhouettes), normals flip with the side the walk is
+    on. u = x + 0.2 is harmonic with zero normal derivative on the plate z = 0.05."""
+    whole, _, _ = cases.mesh3d(3)
+    g = np.linspace(-0.4, 0.4, 13, dtype=np.float32)
+    gx, gy = np.meshgrid(g, g, indexing="ij")
+    ppos = np.stack([gx.ravel(), gy.ravel(), np.full(gx.size, 0.05, np.float32)], axis=1).astype(np.float32)
+    n = len(g)
+    quads = [(i*n + j, (i + 1)*n + j, (i + 1)*n + j + 1, i*n + j + 1) for i in range(n - 1) for j in range(n - 1)]
+    ptri = np.array([t for a, b, c, d in quads for t in ((a, b, c), (a, c, d))], np.int32)
+    plate = (ppos, ptri)
+    x = cases.query_points(112, 3, 0.55, seed=91)
+    x = x[np.abs(x[:, 2] - 0.05) > 0.02]                       # not inside the plate's epsilon shell
+    n_walks = 128
+    family, params = abi.SOL_LINEAR, [1.0, 0.0, 0.0, 0.2]
+    st = run_host(host_solve, str(tmp_path), 3, abi.REFLECTING_NEUMANN, whole, plate, x, n_walks, family, params, 0.0, 0.0, 0.0,
+                  abi.FLT_MAX, 0xBEEF, double_sided=True)
+    rs = ref.RefScene(3, **cases.scene_kwargs(3, abi.REFLECTING_NEUMANN, whole, plate, double_sided=True))
+    _, da, _, _ = rs.closest_point(abi.ABSORBING, x)
+    _, dr, _, _ = rs.closest_point(abi.REFLECTING, x)
+    pts = abi.HostSamplePoints(x, da, dr, nWalks=n_walks, estimationQuantity=abi.SOLUTION, seed=0xF00D)
+    rst = abi.HostStatistics(len(x), 3)
+    pde = abi.PdeDesc.manufactured(family, params, absorptionCoeff=0.0, robinCoeff=0.0)
+    rsteps, _ = rs.solve(abi.WALK_ON_STARS, pde, abi.WalkSettings.default(solveDoubleSided=True), pts, rst)
+    assert np.array_equal(st.nSolutionEstimates, rst.nSolutionEstimates)
+    assert abs(st.totalWalkLength.sum()/float(rsteps) - 1.0) < 0.04
+    z = cases.z_scores(st, rst)
+    assert np.mean(np.abs(z) < 3.0) >= 0.98
+    assert abs(z.mean()) < 0.3 and 0.75 < z.std() < 1.3, (z.mean(), z.std())
+    # and both agree with the exact solution
+    exact = x[:, 0] + 0.2
+    se = np.sqrt(st.solutionM2/np.maximum(st.nSolutionEstimates - 1, 1)/np.maximum(st.nSolutionEstimates, 1))
+    assert np.mean(np.abs(st.solutionMean - exact) < 4.0*se + 2e-3) >= 0.97
 
 
 def test_cooperative_traversal_on_emulated_warps(tmp_path):

@@ -54,6 +54,9 @@ int run(const std::string& dir, const Header& h)
     const char *err = nullptr;
     ReflectingOptions none, opt;
     opt.enabled = true;
+    auto dsIn = rd<int>(dir + "/double_sided.bin", true); // optional: open reflecting surfaces, walks on both sides
+    const bool doubleSided = !dsIn.empty() && dsIn[0] != 0;
+    opt.solveDoubleSided = doubleSided;
     std::vector<float> coeff(ridx.size()/DIM, h.mu);
     if (h.kind == ZB_REFLECTING_ROBIN) { opt.minCoeff = coeff.data(); opt.maxCoeff = coeff.data(); }
     if (!buildWideBvh(DIM, apos.data(), (int)apos.size()/DIM, aidx.data(), (int)aidx.size()/DIM, none, A, &err)) { printf("A: %s\n", err); return 1; }
@@ -69,6 +72,7 @@ int run(const std::string& dir, const Header& h)
     a.estimator = hasR ? ZB_WALK_ON_STARS : ZB_WALK_ON_SPHERES;
     for (int k = 0; k < 3; k++) { a.domainMin[k] = -3; a.domainMax[k] = 3; }
     zb_walk_settings ws{1e-3f, 1e-3f, 1e-3f, h.rr, h.split, 1024, 0, 1024, 0, 1, 1, 0, 0, 0, 0, 0};
+    ws.solveDoubleSided = doubleSided ? 1 : 0;
     a.ws = ws;
     zb_pde_desc pde{};
     pde.absorptionCoeff = h.sigma;
