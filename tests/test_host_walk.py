@@ -63,6 +63,9 @@ CASES = {
     "wost3d_robin_yukawa": dict(dim=3, kind=abi.REFLECTING_ROBIN, family=abi.SOL_EXP_DIR, params=[3**-0.5]*3 + [1.0], sigma=1.0, mu=1.0),
     "wost2d_robin": dict(dim=2, kind=abi.REFLECTING_ROBIN, family=abi.SOL_QUADRATIC, params=[1.0, -0.5, 0.0, 0.3], sigma=0.0, mu=0.7),
     # screened Poisson in 2D: the Bessel-function ball Green's function (distributions.h:678-833)
+    # Walk on Spheres (walk_on_spheres.h:229-288): Dirichlet boundary only; 2D Laplace with C1's cubic, 3D Poisson
+    "wos2d": dict(dim=2, kind=abi.REFLECTING_NONE, family=abi.SOL_CUBIC_2D, params=[0.0]*4, sigma=0.0, mu=0.0),
+    "wos3d_poisson": dict(dim=3, kind=abi.REFLECTING_NONE, family=abi.SOL_QUADRATIC, params=[1.0, -0.5, 0.25, 0.3], sigma=0.0, mu=0.0),
     # the weight window of the demo configs (engine/wost.json: Russian roulette below 0.99, splitting above 1.5;
     # walk_on_stars.h:310-343) on a problem whose throughput falls (screening) and rises (reflectance <= 1 only): roulette
     "wost3d_robin_yukawa_window": dict(dim=3, kind=abi.REFLECTING_ROBIN, family=abi.SOL_EXP_DIR, params=[3**-0.5]*3 + [1.0], sigma=1.0,
@@ -76,18 +79,22 @@ def test_device_walk_code_on_host_matches_reference(ref, host_solve, tmp_path, n
     c = CASES[name]
     dim = c["dim"]
     whole, absorbing, reflecting = cases.mesh3d(3) if dim == 3 else cases.mesh2d(512)
+    wos = c["kind"] == abi.REFLECTING_NONE
+    if wos:
+        absorbing, reflecting = whole, None
     x = cases.query_points(160, dim, 0.6 if dim == 3 else 0.7, seed=77)
     n_walks = 192
     rr, split = c.get("rr", 0.0), c.get("split", abi.FLT_MAX)
     st = run_host(host_solve, str(tmp_path), dim, c["kind"], absorbing, reflecting, x, n_walks, c["family"], c["params"],
                   c["sigma"], c["mu"], rr, split, 0xBEEF)
-    rs = ref.RefScene(dim, **cases.scene_kwargs(dim, c["kind"], absorbing, reflecting, mu=c["mu"]))
+    rs = ref.RefScene(dim, absorbing=absorbing) if wos else ref.RefScene(dim, **cases.scene_kwargs(dim, c["kind"], absorbing, reflecting, mu=c["mu"]))
     _, da, _, _ = rs.closest_point(abi.ABSORBING, x)
-    _, dr, _, _ = rs.closest_point(abi.REFLECTING, x)
+    dr = None if wos else rs.closest_point(abi.REFLECTING, x)[1]
     pts = abi.HostSamplePoints(x, da, dr, nWalks=n_walks, estimationQuantity=abi.SOLUTION, seed=0xF00D)
     rst = abi.HostStatistics(len(x), dim)
     pde = abi.PdeDesc.manufactured(c["family"], c["params"], absorptionCoeff=c["sigma"], robinCoeff=c["mu"])
-    rsteps, _ = rs.solve(abi.WALK_ON_STARS, pde, abi.WalkSettings.default(russianRouletteThreshold=rr, splittingThreshold=split), pts, rst)
+    rsteps, _ = rs.solve(abi.WALK_ON_SPHERES if wos else abi.WALK_ON_STARS, pde,
+                         abi.WalkSettings.default(russianRouletteThreshold=rr, splittingThreshold=split), pts, rst)
     assert np.array_equal(st.nSolutionEstimates, rst.nSolutionEstimates)
     assert abs(st.totalWalkLength.sum()/float(rsteps) - 1.0) < 0.04      # same walk-length distribution
     z = cases.z_scores(st, rst)
