@@ -29,7 +29,8 @@ def host_solve(tmp_path_factory):
 
 
 def run_host(exe, d, dim, kind, absorbing, reflecting, x, n_walks, family, params, sigma, mu, rr, split, seed,
-             types=None, quantities=None, normals=None, directions=None, double_sided=False):
+             types=None, quantities=None, normals=None, directions=None, double_sided=False, kelvin_origin=None,
+             robin_bounds=None):
     hdr = struct.pack("<4i16f4fQ", dim, kind, n_walks, family, *(list(params) + [0.0]*(16 - len(params))), sigma, mu, rr, split, seed)
     open(os.path.join(d, "hdr.bin"), "wb").write(hdr)
     empty = (np.zeros((0, dim), np.float32), np.zeros((0, dim), np.int32))
@@ -45,6 +46,13 @@ def run_host(exe, d, dim, kind, absorbing, reflecting, x, n_walks, family, param
         elif os.path.exists(path):
             os.remove(path)
     np.array([1 if double_sided else 0], np.int32).tofile(os.path.join(d, "double_sided.bin"))
+    np.array([0.0]*4 if kelvin_origin is None else [1.0] + [float(v) for v in kelvin_origin], np.float32).tofile(os.path.join(d, "kelvin.bin"))
+    for name, arr in (("rmin", None if robin_bounds is None else robin_bounds[0]), ("rmax", None if robin_bounds is None else robin_bounds[1])):
+        path = os.path.join(d, name + ".bin")
+        if arr is not None:
+            np.ascontiguousarray(arr, np.float32).tofile(path)
+        elif os.path.exists(path):
+            os.remove(path)
     r = subprocess.run([exe, d], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0 and "status 0" in r.stdout, r.stdout
     out = np.fromfile(os.path.join(d, "out.bin"), np.float32).reshape(-1, 6)
@@ -137,6 +145,36 @@ def test_device_walk_code_on_host_double_sided(ref, host_solve, tmp_path):
     exact = x[:, 0] + 0.2
     se = np.sqrt(st.solutionM2/np.maximum(st.nSolutionEstimates - 1, 1)/np.maximum(st.nSolutionEstimates, 1))
     assert np.mean(np.abs(st.solutionMean - exact) < 4.0*se + 2e-3) >= 0.97
+
+
+@pytest.mark.parametrize("mixed", [False, True])
+def test_device_walk_code_on_host_kelvin_exterior(ref, host_solve, tmp_path, mixed):
+    """BASELINE configs[4]: exterior Laplace problem on the Kelvin-inverted domain, the PDE wrapped on
+    the device like KelvinTransform::transformPde (kelvin_transform.h:282-348; pde.cuh). Dirichlet everywhere (Walk on
+    Spheres), and Neumann data on z > 0 that the inversion turns into Robin conditions with the per-triangle coefficient
+    bounds of computeRobinCoefficients (Walk on Stars, coefficients of either sign)."""
+    from zombie_b200 import kelvin, workloads
+    w = workloads.config5(subdivisions=3, n_points=144, n_walks=128, mixed=mixed)
+    kw = w.scene_kwargs()
+    bounds = (kw["min_robin"], kw["max_robin"]) if mixed else None
+    st = run_host(host_solve, str(tmp_path), 3, abi.REFLECTING_ROBIN if mixed else abi.REFLECTING_NONE, kw["absorbing"],
+                  kw.get("reflecting"), w.points, w.n_walks, abi.SOL_INV_DIST, [float(v) for v in w.pde.params[:4]], 0.0, 0.0, 0.0,
+                  abi.FLT_MAX, 0xBEEF, kelvin_origin=w.kelvin_origin, robin_bounds=bounds)
+    rs = ref.RefScene(3, **kw)
+    _, da, _, _ = rs.closest_point(abi.ABSORBING, w.points)
+    dr = rs.closest_point(abi.REFLECTING, w.points)[1] if mixed else None
+    pts = abi.HostSamplePoints(w.points, da, dr, nWalks=w.n_walks, estimationQuantity=abi.SOLUTION, seed=0xF00D)
+    rst = abi.HostStatistics(pts.n, 3)
+    rsteps, _ = rs.solve(w.estimator, w.pde, w.settings, pts, rst)
+    assert np.array_equal(st.nSolutionEstimates, rst.nSolutionEstimates)
+    assert abs(st.totalWalkLength.sum()/float(rsteps) - 1.0) < 0.05
+    z = cases.z_scores(st, rst)
+    assert np.mean(np.abs(z) < 3.0) >= 0.97
+    assert abs(z.mean()) < 0.35 and 0.7 < z.std() < 1.35, (z.mean(), z.std())
+    if not mixed:
+        u = kelvin.transform_solution_estimate(st.solutionMean, w.points)
+        se = np.linalg.norm(w.points, axis=1)*np.sqrt(st.solutionM2/np.maximum(st.nSolutionEstimates - 1, 1)/np.maximum(st.nSolutionEstimates, 1))
+        assert np.mean(np.abs(u - w.exterior_exact(w.exterior_points)) < 4.0*se + 2e-3) > 0.95
 
 
 def test_cooperative_traversal_on_emulated_warps(tmp_path):

@@ -59,6 +59,11 @@ int run(const std::string& dir, const Header& h)
     opt.solveDoubleSided = doubleSided;
     std::vector<float> coeff(ridx.size()/DIM, h.mu);
     if (h.kind == ZB_REFLECTING_ROBIN) { opt.minCoeff = coeff.data(); opt.maxCoeff = coeff.data(); }
+    // optional per-primitive coefficient bounds (Kelvin-transformed Neumann data: kelvin_transform.h:350-388)
+    auto rminIn = rd<float>(dir + "/rmin.bin", true), rmaxIn = rd<float>(dir + "/rmax.bin", true);
+    if (h.kind == ZB_REFLECTING_ROBIN && rminIn.size() == ridx.size()/DIM && rmaxIn.size() == rminIn.size()) {
+        opt.minCoeff = rminIn.data(); opt.maxCoeff = rmaxIn.data();
+    }
     if (!buildWideBvh(DIM, apos.data(), (int)apos.size()/DIM, aidx.data(), (int)aidx.size()/DIM, none, A, &err)) { printf("A: %s\n", err); return 1; }
     bool hasR = !ridx.empty();
     if (hasR && !buildWideBvh(DIM, rpos.data(), (int)rpos.size()/DIM, ridx.data(), (int)ridx.size()/DIM, opt, R, &err)) { printf("R: %s\n", err); return 1; }
@@ -82,6 +87,16 @@ int run(const std::string& dir, const Header& h)
     pde.family = h.family;
     for (int k = 0; k < 16; k++) pde.params[k] = h.params[k];
     pde.robinCoeff = h.mu;
+    // optional Kelvin wrapper: (flag, origin[3]); the flags of the wrapped PDE as zb_solve_dev sets them (capi.cu;
+    // kelvin_transform.h:340-347)
+    auto kelvinIn = rd<float>(dir + "/kelvin.bin", true);
+    if (kelvinIn.size() == 4 && kelvinIn[0] != 0.0f) {
+        pde.kelvin = 1;
+        for (int k = 0; k < 3; k++) pde.kelvinOrigin[k] = kelvinIn[1 + k];
+        pde.isSourceConstant = 0;
+        pde.absorptionCoeff = 0.0f;
+        if (DIM == 3) { pde.areRobinConditionsPureNeumann = 0; pde.areRobinCoeffsNonnegative = 0; }
+    }
     a.pde = pde;
     a.status = &status;
 
