@@ -20,6 +20,12 @@
 // atomicMin on (squared radius, primitive), which makes them independent of the traversal order (ties on
 // distance resolve to the smaller leaf-order index).
 //
+// Primitive rounds come in two stages (3D): a FILTER round runs a cheap conservative test on 32 primitives — can this
+// triangle still lower the owner's radius? (plane distance and bounding sphere for the closest point; plane-distance
+// bound of the reflectance radius and "no edge to test" for the star radius) — and compacts the survivors into a third
+// list, kept at the end of the primitive queue; a FULL round runs the complete test on 32 survivors. In a warp an early
+// exit is only worth what the slowest lane saves, so the rejection has to happen between rounds, not inside one.
+//
 // Node tests only ever PRUNE (they bound what a subtree can contribute), so they are free to use fast
 // algebraic forms — the cone test below replaces the reference's acos/asin/atan2 (fcpw/core/bounding_volumes.h:
 // 275-321) by products of sines and cosines with explicit slack — as long as they stay conservative; the values
