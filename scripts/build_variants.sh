@@ -6,6 +6,8 @@ cd "$(dirname "$0")/.."
 python -m zombie_b200.build --variant compact                                           # the default build
 python -m zombie_b200.build --variant unrolled_inlined -DZB_UNROLL_CHILD_LOOPS -DZB_INLINE_PRIM_TESTS   # old code shape
 python -m zombie_b200.build --variant unrolled -DZB_UNROLL_CHILD_LOOPS
+python -m zombie_b200.build --variant unroll2 -DZB_CHILD_UNROLL=2
+python -m zombie_b200.build --variant unroll4 -DZB_CHILD_UNROLL=4
 python -m zombie_b200.build --variant inlined -DZB_INLINE_PRIM_TESTS
 python -m zombie_b200.build --variant no_plane_bound -DZB_ROBIN_PLANE_BOUND=0 -DZB_STAR_TWO_STAGE=0
 python -m zombie_b200.build --variant one_stage -DZB_STAR_TWO_STAGE=0

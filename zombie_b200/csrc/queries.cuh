@@ -89,11 +89,17 @@ ZB_DEV uint32_t byte8(uint32_t w0, uint32_t w1, int c)
 #endif
 }
 
-// child loops: "unroll 1" keeps one copy of the body; build with -DZB_UNROLL_CHILD_LOOPS to compare against full unrolling
+// child loops: "unroll 1" keeps one copy of the body. A/B builds: -DZB_CHILD_UNROLL=2 or 4 (some instruction-level
+// parallelism between children at 2x / 4x the code), -DZB_UNROLL_CHILD_LOOPS (full unrolling, the original shape)
 #if defined(ZB_UNROLL_CHILD_LOOPS)
 #define ZB_CHILD_LOOP _Pragma("unroll")
 #else
-#define ZB_CHILD_LOOP _Pragma("unroll 1")
+#ifndef ZB_CHILD_UNROLL
+#define ZB_CHILD_UNROLL 1
+#endif
+#define ZB_PRAGMA_(x) _Pragma(#x)
+#define ZB_PRAGMA(x) ZB_PRAGMA_(x)
+#define ZB_CHILD_LOOP ZB_PRAGMA(unroll ZB_CHILD_UNROLL)
 #endif
 
 // word holding the quantised coordinate bytes of children 0..3 / 4..7: axis 0..2, side 0 = lo, 1 = hi
