@@ -132,7 +132,7 @@ CASES = [
     dict(dim=2, sigma=0.0, reg=0.0, robin_cutoff=1.0),
     dict(dim=2, sigma=0.0, reg=0.05, robin_cutoff=1.0),
 ]
-CPU_ONLY_CASES = [dict(dim=2, sigma=3.0, reg=0.0, robin_cutoff=1.0)]   # its GPU run lives in tests/test_z_rws.py
+CPU_ONLY_CASES = [dict(dim=2, sigma=3.0, reg=0.0, robin_cutoff=1.0)]   # its GPU run lives in tests/test_rws.py
 
 
 @pytest.mark.parametrize("c", CASES + CPU_ONLY_CASES, ids=lambda c: "dim%d_sigma%g_reg%g" % (c["dim"], c["sigma"], c["reg"]))

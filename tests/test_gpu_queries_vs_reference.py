@@ -1,7 +1,6 @@
 """GPU parity of every geometric query against the COMPILED reference on large seeded inputs (200,000 3D / 50,000 2D queries
-per configuration): closest point, closest ray hit, occlusion, star radius. Kept in its own late-sorting file: pytest -x
-stops at the first failure, and this is the test whose star-radius part depends on how the rare reference-BVH-vs-Baseline
-disagreements fall at these sizes (see the comments below); the golden-fixture query tests are in test_gpu_queries.py."""
+per configuration): closest point, closest ray hit, occlusion, star radius. The golden-fixture query tests are in
+test_gpu_queries.py."""
 import numpy as np
 import pytest
 
@@ -33,17 +32,16 @@ def test_queries_match_compiled_reference(ctx, ref, dim, kind):
     tol = 1e-3*max(1.0, float(rr.max()))
     bad = np.abs(rr - gr) > tol
     if bad.any():
-        # FCPW's SNCH traversal occasionally prunes a node that holds an edge its own primitive test classifies as a
-        # silhouette through the `precision` rules (silhouette_edges.inl:88-105), so the reference's BVH deviates from
-        # the reference's brute-force Baseline on a few queries in 10^5 (by more than FCPW's own 1e-3 tolerance). The
-        # device traversal treats nodes within `precision` of the query as candidates and must agree with that Baseline.
-        assert bad.mean() <= 1e-4
+        # The ONLY accepted cause: FCPW's SNCH traversal occasionally prunes a node that holds an edge its own primitive
+        # test classifies as a silhouette through the `precision` rules (silhouette_edges.inl:88-105), so the reference's
+        # BVH deviates from the reference's brute-force Baseline on a few queries in 10^5 (by more than FCPW's own 1e-3
+        # tolerance). The device traversal treats nodes within `precision` of the query as candidates and must agree
+        # with that Baseline on every such row (no rate cap: each row is checked). The Robin radius bound itself is
+        # evaluated in the reference's operation order without FMA contraction (queries.cuh: robinRadiusBound), so
+        # queries nearly coplanar with a primitive, where h^2 mu/(c(h mu - c^2)) cancels, agree as well.
         rb = ref.RefScene(dim, use_baseline=True, **kw)
         base = rb.star_radius(x[bad], minr[bad], da[bad])
-        # ... or it is the Robin radius bound of a triangle the query is almost coplanar with: h -> 0 makes
-        # h^2 mu/(c(h mu - c^2)) cancel, and two float evaluations of it agree to about a percent only
-        ok = (np.abs(base - gr[bad]) <= 1e-5*max(1.0, float(rr.max()))) | (np.abs(rr[bad] - gr[bad]) <= 2e-2*rr[bad])
-        assert ok.all(), (rr[bad], gr[bad], base)
+        assert (np.abs(base - gr[bad]) <= 1e-5*max(1.0, float(rr.max()))).all(), (x[bad], rr[bad], gr[bad], base)
         rb.close()
     assert np.mean(rel_err(rr, gr)[~bad] <= 1e-4) > 0.99   # the Robin radius bound h^2 mu/(c(h mu - c^2)) amplifies float rounding
     assert (rr < 0.999*da).mean() > 0.01   # the query is exercised: some radii are limited by silhouettes / reflectance

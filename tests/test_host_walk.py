@@ -260,14 +260,10 @@ def check_star_radius_against_reference(ref, host_query, tmp_path, dim, kind, mu
     for col, name in ((1, "trigonometric node test"), (2, "algebraic node test + fast primitive test")):
         g = out[:, col]
         bad = np.abs(rr - g) > 1e-3
-        assert bad.mean() <= 2e-4, name
-        if bad.any():
+        if bad.any():   # every such row must be one where the reference's BVH deviates from its own Baseline
             rb = ref.RefScene(dim, use_baseline=True, **kw)
             base = rb.star_radius(x[bad], np.full(int(bad.sum()), 1e-3, np.float32), da[bad])
-            # ... or it is the Robin radius bound of a triangle the query is almost coplanar with: h -> 0 makes
-            # h^2 mu/(c(h mu - c^2)) cancel, and two float evaluations of it agree to about a percent only
-            ok = (np.abs(base - g[bad]) <= 1e-5) | (np.abs(rr[bad] - g[bad]) <= 2e-2*rr[bad])
-            assert ok.all(), (name, rr[bad], g[bad], base)
+            assert (np.abs(base - g[bad]) <= 1e-5).all(), (name, rr[bad], g[bad], base)
         assert np.mean(np.abs(rr - g)[~bad] <= 1e-5*np.maximum(rr[~bad], 1e-3) + 1e-7) > 0.99, name
     assert (rr < 0.999*da).mean() > min_shrunk
 

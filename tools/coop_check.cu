@@ -17,7 +17,7 @@ using namespace zb;
 namespace zb { long long g_coopCount[10] = {0}; }
 #if defined(ZB_HOST_STATS)
 static long long g_seq[5][2] = {{0}};
-namespace zb { long long g_zbClass[12] = {0}; void zbHostRecord(int q, int nodes, int prims) { __atomic_fetch_add(&g_seq[q][0], (long long)nodes, __ATOMIC_RELAXED); __atomic_fetch_add(&g_seq[q][1], (long long)prims, __ATOMIC_RELAXED); } }
+namespace zb { long long g_zbClass[24] = {0}; void zbHostRecord(int q, int nodes, int prims) { __atomic_fetch_add(&g_seq[q][0], (long long)nodes, __ATOMIC_RELAXED); __atomic_fetch_add(&g_seq[q][1], (long long)prims, __ATOMIC_RELAXED); } }
 #endif
 
 static BvhView viewOf(const HostBvh& h, int sign)

@@ -17,7 +17,7 @@ using namespace zb;
 
 struct Rec { int q, nodes, prims; };
 static std::vector<Rec> g_recs;
-namespace zb { long long g_zbClass[12] = {0}; }
+namespace zb { long long g_zbClass[24] = {0}; }
 namespace zb { void zbHostRecord(int query, int nodes, int prims) { g_recs.push_back({query, nodes, prims}); } }
 
 static BvhView viewOf(const HostBvh& h, int sign)
@@ -120,7 +120,7 @@ int main(int argc, char **argv)
     a.recLength = recLen.data(); a.recFlags = recFlags.data(); a.anyGradient = 1;
     for (int i = 0; i < nPts; i++) preparePoint<3>(a, i);
     g_recs.clear();
-    for (int k = 0; k < 12; k++) g_zbClass[k] = 0;
+    for (int k = 0; k < 24; k++) g_zbClass[k] = 0;
 
     // run the walks; per step, collect the cost of each query
     struct StepCost { int nodes[5], prims[5]; int stepIndex; bool onRefl; float distA; float ballR, distNow; };
@@ -148,6 +148,7 @@ int main(int argc, char **argv)
            g_zbClass[4], g_zbClass[7], g_zbClass[5], g_zbClass[6]);
     printf("star edges (fast test): skipped by the sign shortcut %lld, tested in full %lld\n", g_zbClass[8], g_zbClass[9]);
     printf("star children: %lld passed the box test, %lld of them went on to the reflectance bounds\n", g_zbClass[10], g_zbClass[11]);
+    printf("star prims that lowered r2: %lld (robin-only items: %lld); extra rejected by the range bound %lld\n", g_zbClass[12], g_zbClass[13], g_zbClass[14]);
     const char *names[5] = {"closest", "ray", "occlusion", "sample", "star"};
     for (int q = 0; q < 5; q++) {
         std::vector<int> n, p;

@@ -13,7 +13,7 @@
 #include "../zombie_b200/csrc/wide_bvh.h"
 
 using namespace zb;
-namespace zb { long long g_zbClass[12] = {0}; void zbHostRecord(int, int, int) {} }
+namespace zb { long long g_zbClass[24] = {0}; void zbHostRecord(int, int, int) {} }
 
 template <typename T> static std::vector<T> rd(const std::string& p)
 {

@@ -1,9 +1,11 @@
 // C ABI of libzombie_b200.so (include/zombie_b200.h): contexts, scenes (boundary meshes -> wide BVHs on
 // the device), batched geometric queries and the walk-on-spheres / walk-on-stars solve.
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -11,6 +13,7 @@
 #include "../../include/zombie_b200.h"
 #include "capi_common.h"
 #include "walk.cuh"
+#include "wave.cuh"
 #include "rws.cuh"
 #include "wide_bvh.h"
 
@@ -292,6 +295,118 @@ void fillSceneArgs(const zb_scene *scene, SolveArgs& a)
     a.status = scene->ctx->status.as<int>();
 }
 
+
+// ---- wavefront scheduler (wave.cuh): the host side of one solve's walks ----------------------------------------
+int envInt(const char *name, int fallback)
+{
+    const char *v = std::getenv(name);
+    return v && *v ? std::atoi(v) : fallback;
+}
+
+constexpr int kLiveRing = 8;       // live-walk counters in flight
+constexpr int kRoundsPerGroup = 4; // rounds enqueued between two read-backs of the live count
+
+template <int DIM, bool WOST>
+int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
+{
+    zb_context *ctx = scene->ctx;
+    cudaStream_t stream = ctx->stream;
+    // Slots: enough walks in flight to fill the machine several times over (the sort needs a population to find
+    // neighbours in), never more than there are tasks. ZB_WAVE_SLOTS overrides (measurements).
+    const int maxSlots = std::max(128, envInt("ZB_WAVE_SLOTS", 262144));
+    const int nSlots = (int)std::min<long long>(maxSlots, (totalTasks + 127)/128*128);
+    const bool sortSlots = envInt("ZB_WAVE_SORT", 1) != 0;
+    const bool needQueue = a.ws.splittingThreshold < kMaxFloat;
+
+    Carver c0(nullptr);
+    auto carve = [&](Carver& c, WaveSlots& w, uint32_t *&orderA, uint32_t *&orderB, uint32_t *&keysOut, unsigned int *&live) {
+        w.ptDist = c.take<float4>(nSlots); w.projStar = c.take<float4>(nSlots); w.normalPrev = c.take<float4>(nSlots);
+        w.dirThr = c.take<float4>(nSlots); w.acc = c.take<float4>(nSlots); w.rng = c.take<ulonglong2>(nSlots);
+        w.meta = c.take<int4>(nSlots); w.meta2 = c.take<int4>(nSlots);
+        w.queue = needQueue ? (void *)c.take<WalkState<DIM>>((size_t)nSlots*kSplitStack) : nullptr;
+        w.keys = c.take<uint32_t>(nSlots);
+        keysOut = c.take<uint32_t>(nSlots);
+        orderA = c.take<uint32_t>(nSlots);
+        orderB = c.take<uint32_t>(nSlots);
+        live = c.take<unsigned int>(kLiveRing);
+    };
+    WaveSlots w;
+    std::memset(&w, 0, sizeof(w));
+    uint32_t *orderA = nullptr, *orderB = nullptr, *keysOut = nullptr;
+    unsigned int *live = nullptr;
+    carve(c0, w, orderA, orderB, keysOut, live);
+    ZB_CUDA(ctx->wave.reserve(c0.offset + 256));
+    Carver c1(ctx->wave.ptr);
+    carve(c1, w, orderA, orderB, keysOut, live);
+    w.nSlots = nSlots;
+    // Morton frame: the union of the boundary boxes (walks live inside the domain; escapees clamp)
+    float lo[3] = {kMaxFloat, kMaxFloat, kMaxFloat}, hi[3] = {-kMaxFloat, -kMaxFloat, -kMaxFloat};
+    for (int b = 0; b < 2; b++) {
+        if (!scene->boundary[b].present) continue;
+        for (int k = 0; k < 3; k++) {
+            lo[k] = std::min(lo[k], scene->boundary[b].host.boxMin[k]);
+            hi[k] = std::max(hi[k], scene->boundary[b].host.boxMax[k]);
+        }
+    }
+    for (int k = 0; k < 3; k++) {
+        if (!(hi[k] > lo[k])) { lo[k] = 0.0f; hi[k] = 1.0f; }
+        w.sortMin[k] = lo[k];
+        w.sortScale[k] = (DIM == 3 ? 1024.0f : 32768.0f)/(hi[k] - lo[k]);
+    }
+
+    size_t sortBytes = 0;
+    if (sortSlots) {
+        ZB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sortBytes, w.keys, keysOut, orderA, orderB, nSlots, 0, 32, stream));
+        ZB_CUDA(ctx->waveSort.reserve(sortBytes + 256));
+    }
+    if (!ctx->hostLive) ZB_CUDA(cudaMallocHost(&ctx->hostLive, 2*sizeof(unsigned int)));
+    for (int k = 0; k < 2; k++) if (!ctx->evRound[k]) ZB_CUDA(cudaEventCreateWithFlags(&ctx->evRound[k], cudaEventDisableTiming));
+
+    ZB_CUDA(cudaFuncSetAttribute(waveClosestKernel<DIM, WOST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
+    if (WOST) ZB_CUDA(cudaFuncSetAttribute(waveStarKernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
+
+    waveResetKernel<<<blocksFor(nSlots, 256), 256, 0, stream>>>(w, orderA);
+    ZB_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+
+    int nBound = nSlots, round = 0;
+    const bool star = WOST && a.hasReflecting;
+    for (int group = 0;; group++) {
+        for (int g = 0; g < kRoundsPerGroup; g++, round++) {
+            w.order = orderA;
+            w.live = live + round%kLiveRing;
+            ZB_CUDA(cudaMemsetAsync(w.live, 0, sizeof(unsigned int), stream));
+            const int blocks = blocksFor(nBound, 128);
+            if (round > 0) { // round 0 only hands out the first tasks
+                waveClosestKernel<DIM, WOST><<<blocks, 128, kCoopSmem, stream>>>(a, w, nBound);
+                if (star) waveStarKernel<DIM><<<blocks, 128, kCoopSmem, stream>>>(a, w, nBound);
+                ctx->launches += star ? 2 : 1;
+            }
+            waveStepKernel<DIM, WOST><<<blocks, 128, 0, stream>>>(a, w, nBound);
+            ZB_CUDA(cudaGetLastError());
+            ctx->launches += 1;
+            if (sortSlots) {
+                ZB_CUDA(cub::DeviceRadixSort::SortPairs(ctx->waveSort.ptr, sortBytes, w.keys, keysOut, orderA, orderB, nBound, 0, 32, stream));
+                std::swap(orderA, orderB);
+                ctx->launches += 1; // one library call (cub's own kernels are not counted)
+            }
+        }
+        ZB_CUDA(cudaMemcpyAsync(ctx->hostLive + (group & 1), live + (round - 1)%kLiveRing, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+        ZB_CUDA(cudaEventRecord(ctx->evRound[group & 1], stream));
+        if (group >= 1) {
+            // one group of lag: the device never waits for the host
+            ZB_CUDA(cudaEventSynchronize(ctx->evRound[(group - 1) & 1]));
+            unsigned int alive = ctx->hostLive[(group - 1) & 1];
+            if (alive == 0u) break;
+            // the live walks sit at the front of the order (empty slots sort to the end) and, once the task queue has
+            // run dry, their number only falls: later rounds need not look past it
+            if (sortSlots) nBound = std::min(nBound, (int)((alive + 127u)/128u*128u));
+        }
+    }
+    ctx->lastRounds = round;
+    return ZB_OK;
+}
+
 template <int DIM>
 int solveRange(zb_scene *scene, SolveArgs& a, int n, bool anyGradient)
 {
@@ -366,6 +481,10 @@ int solveRange(zb_scene *scene, SolveArgs& a, int n, bool anyGradient)
     ctx->lastGrid = 0;
     ctx->launches += 5; // count, 2 scans (init + scan kernels counted once each), prepare, reduce
     if (totalTasks > 0) {
+        if (envInt("ZB_SCHEDULER_PERSISTENT", 0) == 0) {
+            int rc = a.estimator == ZB_WALK_ON_STARS ? runWavefront<DIM, true>(scene, a, totalTasks) : runWavefront<DIM, false>(scene, a, totalTasks);
+            if (rc != ZB_OK) return rc;
+        } else {
         // persistent grid: a whole number of waves of 128-thread CTAs over all SMs
         int perSm = 0;
         if (a.estimator == ZB_WALK_ON_STARS) {
@@ -384,6 +503,7 @@ int solveRange(zb_scene *scene, SolveArgs& a, int n, bool anyGradient)
         ZB_CUDA(cudaGetLastError());
         ctx->lastGrid = grid;
         ctx->launches += 1;
+        }
     }
     ZB_CUDA(cudaEventRecord(ctx->ev[2], stream));
 
@@ -442,6 +562,8 @@ void zb_context_destroy(zb_context *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->ownsStream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->hostStatus) cudaFreeHost(ctx->hostStatus);
+    if (ctx->hostLive) cudaFreeHost(ctx->hostLive);
+    for (int k = 0; k < 2; k++) if (ctx->evRound[k]) cudaEventDestroy(ctx->evRound[k]);
     for (int k = 0; k < 4; k++) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     for (int k = 0; k < 2; k++) if (ctx->evSplat[k]) cudaEventDestroy(ctx->evSplat[k]);
     delete ctx;

@@ -56,6 +56,10 @@ struct zb_context {
     bool ownsStream = false;
     zb::DeviceBuffer status, counters, perPoint, strat, records, scanTemp, io;
     zb::DeviceBuffer bvcSamples, bvcIo, rwsRecords;
+    zb::DeviceBuffer wave, waveSort;       // walk state of the wavefront scheduler, radix-sort scratch
+    unsigned int *hostLive = nullptr;      // pinned: live-walk counts read back every few rounds
+    cudaEvent_t evRound[2] = {nullptr, nullptr};
+    int lastRounds = 0;
     int *hostStatus = nullptr; // pinned
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; // solve start | walk start | walk end | solve end
     cudaEvent_t evSplat[2] = {nullptr, nullptr};

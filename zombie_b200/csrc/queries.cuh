@@ -32,7 +32,7 @@ struct BvhView {
 #define ZB_COUNT_FLUSH(q)
 #else
 void zbHostRecord(int query, int nodes, int prims);
-extern long long g_zbClass[12]; // star query: [0] items with silhouette tests, [1] without, [2] prims early-out by distance, [3] prims fully tested
+extern long long g_zbClass[24]; // star query: [0] items with silhouette tests, [1] without, [2] prims early-out by distance, [3] prims fully tested
 #define ZB_CLASS(i) g_zbClass[i]++;
 #define ZB_COUNT_DECL int zbNodes = 0, zbPrims = 0;
 #define ZB_COUNT_NODE zbNodes++;
@@ -777,7 +777,8 @@ ZB_DEV bool candidateSilhouette(const Prim<2>& s, int j, const Vec<2>& x, const 
 // farthest vertex (zombie/core/geometry_helpers.h:51-63, 163-180)
 ZB_DEV float farthestVertex(const Prim<3>& t, const Vec<3>& x, Vec<3>& far)
 {
-    float da = norm2(x - t.a), db = norm2(x - t.b), dc = norm2(x - t.c);
+    Vec<3> va = x - t.a, vb = x - t.b, vc = x - t.c;
+    float da = xdot(va, va), db = xdot(vb, vb), dc = xdot(vc, vc);
     if (da >= db && da >= dc) { far = t.a; return sqrtf(da); }
     if (db >= da && db >= dc) { far = t.b; return sqrtf(db); }
     far = t.c;
@@ -786,7 +787,8 @@ ZB_DEV float farthestVertex(const Prim<3>& t, const Vec<3>& x, Vec<3>& far)
 
 ZB_DEV float farthestVertex(const Prim<2>& s, const Vec<2>& x, Vec<2>& far)
 {
-    float da = norm2(x - s.a), db = norm2(x - s.b);
+    Vec<2> va = x - s.a, vb = x - s.b;
+    float da = xdot(va, va), db = xdot(vb, vb);
     if (da > db) { far = s.a; return sqrtf(da); }
     far = s.b;
     return sqrtf(db);
@@ -801,13 +803,16 @@ template <int DIM>
 ZB_DEV float robinRadiusBound(float h, float mu, float cosLower, float cosUpper)
 {
     if (DIM == 3) {
-        float maxCos = sqrtf(h*mu);
+        // written without FMA contraction: h mu - c^2 cancels when the query is nearly coplanar with the triangle
+        float hmu = zb_fmul(h, mu);
+        float maxCos = sqrtf(hmu);
         if (!(maxCos >= cosLower)) return kMaxFloat;
         float c = clampLikeStd(maxCos/1.7320508075688772935f, cosLower, cosUpper);
-        return h*h*mu/(c*(h*mu - c*c));
+        return zb_fmul(zb_fmul(h, h), mu)/zb_fmul(c, zb_fsub(hmu, zb_fmul(c, c)));
     }
-    float c = clampLikeStd(sqrtf(h*mu)/1.4142135623730950488f, cosLower, cosUpper);
-    return (h/c)*expf(c*c/(h*mu));
+    float hmu = zb_fmul(h, mu);
+    float c = clampLikeStd(sqrtf(hmu)/1.4142135623730950488f, cosLower, cosUpper);
+    return zb_fmul(h/c, expf(zb_fmul(c, c)/hmu));
 }
 
 // Shrinks r2 by what one reflecting primitive allows: the distance to each of its silhouette
@@ -859,10 +864,11 @@ ZB_DEV void primStarRadius2(const BvhView& bvh, uint32_t primIdx, const Vec<DIM>
         } else if (r2 > closestDist2) {
             Vec<DIM> far;
             float farDist = farthestVertex(prim, x, far);
-            float h = fabsf(dot(n0, prim.a - x)/dot(n0, n0)); // findClosestPointPlane (geometry.h:62-70)
+            // reference-ordered, uncontracted: h and the two cosines cancel when x is nearly coplanar with the primitive
+            float h = fabsf(xdot(n0, prim.a - x)/xdot(n0, n0)); // findClosestPointPlane (geometry.h:62-70)
             if (h > 0.0f) {
-                float cosUpper = fabsf(dot((x - closestPt)/closestDist, n0));
-                float cosLower = fabsf(dot((x - far)/farDist, n0));
+                float cosUpper = fabsf(xdot((x - closestPt)/closestDist, n0));
+                float cosLower = fabsf(xdot((x - far)/farDist, n0));
                 float radius = robinRadiusBound<DIM>(h, maxCoeff, cosLower, cosUpper);
                 if (radius < kMaxFloat) r2 = fminf(r2, radius*radius);
             } else {
@@ -913,6 +919,33 @@ ZB_DEV void primStarRadius2Fast(const BvhView& bvh, uint32_t primIdx, const Vec<
     primStarRadius2<DIM>(bvh, primIdx, x, r2, flip, precision, silhouetteTests);
 }
 
+#ifndef ZB_ROBIN_RANGE_BOUND
+#define ZB_ROBIN_RANGE_BOUND 1 // 0: only the plane-distance bound (A/B builds)
+#endif
+
+// Second, sharper early exit of the reflectance part of the star-radius test. On a triangle whose plane lies at distance h
+// from x, the point at distance rho has cosine h/rho, so the reference's radius h^2 mu/(c (h mu - c^2)) (robin_bounds.h:48-74)
+// is g(rho) = mu rho^3/(mu rho^2 - h) for some rho between the closest and the farthest point of the triangle — its clamping
+// cosines are exactly h/closestDist and h/farDist (geometry.h:219-226). g is infinite for mu rho^2 <= h and has its only
+// minimum at rho^2 = 3h/mu, so over the superset [h, farDist] of that range its minimum is g at clamp(3h/mu, h^2, farDist^2):
+// a lower bound of the radius this triangle can report, from the plane distance and the three vertex distances alone. It
+// rejects 97 % of the triangles the plane-distance bound lets through (tools/host_probe.cu: of 4.6 M full evaluations on a
+// C3-like solve only 73 K lowered the radius). s = nRaw . (a - x), nn = |nRaw|^2. 0.2 % of slack on the squared radius; not
+// applied where the fused plane distance is itself ill-conditioned (grazing views, h below 0.3 % of the vertex distance).
+ZB_DEV bool robinRangeCannotShrink(const Prim<3>& prim, const Vec<3>& x, float s, float nn, float mu, float r2)
+{
+    if (!ZB_ROBIN_RANGE_BOUND || !(nn > 0.0f)) return false;
+    Vec<3> va = x - prim.a, vb = x - prim.b, vc = x - prim.c;
+    float dFar2 = fmaxf(dot(va, va), fmaxf(dot(vb, vb), dot(vc, vc)));
+    float h2 = s*s/nn;
+    if (!(h2 > 1e-12f && h2 > 1e-5f*dFar2)) return false;
+    float h = sqrtf(h2);
+    float q = fminf(fmaxf(3.0f*h/mu, h2), dFar2);
+    float den = mu*q - h;
+    if (den <= 0.0f) return true; // mu rho^2 <= h over the whole triangle: no reflectance bound (robin_bounds.h:57-58)
+    return q*q*q*mu*mu >= r2*den*den*1.002f;
+}
+
 ZB_DEV float closestPointTriangleFast2(const Vec<3>& pa, const Vec<3>& pb, const Vec<3>& pc, const Vec<3>& x, Vec<3>& pt)
 {
     Vec<3> ab = pb - pa, ac = pc - pa, ax = x - pa;
@@ -954,6 +987,7 @@ ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const V
             float s = dot(nRaw, prim.a - x), nn = dot(nRaw, nRaw);
             float t = fmaxf(r2*maxCoeff*(1.0f/6.7f), 1e-6f); // h > 1e-6 also keeps clear of the closestDist < epsilon case
             robinCannotShrink = nn > 0.0f && s*s >= nn*(t*t);
+            if (!robinCannotShrink) robinCannotShrink = robinRangeCannotShrink(prim, x, s, nn, maxCoeff, r2);
         }
         // ... and when, on top of that, every edge is marked ignoreAdjacentFace (convex edges of a single-sided solve,
         // fcpw_geometric_queries.h:1029-1038) or the subtree holds no silhouette, the triangle has nothing to say
@@ -1044,11 +1078,11 @@ ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const V
             float da = dot(va, va), db = dot(vb, vb), dc = dot(vc, vc);
             Vec<3> vfar = (da >= db && da >= dc) ? va : ((db >= da && db >= dc) ? vb : vc);
             float far2 = fmaxf(da, fmaxf(db, dc));
-            float h = fabsf(dot(n0, prim.a - x)/dot(n0, n0)); // findClosestPointPlane (geometry.h:62-70)
+            float h = fabsf(xdot(n0, prim.a - x)/xdot(n0, n0)); // findClosestPointPlane (geometry.h:62-70), reference-ordered
             if (h > 0.0f) {
-                float cosUpper = fabsf(dot((x - closestPt)/closestDist, n0));
+                float cosUpper = fabsf(xdot((x - closestPt)/closestDist, n0));
                 float farDist = sqrtf(far2);
-                float cosLower = fabsf(dot(vfar/farDist, n0));
+                float cosLower = fabsf(xdot(vfar/farDist, n0));
                 float radius = robinRadiusBound<3>(h, maxCoeff, cosLower, cosUpper);
                 if (radius < kMaxFloat) r2 = fminf(r2, radius*radius);
                 // threshold maxCos >= cosLower, the conditioning h mu/(h mu - c^2) of the bound (robin_bounds.h:48-74), and the
@@ -1062,6 +1096,7 @@ ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const V
         }
     }
     if (redo) r2 = primStarRadius2Redo<3>(bvh.prims, bvh.adjacency, bvh.snchSign, primIdx, x, r2in, flip, precision, silhouetteTests);
+    if (r2 < r2in) { ZB_CLASS(12) if (!silhouetteTests) { ZB_CLASS(13) } }
 }
 
 // Cheap first stage of primStarRadius2Fast for the pooled primitive rounds of coop.cuh: false when the triangle cannot
@@ -1088,7 +1123,8 @@ ZB_DEV bool primStarNeedsFullTest<3>(const BvhView& bvh, uint32_t primIdx, const
     Vec<3> nRaw = cross(prim.b - prim.a, prim.c - prim.a);
     float s = dot(nRaw, prim.a - x), nn = dot(nRaw, nRaw);
     float t = fmaxf(r2*maxCoeff*(1.0f/6.7f), 1e-6f);
-    return !(nn > 0.0f && s*s >= nn*(t*t));
+    if (nn > 0.0f && s*s >= nn*(t*t)) return false;
+    return !robinRangeCannotShrink(prim, x, s, nn, maxCoeff, r2);
 }
 
 // One out-of-line copy of the fast primitive test for all the traversals of a kernel (the private depth-first phase and
@@ -1217,6 +1253,10 @@ ZB_DEV bool starChildBounds(const BvhView& bvh, uint32_t nodeIdx, int c, const V
 // may hide inside; false when the child cannot shrink the radius at all. Conservative with respect to
 // starChildBounds' own tests: the overlap threshold carries 2e-5 of slack on the sine, the Robin cosine bound
 // 1e-5, on top of the 1e-4 rad by which the builder pads every cone.
+#ifndef ZB_NODE_JOINT_BOUND
+#define ZB_NODE_JOINT_BOUND 1 // 0: the reference's interval form r_min/(1 - cos/(mu r_max)) (A/B builds)
+#endif
+
 template <int DIM>
 ZB_DEV bool starChildBoundsFast(const float4& c0, const float4& c1, const Vec<DIM>& x,
                                                     const float lo[DIM], const float hi[DIM], float d2min, float d2max,
@@ -1268,9 +1308,17 @@ ZB_DEV bool starChildBoundsFast(const float4& c0, const float4& c1, const Vec<DI
     if (DIM == 3) {
         // r_min/(1 - cos/(mu r_max)) and r_max/(1 - 1/(mu r_min)) with approximate reciprocals: the denominators are
         // padded by 1e-6 (>> the 2-ulp error of their operands, also where they cancel) on the conservative side
+#if ZB_NODE_JOINT_BOUND
+        // every point y of the subtree has R(y) = rho/(1 - cos/(mu rho)) >= rho^2/(rho - k), k = minCos/maxCoeff, rho = |y - x|
+        // in [rMin, rMax]; that function of rho has its minimum 4k at rho = 2k and is infinite for rho <= k
+        float k = minCos*zb_rcp_fast(maxCoeff)*0.99999f;
+        if (!(rMax > k*1.00001f)) lower = kMaxFloat;
+        else { float rs = fminf(fmaxf(2.0f*k, rMin), rMax); float rb = rs*rs*zb_rcp_fast(rs - k + 1e-6f); lower = fmaxf(rb*rb, d2min); }
+#else
         float a = minCos*zb_rcp_fast(maxCoeff*rMax);
         if (a > 1.00001f) lower = kMaxFloat; // r_max < cos/mu
         else { float rb = rMin*zb_rcp_fast(fmaxf(1.0f - a, 0.0f) + 1e-6f); lower = rb*rb; }
+#endif
         if (!(rMin*minCoeff < 1.0f)) {
             float den = 1.0f - zb_rcp_fast(minCoeff*rMin) - 1e-6f;
             if (den > 0.0f) { float rb = rMax*zb_rcp_fast(den); upper = rb*rb; }

@@ -385,6 +385,7 @@ struct Lane {
     bool firstStep, flip, outerFlip, success, active, gradient;
     bool needClosest; // distA / proj must be recomputed at st.pt before the walk continues
     bool keepDistA;   // ... but only proj is wanted: keep the caller-provided distA (sample point inside the epsilon shell)
+    bool needsFinalProjection; // Walk on Spheres: the walk ran out of steps and proj is that of the previous position
 };
 
 template <int DIM>
@@ -426,6 +427,7 @@ ZB_DEV void beginTask(const SolveArgs& a, Lane<DIM>& L, long long task)
     L.gradient = !a.rwsRecords && a.pts.estimationQuantity[i] == ZB_SOLUTION_AND_GRADIENT;
     L.needClosest = false;
     L.keepDistA = false;
+    L.needsFinalProjection = false;
 
     if (!L.gradient) {
         // estimateSolution (walk_on_spheres.h:354-372; walk_on_stars.h:553-608)
@@ -442,9 +444,16 @@ ZB_DEV void beginTask(const SolveArgs& a, Lane<DIM>& L, long long task)
             L.st.onRefl = a.pts.type[i] == ZB_ON_REFLECTING_BOUNDARY;
             if (a.ws.solveDoubleSided && L.st.onRefl && a.pts.estimateBoundaryNormalAligned &&
                 a.pts.estimateBoundaryNormalAligned[i]) {
-                L.st.normal = -n;
-                L.st.prevDir = -n;
-                L.flip = true;
+                if (a.rwsRecords) {
+                    // a reverse walk keeps the sample's normal and only reverses the direction of approach; its first
+                    // step then flips the normal and queries the star with flipNormalOrientation = true
+                    // (reverse_walk_on_stars.h:127-139, 279-286)
+                    L.st.prevDir = -n;
+                } else {
+                    L.st.normal = -n;
+                    L.st.prevDir = -n;
+                    L.flip = true;
+                }
             }
         } else {
             L.st.normal = vzero<DIM>();
@@ -783,7 +792,7 @@ ZB_DEV StepResult stepBody(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *que
 
     if (weightWindow<DIM>(a, L, queue)) return kRoulette;
     st.walkLength++;
-    if (st.walkLength >= a.ws.maxWalkLength) return kMaxLength;
+    if (st.walkLength >= a.ws.maxWalkLength) { L.needsFinalProjection = !WOST; return kMaxLength; }
     if (a.pde.absorptionCoeff > 0.0f && a.ws.stepsBeforeApplyingTikhonov == st.walkLength) {
         L.g.init(true, a.pde.absorptionCoeff);
     }
@@ -819,6 +828,9 @@ ZB_DEV void finishState(const SolveArgs& a, Lane<DIM>& L, StepResult code, WalkS
         float terminal = 0.0f;
         bool project = WOST ? code == kReached : (code == kReached || code == kMaxLength);
         if (project && !a.ws.ignoreAbsorbingBoundaryContribution) {
+            // a Walk on Spheres walk that ran out of steps projects its LAST position (walk_on_spheres.h:294-308); the step
+            // that moved it there left the distance query pending (the wavefront defers the finish by one round instead)
+            if (!WOST && code == kMaxLength && L.needsFinalProjection) resolveClosest<DIM, WOST>(a, L);
             terminal = pde.dirichlet(a.hasAbsorbing ? L.proj : L.st.pt);
         }
         L.total += L.st.throughput*terminal + L.st.reflContrib + L.st.srcContrib;
@@ -835,6 +847,7 @@ ZB_DEV void finishState(const SolveArgs& a, Lane<DIM>& L, StepResult code, WalkS
         L.firstSphereRadius = 0.0f;
         L.firstStep = true;
         L.flip = L.outerFlip;
+        L.needsFinalProjection = false;
         return;
     }
     long long t = L.task;
@@ -864,6 +877,7 @@ __global__ void __launch_bounds__(128, ZB_WALK_MIN_BLOCKS) walkKernel(SolveArgs 
     L.active = false;
     L.needClosest = false;
     L.keepDistA = false;
+    L.needsFinalProjection = false;
     WalkState<DIM> queue[kSplitStack];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;

@@ -1,0 +1,396 @@
+// Wavefront scheduling of the walks (the shipped scheduler).
+//
+// Round 1 ran every walk inside ONE persistent kernel (walkKernel below in walk.cuh's history): 128 registers, 54 KB of
+// shared memory per CTA, 250 KB of SASS. Its ncu capture (profiles/r2_walkKernel_persistent_ncu.txt) shows 70 % of all
+// warp-stall samples in `no_instruction`: sixteen warps per SM, each in a different phase of the step (distance query,
+// star-radius query, ray casts, Green's-function math), thrash the 32 KB instruction cache, and the issue slots are
+// 14 % busy. The fix is structural: the walk state lives in HBM (120 bytes per walk, SoA) and a ROUND of the solve is
+// a short sequence of small, homogeneous kernels over all live walks,
+//
+//   waveClosestKernel   distance to the absorbing boundary at the walk's position (warp-cooperative traversal) for the
+//                       walks that need it, then the scalar prologue of the step: inside the epsilon shell? does the
+//                       step need a star-radius query?
+//   waveStarKernel      star radius (warp-cooperative traversal) for the walks that need one
+//   waveStepKernel      the rest of the step, one thread per walk: ray cast, boundary sample + occlusion ray, source
+//                       sample, throughput, weight window; walks that ended write their record and the slot takes the
+//                       next task from the global queue (compaction of terminated walks happens here, per slot)
+//   radix sort          (cub) of the live slots by the Morton code of the walk's new position: the 32 queries of a warp
+//                       of the next round are neighbours in space, so they traverse the same BVH nodes (L1 hits) and
+//                       take similar numbers of steps through it (lane efficiency); slots without a walk sort to the
+//                       end, which is also how the tail of a solve shrinks its grids
+//
+// Each kernel's hot loop fits the instruction cache, needs half the registers of the fused kernel, and every warp of
+// a launch runs the same code. State traffic is ~250 bytes per walk step against the ~10^4..10^5 instructions a step
+// costs: noise. Results do not depend on the schedule: a walk's random numbers come from its own pcg32 stream and its
+// record goes to a slot indexed by the task.
+#pragma once
+
+#include "walk.cuh"
+
+namespace zb {
+
+enum : uint32_t {
+    kWfActive = 1u, kWfNeedClosest = 2u, kWfKeepDistA = 4u, kWfFirstStep = 8u, kWfFlip = 16u, kWfOuterFlip = 32u,
+    kWfSuccess = 64u, kWfGradient = 128u, kWfOnRefl = 256u, kWfYukawa = 512u, kWfNeedStar = 1024u, kWfReached = 2048u,
+    kWfFinalProjection = 4096u // Walk on Spheres ran out of steps: finish with kMaxLength once the projection of the last position is known
+};
+
+struct WaveSlots {
+    float4 *ptDist;       // position | distance to the absorbing boundary
+    float4 *projStar;     // closest absorbing-boundary point | star radius of the coming step
+    float4 *normalPrev;   // boundary normal at the position | length of the previous step
+    float4 *dirThr;       // direction of the previous step | throughput
+    float4 *acc;          // reflecting-boundary terms, source terms (current walk state) | task total | first sphere radius
+    ulonglong2 *rng;      // pcg32 state, increment
+    int4 *meta;           // sample point, walk length, task walk length, flags
+    int4 *meta2;          // task (low, high word), finished walk states, queued splits
+    void *queue;          // WalkState<DIM>[kSplitStack] per slot; null when the settings rule splitting out
+    uint32_t *keys;       // Morton key per POSITION of the current order (written by waveStepKernel, sorted by cub)
+    const uint32_t *order; // position -> slot
+    unsigned int *live;   // walks alive after the current round
+    int nSlots;
+    float sortMin[3], sortScale[3];
+};
+
+ZB_DEV uint32_t spreadBits3(uint32_t v) // 10 bits -> every third bit
+{
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+ZB_DEV uint32_t spreadBits2(uint32_t v) // 15 bits -> every second bit
+{
+    v &= 0x7fffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
+template <int DIM>
+ZB_DEV uint32_t mortonKey(const WaveSlots& w, const Vec<DIM>& p)
+{
+    uint32_t q[DIM];
+#pragma unroll
+    for (int k = 0; k < DIM; k++) {
+        float t = (p[k] - w.sortMin[k])*w.sortScale[k];
+        const float top = DIM == 3 ? 1023.0f : 32767.0f;
+        q[k] = (uint32_t)fminf(fmaxf(t, 0.0f), top);
+    }
+    if (DIM == 3) return spreadBits3(q[0]) | (spreadBits3(q[1]) << 1) | (spreadBits3(q[DIM - 1]) << 2);
+    return spreadBits2(q[0]) | (spreadBits2(q[1]) << 1);
+}
+
+template <int DIM> ZB_DEV Vec<DIM> vec3of(const float4& v) { Vec<DIM> r; r[0] = v.x; r[1] = v.y; if (DIM == 3) r[DIM - 1] = v.z; return r; }
+template <int DIM> ZB_DEV float4 pack4(const Vec<DIM>& v, float w) { return make_float4(v[0], v[1], DIM == 3 ? v[DIM - 1] : 0.0f, w); }
+
+// ------------------------------------------------------------------------------------------
+// distance query + scalar prologue of the step
+// ------------------------------------------------------------------------------------------
+template <int DIM, bool WOST>
+__global__ void __launch_bounds__(128) waveClosestKernel(SolveArgs a, WaveSlots w, int nBound)
+{
+#if defined(__CUDA_ARCH__)
+    extern __shared__ __align__(16) unsigned char zbShared[];
+    WarpShared& ws = reinterpret_cast<WarpShared *>(zbShared)[threadIdx.x >> 5];
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    int slot = -1;
+    int4 m = make_int4(0, 0, 0, 0);
+    if (i < nBound) { slot = (int)w.order[i]; m = w.meta[slot]; }
+    uint32_t flags = (uint32_t)m.w;
+    const bool active = (flags & kWfActive) != 0u;
+    if (!__any_sync(0xffffffffu, active)) return;
+
+    // the part of the lane the prologue reads
+    Lane<DIM> L;
+    float4 pd = active ? w.ptDist[slot] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    L.st.pt = vec3of<DIM>(pd);
+    L.distA = pd.w;
+    L.st.walkLength = m.y;
+    L.st.onRefl = (flags & kWfOnRefl) != 0u;
+    L.firstStep = (flags & kWfFirstStep) != 0u;
+    L.keepDistA = (flags & kWfKeepDistA) != 0u;
+    L.flip = (flags & kWfFlip) != 0u;
+
+    const bool qc = active && (flags & kWfNeedClosest) != 0u;
+    if (__any_sync(0xffffffffu, qc)) {
+        Vec<DIM> proj = L.st.pt;
+        if (a.hasAbsorbing) {
+            ClosestHit<DIM> hit;
+            coopClosestPoint<DIM>(a.absorbing, ws, qc, L.st.pt, qc ? closestSearchRadius2<DIM, WOST>(a, L) : 0.0f, hit, a.status);
+            if (qc) {
+                if (!L.keepDistA) L.distA = hit.d;
+                proj = hit.p;
+            }
+        } else if (qc) {
+            // no absorbing boundary: default of GeometricQueries::populate (geometric_queries.h:213-218), as distToAbsorbing
+            float s = 0.0f;
+#pragma unroll
+            for (int k = 0; k < DIM; k++) { float t = fminf(a.domainMin[k] - L.st.pt[k], L.st.pt[k] - a.domainMax[k]); s += t*t; }
+            if (!L.keepDistA) L.distA = sqrtf(s);
+        }
+        if (qc) {
+            flags &= ~(kWfNeedClosest | kWfKeepDistA);
+            pd.w = L.distA;
+            w.ptDist[slot] = pd;
+            float4 ps = w.projStar[slot];
+            w.projStar[slot] = pack4<DIM>(proj, ps.w);
+        }
+    }
+    if (!active) return;
+
+    // loop condition of walk() (walk_on_spheres.h:237, walk_on_stars.h:357)
+    if (flags & kWfFinalProjection) {
+        // the walk already ended: waveStepKernel only waited for the projection
+    } else if (!(L.distA > a.ws.epsilonShellForAbsorbingBoundary)) {
+        flags |= kWfReached;
+    } else if (WOST) {
+        // stepStarPrologue reads the normal / previous direction only for double-sided walks on the boundary
+        float4 np = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        const bool twoSided = a.ws.solveDoubleSided && L.st.onRefl;
+        if (twoSided) {
+            np = w.normalPrev[slot];
+            float4 dt = w.dirThr[slot];
+            L.st.normal = vec3of<DIM>(np);
+            L.st.prevDist = np.w;
+            L.st.prevDir = vec3of<DIM>(dt);
+        }
+        L.firstSphereRadius = L.firstStep ? w.acc[slot].w : 0.0f;
+        float starRadius = 0.0f, r2max = 0.0f;
+        bool need = stepStarPrologue<DIM>(a, L, starRadius, r2max);
+        if (twoSided && L.flip) w.normalPrev[slot] = pack4<DIM>(L.st.normal, np.w);
+        flags = (flags & ~(kWfFlip | kWfNeedStar)) | (L.flip ? kWfFlip : 0u) | (need ? kWfNeedStar : 0u);
+        if (!need) {
+            float4 ps = w.projStar[slot];
+            ps.w = starRadius;
+            w.projStar[slot] = ps;
+        }
+    }
+    m.w = (int)flags;
+    w.meta[slot] = m;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------
+// star radius
+// ------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(128) waveStarKernel(SolveArgs a, WaveSlots w, int nBound)
+{
+#if defined(__CUDA_ARCH__)
+    extern __shared__ __align__(16) unsigned char zbShared[];
+    WarpShared& ws = reinterpret_cast<WarpShared *>(zbShared)[threadIdx.x >> 5];
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    int slot = -1;
+    uint32_t flags = 0u;
+    if (i < nBound) { slot = (int)w.order[i]; flags = (uint32_t)w.meta[slot].w; }
+    const bool qs = (flags & (kWfActive | kWfNeedStar)) == (kWfActive | kWfNeedStar);
+    if (!__any_sync(0xffffffffu, qs)) return;
+    float4 pd = qs ? w.ptDist[slot] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float trivial = 0.0f, r2max = 0.0f;
+    const float eps = a.ws.epsilonShellForReflectingBoundary;
+    if (qs) starQueryNeeded<DIM>(a, eps, pd.w, trivial, r2max);
+    float r2 = coopStarRadius2<DIM>(a.reflecting, ws, qs, vec3of<DIM>(pd), r2max, !(flags & kWfFlip), a.ws.silhouettePrecision, a.status);
+    if (qs) {
+        float r = starQueryResult(a, r2, r2max, eps, pd.w);
+        float4 ps = w.projStar[slot];
+        ps.w = shrinkStarRadius(a, r, pd.w);
+        w.projStar[slot] = ps;
+    }
+#endif
+}
+
+// ------------------------------------------------------------------------------------------
+// the rest of the step, termination, next task
+// ------------------------------------------------------------------------------------------
+template <int DIM>
+ZB_DEV void loadLane(const SolveArgs& a, const WaveSlots& w, int slot, const int4& m, Lane<DIM>& L)
+{
+    const uint32_t flags = (uint32_t)m.w;
+    float4 pd = w.ptDist[slot], ps = w.projStar[slot], np = w.normalPrev[slot], dt = w.dirThr[slot], ac = w.acc[slot];
+    ulonglong2 rg = w.rng[slot];
+    int4 m2 = w.meta2[slot];
+    L.st.pt = vec3of<DIM>(pd);
+    L.distA = pd.w;
+    L.proj = vec3of<DIM>(ps);
+    L.st.normal = vec3of<DIM>(np);
+    L.st.prevDist = np.w;
+    L.st.prevDir = vec3of<DIM>(dt);
+    L.st.throughput = dt.w;
+    L.st.reflContrib = ac.x;
+    L.st.srcContrib = ac.y;
+    L.total = ac.z;
+    L.firstSphereRadius = ac.w;
+    L.rng.state = rg.x;
+    L.rng.inc = rg.y;
+    L.point = m.x;
+    L.st.walkLength = m.y;
+    L.totalLength = m.z;
+    L.task = (long long)(((unsigned long long)(uint32_t)m2.y << 32) | (unsigned long long)(uint32_t)m2.x);
+    L.splits = m2.z;
+    L.nQueued = m2.w;
+    L.active = true;
+    L.needClosest = (flags & kWfNeedClosest) != 0u;
+    L.keepDistA = (flags & kWfKeepDistA) != 0u;
+    L.firstStep = (flags & kWfFirstStep) != 0u;
+    L.flip = (flags & kWfFlip) != 0u;
+    L.outerFlip = (flags & kWfOuterFlip) != 0u;
+    L.success = (flags & kWfSuccess) != 0u;
+    L.gradient = (flags & kWfGradient) != 0u;
+    L.st.onRefl = (flags & kWfOnRefl) != 0u;
+    L.needsFinalProjection = false;
+    L.g.init((flags & kWfYukawa) != 0u, a.pde.absorptionCoeff);
+    L.firstSource = 0.0f;
+    L.gradBoundary = vzero<DIM>();
+    L.gradSource = vzero<DIM>();
+}
+
+template <int DIM>
+ZB_DEV uint32_t storeLane(const WaveSlots& w, int slot, const Lane<DIM>& L)
+{
+    uint32_t flags = kWfActive | (L.needClosest ? kWfNeedClosest : 0u) | (L.keepDistA ? kWfKeepDistA : 0u) |
+                     (L.firstStep ? kWfFirstStep : 0u) | (L.flip ? kWfFlip : 0u) | (L.outerFlip ? kWfOuterFlip : 0u) |
+                     (L.success ? kWfSuccess : 0u) | (L.gradient ? kWfGradient : 0u) | (L.st.onRefl ? kWfOnRefl : 0u) |
+                     (L.g.yukawa ? kWfYukawa : 0u) | (L.needsFinalProjection ? kWfFinalProjection : 0u);
+    w.ptDist[slot] = pack4<DIM>(L.st.pt, L.distA);
+    w.projStar[slot] = pack4<DIM>(L.proj, 0.0f);
+    w.normalPrev[slot] = pack4<DIM>(L.st.normal, L.st.prevDist);
+    w.dirThr[slot] = pack4<DIM>(L.st.prevDir, L.st.throughput);
+    w.acc[slot] = make_float4(L.st.reflContrib, L.st.srcContrib, L.total, L.firstSphereRadius);
+    ulonglong2 rg;
+    rg.x = L.rng.state;
+    rg.y = L.rng.inc;
+    w.rng[slot] = rg;
+    w.meta[slot] = make_int4(L.point, L.st.walkLength, L.totalLength, (int)flags);
+    w.meta2[slot] = make_int4((int)(uint32_t)((unsigned long long)L.task & 0xffffffffull), (int)(uint32_t)((unsigned long long)L.task >> 32),
+                              L.splits, L.nQueued);
+    return flags;
+}
+
+// the gradient estimator's per-task factors are known when the task begins (beginTask): they go straight to its record
+template <int DIM>
+ZB_DEV void storeGradientFactors(const SolveArgs& a, const Lane<DIM>& L)
+{
+    if (!a.anyGradient) return;
+    long long t = L.task;
+    a.recFirstSource[t] = L.firstSource;
+    for (int k = 0; k < DIM; k++) {
+        a.recGradBoundary[(size_t)DIM*t + k] = L.gradBoundary[k];
+        a.recGradSource[(size_t)DIM*t + k] = L.gradSource[k];
+    }
+}
+
+// finishState of the wavefront: as walk.cuh's, but the record's gradient factors were written when the task began
+template <int DIM, bool WOST>
+ZB_DEV void finishStateWave(const SolveArgs& a, Lane<DIM>& L, StepResult code, WalkState<DIM> *queue)
+{
+    PdeEval<DIM> pde{a.pde};
+    L.splits++;
+    if (code != kEscaped) {
+        float terminal = 0.0f;
+        bool project = WOST ? code == kReached : (code == kReached || code == kMaxLength);
+        if (project && !a.ws.ignoreAbsorbingBoundaryContribution) terminal = pde.dirichlet(a.hasAbsorbing ? L.proj : L.st.pt);
+        L.total += L.st.throughput*terminal + L.st.reflContrib + L.st.srcContrib;
+        L.totalLength += L.st.walkLength;
+        L.success = true;
+    }
+    if (L.nQueued > 0) {
+        L.st = queue[--L.nQueued];
+        bool yukawa = a.pde.absorptionCoeff > 0.0f && a.ws.stepsBeforeApplyingTikhonov == 0;
+        L.g.init(yukawa, a.pde.absorptionCoeff);
+        L.distA = kMaxFloat;
+        L.needClosest = true;
+        L.keepDistA = false;
+        L.firstSphereRadius = 0.0f;
+        L.firstStep = true;
+        L.flip = L.outerFlip;
+        L.needsFinalProjection = false;
+        return;
+    }
+    long long t = L.task;
+    a.recSolution[t] = L.total;
+    a.recLength[t] = L.totalLength;
+    a.recFlags[t] = (L.success ? (int)0x80000000 : 0) | (L.splits & 0x7fffffff);
+    L.active = false;
+}
+
+template <int DIM, bool WOST>
+__global__ void __launch_bounds__(128) waveStepKernel(SolveArgs a, WaveSlots w, int nBound)
+{
+#if defined(__CUDA_ARCH__)
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    int slot = -1;
+    int4 m = make_int4(0, 0, 0, 0);
+    if (i < nBound) { slot = (int)w.order[i]; m = w.meta[slot]; }
+    const uint32_t flags = (uint32_t)m.w;
+    Lane<DIM> L;
+    L.active = false;
+    WalkState<DIM> *queue = w.queue && slot >= 0 ? reinterpret_cast<WalkState<DIM> *>(w.queue) + (size_t)slot*kSplitStack : nullptr;
+
+    if (flags & kWfActive) {
+        loadLane<DIM>(a, w, slot, m, L);
+        if (flags & kWfFinalProjection) {
+            L.needsFinalProjection = false;
+            finishStateWave<DIM, WOST>(a, L, kMaxLength, queue);
+        } else if (flags & kWfReached) {
+            finishStateWave<DIM, WOST>(a, L, kReached, queue);
+        } else if (!L.needClosest) {
+            StepResult r = stepBody<DIM, WOST>(a, L, queue, w.projStar[slot].w);
+            // Walk on Spheres ends a walk that ran out of steps with the Dirichlet value at the projection of its LAST
+            // position (walk_on_spheres.h:294-308): that projection is one more distance query (one round) away
+            if (!WOST && r == kMaxLength && L.needsFinalProjection && a.hasAbsorbing && !a.ws.ignoreAbsorbingBoundaryContribution) {
+                L.needClosest = true;
+            } else if (r != kContinue) {
+                L.needsFinalProjection = false;
+                finishStateWave<DIM, WOST>(a, L, r, queue);
+            }
+        }
+    }
+
+    // ---- compaction: slots whose walk ended take the next tasks of the global queue
+    const bool want = slot >= 0 && !L.active;
+    const unsigned need = __ballot_sync(full, want);
+    if (need) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.taskCounter, (unsigned long long)__popc(need));
+        base = __shfl_sync(full, base, 0);
+        long long task = (long long)base + __popc(need & ((1u << lane) - 1u));
+        if (want && task < a.totalTasks) {
+            beginTask<DIM, WOST>(a, L, task);
+            if (L.gradient) storeGradientFactors<DIM>(a, L);
+        }
+    }
+
+    uint32_t key = 0xffffffffu;
+    if (slot >= 0) {
+        if (L.active) {
+            storeLane<DIM>(w, slot, L);
+            key = mortonKey<DIM>(w, L.st.pt);
+        } else if (flags & kWfActive) {
+            m.w = 0;
+            w.meta[slot] = m;
+        }
+        w.keys[i] = key;
+    }
+    const unsigned alive = __ballot_sync(full, L.active);
+    if (lane == 0 && alive) atomicAdd(w.live, (unsigned int)__popc(alive));
+#endif
+}
+
+// slots of a new solve: none holds a walk, order = identity
+__global__ void waveResetKernel(WaveSlots w, uint32_t *order)
+{
+    int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i < w.nSlots) {
+        w.meta[i] = make_int4(0, 0, 0, 0);
+        order[i] = (uint32_t)i;
+    }
+}
+
+} // namespace zb
