@@ -63,3 +63,20 @@ def z_scores(a, b):
     va = a.solution_variance()/np.maximum(1, a.nSolutionEstimates)
     vb = b.solution_variance()/np.maximum(1, b.nSolutionEstimates)
     return (a.solutionMean - b.solutionMean)/np.sqrt(np.maximum(va + vb, 1e-12))
+
+
+def coplanar_primitive_within(positions, indices, x, reach, rel):
+    """True when x lies in the supporting plane (3D) / line (2D) of a primitive whose closest vertex is within `reach`:
+    plane distance below `rel` times that distance. float64 throughout."""
+    p = positions[indices]                      # (n, dim, dim)
+    dim = p.shape[2]
+    if dim == 3:
+        n = np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0])
+    else:
+        e = p[:, 1] - p[:, 0]
+        n = np.stack([e[:, 1], -e[:, 0]], axis=1)
+    n /= np.maximum(np.linalg.norm(n, axis=1, keepdims=True), 1e-300)
+    h = np.abs(np.einsum("ij,ij->i", n, x[None, :] - p[:, 0]))
+    d = np.linalg.norm(p - x[None, None, :], axis=2).min(axis=1)
+    near = d <= reach
+    return bool(np.any(near & (h <= rel*np.maximum(d, 1e-300))))

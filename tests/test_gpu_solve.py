@@ -1,6 +1,6 @@
 """GPU parity tests of the estimators (zb_solve = WalkOnSpheres::solve / WalkOnStars::solve) through the C ABI.
 Per BASELINE.json's north_star the gate is statistical: per-point estimates agree with the reference's CPU
-solver within 3 standard errors (>= 99 % of points; the reference is non-reproducible run to run by design,
+solver within 3 standard errors (>= 99.3 % of >= 2000 points, SURVEY §8d(ii) asks for 99.7 % in expectation; the reference is non-reproducible run to run by design,
 SURVEY.md §8a row R), and both converge to the exact solution at the same RMSE-vs-walk-count rate."""
 import os
 
@@ -64,21 +64,24 @@ def test_estimates_match_reference_golden(ctx, name):
     settings = c.get("settings", abi.WalkSettings.default)()
     steps = sc.solve(c["estimator"], c["pde"](), settings, pts, st)
     assert steps == int(st.totalWalkLength.sum()) and steps > 0
-    assert np.array_equal(st.nSolutionEstimates, r.nSolutionEstimates)
+    # a walk that leaves the bounding domain yields no estimate (walk_on_stars.h:455-460, walk_on_spheres.h:262-267): a
+    # random event of a few walks per million, so the counts agree up to that, not element by element
+    dn = st.nSolutionEstimates.astype(np.int64) - r.nSolutionEstimates
+    assert np.abs(dn).max() <= 1 and np.abs(dn).sum() <= 4, (np.abs(dn).max(), np.abs(dn).sum())
     z = cases.z_scores(st, r)
-    assert np.mean(np.abs(z) < 3.0) >= 0.985, "only %.4f of the points within 3 standard errors" % np.mean(np.abs(z) < 3.0)
-    assert abs(z.mean()) < 0.25 and 0.8 < z.std() < 1.25, (z.mean(), z.std())
+    assert np.mean(np.abs(z) < 3.0) >= 0.993, "only %.4f of the points within 3 standard errors" % np.mean(np.abs(z) < 3.0)
+    assert abs(z.mean()) < 0.1 and 0.9 < z.std() < 1.12, (z.mean(), z.std())
     # same walk-length distribution (the metric's numerator)
     assert abs(steps/float(r.g["steps"]) - 1.0) < 0.03
     # first-sphere radius: same star-radius query, same 1 % shrink
     assert np.allclose(pts.firstSphereRadius, r.g["firstSphereRadius"], rtol=1e-5, atol=1e-7)
     if c["quantity"] == abi.SOLUTION_AND_GRADIENT:
-        assert np.array_equal(st.nGradientEstimates, r.nGradientEstimates)
+        assert np.abs(st.nGradientEstimates.astype(np.int64) - r.nGradientEstimates).sum() <= 8
         se = np.sqrt(st.gradient_variance()/np.maximum(1, st.nGradientEstimates)[:, None] +
                      r.gradient_variance()/np.maximum(1, r.nGradientEstimates)[:, None])
         zg = (st.gradientMean - r.gradientMean)/np.maximum(se, 1e-9)
-        assert np.mean(np.abs(zg) < 3.0) >= 0.985
-        assert abs(zg.mean()) < 0.25 and 0.8 < zg.std() < 1.25
+        assert np.mean(np.abs(zg) < 3.0) >= 0.993
+        assert abs(zg.mean()) < 0.1 and 0.9 < zg.std() < 1.12
     sc.close()
 
 
@@ -234,7 +237,7 @@ def test_kelvin_exterior_problem_matches_reference(ctx, ref, mixed):
     device wraps the PDE like KelvinTransform::transformPde (kelvin_transform.h:282-348); the reference runs the
     same inverted inputs through its own transformPde. Dirichlet variant: also against u = 1/|x - x0|."""
     from zombie_b200 import kelvin
-    w = workloads.config5(subdivisions=4, n_points=384, n_walks=128, mixed=mixed)
+    w = workloads.config5(subdivisions=4, n_points=2048, n_walks=128, mixed=mixed)
     sc = native.Scene(ctx, 3, **w.scene_kwargs())
     rs = ref.RefScene(3, **w.scene_kwargs())
     _, da, _, _ = sc.closest_point(abi.ABSORBING, w.points)
@@ -246,10 +249,13 @@ def test_kelvin_exterior_problem_matches_reference(ctx, ref, mixed):
         out = solver.solve(w.estimator, w.pde, w.settings, pts, st)
         results.append((st, out if np.isscalar(out) else out[0]))
     (gs, gsteps), (rs_, rsteps) = results
-    assert np.array_equal(gs.nSolutionEstimates, rs_.nSolutionEstimates)
+    # a walk that leaves the bounding domain yields no estimate (walk_on_stars.h:455-460): a rare random event in the
+    # inverted geometry, so the counts agree up to a few walks per 1000 points, not element by element
+    dn = gs.nSolutionEstimates.astype(np.int64) - rs_.nSolutionEstimates
+    assert np.abs(dn).max() <= 3 and abs(int(dn.sum())) <= 1e-3*int(rs_.nSolutionEstimates.sum()), (np.abs(dn).max(), dn.sum())
     z = cases.z_scores(gs, rs_)
-    assert np.mean(np.abs(z) < 3.0) >= 0.985, np.mean(np.abs(z) < 3.0)
-    assert abs(z.mean()) < 0.25 and 0.8 < z.std() < 1.25, (z.mean(), z.std())
+    assert np.mean(np.abs(z) < 3.0) >= 0.993, np.mean(np.abs(z) < 3.0)
+    assert abs(z.mean()) < 0.1 and 0.9 < z.std() < 1.12, (z.mean(), z.std())
     assert abs(gsteps/float(rsteps) - 1.0) < 0.05
     if not mixed:
         u = kelvin.transform_solution_estimate(gs.solutionMean, w.points)   # back to the exterior domain

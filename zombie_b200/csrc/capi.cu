@@ -303,42 +303,74 @@ int envInt(const char *name, int fallback)
     return v && *v ? std::atoi(v) : fallback;
 }
 
-constexpr int kLiveRing = 8;       // live-walk counters in flight
-constexpr int kRoundsPerGroup = 4; // rounds enqueued between two read-backs of the live count
+constexpr int kLiveRing = 8;       // live-walk counters in flight per group
+constexpr int kRoundsPerGroup = 4; // rounds enqueued between two read-backs of a group's live count
+constexpr int kMaxWaveGroups = 8;
+
+// One group of slots = an independent sequence of rounds on its own stream. A round's kernels end with a tail (a few warps
+// still inside heavy queries while most SMs idle, ncu: achieved occupancy 14 % of a theoretical 25 %); with several groups
+// in flight the block scheduler fills that tail with another group's kernels. Group g owns the tasks g, g + G, g + 2G, ...,
+// so what a group computes does not depend on how the groups interleave.
+struct WaveGroup {
+    WaveSlots w;
+    uint32_t *orderA = nullptr, *orderB = nullptr, *keysOut = nullptr;
+    unsigned int *live = nullptr;
+    void *sortTemp = nullptr;
+    cudaStream_t stream = nullptr;
+    int nSlots = 0, nBound = 0, round = 0, batches = 0;
+    bool done = false;
+};
 
 template <int DIM, bool WOST>
 int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
 {
     zb_context *ctx = scene->ctx;
     cudaStream_t stream = ctx->stream;
-    // Slots: enough walks in flight to fill the machine several times over (the sort needs a population to find
-    // neighbours in), never more than there are tasks. ZB_WAVE_SLOTS overrides (measurements).
+    // Slots: enough walks in flight to fill the machine several times over, never more than there are tasks.
+    // ZB_WAVE_SLOTS / ZB_WAVE_GROUPS / ZB_WAVE_SORT / ZB_WAVE_BLOCK override (measurements).
     const int maxSlots = std::max(128, envInt("ZB_WAVE_SLOTS", 262144));
-    const int nSlots = (int)std::min<long long>(maxSlots, (totalTasks + 127)/128*128);
-    const bool sortSlots = envInt("ZB_WAVE_SORT", 1) != 0;
+    int nGroups = std::min(kMaxWaveGroups, std::max(1, envInt("ZB_WAVE_GROUPS", 1)));
+    while (nGroups > 1 && totalTasks < (long long)nGroups*4096) nGroups--; // small solves: one group
+    const int sortMode = envInt("ZB_WAVE_SORT", 0);
+    const int qThreads = std::min(128, std::max(32, envInt("ZB_WAVE_BLOCK", 128)/32*32)); // CTA size of the two query kernels
+    const size_t qSmem = (size_t)(qThreads/32)*sizeof(WarpShared);
     const bool needQueue = a.ws.splittingThreshold < kMaxFloat;
+    const int stripeWarps = std::max(1, envInt("ZB_WAVE_STRIPE", 4096)/nGroups); // warps the tail of a solve spreads over (ZB_WAVE_STRIPE=1: compact)
 
-    Carver c0(nullptr);
-    auto carve = [&](Carver& c, WaveSlots& w, uint32_t *&orderA, uint32_t *&orderB, uint32_t *&keysOut, unsigned int *&live) {
-        w.ptDist = c.take<float4>(nSlots); w.projStar = c.take<float4>(nSlots); w.normalPrev = c.take<float4>(nSlots);
-        w.dirThr = c.take<float4>(nSlots); w.acc = c.take<float4>(nSlots); w.rng = c.take<ulonglong2>(nSlots);
-        w.meta = c.take<int4>(nSlots); w.meta2 = c.take<int4>(nSlots);
-        w.queue = needQueue ? (void *)c.take<WalkState<DIM>>((size_t)nSlots*kSplitStack) : nullptr;
-        w.keys = c.take<uint32_t>(nSlots);
-        keysOut = c.take<uint32_t>(nSlots);
-        orderA = c.take<uint32_t>(nSlots);
-        orderB = c.take<uint32_t>(nSlots);
-        live = c.take<unsigned int>(kLiveRing);
-    };
-    WaveSlots w;
-    std::memset(&w, 0, sizeof(w));
-    uint32_t *orderA = nullptr, *orderB = nullptr, *keysOut = nullptr;
-    unsigned int *live = nullptr;
-    carve(c0, w, orderA, orderB, keysOut, live);
-    ZB_CUDA(ctx->wave.reserve(c0.offset + 256));
-    Carver c1(ctx->wave.ptr);
-    carve(c1, w, orderA, orderB, keysOut, live);
-    w.nSlots = nSlots;
+    WaveGroup groups[kMaxWaveGroups];
+    size_t sortBytes = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        if (pass == 1) ZB_CUDA(ctx->wave.reserve(sortBytes + 256)); // sortBytes: total of pass 0
+        Carver c(pass == 0 ? nullptr : ctx->wave.ptr);
+        for (int g = 0; g < nGroups; g++) {
+            WaveGroup& G = groups[g];
+            long long tasksOfGroup = (totalTasks - g + nGroups - 1)/nGroups;
+            const int nSlots = (int)std::min<long long>(maxSlots/nGroups/128*128 > 0 ? maxSlots/nGroups/128*128 : 128, (tasksOfGroup + 127)/128*128);
+            G.nSlots = G.nBound = std::max(nSlots, 128);
+            WaveSlots& w = G.w;
+            std::memset(&w, 0, sizeof(w));
+            const size_t n = (size_t)G.nSlots;
+            w.ptDist = c.take<float4>(n); w.projStar = c.take<float4>(n); w.normalPrev = c.take<float4>(n);
+            w.dirThr = c.take<float4>(n); w.acc = c.take<float4>(n); w.rng = c.take<ulonglong2>(n);
+            w.meta = c.take<int4>(n); w.meta2 = c.take<int4>(n);
+            w.queue = needQueue ? (void *)c.take<WalkState<DIM>>(n*kSplitStack) : nullptr;
+            w.keys = c.take<uint32_t>(n);
+            G.keysOut = c.take<uint32_t>(n);
+            G.orderA = c.take<uint32_t>(n);
+            G.orderB = c.take<uint32_t>(n);
+            G.live = c.take<unsigned int>(kLiveRing);
+            w.taskCounter = c.take<unsigned long long>(1);
+            size_t bytes = 0;
+            ZB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, w.keys, G.keysOut, G.orderA, G.orderB, G.nSlots, 0, 32, stream));
+            G.sortTemp = c.take<char>(bytes + 256);
+            w.nSlots = G.nSlots;
+            w.sortMode = sortMode;
+            w.debugEscapes = envInt("ZB_WAVE_DEBUG", 0);
+            w.taskFirst = g;
+            w.taskStride = nGroups;
+        }
+        sortBytes = c.offset;
+    }
     // Morton frame: the union of the boundary boxes (walks live inside the domain; escapees clamp)
     float lo[3] = {kMaxFloat, kMaxFloat, kMaxFloat}, hi[3] = {-kMaxFloat, -kMaxFloat, -kMaxFloat};
     for (int b = 0; b < 2; b++) {
@@ -348,62 +380,86 @@ int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
             hi[k] = std::max(hi[k], scene->boundary[b].host.boxMax[k]);
         }
     }
-    for (int k = 0; k < 3; k++) {
-        if (!(hi[k] > lo[k])) { lo[k] = 0.0f; hi[k] = 1.0f; }
-        w.sortMin[k] = lo[k];
-        w.sortScale[k] = (DIM == 3 ? 1024.0f : 32768.0f)/(hi[k] - lo[k]);
+    for (int g = 0; g < nGroups; g++) {
+        for (int k = 0; k < 3; k++) {
+            float l = hi[k] > lo[k] ? lo[k] : 0.0f, h = hi[k] > lo[k] ? hi[k] : 1.0f;
+            groups[g].w.sortMin[k] = l;
+            groups[g].w.sortScale[k] = (DIM == 3 ? 1024.0f : 32768.0f)/(h - l);
+        }
     }
 
-    size_t sortBytes = 0;
-    if (sortSlots) {
-        ZB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sortBytes, w.keys, keysOut, orderA, orderB, nSlots, 0, 32, stream));
-        ZB_CUDA(ctx->waveSort.reserve(sortBytes + 256));
-    }
-    if (!ctx->hostLive) ZB_CUDA(cudaMallocHost(&ctx->hostLive, 2*sizeof(unsigned int)));
-    for (int k = 0; k < 2; k++) if (!ctx->evRound[k]) ZB_CUDA(cudaEventCreateWithFlags(&ctx->evRound[k], cudaEventDisableTiming));
+    if (!ctx->hostLive) ZB_CUDA(cudaMallocHost(&ctx->hostLive, 2*kMaxWaveGroups*sizeof(unsigned int)));
+    for (int k = 0; k < 2*kMaxWaveGroups; k++) if (!ctx->evRound[k]) ZB_CUDA(cudaEventCreateWithFlags(&ctx->evRound[k], cudaEventDisableTiming));
+    if (!ctx->evFork) ZB_CUDA(cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming));
+    for (int g = 1; g < nGroups; g++) if (!ctx->waveStreams[g]) ZB_CUDA(cudaStreamCreateWithFlags(&ctx->waveStreams[g], cudaStreamNonBlocking));
 
     ZB_CUDA(cudaFuncSetAttribute(waveClosestKernel<DIM, WOST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
     if (WOST) ZB_CUDA(cudaFuncSetAttribute(waveStarKernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
 
-    waveResetKernel<<<blocksFor(nSlots, 256), 256, 0, stream>>>(w, orderA);
-    ZB_CUDA(cudaGetLastError());
-    ctx->launches += 1;
+    // fork: the group streams start after everything already queued on the context's stream
+    ZB_CUDA(cudaEventRecord(ctx->evFork, stream));
+    for (int g = 0; g < nGroups; g++) {
+        WaveGroup& G = groups[g];
+        G.stream = g == 0 ? stream : ctx->waveStreams[g];
+        if (g > 0) ZB_CUDA(cudaStreamWaitEvent(G.stream, ctx->evFork, 0));
+        ZB_CUDA(cudaMemsetAsync(G.w.taskCounter, 0, sizeof(unsigned long long), G.stream));
+        waveResetKernel<<<blocksFor(G.nSlots, 256), 256, 0, G.stream>>>(G.w, G.orderA);
+        ZB_CUDA(cudaGetLastError());
+        ctx->launches += 1;
+    }
 
-    int nBound = nSlots, round = 0;
     const bool star = WOST && a.hasReflecting;
-    for (int group = 0;; group++) {
-        for (int g = 0; g < kRoundsPerGroup; g++, round++) {
-            w.order = orderA;
-            w.live = live + round%kLiveRing;
-            ZB_CUDA(cudaMemsetAsync(w.live, 0, sizeof(unsigned int), stream));
-            const int blocks = blocksFor(nBound, 128);
-            if (round > 0) { // round 0 only hands out the first tasks
-                waveClosestKernel<DIM, WOST><<<blocks, 128, kCoopSmem, stream>>>(a, w, nBound);
-                if (star) waveStarKernel<DIM><<<blocks, 128, kCoopSmem, stream>>>(a, w, nBound);
-                ctx->launches += star ? 2 : 1;
+    int remaining = nGroups, rounds = 0;
+    while (remaining > 0) {
+        for (int g = 0; g < nGroups; g++) {
+            WaveGroup& G = groups[g];
+            if (G.done) continue;
+            WaveSlots& w = G.w;
+            for (int k = 0; k < kRoundsPerGroup; k++, G.round++) {
+                w.order = G.orderA;
+                w.live = G.live + G.round%kLiveRing;
+                ZB_CUDA(cudaMemsetAsync(w.live, 0, sizeof(unsigned int), G.stream));
+                if (G.round > 0) { // round 0 only hands out the first tasks
+                    // striped over all the group's warps while there are enough walks; in the tail over as many warps as
+                    // there are walks, but never fewer than a few per SM-resident warp slot
+                    const int qWarps = std::max(1, std::min(G.nSlots/32, std::max(G.nBound/32, stripeWarps)));
+                    const int qBlocks = blocksFor(qWarps*32, qThreads);
+                    const int launchedWarps = qBlocks*(qThreads/32);
+                    waveClosestKernel<DIM, WOST><<<qBlocks, qThreads, qSmem, G.stream>>>(a, w, G.nBound, launchedWarps);
+                    if (star) waveStarKernel<DIM><<<qBlocks, qThreads, qSmem, G.stream>>>(a, w, G.nBound, launchedWarps);
+                    ctx->launches += star ? 2 : 1;
+                }
+                waveStepKernel<DIM, WOST><<<blocksFor(G.nBound, 128), 128, 0, G.stream>>>(a, w, G.nBound);
+                ZB_CUDA(cudaGetLastError());
+                size_t bytes = sortBytes; // upper bound of this group's scratch
+                ZB_CUDA(cub::DeviceRadixSort::SortPairs(G.sortTemp, bytes, w.keys, G.keysOut, G.orderA, G.orderB, G.nBound, 0, 32, G.stream));
+                std::swap(G.orderA, G.orderB);
+                ctx->launches += 2; // the step kernel and one library call (cub's own kernels are not counted)
             }
-            waveStepKernel<DIM, WOST><<<blocks, 128, 0, stream>>>(a, w, nBound);
-            ZB_CUDA(cudaGetLastError());
-            ctx->launches += 1;
-            if (sortSlots) {
-                ZB_CUDA(cub::DeviceRadixSort::SortPairs(ctx->waveSort.ptr, sortBytes, w.keys, keysOut, orderA, orderB, nBound, 0, 32, stream));
-                std::swap(orderA, orderB);
-                ctx->launches += 1; // one library call (cub's own kernels are not counted)
+            rounds = std::max(rounds, G.round);
+            const int slot = 2*g + (G.batches & 1);
+            ZB_CUDA(cudaMemcpyAsync(ctx->hostLive + slot, G.live + (G.round - 1)%kLiveRing, sizeof(unsigned int), cudaMemcpyDeviceToHost, G.stream));
+            ZB_CUDA(cudaEventRecord(ctx->evRound[slot], G.stream));
+            if (G.batches >= 1) {
+                // one batch of rounds of lag: the device never waits for the host
+                const int prev = 2*g + ((G.batches - 1) & 1);
+                ZB_CUDA(cudaEventSynchronize(ctx->evRound[prev]));
+                unsigned int alive = ctx->hostLive[prev];
+                if (alive == 0u) { G.done = true; remaining--; }
+                // the live walks sit at the front of the order (empty slots sort to the end) and, once the group's tasks have
+                // run out, their number only falls: later rounds need not look past it
+                else G.nBound = std::min(G.nBound, (int)((alive + 127u)/128u*128u));
             }
-        }
-        ZB_CUDA(cudaMemcpyAsync(ctx->hostLive + (group & 1), live + (round - 1)%kLiveRing, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
-        ZB_CUDA(cudaEventRecord(ctx->evRound[group & 1], stream));
-        if (group >= 1) {
-            // one group of lag: the device never waits for the host
-            ZB_CUDA(cudaEventSynchronize(ctx->evRound[(group - 1) & 1]));
-            unsigned int alive = ctx->hostLive[(group - 1) & 1];
-            if (alive == 0u) break;
-            // the live walks sit at the front of the order (empty slots sort to the end) and, once the task queue has
-            // run dry, their number only falls: later rounds need not look past it
-            if (sortSlots) nBound = std::min(nBound, (int)((alive + 127u)/128u*128u));
+            G.batches++;
         }
     }
-    ctx->lastRounds = round;
+    // join: the context's stream continues after every group
+    for (int g = 1; g < nGroups; g++) {
+        ZB_CUDA(cudaEventRecord(ctx->evRound[2*g], groups[g].stream));
+        ZB_CUDA(cudaStreamWaitEvent(stream, ctx->evRound[2*g], 0));
+    }
+    ctx->lastRounds = rounds;
+    ctx->lastGrid = nGroups;
     return ZB_OK;
 }
 
@@ -563,7 +619,9 @@ void zb_context_destroy(zb_context *ctx)
     if (ctx->ownsStream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->hostStatus) cudaFreeHost(ctx->hostStatus);
     if (ctx->hostLive) cudaFreeHost(ctx->hostLive);
-    for (int k = 0; k < 2; k++) if (ctx->evRound[k]) cudaEventDestroy(ctx->evRound[k]);
+    for (int k = 0; k < 16; k++) if (ctx->evRound[k]) cudaEventDestroy(ctx->evRound[k]);
+    if (ctx->evFork) cudaEventDestroy(ctx->evFork);
+    for (int k = 0; k < 8; k++) if (ctx->waveStreams[k]) cudaStreamDestroy(ctx->waveStreams[k]);
     for (int k = 0; k < 4; k++) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     for (int k = 0; k < 2; k++) if (ctx->evSplat[k]) cudaEventDestroy(ctx->evSplat[k]);
     delete ctx;

@@ -58,7 +58,9 @@ struct zb_context {
     zb::DeviceBuffer bvcSamples, bvcIo, rwsRecords;
     zb::DeviceBuffer wave, waveSort;       // walk state of the wavefront scheduler, radix-sort scratch
     unsigned int *hostLive = nullptr;      // pinned: live-walk counts read back every few rounds
-    cudaEvent_t evRound[2] = {nullptr, nullptr};
+    cudaEvent_t evRound[16] = {};          // two per slot group
+    cudaEvent_t evFork = nullptr;
+    cudaStream_t waveStreams[8] = {};      // streams of the slot groups 1.. (group 0 runs on the context's stream)
     int lastRounds = 0;
     int *hostStatus = nullptr; // pinned
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; // solve start | walk start | walk end | solve end

@@ -60,6 +60,11 @@ extern long long g_coopCount[10]; // [0] closest node items, [1] closest prims, 
 #define ZB_COOP_COUNT(i, n)
 #endif
 
+// debugging hook of tools/gpu_star_debug.cu: reports what lowers a given query's radius in the pooled phase
+#ifndef ZB_COOP_TRACE
+#define ZB_COOP_TRACE(owner, what, value, id)
+#endif
+
 #ifndef ZB_NODE_STACK
 #define ZB_NODE_STACK 1024
 #endif
@@ -72,9 +77,14 @@ extern long long g_coopCount[10]; // [0] closest node items, [1] closest prims, 
 constexpr int kNodeStack = ZB_NODE_STACK; // node items per warp; the top kNodeHeadroom are depth-first headroom
 constexpr int kNodeHeadroom = 128;
 constexpr int kPhase1Budget = ZB_PHASE1_BUDGET; // private stack pops per lane before the warp pools what is left
-constexpr int kRefillPerLane = 8;     // private stack entries a lane hands to the shared lists per refill
+#ifndef ZB_PRIM_QUEUE
+#define ZB_PRIM_QUEUE 1120
+#endif
+constexpr int kPrimQueue = ZB_PRIM_QUEUE; // primitive items per warp; 1120 >= 31 + 32 lanes x 8 leaves x 4 primitives + 63 survivors of the cheap stage (kept at the end)
+constexpr int kPrimSlack = 31 + 63;       // what the queue may hold when a node round or a refill starts: < 32 unfiltered items + the survivor list
+constexpr int kRefillPerLane = (kPrimQueue - kPrimSlack)/128 < 8 ? (kPrimQueue - kPrimSlack)/128 : 8; // private stack entries (<= 4 primitives each) a lane hands over per refill
 constexpr int kRefillLowWater = 192;  // refill when the shared node stack is below this
-constexpr int kPrimQueue = 1120;      // >= 31 + 32 lanes x 8 leaves x 4 primitives, + 63 survivors of the cheap stage (from the end)
+static_assert(kRefillPerLane >= 1 && kNodeStack >= kRefillLowWater + 32*kRefillPerLane, "work lists too small");
 constexpr uint32_t kPrimIndexMask = 0x03ffffffu; // 26 bits: up to 67 M primitives per boundary
 enum : int { kStatusCoopOverflow = 4 };
 
@@ -114,10 +124,11 @@ ZB_COOP int warpInclusiveSum(int v, int lane)
 // how many node items the next node round may pop: bounded by the room their children need on the node stack
 // (7 net entries per popped node) — the last kNodeHeadroom entries are reserved for the depth-first tail, where
 // one node is popped per round and the stack cannot grow by more than 7 per tree level
-ZB_COOP int coopNodeBudget(int nodeTop)
+ZB_COOP int coopNodeBudget(int nodeTop, int primTop, int fullTop)
 {
     int room = (kNodeStack - kNodeHeadroom - nodeTop)/7;
-    return min(min(nodeTop, 32), max(room, 1));
+    int primRoom = (kPrimQueue - primTop - fullTop)/32; // a node has at most 8 leaf children of 4 primitives
+    return min(min(nodeTop, 32), max(min(room, primRoom), 1));
 }
 
 // Appends the surviving children of this lane's node (keys[0..nKeep) ascending; low 3 bits = child slot) to the
@@ -285,7 +296,7 @@ ZB_COOP_NOINLINE void coopClosestPoint(const BvhView& bvh, WarpShared& ws, bool 
         }
 
         // ---- node round: one node per lane
-        int n = coopNodeBudget(nodeTop);
+        int n = coopNodeBudget(nodeTop, primTop, fullTop);
         if (lane == 0) { ZB_COOP_COUNT(0, n) ZB_COOP_COUNT(4, 1) }
         bool have = lane < n;
         uint2 item = make_uint2(0u, 0u);
@@ -372,6 +383,7 @@ ZB_COOP_NOINLINE float coopStarRadius2(const BvhView& bvh, WarpShared& ws, bool 
     ws.qy[lane] = x[1];
     ws.qz[lane] = DIM == 3 ? x[DIM - 1] : 0.0f;
     ws.best[lane] = packBest(r2own, 0u);
+    ZB_COOP_TRACE(lane, "phase-1 radius", r2own, sp)
     ws.flags[lane] = flip ? 1u : 0u;
     int nodeTop = 0, primTop = 0;
     // Two-stage primitive rounds (3D): a FILTER round pops 32 primitives and runs the cheap first stage of the test
@@ -401,7 +413,7 @@ ZB_COOP_NOINLINE float coopStarRadius2(const BvhView& bvh, WarpShared& ws, bool 
                 if (DIM == 3) q[DIM - 1] = ws.qz[owner];
                 r2 = primStarRadius2Call<DIM>(bvh.prims, bvh.adjacency, bvh.snchSign, item & kPrimIndexMask, q, r2, ws.flags[owner] != 0u,
                                               precision, silhouetteTests);
-                if (r2 < before) zb_atomic_min64(&ws.best[owner], packBest(r2, 0u));
+                if (r2 < before) { ZB_COOP_TRACE(owner, silhouetteTests ? "full-round primitive (silhouette tests on)" : "full-round primitive (no silhouette tests)", r2, item & kPrimIndexMask) ZB_COOP_TRACE(owner, "   ... its incoming radius", before, lane) ZB_COOP_TRACE(owner, "   ... query x", q[0], item) ZB_COOP_TRACE(owner, "   ... query y", q[1], ws.flags[owner]) ZB_COOP_TRACE(owner, "   ... query z", q[DIM - 1], fullTop) zb_atomic_min64(&ws.best[owner], packBest(r2, 0u)); }
             }
             fullTop -= n;
             zb_syncwarp();
@@ -441,7 +453,7 @@ ZB_COOP_NOINLINE float coopStarRadius2(const BvhView& bvh, WarpShared& ws, bool 
         }
 
         // ---- node round
-        int n = coopNodeBudget(nodeTop);
+        int n = coopNodeBudget(nodeTop, primTop, fullTop);
         if (lane == 0) { ZB_COOP_COUNT(2, n) ZB_COOP_COUNT(6, 1) }
         bool have = lane < n;
         uint2 item = make_uint2(0u, 0u);
@@ -486,6 +498,7 @@ ZB_COOP_NOINLINE float coopStarRadius2(const BvhView& bvh, WarpShared& ws, bool 
                     insertKey(keys, (zb_float_as_uint(lower) & ~63u) | (uint32_t)c);
                 }
                 if (shrink < r2) {
+                    ZB_COOP_TRACE(owner, "node upper bound", shrink, item.y)
                     zb_atomic_min64(&ws.best[owner], packBest(shrink, 0u));
                     r2 = shrink;
                 }

@@ -9,6 +9,11 @@
 
 #include "vec.cuh"
 
+// debugging hook of tools/gpu_star_debug.cu (reports the intermediate values of one primitive's star-radius test)
+#ifndef ZB_PRIM_TRACE
+#define ZB_PRIM_TRACE(prim, what, a, b, c, d)
+#endif
+
 namespace zb {
 
 struct BvhView {
@@ -870,6 +875,14 @@ ZB_DEV void primStarRadius2(const BvhView& bvh, uint32_t primIdx, const Vec<DIM>
                 float cosUpper = fabsf(xdot((x - closestPt)/closestDist, n0));
                 float cosLower = fabsf(xdot((x - far)/farDist, n0));
                 float radius = robinRadiusBound<DIM>(h, maxCoeff, cosLower, cosUpper);
+                ZB_PRIM_TRACE(primIdx, "exact reflectance: h cosLower cosUpper radius^2", h, cosLower, cosUpper, radius*radius)
+                // The radius is rho/(1 - cos/(mu rho)) >= rho >= closestDist for some point of the primitive. When x lies IN
+                // the primitive's plane, h and the cosines are rounding noise and the formula can return less than that —
+                // in the reference too, where such a primitive then lowers the radius or not depending on whether the
+                // traversal reaches it before or after r2 has fallen below closestDist^2 (the early exit above). Clamping
+                // restores the invariant, which makes the result independent of the visiting order (and of the scheduling
+                // of the cooperative traversal); it changes nothing unless the computed radius violates its own lower bound.
+                radius = fmaxf(radius, closestDist);
                 if (radius < kMaxFloat) r2 = fminf(r2, radius*radius);
             } else {
                 r2 = fminf(r2, closestDist2);
@@ -1083,19 +1096,23 @@ ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const V
                 float cosUpper = fabsf(xdot((x - closestPt)/closestDist, n0));
                 float farDist = sqrtf(far2);
                 float cosLower = fabsf(xdot(vfar/farDist, n0));
-                float radius = robinRadiusBound<3>(h, maxCoeff, cosLower, cosUpper);
+                float radius = fmaxf(robinRadiusBound<3>(h, maxCoeff, cosLower, cosUpper), closestDist); // see primStarRadius2
                 if (radius < kMaxFloat) r2 = fminf(r2, radius*radius);
                 // threshold maxCos >= cosLower, the conditioning h mu/(h mu - c^2) of the bound (robin_bounds.h:48-74), and the
-                // cancellation in cosUpper when x is nearly coplanar with the triangle (its value then sets the radius)
+                // cancellation in h and the cosines when x is nearly coplanar with the triangle (the radius is then h/c with both
+                // at rounding level: only the reference's own operation order reproduces the reference's value)
                 float hmu = h*maxCoeff, maxCos = sqrtf(hmu);
                 float c = clampLikeStd(maxCos/1.7320508075688772935f, cosLower, cosUpper);
-                redo = redo || fabsf(maxCos - cosLower) < 1e-5f || (maxCos >= cosLower && ((hmu - c*c) < 0.3f*hmu || (c == cosUpper && cosUpper < 0.05f)));
+                redo = redo || cosUpper < 0.05f || fabsf(maxCos - cosLower) < 1e-5f || (maxCos >= cosLower && (hmu - c*c) < 0.3f*hmu);
+                ZB_PRIM_TRACE(primIdx, "fast reflectance: h cosLower cosUpper radius^2", h, cosLower, cosUpper, radius*radius)
             } else {
                 r2 = fminf(r2, closestDist2);
             }
         }
     }
+    ZB_PRIM_TRACE(primIdx, "fast result before redo: r2in r2 redo cannotShrink", r2in, r2, redo ? 1.0f : 0.0f, robinCannotShrink ? 1.0f : 0.0f)
     if (redo) r2 = primStarRadius2Redo<3>(bvh.prims, bvh.adjacency, bvh.snchSign, primIdx, x, r2in, flip, precision, silhouetteTests);
+    ZB_PRIM_TRACE(primIdx, "final: r2 | query", r2, x[0], x[1], x[2])
     if (r2 < r2in) { ZB_CLASS(12) if (!silhouetteTests) { ZB_CLASS(13) } }
 }
 

@@ -385,6 +385,7 @@ struct Lane {
     bool firstStep, flip, outerFlip, success, active, gradient;
     bool needClosest; // distA / proj must be recomputed at st.pt before the walk continues
     bool keepDistA;   // ... but only proj is wanted: keep the caller-provided distA (sample point inside the epsilon shell)
+    bool projValid;   // proj is a point of the absorbing boundary (the last distance query found one)
     bool needsFinalProjection; // Walk on Spheres: the walk ran out of steps and proj is that of the previous position
 };
 
@@ -427,6 +428,7 @@ ZB_DEV void beginTask(const SolveArgs& a, Lane<DIM>& L, long long task)
     L.gradient = !a.rwsRecords && a.pts.estimationQuantity[i] == ZB_SOLUTION_AND_GRADIENT;
     L.needClosest = false;
     L.keepDistA = false;
+    L.projValid = false;
     L.needsFinalProjection = false;
 
     if (!L.gradient) {
@@ -540,16 +542,34 @@ ZB_DEV void beginTask(const SolveArgs& a, Lane<DIM>& L, long long task)
 // stepStarPrologue below), so all the walk needs to learn is whether it stands inside the absorbing epsilon shell:
 // the search stops at that radius ("nothing found" leaves distA at +inf, the projection unused). 17 % of the steps
 // of a C3-like solve and a tenth of its closest-point work (tools/host_probe.cu).
+//
+// Every other query is seeded with what the walk already knows: the closest point found at the previous position is a
+// point OF the absorbing boundary, so its distance from the new position bounds the new distance from above and the
+// traversal prunes with it from the root (ZB_SEEDED_CLOSEST; same results — the nearest primitive lies within the bound).
+#ifndef ZB_SEEDED_CLOSEST
+#define ZB_SEEDED_CLOSEST 1
+#endif
 template <int DIM, bool WOST>
 ZB_DEV float closestSearchRadius2(const SolveArgs& a, const Lane<DIM>& L)
 {
-    if (!WOST || !ZB_BOUNDED_CLOSEST || !a.hasReflecting) return kMaxFloat;
-    if (L.keepDistA || L.firstStep || !L.st.onRefl) return kMaxFloat;
-    if (!(a.ws.stepsBeforeUsingMaximalSpheres > L.st.walkLength)) return kMaxFloat; // the maximal-sphere step reads distA
+    float seeded = kMaxFloat;
+    if (ZB_SEEDED_CLOSEST && L.projValid && !L.keepDistA) {
+        // |pt - proj| cancels when the walk is close to the boundary (coordinates of order 1, distance of order 1e-3): the
+        // slack is absolute, a few ulps of the coordinates, on top of a relative one for the primitive test's own rounding
+        Vec<DIM> d = L.st.pt - L.proj;
+        float scale = 0.0f;
+#pragma unroll
+        for (int k = 0; k < DIM; k++) scale = fmaxf(scale, fmaxf(fabsf(L.st.pt[k]), fabsf(L.proj[k])));
+        float bound = sqrtf(dot(d, d))*1.0001f + 16.0f*kEpsilon*scale;
+        seeded = bound*bound;
+    }
+    if (!WOST || !ZB_BOUNDED_CLOSEST || !a.hasReflecting) return seeded;
+    if (L.keepDistA || L.firstStep || !L.st.onRefl) return seeded;
+    if (!(a.ws.stepsBeforeUsingMaximalSpheres > L.st.walkLength)) return seeded; // the maximal-sphere step reads distA
     PdeEval<DIM> pde{a.pde};
-    if (!pde.hasNonZeroRobinCoeff(L.st.pt)) return kMaxFloat;
+    if (!pde.hasNonZeroRobinCoeff(L.st.pt)) return seeded;
     float e = a.ws.epsilonShellForAbsorbingBoundary;
-    return e*e*1.0001f;
+    return fminf(seeded, e*e*1.0001f);
 }
 
 // thread-per-query resolution of a pending distance query (host probe; the kernel does it cooperatively)
@@ -558,6 +578,7 @@ ZB_DEV void resolveClosest(const SolveArgs& a, Lane<DIM>& L)
 {
     int projPrim;
     float d = distToAbsorbing<DIM>(a, L.st.pt, L.proj, projPrim, closestSearchRadius2<DIM, WOST>(a, L));
+    L.projValid = projPrim >= 0;
     if (!L.keepDistA) L.distA = d;
     L.needClosest = false;
     L.keepDistA = false;
@@ -920,6 +941,7 @@ __global__ void __launch_bounds__(128, ZB_WALK_MIN_BLOCKS) walkKernel(SolveArgs 
                 if (qc) {
                     if (!L.keepDistA) L.distA = hit.d;
                     L.proj = hit.p;
+                    L.projValid = hit.prim >= 0;
                     L.needClosest = false;
                     L.keepDistA = false;
                 }

@@ -32,7 +32,8 @@ namespace zb {
 enum : uint32_t {
     kWfActive = 1u, kWfNeedClosest = 2u, kWfKeepDistA = 4u, kWfFirstStep = 8u, kWfFlip = 16u, kWfOuterFlip = 32u,
     kWfSuccess = 64u, kWfGradient = 128u, kWfOnRefl = 256u, kWfYukawa = 512u, kWfNeedStar = 1024u, kWfReached = 2048u,
-    kWfFinalProjection = 4096u // Walk on Spheres ran out of steps: finish with kMaxLength once the projection of the last position is known
+    kWfFinalProjection = 4096u, // Walk on Spheres ran out of steps: finish with kMaxLength once the projection of the last position is known
+    kWfProjValid = 8192u        // projStar.xyz is a point of the absorbing boundary (seeds the next distance query)
 };
 
 struct WaveSlots {
@@ -48,7 +49,11 @@ struct WaveSlots {
     uint32_t *keys;       // Morton key per POSITION of the current order (written by waveStepKernel, sorted by cub)
     const uint32_t *order; // position -> slot
     unsigned int *live;   // walks alive after the current round
+    unsigned long long *taskCounter; // tasks this group has taken; the group owns the tasks first + k*stride
+    int taskFirst, taskStride;
     int nSlots;
+    int debugEscapes;     // ZB_WAVE_DEBUG=1: report walks that leave the bounding domain (device printf)
+    int sortMode;         // 0 fixed pseudo-random rank of the task (default), 1 Morton code of the position, 2 descending distance to the absorbing boundary
     float sortMin[3], sortScale[3];
 };
 
@@ -88,16 +93,32 @@ ZB_DEV uint32_t mortonKey(const WaveSlots& w, const Vec<DIM>& p)
 template <int DIM> ZB_DEV Vec<DIM> vec3of(const float4& v) { Vec<DIM> r; r[0] = v.x; r[1] = v.y; if (DIM == 3) r[DIM - 1] = v.z; return r; }
 template <int DIM> ZB_DEV float4 pack4(const Vec<DIM>& v, float w) { return make_float4(v[0], v[1], DIM == 3 ? v[DIM - 1] : 0.0f, w); }
 
+
+// Thread -> position of the slot order for the two query kernels: STRIPED, warp w of W takes the positions w, w + W, w + 2W, ...
+// Live walks sit at the front of the order, so while every slot holds a walk each warp gets 32 of them, and when a solve
+// runs out of tasks the remaining walks spread over all warps instead of filling a few: a warp with one or two queries
+// brings all 32 lanes to their traversal (coop.cuh pools the work), which is what the tail of a solve needs — compacting
+// the survivors into full warps would leave most SMs idle while a few warps grind through 32 heavy queries each.
+ZB_DEV int stripedPosition(int nWarps)
+{
+#if defined(__CUDA_ARCH__)
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    return (i & 31)*nWarps + (i >> 5);
+#else
+    return 0;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------
 // distance query + scalar prologue of the step
 // ------------------------------------------------------------------------------------------
 template <int DIM, bool WOST>
-__global__ void __launch_bounds__(128) waveClosestKernel(SolveArgs a, WaveSlots w, int nBound)
+__global__ void __launch_bounds__(128) waveClosestKernel(SolveArgs a, WaveSlots w, int nBound, int nWarps)
 {
 #if defined(__CUDA_ARCH__)
     extern __shared__ __align__(16) unsigned char zbShared[];
     WarpShared& ws = reinterpret_cast<WarpShared *>(zbShared)[threadIdx.x >> 5];
-    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    const int i = stripedPosition(nWarps);
     int slot = -1;
     int4 m = make_int4(0, 0, 0, 0);
     if (i < nBound) { slot = (int)w.order[i]; m = w.meta[slot]; }
@@ -115,16 +136,21 @@ __global__ void __launch_bounds__(128) waveClosestKernel(SolveArgs a, WaveSlots 
     L.firstStep = (flags & kWfFirstStep) != 0u;
     L.keepDistA = (flags & kWfKeepDistA) != 0u;
     L.flip = (flags & kWfFlip) != 0u;
+    L.projValid = (flags & kWfProjValid) != 0u;
 
     const bool qc = active && (flags & kWfNeedClosest) != 0u;
     if (__any_sync(0xffffffffu, qc)) {
+        float4 ps = qc ? w.projStar[slot] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        L.proj = vec3of<DIM>(ps);
         Vec<DIM> proj = L.st.pt;
+        bool found = false;
         if (a.hasAbsorbing) {
             ClosestHit<DIM> hit;
             coopClosestPoint<DIM>(a.absorbing, ws, qc, L.st.pt, qc ? closestSearchRadius2<DIM, WOST>(a, L) : 0.0f, hit, a.status);
             if (qc) {
                 if (!L.keepDistA) L.distA = hit.d;
                 proj = hit.p;
+                found = hit.prim >= 0;
             }
         } else if (qc) {
             // no absorbing boundary: default of GeometricQueries::populate (geometric_queries.h:213-218), as distToAbsorbing
@@ -134,10 +160,9 @@ __global__ void __launch_bounds__(128) waveClosestKernel(SolveArgs a, WaveSlots 
             if (!L.keepDistA) L.distA = sqrtf(s);
         }
         if (qc) {
-            flags &= ~(kWfNeedClosest | kWfKeepDistA);
+            flags = (flags & ~(kWfNeedClosest | kWfKeepDistA | kWfProjValid)) | (found ? kWfProjValid : 0u);
             pd.w = L.distA;
             w.ptDist[slot] = pd;
-            float4 ps = w.projStar[slot];
             w.projStar[slot] = pack4<DIM>(proj, ps.w);
         }
     }
@@ -179,12 +204,12 @@ __global__ void __launch_bounds__(128) waveClosestKernel(SolveArgs a, WaveSlots 
 // star radius
 // ------------------------------------------------------------------------------------------
 template <int DIM>
-__global__ void __launch_bounds__(128) waveStarKernel(SolveArgs a, WaveSlots w, int nBound)
+__global__ void __launch_bounds__(128) waveStarKernel(SolveArgs a, WaveSlots w, int nBound, int nWarps)
 {
 #if defined(__CUDA_ARCH__)
     extern __shared__ __align__(16) unsigned char zbShared[];
     WarpShared& ws = reinterpret_cast<WarpShared *>(zbShared)[threadIdx.x >> 5];
-    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    const int i = stripedPosition(nWarps);
     int slot = -1;
     uint32_t flags = 0u;
     if (i < nBound) { slot = (int)w.order[i]; flags = (uint32_t)w.meta[slot].w; }
@@ -243,6 +268,7 @@ ZB_DEV void loadLane(const SolveArgs& a, const WaveSlots& w, int slot, const int
     L.gradient = (flags & kWfGradient) != 0u;
     L.st.onRefl = (flags & kWfOnRefl) != 0u;
     L.needsFinalProjection = false;
+    L.projValid = (flags & kWfProjValid) != 0u;
     L.g.init((flags & kWfYukawa) != 0u, a.pde.absorptionCoeff);
     L.firstSource = 0.0f;
     L.gradBoundary = vzero<DIM>();
@@ -255,7 +281,8 @@ ZB_DEV uint32_t storeLane(const WaveSlots& w, int slot, const Lane<DIM>& L)
     uint32_t flags = kWfActive | (L.needClosest ? kWfNeedClosest : 0u) | (L.keepDistA ? kWfKeepDistA : 0u) |
                      (L.firstStep ? kWfFirstStep : 0u) | (L.flip ? kWfFlip : 0u) | (L.outerFlip ? kWfOuterFlip : 0u) |
                      (L.success ? kWfSuccess : 0u) | (L.gradient ? kWfGradient : 0u) | (L.st.onRefl ? kWfOnRefl : 0u) |
-                     (L.g.yukawa ? kWfYukawa : 0u) | (L.needsFinalProjection ? kWfFinalProjection : 0u);
+                     (L.g.yukawa ? kWfYukawa : 0u) | (L.needsFinalProjection ? kWfFinalProjection : 0u) |
+                     (L.projValid ? kWfProjValid : 0u);
     w.ptDist[slot] = pack4<DIM>(L.st.pt, L.distA);
     w.projStar[slot] = pack4<DIM>(L.proj, 0.0f);
     w.normalPrev[slot] = pack4<DIM>(L.st.normal, L.st.prevDist);
@@ -341,7 +368,13 @@ __global__ void __launch_bounds__(128) waveStepKernel(SolveArgs a, WaveSlots w, 
         } else if (flags & kWfReached) {
             finishStateWave<DIM, WOST>(a, L, kReached, queue);
         } else if (!L.needClosest) {
+            const Vec<DIM> ptBefore = L.st.pt;
+            const float distBefore = L.distA;
             StepResult r = stepBody<DIM, WOST>(a, L, queue, w.projStar[slot].w);
+            if (r == kEscaped && w.debugEscapes)
+                printf("escaped: task %lld point %d step %d from (%.9g %.9g %.9g) distA %.9g ball %.9g proj (%.9g %.9g %.9g) to (%.9g %.9g %.9g)\n", L.task, L.point,
+                       L.st.walkLength, ptBefore[0], ptBefore[1], DIM == 3 ? ptBefore[DIM - 1] : 0.0f, distBefore, L.g.R, L.proj[0], L.proj[1],
+                       DIM == 3 ? L.proj[DIM - 1] : 0.0f, L.st.pt[0], L.st.pt[1], DIM == 3 ? L.st.pt[DIM - 1] : 0.0f);
             // Walk on Spheres ends a walk that ran out of steps with the Dirichlet value at the projection of its LAST
             // position (walk_on_spheres.h:294-308): that projection is one more distance query (one round) away
             if (!WOST && r == kMaxLength && L.needsFinalProjection && a.hasAbsorbing && !a.ws.ignoreAbsorbingBoundaryContribution) {
@@ -358,9 +391,9 @@ __global__ void __launch_bounds__(128) waveStepKernel(SolveArgs a, WaveSlots w, 
     const unsigned need = __ballot_sync(full, want);
     if (need) {
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(a.taskCounter, (unsigned long long)__popc(need));
+        if (lane == 0) base = atomicAdd(w.taskCounter, (unsigned long long)__popc(need));
         base = __shfl_sync(full, base, 0);
-        long long task = (long long)base + __popc(need & ((1u << lane) - 1u));
+        long long task = ((long long)base + __popc(need & ((1u << lane) - 1u)))*w.taskStride + w.taskFirst;
         if (want && task < a.totalTasks) {
             beginTask<DIM, WOST>(a, L, task);
             if (L.gradient) storeGradientFactors<DIM>(a, L);
@@ -371,7 +404,11 @@ __global__ void __launch_bounds__(128) waveStepKernel(SolveArgs a, WaveSlots w, 
     if (slot >= 0) {
         if (L.active) {
             storeLane<DIM>(w, slot, L);
-            key = mortonKey<DIM>(w, L.st.pt);
+            // mode 0: a fixed pseudo-random rank per task (odd multiplier = bijection on 32 bits): which slot a task landed in
+            // depends on the order of the atomics above, the ORDER of the walks does not — warps are composed the same way
+            // on every run, which is what makes the cooperative queries, hence the estimates, repeatable bit for bit
+            key = w.sortMode == 2 ? (~zb_float_as_uint(fminf(L.distA, 1e30f)) & 0x7fffffffu)
+                : (w.sortMode == 1 ? mortonKey<DIM>(w, L.st.pt) : ((uint32_t)L.task*2654435761u) >> 1);
         } else if (flags & kWfActive) {
             m.w = 0;
             w.meta[slot] = m;

@@ -4,6 +4,7 @@ There is no CPU fallback: loading fails loudly when the CUDA library has not bee
 call raises ZombieError when the library reports an error (including "no CUDA device").
 """
 import ctypes as C
+import weakref
 import os
 
 import numpy as np
@@ -100,10 +101,13 @@ class Context:
 
     def __init__(self, device=0):
         self._h = C.c_void_p()
+        self._scenes = weakref.WeakSet()   # a scene must be destroyed before its context, whatever order the GC picks
         _check(lib().zb_context_create(device, C.byref(self._h)), "zb_context_create")
 
     def close(self):
         if self._h:
+            for s in list(self._scenes):
+                s.close()
             lib().zb_context_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -209,10 +213,12 @@ class Scene:
                                      int(solve_double_sided), silhouette_precision, int(watertight),
                                      abi.ptr(self.domain_min), abi.ptr(self.domain_max), C.byref(self._h)),
                "zb_scene_create")
+        ctx._scenes.add(self)
 
     def close(self):
         if self._h:
-            lib().zb_scene_destroy(self._h)
+            if self.ctx._h:   # (a closing context destroys its scenes first)
+                lib().zb_scene_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
