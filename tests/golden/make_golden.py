@@ -102,8 +102,8 @@ def solve_case(name, dim, estimator, kind, pde, settings, pts_xyz, n_walks, quan
 def solves():
     whole3, a3, r3 = cases.mesh3d(3)
     whole2, a2, r2 = cases.mesh2d(512)
-    x3 = cases.query_points(2048, 3, 0.7, seed=13)
-    x2 = cases.query_points(2048, 2, 0.6, seed=13)
+    x3 = cases.query_points(4096, 3, 0.7, seed=13)
+    x2 = cases.query_points(4096, 2, 0.6, seed=13)
     ws = abi.WalkSettings.default()
     solve_case("wos3d", 3, abi.WALK_ON_SPHERES, abi.REFLECTING_NONE, cases.quadratic_pde(), ws, x3, 128, abi.SOLUTION, whole3, None)
     solve_case("wos2d", 2, abi.WALK_ON_SPHERES, abi.REFLECTING_NONE, cases.quadratic_pde(dim=2), ws, x2, 128, abi.SOLUTION, whole2, None)

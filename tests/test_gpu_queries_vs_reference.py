@@ -43,9 +43,8 @@ def test_queries_match_compiled_reference(ctx, ref, dim, kind):
         #     reflectance_boundary_bvh/geometry.h:196-226) and can come out BELOW the primitive's own distance. Whether that
         #     value counts then depends on the visiting order: the primitive is skipped once the radius has fallen below
         #     its squared distance (geometry.h:179-182), so the reference's BVH, its Baseline and any other traversal may
-        #     each report a different radius. The device clamps the bound to the primitive's distance (queries.cuh), which
-        #     makes its result independent of the order; measured on the one such row in 2 x 10^5 queries, this agrees with
-        #     both reference traversals.
+        #     each report a different radius (the device keeps the reference's arithmetic and early exit, so it is one more
+        #     such traversal).
         rb = ref.RefScene(dim, use_baseline=True, **kw)
         base = rb.star_radius(x[bad], minr[bad], da[bad])
         rb.close()

@@ -876,13 +876,6 @@ ZB_DEV void primStarRadius2(const BvhView& bvh, uint32_t primIdx, const Vec<DIM>
                 float cosLower = fabsf(xdot((x - far)/farDist, n0));
                 float radius = robinRadiusBound<DIM>(h, maxCoeff, cosLower, cosUpper);
                 ZB_PRIM_TRACE(primIdx, "exact reflectance: h cosLower cosUpper radius^2", h, cosLower, cosUpper, radius*radius)
-                // The radius is rho/(1 - cos/(mu rho)) >= rho >= closestDist for some point of the primitive. When x lies IN
-                // the primitive's plane, h and the cosines are rounding noise and the formula can return less than that —
-                // in the reference too, where such a primitive then lowers the radius or not depending on whether the
-                // traversal reaches it before or after r2 has fallen below closestDist^2 (the early exit above). Clamping
-                // restores the invariant, which makes the result independent of the visiting order (and of the scheduling
-                // of the cooperative traversal); it changes nothing unless the computed radius violates its own lower bound.
-                radius = fmaxf(radius, closestDist);
                 if (radius < kMaxFloat) r2 = fminf(r2, radius*radius);
             } else {
                 r2 = fminf(r2, closestDist2);
@@ -1096,7 +1089,7 @@ ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const V
                 float cosUpper = fabsf(xdot((x - closestPt)/closestDist, n0));
                 float farDist = sqrtf(far2);
                 float cosLower = fabsf(xdot(vfar/farDist, n0));
-                float radius = fmaxf(robinRadiusBound<3>(h, maxCoeff, cosLower, cosUpper), closestDist); // see primStarRadius2
+                float radius = robinRadiusBound<3>(h, maxCoeff, cosLower, cosUpper);
                 if (radius < kMaxFloat) r2 = fminf(r2, radius*radius);
                 // threshold maxCos >= cosLower, the conditioning h mu/(h mu - c^2) of the bound (robin_bounds.h:48-74), and the
                 // cancellation in h and the cosines when x is nearly coplanar with the triangle (the radius is then h/c with both
