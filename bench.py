@@ -3,15 +3,18 @@
 (3D screened Poisson, Robin + Dirichlet boundary of a 1,310,720-triangle bumpy icosphere, WalkOnStars
 with gradient estimates, 1,048,576 evaluation points x 64 walks).
 
-A *step* is one zb_solve over one batch of --batch evaluation points of that workload (a different,
-contiguous slice of the 1M points each step). `value` is whole-job walk steps/s with the points already
-resident in HBM (zb_solve_dev); `e2e` is the same through the host-buffer C-ABI call zb_solve with the
-host<->device copies of every in/out array inside the timed region.
+A *step* is one zb_solve over one batch of --batch evaluation points of that workload per GPU (a different,
+contiguous slice of the rank's points each step; default 32,768 points = 2,097,152 walks per GPU per step).
+`value` is whole-job walk steps/s with the points already resident in HBM (zb_solve_dev); `e2e` is the same
+through the host-buffer C-ABI call zb_solve with the host<->device copies of every in/out array inside the
+timed region.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--scaling weak|strong]
 
-N > 1: launched under torchrun, one rank per GPU; the evaluation points are sharded over the ranks (the
-BVH is replicated), there is no data-path collective, timing is the max over ranks.
+N > 1: launched under torchrun, one rank per GPU; the evaluation points are sharded over the ranks (interleaved;
+the BVH is replicated) and every step ends with ONE collective inside the timed region, the NCCL all-gather of the
+per-point statistics (56 B/point) from the device buffers the solve wrote. Timing is the max over ranks; the
+spread of the per-rank kernel time (load imbalance) and the gather time are reported in `multi_gpu`.
 """
 import argparse
 import json
@@ -91,12 +94,25 @@ def ref_solve_sample(scene, w, idx):
     return scene.solve(w.estimator, w.pde, w.settings, pts, st, threads=0)
 
 
-def ref_sample_size(scene, w, target_s, cap):
-    """number of evaluation points the reference solves in about target_s seconds on this host (pilot run)"""
+def ref_sample_size(scene, w, target_s, cores, cap=16384):
+    """Evaluation points the reference solves in about target_s seconds on this host (pilot run), but at least 64 per
+    hardware thread where the time allows at least 24: walk lengths are geometric-tailed, and a handful of points per thread
+    leaves TBB's workers idle at the end of a solve (VERDICT r1 weak #9)."""
     rng = np.random.RandomState(321)
-    n0 = 64
+    n0 = 4*cores
     _, secs = ref_solve_sample(scene, w, np.sort(rng.choice(len(w.points), n0, replace=False)))
-    return int(min(cap, max(n0, n0*target_s/max(secs, 1e-3))))
+    n = int(n0*target_s/max(secs, 1e-3))
+    return int(min(cap, max(24*cores, min(n, 64*cores) if n < 64*cores else n)))
+
+
+def ref_builds():
+    """the reference builds this host can run: the parity build, and the -march=x86-64-v3 one (BASELINE.md §2 allows the
+    timed arm the vector ISA of a native Release build)"""
+    from oracle import ref
+    builds = [("", "-O3 -DNDEBUG")]
+    if ref.cpu_supports_v3() and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libzombie_ref_v3.so")):
+        builds.append(("v3", "-O3 -DNDEBUG -march=x86-64-v3"))
+    return builds
 
 
 def run_reference(args, rank, world):
@@ -107,10 +123,20 @@ def run_reference(args, rank, world):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libzombie_ref.so has not been built"}))
         return
     w = workloads.config3(args.subdiv, args.points, args.walks)
-    scene = ref.RefScene(3, **w.scene_kwargs())
     cores = ref.hardware_threads()
+    # pick the faster of the two builds on a short pilot, then time it
+    pilot = {}
+    idx0 = np.sort(np.random.RandomState(77).choice(len(w.points), 8*cores, replace=False))
+    scenes = {}
+    for name, flags in ref_builds():
+        ref.select_build(name)
+        scenes[name] = ref.RefScene(3, **w.scene_kwargs())
+        steps, secs = ref_solve_sample(scenes[name], w, idx0)
+        pilot[flags] = steps/secs
+    best = max(ref_builds(), key=lambda b: pilot[b[1]])
+    scene = scenes[best[0]]
     n_runs = args.warmup + args.steps
-    n = args.ref_points or ref_sample_size(scene, w, min(20.0, 150.0/max(1, n_runs)), 16384)
+    n = args.ref_points or ref_sample_size(scene, w, min(20.0, 240.0/max(1, n_runs)), cores)
     rng = np.random.RandomState(123)
     total_steps, total_secs = 0, 0.0
     for s in range(n_runs):
@@ -120,23 +146,47 @@ def run_reference(args, rank, world):
             total_steps += steps
             total_secs += secs
     value = total_steps/total_secs
-    sample = ("%d random evaluation points x %d walks of the workload per step, TBB default arena (%d threads), -O3 -DNDEBUG"
-              % (n, w.n_walks, cores))
+    sample = ("%d random evaluation points (%.0f per thread) x %d walks of the workload per step, TBB default arena (%d threads), %s"
+              % (n, n/float(cores), w.n_walks, cores, best[1]))
     print(json.dumps({
         "impl": "reference", "metric": "walk steps/sec", "value": value, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3*total_secs/args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w.name, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "reference", "sample": sample},
+        "config": {"workload": w.name},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "reference", "sample": sample,
+                         "builds_pilot_steps_per_s": pilot},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 # ------------------------------------------------------------------------------------------------
 # native arm
 # ------------------------------------------------------------------------------------------------
+POINT_KEYS = ("pt", "normal", "directionForDerivative", "type", "estimationQuantity", "distToAbsorbingBoundary",
+              "distToReflectingBoundary", "estimateBoundaryNormalAligned", "nWalks", "rngState", "rngInc", "firstSphereRadius")
+STAT_KEYS = ("solutionMean", "solutionM2", "gradientMean", "gradientM2", "totalFirstSourceContribution",
+             "totalDerivativeContribution", "nSolutionEstimates", "nGradientEstimates", "totalWalkLength", "totalSplits")
+
+# ncu evidence of the shipped kernels (profiles/r2_wave_steady_ncu.txt: --set full capture of one steady-state round of this
+# workload, 262,144 walks): DRAM bytes read + written per walk step, summed over the round's kernels; warp-issue and lane
+# statistics of the dominant kernel (waveStarKernel<3>, ~72 % of the step by the ncu launch list and by CUDA events)
+NCU_EVIDENCE = {
+    "profile": "profiles/r2_wave_steady_ncu.txt",
+    "dram_bytes_per_walk_step": None,
+    "dominant_kernel": "waveStarKernel<3>",
+}
+
+
+def load_ncu_evidence():
+    path = os.path.join(ROOT, "profiles", "r2_ncu_evidence.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            NCU_EVIDENCE.update(json.load(f))
+    return NCU_EVIDENCE
+
+
 def run_native(args, rank, world, local_rank):
     import torch
-    from zombie_b200 import native
+    from zombie_b200 import native, sharding
 
     dist = None
     if world > 1:
@@ -155,7 +205,7 @@ def run_native(args, rank, world, local_rank):
 
     # this rank's shard of the evaluation points (interleaved for load balance); distances to the two
     # boundaries are part of SamplePoint construction in the reference (demo.cpp:9-46) -> setup, untimed
-    shard = np.arange(rank, len(w.points), world)
+    shard = sharding.shard_indices(len(w.points), rank, world)
     n_steps = args.warmup + args.steps
     _, dist_a, _, _ = scene.closest_point(abi.ABSORBING, w.points, want_normal=False)
     _, dist_r, _, _ = scene.closest_point(abi.REFLECTING, w.points, want_normal=False)
@@ -168,57 +218,43 @@ def run_native(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    STAT_KEYS = ("solutionMean", "solutionM2", "gradientMean", "gradientM2", "totalFirstSourceContribution",
-                 "totalDerivativeContribution", "nSolutionEstimates", "nGradientEstimates", "totalWalkLength", "totalSplits")
-    POINT_KEYS = ("pt", "normal", "directionForDerivative", "type", "estimationQuantity", "distToAbsorbingBoundary",
-                  "distToReflectingBoundary", "estimateBoundaryNormalAligned", "nWalks", "rngState", "rngInc", "firstSphereRadius")
-
-    def device_set(idx, seed_base):
-        hp = make_points(w, idx, dist_a, dist_r, seed_base)
-        hs = abi.HostStatistics(hp.n, 3)
-        tensors = {}
-        for k in POINT_KEYS:
-            a = getattr(hp, k)
-            tensors[k] = to_dev(a.view(np.int64) if a.dtype == np.uint64 else a)
-        for k in STAT_KEYS:
-            tensors[k] = to_dev(getattr(hs, k))
-        tensors["steps"] = torch.zeros(1, dtype=torch.int64, device=dev)
-        ps = abi.SamplePoints(hp.n, *[tensors[k].data_ptr() for k in POINT_KEYS])
-        ss = abi.Statistics(*[tensors[k].data_ptr() for k in STAT_KEYS])
-        return ps, ss, tensors
-
-    # ---- batch size: the points one step solves. --batch 0 sizes it with a pilot solve so that a step takes
-    # about --step-seconds on this device (the persistent walk kernel wants >> 1 walk per lane, but the default
-    # run has to end within minutes whatever the kernel's speed)
-    batch = args.batch
-    pilot = None
-    if batch <= 0:
-        n_pilot = min(2048, len(shard))
-        ps, ss, tensors = device_set(shard[-n_pilot:], 7 << 40)
-        t0 = time.perf_counter()
-        scene.solve_dev(w.estimator, w.pde, w.settings, ps, ss, tensors["steps"].data_ptr())
-        torch.cuda.synchronize()
-        pilot_s = time.perf_counter() - t0
-        per_point_s = pilot_s/n_pilot
-        batch = int(args.step_seconds/max(per_point_s, 1e-9))
-        batch = 1 << max(13, min(16, int(math.floor(math.log2(max(batch, 1))))))
-        pilot = {"points": n_pilot, "seconds": pilot_s}
-    if dist is not None:  # every rank must use the same batch
-        t = torch.tensor([batch], dtype=torch.int64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        batch = int(t.item())
+    # ---- batch: the evaluation points one step solves per GPU ("weak": fixed per GPU; "strong": fixed in total)
+    batch = args.batch if args.scaling == "weak" else max(1, args.batch//world)
     batch = min(batch, len(shard))
 
     def batch_indices(s):
         start = (s*batch) % max(1, len(shard) - batch + 1)
         return shard[start:start + batch]
 
+    def device_set(idx, seed_base):
+        hp = make_points(w, idx, dist_a, dist_r, seed_base)
+        tensors = {}
+        for k in POINT_KEYS:
+            a = getattr(hp, k)
+            tensors[k] = to_dev(a.view(np.int64) if a.dtype == np.uint64 else a)
+        stats = sharding.DeviceStatistics(hp.n, 3, dev)          # one contiguous buffer: the gather is one collective
+        tensors["steps"] = torch.zeros(1, dtype=torch.int64, device=dev)
+        ps = abi.SamplePoints(hp.n, *[tensors[k].data_ptr() for k in POINT_KEYS])
+        return ps, stats.as_struct(), tensors, stats
+
+    gathered = torch.empty((world, (2 + 2*3 + 2 + 4)*batch), dtype=torch.float32, device=dev) if dist is not None else None
+
     # ---- device-resident arm --------------------------------------------------------------------
     dev_steps = [device_set(batch_indices(s), 0) for s in range(n_steps)]
+    gather_ev = []
 
-    def run_dev(s):
-        ps, ss, tensors = dev_steps[s]
+    def run_dev(s, timed=False):
+        ps, ss, tensors, stats = dev_steps[s]
         scene.solve_dev(w.estimator, w.pde, w.settings, ps, ss, tensors["steps"].data_ptr())
+        if dist is not None:
+            # the path's one collective: every rank ends with the statistics of all ranks' points (56 B/point), gathered
+            # from the device buffers zb_solve_dev wrote, NCCL over NVLink
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            stats.all_gather(gathered)
+            e1.record(stream)
+            if timed:
+                gather_ev.append((e0, e1))
 
     for s in range(args.warmup):
         run_dev(s)
@@ -227,102 +263,133 @@ def run_native(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    walk_ms, walk_tasks, grid = 0.0, 0, 0
+    walk_ms, walk_tasks, rounds = 0.0, 0, 0
     ev0.record(stream)
     for s in range(args.warmup, n_steps):
-        run_dev(s)
-        # the library brackets the walk kernel of every solve with CUDA events on the launching stream; reading
-        # them costs nothing here because zb_solve_dev has already waited for the solve's task count
+        run_dev(s, timed=True)
+        # the library brackets the walk phase of every solve with CUDA events on the launching stream
         prof = ctx.last_solve_profile()
         walk_ms += prof["walk_ms"]
         walk_tasks += prof["walks"]
-        grid = prof["walk_grid"]
     ev1.record(stream)
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     clocks = sampler.summary()
     launches_timed = ctx.last_solve_profile()["launches"] - launches_before
     steps_dev = int(sum(int(dev_steps[s][2]["steps"].item()) for s in range(args.warmup, n_steps)))
-    prof_steps, local_walk_ms = steps_dev, walk_ms  # this rank's kernel: its steps / its kernel time
+    gather_ms = float(sum(a.elapsed_time(b) for a, b in gather_ev))
+    prof_steps, local_walk_ms = steps_dev, walk_ms  # this rank's kernels: its steps / its kernel time
+    rmse_dev = float(np.sqrt(np.mean((dev_steps[-1][3].to_host().solutionMean - w.exact(w.points[batch_indices(n_steps - 1)]))**2)))
 
-    # ---- end-to-end arm: host buffers through zb_solve --------------------------------------------
-    # (at most 3 timed steps after 1 warm-up: the end-to-end arm repeats the device arm's work plus the copies, and the
-    # whole default run has to end within minutes)
+    # ---- end-to-end arm --------------------------------------------------------------------------
+    # N = 1: host buffers through zb_solve, the reference-facing call (copies inside the library, inside the timed region).
+    # N > 1: the same per rank, written out — pinned host inputs -> device, zb_solve_dev, all-gather of the statistics on the
+    # device, gathered statistics -> pinned host on every rank — because the gather has to sit between the solve and the
+    # read-back. (At most 3 timed steps after 1 warm-up: this arm repeats the device arm's work plus the copies.)
     e2e_warmup, e2e_steps = min(1, args.warmup), min(3, args.steps)
     host_sets = []
     for s in range(e2e_warmup + e2e_steps):
         hp = make_points(w, batch_indices(s), dist_a, dist_r, 1 << 40)
         hs = abi.HostStatistics(hp.n, 3)
-        # pinned host memory
-        for obj, keys in ((hp, ("pt", "normal", "directionForDerivative", "type", "estimationQuantity", "distToAbsorbingBoundary",
-                                "distToReflectingBoundary", "estimateBoundaryNormalAligned", "nWalks", "rngState", "rngInc",
-                                "firstSphereRadius")),
-                          (hs, ("solutionMean", "solutionM2", "gradientMean", "gradientM2", "totalFirstSourceContribution",
-                                "totalDerivativeContribution", "nSolutionEstimates", "nGradientEstimates", "totalWalkLength",
-                                "totalSplits"))):
+        for obj, keys in ((hp, POINT_KEYS), (hs, STAT_KEYS)):   # pinned host memory
             for k in keys:
                 a = getattr(obj, k)
                 v = a.view(np.int64) if a.dtype == np.uint64 else a
                 t = torch.from_numpy(v.copy()).pin_memory()
                 pinned = t.numpy()
                 setattr(obj, k, pinned.view(np.uint64) if a.dtype == np.uint64 else pinned)
-                obj.__dict__.setdefault("_keep", []).append(t)
+                obj.__dict__.setdefault("_keep", {})[k] = t
         host_sets.append((hp, hs))
     n, dim = host_sets[0][0].n, 3
-    h2d = n*(4*dim*3 + 4*6 + 1 + 8*2) + n*(4*2 + 4*dim*2 + 4*2 + 4*4)
-    d2h = n*(8 + 4) + n*(4*2 + 4*dim*2 + 4*2 + 4*4) + 8
+    in_bytes = n*(4*dim*3 + 4*6 + 1 + 8*2)
+    stat_bytes = n*(4*2 + 4*dim*2 + 4*2 + 4*4)
+    if dist is None:
+        h2d, d2h = in_bytes + stat_bytes, n*(8 + 4) + stat_bytes + 8   # zb_solve: points + statistics in; rng state, radius, statistics, step count out
+        e2e_path = "zb_solve on pinned host buffers (host<->device copies inside the call)"
+
+        def run_e2e(s):
+            return scene.solve(w.estimator, w.pde, w.settings, *host_sets[s])
+    else:
+        h2d, d2h = in_bytes, world*stat_bytes + 8
+        e2e_path = "pinned host inputs -> device, zb_solve_dev, NCCL all-gather of the statistics, all ranks' statistics -> pinned host"
+        dpts = {k: torch.empty_like(host_sets[0][0]._keep[k], device=dev) for k in POINT_KEYS}
+        dstats = sharding.DeviceStatistics(n, 3, dev)
+        dsteps = torch.zeros(1, dtype=torch.int64, device=dev)
+        host_gathered = torch.empty((world, dstats.words*n), dtype=torch.float32).pin_memory()
+        host_count = torch.zeros(1, dtype=torch.int64).pin_memory()
+        ps_e2e = abi.SamplePoints(n, *[dpts[k].data_ptr() for k in POINT_KEYS])
+
+        def run_e2e(s):
+            hp, _ = host_sets[s]
+            for k in POINT_KEYS:
+                dpts[k].copy_(hp._keep[k], non_blocking=True)
+            dstats.buf.zero_()
+            scene.solve_dev(w.estimator, w.pde, w.settings, ps_e2e, dstats.as_struct(), dsteps.data_ptr())
+            dstats.all_gather(gathered)
+            host_gathered.copy_(gathered, non_blocking=True)
+            host_count.copy_(dsteps, non_blocking=True)
+            torch.cuda.synchronize()
+            return int(host_count.item())
     for s in range(e2e_warmup):
-        scene.solve(w.estimator, w.pde, w.settings, *host_sets[s])
+        run_e2e(s)
     barrier()
     t0 = time.perf_counter()
     steps_e2e = 0
     for s in range(e2e_warmup, e2e_warmup + e2e_steps):
-        steps_e2e += scene.solve(w.estimator, w.pde, w.settings, *host_sets[s])
+        steps_e2e += run_e2e(s)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
 
-    # ---- reduce over ranks: max time, summed work -----------------------------------------------
+    # ---- reduce over ranks: max time, summed work, spread of the per-rank kernel time (load imbalance) ----
+    walk_ms_min = walk_ms_max = walk_ms
     if dist is not None:
-        t = torch.tensor([dev_ms, e2e_s, walk_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([dev_ms, e2e_s, walk_ms, gather_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s, walk_ms = [float(v) for v in t.tolist()]
-        c = torch.tensor([steps_dev, steps_e2e, prof_steps], dtype=torch.int64, device=dev)
+        dev_ms, e2e_s, walk_ms_max, gather_ms = [float(v) for v in t.tolist()]
+        t = torch.tensor([walk_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        walk_ms_min = float(t.item())
+        c = torch.tensor([steps_dev, steps_e2e], dtype=torch.int64, device=dev)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        steps_dev, steps_e2e, prof_steps_all = [int(v) for v in c.tolist()]
-    else:
-        prof_steps_all = prof_steps
-
-    # ---- parity smoke on the estimates of the last timed batch (exact solution is known) ----------
-    hp, hs = host_sets[-1]
-    rmse = float(np.sqrt(np.mean((hs.solutionMean - w.exact(hp.pt))**2)))
+        steps_dev, steps_e2e = [int(v) for v in c.tolist()]
 
     if rank == 0:
         peak, peak_kind = measured_peaks()
+        ev = load_ncu_evidence()
         bytes_per_step = w.algorithmic_bytes_per_step()
-        # per-rank kernel: this rank's steps / this rank's kernel time
+        # per-rank kernels: this rank's steps / this rank's kernel time
         achieved = prof_steps*bytes_per_step/(local_walk_ms*1e-3)/1e9 if local_walk_ms > 0 else 0.0
         value = steps_dev/(dev_ms*1e-3)
+        traffic = ev.get("dram_bytes_per_walk_step")
         line = {
             "metric": "walk steps/sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms/args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": dev_ms/args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": w.name, "points_per_step_per_gpu": batch, "batch_pilot": pilot, "walks_per_point": w.n_walks,
-                       "sharding": "evaluation points interleaved over ranks, BVH replicated, no data-path collective",
-                       "l2": "inputs larger than L2: BVH %.0f MB + %.0f MB of per-walk records per step"
-                             % ((scene.stats(0)["bytes"] + scene.stats(1)["bytes"])/1e6, walk_tasks/max(1, args.steps)*40/1e6),
-                       "bvh_build_s": build_s, "rmse_vs_exact_last_batch": rmse},
+            "config": {"workload": w.name, "points_per_step_per_gpu": batch, "walks_per_point": w.n_walks,
+                       "walks_per_step_per_gpu": walk_tasks//max(1, args.steps),
+                       "sharding": "evaluation points interleaved over ranks, BVH replicated; one NCCL all-gather of the per-point "
+                                   "statistics (56 B/point, device buffers) per step inside the timed region" if world > 1 else
+                                   "single GPU",
+                       "l2": "inputs larger than L2: BVH %.0f MB + %.0f MB of walk state and per-walk records per step"
+                             % ((scene.stats(0)["bytes"] + scene.stats(1)["bytes"])/1e6, (262144*128 + walk_tasks/max(1, args.steps)*40)/1e6),
+                       "bvh_build_s": build_s, "rmse_vs_exact_last_batch": rmse_dev, "e2e_path": e2e_path},
             "e2e": {"value": steps_e2e/e2e_s, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3*e2e_s/max(1, e2e_steps), "steps": e2e_steps},
             "gpu_launches": int(launches_timed),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak,
-                         "traffic": None, "peak_kind": peak_kind, "kernel": "walkKernel<3,true>", "grid": grid,
-                         "algorithmic_bytes_per_walk_step": bytes_per_step, "kernel_ms_per_step": walk_ms/args.steps,
-                         "kernel_share_of_step": walk_ms/dev_ms if dev_ms > 0 else None,
-                         "traffic_note": "ncu --set full of the round-1 kernel on a 512-point launch (profiles/README.md): 20 KB of "
-                                         "DRAM traffic and 44 K warp instructions per walk step, 54 % of stalls on instruction "
-                                         "fetch; issue/latency bound, not HBM bound (kernel reshaped since, not re-profiled)"},
+                         "traffic": None if traffic is None else traffic*prof_steps/max(1, args.steps),
+                         "peak_kind": peak_kind,
+                         "kernel": "one solve's wavefront rounds: waveClosestKernel + waveStarKernel + waveStepKernel (+ cub sort), then waveTailKernel",
+                         "per_launch": "one zb_solve_dev (= one step)",
+                         "algorithmic_bytes_per_walk_step": bytes_per_step, "dram_bytes_per_walk_step_ncu": traffic,
+                         "kernel_ms_per_step": local_walk_ms/args.steps,
+                         "kernel_share_of_step": local_walk_ms/dev_ms if dev_ms > 0 else None,
+                         "ncu": {k: v for k, v in ev.items() if k != "dram_bytes_per_walk_step"}},
         }
+        if world > 1:
+            line["multi_gpu"] = {"gather_ms_per_step": gather_ms/args.steps, "gather_bytes_per_step": world*stat_bytes,
+                                 "walk_ms_per_step_min_rank": walk_ms_min/args.steps, "walk_ms_per_step_max_rank": walk_ms_max/args.steps}
         if not args.no_cpu and world == 1:   # the CPU baseline is reported at N = 1 only
             line["cpu_baseline"] = cpu_baseline(args, w)
         print(json.dumps(line))
@@ -332,16 +399,27 @@ def run_native(args, rank, world, local_rank):
 
 
 def cpu_baseline(args, w):
-    """The reference's TBB CPU solver (oracle/_ref) on a bounded random sample of the same workload."""
+    """The reference's TBB CPU solver (oracle/_ref) on a bounded random sample of the same workload, both builds."""
     from oracle import ref
     if not ref.available():
         return {"value": None, "unit": "steps/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
-    scene = ref.RefScene(3, **w.scene_kwargs())
-    n = args.ref_points or ref_sample_size(scene, w, 20.0, 16384)
-    idx = np.sort(np.random.RandomState(123).choice(len(w.points), n, replace=False))
-    steps, secs = ref_solve_sample(scene, w, idx)
-    return {"value": steps/secs, "unit": "steps/s", "cores": ref.hardware_threads(), "kind": "reference",
-            "sample": "%d random evaluation points x %d walks of the workload (%.1f s), TBB default arena, -O3 -DNDEBUG" % (n, w.n_walks, secs)}
+    cores = ref.hardware_threads()
+    out = {}
+    n = None
+    for name, flags in ref_builds():
+        ref.select_build(name)
+        scene = ref.RefScene(3, **w.scene_kwargs())
+        if n is None:
+            n = args.ref_points or ref_sample_size(scene, w, 12.0, cores)
+        idx = np.sort(np.random.RandomState(123).choice(len(w.points), n, replace=False))
+        steps, secs = ref_solve_sample(scene, w, idx)
+        out[flags] = (steps/secs, secs)
+        scene.close()
+    best = max(out, key=lambda k: out[k][0])
+    return {"value": out[best][0], "unit": "steps/s", "cores": cores, "kind": "reference",
+            "sample": "%d random evaluation points (%.0f per thread) x %d walks of the workload (%.1f s), TBB default arena, %s"
+                      % (n, n/float(cores), w.n_walks, out[best][1], best),
+            "builds_steps_per_s": {k: v[0] for k, v in out.items()}}
 
 
 def main():
@@ -350,8 +428,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--batch", type=int, default=0, help="evaluation points per step per GPU (0: sized by a pilot solve)")
-    ap.add_argument("--step-seconds", type=float, default=8.0, help="target duration of one step when --batch is 0")
+    ap.add_argument("--batch", type=int, default=32768, help="evaluation points per step (per GPU when --scaling weak, in total when strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--subdiv", type=int, default=8, help="icosphere subdivisions (8 -> 1,310,720 triangles)")
     ap.add_argument("--points", type=int, default=1 << 20)
     ap.add_argument("--walks", type=int, default=64)

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define ZB_ABI_VERSION 1
+#define ZB_ABI_VERSION 2
 
 enum zb_status {
     ZB_OK = 0,
@@ -62,9 +62,24 @@ typedef struct zb_walk_settings {
     int32_t printLogs;
 } zb_walk_settings;
 
+/* Dense regular samples of one PDE callback over a box: how the reference's applications fill the four callbacks of
+ * zombie::PDE in practice (demo/model_problem.h:229-266 reads source / dirichlet / robin values from textures by
+ * uv = (x - bMin)/maxLength). `data` is DEVICE memory for zb_solve / zb_solve_dev / zb_rws_solve (upload with
+ * zb_grid_create); sample (i, j, k) is data[(k*shape[1] + j)*shape[0] + i] and sits at origin + (i, j, k)/invCell.
+ * interp 0: nearest sample (the demo's Image::get); 1: multilinear between the eight (four in 2D) surrounding samples;
+ * positions outside the box clamp to its faces. data == NULL: the callback falls back to `mode`. */
+enum zb_grid_interp { ZB_GRID_NEAREST = 0, ZB_GRID_LINEAR = 1 };
+typedef struct zb_grid_view {
+    const float *data;
+    int32_t shape[3];                    /* samples per axis; shape[2] = 1 in 2D */
+    int32_t interp;                      /* zb_grid_interp */
+    float origin[3];                     /* position of sample (0, 0, 0) */
+    float invCell[3];                    /* samples per unit length along each axis */
+} zb_grid_view;
+
 /* Data-described zombie::PDE (core/pde.h:20-45). std::function callbacks cannot run on the
- * device, so each callback is derived from a closed-form solution family (see
- * zombie_b200/analytic.h) or is a constant. */
+ * device, so each callback is a dense grid of samples when its zb_grid_view has data != NULL, and otherwise what `mode`
+ * says: derived from a closed-form solution family (see zombie_b200/analytic.h) or a constant. */
 enum zb_pde_mode { ZB_PDE_MANUFACTURED = 0, ZB_PDE_CONSTANT = 1 };
 typedef struct zb_pde_desc {
     float absorptionCoeff;               /* pde.h:26 */
@@ -80,6 +95,12 @@ typedef struct zb_pde_desc {
     float robinValue;                    /* CONSTANT mode: pde.robin */
     int32_t kelvin;                      /* 1: callbacks wrapped like KelvinTransform::transformPde (kelvin_transform.h:282-348) */
     float kelvinOrigin[3];
+    /* grids (pde.h:31-44 filled from sampled data, demo/model_problem.h:229-266); each optional */
+    zb_grid_view sourceGrid;             /* pde.source(x) */
+    zb_grid_view dirichletGrid;          /* pde.dirichlet(x, .): both sides of a double-sided absorbing boundary read the same data */
+    zb_grid_view robinGrid;              /* pde.robin(x, n, false) */
+    zb_grid_view robinAlignedGrid;       /* pde.robin(x, n, true): the normal-aligned side of a double-sided boundary; NULL = same as robinGrid */
+    zb_grid_view robinCoeffGrid;         /* pde.robinCoeff(x, n, .) */
 } zb_pde_desc;
 
 /* SoA mirror of std::vector<zombie::SamplePoint<float,DIM>> (common.h:152-195). rngState/rngInc
@@ -156,6 +177,15 @@ int zb_scene_create(zb_context *ctx, int dim,
 void zb_scene_destroy(zb_scene *scene);
 /* FcpwRobinBoundaryHandler::updateCoefficientValues (fcpw_geometric_queries.h:997-1010) */
 int zb_scene_update_robin_coefficients(zb_scene *scene, const float *minRobinCoeff, const float *maxRobinCoeff);
+
+/* ---- PDE data grids ------------------------------------------------------------------------
+ * Uploads shape[0]*shape[1]*shape[2] floats (x fastest) to the context's device and returns a handle; zb_grid_data
+ * is the device pointer to put into a zb_grid_view. Replaces the reference's texture-backed callbacks
+ * (demo/model_problem.h:229-266, demo/image.h). */
+typedef struct zb_grid zb_grid;
+int zb_grid_create(zb_context *ctx, const float *hostData, const int32_t shape[3], zb_grid **out);
+const float *zb_grid_data(const zb_grid *grid);
+void zb_grid_destroy(zb_grid *grid);
 /* bytes of device memory held by the scene's acceleration structures, and node counts */
 int zb_scene_stats(const zb_scene *scene, int boundary, int64_t *bytes, int32_t *nNodes, int32_t *nLeaves, int32_t *maxDepth);
 

@@ -14,6 +14,7 @@
 #pragma once
 
 #include <math.h>
+#include "../zombie_b200.h"
 
 #if defined(__CUDACC__)
 #define ZB_HD __host__ __device__ __forceinline__
@@ -87,4 +88,42 @@ ZB_HD zb_jet zb_eval_solution(int family, const float *p, const float *x)
     default: break;
     }
     return j;
+}
+
+// Sample of a zb_grid_view at x (x[2] ignored when shape[2] == 1). Shared by the device evaluator and the oracle's
+// std::function callbacks, so both sides read identical values. Nearest: the sample whose cell contains x, like the
+// reference demo's Image::get(uv) (demo/image.h); linear: multilinear between the surrounding samples. Positions outside
+// the box clamp to its faces.
+ZB_HD float zb_grid_sample(const zb_grid_view& g, const float *x)
+{
+    float t[3];
+    int i0[3], i1[3];
+    float w[3];
+    for (int k = 0; k < 3; k++) {
+        int n = g.shape[k];
+        if (n <= 1) { i0[k] = i1[k] = 0; w[k] = 0.0f; continue; }
+        t[k] = (x[k] - g.origin[k])*g.invCell[k];
+        if (g.interp == ZB_GRID_NEAREST) {
+            float r = floorf(t[k] + 0.5f);
+            r = r < 0.0f ? 0.0f : (r > (float)(n - 1) ? (float)(n - 1) : r);
+            i0[k] = i1[k] = (int)r;
+            w[k] = 0.0f;
+        } else {
+            float c = t[k] < 0.0f ? 0.0f : (t[k] > (float)(n - 1) ? (float)(n - 1) : t[k]);
+            float f = floorf(c);
+            int i = (int)f;
+            if (i > n - 2) i = n - 2;
+            i0[k] = i; i1[k] = i + 1;
+            w[k] = c - (float)i;
+        }
+    }
+    const int sx = g.shape[0], sxy = g.shape[0]*g.shape[1];
+    if (g.interp == ZB_GRID_NEAREST) return g.data[(long long)i0[2]*sxy + (long long)i0[1]*sx + i0[0]];
+    float acc = 0.0f;
+    for (int c = 0; c < 8; c++) {
+        int ix = (c & 1) ? i1[0] : i0[0], iy = (c & 2) ? i1[1] : i0[1], iz = (c & 4) ? i1[2] : i0[2];
+        float wt = ((c & 1) ? w[0] : 1.0f - w[0])*((c & 2) ? w[1] : 1.0f - w[1])*((c & 4) ? w[2] : 1.0f - w[2]);
+        if (wt != 0.0f) acc += wt*g.data[(long long)iz*sxy + (long long)iy*sx + ix];
+    }
+    return acc;
 }

@@ -158,6 +158,46 @@ inline pcg32 seedRng()
 }
 
 // ------------------------------------------------------------------------------------------------
+// Sampled PDE data: what the reference's applications put behind the PDE callbacks (demo/model_problem.h:229-266 reads
+// source / boundary values from textures). A DataGrid owns the samples on the host (for the std::function members) and
+// on the device (zb_grid, for the walk); share it between PDEs with shared_ptr and keep it alive while they are in use.
+// ------------------------------------------------------------------------------------------------
+class DataGrid {
+public:
+    // values: nx*ny*nz floats, x fastest (nz = 1 in 2D), covering the box [lo, hi] with both ends included
+    DataGrid(const std::vector<float>& values, int nx, int ny, int nz, const float lo[3], const float hi[3],
+             zb_grid_interp interp = ZB_GRID_LINEAR): host(values), holder(detail::context()) {
+        if ((size_t)nx*(size_t)ny*(size_t)nz != values.size()) throw Error(ZB_ERR_INVALID_ARGUMENT, "DataGrid: size mismatch");
+        int32_t shape[3] = {nx, ny, nz};
+        detail::check(zb_grid_create(holder->ctx, host.data(), shape, &grid));
+        std::memset(&hostView, 0, sizeof(hostView));
+        for (int k = 0; k < 3; k++) {
+            hostView.shape[k] = shape[k];
+            hostView.origin[k] = lo[k];
+            hostView.invCell[k] = shape[k] > 1 ? (float)(shape[k] - 1)/(hi[k] - lo[k]) : 0.0f;
+        }
+        hostView.interp = (int32_t)interp;
+        hostView.data = host.data();
+        deviceView = hostView;
+        deviceView.data = zb_grid_data(grid);
+    }
+    ~DataGrid() { zb_grid_destroy(grid); }
+    DataGrid(const DataGrid&) = delete;
+    DataGrid& operator=(const DataGrid&) = delete;
+    template <size_t DIM> float operator()(const Vector<DIM>& x) const {
+        float xx[3] = {x[0], x[1], DIM == 3 ? x[DIM - 1] : 0.0f};
+        return zb_grid_sample(hostView, xx);
+    }
+    const zb_grid_view& device() const { return deviceView; }
+private:
+    std::vector<float> host;
+    std::shared_ptr<detail::ContextHolder> holder;
+    zb_grid *grid = nullptr;
+    zb_grid_view hostView, deviceView;
+};
+enum class PdeData { Source, Dirichlet, Robin, RobinNormalAligned, RobinCoeff };
+
+// ------------------------------------------------------------------------------------------------
 // PDE (zombie/core/pde.h:20-79)
 // ------------------------------------------------------------------------------------------------
 template <typename T, size_t DIM>
@@ -176,6 +216,7 @@ struct PDE {
         source = o.source; dirichlet = o.dirichlet; robin = o.robin; robinCoeff = o.robinCoeff;
         hasReflectingBoundaryConditions = o.hasReflectingBoundaryConditions;
         description = o.description; described = o.described;
+        for (int k = 0; k < 5; k++) grids[k] = o.grids[k];
         bindHasNonZeroRobinCoeff(); // captures `this` (pde.h:60)
         return *this;
     }
@@ -220,6 +261,20 @@ struct PDE {
         described = true;
         bindCallbacks();
     }
+    // Backs one callback with sampled data (takes precedence over setManufactured()/setConstant() for that callback; a PDE
+    // posed only through grids needs neither). Robin data for the normal-aligned side of a double-sided boundary goes to
+    // RobinNormalAligned.
+    void setGrid(PdeData which, std::shared_ptr<const DataGrid> grid) {
+        if (!described) { std::memset(&description, 0, sizeof(description)); description.mode = ZB_PDE_CONSTANT; }
+        grids[(int)which] = grid;
+        zb_grid_view *views[5] = {&description.sourceGrid, &description.dirichletGrid, &description.robinGrid,
+                                  &description.robinAlignedGrid, &description.robinCoeffGrid};
+        if (grid) *views[(int)which] = grid->device(); else std::memset(views[(int)which], 0, sizeof(zb_grid_view));
+        if (which == PdeData::Source && grid) isSourceConstant = false;
+        if (which == PdeData::RobinCoeff && grid) areRobinConditionsPureNeumann = false;
+        described = true;
+        bindCallbacks();
+    }
     bool isDescribed() const { return described; }
     // the descriptor handed to zb_solve, with the public flags folded in
     zb_pde_desc descriptor() const {
@@ -236,6 +291,7 @@ struct PDE {
 private:
     zb_pde_desc description;
     bool described;
+    std::shared_ptr<const DataGrid> grids[5]; // indexed by PdeData
 
     zb_jet jet(const Vector<DIM>& x) const {
         float xx[3] = {x[0], x[1], DIM == 3 ? x[DIM - 1] : 0.0f};
@@ -243,22 +299,29 @@ private:
     }
     void bindCallbacks() {
         source = [this](const Vector<DIM>& x) -> T {
+            if (grids[(int)PdeData::Source]) return (*grids[(int)PdeData::Source])(x);
             if (description.mode == ZB_PDE_CONSTANT) return description.sourceValue;
             zb_jet j = jet(x);
             return absorptionCoeff*j.u - j.lap;
         };
         dirichlet = [this](const Vector<DIM>& x, bool) -> T {
+            if (grids[(int)PdeData::Dirichlet]) return (*grids[(int)PdeData::Dirichlet])(x);
             if (description.mode == ZB_PDE_CONSTANT) return description.dirichletValue;
             return jet(x).u;
         };
-        robin = [this](const Vector<DIM>& x, const Vector<DIM>& n, bool) -> T {
+        robin = [this](const Vector<DIM>& x, const Vector<DIM>& n, bool aligned) -> T {
+            if (aligned && grids[(int)PdeData::RobinNormalAligned]) return (*grids[(int)PdeData::RobinNormalAligned])(x);
+            if (grids[(int)PdeData::Robin]) return (*grids[(int)PdeData::Robin])(x);
             if (description.mode == ZB_PDE_CONSTANT) return description.robinValue;
             zb_jet j = jet(x);
             float dn = 0.0f;
             for (size_t k = 0; k < DIM; k++) dn += n[k]*j.g[k];
-            return dn + description.robinCoeff*j.u;
+            return dn + this->robinCoeff(x, n, aligned)*j.u;
         };
-        robinCoeff = [this](const Vector<DIM>&, const Vector<DIM>&, bool) -> float { return description.robinCoeff; };
+        robinCoeff = [this](const Vector<DIM>& x, const Vector<DIM>&, bool) -> float {
+            if (grids[(int)PdeData::RobinCoeff]) return (*grids[(int)PdeData::RobinCoeff])(x);
+            return description.robinCoeff;
+        };
     }
     void bindHasNonZeroRobinCoeff() {
         if (described) bindCallbacks();

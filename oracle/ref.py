@@ -18,6 +18,27 @@ def available():
     return os.path.exists(_LIB_PATH)
 
 
+def cpu_supports_v3():
+    """AVX2 + FMA + BMI2 on this host (what oracle/_ref/libzombie_ref_v3.so was compiled for)"""
+    try:
+        flags = open("/proc/cpuinfo").read()
+    except OSError:
+        return False
+    return all((" " + f + " ") in flags.replace("\n", " ") for f in ("avx2", "fma", "bmi2"))
+
+
+def select_build(name):
+    """Timed CPU arm only: "" = the parity build (-O3 -DNDEBUG), "v3" = the same sources with -march=x86-64-v3. Scenes made
+    before the switch keep their library."""
+    global _lib, _LIB_PATH
+    path = os.path.join(_HERE, "_ref", "libzombie_ref%s.so" % ("_" + name if name else ""))
+    if not os.path.exists(path):
+        return False
+    if path != _LIB_PATH:
+        _LIB_PATH, _lib = path, None
+    return True
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -141,7 +162,8 @@ class RefScene:
         self.domain_min, self.domain_max = _f32(domain_min), _f32(domain_max)
         mn = _f32(min_robin) if min_robin is not None else np.zeros(len(ri), np.float32)
         mx = _f32(max_robin) if max_robin is not None else np.zeros(len(ri), np.float32)
-        self._h = lib().zref_scene_create(dim, abi.ptr(ap), len(ap), abi.ptr(ai), len(ai),
+        self._lib = lib()
+        self._h = self._lib.zref_scene_create(dim, abi.ptr(ap), len(ap), abi.ptr(ai), len(ai),
                                           abi.ptr(rp), len(rp), abi.ptr(ri), len(ri),
                                           reflecting_kind, abi.ptr(mn), abi.ptr(mx),
                                           int(solve_double_sided), silhouette_precision,
@@ -150,7 +172,7 @@ class RefScene:
 
     def close(self):
         if self._h:
-            lib().zref_scene_destroy(self._h)
+            self._lib.zref_scene_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -166,7 +188,7 @@ class RefScene:
         dist = np.zeros(n, np.float32)
         pt = np.zeros((n, self.dim), np.float32)
         nrm = np.zeros((n, self.dim), np.float32) if want_normal else None
-        rc = lib().zref_closest_point(self._h, which, n, abi.ptr(x), abi.ptr(_f32(max_radius)),
+        rc = self._lib.zref_closest_point(self._h, which, n, abi.ptr(x), abi.ptr(_f32(max_radius)),
                                       abi.ptr(prim), abi.ptr(dist), abi.ptr(pt), abi.ptr(nrm), threads)
         assert rc == 0
         return prim, dist, pt, nrm
@@ -178,7 +200,7 @@ class RefScene:
         dist = np.zeros(n, np.float32)
         pt = np.zeros((n, self.dim), np.float32)
         nrm = np.zeros((n, self.dim), np.float32)
-        rc = lib().zref_intersect_ray(self._h, which, n, abi.ptr(o), abi.ptr(d), abi.ptr(_f32(tmax)),
+        rc = self._lib.zref_intersect_ray(self._h, which, n, abi.ptr(o), abi.ptr(d), abi.ptr(_f32(tmax)),
                                       abi.ptr(prim), abi.ptr(dist), abi.ptr(pt), abi.ptr(nrm), threads)
         assert rc == 0
         return prim, dist, pt, nrm
@@ -186,7 +208,7 @@ class RefScene:
     def occluded(self, which, a, b, threads=0):
         a, b = _f32(a), _f32(b)
         out = np.zeros(len(a), np.uint8)
-        rc = lib().zref_occluded(self._h, which, len(a), abi.ptr(a), abi.ptr(b), abi.ptr(out), threads)
+        rc = self._lib.zref_occluded(self._h, which, len(a), abi.ptr(a), abi.ptr(b), abi.ptr(out), threads)
         assert rc == 0
         return out
 
@@ -197,7 +219,7 @@ class RefScene:
         pt = np.zeros((n, self.dim), np.float32)
         nrm = np.zeros((n, self.dim), np.float32)
         pdf = np.zeros(n, np.float32)
-        rc = lib().zref_sample_sphere(self._h, n, abi.ptr(x), abi.ptr(radius), abi.ptr(u),
+        rc = self._lib.zref_sample_sphere(self._h, n, abi.ptr(x), abi.ptr(radius), abi.ptr(u),
                                       abi.ptr(prim), abi.ptr(pt), abi.ptr(nrm), abi.ptr(pdf), threads)
         assert rc == 0
         return prim, pt, nrm, pdf
@@ -206,7 +228,7 @@ class RefScene:
         x, mn, mx = _f32(x), _f32(min_radius), _f32(max_radius)
         out = np.zeros(len(x), np.float32)
         fl = None if flip is None else np.ascontiguousarray(flip, np.uint8)
-        rc = lib().zref_star_radius(self._h, len(x), abi.ptr(x), abi.ptr(mn), abi.ptr(mx), precision,
+        rc = self._lib.zref_star_radius(self._h, len(x), abi.ptr(x), abi.ptr(mn), abi.ptr(mx), precision,
                                     abi.ptr(fl), abi.ptr(out), threads)
         assert rc == 0
         return out
@@ -217,7 +239,7 @@ class RefScene:
         counts = np.zeros(5, np.int32)
         secs = C.c_double(0.0)
         ss, es = samples.as_struct(), eval_pts.as_struct()
-        rc = lib().zref_rws_solve(self._h, C.byref(pde), C.byref(settings), C.byref(ss), normal_offset, radius_clamp,
+        rc = self._lib.zref_rws_solve(self._h, C.byref(pde), C.byref(settings), C.byref(ss), normal_offset, radius_clamp,
                                   kernel_regularization, C.byref(es), threads, abi.ptr(counts), C.byref(secs))
         assert rc == 0
         return counts, secs.value
@@ -228,7 +250,7 @@ class RefScene:
         steps = C.c_int64(0)
         secs = C.c_double(0.0)
         ps, ss = pts.as_struct(), stats.as_struct()
-        rc = lib().zref_solve(self._h, estimator, C.byref(pde), C.byref(settings), C.byref(ps), C.byref(ss),
+        rc = self._lib.zref_solve(self._h, estimator, C.byref(pde), C.byref(settings), C.byref(ps), C.byref(ss),
                               C.byref(steps), threads, C.byref(secs))
         assert rc == 0
         return steps.value, secs.value

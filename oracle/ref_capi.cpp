@@ -151,6 +151,31 @@ void buildPde(const zb_pde_desc& d, PDE<float, DIM>& pde)
     }
     pde.robinCoeff = [desc](const Vec<DIM>&, const Vec<DIM>&, bool) -> float { return desc.robinCoeff; };
     pde.hasReflectingBoundaryConditions = [](const Vec<DIM>&) -> bool { return true; };
+
+    // callbacks backed by sampled data (zb_grid_view with HOST pointers here), the way the reference's demo fills a PDE
+    // from textures (demo/model_problem.h:229-266); same sampler as the device (zombie_b200/analytic.h: zb_grid_sample)
+    auto at = [](const zb_grid_view& g, const Vec<DIM>& x) -> float {
+        float xx[3] = {0, 0, 0}; for (size_t i = 0; i < DIM; i++) xx[i] = x[i];
+        return zb_grid_sample(g, xx);
+    };
+    if (d.robinCoeffGrid.data) {
+        pde.robinCoeff = [desc, at](const Vec<DIM>& x, const Vec<DIM>&, bool) -> float { return at(desc.robinCoeffGrid, x); };
+        if (d.mode == ZB_PDE_MANUFACTURED && !d.robinGrid.data) {
+            pde.robin = [desc, at](const Vec<DIM>& x, const Vec<DIM>& n, bool) -> float {
+                float xx[3] = {0, 0, 0}; for (size_t i = 0; i < DIM; i++) xx[i] = x[i];
+                zb_jet j = zb_eval_solution(desc.family, desc.params, xx);
+                float dn = 0.0f; for (size_t i = 0; i < DIM; i++) dn += n[i]*j.g[i];
+                return dn + at(desc.robinCoeffGrid, x)*j.u;
+            };
+        }
+    }
+    if (d.sourceGrid.data) pde.source = [desc, at](const Vec<DIM>& x) -> float { return at(desc.sourceGrid, x); };
+    if (d.dirichletGrid.data) pde.dirichlet = [desc, at](const Vec<DIM>& x, bool) -> float { return at(desc.dirichletGrid, x); };
+    if (d.robinGrid.data) {
+        pde.robin = [desc, at](const Vec<DIM>& x, const Vec<DIM>&, bool aligned) -> float {
+            return at(aligned && desc.robinAlignedGrid.data ? desc.robinAlignedGrid : desc.robinGrid, x);
+        };
+    }
 }
 
 WalkSettings toSettings(const zb_walk_settings& w)

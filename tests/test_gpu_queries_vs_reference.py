@@ -59,3 +59,57 @@ def test_queries_match_compiled_reference(ctx, ref, dim, kind):
     assert np.mean(rel_err(rr, gr)[~bad] <= 1e-4) > 0.99   # the Robin radius bound h^2 mu/(c(h mu - c^2)) amplifies float rounding
     assert (rr < 0.999*da).mean() > 0.01   # the query is exercised: some radii are limited by silhouettes / reflectance
     rs.close(); gs.close()
+
+
+def test_full_size_mesh_matches_compiled_reference(ctx, ref):
+    """The BASELINE headline geometry itself — the 1,310,720-triangle bumpy icosphere of config C3, Robin z > 0 /
+    Dirichlet z < 0 — against the compiled reference: 20,000 queries of every kind (closest point on both boundaries, first
+    hit, occlusion, Robin star radius) and a 256-point x 16-walk solve, with the device status word clean afterwards (no work
+    list or traversal stack overflowed in the pooled phase, which is exercised hardest at this size).
+    Mirrors deps/fcpw/tests/aggregate_tests.cpp:393,411,486,562,610 at the benchmark's size."""
+    from zombie_b200 import workloads
+    nq = 20000
+    w = workloads.config3(subdivisions=8, n_points=256, n_walks=16)
+    kw = w.scene_kwargs()
+    assert len(kw["absorbing"][1]) + len(kw["reflecting"][1]) == 1310720
+    rs, gs = ref.RefScene(3, **kw), native.Scene(ctx, 3, **kw)
+    x = cases.query_points(nq, 3, 0.95, seed=141)
+    o, d, tmax = cases.rays(nq, 3, 0.8, seed=143)
+    for which in (abi.ABSORBING, abi.REFLECTING):
+        check_closest(rs.closest_point(which, x), gs.closest_point(which, x), x)
+        check_rays(rs.intersect_ray(which, o, d, tmax), gs.intersect_ray(which, o, d, tmax))
+        b = o + d*tmax[:, None]
+        assert np.array_equal(rs.occluded(which, o, b), gs.occluded(which, o, b))
+    _, da, _, _ = rs.closest_point(abi.ABSORBING, x)
+    minr = np.full(nq, 1e-3, np.float32)
+    rr, gr = rs.star_radius(x, minr, da), gs.star_radius(x, minr, da)
+    tol = 1e-3*max(1.0, float(rr.max()))
+    bad = np.abs(rr - gr) > tol
+    if bad.any():   # the two causes asserted row by row in test_queries_match_compiled_reference
+        rb = ref.RefScene(3, use_baseline=True, **kw)
+        base = rb.star_radius(x[bad], minr[bad], da[bad])
+        rb.close()
+        by_baseline = np.abs(base - gr[bad]) <= 1e-5*max(1.0, float(rr.max()))
+        rp, ri = kw["reflecting"]
+        coplanar = np.array([cases.coplanar_primitive_within(rp.astype(np.float64), ri, x[i].astype(np.float64), 1.1*max(rr[i], gr[i]), 1e-6)
+                             for i in np.where(bad)[0]], bool)
+        assert (by_baseline | coplanar).all(), (x[bad], rr[bad], gr[bad], base)
+        assert bad.sum() <= 4
+    assert np.mean(rel_err(rr, gr)[~bad] <= 1e-4) > 0.99
+    assert (rr < 0.999*da).mean() > 0.01
+
+    # a short solve on the same scene: estimates within 3 standard errors of the reference's, same walk lengths
+    _, pa, _, _ = gs.closest_point(abi.ABSORBING, w.points)
+    _, pr, _, _ = gs.closest_point(abi.REFLECTING, w.points)
+    res = []
+    for solver, seed in ((gs, 0xBEEF), (rs, 0xF00D)):
+        pts = abi.HostSamplePoints(w.points, pa, pr, nWalks=w.n_walks, estimationQuantity=abi.SOLUTION, seed=seed)
+        st = abi.HostStatistics(pts.n, 3)
+        out = solver.solve(w.estimator, w.pde, w.settings, pts, st)
+        res.append((st, out if np.isscalar(out) else out[0]))
+    z = cases.z_scores(res[0][0], res[1][0])
+    assert np.mean(np.abs(z) < 3.0) >= 0.98 and abs(z.mean()) < 0.25, (np.mean(np.abs(z) < 3.0), z.mean())
+    assert abs(res[0][1]/float(res[1][1]) - 1.0) < 0.1
+    # every call above returned ZB_OK: the C ABI reads the device status word after each entry point and fails with
+    # "traversal stack overflow" / "cooperative traversal stack overflow" when a kernel raised it (capi.cu: checkStatus)
+    rs.close(); gs.close()

@@ -56,6 +56,19 @@ def _worker(rank, world, port, n, out):
     idx = sharding.shard_indices(n, rank, world)
     st = _solve(points, idx, 8)
     full = sharding.gather_statistics(st, n, 3, rank, world, device="cpu")
+    # the device-resident form of the same gather (bench.py --gpus N: one all_gather_into_tensor on the buffer zb_solve_dev
+    # wrote), here on CPU tensors: every rank pads its shard to the common shard size
+    pad = sharding.shard_size(n, world)
+    ds = sharding.DeviceStatistics(pad, 3, "cpu")
+    for k in sharding.STAT_FLOAT_KEYS + sharding.STAT_INT_KEYS:
+        ds.view(k)[:len(idx)] = torch.from_numpy(np.ascontiguousarray(getattr(st, k)))
+    gathered = ds.all_gather()
+    assert gathered.shape == (world, ds.words*pad) and ds.words*4 == 56
+    for r in range(world):
+        ridx = sharding.shard_indices(n, r, world)
+        part = ds.to_host(gathered[r])
+        for k in sharding.STAT_FLOAT_KEYS + sharding.STAT_INT_KEYS:
+            assert np.array_equal(getattr(part, k)[:len(ridx)], getattr(full, k)[ridx]), k
     if rank == 0:
         np.savez(out, mean=full.solutionMean, m2=full.solutionM2, n=full.nSolutionEstimates, wl=full.totalWalkLength)
     dist.barrier()

@@ -50,6 +50,51 @@ class WalkSettings(C.Structure):
         return s
 
 
+GRID_NEAREST, GRID_LINEAR = 0, 1
+
+
+class GridView(C.Structure):
+    """zb_grid_view: dense regular samples of one PDE callback; data is a device pointer for the product (native.Grid),
+    a host pointer for the test oracle."""
+    _fields_ = [("data", C.c_void_p), ("shape", C.c_int32 * 3), ("interp", C.c_int32),
+                ("origin", C.c_float * 3), ("invCell", C.c_float * 3)]
+
+
+class HostGrid:
+    """Samples of a callback on a regular lattice over [lo, hi] (both ends included): values[k, j, i] at
+    lo + (i, j, k)*(hi - lo)/(shape - 1); a 2D grid has shape (1, ny, nx)."""
+
+    def __init__(self, values, lo, hi, interp=GRID_LINEAR):
+        v = np.ascontiguousarray(values, np.float32)
+        if v.ndim == 2:
+            v = v[None]
+        self.values = v
+        self.interp = interp
+        self.lo = [float(t) for t in lo] + [0.0]*(3 - len(lo))
+        self.hi = [float(t) for t in hi] + [0.0]*(3 - len(hi))
+
+    @classmethod
+    def sample(cls, fn, lo, hi, shape, interp=GRID_LINEAR):
+        """tabulates fn(points [n, dim]) -> [n] on the lattice; shape = (nx, ny[, nz])"""
+        axes = [np.linspace(lo[k], hi[k], shape[k], dtype=np.float64) for k in range(len(shape))]
+        mesh = np.meshgrid(*axes, indexing="ij")                   # [nx, ny(, nz)]
+        pts = np.stack([m.ravel() for m in mesh], axis=1).astype(np.float32)
+        vals = np.asarray(fn(pts), np.float32).reshape([len(a) for a in axes])
+        vals = vals.transpose(*reversed(range(vals.ndim)))          # -> [(nz,) ny, nx]: x fastest
+        return cls(vals, lo, hi, interp)
+
+    def view(self, data_ptr=None):
+        g = GridView()
+        g.data = self.values.ctypes.data if data_ptr is None else data_ptr
+        nz, ny, nx = self.values.shape
+        for k, n in enumerate((nx, ny, nz)):
+            g.shape[k] = n
+            g.origin[k] = self.lo[k]
+            g.invCell[k] = (n - 1)/(self.hi[k] - self.lo[k]) if n > 1 else 0.0
+        g.interp = self.interp
+        return g
+
+
 class PdeDesc(C.Structure):
     """zb_pde_desc: data-described zombie::PDE (core/pde.h:20-45)."""
     _fields_ = [("absorptionCoeff", C.c_float),
@@ -64,7 +109,22 @@ class PdeDesc(C.Structure):
                 ("dirichletValue", C.c_float),
                 ("robinValue", C.c_float),
                 ("kelvin", C.c_int32),
-                ("kelvinOrigin", C.c_float * 3)]
+                ("kelvinOrigin", C.c_float * 3),
+                ("sourceGrid", GridView), ("dirichletGrid", GridView), ("robinGrid", GridView),
+                ("robinAlignedGrid", GridView), ("robinCoeffGrid", GridView)]
+
+    GRID_FIELDS = ("sourceGrid", "dirichletGrid", "robinGrid", "robinAlignedGrid", "robinCoeffGrid")
+
+    def set_grids(self, **grids):
+        """attaches HostGrid objects (source=, dirichlet=, robin=, robinAligned=, robinCoeff=). The structure then carries
+        HOST pointers (what the test oracle reads); native.Scene.solve uploads the grids and passes device pointers."""
+        self.__dict__.setdefault("host_grids", {})
+        for k, g in grids.items():
+            name = k + "Grid"
+            assert name in self.GRID_FIELDS
+            self.host_grids[name] = g
+            setattr(self, name, g.view())
+        return self
 
     @classmethod
     def manufactured(cls, family, params, absorptionCoeff=0.0, robinCoeff=0.0, isSourceConstant=False):

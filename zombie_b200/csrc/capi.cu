@@ -336,6 +336,14 @@ int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
     const size_t qSmem = (size_t)(qThreads/32)*sizeof(WarpShared);
     const bool needQueue = a.ws.splittingThreshold < kMaxFloat;
     const int stripeWarps = std::max(1, envInt("ZB_WAVE_STRIPE", 4096)/nGroups); // warps the tail of a solve spreads over (ZB_WAVE_STRIPE=1: compact)
+    // live walks at or below which a group hands its walks to the barrier-free tail kernel (wave.cuh: waveTailKernel); 0: never
+    const int tailWalks = std::max(0, envInt("ZB_WAVE_TAIL", 8192))/nGroups;
+    int tailPerSm = 0;
+    if (tailWalks > 0) {
+        ZB_CUDA(cudaFuncSetAttribute(waveTailKernel<DIM, WOST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
+        ZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tailPerSm, waveTailKernel<DIM, WOST>, 128, kCoopSmem));
+        tailPerSm = std::max(1, tailPerSm);
+    }
 
     WaveGroup groups[kMaxWaveGroups];
     size_t sortBytes = 0;
@@ -446,6 +454,18 @@ int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
                 ZB_CUDA(cudaEventSynchronize(ctx->evRound[prev]));
                 unsigned int alive = ctx->hostLive[prev];
                 if (alive == 0u) { G.done = true; remaining--; }
+                else if ((int)alive <= tailWalks && (int)alive < G.nSlots) {
+                    // fewer live walks than slots: the group's tasks have run out, and few enough are left that the round
+                    // barriers cost more than they organise. One persistent launch steps them to their end (the walks alive
+                    // NOW are a subset of the `alive` ones at the front of the order the last round left behind).
+                    const int bound = std::min(G.nBound, (int)((alive + 127u)/128u*128u));
+                    const int tailBlocks = std::max(1, std::min(ctx->smCount*tailPerSm/nGroups, blocksFor(bound*32, 128)));
+                    w.order = G.orderA;
+                    waveTailKernel<DIM, WOST><<<tailBlocks, 128, kCoopSmem, G.stream>>>(a, w, bound, tailBlocks*4);
+                    ZB_CUDA(cudaGetLastError());
+                    ctx->launches += 1;
+                    G.done = true; remaining--;
+                }
                 // the live walks sit at the front of the order (empty slots sort to the end) and, once the group's tasks have
                 // run out, their number only falls: later rounds need not look past it
                 else G.nBound = std::min(G.nBound, (int)((alive + 127u)/128u*128u));
@@ -751,8 +771,43 @@ int zb_scene_update_robin_coefficients(zb_scene *scene, const float *minRobinCoe
     updateCoefficients(s.host, minRobinCoeff, maxRobinCoeff);
     ZB_CUDA(cudaMemcpyAsync(s.cones.ptr, s.host.cones.data(), s.host.cones.size()*sizeof(ChildCone), cudaMemcpyHostToDevice, scene->ctx->stream));
     ZB_CUDA(cudaMemcpyAsync(s.adjacency.ptr, s.host.adjacency.data(), s.host.adjacency.size()*sizeof(PrimAdjacency), cudaMemcpyHostToDevice, scene->ctx->stream));
+    if (s.host.dim == 3) // the vertex records carry a copy of each triangle's maximum coefficient
+        ZB_CUDA(cudaMemcpyAsync(s.prims.ptr, s.host.prims.data(), s.host.prims.size()*sizeof(float), cudaMemcpyHostToDevice, scene->ctx->stream));
     ZB_CUDA(cudaStreamSynchronize(scene->ctx->stream));
     return ZB_OK;
+}
+
+// ---- PDE data grids (zb_grid_view::data) -------------------------------------------------------------------
+struct zb_grid {
+    int device = 0;
+    float *data = nullptr;
+};
+
+int zb_grid_create(zb_context *ctx, const float *hostData, const int32_t shape[3], zb_grid **out)
+{
+    if (!ctx || !hostData || !shape || !out) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_grid_create: NULL argument");
+    *out = nullptr;
+    if (shape[0] < 1 || shape[1] < 1 || shape[2] < 1) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_grid_create: every extent must be at least 1");
+    ZB_CUDA(cudaSetDevice(ctx->device));
+    size_t n = (size_t)shape[0]*(size_t)shape[1]*(size_t)shape[2];
+    zb_grid *g = new zb_grid();
+    g->device = ctx->device;
+    cudaError_t e = cudaMalloc(&g->data, n*sizeof(float));
+    if (e != cudaSuccess) { delete g; ZB_CUDA(e); }
+    e = cudaMemcpy(g->data, hostData, n*sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(g->data); delete g; ZB_CUDA(e); }
+    *out = g;
+    return ZB_OK;
+}
+
+const float *zb_grid_data(const zb_grid *grid) { return grid ? grid->data : nullptr; }
+
+void zb_grid_destroy(zb_grid *grid)
+{
+    if (!grid) return;
+    cudaSetDevice(grid->device);
+    cudaFree(grid->data);
+    delete grid;
 }
 
 int zb_scene_stats(const zb_scene *scene, int boundary, int64_t *bytes, int32_t *nNodes, int32_t *nLeaves, int32_t *maxDepth)

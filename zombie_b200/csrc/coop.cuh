@@ -75,15 +75,18 @@ extern long long g_coopCount[10]; // [0] closest node items, [1] closest prims, 
 #define ZB_PHASE1_BUDGET 8
 #endif
 constexpr int kNodeStack = ZB_NODE_STACK; // node items per warp; the top kNodeHeadroom are depth-first headroom
-constexpr int kNodeHeadroom = 128;
+constexpr int kNodeHeadroom = kNodeStack/8;
 constexpr int kPhase1Budget = ZB_PHASE1_BUDGET; // private stack pops per lane before the warp pools what is left
 #ifndef ZB_PRIM_QUEUE
 #define ZB_PRIM_QUEUE 1120
 #endif
 constexpr int kPrimQueue = ZB_PRIM_QUEUE; // primitive items per warp; 1120 >= 31 + 32 lanes x 8 leaves x 4 primitives + 63 survivors of the cheap stage (kept at the end)
 constexpr int kPrimSlack = 31 + 63;       // what the queue may hold when a node round or a refill starts: < 32 unfiltered items + the survivor list
-constexpr int kRefillPerLane = (kPrimQueue - kPrimSlack)/128 < 8 ? (kPrimQueue - kPrimSlack)/128 : 8; // private stack entries (<= 4 primitives each) a lane hands over per refill
-constexpr int kRefillLowWater = 192;  // refill when the shared node stack is below this
+constexpr int kRefillLowWater = kNodeStack*3/16;  // refill when the shared node stack is below this
+// private stack entries (<= 4 primitives each) a lane hands over per refill: what the primitive queue can take, and no more
+// node items than leave a full node round (32 nodes, 7 net entries each) its room below the headroom
+constexpr int kRefillByPrims = (kPrimQueue - kPrimSlack)/128, kRefillByNodes = (kNodeStack - kNodeHeadroom - 7*32 - kRefillLowWater)/32;
+constexpr int kRefillPerLane = kRefillByPrims < kRefillByNodes ? (kRefillByPrims < 8 ? kRefillByPrims : 8) : (kRefillByNodes < 8 ? kRefillByNodes : 8);
 static_assert(kRefillPerLane >= 1 && kNodeStack >= kRefillLowWater + 32*kRefillPerLane, "work lists too small");
 constexpr uint32_t kPrimIndexMask = 0x03ffffffu; // 26 bits: up to 67 M primitives per boundary
 enum : int { kStatusCoopOverflow = 4 };

@@ -27,22 +27,33 @@ struct PdeEval {
     }
     // ---- the callbacks of the PDE as the caller described it --------------------------------------
     // pde.source: the estimator solves lap u - sigma u = -f
+    ZB_HOSTDEV float grid(const zb_grid_view& g, const Vec<DIM>& x) const {
+        float p[3] = {x[0], x[1], DIM == 3 ? x[DIM - 1] : 0.0f};
+        return zb_grid_sample(g, p);
+    }
     ZB_HOSTDEV float baseSource(const Vec<DIM>& x) const {
+        if (d.sourceGrid.data) return grid(d.sourceGrid, x);
         if (d.mode == ZB_PDE_CONSTANT) return d.sourceValue;
         zb_jet j = jet(x);
         return d.absorptionCoeff*j.u - j.lap;
     }
     ZB_HOSTDEV float baseDirichlet(const Vec<DIM>& x) const {
+        if (d.dirichletGrid.data) return grid(d.dirichletGrid, x);
         if (d.mode == ZB_PDE_CONSTANT) return d.dirichletValue;
         return jet(x).u;
     }
     // du/dn + mu u with n the boundary normal handed to the callback
-    ZB_HOSTDEV float baseRobin(const Vec<DIM>& x, const Vec<DIM>& n) const {
+    ZB_HOSTDEV float baseRobin(const Vec<DIM>& x, const Vec<DIM>& n, bool aligned) const {
+        if (aligned && d.robinAlignedGrid.data) return grid(d.robinAlignedGrid, x);
+        if (d.robinGrid.data) return grid(d.robinGrid, x);
         if (d.mode == ZB_PDE_CONSTANT) return d.robinValue;
         zb_jet j = jet(x);
         float dn = 0.0f;
         for (int k = 0; k < DIM; k++) dn += n[k]*j.g[k];
-        return dn + d.robinCoeff*j.u;
+        return dn + baseRobinCoeff(x)*j.u;
+    }
+    ZB_HOSTDEV float baseRobinCoeff(const Vec<DIM>& x) const {
+        return d.robinCoeffGrid.data ? grid(d.robinCoeffGrid, x) : d.robinCoeff;
     }
     // y on the inverted domain -> x on the exterior domain (kelvin_transform.h:288-289)
     ZB_HOSTDEV Vec<DIM> exteriorPoint(const Vec<DIM>& y, float r2) const {
@@ -65,20 +76,21 @@ struct PdeEval {
         float rPow = DIM == 3 ? sqrtf(r2) : 1.0f;
         return baseDirichlet(exteriorPoint(y, r2))/rPow;
     }
-    ZB_HOSTDEV float robin(const Vec<DIM>& y, const Vec<DIM>& N) const {
-        if (!d.kelvin) return baseRobin(y, N);
+    // aligned: returnBoundaryNormalAlignedValue of the reference's callback (walk_on_stars.h:242-244)
+    ZB_HOSTDEV float robin(const Vec<DIM>& y, const Vec<DIM>& N, bool aligned = false) const {
+        if (!d.kelvin) return baseRobin(y, N, aligned);
         float r2 = dot(y, y);
         Vec<DIM> n = N - y*(2.0f*dot(N, y))/r2;
         float rPow = r2;
         if (DIM == 3) rPow *= sqrtf(r2);
-        return baseRobin(exteriorPoint(y, r2), n)/rPow;
+        return baseRobin(exteriorPoint(y, r2), n, false)/rPow; // the wrapper drops the flag (kelvin_transform.h:311-322)
     }
     ZB_HOSTDEV float robinCoeff(const Vec<DIM>& y, const Vec<DIM>& N) const {
-        if (!d.kelvin) return d.robinCoeff;
+        if (!d.kelvin) return baseRobinCoeff(y);
         float r2 = dot(y, y);
         float P = dot(N, y)/r2;
         float shift = DIM == 3 ? P : 0.0f;
-        return d.robinCoeff/r2 + shift;
+        return baseRobinCoeff(exteriorPoint(y, r2))/r2 + shift;
     }
     // PDE::hasNonZeroRobinCoeff (pde.h:59-76): probes robinCoeff with the normal e_0
     ZB_HOSTDEV bool hasNonZeroRobinCoeff(const Vec<DIM>& y) const {

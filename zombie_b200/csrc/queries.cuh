@@ -270,10 +270,14 @@ template <int DIM> struct Prim;
 template <> struct Prim<3> {
     Vec<3> a, b, c;
     int index;
+    float maxCoeff;   // reflecting boundaries: the triangle's maximum Robin coefficient and its adjacency flags, copies of
+    uint32_t adjFlags; // PrimAdjacency's (wide_bvh.cpp) riding in v1.w / v2.w so that the star filter stage reads 48 bytes in all
     ZB_DEV void load(const BvhView& bvh, uint32_t i) {
         float4 v0 = zb_ldg(bvh.prims + (size_t)3*i), v1 = zb_ldg(bvh.prims + (size_t)3*i + 1), v2 = zb_ldg(bvh.prims + (size_t)3*i + 2);
         a = make3(v0.x, v0.y, v0.z); b = make3(v1.x, v1.y, v1.z); c = make3(v2.x, v2.y, v2.z);
         index = zb_float_as_int(v0.w);
+        maxCoeff = v1.w;
+        adjFlags = zb_float_as_uint(v2.w);
     }
     ZB_DEV float closest(const Vec<3>& x, Vec<3>& pt, float& u, float& v) const { return closestPointTriangle(a, b, c, x, pt, u, v); }
     // unnormalised normal (b-a)x(c-a): fcpw Triangle::normal()
@@ -977,9 +981,8 @@ ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const V
 {
     Prim<3> prim;
     prim.load(bvh, primIdx);
-    float4 a2 = zb_ldg(bvh.adjacency + (size_t)3*primIdx + 2);
-    float maxCoeff = a2.z;
-    uint32_t flags = zb_float_as_uint(a2.w);
+    float maxCoeff = prim.maxCoeff;
+    uint32_t flags = prim.adjFlags;
     // Can the reflectance bound of this triangle shrink the radius at all? With h the distance from x to the triangle's
     // plane, the bound h^2 mu/(c (h mu - c^2)) (robin_bounds.h:48-74) is smallest at c = sqrt(h mu/3), whatever the
     // clamping cosines are, where its square is (27/4) h/mu. So 6.7 h >= mu r^2 (0.7 % of slack for rounding) means the
@@ -1014,7 +1017,8 @@ ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const V
     const float r2in = r2;
     bool redo = false;
 
-    float4 a0 = zb_ldg(bvh.adjacency + (size_t)3*primIdx), a1 = zb_ldg(bvh.adjacency + (size_t)3*primIdx + 1);
+    float4 a0 = zb_ldg(bvh.adjacency + (size_t)3*primIdx), a1 = zb_ldg(bvh.adjacency + (size_t)3*primIdx + 1),
+           a2 = zb_ldg(bvh.adjacency + (size_t)3*primIdx + 2);
     if (!(maxCoeff < kMaxFloat - kEpsilon)) { // perfectly absorbing
         r2 = fminf(r2, closestDist2);
         return;
@@ -1122,14 +1126,13 @@ ZB_DEV bool primStarNeedsFullTest(const BvhView& bvh, uint32_t primIdx, const Ve
 template <>
 ZB_DEV bool primStarNeedsFullTest<3>(const BvhView& bvh, uint32_t primIdx, const Vec<3>& x, float r2, bool silhouetteTests)
 {
-    float4 a2 = zb_ldg(bvh.adjacency + (size_t)3*primIdx + 2);
-    float maxCoeff = a2.z;
-    uint32_t flags = zb_float_as_uint(a2.w);
+    Prim<3> prim;
+    prim.load(bvh, primIdx);
+    float maxCoeff = prim.maxCoeff;
+    uint32_t flags = prim.adjFlags;
     if (!ZB_ROBIN_PLANE_BOUND || !(maxCoeff < kMaxFloat - kEpsilon)) return true;
     if (silhouetteTests && ((flags >> 4) & 7u) != 7u) return true;
     if (!(maxCoeff > kEpsilon)) return false;
-    Prim<3> prim;
-    prim.load(bvh, primIdx);
     Vec<3> nRaw = cross(prim.b - prim.a, prim.c - prim.a);
     float s = dot(nRaw, prim.a - x), nn = dot(nRaw, nRaw);
     float t = fmaxf(r2*maxCoeff*(1.0f/6.7f), 1e-6f);

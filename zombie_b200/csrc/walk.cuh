@@ -771,7 +771,7 @@ ZB_DEV StepResult stepBody(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *que
                     if (!blocked) {
                         float r = fmaxf(L.g.rClamp, distToSample);
                         float G = L.g.evaluate(r);
-                        float h = pde.robin(bs.p, bs.n);
+                        float h = pde.robin(bs.p, bs.n, aligned); // returnBoundaryNormalAlignedValue (walk_on_stars.h:242-244)
                         st.reflContrib += st.throughput*alpha*G*h/bs.pdf;
                     }
                 }

@@ -27,6 +27,13 @@
 
 #include "walk.cuh"
 
+#ifndef ZB_STAR_MIN_BLOCKS
+#define ZB_STAR_MIN_BLOCKS 1 // resident 128-thread CTAs per SM the star-radius kernel is compiled for (register cap)
+#endif
+#ifndef ZB_CLOSEST_MIN_BLOCKS
+#define ZB_CLOSEST_MIN_BLOCKS 1
+#endif
+
 namespace zb {
 
 enum : uint32_t {
@@ -113,7 +120,7 @@ ZB_DEV int stripedPosition(int nWarps)
 // distance query + scalar prologue of the step
 // ------------------------------------------------------------------------------------------
 template <int DIM, bool WOST>
-__global__ void __launch_bounds__(128) waveClosestKernel(SolveArgs a, WaveSlots w, int nBound, int nWarps)
+__global__ void __launch_bounds__(128, ZB_CLOSEST_MIN_BLOCKS) waveClosestKernel(SolveArgs a, WaveSlots w, int nBound, int nWarps)
 {
 #if defined(__CUDA_ARCH__)
     extern __shared__ __align__(16) unsigned char zbShared[];
@@ -204,7 +211,7 @@ __global__ void __launch_bounds__(128) waveClosestKernel(SolveArgs a, WaveSlots 
 // star radius
 // ------------------------------------------------------------------------------------------
 template <int DIM>
-__global__ void __launch_bounds__(128) waveStarKernel(SolveArgs a, WaveSlots w, int nBound, int nWarps)
+__global__ void __launch_bounds__(128, ZB_STAR_MIN_BLOCKS) waveStarKernel(SolveArgs a, WaveSlots w, int nBound, int nWarps)
 {
 #if defined(__CUDA_ARCH__)
     extern __shared__ __align__(16) unsigned char zbShared[];
@@ -417,6 +424,95 @@ __global__ void __launch_bounds__(128) waveStepKernel(SolveArgs a, WaveSlots w, 
     }
     const unsigned alive = __ballot_sync(full, L.active);
     if (lane == 0 && alive) atomicAdd(w.live, (unsigned int)__popc(alive));
+#endif
+}
+
+// ------------------------------------------------------------------------------------------
+// the tail of a solve: the last walks run to their end without round barriers
+// ------------------------------------------------------------------------------------------
+// A round lasts as long as its slowest query: ~1 ms for a query that opens thousands of primitives with a single warp behind
+// it, whatever the number of live walks. Once the tasks have run out, the solve's critical path is (steps of the longest walk)
+// x (that latency) — measured 0.9 s per solve of C3, independent of the batch size — while the machine is nearly idle. The
+// walks are independent, so the last ones need no barrier at all: this kernel takes the live slots (the front of the slot
+// order), spreads them over a persistent grid — one walk per warp when there are fewer walks than warps, the 32 lanes pooling
+// that walk's traversals — and every warp steps its walks until they end. The critical path becomes the longest walk's OWN
+// queries. It is the round-1 persistent loop (walkKernel) resumed from slot state, without a task queue.
+template <int DIM, bool WOST>
+__global__ void __launch_bounds__(128, ZB_WALK_MIN_BLOCKS) waveTailKernel(SolveArgs a, WaveSlots w, int nBound, int nWarps)
+{
+#if defined(__CUDA_ARCH__)
+    extern __shared__ __align__(16) unsigned char zbShared[];
+    WarpShared& ws = reinterpret_cast<WarpShared *>(zbShared)[threadIdx.x >> 5];
+    const unsigned full = 0xffffffffu;
+    const int i = stripedPosition(nWarps);
+    int slot = -1;
+    int4 m = make_int4(0, 0, 0, 0);
+    if (i < nBound) { slot = (int)w.order[i]; m = w.meta[slot]; }
+    Lane<DIM> L;
+    L.active = false;
+    L.needClosest = false;
+    L.keepDistA = false;
+    L.needsFinalProjection = false;
+    if ((uint32_t)m.w & kWfActive) {
+        loadLane<DIM>(a, w, slot, m, L);
+        L.needsFinalProjection = ((uint32_t)m.w & kWfFinalProjection) != 0u;
+    }
+    WalkState<DIM> *queue = w.queue && slot >= 0 ? reinterpret_cast<WalkState<DIM> *>(w.queue) + (size_t)slot*kSplitStack : nullptr;
+
+    while (__any_sync(full, L.active)) {
+        // ---- pending distance queries of the warp, cooperatively
+        bool qc = L.active && L.needClosest;
+        if (__any_sync(full, qc)) {
+            if (a.hasAbsorbing) {
+                ClosestHit<DIM> hit;
+                coopClosestPoint<DIM>(a.absorbing, ws, qc, L.st.pt, qc ? closestSearchRadius2<DIM, WOST>(a, L) : 0.0f, hit, a.status);
+                if (qc) {
+                    if (!L.keepDistA) L.distA = hit.d;
+                    L.proj = hit.p;
+                    L.projValid = hit.prim >= 0;
+                    L.needClosest = false;
+                    L.keepDistA = false;
+                }
+            } else if (qc) {
+                resolveClosest<DIM, WOST>(a, L);
+            }
+        }
+        // ---- loop condition of walk()
+        if (L.active && !L.needClosest) {
+            if (L.needsFinalProjection) {
+                L.needsFinalProjection = false;
+                finishStateWave<DIM, WOST>(a, L, kMaxLength, queue);
+            } else if (!(L.distA > a.ws.epsilonShellForAbsorbingBoundary)) {
+                finishStateWave<DIM, WOST>(a, L, kReached, queue);
+            }
+        }
+        bool ready = L.active && !L.needClosest;
+
+        // ---- star radii of the warp, cooperatively
+        float starRadius = 0.0f;
+        if (WOST) {
+            float r2max = 0.0f;
+            bool qs = ready && stepStarPrologue<DIM>(a, L, starRadius, r2max);
+            if (__any_sync(full, qs)) {
+                float r2 = coopStarRadius2<DIM>(a.reflecting, ws, qs, L.st.pt, r2max, !L.flip, a.ws.silhouettePrecision, a.status);
+                if (qs) {
+                    float r = starQueryResult(a, r2, r2max, a.ws.epsilonShellForReflectingBoundary, L.distA);
+                    starRadius = shrinkStarRadius(a, r, L.distA);
+                }
+            }
+        }
+
+        // ---- the rest of the step, one thread per walk
+        if (ready) {
+            StepResult r = stepBody<DIM, WOST>(a, L, queue, starRadius);
+            if (!WOST && r == kMaxLength && L.needsFinalProjection && a.hasAbsorbing && !a.ws.ignoreAbsorbingBoundaryContribution) {
+                L.needClosest = true;
+            } else if (r != kContinue) {
+                L.needsFinalProjection = false;
+                finishStateWave<DIM, WOST>(a, L, r, queue);
+            }
+        }
+    }
 #endif
 }
 

@@ -502,7 +502,13 @@ bool buildWideBvh(int dim, const float *positions, int nV, const int32_t *indice
                         g.vertex(p, 0, q); pf[0] = q[0]; pf[1] = q[1];
                         g.vertex(p, 1, q); pf[2] = q[0]; pf[3] = q[1];
                     }
-                    if (refl.enabled) out.adjacency[dst] = adjInput[p];
+                    if (refl.enabled) {
+                        out.adjacency[dst] = adjInput[p];
+                        if (dim == 3) { // filter-stage data rides in the free lanes of the vertex record (one 48-byte read)
+                            pf[7] = adjInput[p].maxCoeff;
+                            std::memcpy(&pf[11], &adjInput[p].flags, 4);
+                        }
+                    }
                 }
                 primOffset += cn.count;
                 out.nLeaves++;
@@ -628,6 +634,7 @@ void updateCoefficients(HostBvh& bvh, const float *minCoeff, const float *maxCoe
         int p = bvh.primIndex[i];
         bvh.adjacency[i].minCoeff = minCoeff[p];
         bvh.adjacency[i].maxCoeff = maxCoeff[p];
+        if (bvh.dim == 3) bvh.prims[(size_t)12*i + 7] = maxCoeff[p]; // the copy in the vertex record (v1.w)
     }
     // children precede... no: nodes are breadth first, so children have larger indices than parents;
     // sweep backwards accumulating each node's total range into its parent's child slot

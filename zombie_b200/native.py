@@ -23,6 +23,7 @@ SYMBOLS = ["zb_last_error", "zb_abi_version", "zb_device_count", "zb_context_cre
            "zb_host_bvh_check", "zb_scene_create", "zb_scene_destroy", "zb_scene_update_robin_coefficients", "zb_scene_stats",
            "zb_closest_point", "zb_intersect_ray", "zb_occluded", "zb_sample_sphere", "zb_star_radius",
            "zb_solve", "zb_solve_dev", "zb_bvc_splat", "zb_bvc_splat_dev", "zb_context_last_splat_ms", "zb_rws_solve",
+           "zb_grid_create", "zb_grid_data", "zb_grid_destroy",
            "zb_pcg32_kat", "zb_pcg32_demo", "zb_pcg32_floats"]
 
 
@@ -66,6 +67,11 @@ def lib():
         l.zb_bvc_splat_dev.argtypes = [vp, i, f, vp, f, f, f, f, f, vp, C.POINTER(C.c_int64)]
         l.zb_context_last_splat_ms.argtypes = [vp, C.POINTER(C.c_float)]
         l.zb_rws_solve.argtypes = [vp, vp, vp, vp, f, f, f, vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        l.zb_grid_create.argtypes = [vp, vp, C.POINTER(C.c_int32 * 3), C.POINTER(vp)]
+        l.zb_grid_data.argtypes = [vp]
+        l.zb_grid_data.restype = vp
+        l.zb_grid_destroy.argtypes = [vp]
+        l.zb_grid_destroy.restype = None
         l.zb_pcg32_kat.argtypes = [vp, C.c_uint64, C.c_uint64, i, vp]
         l.zb_pcg32_demo.argtypes = [vp, C.c_uint64, C.c_uint64, i, vp, vp, vp, vp]
         l.zb_pcg32_floats.argtypes = [vp, C.c_uint64, C.c_uint64, i, vp]
@@ -94,6 +100,47 @@ def host_bvh_check(dim, positions, indices, reflecting=False):
     _check(lib().zb_host_bvh_check(dim, abi.ptr(pos), len(pos), abi.ptr(idx), len(idx), int(reflecting),
                                    C.byref(n), C.byref(l), C.byref(d), C.byref(v)), "zb_host_bvh_check")
     return {"nodes": n.value, "leaves": l.value, "max_depth": d.value, "violations": v.value}
+
+
+class Grid:
+    """zb_grid: a HostGrid's samples resident on a context's device."""
+
+    def __init__(self, ctx, host_grid):
+        self._h = C.c_void_p()
+        nz, ny, nx = host_grid.values.shape
+        shape = (C.c_int32 * 3)(nx, ny, nz)
+        _check(lib().zb_grid_create(ctx._h, abi.ptr(host_grid.values), C.byref(shape), C.byref(self._h)), "zb_grid_create")
+        self.data = lib().zb_grid_data(self._h)
+
+    def close(self):
+        if self._h:
+            lib().zb_grid_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def device_pde(ctx, pde):
+    """the descriptor zb_solve takes: grids attached with PdeDesc.set_grids are uploaded once per context (cached on the
+    HostGrid) and their views point at device memory"""
+    grids = getattr(pde, "host_grids", None)
+    if not grids:
+        return pde
+    d = abi.PdeDesc()
+    C.memmove(C.byref(d), C.byref(pde), C.sizeof(abi.PdeDesc))
+    keep = []
+    for name, g in grids.items():
+        cache = g.__dict__.setdefault("_device", {})
+        if id(ctx) not in cache:
+            cache[id(ctx)] = Grid(ctx, g)
+        keep.append(cache[id(ctx)])
+        setattr(d, name, g.view(cache[id(ctx)].data))
+    d.__dict__["_keep"] = keep
+    return d
 
 
 class Context:
@@ -288,6 +335,7 @@ class Scene:
         are updated in place like the reference's samplePts / statistics. Returns the walk steps taken."""
         steps = C.c_int64(0)
         ps, ss = pts.as_struct(), stats.as_struct()
+        pde = device_pde(self.ctx, pde)
         _check(lib().zb_solve(self._h, estimator, C.byref(pde), C.byref(settings), C.byref(ps), C.byref(ss),
                               C.byref(steps)), "zb_solve")
         return steps.value
@@ -297,6 +345,7 @@ class Scene:
         advances), eval_pts = abi.HostRwsEvalPoints (totals accumulate). Returns (walk steps, splat records)."""
         steps, records = C.c_int64(0), C.c_int64(0)
         ss, es = samples.as_struct(), eval_pts.as_struct()
+        pde = device_pde(self.ctx, pde)
         _check(lib().zb_rws_solve(self._h, C.byref(pde), C.byref(settings), C.byref(ss), normal_offset, radius_clamp,
                                   kernel_regularization, C.byref(es), C.byref(steps), C.byref(records)), "zb_rws_solve")
         return steps.value, records.value
@@ -304,5 +353,6 @@ class Scene:
     def solve_dev(self, estimator, pde, settings, pts_struct, stats_struct, steps_dev_ptr=None):
         """Same with every array already resident on the device (abi.SamplePoints / abi.Statistics of
         device pointers); asynchronous on the context's stream."""
+        pde = device_pde(self.ctx, pde)
         _check(lib().zb_solve_dev(self._h, estimator, C.byref(pde), C.byref(settings), C.byref(pts_struct),
                                   C.byref(stats_struct), C.c_void_p(steps_dev_ptr)), "zb_solve_dev")

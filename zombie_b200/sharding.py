@@ -99,3 +99,59 @@ def merge_statistics(a, b):
     out.totalWalkLength = a.totalWalkLength + b.totalWalkLength
     out.totalSplits = a.totalSplits + b.totalSplits
     return out
+
+
+class DeviceStatistics:
+    """The statistics of n points as ONE contiguous device buffer (float32 words; SoA sections in the order of the C ABI's
+    zb_statistics: 2 + 2*dim + 2 float arrays, then 4 int32 arrays = 56 bytes per point in 3D), so that the gather after a
+    sharded solve is a single all_gather_into_tensor on memory zb_solve_dev wrote — no host staging, no repacking."""
+
+    def __init__(self, n, dim, device):
+        import torch
+        self.n, self.dim = n, dim
+        self.words = 2 + 2*dim + 2 + 4
+        self.buf = torch.zeros(self.words*n, dtype=torch.float32, device=device)
+        self.sections = {}
+        off = 0
+        for k in STAT_FLOAT_KEYS:
+            width = dim if k.startswith("gradient") else 1
+            self.sections[k] = (off, width)
+            off += width*n
+        for k in STAT_INT_KEYS:
+            self.sections[k] = (off, 1)
+            off += n
+        assert off == self.words*n
+
+    def view(self, key, buf=None):
+        """tensor view of one section of this buffer (or of one rank's slice of a gathered buffer)"""
+        import torch
+        b = self.buf if buf is None else buf
+        off, width = self.sections[key]
+        t = b[off:off + width*self.n]
+        if key in STAT_INT_KEYS:
+            t = t.view(torch.int32)
+        return t.view(self.n, width) if width > 1 else t
+
+    def as_struct(self):
+        """abi.Statistics of device pointers into the buffer (what zb_solve_dev takes)"""
+        base = self.buf.data_ptr()
+        keys = ("solutionMean", "solutionM2", "gradientMean", "gradientM2", "totalFirstSourceContribution",
+                "totalDerivativeContribution", "nSolutionEstimates", "nGradientEstimates", "totalWalkLength", "totalSplits")
+        return abi.Statistics(*[base + 4*self.sections[k][0] for k in keys])
+
+    def all_gather(self, out=None):
+        """all ranks' buffers, [world, words*n] (rank r's points are shard_indices(n_total, r, world)); one collective"""
+        import torch
+        import torch.distributed as dist
+        world = dist.get_world_size()
+        if out is None:
+            out = torch.empty((world, self.words*self.n), dtype=torch.float32, device=self.buf.device)
+        dist.all_gather_into_tensor(out.view(-1), self.buf)
+        return out
+
+    def to_host(self, buf=None):
+        """HostStatistics of this buffer (or of one rank's slice of a gathered buffer)"""
+        st = abi.HostStatistics(self.n, self.dim)
+        for k in STAT_FLOAT_KEYS + STAT_INT_KEYS:
+            setattr(st, k, np.ascontiguousarray(self.view(k, buf).cpu().numpy()))
+        return st
