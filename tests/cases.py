@@ -65,8 +65,28 @@ def z_scores(a, b):
     return (a.solutionMean - b.solutionMean)/np.sqrt(np.maximum(va + vb, 1e-12))
 
 
-def coplanar_primitive_within(positions, indices, x, reach, rel):
-    """True when x lies in the supporting plane (3D) / line (2D) of a primitive whose closest vertex is within `reach`:
+def _distance_to_primitives(p, x):
+    """distance from x to every segment (p: [n, 2, 2]) / triangle (p: [n, 3, 3]), float64, vectorised"""
+    def seg(a, b):
+        ab = b - a
+        t = np.clip(np.einsum("ij,ij->i", x[None, :] - a, ab)/np.maximum(np.einsum("ij,ij->i", ab, ab), 1e-300), 0.0, 1.0)
+        return np.linalg.norm(a + ab*t[:, None] - x[None, :], axis=1)
+    if p.shape[2] == 2:
+        return seg(p[:, 0], p[:, 1])
+    a, b, c = p[:, 0], p[:, 1], p[:, 2]
+    n = np.cross(b - a, c - a)
+    nn = np.maximum(np.einsum("ij,ij->i", n, n), 1e-300)
+    q = x[None, :] - n*(np.einsum("ij,ij->i", x[None, :] - a, n)/nn)[:, None]      # projection onto the plane
+    inside = np.ones(len(p), bool)
+    for u, v in ((a, b), (b, c), (c, a)):
+        inside &= np.einsum("ij,ij->i", np.cross(v - u, q - u), n) >= 0.0
+    d_plane = np.abs(np.einsum("ij,ij->i", x[None, :] - a, n))/np.sqrt(nn)
+    d_edges = np.minimum(np.minimum(seg(a, b), seg(b, c)), seg(c, a))
+    return np.where(inside, d_plane, d_edges)
+
+
+def coplanar_primitive_within(positions, indices, x, lo, hi, rel):
+    """True when x lies in the supporting plane (3D) / line (2D) of a primitive whose distance from x is in [lo, hi]:
     plane distance below `rel` times that distance. float64 throughout."""
     p = positions[indices]                      # (n, dim, dim)
     dim = p.shape[2]
@@ -77,6 +97,6 @@ def coplanar_primitive_within(positions, indices, x, reach, rel):
         n = np.stack([e[:, 1], -e[:, 0]], axis=1)
     n /= np.maximum(np.linalg.norm(n, axis=1, keepdims=True), 1e-300)
     h = np.abs(np.einsum("ij,ij->i", n, x[None, :] - p[:, 0]))
-    d = np.linalg.norm(p - x[None, None, :], axis=2).min(axis=1)
-    near = d <= reach
+    d = _distance_to_primitives(p, x)
+    near = (d >= lo) & (d <= hi)
     return bool(np.any(near & (h <= rel*np.maximum(d, 1e-300))))

@@ -37,14 +37,16 @@ def test_queries_match_compiled_reference(ctx, ref, dim, kind):
         #     silhouette through the `precision` rules (silhouette_edges.inl:88-105), so the reference's BVH deviates from
         #     the reference's brute-force Baseline on a few queries in 10^5 (by more than FCPW's own 1e-3 tolerance). The
         #     device traversal treats nodes within `precision` of the query as candidates and must agree with that Baseline.
-        # (2) Robin only: the query point lies IN the plane of a reflecting primitive within reach (plane distance h below
-        #     1e-6 of its distance). The reference's radius for that primitive is h^2 mu/(c (h mu - c^2)) ~ h/c with h and
-        #     the cosine c = h/distance both at the rounding level of the dot products they come from (robin_bounds.h:48-74,
-        #     reflectance_boundary_bvh/geometry.h:196-226) and can come out BELOW the primitive's own distance. Whether that
-        #     value counts then depends on the visiting order: the primitive is skipped once the radius has fallen below
-        #     its squared distance (geometry.h:179-182), so the reference's BVH, its Baseline and any other traversal may
-        #     each report a different radius (the device keeps the reference's arithmetic and early exit, so it is one more
-        #     such traversal).
+        # (2) Robin only: the query point lies IN the plane of a reflecting primitive whose distance is about the radius
+        #     (plane distance h below 1e-5 of the distance d). The reference's radius for that primitive is
+        #     h^2 mu/(c (h mu - c^2)) with h and the cosine c = h/d both at the rounding level of the dot products they come
+        #     from (robin_bounds.h:48-74, reflectance_boundary_bvh/geometry.h:196-226) and comes out up to a few percent
+        #     BELOW d, which no exact evaluation could. Whether that value counts then depends on the visiting order: the
+        #     primitive is skipped once the radius has fallen below its squared distance (geometry.h:179-182), so the
+        #     reference's BVH, its Baseline and any other traversal may each report a different radius — they do: on the
+        #     1.3 M-triangle mesh the reference's BVH and Baseline disagree with each other on such rows by the same 0.5-1 %
+        #     (the device keeps the reference's arithmetic and early exit, so it is one more such traversal; one query per
+        #     launch reproduces the reference's or the Baseline's value on every such row, scripts/star_fullsize_debug.py).
         rb = ref.RefScene(dim, use_baseline=True, **kw)
         base = rb.star_radius(x[bad], minr[bad], da[bad])
         rb.close()
@@ -53,9 +55,11 @@ def test_queries_match_compiled_reference(ctx, ref, dim, kind):
         if kind == abi.REFLECTING_ROBIN:
             rp, ri = reflecting
             for k, i in enumerate(np.where(bad)[0]):
-                coplanar[k] = cases.coplanar_primitive_within(rp.astype(np.float64), ri, x[i].astype(np.float64), 1.1*max(rr[i], gr[i]), 1e-6)
+                coplanar[k] = cases.coplanar_primitive_within(rp.astype(np.float64), ri, x[i].astype(np.float64),
+                                                              0.97*min(rr[i], gr[i]), 1.15*max(rr[i], gr[i]), 1e-5)
         assert (by_baseline | coplanar).all(), (x[bad], rr[bad], gr[bad], base, by_baseline, coplanar)
-        assert coplanar.sum() <= 2 + 2e-5*nq   # a measure-zero configuration: a handful of rows at most
+        assert np.abs(rr - gr)[bad][coplanar & ~by_baseline].max(initial=0.0) <= 0.1*float(rr.max())
+        assert coplanar.sum() <= 2 + 5e-4*nq   # a thin set of configurations: a handful of rows
     assert np.mean(rel_err(rr, gr)[~bad] <= 1e-4) > 0.99   # the Robin radius bound h^2 mu/(c(h mu - c^2)) amplifies float rounding
     assert (rr < 0.999*da).mean() > 0.01   # the query is exercised: some radii are limited by silhouettes / reflectance
     rs.close(); gs.close()
@@ -91,10 +95,12 @@ def test_full_size_mesh_matches_compiled_reference(ctx, ref):
         rb.close()
         by_baseline = np.abs(base - gr[bad]) <= 1e-5*max(1.0, float(rr.max()))
         rp, ri = kw["reflecting"]
-        coplanar = np.array([cases.coplanar_primitive_within(rp.astype(np.float64), ri, x[i].astype(np.float64), 1.1*max(rr[i], gr[i]), 1e-6)
+        coplanar = np.array([cases.coplanar_primitive_within(rp.astype(np.float64), ri, x[i].astype(np.float64),
+                                                             0.97*min(rr[i], gr[i]), 1.15*max(rr[i], gr[i]), 1e-5)
                              for i in np.where(bad)[0]], bool)
         assert (by_baseline | coplanar).all(), (x[bad], rr[bad], gr[bad], base)
-        assert bad.sum() <= 4
+        assert np.abs(rr - gr)[bad].max() <= 0.1*float(rr.max())
+        assert bad.sum() <= 2 + 5e-4*nq
     assert np.mean(rel_err(rr, gr)[~bad] <= 1e-4) > 0.99
     assert (rr < 0.999*da).mean() > 0.01
 

@@ -366,7 +366,7 @@ int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
             G.keysOut = c.take<uint32_t>(n);
             G.orderA = c.take<uint32_t>(n);
             G.orderB = c.take<uint32_t>(n);
-            G.live = c.take<unsigned int>(kLiveRing);
+            G.live = c.take<unsigned int>(kLiveRing*4); // per round in flight: live walks, the two query kernels' warp tickets, padding
             w.taskCounter = c.take<unsigned long long>(1);
             size_t bytes = 0;
             ZB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, w.keys, G.keysOut, G.orderA, G.orderB, G.nSlots, 0, 32, stream));
@@ -404,6 +404,14 @@ int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
     ZB_CUDA(cudaFuncSetAttribute(waveClosestKernel<DIM, WOST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
     if (WOST) ZB_CUDA(cudaFuncSetAttribute(waveStarKernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
 
+    int closestResident = 1, starResident = 1;
+    ZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&closestResident, waveClosestKernel<DIM, WOST>, qThreads, qSmem));
+    if (WOST) ZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&starResident, waveStarKernel<DIM>, qThreads, qSmem));
+    const int residentScale = std::max(1, envInt("ZB_WAVE_PERSIST", 1)); // 0/1: one resident wave; k > 1: k waves' worth of CTAs
+    closestResident = std::max(1, closestResident)*ctx->smCount*residentScale/nGroups;
+    starResident = std::max(1, starResident)*ctx->smCount*residentScale/nGroups;
+    if (envInt("ZB_WAVE_PERSIST", 1) == 0) closestResident = starResident = 1 << 30; // one CTA per 128 positions, as before
+
     // fork: the group streams start after everything already queued on the context's stream
     ZB_CUDA(cudaEventRecord(ctx->evFork, stream));
     for (int g = 0; g < nGroups; g++) {
@@ -425,16 +433,17 @@ int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
             WaveSlots& w = G.w;
             for (int k = 0; k < kRoundsPerGroup; k++, G.round++) {
                 w.order = G.orderA;
-                w.live = G.live + G.round%kLiveRing;
-                ZB_CUDA(cudaMemsetAsync(w.live, 0, sizeof(unsigned int), G.stream));
+                w.live = G.live + 4*(G.round%kLiveRing);
+                ZB_CUDA(cudaMemsetAsync(w.live, 0, 4*sizeof(unsigned int), G.stream));
                 if (G.round > 0) { // round 0 only hands out the first tasks
                     // striped over all the group's warps while there are enough walks; in the tail over as many warps as
                     // there are walks, but never fewer than a few per SM-resident warp slot
                     const int qWarps = std::max(1, std::min(G.nSlots/32, std::max(G.nBound/32, stripeWarps)));
                     const int qBlocks = blocksFor(qWarps*32, qThreads);
-                    const int launchedWarps = qBlocks*(qThreads/32);
-                    waveClosestKernel<DIM, WOST><<<qBlocks, qThreads, qSmem, G.stream>>>(a, w, G.nBound, launchedWarps);
-                    if (star) waveStarKernel<DIM><<<qBlocks, qThreads, qSmem, G.stream>>>(a, w, G.nBound, launchedWarps);
+                    const int virtualWarps = qBlocks*(qThreads/32);
+                    // persistent grids: the CTAs the machine keeps resident draw the virtual warps from a ticket counter
+                    waveClosestKernel<DIM, WOST><<<std::min(qBlocks, closestResident), qThreads, qSmem, G.stream>>>(a, w, G.nBound, virtualWarps);
+                    if (star) waveStarKernel<DIM><<<std::min(qBlocks, starResident), qThreads, qSmem, G.stream>>>(a, w, G.nBound, virtualWarps);
                     ctx->launches += star ? 2 : 1;
                 }
                 waveStepKernel<DIM, WOST><<<blocksFor(G.nBound, 128), 128, 0, G.stream>>>(a, w, G.nBound);
@@ -446,7 +455,7 @@ int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
             }
             rounds = std::max(rounds, G.round);
             const int slot = 2*g + (G.batches & 1);
-            ZB_CUDA(cudaMemcpyAsync(ctx->hostLive + slot, G.live + (G.round - 1)%kLiveRing, sizeof(unsigned int), cudaMemcpyDeviceToHost, G.stream));
+            ZB_CUDA(cudaMemcpyAsync(ctx->hostLive + slot, G.live + 4*((G.round - 1)%kLiveRing), sizeof(unsigned int), cudaMemcpyDeviceToHost, G.stream));
             ZB_CUDA(cudaEventRecord(ctx->evRound[slot], G.stream));
             if (G.batches >= 1) {
                 // one batch of rounds of lag: the device never waits for the host
@@ -1217,10 +1226,74 @@ int zb_rws_solve(zb_scene *scene, const zb_pde_desc *pde, const zb_walk_settings
         if (g.hasReflecting && selfNorm) selfNorm = pde->areRobinConditionsPureNeumann != 0;
         g.useSelfNormalization = selfNorm ? 1 : 0;
         g.status = ctx->status.as<int>();
-        if (scene->dim == 3) rwsGatherKernel<3><<<blocksFor((int)m, kRwsThreads), kRwsThreads, 0, ctx->stream>>>(g);
-        else rwsGatherKernel<2><<<blocksFor((int)m, kRwsThreads), kRwsThreads, 0, ctx->stream>>>(g);
+
+        // spatial culling (rws.cuh): records sorted into tiles with bounding boxes, evaluation points sorted by Morton code
+        RwsCullArgs c;
+        std::memset(&c, 0, sizeof(c));
+        c.records = ctx->rwsRecords.as<float4>();
+        c.nRecords = (long long)count;
+        c.nTiles = (int)((count + kRwsTile - 1)/kRwsTile);
+        c.nSuper = (c.nTiles + kRwsSuper - 1)/kRwsSuper;
+        c.nEval = (int)m;
+        c.evalPt = g.evalPt;
+        float lo[3] = {kMaxFloat, kMaxFloat, kMaxFloat}, hi[3] = {-kMaxFloat, -kMaxFloat, -kMaxFloat};
+        for (int b = 0; b < 2; b++) {
+            if (!scene->boundary[b].present) continue;
+            for (int k = 0; k < 3; k++) {
+                lo[k] = std::min(lo[k], scene->boundary[b].host.boxMin[k]);
+                hi[k] = std::max(hi[k], scene->boundary[b].host.boxMax[k]);
+            }
+        }
+        float diag2 = 0.0f;
+        for (int k = 0; k < 3; k++) {
+            float l = hi[k] > lo[k] ? lo[k] : 0.0f, h = hi[k] > lo[k] ? hi[k] : 1.0f;
+            c.lo[k] = l;
+            c.scale[k] = (scene->dim == 3 ? 1024.0f : 32768.0f)/(h - l);
+            if (k < scene->dim) diag2 += (h - l)*(h - l);
+        }
+        c.invDiag = 1.0f/std::sqrt(std::max(diag2, 1e-30f));
+        size_t sortBytesRec = 0, sortBytesEval = 0;
+        unsigned long long *k64 = nullptr;
+        uint32_t *k32 = nullptr;
+        ZB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sortBytesRec, k64, k64, k32, k32, (int)std::max<unsigned long long>(count, 1), 0, 64, ctx->stream));
+        ZB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sortBytesEval, k32, k32, k32, k32, (int)m, 0, 32, ctx->stream));
+        const size_t nr = (size_t)std::max<unsigned long long>(count, 1);
+        Carver sizing(nullptr);
+        sizing.take<unsigned long long>(2*nr); sizing.take<uint32_t>(2*nr); sizing.take<uint32_t>(4*m);
+        sizing.take<float4>(2*(size_t)(c.nTiles + c.nSuper) + 2); sizing.take<char>(std::max(sortBytesRec, sortBytesEval) + 256);
+        ZB_CUDA(ctx->rwsScratch.reserve(sizing.offset + 16*256)); // + alignment padding of the individual arrays carved below
+        ZB_CUDA(ctx->rwsSorted.reserve(nr*48 + 256));
+        Carver cv(ctx->rwsScratch.ptr);
+        unsigned long long *keysA = cv.take<unsigned long long>(nr), *keysB = cv.take<unsigned long long>(nr);
+        uint32_t *idxA = cv.take<uint32_t>(nr), *idxB = cv.take<uint32_t>(nr);
+        uint32_t *eKeysA = cv.take<uint32_t>(m), *eKeysB = cv.take<uint32_t>(m), *eIdxA = cv.take<uint32_t>(m), *eIdxB = cv.take<uint32_t>(m);
+        c.tileLo = cv.take<float4>((size_t)(c.nTiles + c.nSuper) + 1);
+        c.tileHi = cv.take<float4>((size_t)(c.nTiles + c.nSuper) + 1);
+        char *sortTemp = cv.take<char>(std::max(sortBytesRec, sortBytesEval) + 256);
+        c.sorted = ctx->rwsSorted.as<float4>();
+        c.keys = keysA; c.index = idxA;
+        c.evalKeys = eKeysA; c.evalIndex = eIdxA;
+        if (count > 0) {
+            if (scene->dim == 3) rwsRecordKeysKernel<3><<<blocksFor((int)count, 256), 256, 0, ctx->stream>>>(c);
+            else rwsRecordKeysKernel<2><<<blocksFor((int)count, 256), 256, 0, ctx->stream>>>(c);
+            size_t bytes = sortBytesRec;
+            ZB_CUDA(cub::DeviceRadixSort::SortPairs(sortTemp, bytes, keysA, keysB, idxA, idxB, (int)count, 0, 64, ctx->stream));
+            c.index = idxB;
+            rwsReorderKernel<<<blocksFor((int)count, 256), 256, 0, ctx->stream>>>(c);
+            rwsTileBoundsKernel<<<blocksFor(c.nTiles*32, 256), 256, 0, ctx->stream>>>(c);
+            rwsSuperBoundsKernel<<<blocksFor(c.nSuper*32, 256), 256, 0, ctx->stream>>>(c);
+        }
+        if (scene->dim == 3) rwsEvalKeysKernel<3><<<blocksFor((int)m, 256), 256, 0, ctx->stream>>>(c);
+        else rwsEvalKeysKernel<2><<<blocksFor((int)m, 256), 256, 0, ctx->stream>>>(c);
+        {
+            size_t bytes = sortBytesEval;
+            ZB_CUDA(cub::DeviceRadixSort::SortPairs(sortTemp, bytes, eKeysA, eKeysB, eIdxA, eIdxB, (int)m, 0, 32, ctx->stream));
+        }
+        g.records = c.sorted;
+        if (scene->dim == 3) rwsGatherKernel<3><<<blocksFor((int)m, kRwsThreads), kRwsThreads, 0, ctx->stream>>>(g, eIdxB, c.tileLo, c.tileHi, c.nTiles, c.nSuper);
+        else rwsGatherKernel<2><<<blocksFor((int)m, kRwsThreads), kRwsThreads, 0, ctx->stream>>>(g, eIdxB, c.tileLo, c.tileHi, c.nTiles, c.nSuper);
         ZB_CUDA(cudaGetLastError());
-        ctx->launches += 1;
+        ctx->launches += 8;
         rc = stageOut(ctx, plan);
         if (rc != ZB_OK) return rc;
         if (walkSteps) *walkSteps = steps;

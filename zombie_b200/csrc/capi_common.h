@@ -55,7 +55,7 @@ struct zb_context {
     cudaStream_t stream = nullptr;
     bool ownsStream = false;
     zb::DeviceBuffer status, counters, perPoint, strat, records, scanTemp, io;
-    zb::DeviceBuffer bvcSamples, bvcIo, rwsRecords;
+    zb::DeviceBuffer bvcSamples, bvcIo, rwsRecords, rwsSorted, rwsScratch;
     zb::DeviceBuffer wave, waveSort;       // walk state of the wavefront scheduler, radix-sort scratch
     unsigned int *hostLive = nullptr;      // pinned: live-walk counts read back every few rounds
     cudaEvent_t evRound[16] = {};          // two per slot group

@@ -66,7 +66,7 @@ extern long long g_coopCount[10]; // [0] closest node items, [1] closest prims, 
 #endif
 
 #ifndef ZB_NODE_STACK
-#define ZB_NODE_STACK 1024
+#define ZB_NODE_STACK 512
 #endif
 #ifndef ZB_STAR_TWO_STAGE
 #define ZB_STAR_TWO_STAGE 1 // 0: every pooled primitive round runs the full star test (A/B builds)
@@ -78,9 +78,9 @@ constexpr int kNodeStack = ZB_NODE_STACK; // node items per warp; the top kNodeH
 constexpr int kNodeHeadroom = kNodeStack/8;
 constexpr int kPhase1Budget = ZB_PHASE1_BUDGET; // private stack pops per lane before the warp pools what is left
 #ifndef ZB_PRIM_QUEUE
-#define ZB_PRIM_QUEUE 1120
+#define ZB_PRIM_QUEUE 704
 #endif
-constexpr int kPrimQueue = ZB_PRIM_QUEUE; // primitive items per warp; 1120 >= 31 + 32 lanes x 8 leaves x 4 primitives + 63 survivors of the cheap stage (kept at the end)
+constexpr int kPrimQueue = ZB_PRIM_QUEUE; // primitive items per warp; >= 31 + what one node round may append (coopNodeBudget) + 63 survivors of the cheap stage (kept at the end)
 constexpr int kPrimSlack = 31 + 63;       // what the queue may hold when a node round or a refill starts: < 32 unfiltered items + the survivor list
 constexpr int kRefillLowWater = kNodeStack*3/16;  // refill when the shared node stack is below this
 // private stack entries (<= 4 primitives each) a lane hands over per refill: what the primitive queue can take, and no more

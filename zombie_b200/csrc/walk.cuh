@@ -652,7 +652,7 @@ ZB_DEV bool stepStarPrologue(const SolveArgs& a, Lane<DIM>& L, float& starRadius
 
 // One splat record of a reverse walk: the current ball and the weight the walk carries into it
 // (rws::splatContribution, zombie/variance_reduction/reverse_walk_solver.h:233-283, evaluation-point independent part):
-//   q0 = (centre, R)   q1 = (current normal, v)   q2 = (v * contribution, flags, 0, 0)
+//   q0 = (centre, R)   q1 = (current normal, v)   q2 = (v * contribution, flags, task, step)
 // v = alpha * throughput / pdf (/ normalOffset for samples of the absorbing boundary); flags: bits 0-2 the statistics
 // bucket (0 absorbing, 1 absorbing normal-aligned, 2 reflecting, 3 reflecting normal-aligned, 4 source), bit 3 walk is on
 // the reflecting boundary, bit 4 the ball uses the Yukawa Green's function.
@@ -675,7 +675,10 @@ ZB_DEV void rwsEmit(const SolveArgs& a, const Lane<DIM>& L)
     float4 q0, q1, q2;
     q0.x = L.st.pt[0]; q0.y = L.st.pt[1]; q0.z = DIM == 3 ? L.st.pt[DIM - 1] : 0.0f; q0.w = L.g.R;
     q1.x = L.st.normal[0]; q1.y = L.st.normal[1]; q1.z = DIM == 3 ? L.st.normal[DIM - 1] : 0.0f; q1.w = v;
-    q2.x = v*a.rwsContribution[i]; q2.y = zb_uint_as_float(flags); q2.z = 0.0f; q2.w = 0.0f;
+    // q2.zw: (task, step) — the record's identity, which fixes its place in the gather's order whatever the order of the
+    // appends above was
+    q2.x = v*a.rwsContribution[i]; q2.y = zb_uint_as_float(flags);
+    q2.z = zb_uint_as_float((uint32_t)L.task); q2.w = zb_uint_as_float((uint32_t)L.st.walkLength);
     a.rwsRecords[3*slot] = q0;
     a.rwsRecords[3*slot + 1] = q1;
     a.rwsRecords[3*slot + 2] = q2;

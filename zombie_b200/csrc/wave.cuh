@@ -28,10 +28,10 @@
 #include "walk.cuh"
 
 #ifndef ZB_STAR_MIN_BLOCKS
-#define ZB_STAR_MIN_BLOCKS 1 // resident 128-thread CTAs per SM the star-radius kernel is compiled for (register cap)
+#define ZB_STAR_MIN_BLOCKS 6 // resident 128-thread CTAs per SM the star-radius kernel is compiled for (register cap 85; measured r2m/r2n: 6 > 5, 7, 8)
 #endif
 #ifndef ZB_CLOSEST_MIN_BLOCKS
-#define ZB_CLOSEST_MIN_BLOCKS 1
+#define ZB_CLOSEST_MIN_BLOCKS 6
 #endif
 
 namespace zb {
@@ -55,7 +55,7 @@ struct WaveSlots {
     void *queue;          // WalkState<DIM>[kSplitStack] per slot; null when the settings rule splitting out
     uint32_t *keys;       // Morton key per POSITION of the current order (written by waveStepKernel, sorted by cub)
     const uint32_t *order; // position -> slot
-    unsigned int *live;   // walks alive after the current round
+    unsigned int *live;   // walks alive after the current round; live[1], live[2]: warp tickets of the round's two query kernels
     unsigned long long *taskCounter; // tasks this group has taken; the group owns the tasks first + k*stride
     int taskFirst, taskStride;
     int nSlots;
@@ -116,16 +116,30 @@ ZB_DEV int stripedPosition(int nWarps)
 #endif
 }
 
+// The two query kernels are PERSISTENT: the grid holds as many CTAs as the machine keeps resident, and every warp draws
+// virtual warps (32 striped positions of the slot order each) from a ticket counter until none is left. A launch with one
+// CTA per 128 positions runs in waves — 3.5 of them at 262,144 slots — and the cost of a query is heavy-tailed, so the last
+// wave keeps a few SMs busy while the rest idle (ncu: 16.7 % achieved against 25 % theoretical occupancy); with tickets a
+// warp that drew light queries simply draws again.
+ZB_DEV int nextVirtualWarp(unsigned int *ticket, int nWarps)
+{
+#if defined(__CUDA_ARCH__)
+    unsigned int v = 0u;
+    if ((threadIdx.x & 31) == 0) v = atomicAdd(ticket, 1u);
+    v = __shfl_sync(0xffffffffu, v, 0);
+    return v < (unsigned int)nWarps ? (int)v : -1;
+#else
+    return -1;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------
 // distance query + scalar prologue of the step
 // ------------------------------------------------------------------------------------------
 template <int DIM, bool WOST>
-__global__ void __launch_bounds__(128, ZB_CLOSEST_MIN_BLOCKS) waveClosestKernel(SolveArgs a, WaveSlots w, int nBound, int nWarps)
+ZB_DEV void waveClosestWarp(const SolveArgs& a, const WaveSlots& w, WarpShared& ws, int nBound, int i)
 {
 #if defined(__CUDA_ARCH__)
-    extern __shared__ __align__(16) unsigned char zbShared[];
-    WarpShared& ws = reinterpret_cast<WarpShared *>(zbShared)[threadIdx.x >> 5];
-    const int i = stripedPosition(nWarps);
     int slot = -1;
     int4 m = make_int4(0, 0, 0, 0);
     if (i < nBound) { slot = (int)w.order[i]; m = w.meta[slot]; }
@@ -207,16 +221,26 @@ __global__ void __launch_bounds__(128, ZB_CLOSEST_MIN_BLOCKS) waveClosestKernel(
 #endif
 }
 
-// ------------------------------------------------------------------------------------------
-// star radius
-// ------------------------------------------------------------------------------------------
-template <int DIM>
-__global__ void __launch_bounds__(128, ZB_STAR_MIN_BLOCKS) waveStarKernel(SolveArgs a, WaveSlots w, int nBound, int nWarps)
+template <int DIM, bool WOST>
+__global__ void __launch_bounds__(128, ZB_CLOSEST_MIN_BLOCKS) waveClosestKernel(SolveArgs a, WaveSlots w, int nBound, int nWarps)
 {
 #if defined(__CUDA_ARCH__)
     extern __shared__ __align__(16) unsigned char zbShared[];
     WarpShared& ws = reinterpret_cast<WarpShared *>(zbShared)[threadIdx.x >> 5];
-    const int i = stripedPosition(nWarps);
+    for (int v = nextVirtualWarp(w.live + 1, nWarps); v >= 0; v = nextVirtualWarp(w.live + 1, nWarps)) {
+        waveClosestWarp<DIM, WOST>(a, w, ws, nBound, (int)(threadIdx.x & 31)*nWarps + v);
+        __syncwarp();
+    }
+#endif
+}
+
+// ------------------------------------------------------------------------------------------
+// star radius
+// ------------------------------------------------------------------------------------------
+template <int DIM>
+ZB_DEV void waveStarWarp(const SolveArgs& a, const WaveSlots& w, WarpShared& ws, int nBound, int i)
+{
+#if defined(__CUDA_ARCH__)
     int slot = -1;
     uint32_t flags = 0u;
     if (i < nBound) { slot = (int)w.order[i]; flags = (uint32_t)w.meta[slot].w; }
@@ -232,6 +256,19 @@ __global__ void __launch_bounds__(128, ZB_STAR_MIN_BLOCKS) waveStarKernel(SolveA
         float4 ps = w.projStar[slot];
         ps.w = shrinkStarRadius(a, r, pd.w);
         w.projStar[slot] = ps;
+    }
+#endif
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(128, ZB_STAR_MIN_BLOCKS) waveStarKernel(SolveArgs a, WaveSlots w, int nBound, int nWarps)
+{
+#if defined(__CUDA_ARCH__)
+    extern __shared__ __align__(16) unsigned char zbShared[];
+    WarpShared& ws = reinterpret_cast<WarpShared *>(zbShared)[threadIdx.x >> 5];
+    for (int v = nextVirtualWarp(w.live + 2, nWarps); v >= 0; v = nextVirtualWarp(w.live + 2, nWarps)) {
+        waveStarWarp<DIM>(a, w, ws, nBound, (int)(threadIdx.x & 31)*nWarps + v);
+        __syncwarp();
     }
 #endif
 }
