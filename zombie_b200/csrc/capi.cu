@@ -328,7 +328,7 @@ int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
     cudaStream_t stream = ctx->stream;
     // Slots: enough walks in flight to fill the machine several times over, never more than there are tasks.
     // ZB_WAVE_SLOTS / ZB_WAVE_GROUPS / ZB_WAVE_SORT / ZB_WAVE_BLOCK override (measurements).
-    const int maxSlots = std::max(128, envInt("ZB_WAVE_SLOTS", 262144));
+    const int maxSlots = std::max(128, envInt("ZB_WAVE_SLOTS", 1048576));
     int nGroups = std::min(kMaxWaveGroups, std::max(1, envInt("ZB_WAVE_GROUPS", 1)));
     while (nGroups > 1 && totalTasks < (long long)nGroups*4096) nGroups--; // small solves: one group
     const int sortMode = envInt("ZB_WAVE_SORT", 0);
