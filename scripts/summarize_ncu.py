@@ -15,7 +15,8 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__compute_memory_throughput.avg.pct_of_peak_sustained_elapsed",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "smsp__inst_executed_op_shared_atom.sum"]
+        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "smsp__inst_executed_op_shared_atom.sum",
+        "smsp__warps_eligible.avg.per_cycle_active", "smsp__warps_active.avg.per_cycle_active", "sm__cycles_elapsed.avg"]
 
 
 def ncu(args):
@@ -41,8 +42,14 @@ def main():
                     stalls.append((float(r[i]), h.replace("smsp__warp_issue_stalled_", "").replace("_per_warp_active.pct", "")))
                 except ValueError:
                     pass
+            elif "warps_issue_stalled" in h and h.endswith("per_issue_active.ratio") and "not_issued" not in h:
+                try:
+                    stalls.append((float(r[i]), h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")))
+                except ValueError:
+                    pass
         if stalls:
-            print("  warp stall reasons (% of active warp cycles): " + ", ".join("%s %.1f" % (n, v) for v, n in sorted(stalls, reverse=True)[:8]))
+            tot = sum(v for v, _ in stalls) or 1.0
+            print("  warp stall reasons (share of all stalled-warp samples): " + ", ".join("%s %.1f %%" % (n, 100*v/tot) for v, n in sorted(stalls, reverse=True)[:8]))
     src = ncu(["-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"])
     cur, hdr2, lines = None, None, []
     kernel = None

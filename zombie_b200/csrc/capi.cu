@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(128) closestPointKernel(BvhView bvh, int n, co
     ClosestHit<DIM> hit;
     coopClosestPoint<DIM>(bvh, ws, has, q, r2, hit, status);
     if (!has) return;
+    closestTieBreak<DIM>(bvh, q, hit, status); // exact ties report the largest input index, as FCPW's Baseline does (queries.cuh)
     bool found = hit.prim >= 0;
     prim[i] = found ? bvh.primIndex[hit.prim] : -1;
     dist[i] = found ? hit.d : kMaxFloat;
@@ -345,6 +346,9 @@ int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
         tailPerSm = std::max(1, tailPerSm);
     }
 
+    const bool star = WOST && a.hasReflecting;
+    // the star-radius query as two kernels (private phase, pooled phase: wave.cuh) or as one (ZB_WAVE_STAR_SPLIT=0)
+    const bool starSplit = star && envInt("ZB_WAVE_STAR_SPLIT", 1) != 0;
     WaveGroup groups[kMaxWaveGroups];
     size_t sortBytes = 0;
     for (int pass = 0; pass < 2; pass++) {
@@ -362,6 +366,15 @@ int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
             w.dirThr = c.take<float4>(n); w.acc = c.take<float4>(n); w.rng = c.take<ulonglong2>(n);
             w.meta = c.take<int4>(n); w.meta2 = c.take<int4>(n);
             w.queue = needQueue ? (void *)c.take<WalkState<DIM>>(n*kSplitStack) : nullptr;
+            if (starSplit) {
+                // hand-over of the star-radius query between its two kernels: per virtual thread (slots + one CTA of padding)
+                const size_t nt = n + 128;
+                const size_t rows = std::min<size_t>(kStackSize, 1 + 7*(size_t)kPhase1Budget); // a pop adds at most 7 entries net
+                w.starStride = nt;
+                w.starStack = c.take<uint2>(rows*nt);
+                w.starPending = c.take<uint2>(nt);
+                w.starWarpMask = c.take<uint32_t>(nt/32);
+            }
             w.keys = c.take<uint32_t>(n);
             G.keysOut = c.take<uint32_t>(n);
             G.orderA = c.take<uint32_t>(n);
@@ -403,10 +416,12 @@ int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
 
     ZB_CUDA(cudaFuncSetAttribute(waveClosestKernel<DIM, WOST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
     if (WOST) ZB_CUDA(cudaFuncSetAttribute(waveStarKernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
+    if (WOST) ZB_CUDA(cudaFuncSetAttribute(waveStarPooledKernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
 
     int closestResident = 1, starResident = 1;
     ZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&closestResident, waveClosestKernel<DIM, WOST>, qThreads, qSmem));
-    if (WOST) ZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&starResident, waveStarKernel<DIM>, qThreads, qSmem));
+    if (WOST && !starSplit) ZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&starResident, waveStarKernel<DIM>, qThreads, qSmem));
+    if (WOST && starSplit) ZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&starResident, waveStarPooledKernel<DIM>, qThreads, qSmem));
     const int residentScale = std::max(1, envInt("ZB_WAVE_PERSIST", 1)); // 0/1: one resident wave; k > 1: k waves' worth of CTAs
     closestResident = std::max(1, closestResident)*ctx->smCount*residentScale/nGroups;
     starResident = std::max(1, starResident)*ctx->smCount*residentScale/nGroups;
@@ -424,7 +439,6 @@ int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
         ctx->launches += 1;
     }
 
-    const bool star = WOST && a.hasReflecting;
     int remaining = nGroups, rounds = 0;
     while (remaining > 0) {
         for (int g = 0; g < nGroups; g++) {
@@ -443,8 +457,13 @@ int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
                     const int virtualWarps = qBlocks*(qThreads/32);
                     // persistent grids: the CTAs the machine keeps resident draw the virtual warps from a ticket counter
                     waveClosestKernel<DIM, WOST><<<std::min(qBlocks, closestResident), qThreads, qSmem, G.stream>>>(a, w, G.nBound, virtualWarps);
-                    if (star) waveStarKernel<DIM><<<std::min(qBlocks, starResident), qThreads, qSmem, G.stream>>>(a, w, G.nBound, virtualWarps);
-                    ctx->launches += star ? 2 : 1;
+                    if (starSplit) {
+                        waveStarPrivateKernel<DIM><<<blocksFor(virtualWarps*32, 128), 128, 0, G.stream>>>(a, w, G.nBound, virtualWarps);
+                        waveStarPooledKernel<DIM><<<std::min(qBlocks, starResident), qThreads, qSmem, G.stream>>>(a, w, G.nBound, virtualWarps);
+                    } else if (star) {
+                        waveStarKernel<DIM><<<std::min(qBlocks, starResident), qThreads, qSmem, G.stream>>>(a, w, G.nBound, virtualWarps);
+                    }
+                    ctx->launches += starSplit ? 3 : (star ? 2 : 1);
                 }
                 waveStepKernel<DIM, WOST><<<blocksFor(G.nBound, 128), 128, 0, G.stream>>>(a, w, G.nBound);
                 ZB_CUDA(cudaGetLastError());

@@ -192,13 +192,28 @@ ZB_COOP void coopPushChildren(WarpShared& ws, int& nodeTop, int& primTop, int la
 // key with flag bits in the low 3 bits, y = node index or kLeafFlag | count << 28 | first primitive) to the
 // shared lists. starFlags: bit 2 of x is the "no silhouette" mark of the star-radius traversal. Every lane calls.
 // Only called with primTop < 32 and nodeTop < kRefillLowWater, so the lists cannot overflow.
-ZB_COOP void coopRefill(WarpShared& ws, int& nodeTop, int& primTop, int lane, const uint2 *stack, int& sp, bool starFlags)
+//
+// STACK: where the lanes' private stacks live. LocalStack: the lane's own array (a query run by one function call);
+// StridedStack: rows of a global-memory scratch, entry i of virtual thread t at p[i*stride + t] (the wavefront's star-radius
+// query, whose private phase runs in a kernel of its own and hands the unfinished traversals over through HBM, wave.cuh).
+struct LocalStack {
+    const uint2 *p;
+    ZB_COOP uint2 at(int i) const { return p[i]; }
+};
+struct StridedStack {
+    const uint2 *p;
+    size_t stride;
+    ZB_COOP uint2 at(int i) const { return p[(size_t)i*stride]; }
+};
+
+template <class STACK>
+ZB_COOP void coopRefill(WarpShared& ws, int& nodeTop, int& primTop, int lane, const STACK& stack, int& sp, bool starFlags)
 {
     int take = min(sp, kRefillPerLane);
     int nNodes = 0, nPrims = 0;
 #pragma unroll 1
     for (int k = 0; k < take; k++) {
-        uint32_t y = stack[sp - take + k].y;
+        uint32_t y = stack.at(sp - take + k).y;
         if (y & kLeafFlag) nPrims += (int)((y >> 28) & 7u); else nNodes++;
     }
     int incl = warpInclusiveSum(nNodes | (nPrims << 16), lane), total = zb_shfl(incl, 31);
@@ -206,7 +221,7 @@ ZB_COOP void coopRefill(WarpShared& ws, int& nodeTop, int& primTop, int lane, co
     int slotN = nodeTop + inclN - nNodes, slotP = primTop + inclP - nPrims;
 #pragma unroll 1
     for (int k = 0; k < take; k++) { // bottom to top: the lane's nearest entry ends on top of its group
-        uint2 e = stack[sp - take + k];
+        uint2 e = stack.at(sp - take + k);
         uint32_t sil = starFlags ? (e.x >> 2) & 1u : 0u;
         if (e.y & kLeafFlag) {
             uint32_t first = e.y & 0x0fffffffu, count = (e.y >> 28) & 7u;
@@ -257,7 +272,7 @@ ZB_COOP_NOINLINE void coopClosestPoint(const BvhView& bvh, WarpShared& ws, bool 
 
     while (true) {
         if (primTop < 32 && nodeTop < kRefillLowWater && zb_ballot(sp > 0) != 0u) {
-            coopRefill(ws, nodeTop, primTop, lane, stack, sp, false);
+            coopRefill(ws, nodeTop, primTop, lane, LocalStack{stack}, sp, false);
             zb_syncwarp();
         }
         if (nodeTop == 0 && primTop == 0 && fullTop == 0) break;
@@ -363,24 +378,14 @@ ZB_COOP_NOINLINE void coopClosestPoint(const BvhView& bvh, WarpShared& ws, bool 
 // star radius
 // ------------------------------------------------------------------------------------------
 
-// ReflectanceBvh::computeSquaredStarRadius / findClosestSilhouettePoint for up to 32 queries at once.
-// Every lane of the warp must call this; returns the squared star radius (<= r2max) of the lane's query.
-template <int DIM>
-ZB_COOP_NOINLINE float coopStarRadius2(const BvhView& bvh, WarpShared& ws, bool hasQuery, const Vec<DIM>& x, float r2max,
-                                 bool flip, float precision, int *status)
+// Phase 2 of the star-radius query: pools the traversals phase 1 left unfinished. Every lane of the warp calls; hasQuery:
+// the lane owns a query (x, flip) whose radius so far is r2own and whose unfinished traversal is stack[0..sp). Returns the
+// squared star radius of the lane's query (r2max for lanes without one).
+template <int DIM, class STACK>
+ZB_COOP float coopStarPooled(const BvhView& bvh, WarpShared& ws, bool hasQuery, const Vec<DIM>& x, float r2own, float r2max,
+                             bool flip, float precision, int *status, const STACK& stack, int sp)
 {
     const int lane = zb_lane();
-    // ---- phase 1: private depth-first traversal with a budget
-    uint2 stack[kStackSize];
-    int sp = 0;
-    float r2own = r2max;
-    if (hasQuery) {
-        stack[sp++] = make_uint2(0u, 0u);
-        starRadiusDfs<DIM, true>(bvh, x, r2own, flip, precision, stack, sp, kPhase1Budget, status);
-    }
-    if (zb_ballot(sp > 0) == 0u) return hasQuery ? r2own : r2max;
-
-    // ---- phase 2: pool the unfinished traversals
     zb_syncwarp();
     ws.qx[lane] = x[0];
     ws.qy[lane] = x[1];
@@ -517,6 +522,25 @@ ZB_COOP_NOINLINE float coopStarRadius2(const BvhView& bvh, WarpShared& ws, bool 
     float r2 = coopRadius2(ws, lane);
     zb_syncwarp();
     return hasQuery ? r2 : r2max;
+}
+
+// ReflectanceBvh::computeSquaredStarRadius / findClosestSilhouettePoint for up to 32 queries at once, both phases in one
+// call. Every lane of the warp must call this; returns the squared star radius (<= r2max) of the lane's query.
+template <int DIM>
+ZB_COOP_NOINLINE float coopStarRadius2(const BvhView& bvh, WarpShared& ws, bool hasQuery, const Vec<DIM>& x, float r2max,
+                                 bool flip, float precision, int *status)
+{
+    // ---- phase 1: private depth-first traversal with a budget
+    uint2 stack[kStackSize];
+    int sp = 0;
+    float r2own = r2max;
+    if (hasQuery) {
+        stack[sp++] = make_uint2(0u, 0u);
+        starRadiusDfs<DIM, true>(bvh, x, r2own, flip, precision, stack, sp, kPhase1Budget, status);
+    }
+    if (zb_ballot(sp > 0) == 0u) return hasQuery ? r2own : r2max;
+    // ---- phase 2: pool the unfinished traversals
+    return coopStarPooled<DIM>(bvh, ws, hasQuery, x, r2own, r2max, flip, precision, status, LocalStack{stack}, sp);
 }
 
 } // namespace zb

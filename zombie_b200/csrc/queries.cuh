@@ -511,6 +511,64 @@ ZB_DEV bool closestPoint(const BvhView& bvh, const Vec<DIM>& x, float r2, Closes
     return hit.prim >= 0;
 }
 
+// Which primitive a closest-point query REPORTS when several are exactly equidistant (the closest point lies on a
+// shared edge or vertex: a quarter of random queries on a coarse mesh). FCPW's acceptance test is d*d <= r2
+// (triangles.inl:479, line_segments.inl), so a primitive visited later replaces an equidistant earlier one and the
+// winner depends on the visiting order: the tree topology for the BVH (bvh.inl:1331-1335), the input order for the
+// brute-force Baseline aggregate (baseline.inl:349-372), which therefore returns the LARGEST input index among the
+// primitives whose squared distance d*d equals the minimum. That is the rule here: a second traversal with the search
+// radius fixed at the minimum visits every primitive that can tie (boxes only prune beyond the radius) and keeps the
+// largest caller index; distance and point are that primitive's. Only the batched entry point pays for it — the walk
+// reads neither index nor normal.
+template <int DIM>
+ZB_DEV void closestTieBreak(const BvhView& bvh, const Vec<DIM>& x, ClosestHit<DIM>& hit, int *status)
+{
+    if (hit.prim < 0) return;
+    float r2 = hit.d*hit.d;
+    int bestCaller = zb_ldg(bvh.primIndex + hit.prim);
+    uint2 stack[kStackSize];
+    int sp = 0;
+    stack[sp++] = make_uint2(0u, 0u);
+    while (sp > 0) {
+        uint2 e = stack[--sp];
+        if (e.y & kLeafFlag) {
+            uint32_t first = e.y & 0x0fffffffu, count = (e.y >> 28) & 7u;
+            for (uint32_t i = 0; i < count; i++) {
+                if ((int)(first + i) == hit.prim) continue;
+                float4 cp = primClosestCall<DIM>(bvh.prims, first + i, x);
+                float d2 = cp.w*cp.w;
+                if (d2 > r2) continue;
+                int caller = zb_ldg(bvh.primIndex + first + i);
+                if (d2 < r2 || caller > bestCaller) { // d2 < r2 cannot happen after a complete search; kept for robustness
+                    r2 = d2;
+                    bestCaller = caller;
+                    hit.d = cp.w;
+                    hit.prim = (int)(first + i);
+                    hit.p[0] = cp.x; hit.p[1] = cp.y;
+                    if (DIM == 3) hit.p[DIM - 1] = cp.z;
+                }
+            }
+            continue;
+        }
+        NodeRegs n;
+        loadNode(bvh.nodes, e.y, n);
+        NodeFrame<DIM> f = nodeFrame<DIM>(n);
+        ZB_CHILD_LOOP
+        for (int c = 0; c < 8; c++) {
+            uint32_t meta = childMeta(n, c);
+            if (meta == 0u) continue;
+            float lo[DIM], hi[DIM], d2min, d2max;
+            childBox<DIM>(n, f, c, lo, hi);
+            boxDistance2<DIM>(lo, hi, x, d2min, d2max);
+            // 8 ulps of slack as in the search itself (keys are rounded down): the box bound and the primitive's distance
+            // are rounded differently
+            if (keyValue(zb_float_as_uint(d2min) & ~7u) > r2) continue;
+            if (sp < kStackSize) stack[sp++] = make_uint2(0u, childRef(n, meta));
+            else if (status) zb_atomic_or(status, kStatusStackOverflow);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // rays
 // ------------------------------------------------------------------------------------------

@@ -30,6 +30,9 @@
 #ifndef ZB_STAR_MIN_BLOCKS
 #define ZB_STAR_MIN_BLOCKS 6 // resident 128-thread CTAs per SM the star-radius kernel is compiled for (register cap 85; measured r2m/r2n: 6 > 5, 7, 8)
 #endif
+#ifndef ZB_STAR_PRIVATE_MIN_BLOCKS
+#define ZB_STAR_PRIVATE_MIN_BLOCKS 8 // the private phase of the star-radius query needs no shared memory: registers alone bound its occupancy
+#endif
 #ifndef ZB_CLOSEST_MIN_BLOCKS
 #define ZB_CLOSEST_MIN_BLOCKS 6
 #endif
@@ -56,6 +59,13 @@ struct WaveSlots {
     uint32_t *keys;       // Morton key per POSITION of the current order (written by waveStepKernel, sorted by cub)
     const uint32_t *order; // position -> slot
     unsigned int *live;   // walks alive after the current round; live[1], live[2]: warp tickets of the round's two query kernels
+    // hand-over of the star-radius query from its private phase to its pooled phase (waveStarPrivateKernel -> waveStarPooledKernel),
+    // indexed by VIRTUAL THREAD t = 32*virtual warp + lane: the unfinished traversal's stack entries (entry i at
+    // starStack[i*starStride + t]), its radius so far and stack size, and per virtual warp the lanes that have one
+    uint2 *starStack;
+    uint2 *starPending;   // x: squared radius after the private phase (float bits); y: stack entries left
+    uint32_t *starWarpMask;
+    size_t starStride;
     unsigned long long *taskCounter; // tasks this group has taken; the group owns the tasks first + k*stride
     int taskFirst, taskStride;
     int nSlots;
@@ -237,6 +247,8 @@ __global__ void __launch_bounds__(128, ZB_CLOSEST_MIN_BLOCKS) waveClosestKernel(
 // ------------------------------------------------------------------------------------------
 // star radius
 // ------------------------------------------------------------------------------------------
+// One kernel runs both phases of the cooperative query (coop.cuh). Kept for A/B measurements (ZB_WAVE_STAR_SPLIT=0) and as
+// the statement of what the two kernels below compute together.
 template <int DIM>
 ZB_DEV void waveStarWarp(const SolveArgs& a, const WaveSlots& w, WarpShared& ws, int nBound, int i)
 {
@@ -268,6 +280,90 @@ __global__ void __launch_bounds__(128, ZB_STAR_MIN_BLOCKS) waveStarKernel(SolveA
     WarpShared& ws = reinterpret_cast<WarpShared *>(zbShared)[threadIdx.x >> 5];
     for (int v = nextVirtualWarp(w.live + 2, nWarps); v >= 0; v = nextVirtualWarp(w.live + 2, nWarps)) {
         waveStarWarp<DIM>(a, w, ws, nBound, (int)(threadIdx.x & 31)*nWarps + v);
+        __syncwarp();
+    }
+#endif
+}
+
+// The shipped form: the two phases of the query are two kernels. The fused kernel is 80 KB of SASS of which 44 KB are hot
+// (private depth-first loop, pooled node / filter / full rounds, the primitive test both call); with 24 warps per SM each
+// in a different phase, 48 % of its warp-stall samples are `no_instruction` (profiles/r2_wave_steady_ncu.txt: the 32 KB
+// instruction cache thrashes) and the issue slots are 42 % busy, against 4 % and 69 % for the distance query's 25 KB loop.
+// Split, every warp of a launch runs the same loop, the private phase needs no shared memory (more resident warps), and the
+// pooled phase only sees the warps that have something left. The hand-over — radius so far and the unfinished stack, a few
+// dozen bytes for the queries that have one — goes through HBM. Virtual warps are composed exactly as in the fused
+// kernel, so the two forms return the same bits.
+template <int DIM>
+__global__ void __launch_bounds__(128, ZB_STAR_PRIVATE_MIN_BLOCKS) waveStarPrivateKernel(SolveArgs a, WaveSlots w, int nBound, int nWarps)
+{
+#if defined(__CUDA_ARCH__)
+    const int t = blockIdx.x*blockDim.x + threadIdx.x; // virtual thread: virtual warp t >> 5 (the grid holds nWarps of them), lane t & 31
+    if ((t >> 5) >= nWarps) return;
+    const int i = (t & 31)*nWarps + (t >> 5);
+    int slot = -1;
+    uint32_t flags = 0u;
+    if (i < nBound) { slot = (int)w.order[i]; flags = (uint32_t)w.meta[slot].w; }
+    const bool qs = (flags & (kWfActive | kWfNeedStar)) == (kWfActive | kWfNeedStar);
+    int sp = 0;
+    if (qs) {
+        float4 pd = w.ptDist[slot];
+        float trivial = 0.0f, r2max = 0.0f;
+        const float eps = a.ws.epsilonShellForReflectingBoundary;
+        starQueryNeeded<DIM>(a, eps, pd.w, trivial, r2max);
+        uint2 stack[kStackSize];
+        float r2 = r2max;
+        stack[sp++] = make_uint2(0u, 0u);
+        starRadiusDfs<DIM, true>(a.reflecting, vec3of<DIM>(pd), r2, !(flags & kWfFlip), a.ws.silhouettePrecision, stack, sp, kPhase1Budget, a.status);
+        if (sp == 0) {
+            float r = starQueryResult(a, r2, r2max, eps, pd.w);
+            float4 ps = w.projStar[slot];
+            ps.w = shrinkStarRadius(a, r, pd.w);
+            w.projStar[slot] = ps;
+        } else {
+            w.starPending[t] = make_uint2(zb_float_as_uint(r2), (uint32_t)sp);
+            for (int k = 0; k < sp; k++) w.starStack[(size_t)k*w.starStride + t] = stack[k];
+        }
+    }
+    const unsigned pending = __ballot_sync(0xffffffffu, sp > 0);
+    if ((t & 31) == 0) w.starWarpMask[t >> 5] = pending;
+#endif
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(128, ZB_STAR_MIN_BLOCKS) waveStarPooledKernel(SolveArgs a, WaveSlots w, int nBound, int nWarps)
+{
+#if defined(__CUDA_ARCH__)
+    extern __shared__ __align__(16) unsigned char zbShared[];
+    WarpShared& ws = reinterpret_cast<WarpShared *>(zbShared)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    for (int v = nextVirtualWarp(w.live + 2, nWarps); v >= 0; v = nextVirtualWarp(w.live + 2, nWarps)) {
+        const uint32_t pending = w.starWarpMask[v];
+        if (pending == 0u) continue;
+        const bool qs = (pending >> lane) & 1u;
+        const int t = 32*v + lane;
+        int slot = -1;
+        uint32_t flags = 0u;
+        float4 pd = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        float trivial = 0.0f, r2max = 0.0f, r2own = 0.0f;
+        int sp = 0;
+        const float eps = a.ws.epsilonShellForReflectingBoundary;
+        if (qs) {
+            slot = (int)w.order[lane*nWarps + v];
+            flags = (uint32_t)w.meta[slot].w;
+            pd = w.ptDist[slot];
+            starQueryNeeded<DIM>(a, eps, pd.w, trivial, r2max);
+            uint2 pr = w.starPending[t];
+            r2own = zb_uint_as_float(pr.x);
+            sp = (int)pr.y;
+        }
+        float r2 = coopStarPooled<DIM>(a.reflecting, ws, qs, vec3of<DIM>(pd), qs ? r2own : r2max, r2max, !(flags & kWfFlip), a.ws.silhouettePrecision,
+                                       a.status, StridedStack{w.starStack + t, w.starStride}, sp);
+        if (qs) {
+            float r = starQueryResult(a, r2, r2max, eps, pd.w);
+            float4 ps = w.projStar[slot];
+            ps.w = shrinkStarRadius(a, r, pd.w);
+            w.projStar[slot] = ps;
+        }
         __syncwarp();
     }
 #endif
