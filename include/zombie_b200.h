@@ -199,7 +199,11 @@ int zb_host_bvh_check(int dim, const float *positions, int nVertices, const int3
 /* ---- batched geometric queries (host buffers). These are what the GeometricQueries callbacks
  * bind to; they also expose the primitive index so parity with FCPW can be checked exactly. ---- */
 /* Aggregate::findClosestPoint with BoundingSphere(x, maxR2) (fcpw_geometric_queries.h:1069-1096;
- * fcpw/aggregates/bvh.inl:1391-1418). prim = -1 when nothing lies within the radius. normal may be NULL. */
+ * fcpw/aggregates/bvh.inl:1391-1418). prim = -1 when nothing lies within the radius. normal may be NULL.
+ * Exact ties: when several primitives are equidistant in FCPW's sense (equal d*d; the closest point lies on a
+ * shared edge or vertex), FCPW reports the one it visits last — its BVH by tree topology, its brute-force
+ * Baseline aggregate (baseline.inl:349-372) by input order. This function reports the Baseline's answer on
+ * every query: the LARGEST input index among the tied primitives, with that primitive's point and normal. */
 int zb_closest_point(zb_scene *scene, int boundary, int n, const float *x, const float *maxRadius /* NULL = inf */,
                      int32_t *prim, float *dist, float *pt, float *normal);
 /* Aggregate::intersect(Ray(origin, dir, tMax)) closest hit (bvh.inl:753-771). prim = -1 on miss. */

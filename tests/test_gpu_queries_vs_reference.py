@@ -65,6 +65,45 @@ def test_queries_match_compiled_reference(ctx, ref, dim, kind):
     rs.close(); gs.close()
 
 
+@pytest.mark.parametrize("dim", [3, 2])
+def test_closest_point_index_is_the_reference_baselines(ctx, ref, dim):
+    """Primitive index, bit for bit. When a query is exactly equidistant from several primitives (closest point on a shared
+    edge or vertex) FCPW keeps the one it visits LAST (d*d <= r2 replaces, triangles.inl:479): the reference's BVH answers
+    by its tree topology, the reference's brute-force Baseline aggregate (baseline.inl:349-372) by input order — the largest
+    index among the tied primitives. zb_closest_point states that rule (include/zombie_b200.h) and must therefore equal the
+    Baseline on EVERY query: index, distance, point and normal, with no tie allowance. The reference's BVH must then agree
+    except on exact ties, where its distance and point are still identical."""
+    whole, absorbing, reflecting = cases.mesh3d(4) if dim == 3 else cases.mesh2d(2048)
+    kw = cases.scene_kwargs(dim, abi.REFLECTING_NEUMANN, absorbing, reflecting)
+    nq = 20000
+    x = cases.query_points(nq, dim, 0.99, seed=241)
+    # queries ON vertices and edge midpoints of the boundary and along vertex normals: ties of 2 up to 6 primitives
+    pos, idx = absorbing
+    rng = np.random.RandomState(7)
+    v = pos[idx[rng.randint(0, len(idx), 2000), 0]]
+    e = 0.5*(pos[idx[:2000, 0]] + pos[idx[:2000, 1]])
+    x = np.concatenate([x, v, (v*np.float32(0.75)).astype(np.float32), e]).astype(np.float32)
+    rb, rs, gs = ref.RefScene(dim, use_baseline=True, **kw), ref.RefScene(dim, **kw), native.Scene(ctx, dim, **kw)
+    ties = 0
+    for which in (abi.ABSORBING, abi.REFLECTING):
+        bprim, bd, bpt, bn = rb.closest_point(which, x)
+        gprim, gd, gpt, gn = gs.closest_point(which, x)
+        rprim, rd, rpt, rn = rs.closest_point(which, x)
+        assert np.array_equal(bprim, gprim)
+        assert np.array_equal(bd, gd) and np.array_equal(bpt, gpt)
+        assert np.abs(bn - gn).max() <= 1e-6
+        other = rprim != gprim
+        ties += int(other.sum())
+        assert np.array_equal(rd[other], gd[other]) and (rprim[other] < gprim[other]).all()
+        # bounded searches follow the same rule
+        rad = np.full(len(x), 0.2, np.float32)
+        bprim, bd, _, _ = rb.closest_point(which, x, rad)
+        gprim, gd, _, _ = gs.closest_point(which, x, rad)
+        assert np.array_equal(bprim, gprim) and np.array_equal(bd, gd) and (bprim < 0).any() and (bprim >= 0).any()
+    assert ties > 100   # the rule is exercised
+    rb.close(); rs.close(); gs.close()
+
+
 def test_full_size_mesh_matches_compiled_reference(ctx, ref):
     """The BASELINE headline geometry itself — the 1,310,720-triangle bumpy icosphere of config C3, Robin z > 0 /
     Dirichlet z < 0 — against the compiled reference: 20,000 queries of every kind (closest point on both boundaries, first
