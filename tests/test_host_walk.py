@@ -256,6 +256,12 @@ def check_star_radius_against_reference(ref, host_query, tmp_path, dim, kind, mu
     assert r.returncode == 0, r.stdout
     out = np.fromfile(os.path.join(d, "query_out.bin"), np.float32).reshape(-1, 3)
     assert np.array_equal(out[:, 0], dr)                         # closest-point distance: bit-identical to FCPW
+    # primitive index: the reference's Baseline aggregate on every query (ties go to the largest input index, queries.cuh)
+    rb = ref.RefScene(dim, use_baseline=True, **kw)
+    bprim, bd, _, _ = rb.closest_point(abi.REFLECTING, x)
+    rb.close()
+    gprim = np.fromfile(os.path.join(d, "query_prim.bin"), np.int32)
+    assert np.array_equal(bd, dr) and np.array_equal(gprim, bprim)
     rr = rs.star_radius(x, np.full(len(x), 1e-3, np.float32), da)
     for col, name in ((1, "trigonometric node test"), (2, "algebraic node test + fast primitive test")):
         g = out[:, col]

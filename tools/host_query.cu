@@ -52,11 +52,14 @@ int run(const std::string& dir, int kind, float mu)
     a.status = &status;
     int n = (int)pt.size()/DIM;
     std::vector<float> out(3*(size_t)n);
+    std::vector<int> prim(n);
     for (int i = 0; i < n; i++) {
         Vec<DIM> x = loadVec<DIM>(&pt[DIM*i]);
         ClosestHit<DIM> hit;
         closestPoint<DIM>(v, x, kMaxFloat, hit, &status);
         out[3*i] = hit.d;
+        closestTieBreak<DIM>(v, x, hit, &status); // the index rule of the batched entry point (largest tied input index)
+        prim[i] = hit.prim >= 0 && hit.d == out[3*i] ? v.primIndex[hit.prim] : -1;
         out[3*i + 1] = starRadiusQuery<DIM>(a, x, 1e-3f, maxr[i], 1e-3f, false);
         // the traversal the kernels run in their private phase: algebraic node test, fast primitive test
         float r2max = maxr[i] < kMaxFloat ? maxr[i]*maxr[i] : kMaxFloat, r2 = r2max;
@@ -68,6 +71,9 @@ int run(const std::string& dir, int kind, float mu)
     }
     FILE *f = fopen((dir + "/query_out.bin").c_str(), "wb");
     fwrite(out.data(), 4, out.size(), f);
+    fclose(f);
+    f = fopen((dir + "/query_prim.bin").c_str(), "wb");
+    fwrite(prim.data(), 4, prim.size(), f);
     fclose(f);
     printf("queries %d status %d\n", n, status);
     return status;
