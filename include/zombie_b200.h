@@ -211,6 +211,16 @@ int zb_intersect_ray(zb_scene *scene, int boundary, int n, const float *origin, 
                      int32_t *prim, float *dist, float *pt, float *normal);
 /* !Aggregate::hasLineOfSight(a, b) (fcpw/core/primitive.h:202-212): 1 = occluded */
 int zb_occluded(zb_scene *scene, int boundary, int n, const float *a, const float *b, uint8_t *occluded);
+/* Aggregate::intersect(ray, interactions, checkForOcclusion = false, recordAllHits = true)
+ * (fcpw/aggregates/bvh.inl:890-1028, what intersect{Absorbing,Reflecting}BoundaryAllHits bind to,
+ * fcpw_geometric_queries.h:1116-1136) reduced to its return value: the number of distinct hits within tMax — hits
+ * sorted by distance, neighbours merged when Interaction::operator== holds (interaction.h:20-25). */
+int zb_count_ray_hits(zb_scene *scene, int boundary, int n, const float *origin, const float *dir, const float *tMax /* NULL = inf */,
+                      int32_t *count);
+/* GeometricQueries::insideDomain (core/geometric_queries.h:357-371): 1 when the all-hits counts over both boundaries
+ * along +x, +y (, +z) are all odd; always 1 for a scene created with domainIsWatertight = 0. The inside test of
+ * the domain samplers (variance_reduction/domain_samplers.h:96) and of the demo's solve-region masks. */
+int zb_inside_domain(zb_scene *scene, int n, const float *x, uint8_t *inside);
 /* Aggregate::intersect(sphere, randNums, branchTraversalWeight) (bvh.inl:1257-1288) with the
  * harmonic branch weight of getBranchTraversalWeightCallback (fcpw_geometric_queries.h:1391-1398).
  * prim = -1 when no primitive was sampled. */

@@ -53,6 +53,8 @@ def lib():
         _lib.zref_closest_point.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p]*6 + [C.c_int]
         _lib.zref_intersect_ray.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p]*7 + [C.c_int]
         _lib.zref_occluded.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p]*3 + [C.c_int]
+        _lib.zref_count_ray_hits.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p]*4 + [C.c_int]
+        _lib.zref_inside_domain.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         _lib.zref_sample_sphere.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p]*7 + [C.c_int]
         _lib.zref_star_radius.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
                                           C.c_void_p, C.c_void_p, C.c_int]
@@ -211,6 +213,22 @@ class RefScene:
         rc = self._lib.zref_occluded(self._h, which, len(a), abi.ptr(a), abi.ptr(b), abi.ptr(out), threads)
         assert rc == 0
         return out
+
+    def count_ray_hits(self, which, origin, direction, tmax=None, threads=0):
+        o, d = _f32(origin), _f32(direction)
+        t = None if tmax is None else _f32(tmax)
+        out = np.zeros(len(o), np.int32)
+        rc = self._lib.zref_count_ray_hits(self._h, which, len(o), abi.ptr(o), abi.ptr(d), abi.ptr(t) if t is not None else None,
+                                           abi.ptr(out), threads)
+        assert rc == 0
+        return out
+
+    def inside_domain(self, x, threads=0):
+        x = _f32(x)
+        out = np.zeros(len(x), np.uint8)
+        rc = self._lib.zref_inside_domain(self._h, len(x), abi.ptr(x), abi.ptr(out), threads)
+        assert rc == 0
+        return out.astype(bool)
 
     def sample_sphere(self, x, radius, rand_nums, threads=0):
         x, radius, u = _f32(x), _f32(radius), _f32(rand_nums)

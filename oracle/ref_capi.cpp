@@ -220,6 +220,27 @@ int closestPoint(RefScene<DIM>& s, int which, int n, const float *x, const float
 }
 
 template <size_t DIM>
+int countRayHits(RefScene<DIM>& s, int which, int n, const float *o, const float *d, const float *tMax, int32_t *count, int nThreads)
+{
+    fcpw::Aggregate<DIM> *agg = s.aggregate(which);
+    if (!agg) return ZB_ERR_INVALID_ARGUMENT;
+    forEach<DIM>(n, nThreads, [&](int i) {
+        // fcpw_geometric_queries.h:1116-1136 (intersectAbsorbingBoundaryAllHits), origin not on the boundary
+        fcpw::Ray<DIM> r(toVec<DIM>(o + DIM*i), toVec<DIM>(d + DIM*i), tMax ? tMax[i] : fcpw::maxFloat);
+        std::vector<fcpw::Interaction<DIM>> is;
+        count[i] = agg->intersect(r, is, false, true);
+    });
+    return ZB_OK;
+}
+
+template <size_t DIM>
+int insideDomain(RefScene<DIM>& s, int n, const float *x, uint8_t *inside, int nThreads)
+{
+    forEach<DIM>(n, nThreads, [&](int i) { inside[i] = s.queries->insideDomain(toVec<DIM>(x + DIM*i)) ? 1 : 0; });
+    return ZB_OK;
+}
+
+template <size_t DIM>
 int intersectRay(RefScene<DIM>& s, int which, int n, const float *o, const float *d, const float *tMax,
                  int32_t *prim, float *dist, float *pt, float *normal, int nThreads)
 {
@@ -562,6 +583,19 @@ int zref_intersect_ray(void *scene, int which, int n, const float *o, const floa
     AnyScene *s = (AnyScene *)scene;
     return DISPATCH(s, intersectRay<2>(*s->s2, which, n, o, d, tMax, prim, dist, pt, normal, nThreads),
                        intersectRay<3>(*s->s3, which, n, o, d, tMax, prim, dist, pt, normal, nThreads));
+}
+
+int zref_count_ray_hits(void *scene, int which, int n, const float *o, const float *d, const float *tMax, int32_t *count, int nThreads)
+{
+    AnyScene *s = (AnyScene *)scene;
+    return DISPATCH(s, countRayHits<2>(*s->s2, which, n, o, d, tMax, count, nThreads),
+                       countRayHits<3>(*s->s3, which, n, o, d, tMax, count, nThreads));
+}
+
+int zref_inside_domain(void *scene, int n, const float *x, uint8_t *inside, int nThreads)
+{
+    AnyScene *s = (AnyScene *)scene;
+    return DISPATCH(s, insideDomain<2>(*s->s2, n, x, inside, nThreads), insideDomain<3>(*s->s3, n, x, inside, nThreads));
 }
 
 int zref_occluded(void *scene, int which, int n, const float *a, const float *b, uint8_t *out, int nThreads)

@@ -142,6 +142,37 @@ __global__ void intersectRayKernel(BvhView bvh, int n, const float *origin, cons
     if (normal) storeVec<DIM>(normal + (size_t)DIM*i, nrm);
 }
 
+// Aggregate::intersect(ray, interactions, false, true) reduced to its return value (number of distinct hits)
+template <int DIM>
+__global__ void countRayHitsKernel(BvhView bvh, int n, const float *origin, const float *dir, const float *tMax, int *count, int *status)
+{
+    int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Vec<DIM> o = loadVec<DIM>(origin + (size_t)DIM*i), d = loadVec<DIM>(dir + (size_t)DIM*i);
+    count[i] = countRayHits<DIM>(bvh, o, d, tMax ? tMax[i] : kMaxFloat, status);
+}
+
+// GeometricQueries::insideDomain (core/geometric_queries.h:357-371): one all-hits ray along each coordinate axis over both
+// boundaries; inside when every count is odd
+template <int DIM>
+__global__ void insideDomainKernel(BvhView absorbing, BvhView reflecting, int hasAbsorbing, int hasReflecting, int n, const float *x,
+                                   uint8_t *inside, int *status)
+{
+    int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Vec<DIM> o = loadVec<DIM>(x + (size_t)DIM*i);
+    bool in = true;
+    for (int axis = 0; axis < DIM; axis++) {
+        Vec<DIM> d = vzero<DIM>();
+        d[axis] = 1.0f;
+        int hits = 0;
+        if (hasAbsorbing) hits += countRayHits<DIM>(absorbing, o, d, kMaxFloat, status);
+        if (hasReflecting) hits += countRayHits<DIM>(reflecting, o, d, kMaxFloat, status);
+        in = in && (hits & 1);
+    }
+    inside[i] = in ? 1 : 0;
+}
+
 template <int DIM>
 __global__ void occludedKernel(BvhView bvh, int n, const float *a, const float *b, uint8_t *out, int *status)
 {
@@ -944,6 +975,47 @@ int zb_occluded(zb_scene *scene, int boundary, int n, const float *a, const floa
     rc = stageOut(ctx, plan);
     if (rc != ZB_OK) return rc;
     return checkStatus(ctx, "zb_occluded");
+}
+
+int zb_count_ray_hits(zb_scene *scene, int boundary, int n, const float *origin, const float *dir, const float *tMax, int32_t *count)
+{
+    ZB_QUERY_PROLOGUE("zb_count_ray_hits")
+    ZB_BOUNDARY("zb_count_ray_hits")
+    if (!origin || !dir || !count) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_count_ray_hits: NULL argument");
+    IoPlan plan;
+    size_t oO = plan.addIn(origin, sizeof(float)*dim*n), oDir = plan.addIn(dir, sizeof(float)*dim*n), oT = plan.addIn(tMax, tMax ? sizeof(float)*n : 0);
+    size_t oC = plan.addOut(count, sizeof(int32_t)*n);
+    int rc = stageIn(ctx, plan);
+    if (rc != ZB_OK) return rc;
+    int threads = 128, blocks = blocksFor(n, threads);
+    if (dim == 3) countRayHitsKernel<3><<<blocks, threads, 0, ctx->stream>>>(bvh, n, at<float>(ctx, oO, origin), at<float>(ctx, oDir, dir), at<float>(ctx, oT, tMax), at<int>(ctx, oC, count), ctx->status.as<int>());
+    else countRayHitsKernel<2><<<blocks, threads, 0, ctx->stream>>>(bvh, n, at<float>(ctx, oO, origin), at<float>(ctx, oDir, dir), at<float>(ctx, oT, tMax), at<int>(ctx, oC, count), ctx->status.as<int>());
+    ZB_CUDA(cudaGetLastError());
+    rc = stageOut(ctx, plan);
+    if (rc != ZB_OK) return rc;
+    return checkStatus(ctx, "zb_count_ray_hits");
+}
+
+int zb_inside_domain(zb_scene *scene, int n, const float *x, uint8_t *inside)
+{
+    ZB_QUERY_PROLOGUE("zb_inside_domain")
+    if (!x || !inside) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_inside_domain: NULL argument");
+    if (!scene->watertight) { // geometric_queries.h:358
+        memset(inside, 1, (size_t)n);
+        return ZB_OK;
+    }
+    IoPlan plan;
+    size_t oX = plan.addIn(x, sizeof(float)*dim*n), oI = plan.addOut(inside, (size_t)n);
+    int rc = stageIn(ctx, plan);
+    if (rc != ZB_OK) return rc;
+    int threads = 128, blocks = blocksFor(n, threads);
+    const int hasA = scene->boundary[ZB_ABSORBING].present ? 1 : 0, hasR = scene->boundary[ZB_REFLECTING].present ? 1 : 0;
+    if (dim == 3) insideDomainKernel<3><<<blocks, threads, 0, ctx->stream>>>(scene->boundary[ZB_ABSORBING].view, scene->boundary[ZB_REFLECTING].view, hasA, hasR, n, at<float>(ctx, oX, x), at<uint8_t>(ctx, oI, inside), ctx->status.as<int>());
+    else insideDomainKernel<2><<<blocks, threads, 0, ctx->stream>>>(scene->boundary[ZB_ABSORBING].view, scene->boundary[ZB_REFLECTING].view, hasA, hasR, n, at<float>(ctx, oX, x), at<uint8_t>(ctx, oI, inside), ctx->status.as<int>());
+    ZB_CUDA(cudaGetLastError());
+    rc = stageOut(ctx, plan);
+    if (rc != ZB_OK) return rc;
+    return checkStatus(ctx, "zb_inside_domain");
 }
 
 int zb_sample_sphere(zb_scene *scene, int boundary, int n, const float *x, const float *radius, const float *randNums,

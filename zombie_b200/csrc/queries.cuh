@@ -649,6 +649,76 @@ ZB_DEV bool intersectRay(const BvhView& bvh, const Vec<DIM>& o, const Vec<DIM>& 
     return hit.prim >= 0;
 }
 
+// Aggregate::intersect(Ray, interactions, checkForOcclusion = false, recordAllHits = true) — bvh.inl:890-1028: every
+// primitive the ray hits within tMax, sorted by distance, with adjacent entries merged when their distances differ by less
+// than 1e-6 and their points by less than 1e-3 (Interaction::operator==, interaction.h:20-25: a ray through a shared edge
+// or vertex counts once). Returns the number of distinct hits; GeometricQueries::insideDomain (geometric_queries.h:357-371)
+// takes its parity. Hits are kept in a small sorted list; a ray with more than kMaxAllHits hits sets kStatusStackOverflow.
+constexpr int kMaxAllHits = 48;
+
+template <int DIM>
+ZB_DEV int countRayHits(const BvhView& bvh, const Vec<DIM>& o, const Vec<DIM>& d, float tMax, int *status)
+{
+    uint2 stack[kStackSize];
+    int sp = 0;
+    stack[sp++] = make_uint2(0u, 0u);
+    float ht[kMaxAllHits];
+    Vec<DIM> hp[kMaxAllHits];
+    int nHits = 0;
+    float invD[DIM];
+#pragma unroll
+    for (int k = 0; k < DIM; k++) invD[k] = 1.0f/d[k];
+
+    while (sp > 0) {
+        uint2 e = stack[--sp];
+        if (e.y & kLeafFlag) {
+            uint32_t first = e.y & 0x0fffffffu, count = (e.y >> 28) & 7u;
+            for (uint32_t i = 0; i < count; i++) {
+                Prim<DIM> prim;
+                prim.load(bvh, first + i);
+                float t, bv, bw;
+                if (!prim.intersect(o, d, tMax, t, bv, bw)) continue;
+                if (nHits == kMaxAllHits) { if (status) zb_atomic_or(status, kStatusStackOverflow); continue; }
+                Vec<DIM> p = prim.pointAt(bv, bw);
+                int k = nHits++;
+                while (k > 0 && ht[k - 1] > t) { ht[k] = ht[k - 1]; hp[k] = hp[k - 1]; k--; }
+                ht[k] = t; hp[k] = p;
+            }
+            continue;
+        }
+        NodeRegs n;
+        loadNode(bvh.nodes, e.y, n);
+        NodeFrame<DIM> f = nodeFrame<DIM>(n);
+        ZB_CHILD_LOOP
+        for (int c = 0; c < 8; c++) {
+            uint32_t meta = childMeta(n, c);
+            if (meta == 0u) continue;
+            float lo[DIM], hi[DIM];
+            childBox<DIM>(n, f, c, lo, hi);
+            float tNear = 0.0f, tFar = tMax;
+#pragma unroll
+            for (int k = 0; k < DIM; k++) {
+                float t0 = (lo[k] - o[k])*invD[k], t1 = (hi[k] - o[k])*invD[k];
+                tNear = fmaxf(tNear, fminf(t0, t1));
+                tFar = fminf(tFar, fmaxf(t0, t1));
+            }
+            if (!(tNear <= tFar)) continue;
+            if (sp < kStackSize) stack[sp++] = make_uint2(0u, childRef(n, meta));
+            else if (status) zb_atomic_or(status, kStatusStackOverflow);
+        }
+    }
+    int distinct = 0;
+    for (int k = 0; k < nHits; k++) {
+        bool dup = false;
+        if (k > 0) {
+            Vec<DIM> dp = hp[k] - hp[k - 1];
+            dup = fabsf(ht[k] - ht[k - 1]) < 1e-6f && norm2(dp) < 1e-6f;
+        }
+        if (!dup) distinct++;
+    }
+    return distinct;
+}
+
 // ------------------------------------------------------------------------------------------
 // stochastic sampling of one primitive inside a sphere
 // ------------------------------------------------------------------------------------------

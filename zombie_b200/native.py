@@ -21,7 +21,7 @@ SYMBOLS = ["zb_last_error", "zb_abi_version", "zb_device_count", "zb_context_cre
            "zb_context_set_stream", "zb_context_synchronize", "zb_context_device", "zb_context_sm_count",
            "zb_context_last_solve_profile",
            "zb_host_bvh_check", "zb_scene_create", "zb_scene_destroy", "zb_scene_update_robin_coefficients", "zb_scene_stats",
-           "zb_closest_point", "zb_intersect_ray", "zb_occluded", "zb_sample_sphere", "zb_star_radius",
+           "zb_closest_point", "zb_intersect_ray", "zb_occluded", "zb_count_ray_hits", "zb_inside_domain", "zb_sample_sphere", "zb_star_radius",
            "zb_solve", "zb_solve_dev", "zb_bvc_splat", "zb_bvc_splat_dev", "zb_context_last_splat_ms", "zb_rws_solve",
            "zb_grid_create", "zb_grid_data", "zb_grid_destroy",
            "zb_pcg32_kat", "zb_pcg32_demo", "zb_pcg32_floats"]
@@ -57,6 +57,8 @@ def lib():
         l.zb_closest_point.argtypes = [vp, i, i] + [vp]*6
         l.zb_intersect_ray.argtypes = [vp, i, i] + [vp]*7
         l.zb_occluded.argtypes = [vp, i, i] + [vp]*3
+        l.zb_count_ray_hits.argtypes = [vp, i, i] + [vp]*4
+        l.zb_inside_domain.argtypes = [vp, i, vp, vp]
         l.zb_sample_sphere.argtypes = [vp, i, i] + [vp]*7
         l.zb_star_radius.argtypes = [vp, i, vp, vp, vp, f, vp, vp]
         l.zb_solve.argtypes = [vp, i, vp, vp, vp, vp, vp]
@@ -310,6 +312,22 @@ class Scene:
         out = np.zeros(len(a), np.uint8)
         _check(lib().zb_occluded(self._h, which, len(a), abi.ptr(a), abi.ptr(b), abi.ptr(out)), "zb_occluded")
         return out
+
+    def count_ray_hits(self, which, origin, direction, tmax=None):
+        """number of distinct hits of each ray (FCPW's all-hits intersection, duplicates merged)"""
+        o, d = _f32(origin), _f32(direction)
+        t = None if tmax is None else _f32(tmax)
+        out = np.zeros(len(o), np.int32)
+        _check(lib().zb_count_ray_hits(self._h, which, len(o), abi.ptr(o), abi.ptr(d), abi.ptr(t) if t is not None else None, abi.ptr(out)),
+               "zb_count_ray_hits")
+        return out
+
+    def inside_domain(self, x):
+        """GeometricQueries::insideDomain for a batch of points (bool array)"""
+        x = _f32(x)
+        out = np.zeros(len(x), np.uint8)
+        _check(lib().zb_inside_domain(self._h, len(x), abi.ptr(x), abi.ptr(out)), "zb_inside_domain")
+        return out.astype(bool)
 
     def sample_sphere(self, x, radius, rand_nums, which=abi.REFLECTING):
         x, radius, u = _f32(x), _f32(radius), _f32(rand_nums)
