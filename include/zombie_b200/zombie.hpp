@@ -725,8 +725,19 @@ struct GeometricQueries { // geometric_queries.h:59-124
     std::function<bool(const Vector<DIM>&, const Vector<DIM>&, const Vector<DIM>&, const Vector<DIM>&, bool, bool)> intersectsWithReflectingBoundary;
     std::function<bool(const Vector<DIM>&, float, const Vector<DIM>&, BoundarySample<DIM>&)> sampleReflectingBoundary;
     std::function<float(const Vector<DIM>&, float, float, float, bool)> computeStarRadiusForReflectingBoundary;
+    std::function<bool(const Vector<DIM>&)> insideDomain;
     std::function<bool(const Vector<DIM>&)> insideBoundingDomain;
     std::function<bool(const Vector<DIM>&)> outsideBoundingDomain;
+
+    // batched insideDomain (zb_inside_domain): the inside test of a domain sampler over many candidates at once
+    void insideDomain_batch(const std::vector<Vector<DIM>>& x, std::vector<uint8_t>& inside) const {
+        inside.assign(x.size(), 1);
+        if (!domainIsWatertight || x.empty()) return;
+        if (!(hasNonEmptyAbsorbingBoundary || hasNonEmptyReflectingBoundary)) { inside.assign(x.size(), 0); return; } // no crossing: even count
+        std::vector<float> flat(x.size()*DIM);
+        for (size_t i = 0; i < x.size(); i++) for (size_t k = 0; k < DIM; k++) flat[i*DIM + k] = x[i][k];
+        detail::check(zb_inside_domain(scene(), (int)x.size(), flat.data(), inside.data()));
+    }
 
     // batched forms (what a caller preparing 10^6 sample points should use): unsigned distances
     void computeDistToAbsorbingBoundary_batch(const std::vector<Vector<DIM>>& x, std::vector<float>& dist) const { distances(ZB_ABSORBING, x, dist); }
@@ -829,6 +840,15 @@ private:
             for (size_t k = 0; k < DIM; k++) xx[k] = x[k];
             detail::check(zb_star_radius(scene(), 1, xx, &minRadius, &maxRadius, silhouettePrecision, &flip, &r));
             return r;
+        };
+        insideDomain = [this](const Vector<DIM>& x) -> bool { // geometric_queries.h:357-371
+            if (!domainIsWatertight) return true;
+            if (!(hasNonEmptyAbsorbingBoundary || hasNonEmptyReflectingBoundary)) return false; // no crossing: even count
+            float xx[DIM];
+            uint8_t in = 0;
+            for (size_t k = 0; k < DIM; k++) xx[k] = x[k];
+            detail::check(zb_inside_domain(scene(), 1, xx, &in));
+            return in != 0;
         };
         insideBoundingDomain = [this](const Vector<DIM>& x) -> bool {
             for (size_t k = 0; k < DIM; k++) if (x[k] < domainMin[k] || x[k] > domainMax[k]) return false;

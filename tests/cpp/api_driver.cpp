@@ -107,6 +107,20 @@ static int run(const Header& h, FILE *f, const char *outPath, bool extras)
     float d0 = queries.computeDistToAbsorbingBoundary(x[0], false);
     if (h.nPa > 0 && d0 != distA[0]) { fprintf(stderr, "single/batched distance mismatch %g %g\n", d0, distA[0]); return 4; }
 
+    // insideDomain (all-hits ray parity on the device): evaluation points lie inside, a far point outside; single == batched
+    {
+        std::vector<Vector<DIM>> probe(x.begin(), x.begin() + std::min<size_t>(x.size(), 64));
+        Vector<DIM> far = Vector<DIM>::Constant(7.5f);
+        probe.push_back(far);
+        std::vector<uint8_t> inside;
+        queries.insideDomain_batch(probe, inside);
+        for (size_t i = 0; i + 1 < probe.size(); i++) {
+            if (!inside[i]) { fprintf(stderr, "evaluation point %d reported outside the domain\n", (int)i); return 5; }
+        }
+        if (inside.back()) { fprintf(stderr, "far point reported inside the domain\n"); return 5; }
+        if (queries.insideDomain(probe[0]) != (inside[0] != 0) || queries.insideDomain(far)) { fprintf(stderr, "single/batched insideDomain mismatch\n"); return 5; }
+    }
+
     // Boundary Value Caching splat and Reverse Walk on Stars through the same surface: a cache made of the solved
     // points themselves (solution = estimate, no flux), splatted onto / walked towards two interior points
     float bvcSolution = 0.0f, rwsSolution = 0.0f;

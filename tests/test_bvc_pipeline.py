@@ -130,3 +130,10 @@ def test_pipeline_on_the_device_matches_the_reference_backed_run(ctx, ref):
     assert np.sqrt(np.mean(gerr**2)) < 0.08 and abs(gerr.mean()) < 0.07
     assert abs(np.sqrt(np.mean(gerr**2)) - np.sqrt(np.mean(rerr**2))) < 0.05
     assert np.array_equal(ge.bucketCount, re_.bucketCount)
+    # the domain sampler over the device's inside test (zb_inside_domain) draws the same points as over the reference's
+    # GeometricQueries::insideDomain
+    gb, rscene = bvc.NativeBackend(ctx, native.Scene(ctx, 3, **kw)), ref.RefScene(3, **kw)
+    vol = P.bumpy_sphere_volume()
+    sg = bvc.UniformDomainSampler(gb.inside_domain, [-1.2]*3, [1.2]*3, vol, seed=5).generate_samples(4096)
+    sr = bvc.UniformDomainSampler(rscene.inside_domain, [-1.2]*3, [1.2]*3, vol, seed=5).generate_samples(4096)
+    assert np.array_equal(sg.pt, sr.pt) and 3500 < len(sg) < 4700 and P.bumpy_sphere_inside(sg.pt, margin=-0.03).all()

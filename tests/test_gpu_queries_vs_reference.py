@@ -104,6 +104,39 @@ def test_closest_point_index_is_the_reference_baselines(ctx, ref, dim):
     rb.close(); rs.close(); gs.close()
 
 
+@pytest.mark.parametrize("dim", [3, 2])
+def test_all_hits_counts_and_inside_domain_match_compiled_reference(ctx, ref, dim):
+    """zb_count_ray_hits = Aggregate::intersect(ray, interactions, false, true) as a count (bvh.inl:890-1028: every hit,
+    sorted, duplicates on shared edges merged) and zb_inside_domain = GeometricQueries::insideDomain
+    (geometric_queries.h:357-371: the parity of that count along each axis over both boundaries), on a closed domain split
+    into an absorbing and a reflecting part; query points inside, outside and (2D) in the concave bays of the star."""
+    whole, absorbing, reflecting = cases.mesh3d(4) if dim == 3 else cases.mesh2d(2048)
+    kw = cases.scene_kwargs(dim, abi.REFLECTING_NEUMANN, absorbing, reflecting)
+    rs, gs = ref.RefScene(dim, **kw), native.Scene(ctx, dim, **kw)
+    nq = 50000
+    x = (cases.query_points(nq, dim, 1.0, seed=77)*np.float32(1.6)).astype(np.float32)
+    # points whose axis rays pass exactly through mesh vertices / along edges: the duplicate-merging rule decides
+    pos = whole[0]
+    v = pos[np.random.RandomState(3).randint(0, len(pos), 2000)].copy()
+    v[:, 0] -= np.float32(0.37)
+    x = np.concatenate([x, v]).astype(np.float32)
+    o, d, tmax = cases.rays(nq, dim, 1.2, seed=79)
+    for which in (abi.ABSORBING, abi.REFLECTING):
+        rc, gc = rs.count_ray_hits(which, o, d, tmax*3), gs.count_ray_hits(which, o, d, tmax*3)
+        assert np.array_equal(rc, gc)
+        assert (rc >= 2).any() and (rc == 0).any()
+        ex = np.zeros_like(x)
+        ex[:, 0] = 1.0
+        assert np.array_equal(rs.count_ray_hits(which, x, ex), gs.count_ray_hits(which, x, ex))
+    ri, gi = rs.inside_domain(x), gs.inside_domain(x)
+    assert np.array_equal(ri, gi)
+    assert 0.1 < ri.mean() < 0.9
+    # a domain declared not watertight is "inside" everywhere (geometric_queries.h:358)
+    open_scene = native.Scene(ctx, dim, watertight=False, **kw)
+    assert open_scene.inside_domain(x[:100]).all()
+    open_scene.close(); rs.close(); gs.close()
+
+
 def test_full_size_mesh_matches_compiled_reference(ctx, ref):
     """The BASELINE headline geometry itself — the 1,310,720-triangle bumpy icosphere of config C3, Robin z > 0 /
     Dirichlet z < 0 — against the compiled reference: 20,000 queries of every kind (closest point on both boundaries, first

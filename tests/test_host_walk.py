@@ -396,6 +396,15 @@ def test_device_ray_and_sampling_code_on_host_matches_reference(ref, tmp_path, d
     check_rays(ref_hits, (rays[:, 0].astype(np.int32), rays[:, 1], rays[:, 2:2 + dim], rays[:, 2 + dim:2 + 2*dim]))
     assert np.array_equal(rs.occluded(abi.REFLECTING, o, o + d*tmax[:, None]).astype(bool), rays[:, 2 + 2*dim] > 0.5)
 
+    # all-hits counts (FCPW's recordAllHits intersection with duplicates merged; the parity of the axis-aligned count is
+    # what GeometricQueries::insideDomain reads)
+    hits = np.fromfile(os.path.join(dd, "hits_out.bin"), np.int32).reshape(nq, 2)
+    ex = np.zeros_like(d)
+    ex[:, 0] = 1.0
+    assert np.array_equal(hits[:, 0], rs.count_ray_hits(abi.REFLECTING, o, d, tmax))
+    assert np.array_equal(hits[:, 1], rs.count_ray_hits(abi.REFLECTING, o, ex))
+    assert (hits[:, 1] == 0).mean() > 0.02 and (hits[:, 1] == 1).mean() > 0.02 and (dim == 3 or (hits >= 2).mean() > 0.005)
+
     rprim, rpt, rn, rpdf = rs.sample_sphere(sx, rad, u)
     gprim, gpdf, gpt, gn = smp[:, 0].astype(np.int32), smp[:, 1], smp[:, 2:2 + dim], smp[:, 2 + dim:]
     f = gprim >= 0

@@ -2,7 +2,7 @@
 // (queries.cuh: intersectRay, sampleSphere) compiled for the host and run on a problem dumped by
 // tests/test_host_walk.py — the per-query bodies of intersectRayKernel / occludedKernel / sampleSphereKernel (capi.cu).
 //   nvcc -std=c++17 -O2 -Xcompiler -ffp-contract=off -o host_rays tools/host_rays.cu zombie_b200/csrc/wide_bvh.cpp
-//   host_rays <dir> <dim>   reads <dir>/{pos,idx,o,d,tmax,sx,srad,su}.bin, writes <dir>/rays_out.bin, <dir>/samples_out.bin
+//   host_rays <dir> <dim>   reads <dir>/{pos,idx,o,d,tmax,sx,srad,su}.bin, writes <dir>/rays_out.bin, <dir>/hits_out.bin, <dir>/samples_out.bin
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -71,6 +71,19 @@ int run(const std::string& dir)
     }
     FILE *f = fopen((dir + "/rays_out.bin").c_str(), "wb");
     fwrite(out.data(), 4, out.size(), f);
+    fclose(f);
+
+    // all-hits counts (countRayHits, the body of countRayHitsKernel / insideDomainKernel): per ray the number of distinct
+    // hits within tmax, and of the axis-aligned ray o + t e_0, t < inf
+    std::vector<int> hits(2*(size_t)n);
+    for (int i = 0; i < n; i++) {
+        Vec<DIM> org = loadVec<DIM>(&o[DIM*i]), dir = loadVec<DIM>(&d[DIM*i]), ex = vzero<DIM>();
+        ex[0] = 1.0f;
+        hits[2*i] = countRayHits<DIM>(v, org, dir, tmax[i], &status);
+        hits[2*i + 1] = countRayHits<DIM>(v, org, ex, kMaxFloat, &status);
+    }
+    f = fopen((dir + "/hits_out.bin").c_str(), "wb");
+    fwrite(hits.data(), 4, hits.size(), f);
     fclose(f);
 
     // per sample: prim, pdf, pt[DIM], normal[DIM]

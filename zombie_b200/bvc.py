@@ -183,7 +183,9 @@ class UniformBoundarySampler:
 
 
 class UniformDomainSampler:
-    """UniformDomainSampler (domain_samplers.h:22-108): stratified points of the bounding box that fall inside the region"""
+    """UniformDomainSampler (domain_samplers.h:22-108): stratified points of the bounding box that fall inside the region.
+    inside_solve_region maps an [n, dim] array to a bool array; the reference's demo passes GeometricQueries::insideDomain
+    (demo/model_problem.h), whose batched device form is native.Scene.inside_domain (zb_inside_domain)."""
 
     def __init__(self, inside_solve_region, region_min, region_max, region_volume, seed=0xD0D0):
         self.inside = inside_solve_region
@@ -220,6 +222,10 @@ class NativeBackend:
 
     def splat(self, absorption_coeff, samples, eval_pts, **kw):
         return self.ctx.bvc_splat(self.dim, absorption_coeff, samples, eval_pts, **kw)
+
+    def inside_domain(self, x):
+        """GeometricQueries::insideDomain on the device: the inside test to hand to UniformDomainSampler"""
+        return self.scene.inside_domain(x) if len(x) else np.zeros(0, bool)
 
 
 class BoundaryValueCachingSolver:
