@@ -148,6 +148,8 @@ int main(int argc, char **argv)
            g_zbClass[4], g_zbClass[7], g_zbClass[5], g_zbClass[6]);
     printf("star edges (fast test): skipped by the sign shortcut %lld, tested in full %lld\n", g_zbClass[8], g_zbClass[9]);
     printf("star children: %lld passed the box test, %lld of them went on to the reflectance bounds\n", g_zbClass[10], g_zbClass[11]);
+    printf("star prims redone in the reference's order: %lld of %lld full tests (grazing view %lld, bound threshold %lld, conditioning %lld)\n",
+           g_zbClass[15], g_zbClass[3], g_zbClass[17], g_zbClass[18], g_zbClass[19]);
     printf("star prims that lowered r2: %lld (robin-only items: %lld); extra rejected by the range bound %lld\n", g_zbClass[12], g_zbClass[13], g_zbClass[14]);
     const char *names[5] = {"closest", "ray", "occlusion", "sample", "star"};
     for (int q = 0; q < 5; q++) {

@@ -71,6 +71,9 @@ extern long long g_coopCount[10]; // [0] closest node items, [1] closest prims, 
 #ifndef ZB_STAR_TWO_STAGE
 #define ZB_STAR_TWO_STAGE 1 // 0: every pooled primitive round runs the full star test (A/B builds)
 #endif
+#ifndef ZB_STAR_DEFER_REDO
+#define ZB_STAR_DEFER_REDO 1 // 0: the reference-ordered redo of a star primitive runs inside the full round that asked for it (A/B builds)
+#endif
 #ifndef ZB_PHASE1_BUDGET
 #define ZB_PHASE1_BUDGET 8
 #endif
@@ -97,6 +100,7 @@ struct WarpShared {
     unsigned long long best[32];        // high word: current squared radius (float bits); low word: payload
     float qx[32], qy[32], qz[32];
     unsigned int flags[32];
+    uint32_t redo[64];                  // star radius: primitives whose fast test asked for the reference-ordered redo (same item format)
 };
 
 // four 128-thread CTAs per SM (the register budget of the walk kernel) must also fit in the 227 KB of shared memory,
@@ -399,6 +403,13 @@ ZB_COOP float coopStarPooled(const BvhView& bvh, WarpShared& ws, bool hasQuery, 
     // round runs the whole test on 32 of them. fullTop counts that list (entries ws.prims[kPrimQueue - 1 - k]).
     constexpr bool kTwoStage = DIM == 3 && ZB_STAR_TWO_STAGE;
     int fullTop = 0;
+    // Third stage (3D): a primitive whose fast test lands within rounding distance of a discrete decision is redone with
+    // the reference-ordered arithmetic (primStarRadius2Redo, ~1,900 instructions). A third of the pooled full tests of a
+    // C3 solve ask for it, in more than half of the full rounds at least one lane does (profiles/r2_wave_split_ncu.txt) —
+    // and a warp pays for the redo in full whenever one lane takes it. So the full round only marks such primitives; they
+    // collect in ws.redo and are redone 32 at a time. Radii combine by minimum, so the order of the tests does not matter.
+    constexpr bool kDeferRedo = kTwoStage && ZB_STAR_DEFER_REDO;
+    int redoTop = 0;
     zb_syncwarp();
 
     while (true) {
@@ -406,13 +417,35 @@ ZB_COOP float coopStarPooled(const BvhView& bvh, WarpShared& ws, bool hasQuery, 
             coopRefill(ws, nodeTop, primTop, lane, stack, sp, true);
             zb_syncwarp();
         }
-        if (nodeTop == 0 && primTop == 0 && fullTop == 0) break;
+        const bool drained = nodeTop == 0 && primTop == 0 && fullTop == 0;
+        if (drained && redoTop == 0) break;
+        if (kDeferRedo && (redoTop >= 32 || drained)) {
+            // ---- redo round
+            int n = min(redoTop, 32);
+            if (lane < n) {
+                uint32_t item = ws.redo[redoTop - n + lane];
+                int owner = (int)(item >> 27);
+                bool silhouetteTests = !((item >> 26) & 1u);
+                float before = coopRadius2(ws, owner);
+                Vec<DIM> q;
+                q[0] = ws.qx[owner]; q[1] = ws.qy[owner];
+                if (DIM == 3) q[DIM - 1] = ws.qz[owner];
+                float r2 = primStarRadius2Redo<DIM>(bvh.prims, bvh.adjacency, bvh.snchSign, item & kPrimIndexMask, q, before,
+                                                    ws.flags[owner] != 0u, precision, silhouetteTests);
+                if (r2 < before) zb_atomic_min64(&ws.best[owner], packBest(r2, 0u));
+            }
+            redoTop -= n;
+            zb_syncwarp();
+            continue;
+        }
         if (kTwoStage && (fullTop >= 32 || (nodeTop == 0 && primTop == 0))) {
             // ---- full round on the survivors
             int n = min(fullTop, 32);
             if (lane == 0) { ZB_COOP_COUNT(3, n) ZB_COOP_COUNT(7, 1) }
+            bool needRedo = false;
+            uint32_t item = 0u;
             if (lane < n) {
-                uint32_t item = ws.prims[kPrimQueue - fullTop + lane];
+                item = ws.prims[kPrimQueue - fullTop + lane];
                 int owner = (int)(item >> 27);
                 bool silhouetteTests = !((item >> 26) & 1u);
                 float r2 = coopRadius2(ws, owner), before = r2;
@@ -420,10 +453,16 @@ ZB_COOP float coopStarPooled(const BvhView& bvh, WarpShared& ws, bool hasQuery, 
                 q[0] = ws.qx[owner]; q[1] = ws.qy[owner];
                 if (DIM == 3) q[DIM - 1] = ws.qz[owner];
                 r2 = primStarRadius2Call<DIM>(bvh.prims, bvh.adjacency, bvh.snchSign, item & kPrimIndexMask, q, r2, ws.flags[owner] != 0u,
-                                              precision, silhouetteTests);
+                                              precision, silhouetteTests, kDeferRedo);
+                if (kDeferRedo && r2 < 0.0f) { needRedo = true; r2 = before; }
                 if (r2 < before) { ZB_COOP_TRACE(owner, silhouetteTests ? "full-round primitive (silhouette tests on)" : "full-round primitive (no silhouette tests)", r2, item & kPrimIndexMask) ZB_COOP_TRACE(owner, "   ... its incoming radius", before, lane) ZB_COOP_TRACE(owner, "   ... query x", q[0], item) ZB_COOP_TRACE(owner, "   ... query y", q[1], ws.flags[owner]) ZB_COOP_TRACE(owner, "   ... query z", q[DIM - 1], fullTop) zb_atomic_min64(&ws.best[owner], packBest(r2, 0u)); }
             }
             fullTop -= n;
+            if (kDeferRedo) {
+                unsigned int m = zb_ballot(needRedo);
+                if (needRedo) ws.redo[redoTop + zb_popc(m & ((1u << lane) - 1u))] = item;
+                redoTop += zb_popc(m); // < 32 before the round (else a redo round would have run), <= 63 now
+            }
             zb_syncwarp();
             continue;
         }

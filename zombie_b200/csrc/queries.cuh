@@ -1052,11 +1052,17 @@ ZB_DEV_COLD bool isSilhouetteEdge3Cold(Vec<3> pa, Vec<3> pb, Vec<3> n0, Vec<3> n
 // rounding (the gate on this query is FCPW's 1e-3 silhouette tolerance); roughly half the instructions.
 template <int DIM>
 ZB_DEV void primStarRadius2Fast(const BvhView& bvh, uint32_t primIdx, const Vec<DIM>& x, float& r2, bool flip,
-                                float precision, bool silhouetteTests)
+                                float precision, bool silhouetteTests, bool *deferRedo = nullptr)
 {
     primStarRadius2<DIM>(bvh, primIdx, x, r2, flip, precision, silhouetteTests);
 }
 
+#ifndef ZB_ROBIN_REDO_GRAZING
+#define ZB_ROBIN_REDO_GRAZING 0.01f // ... and when the closest point of the triangle is seen at a cosine below this
+#endif
+#ifndef ZB_ROBIN_REDO_CONDITIONING
+#define ZB_ROBIN_REDO_CONDITIONING 0.05f // the fast reflectance bound is redone in the reference's order when h mu - c^2 < this * h mu
+#endif
 #ifndef ZB_ROBIN_RANGE_BOUND
 #define ZB_ROBIN_RANGE_BOUND 1 // 0: only the plane-distance bound (A/B builds)
 #endif
@@ -1103,9 +1109,12 @@ ZB_DEV float closestPointTriangleFast2(const Vec<3>& pa, const Vec<3>& pb, const
     return norm2(x - pt);
 }
 
+// deferRedo: when given, a primitive that needs the reference-ordered redo is NOT redone here: *deferRedo is set and r2
+// is left untouched, so that the caller can collect such primitives and redo them together (coop.cuh: in a warp the
+// 1,900-instruction redo costs the same whether one lane takes it or all 32 do).
 template <>
 ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const Vec<3>& x, float& r2, bool flip,
-                                   float precision, bool silhouetteTests)
+                                   float precision, bool silhouetteTests, bool *deferRedo)
 {
     Prim<3> prim;
     prim.load(bvh, primIdx);
@@ -1228,7 +1237,8 @@ ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const V
                 // at rounding level: only the reference's own operation order reproduces the reference's value)
                 float hmu = h*maxCoeff, maxCos = sqrtf(hmu);
                 float c = clampLikeStd(maxCos/1.7320508075688772935f, cosLower, cosUpper);
-                redo = redo || cosUpper < 0.05f || fabsf(maxCos - cosLower) < 1e-5f || (maxCos >= cosLower && (hmu - c*c) < 0.3f*hmu);
+                if (cosUpper < ZB_ROBIN_REDO_GRAZING) { ZB_CLASS(17) } else if (fabsf(maxCos - cosLower) < 1e-5f) { ZB_CLASS(18) } else if (maxCos >= cosLower && (hmu - c*c) < ZB_ROBIN_REDO_CONDITIONING*hmu) { ZB_CLASS(19) }
+                redo = redo || cosUpper < ZB_ROBIN_REDO_GRAZING || fabsf(maxCos - cosLower) < 1e-5f || (maxCos >= cosLower && (hmu - c*c) < ZB_ROBIN_REDO_CONDITIONING*hmu);
                 ZB_PRIM_TRACE(primIdx, "fast reflectance: h cosLower cosUpper radius^2", h, cosLower, cosUpper, radius*radius)
             } else {
                 r2 = fminf(r2, closestDist2);
@@ -1236,6 +1246,8 @@ ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const V
         }
     }
     ZB_PRIM_TRACE(primIdx, "fast result before redo: r2in r2 redo cannotShrink", r2in, r2, redo ? 1.0f : 0.0f, robinCannotShrink ? 1.0f : 0.0f)
+    if (redo) { ZB_CLASS(15) }
+    if (redo && deferRedo) { *deferRedo = true; r2 = r2in; return; }
     if (redo) r2 = primStarRadius2Redo<3>(bvh.prims, bvh.adjacency, bvh.snchSign, primIdx, x, r2in, flip, precision, silhouetteTests);
     ZB_PRIM_TRACE(primIdx, "final: r2 | query", r2, x[0], x[1], x[2])
     if (r2 < r2in) { ZB_CLASS(12) if (!silhouetteTests) { ZB_CLASS(13) } }
@@ -1278,14 +1290,15 @@ ZB_DEV
 ZB_DEV_COLD
 #endif
 float primStarRadius2Call(const float4 *prims, const float4 *adjacency, int snchSign, uint32_t primIdx, Vec<DIM> x, float r2,
-                          bool flip, float precision, bool silhouetteTests)
+                          bool flip, float precision, bool silhouetteTests, bool defer = false)
 {
     BvhView bvh{};
     bvh.prims = prims;
     bvh.adjacency = adjacency;
     bvh.snchSign = snchSign;
-    primStarRadius2Fast<DIM>(bvh, primIdx, x, r2, flip, precision, silhouetteTests);
-    return r2;
+    bool deferred = false;
+    primStarRadius2Fast<DIM>(bvh, primIdx, x, r2, flip, precision, silhouetteTests, defer ? &deferred : nullptr);
+    return deferred ? -1.0f : r2; // defer: -1 = "redo this primitive in the reference's order" (primStarRadius2Redo), r2 unchanged
 }
 
 // BoundingCone::overlap (fcpw/core/bounding_volumes.h:275-321): can a normal inside the cone be
