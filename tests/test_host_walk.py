@@ -405,6 +405,19 @@ def test_device_ray_and_sampling_code_on_host_matches_reference(ref, tmp_path, d
     assert np.array_equal(hits[:, 1], rs.count_ray_hits(abi.REFLECTING, o, ex))
     assert (hits[:, 1] == 0).mean() > 0.02 and (hits[:, 1] == 1).mean() > 0.02 and (dim == 3 or (hits >= 2).mean() > 0.005)
 
+    # axis-parallel rays THROUGH mesh vertices (what insideDomain casts from a point level with a vertex): up to six
+    # triangles report the vertex at distances a few ulps apart and merge into one hit only as a chain, and the ray lies in a
+    # face plane of the leaf boxes (0*inf in a product-form slab test)
+    vo = pos[np.random.RandomState(3).randint(0, len(pos), 2000)].astype(np.float32)
+    vo[:, 0] -= np.float32(0.37)
+    for name, a in (("o", vo), ("d", d[:2000]), ("tmax", tmax[:2000])):
+        np.ascontiguousarray(a, np.float32).tofile(os.path.join(dd, name + ".bin"))
+    r = subprocess.run([exe, dd, str(dim)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    vhits = np.fromfile(os.path.join(dd, "hits_out.bin"), np.int32).reshape(2000, 2)
+    assert np.array_equal(vhits[:, 1], rs.count_ray_hits(abi.REFLECTING, vo, ex[:2000]))
+    assert (vhits[:, 1] >= 1).all()
+
     rprim, rpt, rn, rpdf = rs.sample_sphere(sx, rad, u)
     gprim, gpdf, gpt, gn = smp[:, 0].astype(np.int32), smp[:, 1], smp[:, 2:2 + dim], smp[:, 2 + dim:]
     f = gprim >= 0

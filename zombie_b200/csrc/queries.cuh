@@ -696,13 +696,21 @@ ZB_DEV int countRayHits(const BvhView& bvh, const Vec<DIM>& o, const Vec<DIM>& d
             float lo[DIM], hi[DIM];
             childBox<DIM>(n, f, c, lo, hi);
             float tNear = 0.0f, tFar = tMax;
+            bool outside = false;
 #pragma unroll
             for (int k = 0; k < DIM; k++) {
+                if (d[k] == 0.0f) {
+                    // an axis-parallel ray (insideDomain casts nothing else): the slab holds for every t or for none. The
+                    // product form would give 0*inf = NaN for a ray IN a face plane of the box — through a mesh vertex
+                    // that is a corner of its leaf's box — and must not cull the box then (FCPW's NaN comparisons keep it)
+                    outside = outside || o[k] < lo[k] || o[k] > hi[k];
+                    continue;
+                }
                 float t0 = (lo[k] - o[k])*invD[k], t1 = (hi[k] - o[k])*invD[k];
                 tNear = fmaxf(tNear, fminf(t0, t1));
                 tFar = fminf(tFar, fmaxf(t0, t1));
             }
-            if (!(tNear <= tFar)) continue;
+            if (outside || !(tNear <= tFar)) continue;
             if (sp < kStackSize) stack[sp++] = make_uint2(0u, childRef(n, meta));
             else if (status) zb_atomic_or(status, kStatusStackOverflow);
         }
