@@ -166,13 +166,13 @@ POINT_KEYS = ("pt", "normal", "directionForDerivative", "type", "estimationQuant
 STAT_KEYS = ("solutionMean", "solutionM2", "gradientMean", "gradientM2", "totalFirstSourceContribution",
              "totalDerivativeContribution", "nSolutionEstimates", "nGradientEstimates", "totalWalkLength", "totalSplits")
 
-# ncu evidence of the shipped kernels (profiles/r2_wave_steady_ncu.txt: --set full capture of one steady-state round of this
-# workload, 262,144 walks): DRAM bytes read + written per walk step, summed over the round's kernels; warp-issue and lane
-# statistics of the dominant kernel (waveStarKernel<3>, ~72 % of the step by the ncu launch list and by CUDA events)
+# ncu evidence of the shipped kernels: profiles/r2_ncu_evidence.json, written by scripts/ncu_evidence.py from the --set full
+# capture of one steady-state round of this workload (profiles/r2_wave_round_ncu.txt: 984,320 live walks) — DRAM bytes read +
+# written per walk step summed over the round's kernels, and the issue / lane statistics of the dominant kernel
 NCU_EVIDENCE = {
-    "profile": "profiles/r2_wave_steady_ncu.txt",
+    "profile": "profiles/r2_wave_round_ncu.txt",
     "dram_bytes_per_walk_step": None,
-    "dominant_kernel": "waveStarKernel<3>",
+    "dominant_kernel": "waveStarPooledKernel<3>",
 }
 
 
@@ -380,7 +380,7 @@ def run_native(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak,
                          "traffic": None if traffic is None else traffic*prof_steps/max(1, args.steps),
                          "peak_kind": peak_kind,
-                         "kernel": "one solve's wavefront rounds: waveClosestKernel + waveStarKernel + waveStepKernel (+ cub sort), then waveTailKernel",
+                         "kernel": "one solve's wavefront rounds: waveClosestKernel + waveStarPrivateKernel + waveStarPooledKernel + waveStepKernel (+ cub sort), then waveTailKernel",
                          "per_launch": "one zb_solve_dev (= one step)",
                          "algorithmic_bytes_per_walk_step": bytes_per_step, "dram_bytes_per_walk_step_ncu": traffic,
                          "kernel_ms_per_step": local_walk_ms/args.steps,
@@ -388,7 +388,9 @@ def run_native(args, rank, world, local_rank):
                          "ncu": {k: v for k, v in ev.items() if k != "dram_bytes_per_walk_step"}},
         }
         if world > 1:
-            line["multi_gpu"] = {"gather_ms_per_step": gather_ms/args.steps, "gather_bytes_per_step": world*stat_bytes,
+            # the gather's events bracket the collective on each rank, so its time includes waiting for the slowest rank's solve
+            line["multi_gpu"] = {"gather_ms_per_step": gather_ms/args.steps, "gather_includes_wait_for_slowest_rank": True,
+                                 "gather_bytes_per_step": world*stat_bytes,
                                  "walk_ms_per_step_min_rank": walk_ms_min/args.steps, "walk_ms_per_step_max_rank": walk_ms_max/args.steps}
         if not args.no_cpu and world == 1:   # the CPU baseline is reported at N = 1 only
             line["cpu_baseline"] = cpu_baseline(args, w)
