@@ -177,6 +177,11 @@ int zb_scene_create(zb_context *ctx, int dim,
 void zb_scene_destroy(zb_scene *scene);
 /* FcpwRobinBoundaryHandler::updateCoefficientValues (fcpw_geometric_queries.h:997-1010) */
 int zb_scene_update_robin_coefficients(zb_scene *scene, const float *minRobinCoeff, const float *maxRobinCoeff);
+/* The same with the two coefficient arrays (one value per reflecting primitive, input order) already in DEVICE memory;
+ * asynchronous on the context's stream. Both forms refit on the device: per-primitive records, then the coefficient
+ * range of every node bottom-up (ReflectanceBvh::updateCoefficients, reflectance_boundary_bvh/bvh.h:304-367), one
+ * kernel per level of the hierarchy; geometry and topology are untouched. */
+int zb_scene_update_robin_coefficients_dev(zb_scene *scene, const float *minRobinCoeff, const float *maxRobinCoeff);
 
 /* ---- PDE data grids ------------------------------------------------------------------------
  * Uploads shape[0]*shape[1]*shape[2] floats (x fastest) to the context's device and returns a handle; zb_grid_data

@@ -137,6 +137,56 @@ def test_all_hits_counts_and_inside_domain_match_compiled_reference(ctx, ref, di
     open_scene.close(); rs.close(); gs.close()
 
 
+@pytest.mark.parametrize("dim", [3, 2])
+def test_robin_coefficient_refit_on_the_device(ctx, ref, dim):
+    """zb_scene_update_robin_coefficients(_dev) = FcpwRobinBoundaryHandler::updateCoefficientValues
+    (fcpw_geometric_queries.h:997-1010): after the device-side refit of the per-primitive records and of every node's
+    coefficient range, star radii equal those of a scene BUILT with the new coefficients bit for bit, and those of the
+    reference after its own update."""
+    import torch
+    whole, absorbing, reflecting = cases.mesh3d(4) if dim == 3 else cases.mesh2d(2048)
+    n_r = len(reflecting[1])
+    rng = np.random.RandomState(17)
+    mu_old = np.full(n_r, 0.3, np.float32)
+    mn_new = rng.uniform(0.5, 4.0, n_r).astype(np.float32)
+    mx_new = (mn_new*rng.uniform(1.0, 1.5, n_r)).astype(np.float32)
+    kw_old = cases.scene_kwargs(dim, abi.REFLECTING_ROBIN, absorbing, reflecting, mu=1.0)
+    kw_old["min_robin"], kw_old["max_robin"] = mu_old, mu_old
+    kw_new = dict(kw_old, min_robin=mn_new, max_robin=mx_new)
+    nq = 20000
+    x = cases.query_points(nq, dim, 0.99, seed=91)
+    minr = np.full(nq, 1e-3, np.float32)
+    updated, fresh = native.Scene(ctx, dim, **kw_old), native.Scene(ctx, dim, **kw_new)
+    _, da, _, _ = fresh.closest_point(abi.ABSORBING, x)
+    before = updated.star_radius(x, minr, da)
+    want = fresh.star_radius(x, minr, da)
+    assert (before != want).mean() > 0.05                      # the coefficients matter on this problem
+    updated.update_robin_coefficients(mn_new, mx_new)          # host arrays
+    assert np.array_equal(updated.star_radius(x, minr, da), want)
+    updated.update_robin_coefficients(mu_old, mu_old)
+    assert np.array_equal(updated.star_radius(x, minr, da), before)
+    dev = torch.device("cuda", ctx.device)
+    tmn, tmx = torch.from_numpy(mn_new).to(dev), torch.from_numpy(mx_new).to(dev)
+    torch.cuda.synchronize(dev)
+    updated.update_robin_coefficients_dev(tmn.data_ptr(), tmx.data_ptr())   # device arrays, asynchronous
+    assert np.array_equal(updated.star_radius(x, minr, da), want)
+    # and a solve sees the new coefficients: same estimates as on the freshly built scene (deterministic scheduler)
+    pde, _ = cases.exp_pde(mu=1.0, sigma=1.0)
+    xs = x[:512]
+    out = []
+    for sc in (updated, fresh):
+        _, dr, _, _ = sc.closest_point(abi.REFLECTING, xs)
+        pts = abi.HostSamplePoints(xs, da[:512], dr, nWalks=16, estimationQuantity=abi.SOLUTION)
+        st = abi.HostStatistics(len(xs), dim)
+        sc.solve(abi.WALK_ON_STARS, pde, abi.WalkSettings.default(), pts, st)
+        out.append(st.solutionMean.copy())
+    assert np.array_equal(out[0], out[1])
+    rs = ref.RefScene(dim, **kw_new)
+    rr = rs.star_radius(x, minr, da)
+    assert np.mean(np.abs(rr - want) <= 1e-3*max(1.0, float(rr.max()))) > 0.999
+    updated.close(); fresh.close(); rs.close()
+
+
 def test_full_size_mesh_matches_compiled_reference(ctx, ref):
     """The BASELINE headline geometry itself — the 1,310,720-triangle bumpy icosphere of config C3, Robin z > 0 /
     Dirichlet z < 0 — against the compiled reference: 20,000 queries of every kind (closest point on both boundaries, first

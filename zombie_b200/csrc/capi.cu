@@ -28,6 +28,8 @@ thread_local bool g_gradientHint = true;
 struct DeviceBvhStorage {
     HostBvh host;
     DeviceBuffer nodes, prims, primIndex, cones, adjacency;
+    DeviceBuffer coeffScratch;           // Robin coefficient refit: the caller's per-primitive values and a (min, max) per node
+    std::vector<int> levelStart;         // nodes are stored breadth first: level l is [levelStart[l], levelStart[l + 1])
     BvhView view{};
     bool present = false;
     size_t bytes() const { return nodes.capacity + prims.capacity + primIndex.capacity + cones.capacity + adjacency.capacity; }
@@ -820,6 +822,123 @@ void zb_scene_destroy(zb_scene *scene)
     delete scene;
 }
 
+// ---- Robin coefficient refit on the device -----------------------------------------------------------------
+// FcpwRobinBoundaryHandler::updateCoefficientValues -> ReflectanceBvh::updateCoefficients (reflectance_boundary_bvh/bvh.h:304-367):
+// new per-primitive coefficient bounds, then every node's range bottom-up. The hierarchy is stored breadth first, so the
+// refit is one kernel per level from the deepest up; a node reads the ranges its internal children wrote one launch before.
+__global__ void refitPrimCoeffKernel(int nPrims, int dim, const int *primIndex, const float *minCoeff, const float *maxCoeff,
+                                     PrimAdjacency *adjacency, float *prims)
+{
+    int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= nPrims) return;
+    int p = primIndex[i];
+    adjacency[i].minCoeff = minCoeff[p];
+    adjacency[i].maxCoeff = maxCoeff[p];
+    if (dim == 3) prims[(size_t)12*i + 7] = maxCoeff[p]; // the copy the filter stage reads from the vertex record (v1.w)
+}
+
+__global__ void refitNodeCoeffKernel(const WideNode *nodes, ChildCone *cones, const PrimAdjacency *adjacency, float2 *nodeRange,
+                                     int first, int count)
+{
+    int k = blockIdx.x*blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int w = first + k;
+    const WideNode wn = nodes[w];
+    float nodeMin = kMaxFloat, nodeMax = -kMaxFloat;
+    for (int c = 0; c < kWidth; c++) {
+        uint32_t m = (wn.w[6 + (c >> 2)] >> (8*(c & 3))) & 0xffu;
+        if (m == 0u) continue;
+        float mn = kMaxFloat, mx = -kMaxFloat;
+        int n = (int)(m >> 5);
+        if (n > 0) {
+            int firstPrim = (int)wn.w[5] + (int)(m & 31u);
+            for (int i = 0; i < n; i++) {
+                mn = fminf(mn, adjacency[firstPrim + i].minCoeff);
+                mx = fmaxf(mx, adjacency[firstPrim + i].maxCoeff);
+            }
+        } else {
+            float2 r = nodeRange[wn.w[4] + (m & 31u) - 1u];
+            mn = r.x; mx = r.y;
+        }
+        cones[(size_t)w*kWidth + c].minCoeff = mn;
+        cones[(size_t)w*kWidth + c].maxCoeff = mx;
+        nodeMin = fminf(nodeMin, mn);
+        nodeMax = fmaxf(nodeMax, mx);
+    }
+    nodeRange[w] = make_float2(nodeMin, nodeMax);
+}
+
+namespace {
+
+// level boundaries of the breadth-first node array
+bool computeLevels(const HostBvh& h, std::vector<int>& levelStart)
+{
+    const size_t n = h.nodes.size();
+    std::vector<int> depth(n, 0);
+    for (size_t w = 0; w < n; w++) {
+        const uint8_t *meta = reinterpret_cast<const uint8_t *>(&h.nodes[w].w[6]);
+        for (int c = 0; c < kWidth; c++) {
+            uint8_t m = meta[c];
+            if (m != 0 && (m >> 5) == 0) {
+                size_t child = h.nodes[w].w[4] + (m & 31) - 1;
+                if (child <= w || child >= n) return false;
+                depth[child] = depth[w] + 1;
+            }
+        }
+    }
+    levelStart.assign(1, 0);
+    for (size_t w = 1; w < n; w++) {
+        if (depth[w] < depth[w - 1]) return false; // not breadth first
+        if (depth[w] > depth[w - 1]) levelStart.push_back((int)w);
+    }
+    levelStart.push_back((int)n);
+    return true;
+}
+
+// coefficient arrays already on the device (caller order, one value per input primitive)
+int refitRobinCoefficients(zb_scene *scene, const float *devMin, const float *devMax)
+{
+    DeviceBvhStorage& s = scene->boundary[ZB_REFLECTING];
+    zb_context *ctx = scene->ctx;
+    if (s.levelStart.empty() && !computeLevels(s.host, s.levelStart))
+        return fail(ZB_ERR_UNSUPPORTED, "zb_scene_update_robin_coefficients: node array is not breadth first");
+    const int nPrims = s.host.nPrims;
+    const size_t nNodes = s.host.nodes.size();
+    float2 *nodeRange = reinterpret_cast<float2 *>(s.coeffScratch.as<char>() + (((size_t)2*nPrims*sizeof(float) + 255) & ~size_t(255)));
+    refitPrimCoeffKernel<<<(nPrims + 255)/256, 256, 0, ctx->stream>>>(nPrims, s.host.dim, s.primIndex.as<int>(), devMin, devMax,
+                                                                      s.adjacency.as<PrimAdjacency>(), s.prims.as<float>());
+    ZB_CUDA(cudaGetLastError());
+    for (int l = (int)s.levelStart.size() - 2; l >= 0; l--) {
+        const int first = s.levelStart[l], count = s.levelStart[l + 1] - first;
+        refitNodeCoeffKernel<<<(count + 127)/128, 128, 0, ctx->stream>>>(s.nodes.as<WideNode>(), s.cones.as<ChildCone>(),
+                                                                        s.adjacency.as<PrimAdjacency>(), nodeRange, first, count);
+        ZB_CUDA(cudaGetLastError());
+    }
+    (void)nNodes;
+    return ZB_OK;
+}
+
+int reserveCoeffScratch(DeviceBvhStorage& s)
+{
+    const size_t primBytes = ((size_t)2*s.host.nPrims*sizeof(float) + 255) & ~size_t(255);
+    ZB_CUDA(s.coeffScratch.reserve(primBytes + s.host.nodes.size()*sizeof(float2) + 256));
+    return ZB_OK;
+}
+
+} // namespace
+
+int zb_scene_update_robin_coefficients_dev(zb_scene *scene, const float *minRobinCoeff, const float *maxRobinCoeff)
+{
+    if (!scene || !minRobinCoeff || !maxRobinCoeff) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_scene_update_robin_coefficients_dev: NULL argument");
+    DeviceBvhStorage& s = scene->boundary[ZB_REFLECTING];
+    if (!s.present || scene->reflectingKind != ZB_REFLECTING_ROBIN)
+        return fail(ZB_ERR_INVALID_ARGUMENT, "zb_scene_update_robin_coefficients_dev: scene has no Robin boundary");
+    ZB_CUDA(cudaSetDevice(scene->ctx->device));
+    int rc = reserveCoeffScratch(s);
+    if (rc != ZB_OK) return rc;
+    return refitRobinCoefficients(scene, minRobinCoeff, maxRobinCoeff); // asynchronous on the context's stream
+}
+
 int zb_scene_update_robin_coefficients(zb_scene *scene, const float *minRobinCoeff, const float *maxRobinCoeff)
 {
     if (!scene || !minRobinCoeff || !maxRobinCoeff) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_scene_update_robin_coefficients: NULL argument");
@@ -827,11 +946,16 @@ int zb_scene_update_robin_coefficients(zb_scene *scene, const float *minRobinCoe
     if (!s.present || scene->reflectingKind != ZB_REFLECTING_ROBIN)
         return fail(ZB_ERR_INVALID_ARGUMENT, "zb_scene_update_robin_coefficients: scene has no Robin boundary");
     ZB_CUDA(cudaSetDevice(scene->ctx->device));
-    updateCoefficients(s.host, minRobinCoeff, maxRobinCoeff);
-    ZB_CUDA(cudaMemcpyAsync(s.cones.ptr, s.host.cones.data(), s.host.cones.size()*sizeof(ChildCone), cudaMemcpyHostToDevice, scene->ctx->stream));
-    ZB_CUDA(cudaMemcpyAsync(s.adjacency.ptr, s.host.adjacency.data(), s.host.adjacency.size()*sizeof(PrimAdjacency), cudaMemcpyHostToDevice, scene->ctx->stream));
-    if (s.host.dim == 3) // the vertex records carry a copy of each triangle's maximum coefficient
-        ZB_CUDA(cudaMemcpyAsync(s.prims.ptr, s.host.prims.data(), s.host.prims.size()*sizeof(float), cudaMemcpyHostToDevice, scene->ctx->stream));
+    // 8 bytes per primitive go up; the per-primitive records and the hierarchy's coefficient ranges are refitted on the device
+    // (round 1 recomputed them on the host and uploaded the cone, adjacency and vertex arrays again: ~100 MB for 655 K triangles)
+    int rc = reserveCoeffScratch(s);
+    if (rc != ZB_OK) return rc;
+    const size_t bytes = (size_t)s.host.nPrims*sizeof(float);
+    float *devMin = s.coeffScratch.as<float>(), *devMax = devMin + s.host.nPrims;
+    ZB_CUDA(cudaMemcpyAsync(devMin, minRobinCoeff, bytes, cudaMemcpyHostToDevice, scene->ctx->stream));
+    ZB_CUDA(cudaMemcpyAsync(devMax, maxRobinCoeff, bytes, cudaMemcpyHostToDevice, scene->ctx->stream));
+    rc = refitRobinCoefficients(scene, devMin, devMax);
+    if (rc != ZB_OK) return rc;
     ZB_CUDA(cudaStreamSynchronize(scene->ctx->stream));
     return ZB_OK;
 }

@@ -20,7 +20,7 @@ _lib = None
 SYMBOLS = ["zb_last_error", "zb_abi_version", "zb_device_count", "zb_context_create", "zb_context_destroy",
            "zb_context_set_stream", "zb_context_synchronize", "zb_context_device", "zb_context_sm_count",
            "zb_context_last_solve_profile",
-           "zb_host_bvh_check", "zb_scene_create", "zb_scene_destroy", "zb_scene_update_robin_coefficients", "zb_scene_stats",
+           "zb_host_bvh_check", "zb_scene_create", "zb_scene_destroy", "zb_scene_update_robin_coefficients", "zb_scene_update_robin_coefficients_dev", "zb_scene_stats",
            "zb_closest_point", "zb_intersect_ray", "zb_occluded", "zb_count_ray_hits", "zb_inside_domain", "zb_sample_sphere", "zb_star_radius",
            "zb_solve", "zb_solve_dev", "zb_bvc_splat", "zb_bvc_splat_dev", "zb_context_last_splat_ms", "zb_rws_solve",
            "zb_grid_create", "zb_grid_data", "zb_grid_destroy",
@@ -53,6 +53,7 @@ def lib():
         l.zb_scene_destroy.argtypes = [vp]
         l.zb_scene_destroy.restype = None
         l.zb_scene_update_robin_coefficients.argtypes = [vp, vp, vp]
+        l.zb_scene_update_robin_coefficients_dev.argtypes = [vp, vp, vp]
         l.zb_scene_stats.argtypes = [vp, i, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         l.zb_closest_point.argtypes = [vp, i, i] + [vp]*6
         l.zb_intersect_ray.argtypes = [vp, i, i] + [vp]*7
@@ -284,6 +285,12 @@ class Scene:
     def update_robin_coefficients(self, min_robin, max_robin):
         mn, mx = _f32(min_robin), _f32(max_robin)
         _check(lib().zb_scene_update_robin_coefficients(self._h, abi.ptr(mn), abi.ptr(mx)), "zb_scene_update_robin_coefficients")
+
+    def update_robin_coefficients_dev(self, min_ptr, max_ptr):
+        """the same with DEVICE pointers (e.g. tensor.data_ptr() of float32 tensors, one value per reflecting primitive);
+        asynchronous on the context's stream"""
+        _check(lib().zb_scene_update_robin_coefficients_dev(self._h, C.c_void_p(min_ptr), C.c_void_p(max_ptr)),
+               "zb_scene_update_robin_coefficients_dev")
 
     def closest_point(self, which, x, max_radius=None, want_normal=True):
         x = _f32(x)
