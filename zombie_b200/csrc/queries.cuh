@@ -1066,10 +1066,10 @@ ZB_DEV void primStarRadius2Fast(const BvhView& bvh, uint32_t primIdx, const Vec<
 }
 
 #ifndef ZB_ROBIN_REDO_GRAZING
-#define ZB_ROBIN_REDO_GRAZING 0.01f // ... and when the closest point of the triangle is seen at a cosine below this
+#define ZB_ROBIN_REDO_GRAZING 0.02f // ... and when the closest point of the triangle is seen at a cosine below this
 #endif
 #ifndef ZB_ROBIN_REDO_CONDITIONING
-#define ZB_ROBIN_REDO_CONDITIONING 0.05f // the fast reflectance bound is redone in the reference's order when h mu - c^2 < this * h mu
+#define ZB_ROBIN_REDO_CONDITIONING 0.1f // the fast reflectance bound is redone in the reference's order when h mu - c^2 < this * h mu
 #endif
 #ifndef ZB_ROBIN_RANGE_BOUND
 #define ZB_ROBIN_RANGE_BOUND 1 // 0: only the plane-distance bound (A/B builds)

@@ -485,8 +485,11 @@ ZB_DEV void finishStateWave(const SolveArgs& a, Lane<DIM>& L, StepResult code, W
     L.active = false;
 }
 
+#ifndef ZB_STEP_MIN_BLOCKS
+#define ZB_STEP_MIN_BLOCKS 1 // resident CTAs per SM the step kernel is compiled for (1: no register cap, 129 registers -> 3 CTAs; A/B builds)
+#endif
 template <int DIM, bool WOST>
-__global__ void __launch_bounds__(128) waveStepKernel(SolveArgs a, WaveSlots w, int nBound)
+__global__ void __launch_bounds__(128, ZB_STEP_MIN_BLOCKS) waveStepKernel(SolveArgs a, WaveSlots w, int nBound)
 {
 #if defined(__CUDA_ARCH__)
     const int i = blockIdx.x*blockDim.x + threadIdx.x;
