@@ -196,6 +196,13 @@ def test_cooperative_traversal_on_emulated_warps(tmp_path):
         assert "star: mismatches 0" in r.stdout, r.stdout
         worst = float(r.stdout.split("worst rel ")[1].split(")")[0])
         assert worst < 2e-5, r.stdout   # squared radius; fused vs reference-ordered primitive arithmetic
+    # the child-per-lane form of the node rounds (a build option, measured slower on the device) returns the same results
+    exe2 = str(tmp_path / "coop_check_by_child")
+    r = subprocess.run(cmd[:-4] + ["-DZB_STAR_CHILD_PARALLEL=1", "-DZB_CLOSEST_CHILD_PARALLEL=1", "-o", exe2] + cmd[-2:], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    r = subprocess.run([exe2, "5", "1024", "1.0"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert "distance mismatches 0" in r.stdout and "cooperative status 0" in r.stdout and "star: mismatches 0" in r.stdout, r.stdout
 
 
 def test_cooperative_traversal_2d_on_emulated_warps(tmp_path):

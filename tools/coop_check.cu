@@ -8,6 +8,10 @@
 #include <thread>
 #include <vector>
 
+// ZB_TRACE_QUERY=<index>: prints what lowers that query's radius in the pooled phase (the trace hook of coop.cuh)
+static int g_traceWarp = -1, g_traceLane = -1;
+static thread_local int tlsWarpIndex = -1;
+#define ZB_COOP_TRACE(owner, what, value, id) if (tlsWarpIndex == g_traceWarp && (owner) == g_traceLane) printf("    trace: %s: r2 %.9g id %u\n", what, (double)(value), (unsigned)(id));
 #include "../zombie_b200/csrc/rng.cuh"
 #include "../zombie_b200/csrc/coop.cuh"
 #include "../zombie_b200/csrc/wide_bvh.h"
@@ -39,6 +43,7 @@ int main(int argc, char **argv)
     int nQ = argc > 2 ? atoi(argv[2]) : 2048;
     float mu = argc > 3 ? (float)atof(argv[3]) : 1.0f;
     nQ = (nQ + 31)/32*32;
+    if (const char *t = getenv("ZB_TRACE_QUERY")) { g_traceWarp = atoi(t)/32; g_traceLane = atoi(t)%32; }
     std::vector<float> pos; std::vector<int> tri;
     icosphere(subdiv, pos, tri);
     std::vector<int> triA, triR;
@@ -97,6 +102,7 @@ int main(int argc, char **argv)
             lanes.emplace_back([&, l]() {
                 zbemu::tlsWarp = &warp;
                 zbemu::tlsLane = l;
+                tlsWarpIndex = w0/32;
                 int i = w0 + l;
                 Vec<3> q = loadVec<3>(&x[3*i]);
                 bool has = (i%11) != 10; // some lanes sit the query out
@@ -136,6 +142,37 @@ int main(int argc, char **argv)
                     float a = be, b = bf;
                     primStarRadius2<3>(vr, p, q, a, i%7 != 3, 1e-3f, true); if (a < be) { be = a; ie = p; }
                     primStarRadius2Fast<3>(vr, p, q, b, i%7 != 3, 1e-3f, true); if (b < bf) { bf = b; jf = p; }
+                }
+                // does some primitive report less than both results when it is evaluated with another incoming radius?
+                // (the reference's reflectance bound is order dependent on near-coplanar primitives)
+                {
+                    const float target = 0.99999f*std::max(coopStar[i], seqStar[i]);
+                    if (const char *tp = getenv("ZB_TRACE_PRIM")) {
+                        int p = atoi(tp); float inc = (float)atof(getenv("ZB_TRACE_R2"));
+                        for (int sil = 0; sil < 2; sil++) {
+                            float a = inc, b = inc;
+                            primStarRadius2<3>(vr, p, q, a, i%7 != 3, 1e-3f, sil != 0);
+                            primStarRadius2Fast<3>(vr, p, q, b, i%7 != 3, 1e-3f, sil != 0);
+                            float c = primStarRadius2Call<3>(vr.prims, vr.adjacency, vr.snchSign, p, q, inc, i%7 != 3, 1e-3f, sil != 0);
+                            printf("    prim %d incoming %.9g sil %d: exact %.9g fast %.9g call %.9g needsFull %d\n", p, inc, sil, a, b, c,
+                                   (int)primStarNeedsFullTest<3>(vr, p, q, inc, sil != 0));
+                        }
+                    }
+                    float incoming[43] = {r2max[i], seqStar[i], coopStar[i]};
+                    for (int k = 0; k < 40; k++) incoming[3 + k] = std::min(r2max[i], 0.98f*std::min(coopStar[i], seqStar[i])*std::pow(1.08f, (float)k));
+                    int shown = 0;
+                    for (int p = 0; p < vr.nPrims && shown < 4; p++) {
+                        for (int k = 0; k < 43; k++) {
+                            for (int sil = 0; sil < 2; sil++) {
+                                float a = incoming[k], b = incoming[k];
+                                primStarRadius2<3>(vr, p, q, a, i%7 != 3, 1e-3f, sil != 0);
+                                primStarRadius2Fast<3>(vr, p, q, b, i%7 != 3, 1e-3f, sil != 0);
+                                if ((a < target && a < 0.99999f*incoming[k]) || (b < target && b < 0.99999f*incoming[k])) {
+                                    printf("    prim %d with incoming %.9g, silhouette tests %d: exact %.9g fast %.9g\n", p, incoming[k], sil, a, b); shown++;
+                                }
+                            }
+                        }
+                    }
                 }
                 printf("  star mismatch q %d: seq %.9g coop %.9g (one-thread fast %.9g) r2max %.9g | brute exact %.9g (prim %d) brute fast %.9g (prim %d)\n",
                        i, seqStar[i], coopStar[i], r2f, r2max[i], be, ie, bf, jf);

@@ -240,6 +240,138 @@ ZB_COOP void coopRefill(WarpShared& ws, int& nodeTop, int& primTop, int lane, co
     primTop += totalP;
 }
 
+#ifndef ZB_CLOSEST_CHILD_PARALLEL
+#define ZB_CLOSEST_CHILD_PARALLEL 0 // 1: the distance query's node rounds run one child per lane as well (A/B builds)
+#endif
+#ifndef ZB_STAR_CHILD_PARALLEL
+#define ZB_STAR_CHILD_PARALLEL 0 // 1: node rounds of the pooled star query run one CHILD per lane (coopNodeRoundByChild below); measured slower, see there
+#endif
+
+// MEASURED AND NOT SHIPPED (profiles/README.md, r2w): same instruction count as the node-per-lane round (every lane of a group
+// decodes the node again, and the ranking costs what the sorted insertion did), 23.7 instead of 17.7 active lanes per
+// instruction, but 57 % instead of 67 % busy issue slots (shuffle and shared-memory dependencies): 21.4 ms instead of 17.7 ms
+// per round. Kept as a build option (ZB_STAR_CHILD_PARALLEL / ZB_CLOSEST_CHILD_PARALLEL = 1); the emulated-warp test covers it.
+//
+// Node round of the pooled star-radius query, one CHILD per lane. With one node per lane a round of n nodes keeps n lanes
+// busy for eight child tests each, and a pool in its depth-first phase rarely has 32 nodes to give (ncu, one node per lane:
+// 13 of 32 lanes active in the child test, 10 in the push, together half the kernel's instructions). Here the n popped nodes
+// are processed four at a time: the eight lanes of a group test the eight child slots of one node, the node's radius bound
+// is the group's minimum, and the survivors are ranked inside their group by seven shuffles (farther children lower on the
+// lists, the nearest on top) — the same list contents as coopPushChildren produces, in a different order of the groups:
+// passes run from the farthest popped node to the nearest, so the nearest node's nearest child ends on top.
+// STAR = false is the same round for the distance query: the child test is the box distance alone.
+template <int DIM, bool STAR>
+ZB_COOP void coopNodeRoundByChild(const BvhView& bvh, WarpShared& ws, int& nodeTop, int& primTop, int fullTop, int lane,
+                                  float precision, int *status)
+{
+    const int n = coopNodeBudget(nodeTop, primTop, fullTop);
+    if (lane == 0) { if (STAR) { ZB_COOP_COUNT(2, n) ZB_COOP_COUNT(6, 1) } else { ZB_COOP_COUNT(0, n) ZB_COOP_COUNT(4, 1) } }
+    // the popped items leave the list before anything is pushed: lane j keeps item j (0 = top of the list)
+    uint2 mine = make_uint2(0u, 0u);
+    if (lane < n) mine = ws.nodes[nodeTop - 1 - lane];
+    nodeTop -= n;
+    zb_syncwarp();
+    const int g = lane >> 3, c = lane & 7;
+    const uint32_t kNone = 0xffffffffu;
+#pragma unroll 1
+    for (int p = (n + 3)/4 - 1; p >= 0; p--) {
+        const int j = 4*p + g;
+        uint2 item;
+        item.x = (uint32_t)zb_shfl((int)mine.x, j & 31);
+        item.y = (uint32_t)zb_shfl((int)mine.y, j & 31);
+        bool valid = j < n;
+        const int owner = (int)(item.x & 31u);
+        float r2 = 0.0f, upper = kMaxFloat;
+        uint32_t packed = kNone; // lower bound (rounded down to 64 ulps) | primitive count << 3 | child slot; kNone: nothing to push
+        uint32_t ref = 0u, sil = 0u;
+        if (valid) {
+            r2 = coopRadius2(ws, owner);
+            valid = zb_uint_as_float(item.x & ~63u) <= r2;
+        }
+        if (valid) {
+            NodeRegs node;
+            loadNode(bvh.nodes, item.y, node);
+            const uint32_t meta = childMeta(node, c);
+            if (meta != 0u) {
+                Vec<DIM> q;
+                q[0] = ws.qx[owner]; q[1] = ws.qy[owner];
+                if (DIM == 3) q[DIM - 1] = ws.qz[owner];
+                NodeFrame<DIM> f = nodeFrame<DIM>(node);
+                float lo[DIM], hi[DIM], d2min, d2max;
+                childBox<DIM>(node, f, c, lo, hi);
+                boxDistance2<DIM>(lo, hi, q, d2min, d2max);
+                if (!STAR) {
+                    // closest point: every child's farthest corner bounds the radius (bvh.inl:1339-1343), its nearest is the key
+                    upper = d2max;
+                    const uint32_t count = meta >> 5;
+                    packed = (zb_float_as_uint(d2min) & ~63u) | (count << 3) | (uint32_t)c;
+                    ref = count ? node.q[1].y + (meta & 31u) : node.q[1].x + (meta & 31u) - 1u;
+                } else if (!(d2min > r2)) {
+                    const float4 *cone = bvh.cones + (size_t)item.y*16 + 2*c;
+                    float4 c0 = zb_ldg(cone), c1 = zb_ldg(cone + 1);
+                    float lower, up;
+                    bool hasSil;
+                    if (starChildBoundsFast<DIM>(c0, c1, q, lo, hi, d2min, d2max, lower, up, hasSil, precision)) {
+                        upper = up;
+                        const bool parentNoSil = (item.x >> 5) & 1u; // no silhouette above => none below
+                        sil = (!hasSil || parentNoSil) ? 1u : 0u;
+                        const uint32_t count = meta >> 5;
+                        packed = (zb_float_as_uint(lower) & ~63u) | (count << 3) | (uint32_t)c;
+                        ref = count ? node.q[1].y + (meta & 31u) : node.q[1].x + (meta & 31u) - 1u;
+                    }
+                }
+            }
+        }
+        // the node's upper bound of the radius: the minimum over its children (non-negative floats order like their bits)
+        uint32_t shrinkBits = zb_float_as_uint(upper);
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) shrinkBits = zb_umin(shrinkBits, (uint32_t)zb_shfl((int)shrinkBits, lane ^ o));
+        const float shrink = zb_uint_as_float(shrinkBits);
+        if (valid && shrink < r2) {
+            if (c == 0) zb_atomic_min64(&ws.best[owner], packBest(shrink, STAR ? 0u : 0xffffffffu));
+            r2 = shrink;
+        }
+        if (packed != kNone && !(zb_uint_as_float(packed & ~63u) <= r2)) packed = kNone;
+
+        // rank inside the group (farther survivors below) and the group's totals, from the seven other lanes of the group
+        int belowN = 0, belowP = 0, groupN = 0, groupP = 0;
+        if (packed != kNone) { uint32_t cnt = (packed >> 3) & 7u; groupN = cnt == 0u ? 1 : 0; groupP = (int)cnt; }
+#pragma unroll
+        for (int d = 1; d < 8; d++) {
+            uint32_t o = (uint32_t)zb_shfl((int)packed, (lane & ~7) | ((c + d) & 7));
+            if (o != kNone) {
+                uint32_t cnt = (o >> 3) & 7u;
+                int isNode = cnt == 0u ? 1 : 0;
+                groupN += isNode; groupP += (int)cnt;
+                if (packed != kNone && o > packed) { belowN += isNode; belowP += (int)cnt; }
+            }
+        }
+        // groups are stacked 3 (bottom) ... 0 (top): group 0 holds the nearest of the pass's four nodes
+        const uint32_t tot = (uint32_t)groupN | ((uint32_t)groupP << 16);
+        const uint32_t t0 = (uint32_t)zb_shfl((int)tot, 0), t1 = (uint32_t)zb_shfl((int)tot, 8), t2 = (uint32_t)zb_shfl((int)tot, 16),
+                       t3 = (uint32_t)zb_shfl((int)tot, 24);
+        const uint32_t below = (g < 3 ? t3 : 0u) + (g < 2 ? t2 : 0u) + (g < 1 ? t1 : 0u), all = t0 + t1 + t2 + t3;
+        const int totalN = (int)(all & 0xffffu), totalP = (int)(all >> 16);
+        if (nodeTop + totalN > kNodeStack || primTop + totalP + fullTop > kPrimQueue) { // warp-uniform; cannot happen for trees of depth <= 18
+            if (lane == 0 && status) zb_status_or(status, kStatusCoopOverflow);
+            continue;
+        }
+        if (packed != kNone) {
+            const uint32_t cnt = (packed >> 3) & 7u;
+            if (cnt == 0u) {
+                ws.nodes[nodeTop + (int)(below & 0xffffu) + belowN] = make_uint2((packed & ~63u) | (sil << 5) | (uint32_t)owner, ref);
+            } else {
+                const uint32_t head = ((uint32_t)owner << 27) | (sil << 26);
+                const int base = primTop + (int)(below >> 16) + belowP;
+                for (uint32_t i = 0; i < cnt; i++) ws.prims[base + (int)i] = head | (ref + cnt - 1u - i);
+            }
+        }
+        nodeTop += totalN;
+        primTop += totalP;
+    }
+    zb_syncwarp();
+}
+
 // Aggregate::findClosestPoint for up to 32 queries at once (one per lane with hasQuery). Every lane of
 // the warp must call this. r2max: squared search radius. On return hit describes the lane's own query.
 template <int DIM>
@@ -386,133 +518,6 @@ ZB_COOP_NOINLINE void coopClosestPoint(const BvhView& bvh, WarpShared& ws, bool 
 // ------------------------------------------------------------------------------------------
 // star radius
 // ------------------------------------------------------------------------------------------
-
-#ifndef ZB_CLOSEST_CHILD_PARALLEL
-#define ZB_CLOSEST_CHILD_PARALLEL 0 // 1: the distance query's node rounds run one child per lane as well (A/B builds)
-#endif
-#ifndef ZB_STAR_CHILD_PARALLEL
-#define ZB_STAR_CHILD_PARALLEL 1 // 0: node rounds of the pooled star query run one NODE per lane (eight child tests in a loop) as the distance query does (A/B builds)
-#endif
-
-// Node round of the pooled star-radius query, one CHILD per lane. With one node per lane a round of n nodes keeps n lanes
-// busy for eight child tests each, and a pool in its depth-first phase rarely has 32 nodes to give (ncu, one node per lane:
-// 13 of 32 lanes active in the child test, 10 in the push, together half the kernel's instructions). Here the n popped nodes
-// are processed four at a time: the eight lanes of a group test the eight child slots of one node, the node's radius bound
-// is the group's minimum, and the survivors are ranked inside their group by seven shuffles (farther children lower on the
-// lists, the nearest on top) — the same list contents as coopPushChildren produces, in a different order of the groups:
-// passes run from the farthest popped node to the nearest, so the nearest node's nearest child ends on top.
-// STAR = false is the same round for the distance query: the child test is the box distance alone.
-template <int DIM, bool STAR>
-ZB_COOP void coopNodeRoundByChild(const BvhView& bvh, WarpShared& ws, int& nodeTop, int& primTop, int fullTop, int lane,
-                                  float precision, int *status)
-{
-    const int n = coopNodeBudget(nodeTop, primTop, fullTop);
-    if (lane == 0) { if (STAR) { ZB_COOP_COUNT(2, n) ZB_COOP_COUNT(6, 1) } else { ZB_COOP_COUNT(0, n) ZB_COOP_COUNT(4, 1) } }
-    // the popped items leave the list before anything is pushed: lane j keeps item j (0 = top of the list)
-    uint2 mine = make_uint2(0u, 0u);
-    if (lane < n) mine = ws.nodes[nodeTop - 1 - lane];
-    nodeTop -= n;
-    zb_syncwarp();
-    const int g = lane >> 3, c = lane & 7;
-    const uint32_t kNone = 0xffffffffu;
-#pragma unroll 1
-    for (int p = (n + 3)/4 - 1; p >= 0; p--) {
-        const int j = 4*p + g;
-        uint2 item;
-        item.x = (uint32_t)zb_shfl((int)mine.x, j & 31);
-        item.y = (uint32_t)zb_shfl((int)mine.y, j & 31);
-        bool valid = j < n;
-        const int owner = (int)(item.x & 31u);
-        float r2 = 0.0f, upper = kMaxFloat;
-        uint32_t packed = kNone; // lower bound (rounded down to 64 ulps) | primitive count << 3 | child slot; kNone: nothing to push
-        uint32_t ref = 0u, sil = 0u;
-        if (valid) {
-            r2 = coopRadius2(ws, owner);
-            valid = zb_uint_as_float(item.x & ~63u) <= r2;
-        }
-        if (valid) {
-            NodeRegs node;
-            loadNode(bvh.nodes, item.y, node);
-            const uint32_t meta = childMeta(node, c);
-            if (meta != 0u) {
-                Vec<DIM> q;
-                q[0] = ws.qx[owner]; q[1] = ws.qy[owner];
-                if (DIM == 3) q[DIM - 1] = ws.qz[owner];
-                NodeFrame<DIM> f = nodeFrame<DIM>(node);
-                float lo[DIM], hi[DIM], d2min, d2max;
-                childBox<DIM>(node, f, c, lo, hi);
-                boxDistance2<DIM>(lo, hi, q, d2min, d2max);
-                if (!STAR) {
-                    // closest point: every child's farthest corner bounds the radius (bvh.inl:1339-1343), its nearest is the key
-                    upper = d2max;
-                    const uint32_t count = meta >> 5;
-                    packed = (zb_float_as_uint(d2min) & ~63u) | (count << 3) | (uint32_t)c;
-                    ref = count ? node.q[1].y + (meta & 31u) : node.q[1].x + (meta & 31u) - 1u;
-                } else if (!(d2min > r2)) {
-                    const float4 *cone = bvh.cones + (size_t)item.y*16 + 2*c;
-                    float4 c0 = zb_ldg(cone), c1 = zb_ldg(cone + 1);
-                    float lower, up;
-                    bool hasSil;
-                    if (starChildBoundsFast<DIM>(c0, c1, q, lo, hi, d2min, d2max, lower, up, hasSil, precision)) {
-                        upper = up;
-                        const bool parentNoSil = (item.x >> 5) & 1u; // no silhouette above => none below
-                        sil = (!hasSil || parentNoSil) ? 1u : 0u;
-                        const uint32_t count = meta >> 5;
-                        packed = (zb_float_as_uint(lower) & ~63u) | (count << 3) | (uint32_t)c;
-                        ref = count ? node.q[1].y + (meta & 31u) : node.q[1].x + (meta & 31u) - 1u;
-                    }
-                }
-            }
-        }
-        // the node's upper bound of the radius: the minimum over its children (non-negative floats order like their bits)
-        uint32_t shrinkBits = zb_float_as_uint(upper);
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) shrinkBits = zb_umin(shrinkBits, (uint32_t)zb_shfl((int)shrinkBits, lane ^ o));
-        const float shrink = zb_uint_as_float(shrinkBits);
-        if (valid && shrink < r2) {
-            if (c == 0) zb_atomic_min64(&ws.best[owner], packBest(shrink, STAR ? 0u : 0xffffffffu));
-            r2 = shrink;
-        }
-        if (packed != kNone && !(zb_uint_as_float(packed & ~63u) <= r2)) packed = kNone;
-
-        // rank inside the group (farther survivors below) and the group's totals, from the seven other lanes of the group
-        int belowN = 0, belowP = 0, groupN = 0, groupP = 0;
-        if (packed != kNone) { uint32_t cnt = (packed >> 3) & 7u; groupN = cnt == 0u ? 1 : 0; groupP = (int)cnt; }
-#pragma unroll
-        for (int d = 1; d < 8; d++) {
-            uint32_t o = (uint32_t)zb_shfl((int)packed, (lane & ~7) | ((c + d) & 7));
-            if (o != kNone) {
-                uint32_t cnt = (o >> 3) & 7u;
-                int isNode = cnt == 0u ? 1 : 0;
-                groupN += isNode; groupP += (int)cnt;
-                if (packed != kNone && o > packed) { belowN += isNode; belowP += (int)cnt; }
-            }
-        }
-        // groups are stacked 3 (bottom) ... 0 (top): group 0 holds the nearest of the pass's four nodes
-        const uint32_t tot = (uint32_t)groupN | ((uint32_t)groupP << 16);
-        const uint32_t t0 = (uint32_t)zb_shfl((int)tot, 0), t1 = (uint32_t)zb_shfl((int)tot, 8), t2 = (uint32_t)zb_shfl((int)tot, 16),
-                       t3 = (uint32_t)zb_shfl((int)tot, 24);
-        const uint32_t below = (g < 3 ? t3 : 0u) + (g < 2 ? t2 : 0u) + (g < 1 ? t1 : 0u), all = t0 + t1 + t2 + t3;
-        const int totalN = (int)(all & 0xffffu), totalP = (int)(all >> 16);
-        if (nodeTop + totalN > kNodeStack || primTop + totalP + fullTop > kPrimQueue) { // warp-uniform; cannot happen for trees of depth <= 18
-            if (lane == 0 && status) zb_status_or(status, kStatusCoopOverflow);
-            continue;
-        }
-        if (packed != kNone) {
-            const uint32_t cnt = (packed >> 3) & 7u;
-            if (cnt == 0u) {
-                ws.nodes[nodeTop + (int)(below & 0xffffu) + belowN] = make_uint2((packed & ~63u) | (sil << 5) | (uint32_t)owner, ref);
-            } else {
-                const uint32_t head = ((uint32_t)owner << 27) | (sil << 26);
-                const int base = primTop + (int)(below >> 16) + belowP;
-                for (uint32_t i = 0; i < cnt; i++) ws.prims[base + (int)i] = head | (ref + cnt - 1u - i);
-            }
-        }
-        nodeTop += totalN;
-        primTop += totalP;
-    }
-    zb_syncwarp();
-}
 
 // Phase 2 of the star-radius query: pools the traversals phase 1 left unfinished. Every lane of the warp calls; hasQuery:
 // the lane owns a query (x, flip) whose radius so far is r2own and whose unfinished traversal is stack[0..sp). Returns the
