@@ -430,7 +430,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--batch", type=int, default=32768, help="evaluation points per step (per GPU when --scaling weak, in total when strong)")
+    ap.add_argument("--batch", type=int, default=65536, help="evaluation points per step (per GPU when --scaling weak, in total when strong)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--subdiv", type=int, default=8, help="icosphere subdivisions (8 -> 1,310,720 triangles)")
     ap.add_argument("--points", type=int, default=1 << 20)

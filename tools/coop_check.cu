@@ -153,7 +153,7 @@ int main(int argc, char **argv)
                             float a = inc, b = inc;
                             primStarRadius2<3>(vr, p, q, a, i%7 != 3, 1e-3f, sil != 0);
                             primStarRadius2Fast<3>(vr, p, q, b, i%7 != 3, 1e-3f, sil != 0);
-                            float c = primStarRadius2Call<3>(vr.prims, vr.adjacency, vr.snchSign, p, q, inc, i%7 != 3, 1e-3f, sil != 0);
+                            float c = primStarRadius2Call<3>(vr.prims, vr.adjacency, vr.snchSign, p, q, inc, i%7 != 3, 1e-3f, sil != 0).x;
                             printf("    prim %d incoming %.9g sil %d: exact %.9g fast %.9g call %.9g needsFull %d\n", p, inc, sil, a, b, c,
                                    (int)primStarNeedsFullTest<3>(vr, p, q, inc, sil != 0));
                         }

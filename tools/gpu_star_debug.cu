@@ -46,8 +46,8 @@ __global__ void primKernel(BvhView v, float qx, float qy, float qz, int prim)
         float a = r2ins[k], b = r2ins[k];
         primStarRadius2<3>(v, prim, x, a, true, 1e-3f, true);
         primStarRadius2Fast<3>(v, prim, x, b, true, 1e-3f, true);
-        float c = primStarRadius2Call<3>(v.prims, v.adjacency, v.snchSign, prim, x, r2ins[k], true, 1e-3f, true);
-        float d = primStarRadius2Call<3>(v.prims, v.adjacency, v.snchSign, prim, x, r2ins[k], true, 1e-3f, false);
+        float c = primStarRadius2Call<3>(v.prims, v.adjacency, v.snchSign, prim, x, r2ins[k], true, 1e-3f, true).x;
+        float d = primStarRadius2Call<3>(v.prims, v.adjacency, v.snchSign, prim, x, r2ins[k], true, 1e-3f, false).x;
         printf("prim %d r2in %.9g: exact %.9g (r %.8f) fast %.9g (r %.8f) call %.9g call(noSil) %.9g needsFull %d\n", prim, r2ins[k], a, sqrtf(a), b, sqrtf(b), c, d,
                (int)primStarNeedsFullTest<3>(v, prim, x, r2ins[k], true));
     }
@@ -60,7 +60,7 @@ __global__ void divergentKernel(BvhView v, float qx, float qy, float qz, float r
     Vec<3> x = make3(qx, qy, qz);
     int l = threadIdx.x;
     if (l < 15) {
-        float r = primStarRadius2Call<3>(v.prims, v.adjacency, v.snchSign, prims[l], x, r2in, true, 1e-3f, true);
+        float r = primStarRadius2Call<3>(v.prims, v.adjacency, v.snchSign, prims[l], x, r2in, true, 1e-3f, true).x;
         printf("divergent lane %d prim %d: %.9g\n", l, prims[l], r);
     }
 }

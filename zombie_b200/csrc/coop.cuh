@@ -101,6 +101,7 @@ struct WarpShared {
     float qx[32], qy[32], qz[32];
     unsigned int flags[32];
     uint32_t redo[64];                  // star radius: primitives whose fast test asked for the reference-ordered redo (same item format)
+    uint32_t redoRobin[64];             // ... for the redo of their reflectance part only
 };
 
 // four 128-thread CTAs per SM (the register budget of the walk kernel) must also fit in the 227 KB of shared memory,
@@ -546,7 +547,7 @@ ZB_COOP float coopStarPooled(const BvhView& bvh, WarpShared& ws, bool hasQuery, 
     // and a warp pays for the redo in full whenever one lane takes it. So the full round only marks such primitives; they
     // collect in ws.redo and are redone 32 at a time. Radii combine by minimum, so the order of the tests does not matter.
     constexpr bool kDeferRedo = kTwoStage && ZB_STAR_DEFER_REDO;
-    int redoTop = 0;
+    int redoTop = 0, robinTop = 0; // whole-primitive redos (rare: a silhouette decision on its threshold) / reflectance-only redos
     zb_syncwarp();
 
     while (true) {
@@ -555,8 +556,25 @@ ZB_COOP float coopStarPooled(const BvhView& bvh, WarpShared& ws, bool hasQuery, 
             zb_syncwarp();
         }
         const bool drained = nodeTop == 0 && primTop == 0 && fullTop == 0;
-        if (drained && redoTop == 0) break;
-        if (kDeferRedo && (redoTop >= 32 || drained)) {
+        if (drained && redoTop == 0 && robinTop == 0) break;
+        if (kDeferRedo && (robinTop >= 32 || (drained && robinTop > 0))) {
+            // ---- redo round, reflectance part only
+            int n = min(robinTop, 32);
+            if (lane < n) {
+                uint32_t item = ws.redoRobin[robinTop - n + lane];
+                int owner = (int)(item >> 27);
+                float before = coopRadius2(ws, owner);
+                Vec<DIM> q;
+                q[0] = ws.qx[owner]; q[1] = ws.qy[owner];
+                if (DIM == 3) q[DIM - 1] = ws.qz[owner];
+                float r2 = primStarRobinRedo<DIM>(bvh.prims, item & kPrimIndexMask, q, before);
+                if (r2 < before) zb_atomic_min64(&ws.best[owner], packBest(r2, 0u));
+            }
+            robinTop -= n;
+            zb_syncwarp();
+            continue;
+        }
+        if (kDeferRedo && (redoTop >= 32 || (drained && redoTop > 0))) {
             // ---- redo round
             int n = min(redoTop, 32);
             if (lane < n) {
@@ -579,7 +597,7 @@ ZB_COOP float coopStarPooled(const BvhView& bvh, WarpShared& ws, bool hasQuery, 
             // ---- full round on the survivors
             int n = min(fullTop, 32);
             if (lane == 0) { ZB_COOP_COUNT(3, n) ZB_COOP_COUNT(7, 1) }
-            bool needRedo = false;
+            int redoKind = 0;
             uint32_t item = 0u;
             if (lane < n) {
                 item = ws.prims[kPrimQueue - fullTop + lane];
@@ -589,16 +607,20 @@ ZB_COOP float coopStarPooled(const BvhView& bvh, WarpShared& ws, bool hasQuery, 
                 Vec<DIM> q;
                 q[0] = ws.qx[owner]; q[1] = ws.qy[owner];
                 if (DIM == 3) q[DIM - 1] = ws.qz[owner];
-                r2 = primStarRadius2Call<DIM>(bvh.prims, bvh.adjacency, bvh.snchSign, item & kPrimIndexMask, q, r2, ws.flags[owner] != 0u,
-                                              precision, silhouetteTests, kDeferRedo);
-                if (kDeferRedo && r2 < 0.0f) { needRedo = true; r2 = before; }
+                float2 res = primStarRadius2Call<DIM>(bvh.prims, bvh.adjacency, bvh.snchSign, item & kPrimIndexMask, q, r2, ws.flags[owner] != 0u,
+                                                      precision, silhouetteTests, kDeferRedo);
+                r2 = res.x;
+                redoKind = kDeferRedo ? (int)res.y : 0;
                 if (r2 < before) { ZB_COOP_TRACE(owner, silhouetteTests ? "full-round primitive (silhouette tests on)" : "full-round primitive (no silhouette tests)", r2, item & kPrimIndexMask) ZB_COOP_TRACE(owner, "   ... its incoming radius", before, lane) ZB_COOP_TRACE(owner, "   ... query x", q[0], item) ZB_COOP_TRACE(owner, "   ... query y", q[1], ws.flags[owner]) ZB_COOP_TRACE(owner, "   ... query z", q[DIM - 1], fullTop) zb_atomic_min64(&ws.best[owner], packBest(r2, 0u)); }
             }
             fullTop -= n;
             if (kDeferRedo) {
-                unsigned int m = zb_ballot(needRedo);
-                if (needRedo) ws.redo[redoTop + zb_popc(m & ((1u << lane) - 1u))] = item;
+                unsigned int m = zb_ballot(redoKind == 1);
+                if (redoKind == 1) ws.redo[redoTop + zb_popc(m & ((1u << lane) - 1u))] = item;
                 redoTop += zb_popc(m); // < 32 before the round (else a redo round would have run), <= 63 now
+                m = zb_ballot(redoKind == 2);
+                if (redoKind == 2) ws.redoRobin[robinTop + zb_popc(m & ((1u << lane) - 1u))] = item;
+                robinTop += zb_popc(m);
             }
             zb_syncwarp();
             continue;
@@ -621,7 +643,7 @@ ZB_COOP float coopStarPooled(const BvhView& bvh, WarpShared& ws, bool hasQuery, 
                     survivor = primStarNeedsFullTest<DIM>(bvh, item & kPrimIndexMask, q, r2, silhouetteTests);
                 } else {
                     r2 = primStarRadius2Call<DIM>(bvh.prims, bvh.adjacency, bvh.snchSign, item & kPrimIndexMask, q, r2,
-                                                  ws.flags[owner] != 0u, precision, silhouetteTests);
+                                                  ws.flags[owner] != 0u, precision, silhouetteTests).x;
                     if (r2 < before) zb_atomic_min64(&ws.best[owner], packBest(r2, 0u));
                 }
             }

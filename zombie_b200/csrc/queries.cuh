@@ -1038,6 +1038,45 @@ ZB_DEV_COLD float primStarRadius2Redo(const float4 *prims, const float4 *adjacen
     return r2;
 }
 
+// The reflectance part of primStarRadius2 alone, in the reference's order (closest point, plane distance, clamping cosines,
+// radius bound: geometry.h:196-236): what primStarRadius2Fast redoes when only its reflectance bound is ill-conditioned —
+// a grazing view or a bound close to its pole, by far the most frequent reasons for a redo. r2: the radius after the
+// primitive's silhouette part (or any smaller radius found since: radii combine by minimum). ~450 instructions against
+// ~1,900 for the whole primitive.
+template <int DIM>
+ZB_DEV float primStarRobinRedo(const float4 *prims, uint32_t primIdx, Vec<DIM> x, float r2)
+{
+    return r2; // the 2D star test has no fast form and never asks for it
+}
+
+template <>
+ZB_DEV_COLD float primStarRobinRedo<3>(const float4 *prims, uint32_t primIdx, Vec<3> x, float r2)
+{
+    constexpr int DIM = 3;
+    BvhView bvh{};
+    bvh.prims = prims;
+    Prim<DIM> prim;
+    prim.load(bvh, primIdx);
+    Vec<DIM> closestPt;
+    float bu, bv;
+    float closestDist = prim.closest(x, closestPt, bu, bv);
+    float closestDist2 = closestDist*closestDist;
+    if (closestDist2 > r2) return r2;
+    const float maxCoeff = prim.maxCoeff;
+    if (!(maxCoeff > kEpsilon) || !(maxCoeff < kMaxFloat - kEpsilon)) return r2;
+    if (closestDist < kEpsilon) return closestDist; // sic (geometry.h:216)
+    if (!(r2 > closestDist2)) return r2;
+    Vec<DIM> n0 = unitNormal<DIM>(prim);
+    Vec<DIM> far;
+    float farDist = farthestVertex(prim, x, far);
+    float h = fabsf(xdot(n0, prim.a - x)/xdot(n0, n0)); // findClosestPointPlane (geometry.h:62-70)
+    if (!(h > 0.0f)) return fminf(r2, closestDist2);
+    float cosUpper = fabsf(xdot((x - closestPt)/closestDist, n0));
+    float cosLower = fabsf(xdot((x - far)/farDist, n0));
+    float radius = robinRadiusBound<DIM>(h, maxCoeff, cosLower, cosUpper);
+    return radius < kMaxFloat ? fminf(r2, radius*radius) : r2;
+}
+
 // the on-the-edge branch of isSilhouetteEdge3 (atan2 of the dihedral angle): rare, kept out of line
 ZB_DEV_COLD bool isSilhouetteEdge3Cold(Vec<3> pa, Vec<3> pb, Vec<3> n0, Vec<3> n1, Vec<3> viewDir, float d, bool flip,
                                        float precision, float convention)
@@ -1060,7 +1099,7 @@ ZB_DEV_COLD bool isSilhouetteEdge3Cold(Vec<3> pa, Vec<3> pb, Vec<3> n0, Vec<3> n
 // rounding (the gate on this query is FCPW's 1e-3 silhouette tolerance); roughly half the instructions.
 template <int DIM>
 ZB_DEV void primStarRadius2Fast(const BvhView& bvh, uint32_t primIdx, const Vec<DIM>& x, float& r2, bool flip,
-                                float precision, bool silhouetteTests, bool *deferRedo = nullptr)
+                                float precision, bool silhouetteTests, int *deferRedo = nullptr)
 {
     primStarRadius2<DIM>(bvh, primIdx, x, r2, flip, precision, silhouetteTests);
 }
@@ -1117,12 +1156,13 @@ ZB_DEV float closestPointTriangleFast2(const Vec<3>& pa, const Vec<3>& pb, const
     return norm2(x - pt);
 }
 
-// deferRedo: when given, a primitive that needs the reference-ordered redo is NOT redone here: *deferRedo is set and r2
-// is left untouched, so that the caller can collect such primitives and redo them together (coop.cuh: in a warp the
-// 1,900-instruction redo costs the same whether one lane takes it or all 32 do).
+// deferRedo: when given, a primitive that needs a reference-ordered redo is NOT redone here: *deferRedo says which redo
+// (1: the whole primitive, r2 untouched; 2: the reflectance part only, r2 = the radius after the silhouette part), so that the
+// caller can collect such primitives and redo them together (coop.cuh: in a warp a redo costs the same whether one lane
+// takes it or all 32 do).
 template <>
 ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const Vec<3>& x, float& r2, bool flip,
-                                   float precision, bool silhouetteTests, bool *deferRedo)
+                                   float precision, bool silhouetteTests, int *deferRedo)
 {
     Prim<3> prim;
     prim.load(bvh, primIdx);
@@ -1160,7 +1200,8 @@ ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const V
     // ill-conditioned, the primitive is redone with the reference-ordered arithmetic of primStarRadius2, so the
     // two never disagree by more than float rounding.
     const float r2in = r2;
-    bool redo = false;
+    bool redo = false;      // a silhouette decision within rounding distance of its threshold: redo the whole primitive
+    bool redoRobin = false; // the reflectance bound alone is ill-conditioned: redo that part (primStarRobinRedo)
 
     float4 a0 = zb_ldg(bvh.adjacency + (size_t)3*primIdx), a1 = zb_ldg(bvh.adjacency + (size_t)3*primIdx + 1),
            a2 = zb_ldg(bvh.adjacency + (size_t)3*primIdx + 2);
@@ -1224,6 +1265,7 @@ ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const V
         }
     }
 
+    const float r2AfterSilhouettes = r2;
     if (maxCoeff > kEpsilon && !robinCannotShrink) { // reflectance case
         float closestDist = sqrtf(closestDist2);
         if (closestDist < kEpsilon) {
@@ -1246,7 +1288,7 @@ ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const V
                 float hmu = h*maxCoeff, maxCos = sqrtf(hmu);
                 float c = clampLikeStd(maxCos/1.7320508075688772935f, cosLower, cosUpper);
                 if (cosUpper < ZB_ROBIN_REDO_GRAZING) { ZB_CLASS(17) } else if (fabsf(maxCos - cosLower) < 1e-5f) { ZB_CLASS(18) } else if (maxCos >= cosLower && (hmu - c*c) < ZB_ROBIN_REDO_CONDITIONING*hmu) { ZB_CLASS(19) }
-                redo = redo || cosUpper < ZB_ROBIN_REDO_GRAZING || fabsf(maxCos - cosLower) < 1e-5f || (maxCos >= cosLower && (hmu - c*c) < ZB_ROBIN_REDO_CONDITIONING*hmu);
+                redoRobin = cosUpper < ZB_ROBIN_REDO_GRAZING || fabsf(maxCos - cosLower) < 1e-5f || (maxCos >= cosLower && (hmu - c*c) < ZB_ROBIN_REDO_CONDITIONING*hmu);
                 ZB_PRIM_TRACE(primIdx, "fast reflectance: h cosLower cosUpper radius^2", h, cosLower, cosUpper, radius*radius)
             } else {
                 r2 = fminf(r2, closestDist2);
@@ -1254,9 +1296,16 @@ ZB_DEV void primStarRadius2Fast<3>(const BvhView& bvh, uint32_t primIdx, const V
         }
     }
     ZB_PRIM_TRACE(primIdx, "fast result before redo: r2in r2 redo cannotShrink", r2in, r2, redo ? 1.0f : 0.0f, robinCannotShrink ? 1.0f : 0.0f)
-    if (redo) { ZB_CLASS(15) }
-    if (redo && deferRedo) { *deferRedo = true; r2 = r2in; return; }
-    if (redo) r2 = primStarRadius2Redo<3>(bvh.prims, bvh.adjacency, bvh.snchSign, primIdx, x, r2in, flip, precision, silhouetteTests);
+    if (redo || redoRobin) { ZB_CLASS(15) }
+    if (deferRedo) {
+        // 1: redo the whole primitive from r2in; 2: the silhouette part stands, redo the reflectance part only
+        if (redo) { *deferRedo = 1; r2 = r2in; return; }
+        if (redoRobin) { *deferRedo = 2; r2 = r2AfterSilhouettes; return; }
+    } else if (redo) {
+        r2 = primStarRadius2Redo<3>(bvh.prims, bvh.adjacency, bvh.snchSign, primIdx, x, r2in, flip, precision, silhouetteTests);
+    } else if (redoRobin) {
+        r2 = primStarRobinRedo<3>(bvh.prims, primIdx, x, r2AfterSilhouettes);
+    }
     ZB_PRIM_TRACE(primIdx, "final: r2 | query", r2, x[0], x[1], x[2])
     if (r2 < r2in) { ZB_CLASS(12) if (!silhouetteTests) { ZB_CLASS(13) } }
 }
@@ -1297,16 +1346,18 @@ ZB_DEV
 #else
 ZB_DEV_COLD
 #endif
-float primStarRadius2Call(const float4 *prims, const float4 *adjacency, int snchSign, uint32_t primIdx, Vec<DIM> x, float r2,
-                          bool flip, float precision, bool silhouetteTests, bool defer = false)
+float2 primStarRadius2Call(const float4 *prims, const float4 *adjacency, int snchSign, uint32_t primIdx, Vec<DIM> x, float r2,
+                           bool flip, float precision, bool silhouetteTests, bool defer = false)
 {
     BvhView bvh{};
     bvh.prims = prims;
     bvh.adjacency = adjacency;
     bvh.snchSign = snchSign;
-    bool deferred = false;
+    int deferred = 0;
     primStarRadius2Fast<DIM>(bvh, primIdx, x, r2, flip, precision, silhouetteTests, defer ? &deferred : nullptr);
-    return deferred ? -1.0f : r2; // defer: -1 = "redo this primitive in the reference's order" (primStarRadius2Redo), r2 unchanged
+    // x: the radius; y (defer only): 0 done, 1 redo the whole primitive (primStarRadius2Redo), 2 redo its reflectance part
+    // (primStarRobinRedo) — as a float so that the pair travels in registers
+    return make_float2(r2, (float)deferred);
 }
 
 // BoundingCone::overlap (fcpw/core/bounding_volumes.h:275-321): can a normal inside the cone be
@@ -1534,7 +1585,7 @@ ZB_DEV void starRadiusDfs(const BvhView& bvh, const Vec<DIM>& x, float& r2, bool
             uint32_t first = e.y & 0x0fffffffu, count = (e.y >> 28) & 7u;
             for (uint32_t i = 0; i < count; i++) {
                 ZB_COUNT_PRIM
-                if (FAST) r2 = primStarRadius2Call<DIM>(bvh.prims, bvh.adjacency, bvh.snchSign, first + i, x, r2, flip, precision, silhouetteTests);
+                if (FAST) r2 = primStarRadius2Call<DIM>(bvh.prims, bvh.adjacency, bvh.snchSign, first + i, x, r2, flip, precision, silhouetteTests).x;
                 else primStarRadius2<DIM>(bvh, first + i, x, r2, flip, precision, silhouetteTests);
             }
             continue;
