@@ -1,0 +1,157 @@
+"""The reference's Python surface (python/zombie/__init__.py; the call sequence of demo/demo.py:124-540) on top of the C ABI:
+zombie_b200/zombie.py. CPU: the host-side utilities and the data-described PDE. GPU: the demo's Walk on Stars flow end to end
+— dense-grid PDE data, handlers, populate_*, compute_dist_to_boundary, SamplePoint list, WalkOnStars.solve — against the exact
+solution and against the same solve through the ctypes binding."""
+import numpy as np
+import pytest
+
+from tests import cases
+from zombie_b200 import abi, procedural as P, zombie
+
+
+def star_mesh(n=1024):
+    pos, seg = P.star_polygon(n)
+    positions, indices = zombie.FloatNList(dim=2), zombie.IntNList(dim=2)
+    positions.extend(list(pos)); indices.extend(list(seg))
+    return positions, indices
+
+
+def test_factories_validate_dim_and_channels():
+    with pytest.raises(ValueError):
+        zombie.Core.PDE(dim=4)
+    with pytest.raises(ValueError):
+        zombie.Core.PDE(dim=2, channels=4)
+    with pytest.raises(ValueError):
+        zombie.Samplers.create_uniform_triangle_boundary_sampler([], [], dim=2)
+    assert isinstance(zombie.FloatNList(dim=3), zombie.Float3List) and isinstance(zombie.IntNList(dim=2), zombie.Int2List)
+
+
+def test_mesh_utilities_follow_the_reference(tmp_path):
+    obj = tmp_path / "square.obj"
+    obj.write_text("v 0 0\nv 2 0\nv 2 2\nv 0 2\nl 1 2 3 4 1\n")
+    positions, indices = zombie.FloatNList(dim=2), zombie.IntNList(dim=2)
+    zombie.Utils.load_boundary_mesh(str(obj), positions, indices, dim=2)
+    assert len(positions) == 4 and [list(i) for i in indices] == [[0, 1], [1, 2], [2, 3], [3, 0]]
+    zombie.Utils.normalize(positions, dim=2)       # centre of mass to the origin, farthest vertex at distance 1
+    p = zombie.convert_list_to_numpy_array(positions)
+    assert np.allclose(p.mean(axis=0), 0.0, atol=1e-7) and np.isclose(np.linalg.norm(p, axis=1).max(), 1.0)
+    zombie.Utils.flip_orientation(indices, dim=2)
+    assert [list(i) for i in indices] == [[1, 0], [2, 1], [3, 2], [0, 3]]
+    lo, hi = zombie.Utils.compute_bounding_box(positions, True, 1.5, dim=2)
+    assert np.allclose(hi - lo, 1.5*np.sqrt(2.0), rtol=1e-6) and np.allclose(0.5*(lo + hi), 0.0, atol=1e-6)
+    # partition by the predicate at primitive midpoints; vertices re-indexed in order of first use
+    ap, ai, rp, ri = (zombie.FloatNList(dim=2), zombie.IntNList(dim=2), zombie.FloatNList(dim=2), zombie.IntNList(dim=2))
+    zombie.Utils.partition_boundary_mesh(lambda m: m[1] > 0.1, positions, indices, ap, ai, rp, ri, dim=2)
+    assert len(ai) + len(ri) == 4 and len(ri) == 1 and [list(i) for i in ri] == [[0, 1]]
+    assert np.allclose(np.asarray(rp)[np.asarray(ri)[0]], p[np.asarray(indices)[2]])
+    assert abs(zombie.Utils.compute_signed_volume(positions, indices, dim=2)) == pytest.approx(2.0, rel=1e-5)   # the unit-radius square
+
+
+def test_dense_grid_callbacks_are_the_references_dense_grid():
+    """DenseGrid (zombie/utils/dense_grid.h:333-356): cell-centred samples, last axis fastest, nearest cell by default,
+    multilinear with edge clamping when enabled"""
+    nx, ny = 4, 3
+    data = np.arange(nx*ny, dtype=np.float32)              # value = i*ny + j
+    lo, hi = np.array([0.0, 0.0]), np.array([4.0, 3.0])
+    near = zombie.Utils.get_dense_grid_source_callback(data, [nx, ny], lo, hi, dim=2)
+    for x, want in (((0.1, 0.1), 0), ((3.9, 2.9), 11), ((1.5, 0.2), 3), ((2.2, 1.7), 7), ((-1.0, 5.0), 2)):
+        assert near(np.array(x)) == want
+    lin = zombie.Utils.get_dense_grid_source_callback(data, [nx, ny], lo, hi, True, dim=2)
+    assert lin(np.array([1.0, 1.0])) == pytest.approx(0.5*(0 + 3) + 0.5, abs=1e-6)   # halfway between cells (0,*) and (1,*), and (.,0),(.,1)
+    assert lin(np.array([0.2, 0.2])) == pytest.approx(0.0)                          # within half a cell of the border: clamped
+    # the descriptor carries the same samples with x fastest and the lattice of the cell centres
+    pde = zombie.Core.PDE(dim=2)
+    pde.source = near
+    pde.dirichlet = zombie.Core.get_constant_dirichlet_callback(2.5, dim=2)
+    pde.robin_coeff = zombie.Core.get_constant_robin_coefficient_callback(0.0, dim=2)
+    d = pde.descriptor()
+    assert d.mode == abi.PDE_CONSTANT and d.dirichletValue == 2.5 and d.sourceGrid.data
+    assert list(d.sourceGrid.shape) == [nx, ny, 1] and d.sourceGrid.interp == abi.GRID_NEAREST
+    assert np.allclose(list(d.sourceGrid.origin)[:2], [0.5, 0.5]) and np.allclose(list(d.sourceGrid.invCell)[:2], [1.0, 1.0])
+    assert np.array_equal(d.host_grids["sourceGrid"].values[0], data.reshape(nx, ny).T)
+    pde.robin = lambda x, n, aligned: 0.0
+    with pytest.raises(TypeError, match="cannot call back into Python"):
+        pde.descriptor()
+
+
+def test_walk_settings_constructors():
+    s = zombie.Solvers.WalkSettings(1e-3, 2e-3, 512, True)
+    assert s.maxWalkLength == 512 and s.solveDoubleSided == 1 and s.stepsBeforeUsingMaximalSpheres == 512
+    s = zombie.Solvers.WalkSettings(1e-3, 1e-3, 1e-3, 0.99, np.inf, 1024, 0, 1024, False, True, True, False, False, False, False, False)
+    assert s.russianRouletteThreshold == np.float32(0.99) and s.splittingThreshold == np.float32(abi.FLT_MAX)
+
+
+@pytest.mark.gpu
+def test_demo_flow_walk_on_stars_2d(ctx):
+    """demo/demo.py's Walk on Stars run on the star polygon: Laplace problem u = Re (x+iy)^3 with Dirichlet data on y <= 0 and
+    its exact Neumann data on y > 0, both handed over as 512^2 dense grids."""
+    dim = 2
+    positions, indices = star_mesh(2048)
+    bbox = zombie.Utils.compute_bounding_box(positions, True, 1.0, dim=dim)
+    n = 512
+    xs = bbox[0][0] + (np.arange(n) + 0.5)*(bbox[1][0] - bbox[0][0])/n
+    ys = bbox[0][1] + (np.arange(n) + 0.5)*(bbox[1][1] - bbox[0][1])/n
+    X, Y = np.meshgrid(xs, ys, indexing="ij")                     # [nx, ny]: last axis fastest, as DenseGrid stores it
+    u = X**3 - 3.0*X*Y**2
+    # Neumann data du/dn on the star r = 1 + 0.25 sin 5 theta, extended along rays so that the grid lookup near the curve is exact enough
+    th = np.arctan2(Y, X)
+    r = 1.0 + 0.25*np.sin(5.0*th)
+    dr = 1.25*np.cos(5.0*th)
+    bx, by = r*np.cos(th), r*np.sin(th)
+    nrm = np.stack([r*np.cos(th) + dr*np.sin(th), r*np.sin(th) - dr*np.cos(th)], -1)
+    nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
+    dudn = (3.0*bx**2 - 3.0*by**2)*nrm[..., 0] + (-6.0*bx*by)*nrm[..., 1]
+
+    pde = zombie.Core.PDE(dim=dim, channels=1)
+    pde.source = zombie.Core.get_constant_source_callback(0.0, dim=dim)
+    pde.dirichlet = zombie.Utils.get_dense_grid_dirichlet_callback(u.astype(np.float32).ravel(), [n, n], bbox[0], bbox[1], True, dim=dim)
+    pde.robin = zombie.Utils.get_dense_grid_robin_callback(dudn.astype(np.float32).ravel(), [n, n], bbox[0], bbox[1], True, dim=dim)
+    pde.robin_coeff = zombie.Core.get_constant_robin_coefficient_callback(0.0, dim=dim)
+    pde.has_reflecting_boundary_conditions = lambda x: x[1] > 0.0
+    pde.absorption_coeff = 0.0
+    pde.is_source_constant = True
+    pde.are_robin_conditions_pure_neumann = True
+    pde.are_robin_coeffs_nonnegative = True
+
+    ap, ai, rp, ri = (zombie.FloatNList(dim=dim), zombie.IntNList(dim=dim), zombie.FloatNList(dim=dim), zombie.IntNList(dim=dim))
+    zombie.Utils.partition_boundary_mesh(pde.has_reflecting_boundary_conditions, positions, indices, ap, ai, rp, ri, dim=dim)
+    queries = zombie.Core.GeometricQueries(True, bbox[0], bbox[1], dim=dim)
+    dirichlet = zombie.Utils.FcpwDirichletBoundaryHandler(dim=dim)
+    dirichlet.build_acceleration_structure(ap, ai)
+    zombie.Utils.populate_geometric_queries_for_dirichlet_boundary(dirichlet, queries, dim=dim)
+    neumann = zombie.Utils.FcpwNeumannBoundaryHandler(dim=dim)
+    neumann.build_acceleration_structure(rp, ri, zombie.Utils.get_ignore_candidate_silhouette_callback(False))
+    zombie.Utils.populate_geometric_queries_for_neumann_boundary(neumann, zombie.Utils.get_branch_traversal_weight_callback(), queries, dim=dim)
+
+    pts = cases.query_points(600, dim, 0.6, seed=5)
+    solve_locations = zombie.FloatNList(dim=dim)
+    solve_locations.extend(list(pts) + [np.array([3.0, 3.0], np.float32)])           # one location outside the domain
+    da, dr_ = zombie.FloatList(), zombie.FloatList()
+    zombie.Utils.compute_dist_to_boundary(queries, solve_locations, da, dr_, dim=dim)
+    sample_points = []
+    for i, x in enumerate(solve_locations):
+        inside = queries.inside_domain(x)
+        q = zombie.Solvers.EstimationQuantity.Solution if inside else zombie.Solvers.EstimationQuantity.Skip
+        sample_points.append(zombie.Solvers.SamplePoint(x, np.zeros(dim), zombie.Solvers.SampleType.InDomain, q, 1.0, da[i], dr_[i], dim=dim))
+    assert not queries.inside_domain(solve_locations[-1]) and queries.inside_domain(solve_locations[0])
+    sample_pts = zombie.Solvers.SamplePointList(sample_points, dim=dim, channels=1)
+    settings = zombie.Solvers.WalkSettings(1e-3, 1e-3, 1e-3, 0.0, np.inf, 1024, 0, 1024, False, True, True, False, False, False, False, False)
+    n_walks = zombie.IntList([256]*len(sample_pts))
+    stats = zombie.Solvers.create_sample_statistics_list(len(sample_pts), dim=dim, channels=1)
+    solver = zombie.Solvers.WalkOnStars(queries, dim=dim, channels=1)
+    bar = zombie.Utils.ProgressBar(len(sample_pts))
+    solver.solve(pde, settings, n_walks, sample_pts, stats, False, zombie.Utils.get_report_progress_callback(bar))
+    bar.finish()
+
+    est = np.array([stats[i].get_estimated_solution() for i in range(len(pts))])
+    exact = pts[:, 0]**3 - 3.0*pts[:, 0]*pts[:, 1]**2
+    se = np.sqrt(np.array([stats[i].get_estimated_solution_variance() for i in range(len(pts))])/256.0)
+    assert np.sqrt(np.mean((est - exact)**2)) < 0.06
+    assert np.mean(np.abs(est - exact) < 3.0*se + 0.01) > 0.97     # 0.01: the 512^2 lookup of the boundary data
+    assert stats[len(pts)].get_solution_estimate_count() == 0 and stats[0].get_solution_estimate_count() == 256    # Skip is honoured
+    assert stats[0].get_mean_walk_length() > 1.0 and solver.last_walk_steps > 0
+    # a second solve refines progressively (the points' generators moved on)
+    solver.solve(pde, settings, n_walks, sample_pts, stats)
+    assert stats[0].get_solution_estimate_count() == 512
+    est2 = np.array([stats[i].get_estimated_solution() for i in range(len(pts))])
+    assert np.sqrt(np.mean((est2 - exact)**2)) < np.sqrt(np.mean((est - exact)**2)) + 0.005
