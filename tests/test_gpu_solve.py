@@ -228,6 +228,10 @@ def test_2d_demo_like_config(ctx):
         se = np.sqrt(st.solution_variance()/np.maximum(1, st.nSolutionEstimates))
         z = (st.solutionMean - w.exact(w.points))/np.maximum(se, 1e-4)
         assert np.mean(np.abs(z) < 4.0) > 0.96, (w.name, np.mean(np.abs(z) < 4.0), z.mean())
+        # a closed-form family with a z dependence cannot describe a 2D problem (its Laplacian would count the z term): refused
+        bad = abi.PdeDesc.manufactured(abi.SOL_QUADRATIC, [1.0, -0.5, 0.25, 0.3])
+        with pytest.raises(native.ZombieError, match="z dependence"):
+            sc.solve(w.estimator, bad, w.settings, pts, st)
         sc.close()
 
 

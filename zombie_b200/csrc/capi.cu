@@ -1200,6 +1200,10 @@ int zb_solve_dev(zb_scene *scene, int estimator, const zb_pde_desc *pde, const z
         !pts->distToReflectingBoundary || !pts->nWalks || !pts->rngState || !pts->rngInc || !pts->firstSphereRadius)
         return fail(ZB_ERR_INVALID_ARGUMENT, "zb_solve_dev: a required sample-point array is NULL");
     if (pde->mode != ZB_PDE_MANUFACTURED && pde->mode != ZB_PDE_CONSTANT) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_solve_dev: unknown pde mode");
+    // the closed-form families take their Laplacian over three coordinates: a 2D solve must not carry a z term
+    if (scene->dim == 2 && pde->mode == ZB_PDE_MANUFACTURED &&
+        ((pde->family == ZB_SOL_QUADRATIC && pde->params[2] != 0.0f) || pde->family == ZB_SOL_TRIG_3D))
+        return fail(ZB_ERR_INVALID_ARGUMENT, "zb_solve_dev: this solution family has a z dependence and cannot describe a 2D problem");
     if (pde->kelvin && pde->absorptionCoeff > 0.0f) // kelvin_transform.h:285-288
         return fail(ZB_ERR_UNSUPPORTED, "zb_solve_dev: the Kelvin transform does not support non-zero absorption coefficients");
     if (settings->printLogs) return fail(ZB_ERR_UNSUPPORTED, "zb_solve_dev: printLogs is not supported on the device");
