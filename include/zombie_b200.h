@@ -241,7 +241,11 @@ int zb_star_radius(zb_scene *scene, int n, const float *x, const float *minRadiu
  * are in/out. walkSteps (optional) receives the number of walk steps taken by this call. ------ */
 int zb_solve(zb_scene *scene, int estimator, const zb_pde_desc *pde, const zb_walk_settings *settings,
              const zb_sample_points *pts, zb_statistics *stats, int64_t *walkSteps);
-/* same, all arrays already resident on the context's device; asynchronous on the context stream.
+/* same, all arrays already resident on the context's device; no host<->device copy of point or statistics data.
+ * The call enqueues its work on the context's stream in batches of walk rounds and reads one 4-byte live-walk
+ * counter per batch back (with one batch of lag, so the device never idles) to know when the walks have ended: it
+ * returns when the last batch has been enqueued, NOT when it has run — results are ordered behind it on the
+ * context's stream like those of any asynchronous call, but the call itself lasts about as long as the walks.
  * walkSteps_dev points to one int64 on the device. */
 int zb_solve_dev(zb_scene *scene, int estimator, const zb_pde_desc *pde, const zb_walk_settings *settings,
                  const zb_sample_points *pts_dev, zb_statistics *stats_dev, int64_t *walkSteps_dev);

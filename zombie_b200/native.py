@@ -377,7 +377,7 @@ class Scene:
 
     def solve_dev(self, estimator, pde, settings, pts_struct, stats_struct, steps_dev_ptr=None):
         """Same with every array already resident on the device (abi.SamplePoints / abi.Statistics of
-        device pointers); asynchronous on the context's stream."""
+        device pointers); results are ordered on the context's stream (the call enqueues walk rounds until the walks have ended)."""
         pde = device_pde(self.ctx, pde)
         _check(lib().zb_solve_dev(self._h, estimator, C.byref(pde), C.byref(settings), C.byref(pts_struct),
                                   C.byref(stats_struct), C.c_void_p(steps_dev_ptr)), "zb_solve_dev")
