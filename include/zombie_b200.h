@@ -194,6 +194,34 @@ void zb_grid_destroy(zb_grid *grid);
 /* bytes of device memory held by the scene's acceleration structures, and node counts */
 int zb_scene_stats(const zb_scene *scene, int boundary, int64_t *bytes, int32_t *nNodes, int32_t *nLeaves, int32_t *maxDepth);
 
+/* ---- building the hierarchy on the device, moving geometry -----------------------------------------------------
+ * Which builder zb_scene_create uses for scenes created through this context afterwards. HOST_SAH (default): binned
+ * SAH on the host, as the reference builds its hierarchies (fcpw/aggregates/bvh.inl:143-234) — the best trees, 0.5-1 s
+ * per million triangles. DEVICE: Morton order + level-synchronous 8-ary cuts on the GPU (zombie_b200/csrc/bvh_build.cuh),
+ * including the adjacency tables, normal cones and Robin-coefficient ranges of reflecting boundaries
+ * (fcpw_geometric_queries.h:728-795, 892-973; reflectance_boundary_bvh/bvh.h:77-186) — milliseconds, somewhat slower
+ * traversals. Both produce the same layout and the same query results (per-primitive records are bit-identical; the
+ * quantised boxes and cones of either tree are conservative). */
+enum zb_bvh_builder { ZB_BVH_BUILDER_HOST_SAH = 0, ZB_BVH_BUILDER_DEVICE = 1 };
+int zb_context_set_bvh_builder(zb_context *ctx, int builder);
+/* Moving geometry: new positions for ALL vertices of one boundary (same vertex count and connectivity). Replaces
+ * fcpw Scene::updateObjectVertex + Scene::refit (fcpw/fcpw.h:76-107, aggregates/bvh.inl:549-600) and ReflectanceBvh::refit
+ * (reflectance_boundary_bvh/bvh.h:271-312): the hierarchy — boxes, adjacency normals and silhouette marks, cones — is
+ * rebuilt on the device from the mesh kept there (a rebuild costs about what a refit pass would and keeps tree quality
+ * when the motion is large). Current Robin coefficients are kept. The _dev form reads positions from device memory. */
+int zb_scene_update_vertices(zb_scene *scene, int boundary, const float *positions, int nVertices);
+int zb_scene_update_vertices_dev(zb_scene *scene, int boundary, const float *positions, int nVertices);
+/* duration of the last build of this boundary's hierarchy (HOST_SAH: host build + upload; DEVICE: the kernels, by
+ * CUDA events) and the builder that produced it */
+int zb_scene_build_profile(const zb_scene *scene, int boundary, float *ms, int32_t *builder);
+/* Test hooks: soundness check of the hierarchy as it sits on the device (downloaded and checked like zb_host_bvh_check:
+ * every primitive once, inside the quantised box of every enclosing child slot, internal children contiguous, leaves of
+ * 1..4 primitives, breadth-first level table) against the caller's mesh; and the leaf-order per-primitive records
+ * (primIndex: n; prims: n*12 floats in 3D, n*4 in 2D; adjacency: n*12 floats, reflecting boundaries only; NULL skips). */
+int zb_scene_validate(zb_scene *scene, int boundary, const float *positions, int nVertices, const int32_t *indices, int nPrimitives,
+                      int64_t *violations);
+int zb_scene_download_records(zb_scene *scene, int boundary, int32_t *primIndex, float *prims, float *adjacency);
+
 /* Host-only self-check of the acceleration-structure builder (no device needed; used by the CPU tests):
  * builds the wide quantised hierarchy for the mesh exactly as zb_scene_create does and verifies that every
  * primitive is referenced once and lies inside the quantised box of every enclosing child slot.

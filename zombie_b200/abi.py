@@ -9,6 +9,7 @@ ZB_OK = 0
 IN_DOMAIN, ON_ABSORBING_BOUNDARY, ON_REFLECTING_BOUNDARY = 0, 1, 2
 SOLUTION, SOLUTION_AND_GRADIENT, SKIP = 0, 1, 2
 REFLECTING_NONE, REFLECTING_NEUMANN, REFLECTING_ROBIN = 0, 1, 2
+BVH_BUILDER_HOST_SAH, BVH_BUILDER_DEVICE = 0, 1   # zb_bvh_builder
 WALK_ON_SPHERES, WALK_ON_STARS = 0, 1
 ABSORBING, REFLECTING = 0, 1
 PDE_MANUFACTURED, PDE_CONSTANT = 0, 1

@@ -16,6 +16,7 @@
 #include "wave.cuh"
 #include "rws.cuh"
 #include "wide_bvh.h"
+#include "scene_storage.h"
 
 using namespace zb;
 
@@ -24,16 +25,6 @@ namespace {
 // so that solution-only runs do not allocate gradient records; zb_solve_dev alone assumes they may
 thread_local bool g_gradientHint = true;
 } // namespace
-
-struct DeviceBvhStorage {
-    HostBvh host;
-    DeviceBuffer nodes, prims, primIndex, cones, adjacency;
-    DeviceBuffer coeffScratch;           // Robin coefficient refit: the caller's per-primitive values and a (min, max) per node
-    std::vector<int> levelStart;         // nodes are stored breadth first: level l is [levelStart[l], levelStart[l + 1])
-    BvhView view{};
-    bool present = false;
-    size_t bytes() const { return nodes.capacity + prims.capacity + primIndex.capacity + cones.capacity + adjacency.capacity; }
-};
 
 struct zb_scene {
     zb_context *ctx = nullptr;
@@ -73,6 +64,9 @@ int uploadBvh(zb_context *ctx, DeviceBvhStorage& s, int snchSign)
     s.view.nPrims = h.nPrims;
     s.view.snchSign = snchSign;
     s.present = true;
+    s.nNodes = (int)h.nodes.size();
+    s.builder = ZB_BVH_BUILDER_HOST_SAH;
+    s.levelStart.clear();
     ZB_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZB_OK;
 }
@@ -748,6 +742,75 @@ int zb_context_last_solve_profile(zb_context *ctx, float *prepareMs, float *walk
 int zb_context_device(const zb_context *ctx) { return ctx ? ctx->device : -1; }
 int zb_context_sm_count(const zb_context *ctx) { return ctx ? ctx->smCount : 0; }
 
+namespace {
+
+// FCPW's SilhouetteEdge test (silhouette_edges.inl:83-111, Neumann handler, 3D) measures the view direction
+// with the opposite sign of Zombie's ReflectanceTriangle (reflectance_boundary_bvh/geometry.h:196-206); the 2D
+// SilhouetteVertex and ReflectanceLineSegment tests agree (silhouette_vertices.inl:59-85, geometry.h:108-126)
+int snchSignOf(const zb_scene *scene, int boundary)
+{
+    return boundary == ZB_REFLECTING && scene->reflectingKind == ZB_REFLECTING_NEUMANN && scene->dim == 3 ? -1 : 1;
+}
+
+// Builds (or rebuilds) one boundary's hierarchy with the chosen builder. positions / indices / coefficients are HOST
+// arrays; indices and coefficients may be NULL on a rebuild (the copies kept on the device are used).
+int buildBoundary(zb_scene *scene, int boundary, int builder, const float *positions, int nVert, const int32_t *indices, int nPrim,
+                  const float *minCoeff, const float *maxCoeff)
+{
+    zb_context *ctx = scene->ctx;
+    DeviceBvhStorage& s = scene->boundary[boundary];
+    const int dim = scene->dim;
+    const char *which = boundary == ZB_ABSORBING ? "absorbing mesh: " : "reflecting mesh: ";
+    s.reflecting = boundary == ZB_REFLECTING;
+    s.robin = s.reflecting && scene->reflectingKind == ZB_REFLECTING_ROBIN;
+    if (nVert <= 0 || nPrim <= 0) return fail(ZB_ERR_INVALID_ARGUMENT, std::string("zb_scene_create: ") + which + "empty mesh");
+    // the mesh stays on the device: vertices that move later are rebuilt there (zb_scene_update_vertices)
+    s.nVert = nVert;
+    ZB_CUDA(s.meshPos.reserve((size_t)nVert*dim*sizeof(float)));
+    ZB_CUDA(cudaMemcpyAsync(s.meshPos.ptr, positions, (size_t)nVert*dim*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (indices) {
+        ZB_CUDA(s.meshIdx.reserve((size_t)nPrim*dim*sizeof(int32_t)));
+        ZB_CUDA(cudaMemcpyAsync(s.meshIdx.ptr, indices, (size_t)nPrim*dim*sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (s.robin && minCoeff && maxCoeff) {
+        ZB_CUDA(s.coefMin.reserve((size_t)nPrim*sizeof(float)));
+        ZB_CUDA(s.coefMax.reserve((size_t)nPrim*sizeof(float)));
+        ZB_CUDA(cudaMemcpyAsync(s.coefMin.ptr, minCoeff, (size_t)nPrim*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        ZB_CUDA(cudaMemcpyAsync(s.coefMax.ptr, maxCoeff, (size_t)nPrim*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (builder == ZB_BVH_BUILDER_DEVICE) {
+        int rc = buildBvhOnDevice(ctx, s, dim, nPrim, scene->solveDoubleSided != 0, scene->silhouettePrecision, snchSignOf(scene, boundary));
+        if (rc != ZB_OK) lastErrorRef() = std::string("zb_scene_create: ") + which + lastErrorRef();
+        return rc;
+    }
+    if (!indices) return fail(ZB_ERR_INVALID_ARGUMENT, "host BVH builder needs the index array");
+    cudaEvent_t ev0, ev1;
+    ZB_CUDA(cudaEventCreate(&ev0));
+    ZB_CUDA(cudaEventCreate(&ev1));
+    ZB_CUDA(cudaEventRecord(ev0, ctx->stream));
+    ReflectingOptions opt;
+    if (s.reflecting) {
+        opt.enabled = true;
+        opt.solveDoubleSided = scene->solveDoubleSided != 0;
+        opt.silhouettePrecision = scene->silhouettePrecision;
+        opt.minCoeff = s.robin ? minCoeff : nullptr;
+        opt.maxCoeff = s.robin ? maxCoeff : nullptr;
+    }
+    const char *err = nullptr;
+    if (!buildWideBvh(dim, positions, nVert, indices, nPrim, opt, s.host, &err))
+        return fail(ZB_ERR_INVALID_ARGUMENT, std::string("zb_scene_create: ") + which + (err ? err : "?"));
+    int rc = uploadBvh(ctx, s, snchSignOf(scene, boundary));
+    if (rc != ZB_OK) return rc;
+    ZB_CUDA(cudaEventRecord(ev1, ctx->stream));
+    ZB_CUDA(cudaEventSynchronize(ev1));
+    ZB_CUDA(cudaEventElapsedTime(&s.buildMs, ev0, ev1)); // the stream waits for the host build, so this spans build + upload
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    return ZB_OK;
+}
+
+} // namespace
+
 int zb_scene_create(zb_context *ctx, int dim,
                     const float *absorbingPositions, int nAbsorbingVertices,
                     const int32_t *absorbingIndices, int nAbsorbingPrimitives,
@@ -781,33 +844,15 @@ int zb_scene_create(zb_context *ctx, int dim,
         scene->domainMax[k] = domainMax && k < dim ? domainMax[k] : kMaxFloat;
     }
 
-    const char *err = nullptr;
     if (nAbsorbingPrimitives > 0) {
-        ReflectingOptions none;
-        if (!buildWideBvh(dim, absorbingPositions, nAbsorbingVertices, absorbingIndices, nAbsorbingPrimitives,
-                          none, scene->boundary[ZB_ABSORBING].host, &err)) {
-            delete scene;
-            return fail(ZB_ERR_INVALID_ARGUMENT, std::string("zb_scene_create: absorbing mesh: ") + (err ? err : "?"));
-        }
-        int rc = uploadBvh(ctx, scene->boundary[ZB_ABSORBING], 1);
+        int rc = buildBoundary(scene, ZB_ABSORBING, ctx->bvhBuilder, absorbingPositions, nAbsorbingVertices, absorbingIndices,
+                               nAbsorbingPrimitives, nullptr, nullptr);
         if (rc != ZB_OK) { delete scene; return rc; }
     }
     if (nReflectingPrimitives > 0) {
-        ReflectingOptions opt;
-        opt.enabled = true;
-        opt.solveDoubleSided = solveDoubleSided != 0;
-        opt.silhouettePrecision = silhouettePrecision;
-        opt.minCoeff = reflectingKind == ZB_REFLECTING_ROBIN ? minRobinCoeff : nullptr;
-        opt.maxCoeff = reflectingKind == ZB_REFLECTING_ROBIN ? maxRobinCoeff : nullptr;
-        if (!buildWideBvh(dim, reflectingPositions, nReflectingVertices, reflectingIndices, nReflectingPrimitives,
-                          opt, scene->boundary[ZB_REFLECTING].host, &err)) {
-            delete scene;
-            return fail(ZB_ERR_INVALID_ARGUMENT, std::string("zb_scene_create: reflecting mesh: ") + (err ? err : "?"));
-        }
-        // FCPW's SilhouetteEdge test (silhouette_edges.inl:83-111, Neumann handler, 3D) measures the view direction
-        // with the opposite sign of Zombie's ReflectanceTriangle (reflectance_boundary_bvh/geometry.h:196-206); the 2D
-        // SilhouetteVertex and ReflectanceLineSegment tests agree (silhouette_vertices.inl:59-85, geometry.h:108-126)
-        int rc = uploadBvh(ctx, scene->boundary[ZB_REFLECTING], reflectingKind == ZB_REFLECTING_NEUMANN && dim == 3 ? -1 : 1);
+        const bool robin = reflectingKind == ZB_REFLECTING_ROBIN;
+        int rc = buildBoundary(scene, ZB_REFLECTING, ctx->bvhBuilder, reflectingPositions, nReflectingVertices, reflectingIndices,
+                               nReflectingPrimitives, robin ? minRobinCoeff : nullptr, robin ? maxRobinCoeff : nullptr);
         if (rc != ZB_OK) { delete scene; return rc; }
     }
     *out = scene;
@@ -903,7 +948,7 @@ int refitRobinCoefficients(zb_scene *scene, const float *devMin, const float *de
     if (s.levelStart.empty() && !computeLevels(s.host, s.levelStart))
         return fail(ZB_ERR_UNSUPPORTED, "zb_scene_update_robin_coefficients: node array is not breadth first");
     const int nPrims = s.host.nPrims;
-    const size_t nNodes = s.host.nodes.size();
+    const size_t nNodes = (size_t)s.nNodes;
     float2 *nodeRange = reinterpret_cast<float2 *>(s.coeffScratch.as<char>() + (((size_t)2*nPrims*sizeof(float) + 255) & ~size_t(255)));
     refitPrimCoeffKernel<<<(nPrims + 255)/256, 256, 0, ctx->stream>>>(nPrims, s.host.dim, s.primIndex.as<int>(), devMin, devMax,
                                                                       s.adjacency.as<PrimAdjacency>(), s.prims.as<float>());
@@ -915,13 +960,18 @@ int refitRobinCoefficients(zb_scene *scene, const float *devMin, const float *de
         ZB_CUDA(cudaGetLastError());
     }
     (void)nNodes;
+    // the input-order copies a later rebuild (zb_scene_update_vertices) reads
+    if (s.coefMin.ptr && devMin != s.coefMin.as<float>()) {
+        ZB_CUDA(cudaMemcpyAsync(s.coefMin.ptr, devMin, (size_t)nPrims*sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+        ZB_CUDA(cudaMemcpyAsync(s.coefMax.ptr, devMax, (size_t)nPrims*sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     return ZB_OK;
 }
 
 int reserveCoeffScratch(DeviceBvhStorage& s)
 {
     const size_t primBytes = ((size_t)2*s.host.nPrims*sizeof(float) + 255) & ~size_t(255);
-    ZB_CUDA(s.coeffScratch.reserve(primBytes + s.host.nodes.size()*sizeof(float2) + 256));
+    ZB_CUDA(s.coeffScratch.reserve(primBytes + (size_t)s.nNodes*sizeof(float2) + 256));
     return ZB_OK;
 }
 
@@ -998,9 +1048,110 @@ int zb_scene_stats(const zb_scene *scene, int boundary, int64_t *bytes, int32_t 
     if (!scene || boundary < 0 || boundary > 1) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_scene_stats: invalid argument");
     const DeviceBvhStorage& s = scene->boundary[boundary];
     if (bytes) *bytes = s.present ? (int64_t)s.bytes() : 0;
-    if (nNodes) *nNodes = s.present ? (int32_t)s.host.nodes.size() : 0;
+    if (nNodes) *nNodes = s.present ? (int32_t)s.nNodes : 0;
     if (nLeaves) *nLeaves = s.present ? s.host.nLeaves : 0;
     if (maxDepth) *maxDepth = s.present ? s.host.maxDepth : 0;
+    return ZB_OK;
+}
+
+// ---- on-device hierarchy build, moving geometry ------------------------------------------------------------------
+int zb_context_set_bvh_builder(zb_context *ctx, int builder)
+{
+    if (!ctx || (builder != ZB_BVH_BUILDER_HOST_SAH && builder != ZB_BVH_BUILDER_DEVICE))
+        return fail(ZB_ERR_INVALID_ARGUMENT, "zb_context_set_bvh_builder: invalid argument");
+    ctx->bvhBuilder = builder;
+    return ZB_OK;
+}
+
+int zb_scene_build_profile(const zb_scene *scene, int boundary, float *ms, int32_t *builder)
+{
+    if (!scene || boundary < 0 || boundary > 1) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_scene_build_profile: invalid argument");
+    const DeviceBvhStorage& s = scene->boundary[boundary];
+    if (ms) *ms = s.present ? s.buildMs : 0.0f;
+    if (builder) *builder = s.builder;
+    return ZB_OK;
+}
+
+namespace {
+int rebuildMoved(zb_scene *scene, int boundary)
+{
+    DeviceBvhStorage& s = scene->boundary[boundary];
+    int rc = buildBvhOnDevice(scene->ctx, s, scene->dim, s.host.nPrims, scene->solveDoubleSided != 0, scene->silhouettePrecision,
+                              snchSignOf(scene, boundary));
+    if (rc != ZB_OK) lastErrorRef() = "zb_scene_update_vertices: " + lastErrorRef();
+    return rc;
+}
+} // namespace
+
+int zb_scene_update_vertices_dev(zb_scene *scene, int boundary, const float *positions, int nVertices)
+{
+    if (!scene || boundary < 0 || boundary > 1 || !positions) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_scene_update_vertices_dev: invalid argument");
+    DeviceBvhStorage& s = scene->boundary[boundary];
+    if (!s.present) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_scene_update_vertices_dev: the scene has no such boundary");
+    if (nVertices != s.nVert) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_scene_update_vertices_dev: vertex count differs from the scene's");
+    ZB_CUDA(cudaSetDevice(scene->ctx->device));
+    ZB_CUDA(cudaMemcpyAsync(s.meshPos.ptr, positions, (size_t)nVertices*scene->dim*sizeof(float), cudaMemcpyDeviceToDevice, scene->ctx->stream));
+    return rebuildMoved(scene, boundary);
+}
+
+int zb_scene_update_vertices(zb_scene *scene, int boundary, const float *positions, int nVertices)
+{
+    if (!scene || boundary < 0 || boundary > 1 || !positions) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_scene_update_vertices: invalid argument");
+    DeviceBvhStorage& s = scene->boundary[boundary];
+    if (!s.present) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_scene_update_vertices: the scene has no such boundary");
+    if (nVertices != s.nVert) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_scene_update_vertices: vertex count differs from the scene's");
+    ZB_CUDA(cudaSetDevice(scene->ctx->device));
+    ZB_CUDA(cudaMemcpyAsync(s.meshPos.ptr, positions, (size_t)nVertices*scene->dim*sizeof(float), cudaMemcpyHostToDevice, scene->ctx->stream));
+    return rebuildMoved(scene, boundary);
+}
+
+int zb_scene_validate(zb_scene *scene, int boundary, const float *positions, int nVertices, const int32_t *indices, int nPrimitives,
+                      int64_t *violations)
+{
+    if (!scene || boundary < 0 || boundary > 1 || !positions || !indices || !violations)
+        return fail(ZB_ERR_INVALID_ARGUMENT, "zb_scene_validate: invalid argument");
+    DeviceBvhStorage& s = scene->boundary[boundary];
+    if (!s.present || nPrimitives != s.host.nPrims || nVertices != s.nVert)
+        return fail(ZB_ERR_INVALID_ARGUMENT, "zb_scene_validate: mesh does not match the scene's boundary");
+    ZB_CUDA(cudaSetDevice(scene->ctx->device));
+    HostBvh h;
+    h.dim = scene->dim;
+    h.nPrims = s.host.nPrims;
+    h.nodes.resize((size_t)s.nNodes);
+    h.prims.resize((size_t)(scene->dim == 3 ? 12 : 4)*h.nPrims);
+    h.primIndex.resize((size_t)h.nPrims);
+    cudaStream_t st = scene->ctx->stream;
+    ZB_CUDA(cudaMemcpyAsync(h.nodes.data(), s.nodes.ptr, h.nodes.size()*sizeof(WideNode), cudaMemcpyDeviceToHost, st));
+    ZB_CUDA(cudaMemcpyAsync(h.prims.data(), s.prims.ptr, h.prims.size()*sizeof(float), cudaMemcpyDeviceToHost, st));
+    ZB_CUDA(cudaMemcpyAsync(h.primIndex.data(), s.primIndex.ptr, h.primIndex.size()*sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    ZB_CUDA(cudaStreamSynchronize(st));
+    long long bad = 0;
+    for (int32_t p : h.primIndex) if (p < 0 || p >= nPrimitives) bad++;
+    if (bad == 0) bad = validateWideBvh(h, scene->dim, positions, indices);
+    // breadth-first level table: level l + 1 holds exactly the internal children of level l (the coefficient refit relies on it)
+    if (!s.levelStart.empty()) {
+        std::vector<int> levels;
+        if (!computeLevels(h, levels) || levels != s.levelStart) bad++;
+    }
+    *violations = bad;
+    return ZB_OK;
+}
+
+int zb_scene_download_records(zb_scene *scene, int boundary, int32_t *primIndex, float *prims, float *adjacency)
+{
+    if (!scene || boundary < 0 || boundary > 1) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_scene_download_records: invalid argument");
+    DeviceBvhStorage& s = scene->boundary[boundary];
+    if (!s.present) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_scene_download_records: the scene has no such boundary");
+    ZB_CUDA(cudaSetDevice(scene->ctx->device));
+    cudaStream_t st = scene->ctx->stream;
+    const size_t n = (size_t)s.host.nPrims;
+    if (primIndex) ZB_CUDA(cudaMemcpyAsync(primIndex, s.primIndex.ptr, n*sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (prims) ZB_CUDA(cudaMemcpyAsync(prims, s.prims.ptr, n*(scene->dim == 3 ? 12 : 4)*sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (adjacency) {
+        if (!s.view.adjacency) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_scene_download_records: not a reflecting boundary");
+        ZB_CUDA(cudaMemcpyAsync(adjacency, s.adjacency.ptr, n*sizeof(PrimAdjacency), cudaMemcpyDeviceToHost, st));
+    }
+    ZB_CUDA(cudaStreamSynchronize(st));
     return ZB_OK;
 }
 

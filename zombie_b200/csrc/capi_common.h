@@ -63,6 +63,7 @@ struct zb_context {
     cudaStream_t waveStreams[8] = {};      // streams of the slot groups 1.. (group 0 runs on the context's stream)
     int lastRounds = 0;
     int *hostStatus = nullptr; // pinned
+    int bvhBuilder = 0;        // zb_bvh_builder used by zb_scene_create
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; // solve start | walk start | walk end | solve end
     cudaEvent_t evSplat[2] = {nullptr, nullptr};
     bool profiled = false, splatProfiled = false;

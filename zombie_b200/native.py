@@ -20,6 +20,8 @@ _lib = None
 SYMBOLS = ["zb_last_error", "zb_abi_version", "zb_device_count", "zb_context_create", "zb_context_destroy",
            "zb_context_set_stream", "zb_context_synchronize", "zb_context_device", "zb_context_sm_count",
            "zb_context_last_solve_profile",
+           "zb_context_set_bvh_builder", "zb_scene_update_vertices", "zb_scene_update_vertices_dev", "zb_scene_build_profile",
+           "zb_scene_validate", "zb_scene_download_records",
            "zb_host_bvh_check", "zb_scene_create", "zb_scene_destroy", "zb_scene_update_robin_coefficients", "zb_scene_update_robin_coefficients_dev", "zb_scene_stats",
            "zb_closest_point", "zb_intersect_ray", "zb_occluded", "zb_count_ray_hits", "zb_inside_domain", "zb_sample_sphere", "zb_star_radius",
            "zb_solve", "zb_solve_dev", "zb_bvc_splat", "zb_bvc_splat_dev", "zb_context_last_splat_ms", "zb_rws_solve",
@@ -55,6 +57,12 @@ def lib():
         l.zb_scene_update_robin_coefficients.argtypes = [vp, vp, vp]
         l.zb_scene_update_robin_coefficients_dev.argtypes = [vp, vp, vp]
         l.zb_scene_stats.argtypes = [vp, i, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        l.zb_context_set_bvh_builder.argtypes = [vp, i]
+        l.zb_scene_update_vertices.argtypes = [vp, i, vp, i]
+        l.zb_scene_update_vertices_dev.argtypes = [vp, i, vp, i]
+        l.zb_scene_build_profile.argtypes = [vp, i, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+        l.zb_scene_validate.argtypes = [vp, i, vp, i, vp, i, C.POINTER(C.c_int64)]
+        l.zb_scene_download_records.argtypes = [vp, i, vp, vp, vp]
         l.zb_closest_point.argtypes = [vp, i, i] + [vp]*6
         l.zb_intersect_ray.argtypes = [vp, i, i] + [vp]*7
         l.zb_occluded.argtypes = [vp, i, i] + [vp]*3
@@ -175,6 +183,10 @@ class Context:
     def device(self):
         return lib().zb_context_device(self._h)
 
+    def set_bvh_builder(self, builder):
+        """zb_context_set_bvh_builder: abi.BVH_BUILDER_HOST_SAH (default) or abi.BVH_BUILDER_DEVICE for the scenes created afterwards"""
+        _check(lib().zb_context_set_bvh_builder(self._h, int(builder)), "zb_context_set_bvh_builder")
+
     def set_stream(self, cuda_stream):
         _check(lib().zb_context_set_stream(self._h, C.c_void_p(cuda_stream)), "zb_context_set_stream")
 
@@ -238,7 +250,8 @@ class Scene:
 
     def __init__(self, ctx, dim, absorbing=None, reflecting=None, reflecting_kind=abi.REFLECTING_NONE,
                  min_robin=None, max_robin=None, solve_double_sided=False, silhouette_precision=1e-3,
-                 watertight=True, domain_min=None, domain_max=None):
+                 watertight=True, domain_min=None, domain_max=None, builder=None):
+        """builder: abi.BVH_BUILDER_HOST_SAH / abi.BVH_BUILDER_DEVICE for this scene (None: the context's setting)"""
         self.ctx = ctx
         self.dim = dim
         if dim not in (2, 3):
@@ -257,12 +270,18 @@ class Scene:
         mn = _f32(min_robin) if min_robin is not None else np.zeros(len(ri), np.float32)
         mx = _f32(max_robin) if max_robin is not None else np.zeros(len(ri), np.float32)
         self._h = C.c_void_p()
-        _check(lib().zb_scene_create(ctx._h, dim, abi.ptr(ap), len(ap), abi.ptr(ai), len(ai),
-                                     abi.ptr(rp), len(rp), abi.ptr(ri), len(ri),
-                                     reflecting_kind, abi.ptr(mn), abi.ptr(mx),
-                                     int(solve_double_sided), silhouette_precision, int(watertight),
-                                     abi.ptr(self.domain_min), abi.ptr(self.domain_max), C.byref(self._h)),
-               "zb_scene_create")
+        if builder is not None:
+            ctx.set_bvh_builder(builder)
+        try:
+            _check(lib().zb_scene_create(ctx._h, dim, abi.ptr(ap), len(ap), abi.ptr(ai), len(ai),
+                                         abi.ptr(rp), len(rp), abi.ptr(ri), len(ri),
+                                         reflecting_kind, abi.ptr(mn), abi.ptr(mx),
+                                         int(solve_double_sided), silhouette_precision, int(watertight),
+                                         abi.ptr(self.domain_min), abi.ptr(self.domain_max), C.byref(self._h)),
+                   "zb_scene_create")
+        finally:
+            if builder is not None:
+                ctx.set_bvh_builder(abi.BVH_BUILDER_HOST_SAH)
         ctx._scenes.add(self)
 
     def close(self):
@@ -281,6 +300,39 @@ class Scene:
         b, n, l, d = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int32()
         _check(lib().zb_scene_stats(self._h, which, C.byref(b), C.byref(n), C.byref(l), C.byref(d)), "zb_scene_stats")
         return {"bytes": b.value, "nodes": n.value, "leaves": l.value, "max_depth": d.value}
+
+    def update_vertices(self, which, positions):
+        """zb_scene_update_vertices: moving geometry — new positions of all vertices of one boundary; the hierarchy is rebuilt
+        on the device"""
+        pos = _f32(positions)
+        _check(lib().zb_scene_update_vertices(self._h, which, abi.ptr(pos), len(pos)), "zb_scene_update_vertices")
+
+    def update_vertices_dev(self, which, positions_ptr, n_vertices):
+        """the same with a DEVICE pointer to n_vertices*dim floats"""
+        _check(lib().zb_scene_update_vertices_dev(self._h, which, C.c_void_p(positions_ptr), int(n_vertices)),
+               "zb_scene_update_vertices_dev")
+
+    def build_profile(self, which):
+        ms, b = C.c_float(), C.c_int32()
+        _check(lib().zb_scene_build_profile(self._h, which, C.byref(ms), C.byref(b)), "zb_scene_build_profile")
+        return {"ms": ms.value, "builder": b.value}
+
+    def validate(self, which, positions, indices):
+        """zb_scene_validate (test hook): violations of the hierarchy as it sits on the device, against the caller's mesh"""
+        pos = _f32(positions)
+        idx = np.ascontiguousarray(indices, np.int32)
+        v = C.c_int64(-1)
+        _check(lib().zb_scene_validate(self._h, which, abi.ptr(pos), len(pos), abi.ptr(idx), len(idx), C.byref(v)), "zb_scene_validate")
+        return v.value
+
+    def download_records(self, which, n_prims, adjacency=False):
+        """zb_scene_download_records (test hook): leaf-order primitive index, vertex records and adjacency records"""
+        prim = np.zeros(n_prims, np.int32)
+        recs = np.zeros((n_prims, 12 if self.dim == 3 else 4), np.float32)
+        adj = np.zeros((n_prims, 12), np.float32) if adjacency else None
+        _check(lib().zb_scene_download_records(self._h, which, abi.ptr(prim), abi.ptr(recs), abi.ptr(adj) if adjacency else None),
+               "zb_scene_download_records")
+        return prim, recs, adj
 
     def update_robin_coefficients(self, min_robin, max_robin):
         mn, mx = _f32(min_robin), _f32(max_robin)
