@@ -6,6 +6,9 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -68,6 +71,16 @@ int buildBvhOnDevice(zb_context *ctx, DeviceBvhStorage& s, int dim, int nPrim, b
     const int nHalf = refl && dim == 3 ? 3*n : 0;
     Mesh mesh{dim, n, s.nVert, s.meshPos.as<float>(), s.meshIdx.as<int32_t>()};
 
+    // ZB_BUILD_TRACE=1: wall clock of every stage (each closed by a stream synchronisation) on stderr
+    const bool trace = getenv("ZB_BUILD_TRACE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what) {
+        if (!trace) return;
+        cudaStreamSynchronize(st);
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[bvh build] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    };
     cudaEvent_t ev0, ev1;
     ZB_CUDA(cudaEventCreate(&ev0));
     ZB_CUDA(cudaEventCreate(&ev1));
@@ -103,6 +116,7 @@ int buildBvhOnDevice(zb_context *ctx, DeviceBvhStorage& s, int dim, int nPrim, b
         if (!pass) ZB_CUDA(scratch.reserve(c.used + 256));
     }
 
+    mark("scratch");
     // ---- 1. Morton order ----
     const uint32_t boundsInit[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
     ZB_CUDA(cudaMemcpyAsync(k.bounds, boundsInit, sizeof(boundsInit), cudaMemcpyHostToDevice, st));
@@ -116,6 +130,7 @@ int buildBvhOnDevice(zb_context *ctx, DeviceBvhStorage& s, int dim, int nPrim, b
     mortonKernel<<<(n + 255)/256, 256, 0, st>>>(dim, n, k.centroids, k.bounds, k.keys, k.order);
     ZB_CUDA(cudaGetLastError());
     ZB_CUDA(cub::DeviceRadixSort::SortPairs(k.cubTemp, k.cubBytes, k.keys, k.keysAlt, k.order, k.orderAlt, n, 0, dim == 3 ? 63 : 62, st));
+    mark("bounds, keys, sort");
     const uint64_t *keys = k.keysAlt;
     const int *order = k.orderAlt;
 
@@ -145,6 +160,7 @@ int buildBvhOnDevice(zb_context *ctx, DeviceBvhStorage& s, int dim, int nPrim, b
         count = totals[0];
         primCursor += totals[1];
     }
+    mark("topology");
     const int nNodes = first;
     if (primCursor != n) return fail(ZB_ERR_UNSUPPORTED, "device BVH build: primitives lost in the topology pass");
 
@@ -158,6 +174,7 @@ int buildBvhOnDevice(zb_context *ctx, DeviceBvhStorage& s, int dim, int nPrim, b
         ZB_CUDA(s.adjacency.reserve((size_t)n*sizeof(PrimAdjacency)));
     }
 
+    mark("final arrays");
     // ---- 3. adjacency ----
     if (refl) {
         if (dim == 3) {
@@ -180,11 +197,13 @@ int buildBvhOnDevice(zb_context *ctx, DeviceBvhStorage& s, int dim, int nPrim, b
         ZB_CUDA(cudaGetLastError());
     }
 
+    mark("adjacency");
     // ---- 4. leaf-order records ----
     scatterPrimsKernel<<<(n + 255)/256, 256, 0, st>>>(mesh, order, k.leafPos, refl ? k.adjInput : nullptr, s.prims.as<float>(),
                                                      s.primIndex.as<int32_t>(), refl ? s.adjacency.as<PrimAdjacency>() : nullptr);
     ZB_CUDA(cudaGetLastError());
 
+    mark("scatter");
     // ---- 5. boxes, deepest level first ----
     for (int l = (int)levelStart.size() - 2; l >= 0; l--) {
         const int lf = levelStart[l], lc = levelStart[l + 1] - lf;
@@ -192,6 +211,7 @@ int buildBvhOnDevice(zb_context *ctx, DeviceBvhStorage& s, int dim, int nPrim, b
         ZB_CUDA(cudaGetLastError());
     }
 
+    mark("boxes");
     // ---- 6. cones ----
     if (refl) {
         for (size_t l = 0; l + 1 < levelStart.size(); l++) {
@@ -203,6 +223,7 @@ int buildBvhOnDevice(zb_context *ctx, DeviceBvhStorage& s, int dim, int nPrim, b
         }
     }
 
+    mark("cones");
     Box3 rootBox;
     uint32_t leafChildren = 0;
     ZB_CUDA(cudaMemcpyAsync(&rootBox, k.nodeBox, sizeof(Box3), cudaMemcpyDeviceToHost, st));

@@ -270,6 +270,8 @@ class Scene:
         mn = _f32(min_robin) if min_robin is not None else np.zeros(len(ri), np.float32)
         mx = _f32(max_robin) if max_robin is not None else np.zeros(len(ri), np.float32)
         self._h = C.c_void_p()
+        if builder is None and os.environ.get("ZOMBIE_B200_BVH_BUILDER"):  # A/B runs of unmodified scripts: "device" / "host"
+            builder = abi.BVH_BUILDER_DEVICE if os.environ["ZOMBIE_B200_BVH_BUILDER"] == "device" else abi.BVH_BUILDER_HOST_SAH
         if builder is not None:
             ctx.set_bvh_builder(builder)
         try:
