@@ -216,9 +216,15 @@ int buildBvhOnDevice(zb_context *ctx, DeviceBvhStorage& s, int dim, int nPrim, b
     if (refl) {
         for (size_t l = 0; l + 1 < levelStart.size(); l++) {
             const int lf = levelStart[l], lc = levelStart[l + 1] - lf;
-            const long long threads = (long long)lc*kWidth*32;
-            coneLevelKernel<<<(unsigned)((threads + 127)/128), 128, 0, st>>>(mesh, k.topo, lf, lc, s.nodes.as<WideNode>(), order, k.adjInput,
-                                                                           s.cones.as<ChildCone>());
+            // top levels: few slots of many primitives, one CTA per slot; below: one warp per slot
+            if ((long long)lc*kWidth*512 <= (long long)n) {
+                coneLevelKernel<16><<<(unsigned)(lc*kWidth), 512, 0, st>>>(mesh, k.topo, lf, lc, s.nodes.as<WideNode>(), order, k.adjInput,
+                                                                          s.cones.as<ChildCone>());
+            } else {
+                const long long threads = (long long)lc*kWidth*32;
+                coneLevelKernel<1><<<(unsigned)((threads + 127)/128), 128, 0, st>>>(mesh, k.topo, lf, lc, s.nodes.as<WideNode>(), order,
+                                                                                  k.adjInput, s.cones.as<ChildCone>());
+            }
             ZB_CUDA(cudaGetLastError());
         }
     }

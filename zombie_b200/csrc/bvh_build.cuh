@@ -19,15 +19,15 @@
 //      the last (largest) face in the other orientation slot of its edge — the reference's last-writer-wins tables;
 //   4. primitives scattered into leaf order (de-indexed vertex records, adjacency records);
 //   5. boxes bottom-up, one pass per level: exact child boxes, the node's quantisation frame, conservative 8-bit boxes;
-//   6. normal cones, bounding radii, Robin-coefficient ranges and the no-testable-edge mark per child slot, one warp
-//      per slot over the slot's range of the sorted order.
+//   6. normal cones, bounding radii, Robin-coefficient ranges and the no-testable-edge mark per child slot over the slot's
+//      range of the sorted order: one 512-thread CTA per slot on the top levels, one warp per slot below.
 //
 // Per-primitive records are computed with the host builder's un-contracted arithmetic and are bit-identical to its
 // records; the tree differs (spatial-median cuts instead of binned SAH), which changes traversal cost, not results:
 // quantised boxes and cones are conservative, so every query returns what a brute-force scan returns.
 //
 // The per-item logic is host+device so that tools/host_build.cu can run the builder on a CPU against the host
-// builder and the reference (tests/test_host_logic.py); the library only ever runs it from the kernels below.
+// builder and the reference (tests/test_device_builder.py); the library only ever runs it from the kernels below.
 #pragma once
 
 #include <float.h>
@@ -40,6 +40,9 @@ namespace zb {
 namespace lbvh {
 
 constexpr int kLeaf = kMaxLeafSize;
+#if !defined(ZB_LBVH_MEDIAN)
+#define ZB_LBVH_MEDIAN 0
+#endif
 
 struct Mesh {
     int dim;
@@ -169,7 +172,7 @@ ZB_HOSTDEV int leadingZeros64(uint64_t v)
 ZB_HOSTDEV int findSplit(const uint64_t *keys, int first, int last)
 {
     uint64_t a = keys[first], b = keys[last - 1];
-    if (a == b) return first + (last - first)/2;
+    if (a == b || ZB_LBVH_MEDIAN) return first + (last - first)/2;
     int shift = 63 - leadingZeros64(a ^ b); // the differing bit
     int lo = first, hi = last - 1;          // keys[lo] agrees with a above `shift`, keys[hi] does not
     while (hi - lo > 1) {
@@ -653,26 +656,9 @@ __global__ void __launch_bounds__(128) writeLevelKernel(int dim, const TopoNode 
     writeNode(dim, topo, first + k, prims, nodeBox, nodes);
 }
 
-// one warp per child slot of the nodes [first, first + count)
-__global__ void __launch_bounds__(128) coneLevelKernel(Mesh m, const TopoNode *topo, int first, int count, const WideNode *nodes,
-                                                       const int *order, const PrimAdjacency *adjInput, ChildCone *cones)
+// butterfly over the lanes of a warp: every lane ends with the same sums (float additions commute pairwise)
+__device__ __forceinline__ void coneWarpReduce(ConeSums& sums)
 {
-    const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x*blockDim.x + threadIdx.x) >> 5;
-    if (warp >= (long long)count*kWidth) return;
-    const int w = first + (int)(warp >> 3), c = (int)(warp & 7);
-    const TopoNode& n = topo[w];
-    if (c >= n.nChildren) {
-        if (lane == 0) cones[(size_t)w*kWidth + c] = emptyCone();
-        return;
-    }
-    const int s = n.bounds[c], e = n.bounds[c + 1];
-    float lo[3], hi[3], centre[3];
-    decodeChild(nodes[w], c, lo, hi);
-    for (int k = 0; k < 3; k++) centre[k] = 0.5f*(lo[k] + hi[k]);
-    ConeSums sums;
-    coneInit(sums);
-    for (int i = s + lane; i < e; i += 32) coneAccumulate(m, adjInput, order[i], centre, sums);
     for (int o = 16; o > 0; o >>= 1) {
         ConeSums other;
         for (int k = 0; k < 3; k++) other.axis[k] = __shfl_xor_sync(0xffffffffu, sums.axis[k], o);
@@ -683,16 +669,56 @@ __global__ void __launch_bounds__(128) coneLevelKernel(Mesh m, const TopoNode *t
         other.anyTestable = __shfl_xor_sync(0xffffffffu, sums.anyTestable, o);
         coneMerge(sums, other);
     }
-    // the butterfly leaves every lane with the same sums (float additions commute pairwise), so all lanes agree on the axis
+}
+
+// Child slots of the nodes [first, first + count). WARPS = 1: one warp per slot, four slots per CTA (the deep levels:
+// many slots of few primitives). WARPS = 16: one 512-thread CTA per slot (the top levels: a handful of slots of up to
+// nPrim/8 primitives each), partial sums combined through shared memory in a fixed order.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS == 1 ? 128 : 32*WARPS) coneLevelKernel(Mesh m, const TopoNode *topo, int first, int count,
+                                                                            const WideNode *nodes, const int *order,
+                                                                            const PrimAdjacency *adjInput, ChildCone *cones)
+{
+    __shared__ ConeSums partial[WARPS];
+    __shared__ float partialHalf[WARPS];
+    const int lane = threadIdx.x & 31, warpInCta = threadIdx.x >> 5;
+    const long long slot = WARPS == 1 ? ((long long)blockIdx.x*blockDim.x + threadIdx.x) >> 5 : (long long)blockIdx.x;
+    if (slot >= (long long)count*kWidth) return;
+    const int w = first + (int)(slot >> 3), c = (int)(slot & 7);
+    const TopoNode& n = topo[w];
+    if (c >= n.nChildren) {
+        if (threadIdx.x == 0 || (WARPS == 1 && lane == 0)) cones[(size_t)w*kWidth + c] = emptyCone();
+        return;
+    }
+    const int s = n.bounds[c], e = n.bounds[c + 1];
+    const int tid = WARPS == 1 ? lane : (int)threadIdx.x, stride = 32*WARPS;
+    float lo[3], hi[3], centre[3];
+    decodeChild(nodes[w], c, lo, hi);
+    for (int k = 0; k < 3; k++) centre[k] = 0.5f*(lo[k] + hi[k]);
+    ConeSums sums;
+    coneInit(sums);
+    for (int i = s + tid; i < e; i += stride) coneAccumulate(m, adjInput, order[i], centre, sums);
+    coneWarpReduce(sums);
+    if (WARPS > 1) {
+        if (lane == 0) partial[warpInCta] = sums;
+        __syncthreads();
+        sums = partial[0];
+        for (int k = 1; k < WARPS; k++) coneMerge(sums, partial[k]);
+    }
     ChildCone cone;
     float axis[3];
-    if (coneFromSums(sums, cone, axis)) {
+    if (coneFromSums(sums, cone, axis)) { // the same sums in every thread: a uniform branch
         float half = 0.0f;
-        for (int i = s + lane; i < e; i += 32) half = fmaxf(half, coneHalfAngle(m, adjInput, order[i], axis));
+        for (int i = s + tid; i < e; i += stride) half = fmaxf(half, coneHalfAngle(m, adjInput, order[i], axis));
         for (int o = 16; o > 0; o >>= 1) half = fmaxf(half, __shfl_xor_sync(0xffffffffu, half, o));
+        if (WARPS > 1) {
+            if (lane == 0) partialHalf[warpInCta] = half;
+            __syncthreads();
+            for (int k = 0; k < WARPS; k++) half = fmaxf(half, partialHalf[k]);
+        }
         coneFinish(cone, axis, half);
     }
-    if (lane == 0) cones[(size_t)w*kWidth + c] = cone;
+    if (tid == 0) cones[(size_t)w*kWidth + c] = cone;
 }
 
 #endif // __CUDACC__
