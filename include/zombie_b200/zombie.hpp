@@ -619,6 +619,11 @@ inline std::shared_ptr<MeshData> flatten(const std::vector<Vector<DIM>>& positio
 }
 } // namespace detail
 
+// Which builder the scenes created afterwards use (zb_context_set_bvh_builder): ZB_BVH_BUILDER_HOST_SAH (default; the
+// role of the reference's serial SAH build, fcpw/aggregates/bvh.inl:143-234) or ZB_BVH_BUILDER_DEVICE (on the GPU, in
+// milliseconds; for meshes that change often).
+inline void setBvhBuilder(int builder) { detail::check(zb_context_set_bvh_builder(detail::context()->ctx, builder)); }
+
 // getIgnoreCandidateSilhouetteCallback (fcpw_geometric_queries.h:1029-1038): the rule is data here
 struct IgnoreCandidateSilhouette {
     bool solveDoubleSided;

@@ -92,7 +92,7 @@ int buildBvhOnDevice(zb_context *ctx, DeviceBvhStorage& s, int dim, int nPrim, b
     if (nHalf) cub::DeviceRadixSort::SortPairs(nullptr, cubSortHe, (uint64_t *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, nHalf, 0, 64, st);
     cub::DeviceScan::InclusiveSum(nullptr, cubScan, (int *)nullptr, (int *)nullptr, cap, st);
     Scratch k{};
-    DeviceBuffer scratch;
+    DeviceBuffer& scratch = ctx->bvhBuild;
     for (int pass = 0; pass < 2; pass++) {
         Carver c;
         c.base = pass ? scratch.as<char>() : nullptr;

@@ -56,6 +56,7 @@ struct zb_context {
     bool ownsStream = false;
     zb::DeviceBuffer status, counters, perPoint, strat, records, scanTemp, io;
     zb::DeviceBuffer bvcSamples, bvcIo, rwsRecords, rwsSorted, rwsScratch;
+    zb::DeviceBuffer bvhBuild;             // scratch of the on-device hierarchy builder (grow-only: rebuilds of moving geometry allocate nothing)
     zb::DeviceBuffer wave, waveSort;       // walk state of the wavefront scheduler, radix-sort scratch
     unsigned int *hostLive = nullptr;      // pinned: live-walk counts read back every few rounds
     cudaEvent_t evRound[16] = {};          // two per slot group
