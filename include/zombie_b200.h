@@ -278,6 +278,24 @@ int zb_solve(zb_scene *scene, int estimator, const zb_pde_desc *pde, const zb_wa
 int zb_solve_dev(zb_scene *scene, int estimator, const zb_pde_desc *pde, const zb_walk_settings *settings,
                  const zb_sample_points *pts_dev, zb_statistics *stats_dev, int64_t *walkSteps_dev);
 
+/* ---- vector-valued solves: WalkOnSpheres<T, DIM> / WalkOnStars<T, DIM>::solve with T = Array<float, C>, the channels of
+ * the reference's bindings (python/zombie_bindings.cpp:37-44: 1, 3 or more value channels; core/pde.h:31-44: source,
+ * dirichlet and robin return T, absorptionCoeff and robinCoeff stay floats). C PDE descriptors, C statistics structs,
+ * ONE set of walks: geometry, random numbers, throughput and the weight window are shared exactly as the reference
+ * shares them between the components of T; every channel evaluates its own source / Dirichlet / Robin data at the
+ * points the walk samples and keeps its own estimates. Channel c of the result equals a scalar zb_solve of pdes[c] on
+ * the same generators (up to the contraction of multiply-adds); the cost is that of one scalar solve plus a few
+ * loads and stores per channel and step. The descriptors must agree in everything that steers the walk
+ * (absorptionCoeff, robinCoeff / robinCoeffGrid, the three flags, kelvin); sample-point arrays are shared, rng state
+ * advances once. nChannels 1..256. ---- */
+int zb_solve_channels(zb_scene *scene, int estimator, int nChannels, const zb_pde_desc *pdes /* nChannels */,
+                      const zb_walk_settings *settings, const zb_sample_points *pts, zb_statistics *stats /* nChannels, in/out */,
+                      int64_t *walkSteps);
+/* same with the sample-point arrays and the arrays inside every stats[c] resident on the context's device (pdes and the
+ * stats structs themselves are host memory); stream semantics of zb_solve_dev */
+int zb_solve_channels_dev(zb_scene *scene, int estimator, int nChannels, const zb_pde_desc *pdes, const zb_walk_settings *settings,
+                          const zb_sample_points *pts_dev, zb_statistics *stats, int64_t *walkSteps_dev);
+
 /* ---- Boundary Value Caching: replaces the splat stage of bvc::BoundaryValueCaching
  * (zombie/variance_reduction/boundary_value_caching.h:371-502, 682-811): every cache sample is splatted onto
  * every evaluation point with the free-space Green's function of the PDE (Harmonic / Yukawa,

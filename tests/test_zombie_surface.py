@@ -20,7 +20,8 @@ def test_factories_validate_dim_and_channels():
     with pytest.raises(ValueError):
         zombie.Core.PDE(dim=4)
     with pytest.raises(ValueError):
-        zombie.Core.PDE(dim=2, channels=4)
+        zombie.Core.PDE(dim=2, channels=0)
+    assert zombie.Core.PDE(dim=2, channels=3).channels == 3
     with pytest.raises(ValueError):
         zombie.Samplers.create_uniform_triangle_boundary_sampler([], [], dim=2)
     assert isinstance(zombie.FloatNList(dim=3), zombie.Float3List) and isinstance(zombie.IntNList(dim=2), zombie.Int2List)
@@ -157,3 +158,72 @@ def test_demo_flow_walk_on_stars_2d(ctx):
     assert stats[0].get_solution_estimate_count() == 512
     est2 = np.array([stats[i].get_estimated_solution() for i in range(len(pts))])
     assert np.sqrt(np.mean((est2 - exact)**2)) < np.sqrt(np.mean((est - exact)**2)) + 0.005
+
+
+def test_vector_valued_pde_descriptors():
+    """channels = 3 (the reference's T = Array<float, 3>): constants take three values, dense grids three values per cell with the
+    channel index fastest; one descriptor per channel, sharing what steers the walk"""
+    nx, ny = 4, 3
+    data = np.arange(nx*ny*3, dtype=np.float32).reshape(nx*ny, 3)
+    pde = zombie.Core.PDE(dim=2, channels=3)
+    pde.source = zombie.Utils.get_dense_grid_source_callback(data, [nx, ny], np.zeros(2), np.array([4.0, 3.0]), dim=2, channels=3)
+    pde.dirichlet = zombie.Core.get_constant_dirichlet_callback([1.0, 2.0, 3.0], dim=2, channels=3)
+    pde.robin = zombie.Core.get_constant_robin_callback(0.5, dim=2, channels=3)
+    pde.robin_coeff = zombie.Core.get_constant_robin_coefficient_callback(0.25, dim=2)
+    pde.absorption_coeff = 2.0
+    pde.are_robin_conditions_pure_neumann = False
+    ds = pde.descriptors()
+    assert len(ds) == 3
+    for c, d in enumerate(ds):
+        assert d.dirichletValue == c + 1.0 and d.robinValue == 0.5 and d.robinCoeff == 0.25 and d.absorptionCoeff == 2.0
+        assert np.array_equal(d.host_grids["sourceGrid"].values[0], data[:, c].reshape(nx, ny).T)
+    with pytest.raises(ValueError):
+        zombie.Core.get_constant_source_callback([1.0, 2.0], dim=2, channels=3)
+    stats = zombie.Solvers.create_sample_statistics_list(5, dim=2, channels=3)
+    assert stats[0].get_estimated_solution().shape == (3,) and stats[0].get_estimated_gradient().shape == (2, 3)
+
+
+@pytest.mark.gpu
+def test_vector_valued_solve_through_the_surface(ctx):
+    """WalkOnSpheres with channels = 3 on the star polygon: every channel equals the scalar solve of its data on the same generators"""
+    dim = 2
+    positions, indices = star_mesh(1024)
+    queries = zombie.Core.GeometricQueries(True, np.array([-2.0, -2.0]), np.array([2.0, 2.0]), dim=dim)
+    handler = zombie.Utils.FcpwDirichletBoundaryHandler(dim=dim)
+    handler.build_acceleration_structure(positions, indices)
+    zombie.Utils.populate_geometric_queries_for_dirichlet_boundary(handler, queries, dim=dim)
+    n = 256
+    lo, hi = np.array([-1.5, -1.5]), np.array([1.5, 1.5])
+    xs = lo[0] + (np.arange(n) + 0.5)*(hi[0] - lo[0])/n
+    X, Y = np.meshgrid(xs, xs, indexing="ij")
+    u = np.stack([X**3 - 3.0*X*Y**2, X*Y, X**2 - Y**2 + 0.5], axis=-1).astype(np.float32)     # three harmonic functions
+
+    def problem(channels, cols):
+        pde = zombie.Core.PDE(dim=dim, channels=channels)
+        pde.source = zombie.Core.get_constant_source_callback(0.0, dim=dim, channels=channels)
+        pde.dirichlet = zombie.Utils.get_dense_grid_dirichlet_callback(u[..., cols].reshape(-1, channels), [n, n], lo, hi, True, dim=dim, channels=channels)
+        pde.is_source_constant = True
+        return pde
+
+    pts = cases.query_points(300, dim, 0.6, seed=2)
+    settings = zombie.Solvers.WalkSettings(1e-3, 1e-3, 1024, False)
+
+    def solve(pde, channels):
+        zombie._SamplePoint._next_stream = 1000      # the same pcg32 streams for every run
+        sp = [zombie.Solvers.SamplePoint(x, np.zeros(dim), zombie.Solvers.SampleType.InDomain, zombie.Solvers.EstimationQuantity.SolutionAndGradient,
+                                         1.0, queries.compute_dist_to_absorbing_boundary(x), abi.FLT_MAX, dim=dim, channels=channels) for x in pts]
+        stats = zombie.Solvers.create_sample_statistics_list(len(sp), dim=dim, channels=channels)
+        zombie.Solvers.WalkOnSpheres(queries, dim=dim, channels=channels).solve(pde, settings, zombie.IntList([64]*len(sp)), sp, stats)
+        return stats
+
+    vec = solve(problem(3, [0, 1, 2]), 3)
+    est = np.array([vec[i].get_estimated_solution() for i in range(len(pts))])            # [points, 3]
+    grad = np.array([vec[i].get_estimated_gradient() for i in range(len(pts))])           # [points, 2, 3]
+    for c in range(3):
+        one = solve(problem(1, [c]), 1)
+        assert np.allclose(est[:, c], [one[i].get_estimated_solution() for i in range(len(pts))], rtol=0, atol=2e-5)
+        assert np.allclose(grad[:, :, c], [one[i].get_estimated_gradient() for i in range(len(pts))], rtol=0, atol=2e-4)
+        assert vec[0].get_mean_walk_length() == one[0].get_mean_walk_length()
+    exact = np.stack([pts[:, 0]**3 - 3.0*pts[:, 0]*pts[:, 1]**2, pts[:, 0]*pts[:, 1], pts[:, 0]**2 - pts[:, 1]**2 + 0.5], axis=-1)
+    se = np.sqrt(np.array([vec[i].get_estimated_solution_variance() for i in range(len(pts))])/64.0)
+    assert np.mean(np.abs(est - exact) < 3.0*se + 0.01) > 0.97

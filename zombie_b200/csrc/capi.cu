@@ -24,6 +24,10 @@ namespace {
 // zb_solve knows from the host arrays whether any point asks for gradients and tells zb_solve_dev
 // so that solution-only runs do not allocate gradient records; zb_solve_dev alone assumes they may
 thread_local bool g_gradientHint = true;
+// zb_solve_channels(_dev) hands the extra value channels (descriptors and statistics already on the device) to the
+// zb_solve_dev it calls for channel 0
+struct ExtraChannels { int n = 0; const zb_pde_desc *pde = nullptr; const zb_statistics *stats = nullptr; };
+thread_local ExtraChannels g_extra;
 } // namespace
 
 struct zb_scene {
@@ -602,6 +606,15 @@ int solveRange(zb_scene *scene, SolveArgs& a, int n, bool anyGradient)
     }
     a.taskCounter = ctx->counters.as<unsigned long long>();
     ZB_CUDA(cudaMemsetAsync(a.taskCounter, 0, sizeof(unsigned long long), stream));
+    if (a.nExtra > 0) { // per-task sums and records of the extra value channels
+        const size_t per = (size_t)a.nExtra*nt;
+        ZB_CUDA(ctx->channelRecords.reserve(4*per*sizeof(float) + 256));
+        a.xRefl = ctx->channelRecords.as<float>();
+        a.xSrc = a.xRefl + per;
+        a.xRecSolution = a.xSrc + per;
+        a.xRecFirstSource = a.xRecSolution + per;
+        ZB_CUDA(cudaMemsetAsync(a.xRefl, 0, 4*per*sizeof(float), stream));
+    }
 
     ZB_CUDA(cudaFuncSetAttribute(preparePointsKernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
     preparePointsKernel<DIM><<<blocksFor(n, threads), threads, kCoopSmem, stream>>>(a);
@@ -641,6 +654,11 @@ int solveRange(zb_scene *scene, SolveArgs& a, int n, bool anyGradient)
     if (a.rwsRecords) rwsFinishKernel<DIM><<<blocksFor(n, threads), threads, 0, stream>>>(a);
     else reducePointsKernel<DIM><<<blocksFor(n, threads), threads, 0, stream>>>(a);
     ZB_CUDA(cudaGetLastError());
+    if (a.nExtra > 0 && !a.rwsRecords) {
+        reduceExtraChannelsKernel<DIM><<<blocksFor(n*a.nExtra, threads), threads, 0, stream>>>(a);
+        ZB_CUDA(cudaGetLastError());
+        ctx->launches += 1;
+    }
     ZB_CUDA(cudaEventRecord(ctx->ev[3], stream));
     ctx->profiled = true;
     return ZB_OK;
@@ -1373,6 +1391,9 @@ int zb_solve_dev(zb_scene *scene, int estimator, const zb_pde_desc *pde, const z
     }
     a.pts = *pts;
     a.stats = *stats;
+    a.nExtra = g_extra.n;
+    a.extraPde = g_extra.pde;
+    a.extraStats = g_extra.stats;
     a.walkSteps = ctx->counters.as<long long>() + 1;
     ZB_CUDA(cudaMemsetAsync(a.walkSteps, 0, sizeof(long long), ctx->stream));
 
@@ -1465,6 +1486,120 @@ int zb_solve(zb_scene *scene, int estimator, const zb_pde_desc *pde, const zb_wa
     if (rc != ZB_OK) return rc;
     if (walkSteps) ZB_CUDA(cudaMemcpyAsync(walkSteps, base + stepsOff, 8, cudaMemcpyDeviceToHost, ctx->stream));
     return stageOut(ctx, plan);
+}
+
+// ---- vector-valued solves: C value channels on one set of walks -------------------------------------------------
+namespace {
+// descriptors and statistics structs of channels 1.. -> device; what zb_solve_dev does to a Kelvin-wrapped PDE's flags is done here
+int uploadExtraChannels(zb_scene *scene, int nChannels, const zb_pde_desc *pdes, const zb_statistics *statsDev /* device pointers inside */,
+                        ExtraChannels& out)
+{
+    zb_context *ctx = scene->ctx;
+    const int nExtra = nChannels - 1;
+    out = ExtraChannels();
+    if (nExtra == 0) return ZB_OK;
+    std::vector<zb_pde_desc> d(pdes + 1, pdes + nChannels);
+    for (auto& e : d) {
+        if (e.kelvin) {
+            e.isSourceConstant = 0;
+            e.absorptionCoeff = 0.0f;
+            if (scene->dim == 3) { e.areRobinConditionsPureNeumann = 0; e.areRobinCoeffsNonnegative = 0; }
+        }
+    }
+    const size_t descBytes = (nExtra*sizeof(zb_pde_desc) + 255) & ~size_t(255);
+    ZB_CUDA(ctx->channelDesc.reserve(descBytes + nExtra*sizeof(zb_statistics) + 256));
+    char *base = ctx->channelDesc.as<char>();
+    // pageable sources: the copies are staged before the call returns, so the vectors may go out of scope
+    ZB_CUDA(cudaMemcpyAsync(base, d.data(), nExtra*sizeof(zb_pde_desc), cudaMemcpyHostToDevice, ctx->stream));
+    ZB_CUDA(cudaMemcpyAsync(base + descBytes, statsDev + 1, nExtra*sizeof(zb_statistics), cudaMemcpyHostToDevice, ctx->stream));
+    out.n = nExtra;
+    out.pde = reinterpret_cast<const zb_pde_desc *>(base);
+    out.stats = reinterpret_cast<const zb_statistics *>(base + descBytes);
+    return ZB_OK;
+}
+
+int checkChannels(const char *who, const zb_scene *scene, int nChannels, const zb_pde_desc *pdes, const zb_statistics *stats)
+{
+    if (!scene || !pdes || !stats) return fail(ZB_ERR_INVALID_ARGUMENT, std::string(who) + ": NULL argument");
+    if (nChannels < 1 || nChannels > 256) return fail(ZB_ERR_INVALID_ARGUMENT, std::string(who) + ": nChannels must be 1..256");
+    for (int c = 1; c < nChannels; c++) {
+        // the walk is channel 0's: what steers it — screening, the Robin coefficient, the flags — is scalar in the reference
+        // as well (PDE<T, DIM>::absorptionCoeff and robinCoeff are floats for every T, core/pde.h:26-44)
+        const zb_pde_desc &a = pdes[0], &b = pdes[c];
+        if (a.absorptionCoeff != b.absorptionCoeff || a.isSourceConstant != b.isSourceConstant ||
+            a.areRobinConditionsPureNeumann != b.areRobinConditionsPureNeumann || a.areRobinCoeffsNonnegative != b.areRobinCoeffsNonnegative ||
+            a.kelvin != b.kelvin || a.robinCoeff != b.robinCoeff || a.robinCoeffGrid.data != b.robinCoeffGrid.data)
+            return fail(ZB_ERR_INVALID_ARGUMENT, std::string(who) + ": the channels must share absorptionCoeff, Robin coefficient, Kelvin wrapping and PDE flags");
+        if (b.mode != ZB_PDE_MANUFACTURED && b.mode != ZB_PDE_CONSTANT) return fail(ZB_ERR_INVALID_ARGUMENT, std::string(who) + ": unknown pde mode");
+        if (scene->dim == 2 && b.mode == ZB_PDE_MANUFACTURED && ((b.family == ZB_SOL_QUADRATIC && b.params[2] != 0.0f) || b.family == ZB_SOL_TRIG_3D))
+            return fail(ZB_ERR_INVALID_ARGUMENT, std::string(who) + ": this solution family has a z dependence and cannot describe a 2D problem");
+    }
+    return ZB_OK;
+}
+} // namespace
+
+int zb_solve_channels_dev(zb_scene *scene, int estimator, int nChannels, const zb_pde_desc *pdes, const zb_walk_settings *settings,
+                          const zb_sample_points *pts, zb_statistics *stats, int64_t *walkSteps_dev)
+{
+    int rc = checkChannels("zb_solve_channels_dev", scene, nChannels, pdes, stats);
+    if (rc != ZB_OK) return rc;
+    ZB_CUDA(cudaSetDevice(scene->ctx->device));
+    ExtraChannels extra;
+    rc = uploadExtraChannels(scene, nChannels, pdes, stats, extra);
+    if (rc != ZB_OK) return rc;
+    g_extra = extra;
+    rc = zb_solve_dev(scene, estimator, &pdes[0], settings, pts, &stats[0], walkSteps_dev);
+    g_extra = ExtraChannels();
+    return rc;
+}
+
+int zb_solve_channels(zb_scene *scene, int estimator, int nChannels, const zb_pde_desc *pdes, const zb_walk_settings *settings,
+                      const zb_sample_points *pts, zb_statistics *stats, int64_t *walkSteps)
+{
+    int rc = checkChannels("zb_solve_channels", scene, nChannels, pdes, stats);
+    if (rc != ZB_OK) return rc;
+    if (!pts) return fail(ZB_ERR_INVALID_ARGUMENT, "zb_solve_channels: NULL argument");
+    if (nChannels == 1 || pts->n <= 0) return zb_solve(scene, estimator, &pdes[0], settings, pts, &stats[0], walkSteps);
+    zb_context *ctx = scene->ctx;
+    ZB_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)pts->n, dim = (size_t)scene->dim;
+    const int nExtra = nChannels - 1;
+    // statistics of channels 1..: ten arrays each, staged in one device buffer (in/out like channel 0's)
+    const size_t words = (8 + 2*dim)*n, stride = (words*4 + 255) & ~size_t(255);
+    ZB_CUDA(ctx->channelIo.reserve(stride*nExtra + 256));
+    std::vector<zb_statistics> dev(nChannels);
+    struct Span { void *host; char *device; size_t bytes; };
+    std::vector<Span> spans;
+    for (int c = 1; c < nChannels; c++) {
+        const zb_statistics& h = stats[c];
+        if (!h.solutionMean || !h.solutionM2 || !h.gradientMean || !h.gradientM2 || !h.totalFirstSourceContribution ||
+            !h.totalDerivativeContribution || !h.nSolutionEstimates || !h.nGradientEstimates || !h.totalWalkLength || !h.totalSplits)
+            return fail(ZB_ERR_INVALID_ARGUMENT, "zb_solve_channels: a statistics array is NULL");
+        char *p = ctx->channelIo.as<char>() + stride*(c - 1);
+        auto put = [&](void *host, size_t count) { Span sp{host, p, 4*count}; spans.push_back(sp); p += 4*count; return sp.device; };
+        zb_statistics& d = dev[c];
+        d.solutionMean = (float *)put(h.solutionMean, n);
+        d.solutionM2 = (float *)put(h.solutionM2, n);
+        d.gradientMean = (float *)put(h.gradientMean, dim*n);
+        d.gradientM2 = (float *)put(h.gradientM2, dim*n);
+        d.totalFirstSourceContribution = (float *)put(h.totalFirstSourceContribution, n);
+        d.totalDerivativeContribution = (float *)put(h.totalDerivativeContribution, n);
+        d.nSolutionEstimates = (int32_t *)put(h.nSolutionEstimates, n);
+        d.nGradientEstimates = (int32_t *)put(h.nGradientEstimates, n);
+        d.totalWalkLength = (int32_t *)put(h.totalWalkLength, n);
+        d.totalSplits = (int32_t *)put(h.totalSplits, n);
+    }
+    for (const Span& sp : spans) ZB_CUDA(cudaMemcpyAsync(sp.device, sp.host, sp.bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ExtraChannels extra;
+    rc = uploadExtraChannels(scene, nChannels, pdes, dev.data(), extra);
+    if (rc != ZB_OK) return rc;
+    g_extra = extra;
+    rc = zb_solve(scene, estimator, &pdes[0], settings, pts, &stats[0], walkSteps); // stages channel 0, runs the walks, folds every channel
+    g_extra = ExtraChannels();
+    if (rc != ZB_OK) return rc;
+    for (const Span& sp : spans) ZB_CUDA(cudaMemcpyAsync(sp.host, sp.device, sp.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ZB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZB_OK;
 }
 
 int zb_rws_solve(zb_scene *scene, const zb_pde_desc *pde, const zb_walk_settings *settings, const zb_rws_samples *smp,

@@ -56,6 +56,7 @@ struct zb_context {
     bool ownsStream = false;
     zb::DeviceBuffer status, counters, perPoint, strat, records, scanTemp, io;
     zb::DeviceBuffer bvcSamples, bvcIo, rwsRecords, rwsSorted, rwsScratch;
+    zb::DeviceBuffer channelRecords, channelDesc, channelIo; // extra value channels of zb_solve_channels: per-task sums, descriptors, staged statistics
     zb::DeviceBuffer bvhBuild;             // scratch of the on-device hierarchy builder (grow-only: rebuilds of moving geometry allocate nothing)
     zb::DeviceBuffer wave, waveSort;       // walk state of the wavefront scheduler, radix-sort scratch
     unsigned int *hostLive = nullptr;      // pinned: live-walk counts read back every few rounds

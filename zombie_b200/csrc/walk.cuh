@@ -59,6 +59,14 @@ struct SolveArgs {
     const float *rwsPdf;              // per sample point
     const float *rwsContribution;     // per sample point
     float rwsNormalOffset;            // normalOffsetForAbsorbingBoundary
+    // Extra value channels (zb_solve_channels: the reference's vector-valued T, python/zombie_bindings.cpp:37-44). The walk —
+    // geometry, random numbers, throughput, weight window — is channel 0's; every further channel only evaluates its own
+    // source / Dirichlet / Robin data at the points the walk samples and keeps its own sums, per task:
+    int nExtra;
+    const zb_pde_desc *extraPde;      // device, nExtra descriptors
+    const zb_statistics *extraStats;  // device, nExtra structs of device pointers
+    float *xRefl, *xSrc;              // nExtra x totalTasks: reflecting-boundary / source terms of the task's current walk state
+    float *xRecSolution, *xRecFirstSource; // nExtra x totalTasks: the task's record
 };
 
 template <int DIM>
@@ -366,6 +374,53 @@ __global__ void __launch_bounds__(128) preparePointsKernel(SolveArgs a)
 // ------------------------------------------------------------------------------------------
 
 // everything a lane keeps between steps
+// ---- extra value channels -----------------------------------------------------------------------------------------
+// Out of line: a scalar solve (nExtra = 0) never executes them and they stay out of the step kernel's hot instruction footprint.
+// Each mirrors the expression of the scalar path it shadows, so channel c of a multi-channel solve equals a scalar solve of
+// that channel's PDE on the same generators up to the contraction of multiply-adds.
+template <int DIM>
+ZB_DEV_COLD void extraSourceTerm(const SolveArgs& a, long long task, Vec<DIM> p, float throughput, float gnorm)
+{
+    for (int c = 0; c < a.nExtra; c++) {
+        PdeEval<DIM> pde{a.extraPde[c]};
+        a.xSrc[(size_t)c*a.totalTasks + task] += throughput*(gnorm*pde.source(p));
+    }
+}
+template <int DIM>
+ZB_DEV_COLD void extraRobinTerm(const SolveArgs& a, long long task, Vec<DIM> p, Vec<DIM> n, bool aligned, float weight, float pdf)
+{
+    for (int c = 0; c < a.nExtra; c++) {
+        PdeEval<DIM> pde{a.extraPde[c]};
+        a.xRefl[(size_t)c*a.totalTasks + task] += weight*pde.robin(p, n, aligned)/pdf;
+    }
+}
+// the first ball of a gradient estimate (beginTask): the channel's first source term goes to its record and into its sums
+template <int DIM>
+ZB_DEV_COLD void extraFirstSource(const SolveArgs& a, long long task, Vec<DIM> p, float throughput, float gnorm)
+{
+    for (int c = 0; c < a.nExtra; c++) {
+        PdeEval<DIM> pde{a.extraPde[c]};
+        float first = gnorm*pde.source(p);
+        a.xRecFirstSource[(size_t)c*a.totalTasks + task] = first;
+        a.xSrc[(size_t)c*a.totalTasks + task] += throughput*first;
+    }
+}
+// a walk state ended: fold the channel's terminal contribution and sums into the task's record (not when the walk escaped)
+template <int DIM>
+ZB_DEV_COLD void extraFinishState(const SolveArgs& a, long long task, bool keep, bool project, Vec<DIM> p, float throughput)
+{
+    for (int c = 0; c < a.nExtra; c++) {
+        size_t k = (size_t)c*a.totalTasks + task;
+        if (keep) {
+            float terminal = 0.0f;
+            if (project) { PdeEval<DIM> pde{a.extraPde[c]}; terminal = pde.dirichlet(p); }
+            a.xRecSolution[k] += throughput*terminal + a.xRefl[k] + a.xSrc[k];
+        }
+        a.xRefl[k] = 0.0f;
+        a.xSrc[k] = 0.0f;
+    }
+}
+
 template <int DIM>
 struct Lane {
     WalkState<DIM> st;
@@ -491,17 +546,19 @@ ZB_DEV void beginTask(const SolveArgs& a, Lane<DIM>& L, long long task)
 
     if (!a.ws.ignoreSourceContribution) {
         float gnorm = L.g.norm();
+        Vec<DIM> sourcePt = x;
         if (a.pde.isSourceConstant) {
             L.firstSource = gnorm*pde.source(x);
         } else {
             Vec<DIM> dir = uniformDirection(strat + (DIM - 1)*(2*w + 0), (Vec<DIM> *)nullptr);
             float sourceRadius, sourcePdf;
-            Vec<DIM> sourcePt = L.g.sampleVolume(dir, L.rng, sourceRadius, sourcePdf);
+            sourcePt = L.g.sampleVolume(dir, L.rng, sourceRadius, sourcePdf);
             if (anti == 1) sourcePt = x - (sourcePt - x);
             L.firstSource = gnorm*pde.source(sourcePt);
             L.gradSource = L.g.gradient(sourceRadius, sourcePt)/(sourcePdf*gnorm);
         }
         L.st.srcContrib += L.st.throughput*L.firstSource;
+        if (a.nExtra) extraFirstSource<DIM>(a, task, sourcePt, L.st.throughput, gnorm);
     }
 
     const float *ub = strat + (DIM - 1)*(2*w + 1);
@@ -697,15 +754,17 @@ ZB_DEV StepResult stepBody(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *que
         L.g.updateBall(st.pt, L.distA);
         if (!a.ws.ignoreSourceContribution) {
             float contribution;
+            Vec<DIM> sourcePt = st.pt;
             if (a.pde.isSourceConstant) {
                 contribution = L.g.norm()*pde.source(st.pt);
             } else {
                 Vec<DIM> sdir = uniformDirection<DIM>(L.rng);
                 float r, pdf;
-                Vec<DIM> sourcePt = L.g.sampleVolume(sdir, L.rng, r, pdf);
+                sourcePt = L.g.sampleVolume(sdir, L.rng, r, pdf);
                 contribution = L.g.norm()*pde.source(sourcePt);
             }
             st.srcContrib += st.throughput*contribution;
+            if (a.nExtra) extraSourceTerm<DIM>(a, L.task, sourcePt, st.throughput, L.g.norm());
         }
         Vec<DIM> dir = uniformDirection<DIM>(L.rng);
         st.pt = st.pt + dir*L.distA;
@@ -776,6 +835,7 @@ ZB_DEV StepResult stepBody(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *que
                         float G = L.g.evaluate(r);
                         float h = pde.robin(bs.p, bs.n, aligned); // returnBoundaryNormalAlignedValue (walk_on_stars.h:242-244)
                         st.reflContrib += st.throughput*alpha*G*h/bs.pdf;
+                        if (a.nExtra) extraRobinTerm<DIM>(a, L.task, bs.p, bs.n, aligned, st.throughput*alpha*G, bs.pdf);
                     }
                 }
             }
@@ -787,6 +847,7 @@ ZB_DEV StepResult stepBody(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *que
             Vec<DIM> sourcePt = L.g.sampleVolume(dir, L.rng, sourceRadius, sourcePdf);
             if (sourceRadius <= nextDist) {
                 st.srcContrib += st.throughput*(L.g.norm()*pde.source(sourcePt));
+                if (a.nExtra) extraSourceTerm<DIM>(a, L.task, sourcePt, st.throughput, L.g.norm());
             }
         }
 
@@ -860,6 +921,10 @@ ZB_DEV void finishState(const SolveArgs& a, Lane<DIM>& L, StepResult code, WalkS
         L.total += L.st.throughput*terminal + L.st.reflContrib + L.st.srcContrib;
         L.totalLength += L.st.walkLength;
         L.success = true;
+        if (a.nExtra) extraFinishState<DIM>(a, L.task, true, project && !a.ws.ignoreAbsorbingBoundaryContribution,
+                                            a.hasAbsorbing ? L.proj : L.st.pt, L.st.throughput);
+    } else if (a.nExtra) {
+        extraFinishState<DIM>(a, L.task, false, false, L.st.pt, 0.0f);
     }
     if (L.nQueued > 0) {
         L.st = queue[--L.nQueued];
@@ -993,19 +1058,22 @@ ZB_DEV void welford(float estimate, float& mean, float& m2, int n)
     m2 += delta*delta2;
 }
 
+// One channel's fold: channel 0 (primary) reads the solve's own PDE, statistics and records; an extra channel (zb_solve_channels)
+// its own sums over the same walks.
 template <int DIM>
-ZB_DEV long long reducePoint(const SolveArgs& a, int i)
+ZB_DEV long long reduceChannel(const SolveArgs& a, int i, const zb_pde_desc& pdeDesc, const zb_statistics& stats, const float *recSolution,
+                               const float *recFirstSource, bool primary)
 {
     int quantity = a.pts.estimationQuantity[i];
-    PdeEval<DIM> pde{a.pde};
+    PdeEval<DIM> pde{pdeDesc};
 
-    float mean = a.stats.solutionMean[i], m2 = a.stats.solutionM2[i];
-    int nSol = a.stats.nSolutionEstimates[i], nGrad = a.stats.nGradientEstimates[i];
-    int walkLength = a.stats.totalWalkLength[i], splits = a.stats.totalSplits[i];
-    float firstSourceTotal = a.stats.totalFirstSourceContribution[i];
-    float derivativeTotal = a.stats.totalDerivativeContribution[i];
+    float mean = stats.solutionMean[i], m2 = stats.solutionM2[i];
+    int nSol = stats.nSolutionEstimates[i], nGrad = stats.nGradientEstimates[i];
+    int walkLength = stats.totalWalkLength[i], splits = stats.totalSplits[i];
+    float firstSourceTotal = stats.totalFirstSourceContribution[i];
+    float derivativeTotal = stats.totalDerivativeContribution[i];
     float gmean[DIM], gm2[DIM];
-    for (int k = 0; k < DIM; k++) { gmean[k] = a.stats.gradientMean[(size_t)DIM*i + k]; gm2[k] = a.stats.gradientM2[(size_t)DIM*i + k]; }
+    for (int k = 0; k < DIM; k++) { gmean[k] = stats.gradientMean[(size_t)DIM*i + k]; gm2[k] = stats.gradientM2[(size_t)DIM*i + k]; }
 
     if (quantity == ZB_SOLUTION && a.pts.type[i] == ZB_ON_ABSORBING_BOUNDARY) {
         if (nSol == 0) {
@@ -1013,7 +1081,7 @@ ZB_DEV long long reducePoint(const SolveArgs& a, int i)
             if (!a.ws.ignoreAbsorbingBoundaryContribution) value = pde.dirichlet(loadVec<DIM>(a.pts.pt + (size_t)DIM*i));
             nSol += 1;
             welford(value, mean, m2, nSol);
-            a.pts.firstSphereRadius[i] = 0.0f;
+            if (primary) a.pts.firstSphereRadius[i] = 0.0f;
         }
     } else {
         long long begin = a.taskOffset[i], end = a.taskOffset[i + 1];
@@ -1034,9 +1102,9 @@ ZB_DEV long long reducePoint(const SolveArgs& a, int i)
             int flags = a.recFlags[t];
             walkLength += a.recLength[t];
             if (!(flags & (int)0x80000000)) continue;
-            float total = a.recSolution[t];
+            float total = recSolution[t];
             if (gradient) {
-                float firstSource = a.recFirstSource[t];
+                float firstSource = recFirstSource[t];
                 float boundaryContribution = total - firstSource;
                 float derivative = 0.0f;
                 float est[DIM];
@@ -1060,24 +1128,32 @@ ZB_DEV long long reducePoint(const SolveArgs& a, int i)
             splits += flags & 0x7fffffff;
         }
         // the point's generator moves on, so a later solve() on the same points draws fresh walks
-        Pcg32 rng;
-        rng.state = a.pointState[i];
-        rng.inc = a.pts.rngInc[i];
-        rng.advance((uint64_t)(end - begin) + 1u);
-        a.pts.rngState[i] = rng.state;
+        if (primary) {
+            Pcg32 rng;
+            rng.state = a.pointState[i];
+            rng.inc = a.pts.rngInc[i];
+            rng.advance((uint64_t)(end - begin) + 1u);
+            a.pts.rngState[i] = rng.state;
+        }
     }
 
-    long long stepsTaken = (long long)walkLength - (long long)a.stats.totalWalkLength[i];
-    a.stats.solutionMean[i] = mean;
-    a.stats.solutionM2[i] = m2;
-    a.stats.nSolutionEstimates[i] = nSol;
-    a.stats.nGradientEstimates[i] = nGrad;
-    a.stats.totalWalkLength[i] = walkLength;
-    a.stats.totalSplits[i] = splits;
-    a.stats.totalFirstSourceContribution[i] = firstSourceTotal;
-    a.stats.totalDerivativeContribution[i] = derivativeTotal;
-    for (int k = 0; k < DIM; k++) { a.stats.gradientMean[(size_t)DIM*i + k] = gmean[k]; a.stats.gradientM2[(size_t)DIM*i + k] = gm2[k]; }
+    long long stepsTaken = (long long)walkLength - (long long)stats.totalWalkLength[i];
+    stats.solutionMean[i] = mean;
+    stats.solutionM2[i] = m2;
+    stats.nSolutionEstimates[i] = nSol;
+    stats.nGradientEstimates[i] = nGrad;
+    stats.totalWalkLength[i] = walkLength;
+    stats.totalSplits[i] = splits;
+    stats.totalFirstSourceContribution[i] = firstSourceTotal;
+    stats.totalDerivativeContribution[i] = derivativeTotal;
+    for (int k = 0; k < DIM; k++) { stats.gradientMean[(size_t)DIM*i + k] = gmean[k]; stats.gradientM2[(size_t)DIM*i + k] = gm2[k]; }
     return stepsTaken;
+}
+
+template <int DIM>
+ZB_DEV long long reducePoint(const SolveArgs& a, int i)
+{
+    return reduceChannel<DIM>(a, i, a.pde, a.stats, a.recSolution, a.recFirstSource, true);
 }
 
 template <int DIM>
@@ -1090,6 +1166,18 @@ __global__ void reducePointsKernel(SolveArgs a)
     for (int o = 16; o > 0; o >>= 1) stepsTaken += __shfl_down_sync(0xffffffffu, stepsTaken, o);
     if ((threadIdx.x & 31) == 0 && stepsTaken) atomicAdd((unsigned long long *)a.walkSteps, (unsigned long long)stepsTaken);
 #endif
+}
+
+// extra value channels: the same fold over the same walks, one thread per (channel, point)
+template <int DIM>
+__global__ void reduceExtraChannelsKernel(SolveArgs a)
+{
+    long long k = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (k >= (long long)a.pts.n*a.nExtra) return;
+    int c = (int)(k/a.pts.n), i = (int)(k - (long long)c*a.pts.n);
+    if (a.pts.estimationQuantity[i] == ZB_SKIP) return;
+    reduceChannel<DIM>(a, i, a.extraPde[c], a.extraStats[c], a.xRecSolution + (size_t)c*a.totalTasks,
+                       a.anyGradient ? a.xRecFirstSource + (size_t)c*a.totalTasks : nullptr, false);
 }
 
 } // namespace zb

@@ -24,7 +24,7 @@ SYMBOLS = ["zb_last_error", "zb_abi_version", "zb_device_count", "zb_context_cre
            "zb_scene_validate", "zb_scene_download_records",
            "zb_host_bvh_check", "zb_scene_create", "zb_scene_destroy", "zb_scene_update_robin_coefficients", "zb_scene_update_robin_coefficients_dev", "zb_scene_stats",
            "zb_closest_point", "zb_intersect_ray", "zb_occluded", "zb_count_ray_hits", "zb_inside_domain", "zb_sample_sphere", "zb_star_radius",
-           "zb_solve", "zb_solve_dev", "zb_bvc_splat", "zb_bvc_splat_dev", "zb_context_last_splat_ms", "zb_rws_solve",
+           "zb_solve", "zb_solve_dev", "zb_solve_channels", "zb_solve_channels_dev", "zb_bvc_splat", "zb_bvc_splat_dev", "zb_context_last_splat_ms", "zb_rws_solve",
            "zb_grid_create", "zb_grid_data", "zb_grid_destroy",
            "zb_pcg32_kat", "zb_pcg32_demo", "zb_pcg32_floats"]
 
@@ -72,6 +72,8 @@ def lib():
         l.zb_star_radius.argtypes = [vp, i, vp, vp, vp, f, vp, vp]
         l.zb_solve.argtypes = [vp, i, vp, vp, vp, vp, vp]
         l.zb_solve_dev.argtypes = [vp, i, vp, vp, vp, vp, vp]
+        l.zb_solve_channels.argtypes = [vp, i, i, vp, vp, vp, vp, vp]
+        l.zb_solve_channels_dev.argtypes = [vp, i, i, vp, vp, vp, vp, vp]
         l.zb_host_bvh_check.argtypes = [i, vp, i, vp, i, i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                         C.POINTER(C.c_int64)]
         l.zb_bvc_splat.argtypes = [vp, i, f, vp, f, f, f, f, f, vp, C.POINTER(C.c_int64)]
@@ -417,6 +419,22 @@ class Scene:
         pde = device_pde(self.ctx, pde)
         _check(lib().zb_solve(self._h, estimator, C.byref(pde), C.byref(settings), C.byref(ps), C.byref(ss),
                               C.byref(steps)), "zb_solve")
+        return steps.value
+
+    def solve_channels(self, estimator, pdes, settings, pts, stats_list):
+        """zb_solve_channels: the reference's vector-valued solve (T = Array<float, C>): one set of walks, one PdeDesc and
+        one abi.HostStatistics per channel. Returns the walk steps taken."""
+        if len(pdes) != len(stats_list) or not pdes:
+            raise ZombieError("solve_channels: one statistics object per PDE descriptor")
+        steps = C.c_int64(0)
+        ps = pts.as_struct()
+        dev = [device_pde(self.ctx, p) for p in pdes]
+        pde_arr = (abi.PdeDesc * len(dev))()
+        for k, d in enumerate(dev):
+            C.memmove(C.byref(pde_arr, k*C.sizeof(abi.PdeDesc)), C.byref(d), C.sizeof(abi.PdeDesc))
+        st_arr = (abi.Statistics * len(stats_list))(*[s.as_struct() for s in stats_list])
+        _check(lib().zb_solve_channels(self._h, estimator, len(dev), pde_arr, C.byref(settings), C.byref(ps), st_arr, C.byref(steps)),
+               "zb_solve_channels")
         return steps.value
 
     def rws_solve(self, pde, settings, samples, eval_pts, normal_offset, radius_clamp=0.0, kernel_regularization=0.0):

@@ -10,7 +10,9 @@ SamplePointList / create_sample_statistics_list / WalkOnSpheres / WalkOnStars â€
   the demo uses) describe a zb_grid_view or a constant; an arbitrary Python callable is accepted only for
   has_reflecting_boundary_conditions, which is evaluated on the host (partition_boundary_mesh). Assigning any other callable
   to source / dirichlet / robin / robin_coeff raises at solve time.
-* channels must be 1 (vector-valued T is out of scope).
+* channels > 1 (the reference's T = Array<float, channels>) runs as ONE set of walks with one data descriptor and one set of
+  statistics per channel (zb_solve_channels): constant callbacks take `channels` values, dense grids `channels` values per
+  cell (last axis), and the statistics getters return one value per channel.
 * walk_state_callback / terminal_contribution_callback / report_progress are accepted and ignored (no host callbacks inside
   walks); run_single_threaded is ignored.
 The list types are Python lists of numpy rows; convert_list_to_numpy_array gives the array."""
@@ -29,8 +31,8 @@ def _check_dim(dim):
 
 
 def _check_channels(channels):
-    if channels != 1:
-        raise ValueError("zombie_b200 solves scalar problems: channels must be 1, got %r" % (channels,))
+    if not isinstance(channels, (int, np.integer)) or not 1 <= channels <= 256:
+        raise ValueError("channels must be an integer in 1..256, got %r" % (channels,))
 
 
 # ---- list types -------------------------------------------------------------------------------
@@ -104,11 +106,18 @@ def _context():
 class ConstantCallback:
     """what Core.get_constant_*_callback returns"""
 
-    def __init__(self, value):
-        self.value = float(np.asarray(value).reshape(-1)[0])
+    def __init__(self, value, channels=1):
+        v = np.asarray(value, np.float64).reshape(-1)
+        if v.size not in (1, channels):
+            raise ValueError("constant callback: %d values for %d channels" % (v.size, channels))
+        self.values = np.broadcast_to(v, (channels,)).copy()
+        self.value = float(self.values[0])
+
+    def channel(self, c):
+        return ConstantCallback(self.values[c])
 
     def __call__(self, *args):
-        return self.value
+        return self.value if len(self.values) == 1 else self.values.copy()
 
 
 class DenseGridCallback:
@@ -116,11 +125,28 @@ class DenseGridCallback:
     samples over [grid_min, grid_max], last axis fastest, nearest-cell lookup or multilinear interpolation with edge clamping â€”
     as an abi.HostGrid: the same samples on the lattice of the cell centres."""
 
-    def __init__(self, data, shape, grid_min, grid_max, dim, enable_interpolation=False, aligned_data=None):
+    def __init__(self, data, shape, grid_min, grid_max, dim, enable_interpolation=False, aligned_data=None, channels=1):
         shape = [int(s) for s in np.asarray(shape).reshape(-1)[:dim]]
         self.dim = dim
-        self.grid = self._grid(data, shape, grid_min, grid_max, dim, enable_interpolation)
-        self.aligned_grid = None if aligned_data is None else self._grid(aligned_data, shape, grid_min, grid_max, dim, enable_interpolation)
+        # DenseGrid<float, CHANNELS, DIM>: `channels` values per cell, the channel index fastest
+        def split(d):
+            v = np.asarray(d, np.float32).reshape(-1)
+            if v.size != int(np.prod(shape))*channels:
+                raise ValueError("dense grid: %d values for shape %s x %d channels" % (v.size, shape, channels))
+            v = v.reshape(-1, channels)
+            return [self._grid(np.ascontiguousarray(v[:, c]), shape, grid_min, grid_max, dim, enable_interpolation) for c in range(channels)]
+        self.grids = split(data)
+        self.aligned_grids = None if aligned_data is None else split(aligned_data)
+        self.grid = self.grids[0]
+        self.aligned_grid = None if self.aligned_grids is None else self.aligned_grids[0]
+
+    def channel(self, c):
+        o = object.__new__(DenseGridCallback)
+        o.dim = self.dim
+        o.grids = [self.grids[c]]
+        o.aligned_grids = None if self.aligned_grids is None else [self.aligned_grids[c]]
+        o.grid, o.aligned_grid = o.grids[0], (None if o.aligned_grids is None else o.aligned_grids[0])
+        return o
 
     @staticmethod
     def _grid(data, shape, grid_min, grid_max, dim, enable_interpolation):
@@ -166,8 +192,9 @@ class DenseGridCallback:
 class _PDE:
     """zombie::PDE<float, DIM> (core/pde.h:20-45) with the attribute names of the binding (zombie_bindings.h)"""
 
-    def __init__(self, dim):
+    def __init__(self, dim, channels=1):
         self.dim = dim
+        self.channels = channels
         self.absorption_coeff = 0.0
         self.is_source_constant = False
         self.are_robin_conditions_pure_neumann = True
@@ -178,6 +205,20 @@ class _PDE:
         self.robin_coeff = ConstantCallback(0.0)
         self.has_reflecting_boundary_conditions = lambda x: False
         self.kelvin_origin = None   # set by KelvinTransform-style callers: solve on the inverted domain
+
+    def descriptors(self):
+        """one zb_pde_desc per value channel (zb_solve_channels): what steers the walk is shared, the data are the channel's"""
+        out = []
+        for c in range(self.channels):
+            one = _PDE(self.dim)
+            for f in ("absorption_coeff", "is_source_constant", "are_robin_conditions_pure_neumann", "are_robin_coeffs_nonnegative",
+                      "kelvin_origin", "robin_coeff"):
+                setattr(one, f, getattr(self, f))
+            for f in ("source", "dirichlet", "robin"):
+                cb = getattr(self, f)
+                setattr(one, f, cb.channel(c) if isinstance(cb, (ConstantCallback, DenseGridCallback)) and self.channels > 1 else cb)
+            out.append(one.descriptor())
+        return out
 
     def descriptor(self):
         """the zb_pde_desc of this PDE"""
@@ -410,25 +451,38 @@ class _SamplePoint:
 class _SampleStatistics:
     """zombie::SampleStatistics<float, DIM> (point_estimation/common.h:201-395): a view of row i of the SoA statistics"""
 
-    def __init__(self, owner, i):
+    def __init__(self, owner, i, others=()):
         self._o, self._i = owner, i
+        self._all = (owner,) + tuple(others)   # one HostStatistics per value channel
+
+    def _per_channel(self, f):
+        """a float for scalar problems, one entry per channel (the reference's T = Array<float, channels>) otherwise"""
+        if len(self._all) == 1:
+            return f(self._o)
+        return np.array([f(o) for o in self._all])
 
     def get_estimated_solution(self):
-        return float(self._o.solutionMean[self._i])
+        return self._per_channel(lambda o: float(o.solutionMean[self._i]))
 
     def get_estimated_solution_variance(self):
         n = int(self._o.nSolutionEstimates[self._i])
-        return float(self._o.solutionM2[self._i]/max(1, n - 1))
+        return self._per_channel(lambda o: float(o.solutionM2[self._i]/max(1, n - 1)))
 
     def get_estimated_gradient(self):
-        return self._o.gradientMean[self._i].copy()
+        """DIM entries (of T: with several channels, rows = coordinates, columns = channels)"""
+        if len(self._all) == 1:
+            return self._o.gradientMean[self._i].copy()
+        return np.stack([o.gradientMean[self._i] for o in self._all], axis=1)
 
     def get_estimated_gradient_variance(self):
         n = int(self._o.nGradientEstimates[self._i])
-        return self._o.gradientM2[self._i]/max(1, n - 1)
+        if len(self._all) == 1:
+            return self._o.gradientM2[self._i]/max(1, n - 1)
+        return np.stack([o.gradientM2[self._i]/max(1, n - 1) for o in self._all], axis=1)
 
     def get_estimated_derivative(self):
-        return float(self._o.totalDerivativeContribution[self._i]/max(1, int(self._o.nSolutionEstimates[self._i])))
+        n = max(1, int(self._o.nSolutionEstimates[self._i]))
+        return self._per_channel(lambda o: float(o.totalDerivativeContribution[self._i]/n))
 
     def get_solution_estimate_count(self):
         return int(self._o.nSolutionEstimates[self._i])
@@ -441,8 +495,9 @@ class _SampleStatistics:
 
 
 class _SampleStatisticsList:
-    def __init__(self, n, dim):
-        self.host = abi.HostStatistics(n, dim)
+    def __init__(self, n, dim, channels=1):
+        self.hosts = [abi.HostStatistics(n, dim) for _ in range(channels)]
+        self.host = self.hosts[0]
 
     def __len__(self):
         return self.host.n
@@ -450,7 +505,7 @@ class _SampleStatisticsList:
     def __getitem__(self, i):
         if not -self.host.n <= i < self.host.n:
             raise IndexError(i)
-        return _SampleStatistics(self.host, i % self.host.n)
+        return _SampleStatistics(self.host, i % self.host.n, self.hosts[1:])
 
 
 class _WalkSolver:
@@ -481,7 +536,12 @@ class _WalkSolver:
         for i, p in enumerate(sample_pts):   # generators that already advanced (progressive solves) continue where they stopped
             if p.rng_state is not None:
                 pts.rngState[i], pts.rngInc[i] = p.rng_state, p.rng_inc
-        self.last_walk_steps = q.scene().solve(self.estimator, pde.descriptor(), walk_settings, pts, sample_statistics.host)
+        if len(sample_statistics.hosts) != pde.channels:
+            raise ValueError("the PDE has %d value channels, the statistics %d" % (pde.channels, len(sample_statistics.hosts)))
+        if pde.channels == 1:
+            self.last_walk_steps = q.scene().solve(self.estimator, pde.descriptor(), walk_settings, pts, sample_statistics.host)
+        else:   # T = Array<float, channels>: one set of walks for all channels
+            self.last_walk_steps = q.scene().solve_channels(self.estimator, pde.descriptors(), walk_settings, pts, sample_statistics.hosts)
         for i, p in enumerate(sample_pts):
             p.rng_state, p.rng_inc = int(pts.rngState[i]), int(pts.rngInc[i])
             p.first_sphere_radius = float(pts.firstSphereRadius[i])
@@ -497,7 +557,7 @@ class Core:
     @staticmethod
     def PDE(*, dim, channels=1):
         _check_dim(dim); _check_channels(channels)
-        return _PDE(dim)
+        return _PDE(dim, channels)
 
     @staticmethod
     def GeometricQueries(domain_is_watertight=True, domain_min=None, domain_max=None, *, dim):
@@ -509,7 +569,7 @@ class Core:
     @staticmethod
     def get_constant_source_callback(value, *, dim, channels=1):
         _check_dim(dim); _check_channels(channels)
-        return ConstantCallback(value)
+        return ConstantCallback(value, channels)
 
     get_constant_dirichlet_callback = get_constant_source_callback
     get_constant_robin_callback = get_constant_source_callback
@@ -543,12 +603,12 @@ class Solvers:
     @staticmethod
     def SampleStatisticsList(n=0, *, dim, channels=1):
         _check_dim(dim); _check_channels(channels)
-        return _SampleStatisticsList(n, dim)
+        return _SampleStatisticsList(n, dim, channels)
 
     @staticmethod
     def create_sample_statistics_list(n, *, dim, channels=1):
         _check_dim(dim); _check_channels(channels)
-        return _SampleStatisticsList(n, dim)
+        return _SampleStatisticsList(n, dim, channels)
 
     @staticmethod
     def WalkOnSpheres(geometric_queries, walk_state_callback=None, terminal_contribution_callback=None, *, dim, channels=1):
@@ -704,30 +764,30 @@ class Utils:
         _refill(dist_to_reflecting_boundary, [float(v) for v in dr])
 
     @staticmethod
-    def _dense(data, args, dim, with_aligned):
+    def _dense(data, args, dim, with_aligned, channels=1):
         # (data, shape, min, max[, interp]) or (data, aligned data, shape, min, max[, interp])
         if with_aligned and len(args) >= 4 and np.asarray(args[1]).size == dim and np.asarray(args[0]).size != dim:
             aligned, shape, lo, hi = args[0], args[1], args[2], args[3]
             interp = bool(args[4]) if len(args) > 4 else False
-            return DenseGridCallback(data, shape, lo, hi, dim, interp, aligned)
+            return DenseGridCallback(data, shape, lo, hi, dim, interp, aligned, channels)
         shape, lo, hi = args[0], args[1], args[2]
         interp = bool(args[3]) if len(args) > 3 else False
-        return DenseGridCallback(data, shape, lo, hi, dim, interp)
+        return DenseGridCallback(data, shape, lo, hi, dim, interp, None, channels)
 
     @staticmethod
     def get_dense_grid_source_callback(data, *args, dim, channels=1):
         _check_dim(dim); _check_channels(channels)
-        return Utils._dense(data, args, dim, False)
+        return Utils._dense(data, args, dim, False, channels)
 
     @staticmethod
     def get_dense_grid_dirichlet_callback(data, *args, dim, channels=1):
         _check_dim(dim); _check_channels(channels)
-        return Utils._dense(data, args, dim, True)
+        return Utils._dense(data, args, dim, True, channels)
 
     @staticmethod
     def get_dense_grid_robin_callback(data, *args, dim, channels=1):
         _check_dim(dim); _check_channels(channels)
-        return Utils._dense(data, args, dim, True)
+        return Utils._dense(data, args, dim, True, channels)
 
     @staticmethod
     def get_dense_grid_robin_coefficient_callback(data, *args, dim):
