@@ -608,12 +608,15 @@ int solveRange(zb_scene *scene, SolveArgs& a, int n, bool anyGradient)
     ZB_CUDA(cudaMemsetAsync(a.taskCounter, 0, sizeof(unsigned long long), stream));
     if (a.nExtra > 0) { // per-task sums and records of the extra value channels
         const size_t per = (size_t)a.nExtra*nt;
-        ZB_CUDA(ctx->channelRecords.reserve(4*per*sizeof(float) + 256));
-        a.xRefl = ctx->channelRecords.as<float>();
+        ZB_CUDA(ctx->channelRecords.reserve(256 + 4*per*sizeof(float) + 256));
+        a.xRefl = reinterpret_cast<float *>(ctx->channelRecords.as<char>() + 256);
         a.xSrc = a.xRefl + per;
         a.xRecSolution = a.xSrc + per;
         a.xRecFirstSource = a.xRecSolution + per;
         ZB_CUDA(cudaMemsetAsync(a.xRefl, 0, 4*per*sizeof(float), stream));
+        ExtraChannelsView view{a.nExtra, totalTasks, a.extraPde, a.xRefl, a.xSrc, a.xRecSolution, a.xRecFirstSource};
+        ZB_CUDA(cudaMemcpyAsync(ctx->channelRecords.ptr, &view, sizeof(view), cudaMemcpyHostToDevice, stream)); // staged before the call returns
+        a.extra = ctx->channelRecords.as<ExtraChannelsView>();
     }
 
     ZB_CUDA(cudaFuncSetAttribute(preparePointsKernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));

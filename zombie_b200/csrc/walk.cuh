@@ -28,6 +28,14 @@ enum : int { kStatusSplitOverflow = 2 };
 constexpr int kSplitStack = 6;
 constexpr int kTaskChunk = 64; // tasks a warp reserves per global atomic
 
+// what the extra value channels of a solve need on the device, kept in DEVICE memory and handed around as one pointer
+struct ExtraChannelsView {
+    int n;
+    long long tasks;
+    const zb_pde_desc *pde;
+    float *refl, *src, *recSolution, *recFirstSource;
+};
+
 struct SolveArgs {
     BvhView absorbing, reflecting;
     int hasAbsorbing, hasReflecting, reflectingKind, estimator;
@@ -67,6 +75,7 @@ struct SolveArgs {
     const zb_statistics *extraStats;  // device, nExtra structs of device pointers
     float *xRefl, *xSrc;              // nExtra x totalTasks: reflecting-boundary / source terms of the task's current walk state
     float *xRecSolution, *xRecFirstSource; // nExtra x totalTasks: the task's record
+    const ExtraChannelsView *extra;   // the same as one device-resident struct; NULL for scalar solves (what the walk kernels test)
 };
 
 template <int DIM>
@@ -376,48 +385,55 @@ __global__ void __launch_bounds__(128) preparePointsKernel(SolveArgs a)
 // everything a lane keeps between steps
 // ---- extra value channels -----------------------------------------------------------------------------------------
 // Out of line: a scalar solve (nExtra = 0) never executes them and they stay out of the step kernel's hot instruction footprint.
+// They take ONE pointer to a device-resident view: a reference to SolveArgs would force every thread of the calling kernel to
+// copy the whole parameter block to local memory just to have an address to pass (measured: +1 KB of stack and -4 % walk
+// steps/s), and seven by-value fields cost the step kernel nine registers, i.e. one resident CTA per SM.
 // Each mirrors the expression of the scalar path it shadows, so channel c of a multi-channel solve equals a scalar solve of
 // that channel's PDE on the same generators up to the contraction of multiply-adds.
 template <int DIM>
-ZB_DEV_COLD void extraSourceTerm(const SolveArgs& a, long long task, Vec<DIM> p, float throughput, float gnorm)
+ZB_DEV_COLD void extraSourceTerm(const ExtraChannelsView *vp, long long task, Vec<DIM> p, float throughput, float gnorm)
 {
-    for (int c = 0; c < a.nExtra; c++) {
-        PdeEval<DIM> pde{a.extraPde[c]};
-        a.xSrc[(size_t)c*a.totalTasks + task] += throughput*(gnorm*pde.source(p));
+    const ExtraChannelsView v = *vp;
+    for (int c = 0; c < v.n; c++) {
+        PdeEval<DIM> pde{v.pde[c]};
+        v.src[(size_t)c*v.tasks + task] += throughput*(gnorm*pde.source(p));
     }
 }
 template <int DIM>
-ZB_DEV_COLD void extraRobinTerm(const SolveArgs& a, long long task, Vec<DIM> p, Vec<DIM> n, bool aligned, float weight, float pdf)
+ZB_DEV_COLD void extraRobinTerm(const ExtraChannelsView *vp, long long task, Vec<DIM> p, Vec<DIM> n, bool aligned, float weight, float pdf)
 {
-    for (int c = 0; c < a.nExtra; c++) {
-        PdeEval<DIM> pde{a.extraPde[c]};
-        a.xRefl[(size_t)c*a.totalTasks + task] += weight*pde.robin(p, n, aligned)/pdf;
+    const ExtraChannelsView v = *vp;
+    for (int c = 0; c < v.n; c++) {
+        PdeEval<DIM> pde{v.pde[c]};
+        v.refl[(size_t)c*v.tasks + task] += weight*pde.robin(p, n, aligned)/pdf;
     }
 }
 // the first ball of a gradient estimate (beginTask): the channel's first source term goes to its record and into its sums
 template <int DIM>
-ZB_DEV_COLD void extraFirstSource(const SolveArgs& a, long long task, Vec<DIM> p, float throughput, float gnorm)
+ZB_DEV_COLD void extraFirstSource(const ExtraChannelsView *vp, long long task, Vec<DIM> p, float throughput, float gnorm)
 {
-    for (int c = 0; c < a.nExtra; c++) {
-        PdeEval<DIM> pde{a.extraPde[c]};
+    const ExtraChannelsView v = *vp;
+    for (int c = 0; c < v.n; c++) {
+        PdeEval<DIM> pde{v.pde[c]};
         float first = gnorm*pde.source(p);
-        a.xRecFirstSource[(size_t)c*a.totalTasks + task] = first;
-        a.xSrc[(size_t)c*a.totalTasks + task] += throughput*first;
+        v.recFirstSource[(size_t)c*v.tasks + task] = first;
+        v.src[(size_t)c*v.tasks + task] += throughput*first;
     }
 }
 // a walk state ended: fold the channel's terminal contribution and sums into the task's record (not when the walk escaped)
 template <int DIM>
-ZB_DEV_COLD void extraFinishState(const SolveArgs& a, long long task, bool keep, bool project, Vec<DIM> p, float throughput)
+ZB_DEV_COLD void extraFinishState(const ExtraChannelsView *vp, long long task, bool keep, bool project, Vec<DIM> p, float throughput)
 {
-    for (int c = 0; c < a.nExtra; c++) {
-        size_t k = (size_t)c*a.totalTasks + task;
+    const ExtraChannelsView v = *vp;
+    for (int c = 0; c < v.n; c++) {
+        size_t k = (size_t)c*v.tasks + task;
         if (keep) {
             float terminal = 0.0f;
-            if (project) { PdeEval<DIM> pde{a.extraPde[c]}; terminal = pde.dirichlet(p); }
-            a.xRecSolution[k] += throughput*terminal + a.xRefl[k] + a.xSrc[k];
+            if (project) { PdeEval<DIM> pde{v.pde[c]}; terminal = pde.dirichlet(p); }
+            v.recSolution[k] += throughput*terminal + v.refl[k] + v.src[k];
         }
-        a.xRefl[k] = 0.0f;
-        a.xSrc[k] = 0.0f;
+        v.refl[k] = 0.0f;
+        v.src[k] = 0.0f;
     }
 }
 
@@ -558,7 +574,7 @@ ZB_DEV void beginTask(const SolveArgs& a, Lane<DIM>& L, long long task)
             L.gradSource = L.g.gradient(sourceRadius, sourcePt)/(sourcePdf*gnorm);
         }
         L.st.srcContrib += L.st.throughput*L.firstSource;
-        if (a.nExtra) extraFirstSource<DIM>(a, task, sourcePt, L.st.throughput, gnorm);
+        if (a.extra) extraFirstSource<DIM>(a.extra, task, sourcePt, L.st.throughput, gnorm);
     }
 
     const float *ub = strat + (DIM - 1)*(2*w + 1);
@@ -764,7 +780,7 @@ ZB_DEV StepResult stepBody(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *que
                 contribution = L.g.norm()*pde.source(sourcePt);
             }
             st.srcContrib += st.throughput*contribution;
-            if (a.nExtra) extraSourceTerm<DIM>(a, L.task, sourcePt, st.throughput, L.g.norm());
+            if (a.extra) extraSourceTerm<DIM>(a.extra, L.task, sourcePt, st.throughput, L.g.norm());
         }
         Vec<DIM> dir = uniformDirection<DIM>(L.rng);
         st.pt = st.pt + dir*L.distA;
@@ -835,7 +851,7 @@ ZB_DEV StepResult stepBody(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *que
                         float G = L.g.evaluate(r);
                         float h = pde.robin(bs.p, bs.n, aligned); // returnBoundaryNormalAlignedValue (walk_on_stars.h:242-244)
                         st.reflContrib += st.throughput*alpha*G*h/bs.pdf;
-                        if (a.nExtra) extraRobinTerm<DIM>(a, L.task, bs.p, bs.n, aligned, st.throughput*alpha*G, bs.pdf);
+                        if (a.extra) extraRobinTerm<DIM>(a.extra, L.task, bs.p, bs.n, aligned, st.throughput*alpha*G, bs.pdf);
                     }
                 }
             }
@@ -847,7 +863,7 @@ ZB_DEV StepResult stepBody(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *que
             Vec<DIM> sourcePt = L.g.sampleVolume(dir, L.rng, sourceRadius, sourcePdf);
             if (sourceRadius <= nextDist) {
                 st.srcContrib += st.throughput*(L.g.norm()*pde.source(sourcePt));
-                if (a.nExtra) extraSourceTerm<DIM>(a, L.task, sourcePt, st.throughput, L.g.norm());
+                if (a.extra) extraSourceTerm<DIM>(a.extra, L.task, sourcePt, st.throughput, L.g.norm());
             }
         }
 
@@ -921,10 +937,10 @@ ZB_DEV void finishState(const SolveArgs& a, Lane<DIM>& L, StepResult code, WalkS
         L.total += L.st.throughput*terminal + L.st.reflContrib + L.st.srcContrib;
         L.totalLength += L.st.walkLength;
         L.success = true;
-        if (a.nExtra) extraFinishState<DIM>(a, L.task, true, project && !a.ws.ignoreAbsorbingBoundaryContribution,
+        if (a.extra) extraFinishState<DIM>(a.extra, L.task, true, project && !a.ws.ignoreAbsorbingBoundaryContribution,
                                             a.hasAbsorbing ? L.proj : L.st.pt, L.st.throughput);
-    } else if (a.nExtra) {
-        extraFinishState<DIM>(a, L.task, false, false, L.st.pt, 0.0f);
+    } else if (a.extra) {
+        extraFinishState<DIM>(a.extra, L.task, false, false, L.st.pt, 0.0f);
     }
     if (L.nQueued > 0) {
         L.st = queue[--L.nQueued];

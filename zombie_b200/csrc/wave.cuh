@@ -464,10 +464,10 @@ ZB_DEV void finishStateWave(const SolveArgs& a, Lane<DIM>& L, StepResult code, W
         L.total += L.st.throughput*terminal + L.st.reflContrib + L.st.srcContrib;
         L.totalLength += L.st.walkLength;
         L.success = true;
-        if (a.nExtra) extraFinishState<DIM>(a, L.task, true, project && !a.ws.ignoreAbsorbingBoundaryContribution,
+        if (a.extra) extraFinishState<DIM>(a.extra, L.task, true, project && !a.ws.ignoreAbsorbingBoundaryContribution,
                                             a.hasAbsorbing ? L.proj : L.st.pt, L.st.throughput);
-    } else if (a.nExtra) {
-        extraFinishState<DIM>(a, L.task, false, false, L.st.pt, 0.0f);
+    } else if (a.extra) {
+        extraFinishState<DIM>(a.extra, L.task, false, false, L.st.pt, 0.0f);
     }
     if (L.nQueued > 0) {
         L.st = queue[--L.nQueued];

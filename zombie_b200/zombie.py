@@ -114,7 +114,7 @@ class ConstantCallback:
         self.value = float(self.values[0])
 
     def channel(self, c):
-        return ConstantCallback(self.values[c])
+        return ConstantCallback(self.values[c] if len(self.values) > 1 else self.values[0])
 
     def __call__(self, *args):
         return self.value if len(self.values) == 1 else self.values.copy()
