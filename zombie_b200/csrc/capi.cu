@@ -372,8 +372,10 @@ int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
     const int tailWalks = std::max(0, envInt("ZB_WAVE_TAIL", 8192))/nGroups;
     int tailPerSm = 0;
     if (tailWalks > 0) {
-        ZB_CUDA(cudaFuncSetAttribute(waveTailKernel<DIM, WOST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
-        ZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tailPerSm, waveTailKernel<DIM, WOST>, 128, kCoopSmem));
+        ZB_CUDA(cudaFuncSetAttribute(waveTailKernel<DIM, WOST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
+        ZB_CUDA(cudaFuncSetAttribute(waveTailKernel<DIM, WOST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
+        if (a.extra) ZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tailPerSm, waveTailKernel<DIM, WOST, true>, 128, kCoopSmem));
+        else ZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tailPerSm, waveTailKernel<DIM, WOST, false>, 128, kCoopSmem));
         tailPerSm = std::max(1, tailPerSm);
     }
 
@@ -496,7 +498,9 @@ int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
                     }
                     ctx->launches += starSplit ? 3 : (star ? 2 : 1);
                 }
-                waveStepKernel<DIM, WOST><<<blocksFor(G.nBound, 128), 128, 0, G.stream>>>(a, w, G.nBound);
+                // solves with extra value channels run their own instantiations: the scalar kernels carry none of that code
+                if (a.extra) waveStepKernel<DIM, WOST, true><<<blocksFor(G.nBound, 128), 128, 0, G.stream>>>(a, w, G.nBound);
+                else waveStepKernel<DIM, WOST, false><<<blocksFor(G.nBound, 128), 128, 0, G.stream>>>(a, w, G.nBound);
                 ZB_CUDA(cudaGetLastError());
                 size_t bytes = sortBytes; // upper bound of this group's scratch
                 ZB_CUDA(cub::DeviceRadixSort::SortPairs(G.sortTemp, bytes, w.keys, G.keysOut, G.orderA, G.orderB, G.nBound, 0, 32, G.stream));
@@ -520,7 +524,8 @@ int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
                     const int bound = std::min(G.nBound, (int)((alive + 127u)/128u*128u));
                     const int tailBlocks = std::max(1, std::min(ctx->smCount*tailPerSm/nGroups, blocksFor(bound*32, 128)));
                     w.order = G.orderA;
-                    waveTailKernel<DIM, WOST><<<tailBlocks, 128, kCoopSmem, G.stream>>>(a, w, bound, tailBlocks*4);
+                    if (a.extra) waveTailKernel<DIM, WOST, true><<<tailBlocks, 128, kCoopSmem, G.stream>>>(a, w, bound, tailBlocks*4);
+                    else waveTailKernel<DIM, WOST, false><<<tailBlocks, 128, kCoopSmem, G.stream>>>(a, w, bound, tailBlocks*4);
                     ZB_CUDA(cudaGetLastError());
                     ctx->launches += 1;
                     G.done = true; remaining--;
@@ -628,6 +633,8 @@ int solveRange(zb_scene *scene, SolveArgs& a, int n, bool anyGradient)
     ctx->lastGrid = 0;
     ctx->launches += 5; // count, 2 scans (init + scan kernels counted once each), prepare, reduce
     if (totalTasks > 0) {
+        if (a.extra && envInt("ZB_SCHEDULER_PERSISTENT", 0) != 0)
+            return fail(ZB_ERR_UNSUPPORTED, "zb_solve_channels: the persistent debug scheduler does not carry value channels");
         if (envInt("ZB_SCHEDULER_PERSISTENT", 0) == 0) {
             int rc = a.estimator == ZB_WALK_ON_STARS ? runWavefront<DIM, true>(scene, a, totalTasks) : runWavefront<DIM, false>(scene, a, totalTasks);
             if (rc != ZB_OK) return rc;

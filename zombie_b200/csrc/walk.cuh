@@ -471,7 +471,8 @@ ZB_DEV int findPoint(const long long *offsets, int n, long long task)
     return lo;
 }
 
-template <int DIM, bool WOST>
+// CH: the solve carries extra value channels (zb_solve_channels); the scalar instantiations contain none of their code
+template <int DIM, bool WOST, bool CH = false>
 ZB_DEV void beginTask(const SolveArgs& a, Lane<DIM>& L, long long task)
 {
     PdeEval<DIM> pde{a.pde};
@@ -574,7 +575,7 @@ ZB_DEV void beginTask(const SolveArgs& a, Lane<DIM>& L, long long task)
             L.gradSource = L.g.gradient(sourceRadius, sourcePt)/(sourcePdf*gnorm);
         }
         L.st.srcContrib += L.st.throughput*L.firstSource;
-        if (a.extra) extraFirstSource<DIM>(a.extra, task, sourcePt, L.st.throughput, gnorm);
+        if (CH) extraFirstSource<DIM>(a.extra, task, sourcePt, L.st.throughput, gnorm);
     }
 
     const float *ub = strat + (DIM - 1)*(2*w + 1);
@@ -760,7 +761,7 @@ ZB_DEV void rwsEmit(const SolveArgs& a, const Lane<DIM>& L)
 // The rest of one iteration of the while loop of WalkOnStars::walk (walk_on_stars.h:401-487) given the
 // star radius, or the whole iteration of WalkOnSpheres::walk (walk_on_spheres.h:237-288). The distance
 // to the absorbing boundary at the new position is left pending (L.needClosest).
-template <int DIM, bool WOST>
+template <int DIM, bool WOST, bool CH = false>
 ZB_DEV StepResult stepBody(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *queue, float starRadius)
 {
     PdeEval<DIM> pde{a.pde};
@@ -780,7 +781,7 @@ ZB_DEV StepResult stepBody(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *que
                 contribution = L.g.norm()*pde.source(sourcePt);
             }
             st.srcContrib += st.throughput*contribution;
-            if (a.extra) extraSourceTerm<DIM>(a.extra, L.task, sourcePt, st.throughput, L.g.norm());
+            if (CH) extraSourceTerm<DIM>(a.extra, L.task, sourcePt, st.throughput, L.g.norm());
         }
         Vec<DIM> dir = uniformDirection<DIM>(L.rng);
         st.pt = st.pt + dir*L.distA;
@@ -851,7 +852,7 @@ ZB_DEV StepResult stepBody(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *que
                         float G = L.g.evaluate(r);
                         float h = pde.robin(bs.p, bs.n, aligned); // returnBoundaryNormalAlignedValue (walk_on_stars.h:242-244)
                         st.reflContrib += st.throughput*alpha*G*h/bs.pdf;
-                        if (a.extra) extraRobinTerm<DIM>(a.extra, L.task, bs.p, bs.n, aligned, st.throughput*alpha*G, bs.pdf);
+                        if (CH) extraRobinTerm<DIM>(a.extra, L.task, bs.p, bs.n, aligned, st.throughput*alpha*G, bs.pdf);
                     }
                 }
             }
@@ -863,7 +864,7 @@ ZB_DEV StepResult stepBody(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *que
             Vec<DIM> sourcePt = L.g.sampleVolume(dir, L.rng, sourceRadius, sourcePdf);
             if (sourceRadius <= nextDist) {
                 st.srcContrib += st.throughput*(L.g.norm()*pde.source(sourcePt));
-                if (a.extra) extraSourceTerm<DIM>(a.extra, L.task, sourcePt, st.throughput, L.g.norm());
+                if (CH) extraSourceTerm<DIM>(a.extra, L.task, sourcePt, st.throughput, L.g.norm());
             }
         }
 
@@ -918,7 +919,7 @@ ZB_DEV StepResult walkStep(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *que
 
 
 // a walk state finished: fold it into the task total and start a queued split or emit the record
-template <int DIM, bool WOST>
+template <int DIM, bool WOST, bool CH = false>
 ZB_DEV void finishState(const SolveArgs& a, Lane<DIM>& L, StepResult code, WalkState<DIM> *queue)
 {
     PdeEval<DIM> pde{a.pde};
@@ -937,9 +938,9 @@ ZB_DEV void finishState(const SolveArgs& a, Lane<DIM>& L, StepResult code, WalkS
         L.total += L.st.throughput*terminal + L.st.reflContrib + L.st.srcContrib;
         L.totalLength += L.st.walkLength;
         L.success = true;
-        if (a.extra) extraFinishState<DIM>(a.extra, L.task, true, project && !a.ws.ignoreAbsorbingBoundaryContribution,
+        if (CH) extraFinishState<DIM>(a.extra, L.task, true, project && !a.ws.ignoreAbsorbingBoundaryContribution,
                                             a.hasAbsorbing ? L.proj : L.st.pt, L.st.throughput);
-    } else if (a.extra) {
+    } else if (CH) {
         extraFinishState<DIM>(a.extra, L.task, false, false, L.st.pt, 0.0f);
     }
     if (L.nQueued > 0) {

@@ -452,7 +452,7 @@ ZB_DEV void storeGradientFactors(const SolveArgs& a, const Lane<DIM>& L)
 }
 
 // finishState of the wavefront: as walk.cuh's, but the record's gradient factors were written when the task began
-template <int DIM, bool WOST>
+template <int DIM, bool WOST, bool CH = false>
 ZB_DEV void finishStateWave(const SolveArgs& a, Lane<DIM>& L, StepResult code, WalkState<DIM> *queue)
 {
     PdeEval<DIM> pde{a.pde};
@@ -464,9 +464,9 @@ ZB_DEV void finishStateWave(const SolveArgs& a, Lane<DIM>& L, StepResult code, W
         L.total += L.st.throughput*terminal + L.st.reflContrib + L.st.srcContrib;
         L.totalLength += L.st.walkLength;
         L.success = true;
-        if (a.extra) extraFinishState<DIM>(a.extra, L.task, true, project && !a.ws.ignoreAbsorbingBoundaryContribution,
+        if (CH) extraFinishState<DIM>(a.extra, L.task, true, project && !a.ws.ignoreAbsorbingBoundaryContribution,
                                             a.hasAbsorbing ? L.proj : L.st.pt, L.st.throughput);
-    } else if (a.extra) {
+    } else if (CH) {
         extraFinishState<DIM>(a.extra, L.task, false, false, L.st.pt, 0.0f);
     }
     if (L.nQueued > 0) {
@@ -492,7 +492,7 @@ ZB_DEV void finishStateWave(const SolveArgs& a, Lane<DIM>& L, StepResult code, W
 #ifndef ZB_STEP_MIN_BLOCKS
 #define ZB_STEP_MIN_BLOCKS 1 // resident CTAs per SM the step kernel is compiled for (1: no register cap, 129 registers -> 3 CTAs; A/B builds)
 #endif
-template <int DIM, bool WOST>
+template <int DIM, bool WOST, bool CH = false>
 __global__ void __launch_bounds__(128, ZB_STEP_MIN_BLOCKS) waveStepKernel(SolveArgs a, WaveSlots w, int nBound)
 {
 #if defined(__CUDA_ARCH__)
@@ -511,13 +511,13 @@ __global__ void __launch_bounds__(128, ZB_STEP_MIN_BLOCKS) waveStepKernel(SolveA
         loadLane<DIM>(a, w, slot, m, L);
         if (flags & kWfFinalProjection) {
             L.needsFinalProjection = false;
-            finishStateWave<DIM, WOST>(a, L, kMaxLength, queue);
+            finishStateWave<DIM, WOST, CH>(a, L, kMaxLength, queue);
         } else if (flags & kWfReached) {
-            finishStateWave<DIM, WOST>(a, L, kReached, queue);
+            finishStateWave<DIM, WOST, CH>(a, L, kReached, queue);
         } else if (!L.needClosest) {
             const Vec<DIM> ptBefore = L.st.pt;
             const float distBefore = L.distA;
-            StepResult r = stepBody<DIM, WOST>(a, L, queue, w.projStar[slot].w);
+            StepResult r = stepBody<DIM, WOST, CH>(a, L, queue, w.projStar[slot].w);
             if (r == kEscaped && w.debugEscapes)
                 printf("escaped: task %lld point %d step %d from (%.9g %.9g %.9g) distA %.9g ball %.9g proj (%.9g %.9g %.9g) to (%.9g %.9g %.9g)\n", L.task, L.point,
                        L.st.walkLength, ptBefore[0], ptBefore[1], DIM == 3 ? ptBefore[DIM - 1] : 0.0f, distBefore, L.g.R, L.proj[0], L.proj[1],
@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(128, ZB_STEP_MIN_BLOCKS) waveStepKernel(SolveA
                 L.needClosest = true;
             } else if (r != kContinue) {
                 L.needsFinalProjection = false;
-                finishStateWave<DIM, WOST>(a, L, r, queue);
+                finishStateWave<DIM, WOST, CH>(a, L, r, queue);
             }
         }
     }
@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(128, ZB_STEP_MIN_BLOCKS) waveStepKernel(SolveA
         base = __shfl_sync(full, base, 0);
         long long task = ((long long)base + __popc(need & ((1u << lane) - 1u)))*w.taskStride + w.taskFirst;
         if (want && task < a.totalTasks) {
-            beginTask<DIM, WOST>(a, L, task);
+            beginTask<DIM, WOST, CH>(a, L, task);
             if (L.gradient) storeGradientFactors<DIM>(a, L);
         }
     }
@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(128, ZB_STEP_MIN_BLOCKS) waveStepKernel(SolveA
 // order), spreads them over a persistent grid — one walk per warp when there are fewer walks than warps, the 32 lanes pooling
 // that walk's traversals — and every warp steps its walks until they end. The critical path becomes the longest walk's OWN
 // queries. It is the round-1 persistent loop (walkKernel) resumed from slot state, without a task queue.
-template <int DIM, bool WOST>
+template <int DIM, bool WOST, bool CH = false>
 __global__ void __launch_bounds__(128, ZB_WALK_MIN_BLOCKS) waveTailKernel(SolveArgs a, WaveSlots w, int nBound, int nWarps)
 {
 #if defined(__CUDA_ARCH__)
@@ -621,9 +621,9 @@ __global__ void __launch_bounds__(128, ZB_WALK_MIN_BLOCKS) waveTailKernel(SolveA
         if (L.active && !L.needClosest) {
             if (L.needsFinalProjection) {
                 L.needsFinalProjection = false;
-                finishStateWave<DIM, WOST>(a, L, kMaxLength, queue);
+                finishStateWave<DIM, WOST, CH>(a, L, kMaxLength, queue);
             } else if (!(L.distA > a.ws.epsilonShellForAbsorbingBoundary)) {
-                finishStateWave<DIM, WOST>(a, L, kReached, queue);
+                finishStateWave<DIM, WOST, CH>(a, L, kReached, queue);
             }
         }
         bool ready = L.active && !L.needClosest;
@@ -644,12 +644,12 @@ __global__ void __launch_bounds__(128, ZB_WALK_MIN_BLOCKS) waveTailKernel(SolveA
 
         // ---- the rest of the step, one thread per walk
         if (ready) {
-            StepResult r = stepBody<DIM, WOST>(a, L, queue, starRadius);
+            StepResult r = stepBody<DIM, WOST, CH>(a, L, queue, starRadius);
             if (!WOST && r == kMaxLength && L.needsFinalProjection && a.hasAbsorbing && !a.ws.ignoreAbsorbingBoundaryContribution) {
                 L.needClosest = true;
             } else if (r != kContinue) {
                 L.needsFinalProjection = false;
-                finishStateWave<DIM, WOST>(a, L, r, queue);
+                finishStateWave<DIM, WOST, CH>(a, L, r, queue);
             }
         }
     }

@@ -72,8 +72,12 @@ def lib():
         l.zb_star_radius.argtypes = [vp, i, vp, vp, vp, f, vp, vp]
         l.zb_solve.argtypes = [vp, i, vp, vp, vp, vp, vp]
         l.zb_solve_dev.argtypes = [vp, i, vp, vp, vp, vp, vp]
-        l.zb_solve_channels.argtypes = [vp, i, i, vp, vp, vp, vp, vp]
-        l.zb_solve_channels_dev.argtypes = [vp, i, i, vp, vp, vp, vp, vp]
+        try:
+            l.zb_solve_channels.argtypes = [vp, i, i, vp, vp, vp, vp, vp]
+            l.zb_solve_channels_dev.argtypes = [vp, i, i, vp, vp, vp, vp, vp]
+        except AttributeError:
+            if "ZOMBIE_B200_LIB" not in os.environ:   # only an older A/B variant library may lack them
+                raise
         l.zb_host_bvh_check.argtypes = [i, vp, i, vp, i, i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                         C.POINTER(C.c_int64)]
         l.zb_bvc_splat.argtypes = [vp, i, f, vp, f, f, f, f, f, vp, C.POINTER(C.c_int64)]
