@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define ZB_ABI_VERSION 2
+#define ZB_ABI_VERSION 3 /* 3: on-device builder, moving geometry, value channels (additions only) */
 
 enum zb_status {
     ZB_OK = 0,

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_abi_version():
-    assert native.lib().zb_abi_version() == 2   # 2: zb_pde_desc carries zb_grid_view members
+    assert native.lib().zb_abi_version() == 3   # 2: zb_pde_desc carries zb_grid_view members; 3: device builder, moving geometry, value channels
 
 
 def test_struct_layouts_match_header(tmp_path):
