@@ -346,6 +346,7 @@ constexpr int kMaxWaveGroups = 8;
 struct WaveGroup {
     WaveSlots w;
     uint32_t *orderA = nullptr, *orderB = nullptr, *keysOut = nullptr;
+    uint32_t *orderStep = nullptr, *stepKeys = nullptr, *stepKeysOut = nullptr; // the step kernel's own order (waveStepKeyKernel)
     unsigned int *live = nullptr;
     void *sortTemp = nullptr;
     cudaStream_t stream = nullptr;
@@ -370,6 +371,7 @@ int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
     const int stripeWarps = std::max(1, envInt("ZB_WAVE_STRIPE", 4096)/nGroups); // warps the tail of a solve spreads over (ZB_WAVE_STRIPE=1: compact)
     // live walks at or below which a group hands its walks to the barrier-free tail kernel (wave.cuh: waveTailKernel); 0: never
     const int tailWalks = std::max(0, envInt("ZB_WAVE_TAIL", 8192))/nGroups;
+    const bool stepSort = envInt("ZB_WAVE_STEP_SORT", 1) != 0; // the step kernel's own order, by star radius class (A/B: 0)
     int tailPerSm = 0;
     if (tailWalks > 0) {
         ZB_CUDA(cudaFuncSetAttribute(waveTailKernel<DIM, WOST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
@@ -412,6 +414,9 @@ int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
             G.keysOut = c.take<uint32_t>(n);
             G.orderA = c.take<uint32_t>(n);
             G.orderB = c.take<uint32_t>(n);
+            G.orderStep = c.take<uint32_t>(n);
+            G.stepKeys = c.take<uint32_t>(n);
+            G.stepKeysOut = c.take<uint32_t>(n);
             G.live = c.take<unsigned int>(kLiveRing*4); // per round in flight: live walks, the two query kernels' warp tickets, padding
             w.taskCounter = c.take<unsigned long long>(1);
             size_t bytes = 0;
@@ -498,12 +503,23 @@ int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
                     }
                     ctx->launches += starSplit ? 3 : (star ? 2 : 1);
                 }
+                // the step kernel takes the round's walks in the order of the work they will do (wave.cuh: waveStepKeyKernel)
+                const uint32_t *sortValues = G.orderA;
+                if (stepSort && star && G.round > 0) {
+                    waveStepKeyKernel<<<blocksFor(G.nBound, 256), 256, 0, G.stream>>>(w, G.nBound, G.stepKeys);
+                    ZB_CUDA(cudaGetLastError());
+                    size_t tmp = sortBytes;
+                    ZB_CUDA(cub::DeviceRadixSort::SortPairs(G.sortTemp, tmp, G.stepKeys, G.stepKeysOut, G.orderA, G.orderStep, G.nBound, 0, 8, G.stream));
+                    w.order = G.orderStep;
+                    sortValues = G.orderStep;
+                    ctx->launches += 2;
+                }
                 // solves with extra value channels run their own instantiations: the scalar kernels carry none of that code
                 if (a.extra) waveStepKernel<DIM, WOST, true><<<blocksFor(G.nBound, 128), 128, 0, G.stream>>>(a, w, G.nBound);
                 else waveStepKernel<DIM, WOST, false><<<blocksFor(G.nBound, 128), 128, 0, G.stream>>>(a, w, G.nBound);
                 ZB_CUDA(cudaGetLastError());
                 size_t bytes = sortBytes; // upper bound of this group's scratch
-                ZB_CUDA(cub::DeviceRadixSort::SortPairs(G.sortTemp, bytes, w.keys, G.keysOut, G.orderA, G.orderB, G.nBound, 0, 32, G.stream));
+                ZB_CUDA(cub::DeviceRadixSort::SortPairs(G.sortTemp, bytes, w.keys, G.keysOut, sortValues, G.orderB, G.nBound, 0, 32, G.stream));
                 std::swap(G.orderA, G.orderB);
                 ctx->launches += 2; // the step kernel and one library call (cub's own kernels are not counted)
             }

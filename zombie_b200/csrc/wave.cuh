@@ -656,6 +656,30 @@ __global__ void __launch_bounds__(128, ZB_WALK_MIN_BLOCKS) waveTailKernel(SolveA
 #endif
 }
 
+// The step kernel runs one thread per walk through per-thread traversals (ray cast, sampling descent, occlusion ray) whose
+// trip counts grow with the star radius: a warp lasts as long as the lane with the largest ball (3.9 of 32 lanes per instruction
+// in the hash order the cooperative query kernels want). This kernel classes every position of the round's order by the work its
+// walk will do there — 0: no step (the walk ends or waits), 1..: eight classes per octave of the star radius — and an 8-bit
+// stable radix sort (one pass) of the order by that class gives the step kernel warps of similar walks. The step kernel's
+// results do not depend on its order (no cooperative operation in it), and the next round's order is sorted from the task keys
+// again, so estimates stay bit-identical.
+__global__ void waveStepKeyKernel(WaveSlots w, int nBound, uint32_t *stepKeys)
+{
+    int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= nBound) return;
+    const int slot = (int)w.order[i];
+    const uint32_t flags = (uint32_t)w.meta[slot].w;
+    uint32_t key = 255u;
+    if (flags & kWfActive) {
+        key = 0u;
+        if (!(flags & (kWfNeedClosest | kWfReached | kWfFinalProjection))) {
+            float l = (log2f(fmaxf(w.projStar[slot].w, 4.8828125e-4f)) + 11.0f)*8.0f;
+            key = 1u + (uint32_t)fminf(fmaxf(l, 0.0f), 120.0f);
+        }
+    }
+    stepKeys[i] = key;
+}
+
 // slots of a new solve: none holds a walk, order = identity
 __global__ void waveResetKernel(WaveSlots w, uint32_t *order)
 {
