@@ -992,6 +992,38 @@ int64_t solveVector(int estimator, const GeometricQueries<DIM>& queries, const P
 }
 } // namespace detail
 
+// Vector-valued problems — the reference's T = Array<float, C>, the `channels` of its bindings (python/zombie_bindings.cpp:37-44;
+// core/pde.h:26-44: source / dirichlet / robin return T, absorptionCoeff and robinCoeff stay floats): one scalar PDE description
+// and one statistics vector per channel, ONE set of walks (zb_solve_channels). pdes must agree in everything that steers the
+// walk (absorptionCoeff, Robin coefficient, the three flags); samplePts are shared and their generators advance once.
+// Channel c of the result equals solve(pdes[c], ...) on the same generators up to the contraction of multiply-adds.
+template <size_t DIM>
+inline int64_t solveChannels(int estimator, const GeometricQueries<DIM>& queries, const std::vector<PDE<float, DIM>>& pdes,
+                             const WalkSettings& settings, const std::vector<int>& nWalks, std::vector<SamplePoint<float, DIM>>& samplePts,
+                             std::vector<std::vector<SampleStatistics<float, DIM>>>& statistics)
+{
+    const size_t nChannels = pdes.size(), nPoints = samplePts.size();
+    if (nChannels == 0) throw Error(ZB_ERR_INVALID_ARGUMENT, "solveChannels: no PDE given");
+    if (nWalks.size() != nPoints) throw Error(ZB_ERR_INVALID_ARGUMENT, "solveChannels: nWalks and samplePts differ in length");
+    statistics.resize(nChannels);
+    for (auto& s : statistics) if (s.size() != nPoints) { s.clear(); s.resize(nPoints); }
+    if (nPoints == 0) return 0;
+    std::vector<zb_pde_desc> descs;
+    for (const auto& p : pdes) descs.push_back(p.descriptor());
+    zb_walk_settings ws = settings.toAbi();
+    std::vector<detail::Marshal<float, DIM>> m(nChannels);
+    std::vector<zb_statistics> st(nChannels);
+    for (size_t c = 0; c < nChannels; c++) { m[c].gather(nWalks, samplePts, statistics[c]); st[c] = m[c].statistics(); }
+    zb_sample_points p = m[0].points();
+    int64_t steps = 0;
+    detail::check(zb_solve_channels(queries.scene(), estimator, (int)nChannels, descs.data(), &ws, &p, st.data(), &steps));
+    for (size_t c = nChannels; c-- > 0;) {                    // channel 0 last: it carries the advanced generators
+        std::vector<SamplePoint<float, DIM>> scratch = samplePts;
+        m[c].scatter(c == 0 ? samplePts : scratch, statistics[c]);
+    }
+    return steps;
+}
+
 template <typename T, size_t DIM>
 class WalkOnSpheres { // walk_on_spheres.h:26-44
 public:

@@ -3,6 +3,7 @@
 // binary file written by tests/test_cpp_api.py and writing the statistics back. Built by the tests with
 //   g++ -std=c++17 -I include tests/cpp/api_driver.cpp -L zombie_b200 -lzombie_b200
 // Exit codes: 0 ok, 3 = zombie_b200::Error (message on stderr), 2 = bad usage / IO.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -91,6 +92,7 @@ static int run(const Header& h, FILE *f, const char *outPath, bool extras)
     }
     std::vector<SampleStatistics<float, DIM>> statistics;
     WalkSettings settings(h.epsA, h.epsR, h.maxWalkLength, h.solveDoubleSided != 0);
+    const std::vector<SamplePoint<float, DIM>> initialPts = samplePts; // generators before any solve
 
     int64_t steps = 0;
     if (h.estimator == ZB_WALK_ON_SPHERES) {
@@ -119,6 +121,29 @@ static int run(const Header& h, FILE *f, const char *outPath, bool extras)
         }
         if (inside.back()) { fprintf(stderr, "far point reported inside the domain\n"); return 5; }
         if (queries.insideDomain(probe[0]) != (inside[0] != 0) || queries.insideDomain(far)) { fprintf(stderr, "single/batched insideDomain mismatch\n"); return 5; }
+    }
+
+    // Vector-valued solve through the same surface (the reference's T = Array<float, C>): two channels on one set of walks —
+    // the problem's own data and constant data; channel 0 must reproduce the scalar solve above on the same generators
+    if (extras) {
+        PDE<float, DIM> flat = pde;
+        flat.setConstant(0.25f, -0.5f, 0.125f, h.robinCoeff);
+        flat.isSourceConstant = pde.isSourceConstant;
+        flat.areRobinConditionsPureNeumann = pde.areRobinConditionsPureNeumann;
+        flat.areRobinCoeffsNonnegative = pde.areRobinCoeffsNonnegative;
+        std::vector<SamplePoint<float, DIM>> pts2 = initialPts;
+        std::vector<std::vector<SampleStatistics<float, DIM>>> channelStats;
+        int64_t steps2 = solveChannels<DIM>(h.estimator, queries, {pde, flat}, settings, nWalks, pts2, channelStats);
+        if (steps2 != steps) { fprintf(stderr, "channel solve took %lld steps, scalar solve %lld\n", (long long)steps2, (long long)steps); return 6; }
+        for (int i = 0; i < h.nPts; i++) {
+            float a = channelStats[0][i].getEstimatedSolution(), b = statistics[i].getEstimatedSolution();
+            if (std::fabs(a - b) > 2e-5f*std::max(1.0f, std::fabs(b)) || pts2[i].rng.state != samplePts[i].rng.state ||
+                channelStats[1][i].getSolutionEstimateCount() != statistics[i].getSolutionEstimateCount() ||
+                !std::isfinite(channelStats[1][i].getEstimatedSolution())) {
+                fprintf(stderr, "channel solve deviates at point %d: %g vs %g\n", i, a, b);
+                return 6;
+            }
+        }
     }
 
     // Boundary Value Caching splat and Reverse Walk on Stars through the same surface: a cache made of the solved

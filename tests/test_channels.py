@@ -160,3 +160,37 @@ def test_channel_argument_checks(ctx):
     scene.solve(abi.WALK_ON_SPHERES, first, abi.WalkSettings.default(), _points(scene, x, 4, abi.SOLUTION), st2)
     assert np.array_equal(st1.solutionMean, st2.solutionMean)
     scene.close()
+
+
+def test_device_resident_channels_match_host_buffers(ctx):
+    """zb_solve_channels_dev on torch tensors == zb_solve_channels on host arrays (same seeds -> identical statistics, every channel)"""
+    import torch
+    w = workloads.config3(subdivisions=3, n_points=256, n_walks=16)
+    scene = native.Scene(ctx, 3, **w.scene_kwargs())
+    pdes = [w.pde, _constant(w.pde, 0.7, -1.3, 0.4)]
+    pts = _points(scene, w.points, w.n_walks, w.quantity)
+    host = [abi.HostStatistics(pts.n, 3) for _ in pdes]
+    hp = _points(scene, w.points, w.n_walks, w.quantity)
+    steps_host = scene.solve_channels(w.estimator, pdes, w.settings, hp, host)
+    dev = torch.device("cuda", 0)
+    keys_p = ("pt", "normal", "directionForDerivative", "type", "estimationQuantity", "distToAbsorbingBoundary",
+              "distToReflectingBoundary", "estimateBoundaryNormalAligned", "nWalks", "rngState", "rngInc", "firstSphereRadius")
+    keys_s = ("solutionMean", "solutionM2", "gradientMean", "gradientM2", "totalFirstSourceContribution",
+              "totalDerivativeContribution", "nSolutionEstimates", "nGradientEstimates", "totalWalkLength", "totalSplits")
+    tp = {}
+    for k in keys_p:
+        a = getattr(pts, k)
+        tp[k] = torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a).to(dev)
+    ts = [{k: torch.from_numpy(getattr(abi.HostStatistics(pts.n, 3), k)).to(dev) for k in keys_s} for _ in pdes]
+    steps = torch.zeros(1, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    ps = abi.SamplePoints(pts.n, *[tp[k].data_ptr() for k in keys_p])
+    ss = [abi.Statistics(*[t[k].data_ptr() for k in keys_s]) for t in ts]
+    scene.solve_channels_dev(w.estimator, pdes, w.settings, ps, ss, steps.data_ptr())
+    ctx.synchronize()
+    assert int(steps.item()) == steps_host
+    for c in range(2):
+        for k in ("solutionMean", "solutionM2", "gradientMean", "totalWalkLength", "nSolutionEstimates", "totalDerivativeContribution"):
+            assert np.array_equal(ts[c][k].cpu().numpy(), getattr(host[c], k)), (c, k)
+    assert np.array_equal(tp["rngState"].cpu().numpy().view(np.uint64), hp.rngState)
+    scene.close()

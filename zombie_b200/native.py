@@ -441,6 +441,16 @@ class Scene:
                "zb_solve_channels")
         return steps.value
 
+    def solve_channels_dev(self, estimator, pdes, settings, pts_struct, stats_structs, steps_dev_ptr=None):
+        """zb_solve_channels_dev: the same with every array resident on the device (one abi.Statistics of device pointers per channel)"""
+        dev = [device_pde(self.ctx, p) for p in pdes]
+        pde_arr = (abi.PdeDesc * len(dev))()
+        for k, d in enumerate(dev):
+            C.memmove(C.byref(pde_arr, k*C.sizeof(abi.PdeDesc)), C.byref(d), C.sizeof(abi.PdeDesc))
+        st_arr = (abi.Statistics * len(stats_structs))(*stats_structs)
+        _check(lib().zb_solve_channels_dev(self._h, estimator, len(dev), pde_arr, C.byref(settings), C.byref(pts_struct), st_arr,
+                                           C.c_void_p(steps_dev_ptr)), "zb_solve_channels_dev")
+
     def rws_solve(self, pde, settings, samples, eval_pts, normal_offset, radius_clamp=0.0, kernel_regularization=0.0):
         """rws::ReverseWalkOnStarsSolver::solve (reverse_walk_solver.h:287-330): samples = abi.HostRwsSamples (rngState
         advances), eval_pts = abi.HostRwsEvalPoints (totals accumulate). Returns (walk steps, splat records)."""
