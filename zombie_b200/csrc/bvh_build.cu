@@ -166,12 +166,12 @@ int buildBvhOnDevice(zb_context *ctx, DeviceBvhStorage& s, int dim, int nPrim, b
 
     // ---- final arrays ----
     const int primFloats = dim == 3 ? 12 : 4;
-    ZB_CUDA(s.nodes.reserve((size_t)nNodes*sizeof(WideNode)));
-    ZB_CUDA(s.prims.reserve((size_t)primFloats*n*sizeof(float)));
-    ZB_CUDA(s.primIndex.reserve((size_t)n*sizeof(int32_t)));
+    ZB_CUDA(s.nodes.reserveExact((size_t)nNodes*sizeof(WideNode)));
+    ZB_CUDA(s.prims.reserveExact((size_t)primFloats*n*sizeof(float)));
+    ZB_CUDA(s.primIndex.reserveExact((size_t)n*sizeof(int32_t)));
     if (refl) {
-        ZB_CUDA(s.cones.reserve((size_t)nNodes*kWidth*sizeof(ChildCone)));
-        ZB_CUDA(s.adjacency.reserve((size_t)n*sizeof(PrimAdjacency)));
+        ZB_CUDA(s.cones.reserveExact((size_t)nNodes*kWidth*sizeof(ChildCone)));
+        ZB_CUDA(s.adjacency.reserveExact((size_t)n*sizeof(PrimAdjacency)));
     }
 
     mark("final arrays");

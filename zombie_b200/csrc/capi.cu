@@ -46,9 +46,9 @@ namespace {
 int uploadBvh(zb_context *ctx, DeviceBvhStorage& s, int snchSign)
 {
     const HostBvh& h = s.host;
-    ZB_CUDA(s.nodes.reserve(h.nodes.size()*sizeof(WideNode)));
-    ZB_CUDA(s.prims.reserve(h.prims.size()*sizeof(float)));
-    ZB_CUDA(s.primIndex.reserve(h.primIndex.size()*sizeof(int32_t)));
+    ZB_CUDA(s.nodes.reserveExact(h.nodes.size()*sizeof(WideNode)));
+    ZB_CUDA(s.prims.reserveExact(h.prims.size()*sizeof(float)));
+    ZB_CUDA(s.primIndex.reserveExact(h.primIndex.size()*sizeof(int32_t)));
     ZB_CUDA(cudaMemcpyAsync(s.nodes.ptr, h.nodes.data(), h.nodes.size()*sizeof(WideNode), cudaMemcpyHostToDevice, ctx->stream));
     ZB_CUDA(cudaMemcpyAsync(s.prims.ptr, h.prims.data(), h.prims.size()*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     ZB_CUDA(cudaMemcpyAsync(s.primIndex.ptr, h.primIndex.data(), h.primIndex.size()*sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -58,8 +58,8 @@ int uploadBvh(zb_context *ctx, DeviceBvhStorage& s, int snchSign)
     s.view.cones = nullptr;
     s.view.adjacency = nullptr;
     if (!h.cones.empty()) {
-        ZB_CUDA(s.cones.reserve(h.cones.size()*sizeof(ChildCone)));
-        ZB_CUDA(s.adjacency.reserve(h.adjacency.size()*sizeof(PrimAdjacency)));
+        ZB_CUDA(s.cones.reserveExact(h.cones.size()*sizeof(ChildCone)));
+        ZB_CUDA(s.adjacency.reserveExact(h.adjacency.size()*sizeof(PrimAdjacency)));
         ZB_CUDA(cudaMemcpyAsync(s.cones.ptr, h.cones.data(), h.cones.size()*sizeof(ChildCone), cudaMemcpyHostToDevice, ctx->stream));
         ZB_CUDA(cudaMemcpyAsync(s.adjacency.ptr, h.adjacency.data(), h.adjacency.size()*sizeof(PrimAdjacency), cudaMemcpyHostToDevice, ctx->stream));
         s.view.cones = s.cones.as<float4>();

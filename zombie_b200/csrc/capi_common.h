@@ -44,6 +44,14 @@ struct DeviceBuffer {
         if (e == cudaSuccess) capacity = want;
         return e;
     }
+    // exact size (long-lived arrays: the hierarchies of a scene), still grow-only
+    cudaError_t reserveExact(size_t bytes) {
+        if (bytes <= capacity) return cudaSuccess;
+        if (ptr) { cudaFree(ptr); ptr = nullptr; capacity = 0; }
+        cudaError_t e = cudaMalloc(&ptr, bytes);
+        if (e == cudaSuccess) capacity = bytes;
+        return e;
+    }
     template <typename T> T *as() const { return reinterpret_cast<T *>(ptr); }
 };
 

@@ -634,14 +634,25 @@ ZB_DEV bool intersectRay(const BvhView& bvh, const Vec<DIM>& o, const Vec<DIM>& 
                 tNear = fmaxf(tNear, fminf(t0, t1));
                 tFar = fminf(tFar, fmaxf(t0, t1));
             }
-            if (tNear <= tFar) insertKey(keys, (zb_float_as_uint(tNear) & ~7u) | (uint32_t)c);
+            if (tNear <= tFar) {
+                if (ANY_HIT) {
+                    // an occlusion test only asks WHETHER something is hit: the visiting order cannot change the answer,
+                    // so the children go to the stack as they come, without the sorted insertion of the closest-hit search
+                    if (sp < kStackSize) stack[sp++] = make_uint2(zb_float_as_uint(tNear) & ~7u, childRef(n, childMeta(n, c)));
+                    else if (status) zb_atomic_or(status, kStatusStackOverflow);
+                } else {
+                    insertKey(keys, (zb_float_as_uint(tNear) & ~7u) | (uint32_t)c);
+                }
+            }
         }
+        if (!ANY_HIT) {
 #pragma unroll
-        for (int c = 7; c >= 0; c--) {
-            uint32_t key = keys[c];
-            if (key != 0xffffffffu) {
-                if (sp < kStackSize) stack[sp++] = make_uint2(key, childRef(n, childMeta(n, key & 7u)));
-                else if (status) zb_atomic_or(status, kStatusStackOverflow);
+            for (int c = 7; c >= 0; c--) {
+                uint32_t key = keys[c];
+                if (key != 0xffffffffu) {
+                    if (sp < kStackSize) stack[sp++] = make_uint2(key, childRef(n, childMeta(n, key & 7u)));
+                    else if (status) zb_atomic_or(status, kStatusStackOverflow);
+                }
             }
         }
     }
