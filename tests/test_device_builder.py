@@ -243,10 +243,14 @@ def test_device_build_at_baseline_size(ctx):
     dev = native.Scene(ctx, 3, builder=abi.BVH_BUILDER_DEVICE, **kw)
     for which, key in ((abi.ABSORBING, "absorbing"), (abi.REFLECTING, "reflecting")):
         assert dev.validate(which, *kw[key]) == 0
-        hp, dp = host.build_profile(which), dev.build_profile(which)
-        print("build of %d primitives: host SAH %.0f ms, device %.2f ms; nodes %d vs %d" % (
-            len(kw[key][1]), hp["ms"], dp["ms"], host.stats(which)["nodes"], dev.stats(which)["nodes"]))
-        assert dp["ms"] < 0.25*hp["ms"]
+        hp, first = host.build_profile(which), dev.build_profile(which)
+        # the build a moving mesh pays every frame: buffers and scratch in place (the first build of a size also pays cudaMalloc)
+        dev.update_vertices(which, kw[key][0])
+        assert dev.validate(which, *kw[key]) == 0
+        dp = dev.build_profile(which)
+        print("build of %d primitives: host SAH %.0f ms, device %.2f ms (first build of this size %.1f ms); nodes %d vs %d" % (
+            len(kw[key][1]), hp["ms"], dp["ms"], first["ms"], host.stats(which)["nodes"], dev.stats(which)["nodes"]))
+        assert dp["ms"] < 0.1*hp["ms"]
     x = w.points
     for which in (abi.ABSORBING, abi.REFLECTING):
         for a, b in zip(host.closest_point(which, x), dev.closest_point(which, x)):
