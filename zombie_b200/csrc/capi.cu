@@ -380,6 +380,8 @@ int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
         else ZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tailPerSm, waveTailKernel<DIM, WOST, false>, 128, kCoopSmem));
         tailPerSm = std::max(1, tailPerSm);
     }
+    // the tail kernel steps ONE walk per lane of its resident grid: never hand it more walks than that
+    const int tailCapacity = tailWalks > 0 ? std::max(1, ctx->smCount*tailPerSm/nGroups)*128 : 0;
 
     const bool star = WOST && a.hasReflecting;
     // the star-radius query as two kernels (private phase, pooled phase: wave.cuh) or as one (ZB_WAVE_STAR_SPLIT=0)
@@ -477,6 +479,11 @@ int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
         ctx->launches += 1;
     }
 
+    // ZB_WAVE_TRACE=1 (group 0 only): CUDA-event time and position bound of every round on stderr after the solve
+    const bool traceRounds = envInt("ZB_WAVE_TRACE", 0) != 0;
+    std::vector<cudaEvent_t> traceEvents;
+    std::vector<int> traceBound;
+    if (traceRounds) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, groups[0].stream); traceEvents.push_back(e); }
     int remaining = nGroups, rounds = 0;
     while (remaining > 0) {
         for (int g = 0; g < nGroups; g++) {
@@ -522,6 +529,7 @@ int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
                 ZB_CUDA(cub::DeviceRadixSort::SortPairs(G.sortTemp, bytes, w.keys, G.keysOut, sortValues, G.orderB, G.nBound, 0, 32, G.stream));
                 std::swap(G.orderA, G.orderB);
                 ctx->launches += 2; // the step kernel and one library call (cub's own kernels are not counted)
+                if (traceRounds && g == 0) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, G.stream); traceEvents.push_back(e); traceBound.push_back(G.nBound); }
             }
             rounds = std::max(rounds, G.round);
             const int slot = 2*g + (G.batches & 1);
@@ -533,7 +541,7 @@ int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
                 ZB_CUDA(cudaEventSynchronize(ctx->evRound[prev]));
                 unsigned int alive = ctx->hostLive[prev];
                 if (alive == 0u) { G.done = true; remaining--; }
-                else if ((int)alive <= tailWalks && (int)alive < G.nSlots) {
+                else if ((int)alive <= std::min(tailWalks, tailCapacity) && (int)alive < G.nSlots) {
                     // fewer live walks than slots: the group's tasks have run out, and few enough are left that the round
                     // barriers cost more than they organise. One persistent launch steps them to their end (the walks alive
                     // NOW are a subset of the `alive` ones at the front of the order the last round left behind).
@@ -557,6 +565,16 @@ int runWavefront(zb_scene *scene, SolveArgs& a, long long totalTasks)
     for (int g = 1; g < nGroups; g++) {
         ZB_CUDA(cudaEventRecord(ctx->evRound[2*g], groups[g].stream));
         ZB_CUDA(cudaStreamWaitEvent(stream, ctx->evRound[2*g], 0));
+    }
+    if (traceRounds) {
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, groups[0].stream); traceEvents.push_back(e); traceBound.push_back(-1);
+        cudaEventSynchronize(e);
+        for (size_t k = 1; k < traceEvents.size(); k++) {
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, traceEvents[k - 1], traceEvents[k]);
+            fprintf(stderr, "[wave round] %4zu bound %8d %9.3f ms%s\n", k - 1, traceBound[k - 1], ms, traceBound[k - 1] < 0 ? " (tail kernel)" : "");
+        }
+        for (cudaEvent_t ev : traceEvents) cudaEventDestroy(ev);
     }
     ctx->lastRounds = rounds;
     ctx->lastGrid = nGroups;
