@@ -208,7 +208,8 @@ int zb_context_set_bvh_builder(zb_context *ctx, int builder);
  * fcpw Scene::updateObjectVertex + Scene::refit (fcpw/fcpw.h:76-107, aggregates/bvh.inl:549-600) and ReflectanceBvh::refit
  * (reflectance_boundary_bvh/bvh.h:271-312): the hierarchy — boxes, adjacency normals and silhouette marks, cones — is
  * rebuilt on the device from the mesh kept there (a rebuild costs about what a refit pass would and keeps tree quality
- * when the motion is large). Current Robin coefficients are kept. The _dev form reads positions from device memory. */
+ * when the motion is large). Current Robin coefficients are kept, and so is the bounding domain given at creation
+ * (domainMin / domainMax: make it large enough for the motion). The _dev form reads positions from device memory. */
 int zb_scene_update_vertices(zb_scene *scene, int boundary, const float *positions, int nVertices);
 int zb_scene_update_vertices_dev(zb_scene *scene, int boundary, const float *positions, int nVertices);
 /* duration of the last build of this boundary's hierarchy (HOST_SAH: host build + upload; DEVICE: the kernels, by
