@@ -185,4 +185,4 @@ def test_demo_engine_four_channels_are_the_colour_solution(ctx, engine, tmp_path
     lum = 0.299*colour[..., 0] + 0.587*colour[..., 1] + 0.114*colour[..., 2]
     assert np.abs(lum - gray)[visible1].max() < 5e-5
     assert np.all(colour[..., 3] == 0.0)
-    assert np.abs(colour[..., 0] - colour[..., 2])[visible1].max() > 0.05      # the channels do differ
+    assert np.abs(colour[..., 0] - colour[..., 2])[visible1].max() > 0.01      # the channels do differ (the Dirichlet texture is nearly gray: 5/255 at most)
