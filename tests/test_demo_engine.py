@@ -67,8 +67,9 @@ def test_fixture_and_texture_convention(engine, tmp_path):
     assert np.mean(got == want) > 0.995     # positions within rounding of a pixel edge may fall either way
 
 
-def run_demo(engine, tmp_path, channels):
-    cfg = json.loads(engine["config_wost"].tobytes().decode())
+def setup_problem(engine, tmp_path, channels, config="wost"):
+    """ModelProblem (model_problem.h:129-207) + the evaluation grid and its distance info (grid.h:22-40, demo.cpp:9-24)"""
+    cfg = json.loads(engine["config_" + config].tobytes().decode())
     solver_cfg, out_cfg, mp = cfg["solver"], cfg["output"], cfg["modelProblem"]
     dim = 2
     obj = str(tmp_path / "geometry.obj")
@@ -123,6 +124,30 @@ def run_demo(engine, tmp_path, channels):
     zombie.Utils.compute_dist_to_boundary(queries, solve_locations, da, dr, dim=dim)
     inside = queries.inside_domain_batch(grid).astype(bool)
     where = np.where(inside)[0]
+    meshes = tuple(np.array(a, t) for a, t in ((ap, np.float32), (ai, np.int32), (rp, np.float32), (ri, np.int32)))
+    return dict(cfg=cfg, pde=pde, queries=queries, bbox=bbox, grid=grid, da=np.array(da, np.float32), dr=np.array(dr, np.float32),
+                where=where, res=res, meshes=meshes)
+
+
+def to_image(problem, values, channels=1):
+    """saveGridValues (grid.h:43-85): image(j, i) = value at grid index i*res + j, zero outside the domain and inside the boundary mask"""
+    res, where = problem["res"], problem["where"]
+    dist = np.minimum(problem["da"], problem["dr"])
+    image = np.zeros((res, res) if channels == 1 else (res, res, channels), np.float32)
+    visible = np.zeros((res, res), bool)
+    keep = dist[where] >= problem["cfg"]["output"]["boundaryDistanceMask"]
+    i, j = np.divmod(where[keep], res)
+    image[j, i] = np.asarray(values)[keep]
+    visible[j, i] = True
+    return image, visible
+
+
+def run_demo(engine, tmp_path, channels):
+    """runWalkOnStars (demo.cpp:95-150) on the problem of engine/wost.json"""
+    P = setup_problem(engine, tmp_path, channels)
+    cfg, pde, queries, grid, da, dr, where, res = (P[k] for k in ("cfg", "pde", "queries", "grid", "da", "dr", "where", "res"))
+    solver_cfg, out_cfg, mp = cfg["solver"], cfg["output"], cfg["modelProblem"]
+    dim = 2
     zombie._SamplePoint._next_stream = 0x5EED
     sample_pts = zombie.Solvers.SamplePointList(
         [zombie.Solvers.SamplePoint(grid[k], np.zeros(dim), zombie.Solvers.SampleType.InDomain, zombie.Solvers.EstimationQuantity.Solution,
@@ -138,19 +163,64 @@ def run_demo(engine, tmp_path, channels):
     solver = zombie.Solvers.WalkOnStars(queries, dim=dim, channels=channels)
     solver.solve(pde, settings, zombie.IntList([solver_cfg["nWalks"]]*len(sample_pts)), sample_pts, stats)
 
-    # saveGridValues (grid.h:43-85): image(j, i) = value at index i*res + j, zero where masked
-    dist = np.minimum(np.array(da), np.array(dr))
-    shape_c = (res, res) if channels == 1 else (res, res, channels)
-    image, variance = np.zeros(shape_c, np.float32), np.zeros(shape_c, np.float32)
-    visible = np.zeros((res, res), bool)
-    for n, k in enumerate(where):
-        i, j = divmod(int(k), res)
-        if dist[k] < out_cfg["boundaryDistanceMask"]:
-            continue
-        image[j, i] = stats[n].get_estimated_solution()
-        variance[j, i] = stats[n].get_estimated_solution_variance()
-        visible[j, i] = True
+    n = len(where)
+    image, visible = to_image(P, np.array([stats[k].get_estimated_solution() for k in range(n)]), channels)
+    variance, _ = to_image(P, np.array([stats[k].get_estimated_solution_variance() for k in range(n)]), channels)
     return image, variance, visible, solver_cfg["nWalks"]
+
+
+class TextureData:
+    """host values of the demo's PDE callbacks at arrays of points (model_problem.h:230-262), for the cache bookkeeping of
+    zombie_b200.bvc: Image::get((x - bMin)/maxLength) of the luminance textures"""
+
+    def __init__(self, engine, bbox, robin_coeff):
+        self.lo, self.length = np.asarray(bbox[0], np.float64), float(np.max(bbox[1] - bbox[0]))
+        self.textures = {k: pfm.luminance(engine[k]) for k in ("source", "reflecting")}
+        self.mu = robin_coeff
+
+    def _get(self, name, x):
+        return texture_lookup(self.textures[name], (np.asarray(x, np.float64) - self.lo)/self.length).astype(np.float32)
+
+    def source(self, x):
+        return self._get("source", x)
+
+    def robin(self, x, n):
+        return self._get("reflecting", x)
+
+    def robin_coeff(self, x, n):
+        return np.full(len(x), self.mu, np.float32)
+
+
+def run_demo_bvc(engine, tmp_path):
+    """runBoundaryValueCaching (demo.cpp:199-319) on the problem of engine/bvc.json, over zombie_b200.bvc"""
+    from zombie_b200 import abi, bvc
+    P = setup_problem(engine, tmp_path, 1, "bvc")
+    cfg, pde, queries, bbox, grid, da, dr, where = (P[k] for k in ("cfg", "pde", "queries", "bbox", "grid", "da", "dr", "where"))
+    sc, mp = cfg["solver"], cfg["modelProblem"]
+    eps_a = sc["epsilonShellForAbsorbingBoundary"]
+    settings = zombie.Solvers.WalkSettings(eps_a, sc["epsilonShellForReflectingBoundary"], 1e-3, sc["russianRouletteThreshold"],
+                                           sc["splittingThreshold"], sc["maxWalkLength"], 0, sc["maxWalkLength"], mp["solveDoubleSided"], True, True,
+                                           False, sc["ignoreAbsorbingBoundaryContribution"], sc["ignoreReflectingBoundaryContribution"],
+                                           sc["ignoreSourceContribution"], False)
+    offset_a, offset_r = 5.0*eps_a, 0.0                      # normalOffsetFor{Absorbing,Reflecting}Boundary defaults (:240-242)
+    ap, ai, rp, ri = P["meshes"]
+    inside_box = lambda p: np.all((p >= bbox[0]) & (p <= bbox[1]), axis=1)    # queries.insideBoundingDomain (:181-187)
+    sa = bvc.UniformBoundarySampler(ap, ai, inside_solve_region=inside_box, seed=21)
+    sr = bvc.UniformBoundarySampler(rp, ri, inside_solve_region=inside_box, seed=22)
+    sa.initialize(offset_a, mp["solveDoubleSided"])
+    sr.initialize(offset_r, mp["solveDoubleSided"])
+    assert sc["ignoreSourceContribution"]                     # -> domainCacheSize = 0 (:271)
+    backend = bvc.NativeBackend(zombie._context(), queries.scene())
+    solver = bvc.BoundaryValueCachingSolver(backend, sa, sr, None, seed=23)
+    solver.generate_samples(sc["absorbingBoundaryCacheSize"], sc["reflectingBoundaryCacheSize"], 0, offset_a, offset_r)
+    desc = pde.descriptor()
+    solver.compute_sample_estimates(desc, settings, sc["nWalksForCachedSolutionEstimates"], sc["nWalksForCachedGradientEstimates"], abi.FLT_MAX,
+                                    TextureData(engine, bbox, mp["robinCoeff"]))
+    e = abi.HostBvcEvalPoints(grid[where], da[where], dr[where])
+    solver.splat(desc, e, sc["radiusClampForKernels"], 0.0, abi.FLT_MAX, offset_a, offset_r)
+    solver.estimate_solution_near_boundary(desc, settings, e, offset_a, offset_r, sc["nWalksForCachedSolutionEstimates"])
+    image, visible = to_image(P, e.solution)
+    return image, visible, solver
 
 
 @pytest.mark.gpu
@@ -186,3 +256,65 @@ def test_demo_engine_four_channels_are_the_colour_solution(ctx, engine, tmp_path
     assert np.abs(lum - gray)[visible1].max() < 5e-5
     assert np.all(colour[..., 3] == 0.0)
     assert np.abs(colour[..., 0] - colour[..., 2])[visible1].max() > 0.01      # the channels do differ (the Dirichlet texture is nearly gray: 5/255 at most)
+
+
+@pytest.mark.gpu
+def test_demo_engine_boundary_value_caching_matches_the_references_image(ctx, engine, tmp_path):
+    """engine/bvc.json against solutions/bvc.pfm. Both images are smooth (every pixel reads the same cache), so they differ by a
+    smooth error field rather than by pixel noise: the reference's own bvc and rws images differ by 0.018 RMS, its bvc and wost
+    images by 0.037 (the 128-walk noise of the latter)."""
+    image, visible, solver = run_demo_bvc(engine, tmp_path)
+    ref = engine["ref_bvc"][::-1]
+    assert (visible != (ref != 0.0)).mean() < 2e-3
+    both = visible & (ref != 0.0)
+    diff = (image - ref)[both]
+    assert float(np.sqrt(np.mean(diff**2))) < 0.03 and abs(float(diff.mean())) < 0.015, (np.sqrt(np.mean(diff**2)), diff.mean())
+    # and against the reference's Walk on Stars image of the same problem: within its pixel noise
+    wost = engine["ref_wost"][::-1]
+    d2 = (image - wost)[both]
+    assert float(np.sqrt(np.mean(d2**2))) < 0.05
+    c = solver.caches
+    assert len(c["absorbing"]) == 3072 and len(c["reflecting"]) == 3072 and "domain" not in c
+
+
+def run_demo_rws(engine, tmp_path):
+    """runReverseWalkOnStars (demo.cpp:330-454) on the problem of engine/rws.json: samples of the absorbing boundary displaced
+    inward by five epsilon walk backwards and splat onto the evaluation grid (zb_rws_solve)"""
+    from zombie_b200 import abi, bvc
+    P = setup_problem(engine, tmp_path, 1, "rws")
+    cfg, pde, queries, bbox, grid, where = (P[k] for k in ("cfg", "pde", "queries", "bbox", "grid", "where"))
+    sc, mp = cfg["solver"], cfg["modelProblem"]
+    eps_a = sc["epsilonShellForAbsorbingBoundary"]
+    settings = zombie.Solvers.WalkSettings(eps_a, sc["epsilonShellForReflectingBoundary"], 1e-3, sc["russianRouletteThreshold"],
+                                           sc["splittingThreshold"], sc["maxWalkLength"], 0, sc["maxWalkLength"], mp["solveDoubleSided"], False, False,
+                                           False, sc["ignoreAbsorbingBoundaryContribution"], sc["ignoreReflectingBoundaryContribution"],
+                                           sc["ignoreSourceContribution"], False)
+    offset_a = 5.0*eps_a
+    ap, ai, rp, ri = P["meshes"]
+    inside_box = lambda p: np.all((p >= bbox[0]) & (p <= bbox[1]), axis=1)
+    sa = bvc.UniformBoundarySampler(ap, ai, inside_solve_region=inside_box, seed=31)
+    sa.initialize(offset_a, mp["solveDoubleSided"])
+    assert sc["ignoreReflectingBoundaryContribution"] and sc["ignoreSourceContribution"]   # -> those sample counts are 0 (:398, 416)
+    s = sa.generate_samples(sc["absorbingBoundarySampleCount"], abi.ON_ABSORBING_BOUNDARY, offset_a)
+    scene = queries.scene()
+    da = scene.closest_point(abi.ABSORBING, s.pt, want_normal=False)[1]
+    dr = scene.closest_point(abi.REFLECTING, s.pt, want_normal=False)[1]
+    smp = abi.HostRwsSamples(s.pt, s.normal, s.type, s.pdf, da, dr, seed=0xE61E)
+    ev = abi.HostRwsEvalPoints(grid[where])
+    steps, records = scene.rws_solve(pde.descriptor(), settings, smp, ev, offset_a, radius_clamp=sc["radiusClampForKernels"], kernel_regularization=0.0)
+    assert steps > 0 and records >= steps
+    image, visible = to_image(P, ev.estimated_solution(smp.group_counts()))
+    return image, visible
+
+
+@pytest.mark.gpu
+def test_demo_engine_reverse_walk_on_stars_matches_the_references_image(ctx, engine, tmp_path):
+    """engine/rws.json (614,400 reverse walks) against solutions/rws.pfm; see the BVC test for the scale of the differences"""
+    image, visible = run_demo_rws(engine, tmp_path)
+    ref = engine["ref_rws"][::-1]
+    assert (visible != (ref != 0.0)).mean() < 2e-3
+    both = visible & (ref != 0.0)
+    diff = (image - ref)[both]
+    assert float(np.sqrt(np.mean(diff**2))) < 0.03 and abs(float(diff.mean())) < 0.015, (np.sqrt(np.mean(diff**2)), diff.mean())
+    d2 = (image - engine["ref_wost"][::-1])[both]
+    assert float(np.sqrt(np.mean(d2**2))) < 0.05
