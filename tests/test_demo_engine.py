@@ -204,10 +204,10 @@ def run_demo_bvc(engine, tmp_path):
                                            sc["ignoreSourceContribution"], False)
     offset_a, offset_r = 5.0*eps_a, 0.0                      # normalOffsetFor{Absorbing,Reflecting}Boundary defaults (:240-242)
     ap, ai, rp, ri = P["meshes"]
-    # queries.insideBoundingDomain (:181-187). The engine's outline has long segments lying ON the bounding box: whether their
-    # midpoints pass an exact comparison hangs on the last bit of the box's corner (8.8 % of the reflecting boundary drops out of
-    # the sampler when they do not, and the cache then misses that part of the boundary integral), hence the ulp-sized tolerance
-    inside_box = lambda p: np.all((p >= bbox[0] - 1e-5) & (p <= bbox[1] + 1e-5), axis=1)
+    # queries.insideBoundingDomain (:181-187), exact comparisons. The engine's outline has long segments lying ON the bounding box;
+    # they pass because computeBoundingBox pads the box by epsilon (without the padding 8.8 % of the reflecting boundary drops out
+    # of the sampler by an ulp and the cache misses that part of the boundary integral: -0.09 on the whole image)
+    inside_box = lambda p: np.all((p >= bbox[0]) & (p <= bbox[1]), axis=1)
     sa = bvc.UniformBoundarySampler(ap, ai, inside_solve_region=inside_box, seed=21)
     sr = bvc.UniformBoundarySampler(rp, ri, inside_solve_region=inside_box, seed=22)
     sa.initialize(offset_a, mp["solveDoubleSided"])
@@ -295,7 +295,7 @@ def run_demo_rws(engine, tmp_path):
                                            sc["ignoreSourceContribution"], False)
     offset_a = 5.0*eps_a
     ap, ai, rp, ri = P["meshes"]
-    inside_box = lambda p: np.all((p >= bbox[0] - 1e-5) & (p <= bbox[1] + 1e-5), axis=1)   # see run_demo_bvc
+    inside_box = lambda p: np.all((p >= bbox[0]) & (p <= bbox[1]), axis=1)   # see run_demo_bvc
     sa = bvc.UniformBoundarySampler(ap, ai, inside_solve_region=inside_box, seed=31)
     sa.initialize(offset_a, mp["solveDoubleSided"])
     assert sc["ignoreReflectingBoundaryContribution"] and sc["ignoreSourceContribution"]   # -> those sample counts are 0 (:398, 416)

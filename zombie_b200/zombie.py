@@ -674,9 +674,12 @@ class Utils:
     def compute_bounding_box(positions, make_square, scale, *, dim):
         """computeBoundingBox (fcpw_geometric_queries.h:292-317)"""
         p = _points(positions, dim)
-        cm = p.mean(axis=0, dtype=np.float32)
+        cm = (np.cumsum(p, axis=0, dtype=np.float32)[-1]/np.float32(len(p))).astype(np.float32)   # summed in order, like the reference
         q = (p - cm)*np.float32(scale) + cm
-        lo, hi = q.min(axis=0), q.max(axis=0)
+        # fcpw::BoundingBox::expandToInclude pads every point by epsilon (fcpw/core/bounding_volumes.h:45-49): geometry lying ON the
+        # box (the demo's engine outline does) is inside it for the exact comparisons of insideBoundingDomain
+        eps = np.float32(np.finfo(np.float32).eps)
+        lo, hi = (q - eps).min(axis=0), (q + eps).max(axis=0)
         if make_square:
             centre, half = 0.5*(lo + hi), np.float32(0.5*(hi - lo).max())
             lo, hi = centre - half, centre + half
