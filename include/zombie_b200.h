@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define ZB_ABI_VERSION 3 /* 3: on-device builder, moving geometry, value channels (additions only) */
+#define ZB_ABI_VERSION 3 /* 3: on-device builder, moving geometry, value channels, per-side Dirichlet data (zb_pde_desc grew at its end) */
 
 enum zb_status {
     ZB_OK = 0,
@@ -97,10 +97,16 @@ typedef struct zb_pde_desc {
     float kelvinOrigin[3];
     /* grids (pde.h:31-44 filled from sampled data, demo/model_problem.h:229-266); each optional */
     zb_grid_view sourceGrid;             /* pde.source(x) */
-    zb_grid_view dirichletGrid;          /* pde.dirichlet(x, .): both sides of a double-sided absorbing boundary read the same data */
+    zb_grid_view dirichletGrid;          /* pde.dirichlet(x, false) */
     zb_grid_view robinGrid;              /* pde.robin(x, n, false) */
     zb_grid_view robinAlignedGrid;       /* pde.robin(x, n, true): the normal-aligned side of a double-sided boundary; NULL = same as robinGrid */
     zb_grid_view robinCoeffGrid;         /* pde.robinCoeff(x, n, .) */
+    /* pde.dirichlet(x, true): the normal-aligned side of a double-sided absorbing boundary (walk_on_spheres.h:300-308,
+     * walk_on_stars.h:499-506: the side the closest primitive's normal points to, when WalkSettings::solveDoubleSided);
+     * grid with data == NULL and hasDirichletAlignedValue == 0: both sides read the same data */
+    zb_grid_view dirichletAlignedGrid;
+    float dirichletAlignedValue;         /* CONSTANT mode, when hasDirichletAlignedValue != 0 */
+    int32_t hasDirichletAlignedValue;
 } zb_pde_desc;
 
 /* SoA mirror of std::vector<zombie::SamplePoint<float,DIM>> (common.h:152-195). rngState/rngInc

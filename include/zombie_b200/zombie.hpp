@@ -195,7 +195,7 @@ private:
     zb_grid *grid = nullptr;
     zb_grid_view hostView, deviceView;
 };
-enum class PdeData { Source, Dirichlet, Robin, RobinNormalAligned, RobinCoeff };
+enum class PdeData { Source, Dirichlet, Robin, RobinNormalAligned, RobinCoeff, DirichletNormalAligned };
 
 // ------------------------------------------------------------------------------------------------
 // PDE (zombie/core/pde.h:20-79)
@@ -216,7 +216,7 @@ struct PDE {
         source = o.source; dirichlet = o.dirichlet; robin = o.robin; robinCoeff = o.robinCoeff;
         hasReflectingBoundaryConditions = o.hasReflectingBoundaryConditions;
         description = o.description; described = o.described;
-        for (int k = 0; k < 5; k++) grids[k] = o.grids[k];
+        for (int k = 0; k < 6; k++) grids[k] = o.grids[k];
         bindHasNonZeroRobinCoeff(); // captures `this` (pde.h:60)
         return *this;
     }
@@ -263,12 +263,12 @@ struct PDE {
     }
     // Backs one callback with sampled data (takes precedence over setManufactured()/setConstant() for that callback; a PDE
     // posed only through grids needs neither). Robin data for the normal-aligned side of a double-sided boundary goes to
-    // RobinNormalAligned.
+    // RobinNormalAligned, Dirichlet data for that side (walk_on_spheres.h:300-308) to DirichletNormalAligned.
     void setGrid(PdeData which, std::shared_ptr<const DataGrid> grid) {
         if (!described) { std::memset(&description, 0, sizeof(description)); description.mode = ZB_PDE_CONSTANT; }
         grids[(int)which] = grid;
-        zb_grid_view *views[5] = {&description.sourceGrid, &description.dirichletGrid, &description.robinGrid,
-                                  &description.robinAlignedGrid, &description.robinCoeffGrid};
+        zb_grid_view *views[6] = {&description.sourceGrid, &description.dirichletGrid, &description.robinGrid,
+                                  &description.robinAlignedGrid, &description.robinCoeffGrid, &description.dirichletAlignedGrid};
         if (grid) *views[(int)which] = grid->device(); else std::memset(views[(int)which], 0, sizeof(zb_grid_view));
         if (which == PdeData::Source && grid) isSourceConstant = false;
         if (which == PdeData::RobinCoeff && grid) areRobinConditionsPureNeumann = false;
@@ -291,7 +291,7 @@ struct PDE {
 private:
     zb_pde_desc description;
     bool described;
-    std::shared_ptr<const DataGrid> grids[5]; // indexed by PdeData
+    std::shared_ptr<const DataGrid> grids[6]; // indexed by PdeData
 
     zb_jet jet(const Vector<DIM>& x) const {
         float xx[3] = {x[0], x[1], DIM == 3 ? x[DIM - 1] : 0.0f};
@@ -304,9 +304,11 @@ private:
             zb_jet j = jet(x);
             return absorptionCoeff*j.u - j.lap;
         };
-        dirichlet = [this](const Vector<DIM>& x, bool) -> T {
+        dirichlet = [this](const Vector<DIM>& x, bool aligned) -> T {
+            if (aligned && grids[(int)PdeData::DirichletNormalAligned]) return (*grids[(int)PdeData::DirichletNormalAligned])(x);
             if (grids[(int)PdeData::Dirichlet]) return (*grids[(int)PdeData::Dirichlet])(x);
-            if (description.mode == ZB_PDE_CONSTANT) return description.dirichletValue;
+            if (description.mode == ZB_PDE_CONSTANT)
+                return aligned && description.hasDirichletAlignedValue ? description.dirichletAlignedValue : description.dirichletValue;
             return jet(x).u;
         };
         robin = [this](const Vector<DIM>& x, const Vector<DIM>& n, bool aligned) -> T {

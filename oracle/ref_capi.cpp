@@ -146,7 +146,9 @@ void buildPde(const zb_pde_desc& d, PDE<float, DIM>& pde)
         };
     } else {
         pde.source = [desc](const Vec<DIM>&) -> float { return desc.sourceValue; };
-        pde.dirichlet = [desc](const Vec<DIM>&, bool) -> float { return desc.dirichletValue; };
+        pde.dirichlet = [desc](const Vec<DIM>&, bool aligned) -> float {
+            return aligned && desc.hasDirichletAlignedValue ? desc.dirichletAlignedValue : desc.dirichletValue;
+        };
         pde.robin = [desc](const Vec<DIM>&, const Vec<DIM>&, bool) -> float { return desc.robinValue; };
     }
     pde.robinCoeff = [desc](const Vec<DIM>&, const Vec<DIM>&, bool) -> float { return desc.robinCoeff; };
@@ -170,7 +172,11 @@ void buildPde(const zb_pde_desc& d, PDE<float, DIM>& pde)
         }
     }
     if (d.sourceGrid.data) pde.source = [desc, at](const Vec<DIM>& x) -> float { return at(desc.sourceGrid, x); };
-    if (d.dirichletGrid.data) pde.dirichlet = [desc, at](const Vec<DIM>& x, bool) -> float { return at(desc.dirichletGrid, x); };
+    if (d.dirichletGrid.data) {
+        pde.dirichlet = [desc, at](const Vec<DIM>& x, bool aligned) -> float {
+            return at(aligned && desc.dirichletAlignedGrid.data ? desc.dirichletAlignedGrid : desc.dirichletGrid, x);
+        };
+    }
     if (d.robinGrid.data) {
         pde.robin = [desc, at](const Vec<DIM>& x, const Vec<DIM>&, bool aligned) -> float {
             return at(aligned && desc.robinAlignedGrid.data ? desc.robinAlignedGrid : desc.robinGrid, x);

@@ -112,12 +112,13 @@ class PdeDesc(C.Structure):
                 ("kelvin", C.c_int32),
                 ("kelvinOrigin", C.c_float * 3),
                 ("sourceGrid", GridView), ("dirichletGrid", GridView), ("robinGrid", GridView),
-                ("robinAlignedGrid", GridView), ("robinCoeffGrid", GridView)]
+                ("robinAlignedGrid", GridView), ("robinCoeffGrid", GridView),
+                ("dirichletAlignedGrid", GridView), ("dirichletAlignedValue", C.c_float), ("hasDirichletAlignedValue", C.c_int32)]
 
-    GRID_FIELDS = ("sourceGrid", "dirichletGrid", "robinGrid", "robinAlignedGrid", "robinCoeffGrid")
+    GRID_FIELDS = ("sourceGrid", "dirichletGrid", "robinGrid", "robinAlignedGrid", "robinCoeffGrid", "dirichletAlignedGrid")
 
     def set_grids(self, **grids):
-        """attaches HostGrid objects (source=, dirichlet=, robin=, robinAligned=, robinCoeff=). The structure then carries
+        """attaches HostGrid objects (source=, dirichlet=, dirichletAligned=, robin=, robinAligned=, robinCoeff=). The structure then carries
         HOST pointers (what the test oracle reads); native.Scene.solve uploads the grids and passes device pointers."""
         self.__dict__.setdefault("host_grids", {})
         for k, g in grids.items():

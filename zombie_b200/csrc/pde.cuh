@@ -37,9 +37,11 @@ struct PdeEval {
         zb_jet j = jet(x);
         return d.absorptionCoeff*j.u - j.lap;
     }
-    ZB_HOSTDEV float baseDirichlet(const Vec<DIM>& x) const {
+    // aligned: returnBoundaryNormalAlignedValue — the side of a double-sided absorbing boundary its normal points to
+    ZB_HOSTDEV float baseDirichlet(const Vec<DIM>& x, bool aligned) const {
+        if (aligned && d.dirichletAlignedGrid.data) return grid(d.dirichletAlignedGrid, x);
         if (d.dirichletGrid.data) return grid(d.dirichletGrid, x);
-        if (d.mode == ZB_PDE_CONSTANT) return d.dirichletValue;
+        if (d.mode == ZB_PDE_CONSTANT) return aligned && d.hasDirichletAlignedValue ? d.dirichletAlignedValue : d.dirichletValue;
         return jet(x).u;
     }
     // du/dn + mu u with n the boundary normal handed to the callback
@@ -70,11 +72,11 @@ struct PdeEval {
         if (DIM == 3) rPow *= sqrtf(r2);
         return baseSource(exteriorPoint(y, r2))/rPow;
     }
-    ZB_HOSTDEV float dirichlet(const Vec<DIM>& y) const {
-        if (!d.kelvin) return baseDirichlet(y);
+    ZB_HOSTDEV float dirichlet(const Vec<DIM>& y, bool aligned = false) const {
+        if (!d.kelvin) return baseDirichlet(y, aligned);
         float r2 = dot(y, y);
         float rPow = DIM == 3 ? sqrtf(r2) : 1.0f;
-        return baseDirichlet(exteriorPoint(y, r2))/rPow;
+        return baseDirichlet(exteriorPoint(y, r2), aligned)/rPow;
     }
     // aligned: returnBoundaryNormalAlignedValue of the reference's callback (walk_on_stars.h:242-244)
     ZB_HOSTDEV float robin(const Vec<DIM>& y, const Vec<DIM>& N, bool aligned = false) const {

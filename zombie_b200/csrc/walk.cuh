@@ -422,14 +422,14 @@ ZB_DEV_COLD void extraFirstSource(const ExtraChannelsView *vp, long long task, V
 }
 // a walk state ended: fold the channel's terminal contribution and sums into the task's record (not when the walk escaped)
 template <int DIM>
-ZB_DEV_COLD void extraFinishState(const ExtraChannelsView *vp, long long task, bool keep, bool project, Vec<DIM> p, float throughput)
+ZB_DEV_COLD void extraFinishState(const ExtraChannelsView *vp, long long task, bool keep, bool project, Vec<DIM> p, float throughput, bool aligned)
 {
     const ExtraChannelsView v = *vp;
     for (int c = 0; c < v.n; c++) {
         size_t k = (size_t)c*v.tasks + task;
         if (keep) {
             float terminal = 0.0f;
-            if (project) { PdeEval<DIM> pde{v.pde[c]}; terminal = pde.dirichlet(p); }
+            if (project) { PdeEval<DIM> pde{v.pde[c]}; terminal = pde.dirichlet(p, aligned); }
             v.recSolution[k] += throughput*terminal + v.refl[k] + v.src[k];
         }
         v.refl[k] = 0.0f;
@@ -458,6 +458,7 @@ struct Lane {
     bool keepDistA;   // ... but only proj is wanted: keep the caller-provided distA (sample point inside the epsilon shell)
     bool projValid;   // proj is a point of the absorbing boundary (the last distance query found one)
     bool needsFinalProjection; // Walk on Spheres: the walk ran out of steps and proj is that of the previous position
+    bool dirichletAligned;     // double-sided solves: st.pt lies on the side of the absorbing boundary its normal points to (proj's primitive)
 };
 
 template <int DIM>
@@ -502,6 +503,7 @@ ZB_DEV void beginTask(const SolveArgs& a, Lane<DIM>& L, long long task)
     L.keepDistA = false;
     L.projValid = false;
     L.needsFinalProjection = false;
+    L.dirichletAligned = false;
 
     if (!L.gradient) {
         // estimateSolution (walk_on_spheres.h:354-372; walk_on_stars.h:553-608)
@@ -646,6 +648,18 @@ ZB_DEV float closestSearchRadius2(const SolveArgs& a, const Lane<DIM>& L)
     return fminf(seeded, e*e*1.0001f);
 }
 
+// returnBoundaryNormalAlignedValue of the terminal contribution (walk_on_spheres.h:300-308, walk_on_stars.h:499-506):
+// solveDoubleSided && signedDistance > 0, the sign being that of (x - p) . n for the closest primitive's normal
+// (fcpw Interaction::signedDistance, interaction.h:32-34). prim: leaf-order index of the closest primitive, < 0 = none.
+template <int DIM>
+ZB_DEV bool onNormalAlignedSide(const SolveArgs& a, const Vec<DIM>& x, const Vec<DIM>& p, int prim)
+{
+    if (!a.ws.solveDoubleSided || prim < 0) return false;
+    Prim<DIM> pr;
+    pr.load(a.absorbing, (uint32_t)prim);
+    return dot(x - p, unitNormal<DIM>(pr)) > 0.0f;
+}
+
 // thread-per-query resolution of a pending distance query (host probe; the kernel does it cooperatively)
 template <int DIM, bool WOST = true>
 ZB_DEV void resolveClosest(const SolveArgs& a, Lane<DIM>& L)
@@ -653,6 +667,7 @@ ZB_DEV void resolveClosest(const SolveArgs& a, Lane<DIM>& L)
     int projPrim;
     float d = distToAbsorbing<DIM>(a, L.st.pt, L.proj, projPrim, closestSearchRadius2<DIM, WOST>(a, L));
     L.projValid = projPrim >= 0;
+    L.dirichletAligned = a.hasAbsorbing && onNormalAlignedSide<DIM>(a, L.st.pt, L.proj, projPrim);
     if (!L.keepDistA) L.distA = d;
     L.needClosest = false;
     L.keepDistA = false;
@@ -933,15 +948,15 @@ ZB_DEV void finishState(const SolveArgs& a, Lane<DIM>& L, StepResult code, WalkS
             // a Walk on Spheres walk that ran out of steps projects its LAST position (walk_on_spheres.h:294-308); the step
             // that moved it there left the distance query pending (the wavefront defers the finish by one round instead)
             if (!WOST && code == kMaxLength && L.needsFinalProjection) resolveClosest<DIM, WOST>(a, L);
-            terminal = pde.dirichlet(a.hasAbsorbing ? L.proj : L.st.pt);
+            terminal = pde.dirichlet(a.hasAbsorbing ? L.proj : L.st.pt, L.dirichletAligned);
         }
         L.total += L.st.throughput*terminal + L.st.reflContrib + L.st.srcContrib;
         L.totalLength += L.st.walkLength;
         L.success = true;
         if (CH) extraFinishState<DIM>(a.extra, L.task, true, project && !a.ws.ignoreAbsorbingBoundaryContribution,
-                                            a.hasAbsorbing ? L.proj : L.st.pt, L.st.throughput);
+                                            a.hasAbsorbing ? L.proj : L.st.pt, L.st.throughput, L.dirichletAligned);
     } else if (CH) {
-        extraFinishState<DIM>(a.extra, L.task, false, false, L.st.pt, 0.0f);
+        extraFinishState<DIM>(a.extra, L.task, false, false, L.st.pt, 0.0f, false);
     }
     if (L.nQueued > 0) {
         L.st = queue[--L.nQueued];
@@ -1027,6 +1042,7 @@ __global__ void __launch_bounds__(128, ZB_WALK_MIN_BLOCKS) walkKernel(SolveArgs 
                     if (!L.keepDistA) L.distA = hit.d;
                     L.proj = hit.p;
                     L.projValid = hit.prim >= 0;
+                    L.dirichletAligned = onNormalAlignedSide<DIM>(a, L.st.pt, hit.p, hit.prim);
                     L.needClosest = false;
                     L.keepDistA = false;
                 }
@@ -1095,7 +1111,9 @@ ZB_DEV long long reduceChannel(const SolveArgs& a, int i, const zb_pde_desc& pde
     if (quantity == ZB_SOLUTION && a.pts.type[i] == ZB_ON_ABSORBING_BOUNDARY) {
         if (nSol == 0) {
             float value = 0.0f;
-            if (!a.ws.ignoreAbsorbingBoundaryContribution) value = pde.dirichlet(loadVec<DIM>(a.pts.pt + (size_t)DIM*i));
+            // walk_on_spheres.h:331-337, walk_on_stars.h:529-535: the sample's own side flag
+            bool aligned = a.ws.solveDoubleSided && a.pts.estimateBoundaryNormalAligned && a.pts.estimateBoundaryNormalAligned[i];
+            if (!a.ws.ignoreAbsorbingBoundaryContribution) value = pde.dirichlet(loadVec<DIM>(a.pts.pt + (size_t)DIM*i), aligned);
             nSol += 1;
             welford(value, mean, m2, nSol);
             if (primary) a.pts.firstSphereRadius[i] = 0.0f;

@@ -43,7 +43,8 @@ enum : uint32_t {
     kWfActive = 1u, kWfNeedClosest = 2u, kWfKeepDistA = 4u, kWfFirstStep = 8u, kWfFlip = 16u, kWfOuterFlip = 32u,
     kWfSuccess = 64u, kWfGradient = 128u, kWfOnRefl = 256u, kWfYukawa = 512u, kWfNeedStar = 1024u, kWfReached = 2048u,
     kWfFinalProjection = 4096u, // Walk on Spheres ran out of steps: finish with kMaxLength once the projection of the last position is known
-    kWfProjValid = 8192u        // projStar.xyz is a point of the absorbing boundary (seeds the next distance query)
+    kWfProjValid = 8192u,       // projStar.xyz is a point of the absorbing boundary (seeds the next distance query)
+    kWfAligned = 16384u         // double-sided solves: the walk stands on the normal-aligned side of the absorbing boundary (its closest primitive)
 };
 
 struct WaveSlots {
@@ -174,7 +175,7 @@ ZB_DEV void waveClosestWarp(const SolveArgs& a, const WaveSlots& w, WarpShared& 
         float4 ps = qc ? w.projStar[slot] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         L.proj = vec3of<DIM>(ps);
         Vec<DIM> proj = L.st.pt;
-        bool found = false;
+        bool found = false, alignedSide = false;
         if (a.hasAbsorbing) {
             ClosestHit<DIM> hit;
             coopClosestPoint<DIM>(a.absorbing, ws, qc, L.st.pt, qc ? closestSearchRadius2<DIM, WOST>(a, L) : 0.0f, hit, a.status);
@@ -182,6 +183,7 @@ ZB_DEV void waveClosestWarp(const SolveArgs& a, const WaveSlots& w, WarpShared& 
                 if (!L.keepDistA) L.distA = hit.d;
                 proj = hit.p;
                 found = hit.prim >= 0;
+                alignedSide = onNormalAlignedSide<DIM>(a, L.st.pt, hit.p, hit.prim);
             }
         } else if (qc) {
             // no absorbing boundary: default of GeometricQueries::populate (geometric_queries.h:213-218), as distToAbsorbing
@@ -191,7 +193,7 @@ ZB_DEV void waveClosestWarp(const SolveArgs& a, const WaveSlots& w, WarpShared& 
             if (!L.keepDistA) L.distA = sqrtf(s);
         }
         if (qc) {
-            flags = (flags & ~(kWfNeedClosest | kWfKeepDistA | kWfProjValid)) | (found ? kWfProjValid : 0u);
+            flags = (flags & ~(kWfNeedClosest | kWfKeepDistA | kWfProjValid | kWfAligned)) | (found ? kWfProjValid : 0u) | (alignedSide ? kWfAligned : 0u);
             pd.w = L.distA;
             w.ptDist[slot] = pd;
             w.projStar[slot] = pack4<DIM>(proj, ps.w);
@@ -409,6 +411,7 @@ ZB_DEV void loadLane(const SolveArgs& a, const WaveSlots& w, int slot, const int
     L.st.onRefl = (flags & kWfOnRefl) != 0u;
     L.needsFinalProjection = false;
     L.projValid = (flags & kWfProjValid) != 0u;
+    L.dirichletAligned = (flags & kWfAligned) != 0u;
     L.g.init((flags & kWfYukawa) != 0u, a.pde.absorptionCoeff);
     L.firstSource = 0.0f;
     L.gradBoundary = vzero<DIM>();
@@ -422,7 +425,7 @@ ZB_DEV uint32_t storeLane(const WaveSlots& w, int slot, const Lane<DIM>& L)
                      (L.firstStep ? kWfFirstStep : 0u) | (L.flip ? kWfFlip : 0u) | (L.outerFlip ? kWfOuterFlip : 0u) |
                      (L.success ? kWfSuccess : 0u) | (L.gradient ? kWfGradient : 0u) | (L.st.onRefl ? kWfOnRefl : 0u) |
                      (L.g.yukawa ? kWfYukawa : 0u) | (L.needsFinalProjection ? kWfFinalProjection : 0u) |
-                     (L.projValid ? kWfProjValid : 0u);
+                     (L.projValid ? kWfProjValid : 0u) | (L.dirichletAligned ? kWfAligned : 0u);
     w.ptDist[slot] = pack4<DIM>(L.st.pt, L.distA);
     w.projStar[slot] = pack4<DIM>(L.proj, 0.0f);
     w.normalPrev[slot] = pack4<DIM>(L.st.normal, L.st.prevDist);
@@ -460,14 +463,14 @@ ZB_DEV void finishStateWave(const SolveArgs& a, Lane<DIM>& L, StepResult code, W
     if (code != kEscaped) {
         float terminal = 0.0f;
         bool project = WOST ? code == kReached : (code == kReached || code == kMaxLength);
-        if (project && !a.ws.ignoreAbsorbingBoundaryContribution) terminal = pde.dirichlet(a.hasAbsorbing ? L.proj : L.st.pt);
+        if (project && !a.ws.ignoreAbsorbingBoundaryContribution) terminal = pde.dirichlet(a.hasAbsorbing ? L.proj : L.st.pt, L.dirichletAligned);
         L.total += L.st.throughput*terminal + L.st.reflContrib + L.st.srcContrib;
         L.totalLength += L.st.walkLength;
         L.success = true;
         if (CH) extraFinishState<DIM>(a.extra, L.task, true, project && !a.ws.ignoreAbsorbingBoundaryContribution,
-                                            a.hasAbsorbing ? L.proj : L.st.pt, L.st.throughput);
+                                            a.hasAbsorbing ? L.proj : L.st.pt, L.st.throughput, L.dirichletAligned);
     } else if (CH) {
-        extraFinishState<DIM>(a.extra, L.task, false, false, L.st.pt, 0.0f);
+        extraFinishState<DIM>(a.extra, L.task, false, false, L.st.pt, 0.0f, false);
     }
     if (L.nQueued > 0) {
         L.st = queue[--L.nQueued];
@@ -610,6 +613,7 @@ __global__ void __launch_bounds__(128, ZB_WALK_MIN_BLOCKS) waveTailKernel(SolveA
                     if (!L.keepDistA) L.distA = hit.d;
                     L.proj = hit.p;
                     L.projValid = hit.prim >= 0;
+                    L.dirichletAligned = onNormalAlignedSide<DIM>(a, L.st.pt, hit.p, hit.prim);
                     L.needClosest = false;
                     L.keepDistA = false;
                 }

@@ -239,7 +239,7 @@ class _PDE:
                 if name == "robin" and cb.aligned_grid is not None:
                     grids["robinAligned"] = cb.aligned_grid
                 if name == "dirichlet" and cb.aligned_grid is not None:
-                    raise ValueError("zombie_b200 reads one Dirichlet value on both sides of an absorbing boundary (DESIGN.md section 5)")
+                    grids["dirichletAligned"] = cb.aligned_grid
             else:
                 raise TypeError("PDE.%s must come from get_dense_grid_*_callback or get_constant_*_callback: walks run on the "
                                 "device and cannot call back into Python" % name)
