@@ -30,7 +30,7 @@ def host_solve(tmp_path_factory):
 
 def run_host(exe, d, dim, kind, absorbing, reflecting, x, n_walks, family, params, sigma, mu, rr, split, seed,
              types=None, quantities=None, normals=None, directions=None, double_sided=False, kelvin_origin=None,
-             robin_bounds=None):
+             robin_bounds=None, sides=None, channels=None):
     hdr = struct.pack("<4i16f4fQ", dim, kind, n_walks, family, *(list(params) + [0.0]*(16 - len(params))), sigma, mu, rr, split, seed)
     open(os.path.join(d, "hdr.bin"), "wb").write(hdr)
     empty = (np.zeros((0, dim), np.float32), np.zeros((0, dim), np.int32))
@@ -48,6 +48,13 @@ def run_host(exe, d, dim, kind, absorbing, reflecting, x, n_walks, family, param
     np.array([1 if double_sided else 0], np.int32).tofile(os.path.join(d, "double_sided.bin"))
     np.array([0.0]*4 if kelvin_origin is None else [1.0] + [float(v) for v in kelvin_origin], np.float32).tofile(os.path.join(d, "kelvin.bin"))
     for name, arr in (("rmin", None if robin_bounds is None else robin_bounds[0]), ("rmax", None if robin_bounds is None else robin_bounds[1])):
+        path = os.path.join(d, name + ".bin")
+        if arr is not None:
+            np.ascontiguousarray(arr, np.float32).tofile(path)
+        elif os.path.exists(path):
+            os.remove(path)
+    # optional: constant Dirichlet data of the two sides of a double-sided boundary; parameter sets of extra value channels
+    for name, arr in (("sides", sides), ("channels", None if channels is None else np.asarray(channels, np.float32).reshape(-1, 16))):
         path = os.path.join(d, name + ".bin")
         if arr is not None:
             np.ascontiguousarray(arr, np.float32).tofile(path)
@@ -440,3 +447,39 @@ def test_device_ray_and_sampling_code_on_host_matches_reference(ref, tmp_path, d
     a = pos[idx[gprim[f], 0]]
     assert np.abs(((gpt[f] - a)*gn[f]).sum(axis=1)).max() < 1e-5   # the sample lies on the primitive it names
     rs.close()
+
+
+def test_value_channels_on_host_equal_scalar_runs(host_solve, tmp_path):
+    """zb_solve_channels' device code (walk.cuh: extra*Term, reduceChannel; the CH instantiations) on the CPU: two extra channels
+    on the walks of a Robin / screened-Poisson gradient solve equal scalar runs of their PDEs on the same generators"""
+    c = CASES["wost3d_robin_yukawa"]
+    whole, absorbing, reflecting = cases.mesh3d(2)
+    x = cases.query_points(24, 3, 0.6, seed=4)
+    k = 3**-0.5
+    extra = [[k, -k, k, 0.5] + [0.0]*12, [0.0, 0.6, 0.8, -2.0] + [0.0]*12]
+    q = np.full(len(x), abi.SOLUTION_AND_GRADIENT, np.int32)
+    d = str(tmp_path)
+    run_host(host_solve, d, 3, c["kind"], absorbing, reflecting, x, 16, c["family"], c["params"], c["sigma"], c["mu"], 0.0, abi.FLT_MAX, 77,
+             quantities=q, channels=extra)
+    multi = [np.fromfile(os.path.join(d, "out_c%d.bin" % j), np.float32).reshape(-1, 6) for j in range(2)]
+    for j, params in enumerate(extra):
+        st = run_host(host_solve, d, 3, c["kind"], absorbing, reflecting, x, 16, c["family"], params[:4], c["sigma"], c["mu"], 0.0, abi.FLT_MAX, 77,
+                      quantities=q)
+        assert np.array_equal(multi[j][:, 2].astype(np.int32), st.nSolutionEstimates)
+        assert np.allclose(multi[j][:, 0], st.solutionMean, rtol=0, atol=2e-5*max(1.0, float(np.abs(st.solutionMean).max())))
+        assert np.allclose(multi[j][:, 1], st.solutionM2, rtol=1e-3, atol=1e-5)
+    assert not np.allclose(multi[0][:, 0], multi[1][:, 0])
+
+
+def test_two_sided_dirichlet_data_on_host_match_reference(host_solve, tmp_path, ref):
+    """the side flag of double-sided solves (walk.cuh: onNormalAlignedSide -> pde.dirichlet(x, aligned)) on the CPU against the
+    compiled reference: constant data 1 / 3 on the two sides of a closed curve"""
+    from tests.test_double_sided_dirichlet import constant_pde, problem, scene_kwargs, solve
+    pos, seg, x, inside = problem(n=300)
+    r = solve(ref.RefScene(2, **scene_kwargs(pos, seg)), constant_pde(), x, n_walks=16)
+    st = run_host(host_solve, str(tmp_path), 2, abi.REFLECTING_NONE, (pos, seg), None, x, 16, abi.SOL_CUBIC_2D, [0.0]*4, 0.0, 0.0, 0.0, abi.FLT_MAX, 5,
+                  double_sided=True, sides=[1.0, 3.0])
+    ok = (st.nSolutionEstimates > 0) & (r.nSolutionEstimates > 0)
+    ins, out = st.solutionMean[inside & ok], st.solutionMean[~inside & ok]
+    assert (ins == 1.0).mean() > 0.8 and (ins < 1.5).all() and (out == 3.0).mean() > 0.8 and (out > 2.5).all()
+    assert abs(out.mean() - r.solutionMean[~inside & ok].mean()) < 0.03 and abs(ins.mean() - r.solutionMean[inside & ok].mean()) < 0.03

@@ -4,7 +4,9 @@
 //   nvcc -std=c++17 -O2 -DZB_HOST_STATS -Xcompiler -ffp-contract=off -o /tmp/host_solve tools/host_solve.cu zombie_b200/csrc/wide_bvh.cpp
 //   /tmp/host_solve <dir>   reads <dir>/{hdr,apos,aidx,rpos,ridx,pts}.bin and, when present, per-point
 //   {type,quantity}.bin (int32) and {normal,dir}.bin (float, dim per point); writes <dir>/out.bin
-//   (mean, m2, n, total walk length, derivative sum, firstSphereRadius per point)
+//   (mean, m2, n, total walk length, derivative sum, firstSphereRadius per point). Optional: sides.bin (two floats: constant
+//   Dirichlet data of the two sides of a double-sided absorbing boundary, no source) and channels.bin (16 floats per extra
+//   value channel: the parameters of its solution family; its estimates go to out_c<k>.bin as mean, m2, n, gradient mean)
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -97,8 +99,22 @@ int run(const std::string& dir, const Header& h)
         pde.absorptionCoeff = 0.0f;
         if (DIM == 3) { pde.areRobinConditionsPureNeumann = 0; pde.areRobinCoeffsNonnegative = 0; }
     }
+    // optional: two-sided constant Dirichlet data (zb_pde_desc.dirichletAlignedValue)
+    auto sidesIn = rd<float>(dir + "/sides.bin", true);
+    if (sidesIn.size() == 2) {
+        pde.mode = ZB_PDE_CONSTANT;
+        pde.isSourceConstant = 1;
+        pde.dirichletValue = sidesIn[0];
+        pde.dirichletAlignedValue = sidesIn[1];
+        pde.hasDirichletAlignedValue = 1;
+    }
     a.pde = pde;
     a.status = &status;
+    // optional: extra value channels riding on the walks (zb_solve_channels)
+    auto channelsIn = rd<float>(dir + "/channels.bin", true);
+    const int nExtra = (int)channelsIn.size()/16;
+    std::vector<zb_pde_desc> extraPde(nExtra, pde);
+    for (int c = 0; c < nExtra; c++) for (int k = 0; k < 16; k++) extraPde[c].params[k] = channelsIn[16*c + k];
 
     std::vector<float> nrm(DIM*nPts, 0.0f), dA(nPts), dR(nPts, kMaxFloat), fsr(nPts, 0.0f);
     std::vector<int> type(nPts, 0), quantity(nPts, ZB_SOLUTION), nWalks(nPts, h.nWalks);
@@ -135,17 +151,41 @@ int run(const std::string& dir, const Header& h)
     a.recLength = recLen.data(); a.recFlags = recFlags.data(); a.anyGradient = 1;
     long long steps = 0;
     a.walkSteps = &steps;
+    std::vector<float> xRefl((size_t)nExtra*total, 0.0f), xSrc(xRefl), xRecSol(xRefl), xRecFS(xRefl);
+    ExtraChannelsView view{nExtra, total, extraPde.data(), xRefl.data(), xSrc.data(), xRecSol.data(), xRecFS.data()};
+    if (nExtra) {
+        a.nExtra = nExtra; a.extraPde = extraPde.data();
+        a.xRefl = xRefl.data(); a.xSrc = xSrc.data(); a.xRecSolution = xRecSol.data(); a.xRecFirstSource = xRecFS.data();
+        a.extra = &view;
+    }
     for (int i = 0; i < nPts; i++) preparePoint<DIM>(a, i);
     for (long long t = 0; t < total; t++) {
         Lane<DIM> L; L.active = false;
         WalkState<DIM> queue[kSplitStack];
-        if (hasR) {
+        if (nExtra && hasR) {
+            beginTask<DIM, true, true>(a, L, t);
+            while (L.active) { StepResult r = walkStep<DIM, true, true>(a, L, queue); if (r != kContinue) finishState<DIM, true, true>(a, L, r, queue); }
+        } else if (nExtra) {
+            beginTask<DIM, false, true>(a, L, t);
+            while (L.active) { StepResult r = walkStep<DIM, false, true>(a, L, queue); if (r != kContinue) finishState<DIM, false, true>(a, L, r, queue); }
+        } else if (hasR) {
             beginTask<DIM, true>(a, L, t);
             while (L.active) { StepResult r = walkStep<DIM, true>(a, L, queue); if (r != kContinue) finishState<DIM, true>(a, L, r, queue); }
         } else {
             beginTask<DIM, false>(a, L, t);
             while (L.active) { StepResult r = walkStep<DIM, false>(a, L, queue); if (r != kContinue) finishState<DIM, false>(a, L, r, queue); }
         }
+    }
+    // the extra channels fold the same walk records with their own sums (before channel 0 advances the generators)
+    for (int c = 0; c < nExtra; c++) {
+        std::vector<float> cm(nPts, 0), cm2(nPts, 0), cgm(DIM*nPts, 0), cgm2(DIM*nPts, 0), cfs(nPts, 0), cdc(nPts, 0);
+        std::vector<int> cns(nPts, 0), cng(nPts, 0), cwl(nPts, 0), csp(nPts, 0);
+        zb_statistics cs{cm.data(), cm2.data(), cgm.data(), cgm2.data(), cfs.data(), cdc.data(), cns.data(), cng.data(), cwl.data(), csp.data()};
+        for (int i = 0; i < nPts; i++)
+            if (quantity[i] != ZB_SKIP) reduceChannel<DIM>(a, i, extraPde[c], cs, xRecSol.data() + (size_t)c*total, xRecFS.data() + (size_t)c*total, false);
+        FILE *fc = fopen((dir + "/out_c" + std::to_string(c) + ".bin").c_str(), "wb");
+        for (int i = 0; i < nPts; i++) { float rec[6] = {cm[i], cm2[i], (float)cns[i], cgm[DIM*i], cgm[DIM*i + 1], DIM == 3 ? cgm[DIM*i + DIM - 1] : 0.0f}; fwrite(rec, 4, 6, fc); }
+        fclose(fc);
     }
     for (int i = 0; i < nPts; i++) steps += reducePoint<DIM>(a, i);
     printf("points %d walks %lld steps %lld status %d\n", nPts, total, steps, status);

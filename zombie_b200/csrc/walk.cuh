@@ -919,7 +919,7 @@ ZB_DEV StepResult stepBody(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *que
 }
 
 // thread-per-query version of one whole step (host probe)
-template <int DIM, bool WOST>
+template <int DIM, bool WOST, bool CH = false>
 ZB_DEV StepResult walkStep(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *queue)
 {
     if (L.needClosest) resolveClosest<DIM, WOST>(a, L);
@@ -928,7 +928,7 @@ ZB_DEV StepResult walkStep(const SolveArgs& a, Lane<DIM>& L, WalkState<DIM> *que
     if (WOST && stepStarPrologue<DIM>(a, L, starRadius, r2max)) {
         starRadius = shrunkStarRadius<DIM>(a, L.st.pt, L.distA, L.flip);
     }
-    return stepBody<DIM, WOST>(a, L, queue, starRadius);
+    return stepBody<DIM, WOST, CH>(a, L, queue, starRadius);
 }
 
 
