@@ -73,7 +73,8 @@ def main():
     line = {"metric": "bvc splat pairs/sec", "value": pairs/(best*1e-3), "unit": "pairs/s", "ms": best, "n_eval": n, "n_samples": args.samples,
             "sigma": args.sigma, "roofline": {"bound": "fp32", "achieved": flops/(best*1e-3)/1e12, "peak": peak, "unit": "TFLOP/s",
                                               "frac": flops/(best*1e-3)/1e12/peak, "flop_per_pair": 80, "sm": sm}}
-    # parity + CPU baseline on a bounded sample
+    # cpu_baseline leg (like bench.py's): the reference's splat on a bounded sample of the same evaluation points, timed on the host;
+    # its values double as a spot check of the device result
     from oracle import ref
     if ref.available():
         k = min(args.ref_eval, n)

@@ -1,6 +1,6 @@
 """Diagnostic run on a GPU box: queries and estimators of libzombie_b200.so against the reference oracle."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from zombie_b200 import abi, native, procedural as P
 from oracle import ref

@@ -1,6 +1,6 @@
 """Diagnostic: star-radius rows of the full-size parity test that deviate from the reference's BVH; prints every value."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from tests import cases
 from zombie_b200 import abi, native, workloads

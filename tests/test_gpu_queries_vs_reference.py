@@ -46,7 +46,7 @@ def test_queries_match_compiled_reference(ctx, ref, dim, kind):
         #     reference's BVH, its Baseline and any other traversal may each report a different radius — they do: on the
         #     1.3 M-triangle mesh the reference's BVH and Baseline disagree with each other on such rows by the same 0.5-1 %
         #     (the device keeps the reference's arithmetic and early exit, so it is one more such traversal; one query per
-        #     launch reproduces the reference's or the Baseline's value on every such row, scripts/star_fullsize_debug.py).
+        #     launch reproduces the reference's or the Baseline's value on every such row, tests/diagnostics/star_fullsize_debug.py).
         rb = ref.RefScene(dim, use_baseline=True, **kw)
         base = rb.star_radius(x[bad], minr[bad], da[bad])
         rb.close()
