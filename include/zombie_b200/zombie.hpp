@@ -261,6 +261,13 @@ struct PDE {
         described = true;
         bindCallbacks();
     }
+    // constant Dirichlet data for the normal-aligned side of a double-sided absorbing boundary (with setConstant(); the other side
+    // keeps dirichletValue): pde.dirichlet(x, true) of walk_on_spheres.h:300-308
+    void setDirichletNormalAlignedValue(float value) {
+        description.dirichletAlignedValue = value;
+        description.hasDirichletAlignedValue = 1;
+        bindCallbacks();
+    }
     // Backs one callback with sampled data (takes precedence over setManufactured()/setConstant() for that callback; a PDE
     // posed only through grids needs neither). Robin data for the normal-aligned side of a double-sided boundary goes to
     // RobinNormalAligned, Dirichlet data for that side (walk_on_spheres.h:300-308) to DirichletNormalAligned.
