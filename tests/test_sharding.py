@@ -90,3 +90,69 @@ def test_two_rank_sharded_solve_equals_single_process(ref, tmp_path):
     assert np.array_equal(g["m2"], single.solutionM2)
     assert np.array_equal(g["n"], single.nSolutionEstimates)
     assert np.array_equal(g["wl"], single.totalWalkLength)
+
+
+# ---- Reverse Walk on Stars: samples sharded, totals all-reduced; BVC: cache shards all-gathered --------------------------------
+def _rws_problem():
+    from zombie_b200 import bvc, procedural as P
+    whole, absorbing, reflecting = cases.mesh3d(2)
+    sa, sr = bvc.UniformBoundarySampler(*absorbing, seed=1), bvc.UniformBoundarySampler(*reflecting, seed=2)
+    sd = bvc.UniformDomainSampler(lambda p: P.bumpy_sphere_inside(p), [-1.2]*3, [1.2]*3, P.bumpy_sphere_volume(), seed=3)
+    sa.initialize(0.01, False)
+    sr.initialize(0.0, False)
+    s = bvc.Samples.concatenate([sa.generate_samples(600, abi.ON_ABSORBING_BOUNDARY, 0.01), sr.generate_samples(300, abi.ON_REFLECTING_BOUNDARY, 0.0),
+                                 sd.generate_samples(300)])
+    return absorbing, reflecting, s, cases.query_points(40, 3, 0.6, seed=5)
+
+
+def _rws_solve(s, idx, x):
+    from oracle import ref
+    absorbing, reflecting = _rws_problem()[:2]
+    rs = ref.RefScene(3, **cases.scene_kwargs(3, abi.REFLECTING_NEUMANN, absorbing, reflecting))
+    da = rs.closest_point(abi.ABSORBING, s.pt[idx], want_normal=False)[1]
+    dr = rs.closest_point(abi.REFLECTING, s.pt[idx], want_normal=False)[1]
+    smp = abi.HostRwsSamples(s.pt[idx], s.normal[idx], s.type[idx], s.pdf[idx], da, dr, seed=0xF00D, streams=idx.astype(np.uint64))
+    ev = abi.HostRwsEvalPoints(x)
+    rs.rws_solve(cases.quadratic_pde(), abi.WalkSettings.default(), smp, ev, 0.01)
+    return smp, ev
+
+
+def _rws_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    absorbing, reflecting, s, x = _rws_problem()
+    idx = sharding.shard_indices(len(s), rank, world)
+    smp, ev = _rws_solve(s, idx, x)
+    sharding.allreduce_rws_totals(ev)
+    counts = sharding.allreduce_counts(smp.group_counts())
+    # the cache all-gather of Boundary Value Caching on the same shards: every rank ends up with all samples, in rank order
+    from zombie_b200 import bvc
+    local = bvc.Samples(s.pt[idx], s.normal[idx], 0, 1.0, False)
+    for k in sharding.BVC_SAMPLE_KEYS[2:]:
+        setattr(local, k, getattr(s, k)[idx])
+    local.solution = (idx + 0.5).astype(np.float32)            # stands for the estimates a rank computed for its shard
+    full = sharding.allgather_bvc_cache(local)
+    order = np.concatenate([sharding.shard_indices(len(s), r, world) for r in range(world)])
+    assert np.array_equal(full.pt, s.pt[order]) and np.array_equal(full.type, s.type[order]) and np.array_equal(full.pdf, s.pdf[order])
+    assert np.array_equal(full.solution, (order + 0.5).astype(np.float32))
+    if rank == 0:
+        np.savez(out, totals=ev.totals, counts=counts)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_reverse_walks_allreduce_to_the_single_process_totals(ref, tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path/"rws.npz")
+    mp.spawn(_rws_worker, args=(2, port, out), nprocs=2, join=True)
+    g = np.load(out)
+    absorbing, reflecting, smp_all, x = _rws_problem()
+    smp, single = _rws_solve(smp_all, np.arange(len(smp_all), dtype=np.int64), x)
+    assert np.array_equal(g["counts"], smp.group_counts())
+    # the same walks (a stream per sample), summed in another order
+    scale = np.abs(single.totals).max(axis=0) + 1e-6
+    assert (np.abs(g["totals"] - single.totals)/scale).max() < 1e-4

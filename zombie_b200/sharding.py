@@ -155,3 +155,68 @@ class DeviceStatistics:
         for k in STAT_FLOAT_KEYS + STAT_INT_KEYS:
             setattr(st, k, np.ascontiguousarray(self.view(k, buf).cpu().numpy()))
         return st
+
+
+# ---- Reverse Walk on Stars and Boundary Value Caching over several GPUs ------------------------------------------
+def allreduce_rws_totals(eval_pts, device="cpu"):
+    """Reverse Walk on Stars with the SAMPLE walks sharded over the ranks and the evaluation points replicated: every rank's
+    zb_rws_solve adds its samples' splats to its own copy of the six running sums per evaluation point
+    (rws::EvaluationPoint, reverse_walk_solver.h:20-52); the sums of the whole job are their sum over the ranks — one
+    all-reduce of 24 B per evaluation point (NCCL on the GPU box, gloo in the CPU test). eval_pts: abi.HostRwsEvalPoints,
+    updated in place. Divide by the GLOBAL sample counts afterwards (allreduce_counts)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(eval_pts.totals)).to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    eval_pts.totals[...] = t.cpu().numpy()
+    return eval_pts
+
+
+def allreduce_counts(counts, device="cpu"):
+    """the per-group sample counts (abi.HostRwsSamples.group_counts) of the whole job"""
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.asarray(counts, np.int64).copy()).to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy()
+
+
+BVC_SAMPLE_KEYS = ("pt", "normal", "type", "pdf", "aligned", "dist_a", "dist_r", "robin_coeff", "solution", "normal_derivative", "contribution")
+
+
+def allgather_bvc_cache(local, device="cpu"):
+    """Boundary Value Caching with the CACHE samples sharded over the ranks for the walks (compute_sample_estimates on each
+    rank's shard) and the evaluation points sharded for the splat: the splat needs every cache sample on every rank, so the
+    finished shards are all-gathered — a few MB (boundary_value_caching.h: the cache is 10^4..10^5 samples). local: a
+    bvc.Samples; returns the bvc.Samples of all ranks in rank order. The pdf of a sample is that of the whole sampler, so
+    nothing is rescaled."""
+    import torch
+    import torch.distributed as dist
+    from . import bvc
+    world = dist.get_world_size()
+    n = torch.tensor([len(local)], dtype=torch.int64, device=device)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(s.item()) for s in sizes]
+    pad = max(sizes) if sizes else 0
+    parts = [dict() for _ in range(world)]
+    for k in BVC_SAMPLE_KEYS:
+        a = np.ascontiguousarray(getattr(local, k))
+        width = int(np.prod(a.shape[1:])) if a.ndim > 1 else 1
+        buf = np.zeros((pad, width), a.dtype)
+        buf[:len(a)] = a.reshape(len(a), width)
+        t = torch.from_numpy(buf).to(device)
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        for r in range(world):
+            g = out[r].cpu().numpy()[:sizes[r]]
+            parts[r][k] = g.reshape((sizes[r],) + a.shape[1:])
+    gathered = []
+    for r in range(world):
+        if sizes[r] == 0:
+            continue
+        s = bvc.Samples(parts[r]["pt"], parts[r]["normal"], 0, 1.0, False)
+        for k in BVC_SAMPLE_KEYS[2:]:
+            setattr(s, k, parts[r][k])
+        gathered.append(s)
+    return bvc.Samples.concatenate(gathered)
