@@ -483,3 +483,21 @@ def test_two_sided_dirichlet_data_on_host_match_reference(host_solve, tmp_path, 
     ins, out = st.solutionMean[inside & ok], st.solutionMean[~inside & ok]
     assert (ins == 1.0).mean() > 0.8 and (ins < 1.5).all() and (out == 3.0).mean() > 0.8 and (out > 2.5).all()
     assert abs(out.mean() - r.solutionMean[~inside & ok].mean()) < 0.03 and abs(ins.mean() - r.solutionMean[inside & ok].mean()) < 0.03
+
+
+def test_value_channels_on_host_walk_on_spheres_2d(host_solve, tmp_path):
+    """the same for Walk on Spheres in 2D (sampled source, no reflecting boundary): channels with other quadratic solutions"""
+    (pos, seg), _, _ = cases.mesh2d(256)
+    x = cases.query_points(20, 2, 0.5, seed=8)
+    extra = [[0.25, 2.0, 0.0, -1.0] + [0.0]*12]
+    q = np.full(len(x), abi.SOLUTION_AND_GRADIENT, np.int32)
+    d = str(tmp_path)
+    run_host(host_solve, d, 2, abi.REFLECTING_NONE, (pos, seg), None, x, 24, abi.SOL_QUADRATIC, [1.0, -0.5, 0.0, 0.3], 0.0, 0.0, 0.0, abi.FLT_MAX, 9,
+             quantities=q, channels=extra)
+    multi = np.fromfile(os.path.join(d, "out_c0.bin"), np.float32).reshape(-1, 6)
+    st = run_host(host_solve, d, 2, abi.REFLECTING_NONE, (pos, seg), None, x, 24, abi.SOL_QUADRATIC, extra[0][:4], 0.0, 0.0, 0.0, abi.FLT_MAX, 9, quantities=q)
+    assert np.array_equal(multi[:, 2].astype(np.int32), st.nSolutionEstimates)
+    assert np.allclose(multi[:, 0], st.solutionMean, rtol=0, atol=2e-5*max(1.0, float(np.abs(st.solutionMean).max())))
+    exact = 0.25*x[:, 0]**2 + 2.0*x[:, 1]**2 - 1.0
+    se = np.sqrt(multi[:, 1]/np.maximum(1.0, multi[:, 2] - 1.0)/np.maximum(1.0, multi[:, 2]))
+    assert np.mean(np.abs(multi[:, 0] - exact) < 4.0*se + 5e-3) > 0.9
